@@ -1,0 +1,74 @@
+/* gymcity_b200.h -- C-ABI of libgymcity_b200.so (sm_100a CUDA), the drop-in boundary for the
+ * environment-tick path of smearle/gym-city.
+ *
+ * The reference has no C plugin ABI for this path: its operator boundary is SWIG over the whole
+ * C++ `Micropolis` class (reference .../MicropolisEngine/swig/micropolisengine.i:66-74) consumed by
+ * gym_city/envs/corecontrol.py, and plain torch calls for Game of Life
+ * (game_of_life/envs/multi_env.py).  This header is what a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Conventions: plain pointers and sizes only; int return 0 = ok, negative = error
+ * (text via *_last_error); no exceptions cross the boundary; one handle per GPU; a handle is not
+ * re-entrant; all device work is enqueued on the caller's stream (`void *stream` is a
+ * cudaStream_t / CUstream, NULL = legacy default stream).
+ */
+#ifndef GYMCITY_B200_H
+#define GYMCITY_B200_H
+
+#include <stdint.h>
+#include "mp_snapshot.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ DLPack hand-off
+ * Wraps a borrowed device buffer as a DLManagedTensor* (DLPack v0.8 struct layout) whose deleter
+ * frees only the descriptor.  dtype_code: 0 int, 1 uint, 2 float.  The caller wraps the pointer in
+ * a PyCapsule named "dltensor" and calls torch.from_dlpack (reference hand-off point:
+ * storage.py:84-94 RolloutStorage.insert; envs.py:363-375 VecPyTorch.step_wait). */
+void *gcb_dlpack_wrap(void *dev_ptr, int dtype_code, int bits, int ndim, const int64_t *shape,
+                      int device);
+
+/* ------------------------------------------------------------------ Game of Life (golb_*) */
+typedef void *golb_handle;
+
+enum golb_buffer {
+    GOLB_ROWS = 0,   /* uint32 [n_envs * W]   bit y of rows[env*W + x] = cell [x][y]            */
+    GOLB_OBS,        /* multi: float32 [n,2,W,W] (multi_env.py:235-240); classic: uint8 [n,1,W,W] */
+    GOLB_REWARD,     /* float32 [n]                                                              */
+    GOLB_POP,        /* int32 [n] population after the tick                                      */
+    GOLB_DONE        /* uint8 [n]                                                                */
+};
+
+/* Replaces GoLMultiEnv.configure (game_of_life/envs/multi_env.py:34-129) when classic = 0 and
+ * GameOfLifeEnv.configure (game_of_life/envs/env.py:30-97) batched over n_envs when classic = 1.
+ * 3 <= width <= 32.  Returns NULL on bad arguments or if no CUDA device `device` exists. */
+golb_handle golb_create(int n_envs, int width, int max_step, int classic, int device);
+void golb_destroy(golb_handle h);
+const char *golb_last_error(golb_handle h);
+
+/* GoLMultiEnv.set_params (multi_env.py:146-160): target population and the parameter range. */
+int golb_set_target(golb_handle h, float trg_pop, float range);
+
+/* World.repopulate_cells (world_pytorch.py:75-82 / world.py:87-92): each cell alive w.p.
+ * prob_life in [0,1]; also clears step_count and the classic world's stale references. */
+int golb_reset(golb_handle h, uint32_t seed, float prob_life, void *stream);
+
+/* Upload / download explicit boards: uint8 [n_envs][W][W] on the HOST (parity tests, fixtures). */
+int golb_set_state(golb_handle h, const uint8_t *cells_host, void *stream);
+int golb_get_state(golb_handle h, uint8_t *cells_host);
+
+/* GoLMultiEnv.step (multi_env.py:170-232) / GameOfLifeEnv.step (env.py:125-182):
+ * actions_dev = int64 [n_envs] DEVICE pointer, flat index a = x*W + y. */
+int golb_step(golb_handle h, const int64_t *actions_dev, void *stream);
+
+/* Same, end to end with HOST buffers: copies actions H2D, steps, copies rewards D2H, syncs. */
+int golb_step_host(golb_handle h, const int64_t *actions_host, float *reward_host, void *stream);
+
+/* Borrowed device pointers (owned by the handle, valid until golb_destroy). */
+void *golb_ptr(golb_handle h, int which);
+int golb_step_count(golb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMCITY_B200_H */
