@@ -1,0 +1,1717 @@
+// mp_sim.h -- the Micropolis simulation step: 16-phase cycle, map scan, zones, traffic, power
+// flood fill, overlay scans, census / valves / tax / evaluation.
+//
+// Functions marked [ALL] are entered by every thread of the env's CTA (they contain barriers and
+// strided parallel loops); functions marked [LEAD] run on the lead thread only -- that is the
+// RNG-ordered serial lane (every draw of the per-env simRandom stream happens there, in the
+// reference's call order).  Each function cites the reference code whose results it reproduces
+// (paths relative to .../MicropolisEngine/src/).
+#pragma once
+#include "mp_state.h"
+
+namespace mp {
+
+#define S (*e.s)
+
+MPN void city_evaluation(Env &e);                       // mp_eval part below
+MPN void move_objects(Env &e);                          // mp_sprites.h
+MPN void do_disasters(Env &e);                          // mp_sprites.h
+MPN void make_explosion_at(Env &e, int x, int y);       // mp_sprites.h
+MPN void make_explosion(Env &e, int x, int y);          // mp_sprites.h
+MPN void generate_train(Env &e, int x, int y);          // mp_sprites.h
+MPN void generate_ship(Env &e);                         // mp_sprites.h
+MPN void generate_plane(Env &e, int x, int y);          // mp_sprites.h
+MPN void generate_copter(Env &e, int x, int y);         // mp_sprites.h
+MPD int get_sprite(Env &e, int type);                   // mp_sprites.h
+MPD int boat_distance(Env &e, int x, int y);            // mp_sprites.h
+
+// ------------------------------------------------------------------ phase 0
+// [LEAD] simulate.cpp:546-670 setValves.  fp32 throughout like the reference, including the
+// `resRatio = min(indRatio, ...)` slip at :644.
+MPN void set_valves(Env &e)
+{
+    const int16_t taxTable[21] = { 200, 150, 120, 100, 80, 50, 30, 0, -10, -40, -100,
+        -150, -200, -250, -300, -350, -400, -450, -500, -550, -600 };
+    const float extMarketParamTable[3] = { 1.2f, 1.1f, 0.98f };
+    const float birthRate = 0.02f, laborBaseMax = 1.3f, internalMarketDenom = 3.7f;
+    const float projectedIndPopMin = 5.0f, resRatioDefault = 1.3f;
+    const float resRatioMax = 2, comRatioMax = 2, indRatioMax = 2, taxTableScale = 600;
+    int16_t *mh = e.miscHist;
+    mh[1] = f2s(S.externalMarket);
+    mh[2] = S.resPop; mh[3] = S.comPop; mh[4] = S.indPop;
+    mh[5] = S.resValve; mh[6] = S.comValve; mh[7] = S.indValve;
+    mh[10] = S.crimeRamp; mh[11] = S.pollutionRamp; mh[12] = S.landValueAverage;
+    mh[13] = S.crimeAverage; mh[14] = S.pollutionAverage; mh[15] = (int16_t)S.gameLevel;
+    mh[16] = (int16_t)S.cityClass; mh[17] = S.cityScore;
+
+    float normalizedResPop = (float)S.resPop / 8.0f;
+    S.totalPopLast = S.totalPop;
+    S.totalPop = f2s(normalizedResPop + S.comPop + S.indPop);
+    float employment;
+    if (S.resPop > 0) employment = (float)(e.comHist[1] + e.indHist[1]) / normalizedResPop;
+    else employment = 1;
+    float migration = normalizedResPop * (employment - 1);
+    float births = normalizedResPop * birthRate;
+    float projectedResPop = normalizedResPop + migration + births;
+    float temp = (float)(e.comHist[1] + e.indHist[1]);
+    float laborBase;
+    if (temp > 0.0f) laborBase = (float)e.resHist[1] / temp;
+    else laborBase = 1;
+    laborBase = tclamp(laborBase, 0.0f, laborBaseMax);
+    float internalMarket = (float)(normalizedResPop + S.comPop + S.indPop) / internalMarketDenom;
+    float projectedComPop = internalMarket * laborBase;
+    float projectedIndPop = S.indPop * laborBase * extMarketParamTable[S.gameLevel];
+    projectedIndPop = tmax(projectedIndPop, projectedIndPopMin);
+    float resRatio, comRatio, indRatio;
+    if (normalizedResPop > 0) resRatio = projectedResPop / normalizedResPop;
+    else resRatio = resRatioDefault;
+    if (S.comPop > 0) comRatio = projectedComPop / (float)S.comPop;
+    else comRatio = projectedComPop;
+    if (S.indPop > 0) indRatio = projectedIndPop / (float)S.indPop;
+    else indRatio = projectedIndPop;
+    resRatio = tmin(resRatio, resRatioMax);
+    comRatio = tmin(comRatio, comRatioMax);
+    resRatio = tmin(indRatio, indRatioMax);        // sic
+    int16_t z = tmin((int16_t)(S.cityTax + S.gameLevel), (int16_t)20);
+    resRatio = (resRatio - 1) * taxTableScale + taxTable[z];
+    comRatio = (comRatio - 1) * taxTableScale + taxTable[z];
+    indRatio = (indRatio - 1) * taxTableScale + taxTable[z];
+    S.resValve = (int16_t)tclamp(S.resValve + f2s(resRatio), -RES_VALVE_RANGE, RES_VALVE_RANGE);
+    S.comValve = (int16_t)tclamp(S.comValve + f2s(comRatio), -COM_VALVE_RANGE, COM_VALVE_RANGE);
+    S.indValve = (int16_t)tclamp(S.indValve + f2s(indRatio), -IND_VALVE_RANGE, IND_VALVE_RANGE);
+    if (S.resCap && S.resValve > 0) S.resValve = 0;
+    if (S.comCap && S.comValve > 0) S.comValve = 0;
+    if (S.indCap && S.indValve > 0) S.indValve = 0;
+}
+
+// [LEAD] simulate.cpp:674-703 clearCensus, scalar part (the two station maps are cleared by ALL)
+MPD void clear_census_scalars(Env &e)
+{
+    S.poweredZoneCount = 0; S.unpoweredZoneCount = 0; S.firePop = 0; S.roadTotal = 0;
+    S.railTotal = 0; S.resPop = 0; S.comPop = 0; S.indPop = 0; S.resZonePop = 0;
+    S.comZonePop = 0; S.indZonePop = 0; S.hospitalPop = 0; S.churchPop = 0;
+    S.policeStationPop = 0; S.fireStationPop = 0; S.stadiumPop = 0; S.coalPowerPop = 0;
+    S.nuclearPowerPop = 0; S.seaportPop = 0; S.airportPop = 0; S.powerStackPointer = 0;
+}
+
+// ------------------------------------------------------------------ power stack / zone power
+MPD void push_power_stack(Env &e, int x, int y)          // power.cpp:163-169
+{
+    if (S.powerStackPointer < POWER_STACK_SIZE - 2) {
+        S.powerStackPointer++;
+        e.pstack[S.powerStackPointer] = (uint16_t)tix(x, y);
+    }
+}
+
+// [LEAD] zone.cpp:419-437 setZonePower
+MPD bool set_zone_power(Env &e, int x, int y)
+{
+    int v = e.map[tix(x, y)], t = v & LOMASK;
+    if (t == T_NUCLEAR || t == T_POWERPLANT || pwr_get(e, x, y)) {
+        e.map[tix(x, y)] = (uint16_t)(v | PWRBIT);
+        return true;
+    }
+    e.map[tix(x, y)] = (uint16_t)(v & ~PWRBIT);
+    return false;
+}
+
+// ------------------------------------------------------------------ traffic (traffic.cpp)
+MPD bool road_test(int mv)                                // traffic.cpp:489-503
+{
+    int t = mv & LOMASK;
+    if (t < T_ROADBASE || t > T_LASTRAIL) return false;
+    if (t >= T_POWERBASE && t < T_LASTPOWER) return false;
+    return true;
+}
+
+// [LEAD] traffic.cpp:227-249 findPerimeterRoad
+MPD bool find_perimeter_road(Env &e, int &x, int &y)
+{
+    const int8_t px[12] = { -1, 0, 1, 2, 2, 2, 1, 0, -1, -2, -2, -2 };
+    const int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
+    for (int z = 0; z < 12; z++) {
+        int tx = x + px[z], ty = y + py[z];
+        if (inb(tx, ty) && road_test(e.map[tix(tx, ty)])) {
+            x = tx; y = ty;
+            return true;
+        }
+    }
+    return false;
+}
+
+MPD int tile_toward(const Env &e, int x, int y, int dir, int dflt)   // traffic.cpp:383-427
+{
+    switch (dir) {
+    case D_N: return y > 0 ? (e.map[tix(x, y - 1)] & LOMASK) : dflt;
+    case D_E: return x < WORLD_W - 1 ? (e.map[tix(x + 1, y)] & LOMASK) : dflt;
+    case D_S: return y < WORLD_H - 1 ? (e.map[tix(x, y + 1)] & LOMASK) : dflt;
+    case D_W: return x > 0 ? (e.map[tix(x - 1, y)] & LOMASK) : dflt;
+    default: return dflt;
+    }
+}
+
+// [LEAD] traffic.cpp:333-376 tryGo
+MPD int try_go(Env &e, int x, int y, int dirLast)
+{
+    int dirs[4], dir = D_N, count = 0;
+    for (int i = 0; i < 4; i++) {
+        if (dir != dirLast && road_test(tile_toward(e, x, y, dir, T_DIRT))) {
+            dirs[i] = dir;
+            count++;
+        } else {
+            dirs[i] = D_INVALID;
+        }
+        dir = rot45(dir, 2);
+    }
+    if (count == 0) return D_INVALID;
+    if (count == 1) {
+        for (int i = 0; i < 4; i++) if (dirs[i] != D_INVALID) return dirs[i];
+    }
+    int i = rnd16(e) & 3;
+    while (dirs[i] == D_INVALID) i = (i + 1) & 3;
+    return dirs[i];
+}
+
+// [LEAD] traffic.cpp:436-480 driveDone
+MPD bool drive_done(const Env &e, int x, int y, int dest)
+{
+    const int lo[3] = { T_COMBASE, T_LHTHR, T_LHTHR };
+    const int hi[3] = { T_NUCLEAR, T_PORT, T_COMBASE };
+    int l = lo[dest], h = hi[dest], z;
+    if (y > 0) { z = e.map[tix(x, y - 1)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (x < WORLD_W - 1) { z = e.map[tix(x + 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (y < WORLD_H - 1) { z = e.map[tix(x, y + 1)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (x > 0) { z = e.map[tix(x - 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
+    return false;
+}
+
+// [LEAD] traffic.cpp:287-323 tryDrive
+MPD bool try_drive(Env &e, int x, int y, int dest)
+{
+    int dirLast = D_INVALID;
+    for (int16_t dist = 0; dist < MAX_TRAFFIC_DISTANCE; dist++) {
+        int dir = try_go(e, x, y, dirLast);
+        if (dir != D_INVALID) {
+            pos_move(x, y, dir);
+            dirLast = rot45(dir, 4);
+            if (dist & 1) {
+                S.curMapStackPointer++;
+                S.curMapStack[S.curMapStackPointer] = (int16_t)tix(x, y);
+            }
+            if (drive_done(e, x, y, dest)) return true;
+        } else {
+            if (S.curMapStackPointer > 0) {
+                S.curMapStackPointer--;
+                dist += 3;
+            } else {
+                return false;
+            }
+        }
+    }
+    return false;
+}
+
+// [LEAD] traffic.cpp:164-201 addToTrafficDensityMap
+MPD void add_to_traffic_density(Env &e)
+{
+    while (S.curMapStackPointer > 0) {
+        int p = S.curMapStack[S.curMapStackPointer];
+        S.curMapStackPointer--;
+        int x = p / WORLD_H, y = p - x * WORLD_H;
+        int t = e.map[p] & LOMASK;
+        if (t >= T_ROADBASE && t < T_POWERBASE) {
+            int traffic = b2get(e.traffic, x, y) + 50;
+            traffic = tmin(traffic, 240);
+            b2set(e.traffic, x, y, traffic);
+            if (traffic >= 240 && rnd(e, 5) == 0) {
+                S.trafMaxX = (int16_t)x; S.trafMaxY = (int16_t)y;
+                int sp = get_sprite(e, SPR_HELICOPTER);
+                if (sp >= 0 && e.spr[sp].control == -1) {
+                    e.spr[sp].destX = (int16_t)(S.trafMaxX * 16);
+                    e.spr[sp].destY = (int16_t)(S.trafMaxY * 16);
+                }
+            }
+        }
+    }
+}
+
+// [LEAD] traffic.cpp:126-156 makeTraffic: 1 = trip found, 0 = no trip, -1 = no road at all
+MPN int make_traffic(Env &e, int x, int y, int dest)
+{
+    S.curMapStackPointer = 0;
+    if (find_perimeter_road(e, x, y)) {
+        if (try_drive(e, x, y, dest)) {
+            add_to_traffic_density(e);
+            return 1;
+        }
+        return 0;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------ zones (zone.cpp)
+MPD void inc_rate_of_growth(Env &e, int x, int y, int amount)      // zone.cpp:300-306
+{
+    int v = s8get(e.rog, x, y);
+    v = tclamp(v + amount * 4, -200, 200);
+    s8set(e.rog, x, y, v);
+}
+
+MPD int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:271-293
+{
+    int16_t lv = (int16_t)b2get(e.landval, x, y);
+    lv = (int16_t)(lv - b2get(e.pollution, x, y));
+    if (lv < 30) return 0;
+    if (lv < 80) return 1;
+    if (lv < 150) return 2;
+    return 3;
+}
+
+// [LEAD] zone.cpp:315-352 zonePlop
+MPN bool zone_plop(Env &e, int x, int y, int base)
+{
+    for (int z = 0; z < 9; z++) {
+        int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
+        if (inb(xx, yy)) {
+            int t = e.map[tix(xx, yy)] & LOMASK;
+            if (t >= T_FLOOD && t < T_ROADBASE) return false;
+        }
+    }
+    for (int z = 0; z < 9; z++) {
+        int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
+        if (inb(xx, yy)) e.map[tix(xx, yy)] = (uint16_t)(base + BNCNBIT);
+        base++;
+    }
+    set_zone_power(e, x, y);
+    e.map[tix(x, y)] |= ZONEBIT + BULLBIT;
+    return true;
+}
+
+MPD int16_t do_free_pop(const Env &e, int x, int y)                // zone.cpp:360-377
+{
+    int16_t count = 0;
+    for (int xx = x - 1; xx <= x + 1; xx++)
+        for (int yy = y - 1; yy <= y + 1; yy++)
+            if (inb(xx, yy)) {
+                int t = e.map[tix(xx, yy)] & LOMASK;
+                if (t >= T_LHTHR && t <= T_HHTHR) count++;
+            }
+    return count;
+}
+
+MPD int16_t res_zone_pop(int t) { return (int16_t)((((t - T_RZB) / 9) % 4) * 8 + 16); }   // zone.cpp:727
+MPD int16_t com_zone_pop(int t) { return t == T_COMCLR ? (int16_t)0 : (int16_t)(((t - T_CZB) / 9) % 5 + 1); }
+MPD int16_t ind_zone_pop(int t) { return t == T_INDCLR ? (int16_t)0 : (int16_t)((((t - T_IZB) / 9) % 4) + 1); }
+
+MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:493-517
+{
+    const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
+    int16_t z = (int16_t)(e.map[tix(x, y)] & LOMASK);
+    if (z && (z < T_RESBASE || z > T_RESBASE + 8)) return -1;
+    int16_t score = 1;
+    for (z = 0; z < 4; z++) {
+        int xx = x + dx[z], yy = y + dy[z];
+        if (inb(xx, yy) && e.map[tix(xx, yy)] != T_DIRT && (e.map[tix(xx, yy)] & LOMASK) <= T_LASTROAD)
+            score++;
+    }
+    return score;
+}
+
+// [LEAD] zone.cpp:444-484 buildHouse
+MPD void build_house(Env &e, int x, int y, int value)
+{
+    const int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
+    int16_t best = 0, hscore = 0;
+    for (int16_t z = 1; z < 9; z++) {
+        int xx = x + zx[z], yy = y + zy[z];
+        if (inb(xx, yy)) {
+            int16_t score = eval_lot(e, xx, yy);
+            if (score != 0) {
+                if (score > hscore) { hscore = score; best = z; }
+                if (score == hscore && !(rnd16(e) & 7)) best = z;
+            }
+        }
+    }
+    if (best) {
+        int xx = x + zx[best], yy = y + zy[best];
+        if (inb(xx, yy)) e.map[tix(xx, yy)] = (uint16_t)(T_HOUSE + BLBNCNBIT + rnd(e, 2) + value * 3);
+    }
+}
+
+MPD void res_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:741-747
+{
+    int16_t base = (int16_t)(((value * 4 + den) * 9) + T_RZB - 4);
+    zone_plop(e, x, y, base);
+}
+MPD void com_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:900-906
+{
+    int16_t base = (int16_t)(((value * 5) + den) * 9 + T_CZB - 4);
+    zone_plop(e, x, y, base);
+}
+MPD void ind_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:1005-1009
+{
+    int16_t base = (int16_t)(((value * 4) + den) * 9 + T_IND1);
+    zone_plop(e, x, y, base);
+}
+
+// [LEAD] zone.cpp:596-630 doResIn
+MPD void do_res_in(Env &e, int x, int y, int pop, int value)
+{
+    if (b2get(e.pollution, x, y) > 128) return;
+    int t = e.map[tix(x, y)] & LOMASK;
+    if (t == T_FREEZ) {
+        if (pop < 8) {
+            build_house(e, x, y, value);
+            inc_rate_of_growth(e, x, y, 1);
+            return;
+        }
+        if (b2get(e.pop, x, y) > 64) {
+            res_plop(e, x, y, 0, value);
+            inc_rate_of_growth(e, x, y, 8);
+        }
+        return;
+    }
+    if (pop < 40) {
+        res_plop(e, x, y, (pop / 8) - 1, value);
+        inc_rate_of_growth(e, x, y, 8);
+    }
+}
+
+// [LEAD] zone.cpp:639-704 doResOut
+MPD void do_res_out(Env &e, int x, int y, int pop, int value)
+{
+    const int8_t brdr[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
+    if (!pop) return;
+    if (pop > 16) {
+        res_plop(e, x, y, (pop - 24) / 8, value);
+        inc_rate_of_growth(e, x, y, -8);
+        return;
+    }
+    if (pop == 16) {
+        inc_rate_of_growth(e, x, y, -8);
+        e.map[tix(x, y)] = (uint16_t)(T_FREEZ | BLBNCNBIT | ZONEBIT);
+        for (int xx = x - 1; xx <= x + 1; xx++)
+            for (int yy = y - 1; yy <= y + 1; yy++)
+                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) != T_FREEZ)
+                    e.map[tix(xx, yy)] = (uint16_t)(T_LHTHR + value + rnd(e, 2) + BLBNCNBIT);
+    }
+    if (pop < 16) {
+        inc_rate_of_growth(e, x, y, -1);
+        int z = 0;
+        for (int xx = x - 1; xx <= x + 1; xx++)
+            for (int yy = y - 1; yy <= y + 1; yy++) {
+                if (inb(xx, yy)) {
+                    int loc = e.map[tix(xx, yy)] & LOMASK;
+                    if (loc >= T_LHTHR && loc <= T_HHTHR) {
+                        e.map[tix(xx, yy)] = (uint16_t)(brdr[z] + BLBNCNBIT + T_FREEZ - 4);
+                        return;
+                    }
+                }
+                z++;
+            }
+    }
+}
+
+// [LEAD] zone.cpp:240-264 makeHospital
+MPD void make_hospital(Env &e, int x, int y)
+{
+    if (S.needHospital > 0) {
+        zone_plop(e, x, y, T_HOSPITAL - 4);
+        S.needHospital = 0;
+        return;
+    }
+    if (S.needChurch > 0) {
+        int churchType = rnd(e, 7);
+        int tile = churchType == 0 ? (int)T_CHURCH0 : T_CHURCH1 + ((churchType - 1) * 9);
+        zone_plop(e, x, y, tile - 4);
+        S.needChurch = 0;
+    }
+}
+
+MPD int16_t eval_res(const Env &e, int x, int y, int traf)         // zone.cpp:757-777
+{
+    if (traf < 0) return -3000;
+    int16_t v = (int16_t)b2get(e.landval, x, y);
+    v = (int16_t)(v - b2get(e.pollution, x, y));
+    if (v < 0) v = 0;
+    else v = (int16_t)tmin(v * 32, 6000);
+    return (int16_t)(v - 3000);
+}
+
+// [LEAD] zone.cpp:526-587 doResidential
+MPN void do_residential(Env &e, int x, int y, bool zonePower)
+{
+    S.resZonePop++;
+    int t = e.map[tix(x, y)] & LOMASK;
+    int16_t tpop = (t == T_FREEZ) ? do_free_pop(e, x, y) : res_zone_pop(t);
+    S.resPop = (int16_t)(S.resPop + tpop);
+    int16_t trf = (tpop > rnd(e, 35)) ? (int16_t)make_traffic(e, x, y, 0) : (int16_t)1;
+    if (trf == -1) {
+        do_res_out(e, x, y, tpop, land_pollution_value(e, x, y));
+        return;
+    }
+    if (t == T_FREEZ || !(rnd16(e) & 7)) {
+        int16_t locvalve = eval_res(e, x, y, trf);
+        int16_t zscore = (int16_t)(S.resValve + locvalve);
+        if (!zonePower) zscore = -500;
+        if (zscore > -350 && ((int16_t)(zscore - 26380) > (int16_t)rnd16s(e))) {
+            if (!tpop && !(rnd16(e) & 3)) {
+                make_hospital(e, x, y);
+                return;
+            }
+            do_res_in(e, x, y, tpop, land_pollution_value(e, x, y));
+            return;
+        }
+        if (zscore < 350 && ((int16_t)(zscore + 26380) < (int16_t)rnd16s(e)))
+            do_res_out(e, x, y, tpop, land_pollution_value(e, x, y));
+    }
+}
+
+// [LEAD] zone.cpp:786-888 doCommercial / doComIn / doComOut
+MPN void do_commercial(Env &e, int x, int y, bool zonePower)
+{
+    int t = e.map[tix(x, y)] & LOMASK;
+    S.comZonePop++;
+    int16_t tpop = com_zone_pop(t);
+    S.comPop = (int16_t)(S.comPop + tpop);
+    int16_t trf = (tpop > rnd(e, 5)) ? (int16_t)make_traffic(e, x, y, 1) : (int16_t)1;   // ZT_INDUSTRIAL
+    if (trf == -1) {
+        int value = land_pollution_value(e, x, y);
+        if (tpop > 1) { com_plop(e, x, y, tpop - 2, value); inc_rate_of_growth(e, x, y, -8); }
+        else if (tpop == 1) { zone_plop(e, x, y, T_COMBASE); inc_rate_of_growth(e, x, y, -8); }
+        return;
+    }
+    if (!(rnd16(e) & 7)) {
+        int16_t locvalve = (trf < 0) ? (int16_t)-3000 : (int16_t)s8get(e.comRate, x, y);
+        int16_t zscore = (int16_t)(S.comValve + locvalve);
+        if (!zonePower) zscore = -500;
+        if (trf && zscore > -350 && ((int16_t)(zscore - 26380) > (int16_t)rnd16s(e))) {
+            int value = land_pollution_value(e, x, y);
+            int16_t z = (int16_t)(b2get(e.landval, x, y) >> 5);
+            if (tpop > z) return;
+            if (tpop < 5) { com_plop(e, x, y, tpop, value); inc_rate_of_growth(e, x, y, 8); }
+            return;
+        }
+        if (zscore < 350 && ((int16_t)(zscore + 26380) < (int16_t)rnd16s(e))) {
+            int value = land_pollution_value(e, x, y);
+            if (tpop > 1) { com_plop(e, x, y, tpop - 2, value); inc_rate_of_growth(e, x, y, -8); }
+            else if (tpop == 1) { zone_plop(e, x, y, T_COMBASE); inc_rate_of_growth(e, x, y, -8); }
+        }
+    }
+}
+
+// [LEAD] zone.cpp:187-232 setSmoke
+MPD void set_smoke(Env &e, int x, int y, bool zonePower)
+{
+    const uint8_t aniThis[8] = { 1, 0, 1, 1, 0, 0, 1, 1 };
+    const int8_t dx1[8] = { -1, 0, 1, 0, 0, 0, 0, 1 }, dy1[8] = { -1, 0, -1, -1, 0, 0, -1, -1 };
+    const int16_t aniTabB[8] = { 0, 0, 36, 44, 0, 0, 52, 60 };
+    const int16_t aniTabC[8] = { T_IND1, 0, T_IND2, T_IND4, 0, 0, T_IND6, T_IND8 };
+    const int16_t aniTabD[8] = { T_IND1, 0, T_IND3, T_IND5, 0, 0, T_IND7, T_IND9 };
+    int t = e.map[tix(x, y)] & LOMASK;
+    if (t < T_IZB) return;
+    int z = ((t - T_IZB) >> 3) & 7;
+    if (!aniThis[z]) return;
+    int xx = x + dx1[z], yy = y + dy1[z];
+    if (!inb(xx, yy)) return;
+    if (zonePower) {
+        if ((e.map[tix(xx, yy)] & LOMASK) == aniTabC[z])
+            e.map[tix(xx, yy)] = (uint16_t)((ANIMBIT | CONDBIT | BURNBIT) | (T_SMOKEBASE + aniTabB[z]));
+    } else {
+        if ((e.map[tix(xx, yy)] & LOMASK) > aniTabC[z])
+            e.map[tix(xx, yy)] = (uint16_t)((CONDBIT | BURNBIT) | aniTabD[z]);
+    }
+}
+
+MPD void do_ind_out(Env &e, int x, int y, int pop, int value)      // zone.cpp:969-981
+{
+    if (pop > 1) { ind_plop(e, x, y, pop - 2, value); inc_rate_of_growth(e, x, y, -8); return; }
+    if (pop == 1) { zone_plop(e, x, y, T_INDBASE); inc_rate_of_growth(e, x, y, -8); }
+}
+
+// [LEAD] zone.cpp:916-957 doIndustrial
+MPN void do_industrial(Env &e, int x, int y, bool zonePower)
+{
+    int t = e.map[tix(x, y)] & LOMASK;
+    S.indZonePop++;
+    set_smoke(e, x, y, zonePower);
+    int16_t tpop = ind_zone_pop(t);
+    S.indPop = (int16_t)(S.indPop + tpop);
+    int16_t trf = (tpop > rnd(e, 5)) ? (int16_t)make_traffic(e, x, y, 2) : (int16_t)1;   // ZT_RESIDENTIAL
+    if (trf == -1) {
+        int v = rnd16(e) & 1;
+        do_ind_out(e, x, y, tpop, v);
+        return;
+    }
+    if (!(rnd16(e) & 7)) {
+        int16_t zscore = (int16_t)(S.indValve + (trf < 0 ? -1000 : 0));
+        if (!zonePower) zscore = -500;
+        if (zscore > -350 && ((int16_t)(zscore - 26380) > (int16_t)rnd16s(e))) {
+            int v = rnd16(e) & 1;
+            if (tpop < 4) { ind_plop(e, x, y, tpop, v); inc_rate_of_growth(e, x, y, 8); }
+            return;
+        }
+        if (zscore < 350 && ((int16_t)(zscore + 26380) < (int16_t)rnd16s(e))) {
+            int v = rnd16(e) & 1;
+            do_ind_out(e, x, y, tpop, v);
+        }
+    }
+}
+
+// [LEAD] simulate.cpp:1390-1421 repairZone
+MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
+{
+    int tile = zCent - 2 - zSize;
+    for (int yy = -1; yy < zSize - 1; yy++)
+        for (int xx = -1; xx < zSize - 1; xx++) {
+            int ax = x + xx, ay = y + yy;
+            tile++;
+            if (inb(ax, ay)) {
+                int mv = e.map[tix(ax, ay)];
+                if (mv & ZONEBIT) continue;
+                if (mv & ANIMBIT) continue;
+                int mt = mv & LOMASK;
+                if (mt < T_RUBBLE || mt >= T_ROADBASE) e.map[tix(ax, ay)] = (uint16_t)(tile | CONDBIT | BURNBIT);
+            }
+        }
+}
+
+// [LEAD] zone.cpp:127-180 doHospitalChurch
+MPD void do_hospital_church(Env &e, int x, int y)
+{
+    int t = e.map[tix(x, y)] & LOMASK;
+    if (t == T_HOSPITAL) {
+        S.hospitalPop++;
+        if (!(S.cityTime & 15)) repair_zone(e, x, y, T_HOSPITAL, 3);
+        if (S.needHospital == -1 && !rnd(e, 20)) zone_plop(e, x, y, T_RESBASE);
+    } else if (t == T_CHURCH0 || t == T_CHURCH1 || t == T_CHURCH2 || t == T_CHURCH3 || t == T_CHURCH4
+               || t == T_CHURCH5 || t == T_CHURCH6 || t == T_CHURCH7) {
+        S.churchPop++;
+        if (!(S.cityTime & 15)) repair_zone(e, x, y, t, 3);
+        if (S.needChurch == -1 && !rnd(e, 20)) zone_plop(e, x, y, T_RESBASE);
+        // the simulateChurch callback is a no-op for state (micropolisgenericengine.py:1198-1310)
+    }
+}
+
+// [LEAD] simulate.cpp:1652-1705 doMeltdown
+MPN void do_meltdown(Env &e, int x, int y)
+{
+    make_explosion(e, x - 1, y - 1);
+    make_explosion(e, x - 1, y + 2);
+    make_explosion(e, x + 2, y - 1);
+    make_explosion(e, x + 2, y + 2);
+    for (int xx = x - 1; xx < x + 3; xx++)
+        for (int yy = y - 1; yy < y + 3; yy++) tset(e, xx, yy, random_fire(e));
+    for (int z = 0; z < 200; z++) {
+        int xx = x - 20 + rnd(e, 40);
+        int yy = y - 15 + rnd(e, 30);
+        if (!inb(xx, yy)) continue;
+        int t = e.map[tix(xx, yy)];
+        if (t & ZONEBIT) continue;
+        if ((t & BURNBIT) || t == T_DIRT) e.map[tix(xx, yy)] = T_RADTILE;
+    }
+}
+
+// [LEAD] simulate.cpp:1430-1585 doSpecialZone (+ drawStadium :1588, doAirport :1606, coalSmoke :1624)
+MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
+{
+    const int meltdownTable[3] = { 30000, 20000, 10000 };
+    int t = e.map[tix(x, y)] & LOMASK;
+    switch (t) {
+    case T_POWERPLANT: {
+        S.coalPowerPop++;
+        if ((S.cityTime & 7) == 0) repair_zone(e, x, y, T_POWERPLANT, 4);
+        push_power_stack(e, x, y);
+        const int16_t sm[4] = { T_COALSMOKE1, T_COALSMOKE2, T_COALSMOKE3, T_COALSMOKE4 };
+        const int8_t dx[4] = { 1, 2, 1, 2 }, dy[4] = { -1, -1, 0, 0 };
+        for (int i = 0; i < 4; i++)
+            tset(e, x + dx[i], y + dy[i], sm[i] | ANIMBIT | CONDBIT | PWRBIT | BURNBIT);
+        return;
+    }
+    case T_NUCLEAR:
+        if (S.enableDisasters && !rnd(e, (int16_t)meltdownTable[S.gameLevel])) {
+            do_meltdown(e, x, y);
+            return;
+        }
+        S.nuclearPowerPop++;
+        if ((S.cityTime & 7) == 0) repair_zone(e, x, y, T_NUCLEAR, 4);
+        push_power_stack(e, x, y);
+        return;
+    case T_FIRESTATION:
+    case T_POLICESTATION: {
+        bool fire = (t == T_FIRESTATION);
+        if (fire) S.fireStationPop++; else S.policeStationPop++;
+        if (!(S.cityTime & 7)) repair_zone(e, x, y, t, 3);
+        int z = (int)(fire ? S.fireEffect : S.policeEffect);
+        if (!powerOn) z = z / 2;
+        int px = x, py = y;
+        if (!find_perimeter_road(e, px, py)) z = z / 2;
+        int16_t *m = fire ? e.fireSt : e.policeSt;
+        s8set(m, px, py, s8get(m, px, py) + z);
+        return;
+    }
+    case T_STADIUM:
+        S.stadiumPop++;
+        if (!(S.cityTime & 15)) repair_zone(e, x, y, T_STADIUM, 4);
+        if (powerOn && ((S.cityTime + x + y) & 31) == 0) {
+            int z = T_FULLSTADIUM - 5;
+            for (int yy = y - 1; yy < y + 3; yy++)
+                for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
+            e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
+            tset(e, x + 1, y, T_FOOTBALLGAME1 + ANIMBIT);
+            tset(e, x + 1, y + 1, T_FOOTBALLGAME2 + ANIMBIT);
+        }
+        return;
+    case T_FULLSTADIUM:
+        S.stadiumPop++;
+        if (((S.cityTime + x + y) & 7) == 0) {
+            int z = T_STADIUM - 5;
+            for (int yy = y - 1; yy < y + 3; yy++)
+                for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
+            e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
+        }
+        return;
+    case T_AIRPORT:
+        S.airportPop++;
+        if ((S.cityTime & 7) == 0) repair_zone(e, x, y, T_AIRPORT, 6);
+        if (powerOn) {
+            if ((tget(e, x + 1, y - 1) & LOMASK) == T_RADAR)
+                tset(e, x + 1, y - 1, T_RADAR0 + ANIMBIT + CONDBIT + BURNBIT);
+        } else {
+            tset(e, x + 1, y - 1, T_RADAR + CONDBIT + BURNBIT);
+        }
+        if (powerOn) {
+            if (rnd(e, 5) == 0) { generate_plane(e, x, y); return; }
+            if (rnd(e, 12) == 0) generate_copter(e, x, y);
+        }
+        return;
+    case T_PORT:
+        S.seaportPop++;
+        if ((S.cityTime & 15) == 0) repair_zone(e, x, y, T_PORT, 4);
+        if (powerOn && get_sprite(e, SPR_SHIP) < 0) generate_ship(e);
+        return;
+    default:
+        return;
+    }
+}
+
+// [LEAD] zone.cpp:79-120 doZone
+MPD void do_zone(Env &e, int x, int y)
+{
+    bool pw = set_zone_power(e, x, y);
+    if (pw) S.poweredZoneCount++; else S.unpoweredZoneCount++;
+    int t = e.map[tix(x, y)] & LOMASK;
+    if (t > T_PORTBASE && t < T_CHURCH1BASE) { do_special_zone(e, x, y, pw); return; }
+    if (t < T_HOSPITAL) { do_residential(e, x, y, pw); return; }
+    if (t < T_COMBASE || (t >= T_CHURCH1BASE && t <= T_CHURCH7LAST)) { do_hospital_church(e, x, y); return; }
+    if (t < T_INDBASE) { do_commercial(e, x, y, pw); return; }
+    if (t < T_CHURCH1BASE) { do_industrial(e, x, y, pw); return; }
+}
+
+// ------------------------------------------------------------------ fire / flood / radiation
+// [LEAD] simulate.cpp:1336-1381 fireZone (also disasters.cpp doFlood)
+MPD void fire_zone(Env &e, int x, int y, int ch)
+{
+    int v = tclamp(s8get(e.rog, x, y) - 20, -200, 200);
+    s8set(e.rog, x, y, v);
+    ch &= LOMASK;
+    int xymax = ch < T_PORTBASE ? 2 : (ch == T_AIRPORT ? 5 : 4);
+    for (int dx = -1; dx < xymax; dx++)
+        for (int dy = -1; dy < xymax; dy++) {
+            int xx = x + dx, yy = y + dy;
+            if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map[tix(xx, yy)] |= BULLBIT;
+        }
+}
+
+// [LEAD] simulate.cpp:1280-1327 doFire
+MPN void do_fire(Env &e, int x, int y)
+{
+    const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
+    for (int z = 0; z < 4; z++) {
+        if ((rnd16(e) & 7) == 0) {
+            int xx = x + dx[z], yy = y + dy[z];
+            if (inb(xx, yy)) {
+                int c = e.map[tix(xx, yy)];
+                if (!(c & BURNBIT)) continue;
+                if (c & ZONEBIT) {
+                    fire_zone(e, xx, yy, c);
+                    if ((c & LOMASK) > T_IZB) make_explosion_at(e, xx * 16 + 8, yy * 16 + 8);
+                }
+                e.map[tix(xx, yy)] = (uint16_t)random_fire(e);
+            }
+        }
+    }
+    int16_t rate = 10;
+    int z = s8get(e.fireEff, x, y);
+    if (z > 0) {
+        rate = 3;
+        if (z > 20) rate = 2;
+        if (z > 100) rate = 1;
+    }
+    if (rnd(e, rate) == 0) e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+}
+
+// [LEAD] disasters.cpp:375-405 doFlood
+MPN void do_flood(Env &e, int x, int y)
+{
+    const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
+    if (S.floodCount > 0) {
+        for (int z = 0; z < 4; z++) {
+            if ((rnd16(e) & 7) == 0) {
+                int xx = x + dx[z], yy = y + dy[z];
+                if (inb(xx, yy)) {
+                    int c = e.map[tix(xx, yy)], t = c & LOMASK;
+                    if ((c & BURNBIT) == BURNBIT || c == T_DIRT || (t >= T_WOODS5 && t < T_FLOOD)) {
+                        if ((c & ZONEBIT) == ZONEBIT) fire_zone(e, xx, yy, c);
+                        e.map[tix(xx, yy)] = (uint16_t)(T_FLOOD + rnd(e, 2));
+                    }
+                }
+            }
+        }
+    } else if ((rnd16(e) & 15) == 0) {
+        e.map[tix(x, y)] = T_DIRT;
+    }
+}
+
+// ------------------------------------------------------------------ roads / rails
+// [LEAD] simulate.cpp:1114-1245 doBridge
+MPN bool do_bridge(Env &e, int x, int y, int tile)
+{
+    const int8_t HDx[7] = { -2, 2, -2, -1, 0, 1, 2 }, HDy[7] = { -1, -1, 0, 0, 0, 0, 0 };
+    const int16_t HBRTAB[7] = { T_HBRDG1 | BULLBIT, T_HBRDG3 | BULLBIT, T_HBRDG0 | BULLBIT, T_RIVER,
+        T_BRWH | BULLBIT, T_RIVER, T_HBRDG2 | BULLBIT };
+    const int16_t HBRTAB2[7] = { T_RIVER, T_RIVER, T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT,
+        T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT };
+    const int8_t VDx[7] = { 0, 1, 0, 0, 0, 0, 1 }, VDy[7] = { -2, -2, -1, 0, 1, 2, 2 };
+    const int16_t VBRTAB[7] = { T_VBRDG0 | BULLBIT, T_VBRDG1 | BULLBIT, T_RIVER, T_BRWV | BULLBIT,
+        T_RIVER, T_VBRDG2 | BULLBIT, T_VBRDG3 | BULLBIT };
+    const int16_t VBRTAB2[7] = { T_VBRIDGE | BULLBIT, T_RIVER, T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT,
+        T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT, T_RIVER };
+    if (tile == T_BRWV) {
+        if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
+            for (int z = 0; z < 7; z++) {
+                int xx = x + VDx[z], yy = y + VDy[z];
+                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (VBRTAB[z] & LOMASK))
+                    e.map[tix(xx, yy)] = (uint16_t)VBRTAB2[z];
+            }
+        return true;
+    }
+    if (tile == T_BRWH) {
+        if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
+            for (int z = 0; z < 7; z++) {
+                int xx = x + HDx[z], yy = y + HDy[z];
+                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (HBRTAB[z] & LOMASK))
+                    e.map[tix(xx, yy)] = (uint16_t)HBRTAB2[z];
+            }
+        return true;
+    }
+    if (boat_distance(e, x, y) < 300 || !(rnd16(e) & 7)) {
+        if (tile & 1) {
+            if (x < WORLD_W - 1 && e.map[tix(x + 1, y)] == T_CHANNEL) {
+                for (int z = 0; z < 7; z++) {
+                    int xx = x + VDx[z], yy = y + VDy[z];
+                    if (inb(xx, yy)) {
+                        int m = e.map[tix(xx, yy)];
+                        if (m == T_CHANNEL || ((m & 15) == (VBRTAB2[z] & 15))) e.map[tix(xx, yy)] = (uint16_t)VBRTAB[z];
+                    }
+                }
+                return true;
+            }
+            return false;
+        } else {
+            if (y > 0 && e.map[tix(x, y - 1)] == T_CHANNEL) {
+                for (int z = 0; z < 7; z++) {
+                    int xx = x + HDx[z], yy = y + HDy[z];
+                    if (inb(xx, yy)) {
+                        int m = e.map[tix(xx, yy)];
+                        if (((m & 15) == (HBRTAB2[z] & 15)) || m == T_CHANNEL) e.map[tix(xx, yy)] = (uint16_t)HBRTAB[z];
+                    }
+                }
+                return true;
+            }
+            return false;
+        }
+    }
+    return false;
+}
+
+// [LEAD] simulate.cpp:1048-1111 doRoad
+MPD void do_road(Env &e, int x, int y)
+{
+    const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
+    S.roadTotal++;
+    int mv = e.map[tix(x, y)], tile = mv & LOMASK;
+    if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {
+        if ((rnd16(e) & 511) == 0) {
+            if (!(mv & CONDBIT)) {
+                if (S.roadEffect < (rnd16(e) & 31)) {
+                    if ((tile & 15) < 2 || (tile & 15) == 15) e.map[tix(x, y)] = T_RIVER;
+                    else e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+                    return;
+                }
+            }
+        }
+    }
+    if ((mv & BURNBIT) == 0) {
+        S.roadTotal = (int16_t)(S.roadTotal + 4);
+        if (do_bridge(e, x, y, tile)) return;
+    }
+    int16_t tden;
+    if (tile < T_LTRFBASE) tden = 0;
+    else if (tile < T_HTRFBASE) tden = 1;
+    else { S.roadTotal++; tden = 2; }
+    int16_t td = (int16_t)(b2get(e.traffic, x, y) >> 6);
+    if (td > 1) td--;
+    if (tden != td) {
+        int16_t z = (int16_t)(((tile - T_ROADBASE) & 15) + densityTable[td]);
+        z |= mv & (ALLBITS - ANIMBIT);
+        if (td > 0) z |= ANIMBIT;
+        e.map[tix(x, y)] = (uint16_t)z;
+    }
+}
+
+// [LEAD] simulate.cpp:1005-1037 doRail
+MPD void do_rail(Env &e, int x, int y)
+{
+    S.railTotal++;
+    generate_train(e, x, y);
+    if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {
+        if (!(rnd16(e) & 511)) {
+            int cv = e.map[tix(x, y)];
+            if (!(cv & CONDBIT)) {
+                if (S.roadEffect < (rnd16(e) & 31)) {
+                    int t = cv & LOMASK;
+                    if (t < T_RAILBASE + 2) e.map[tix(x, y)] = T_RIVER;
+                    else e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ map scan
+MPD bool tile_is_active(int v) { return (v & LOMASK) >= T_FLOOD; }   // simulate.cpp:937-945
+
+// [LEAD] simulate.cpp:929-997 body of mapScan for one tile
+MPD void scan_tile(Env &e, int idx)
+{
+    int mv = e.map[idx], tile = mv & LOMASK;
+    int x = idx / WORLD_H, y = idx - x * WORLD_H;
+    if (tile < T_ROADBASE) {
+        if (tile >= T_FIREBASE) {
+            S.firePop++;
+            if (!(rnd16(e) & 3)) do_fire(e, x, y);
+            return;
+        }
+        if (tile < T_RADTILE) do_flood(e, x, y);
+        else if ((rnd16(e) & 4095) == 0) e.map[idx] = T_DIRT;        // doRadTile :1040-1045
+        return;
+    }
+    if (S.newPower && (mv & CONDBIT)) set_zone_power(e, x, y);
+    if (tile >= T_ROADBASE && tile < T_POWERBASE) { do_road(e, x, y); return; }
+    if (mv & ZONEBIT) { do_zone(e, x, y); return; }
+    if (tile >= T_RAILBASE && tile < T_RESBASE) { do_rail(e, x, y); return; }
+    if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) e.map[idx] = (uint16_t)random_rubble(e);
+}
+
+// [ALL] mapScan(x1, x2).  The scan order is linear memory order (x outer, y inner over the
+// column-major map).  Device: warp 0 looks at 32 tiles at a time (one 64-byte row of the packed
+// uint16 map), a ballot finds the tiles the reference would not skip, and lane 0 processes them
+// one by one in order; after each processed tile the ballot is re-taken for the tiles behind it
+// because processing may have changed them (fire spread, zonePlop, ...).
+MPD void map_scan(Env &e, int x1, int x2)
+{
+    const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
+#if defined(__CUDA_ARCH__)
+    if (e.c.tid < 32) {
+        const int lane = e.c.tid;
+        for (int base = i0; base < i1; base += 32) {
+            int idx = base + lane;
+            bool ok = idx < i1;
+            unsigned m = __ballot_sync(0xffffffffu, ok && tile_is_active(e.map[ok ? idx : i0]));
+            while (m) {
+                int b = __ffs(m) - 1;
+                if (lane == 0) scan_tile(e, base + b);
+                __syncwarp();
+                unsigned hi = (b == 31) ? 0u : (0xffffffffu << (b + 1));
+                m = __ballot_sync(0xffffffffu, ok && tile_is_active(e.map[ok ? idx : i0])) & hi;
+            }
+        }
+    }
+#else
+    for (int idx = i0; idx < i1; idx++)
+        if (tile_is_active(e.map[idx])) scan_tile(e, idx);
+#endif
+    e.c.sync();
+}
+
+// ------------------------------------------------------------------ phase 9: census, tax
+// [LEAD] simulate.cpp:712-780 take10Census
+MPN void take10_census(Env &e)
+{
+    for (int x = 118; x >= 0; x--) {
+        e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
+        e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
+        e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
+    }
+    e.resHist[0] = (int16_t)(S.resPop / 8);
+    e.comHist[0] = S.comPop;
+    e.indHist[0] = S.indPop;
+    S.crimeRamp = (int16_t)(S.crimeRamp + (S.crimeAverage - S.crimeRamp) / 4);
+    e.crimeHist[0] = tmin(S.crimeRamp, (int16_t)255);
+    S.pollutionRamp = (int16_t)(S.pollutionRamp + (S.pollutionAverage - S.pollutionRamp) / 4);
+    e.pollutionHist[0] = tmin(S.pollutionRamp, (int16_t)255);
+    int16_t x = (int16_t)((S.cashFlow / 20) + 128);
+    e.moneyHist[0] = tclamp(x, (int16_t)0, (int16_t)255);
+    int16_t resPopScaled = (int16_t)(S.resPop >> 8);
+    if (S.hospitalPop < resPopScaled) S.needHospital = 1;
+    if (S.hospitalPop > resPopScaled) S.needHospital = -1;
+    if (S.hospitalPop == resPopScaled) S.needHospital = 0;
+    int faithfulPop = resPopScaled + S.faith;
+    if (S.churchPop < faithfulPop) S.needChurch = 1;
+    if (S.churchPop > faithfulPop) S.needChurch = -1;
+    if (S.churchPop == faithfulPop) S.needChurch = 0;
+}
+
+// [LEAD] simulate.cpp:784-826 take120Census
+MPN void take120_census(Env &e)
+{
+    for (int x = 238; x >= 120; x--) {
+        e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
+        e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
+        e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
+    }
+    e.resHist[120] = (int16_t)(S.resPop / 8);
+    e.comHist[120] = S.comPop;
+    e.indHist[120] = S.indPop;
+    e.crimeHist[120] = e.crimeHist[0];
+    e.pollutionHist[120] = e.pollutionHist[0];
+    e.moneyHist[120] = e.moneyHist[0];
+}
+
+// [LEAD] budget.cpp:107-316 doBudgetNow(false)
+MPN void do_budget(Env &e)
+{
+    int64_t fireInt = (int)(S.fireFund * S.firePercent);
+    int64_t policeInt = (int)(S.policeFund * S.policePercent);
+    int64_t roadInt = (int)(S.roadFund * S.roadPercent);
+    int64_t total = fireInt + policeInt + roadInt;
+    int64_t yum = S.taxFund + S.totalFunds;
+    if (yum > total) {
+        S.fireValue = fireInt; S.policeValue = policeInt; S.roadValue = roadInt;
+    } else if (total > 0) {
+        if (yum > roadInt) {
+            S.roadValue = roadInt;
+            yum -= roadInt;
+            if (yum > fireInt) {
+                S.fireValue = fireInt;
+                yum -= fireInt;
+                if (yum > policeInt) {
+                    S.policeValue = policeInt;
+                    yum -= policeInt;
+                } else {
+                    S.policeValue = yum;
+                    S.policePercent = yum > 0 ? ((float)yum) / ((float)S.policeFund) : 0.0f;
+                }
+            } else {
+                S.fireValue = yum;
+                S.policeValue = 0;
+                S.policePercent = 0.0f;
+                S.firePercent = yum > 0 ? ((float)yum) / ((float)S.fireFund) : 0.0f;
+            }
+        } else {
+            S.roadValue = yum;
+            S.fireValue = 0; S.policeValue = 0;
+            S.firePercent = 0.0f; S.policePercent = 0.0f;
+            S.roadPercent = yum > 0 ? ((float)yum) / ((float)S.roadFund) : 0.0f;
+        }
+    } else {
+        S.fireValue = 0; S.policeValue = 0; S.roadValue = 0;
+        S.firePercent = 1.0f; S.policePercent = 1.0f; S.roadPercent = 1.0f;
+    }
+    for (;;) {
+        if (!S.autoBudget) {
+            // showBudgetWindowAndStartWaiting is a front-end callback (no state)
+            S.fireSpend = S.fireValue; S.policeSpend = S.policeValue; S.roadSpend = S.roadValue;
+            total = S.fireSpend + S.policeSpend + S.roadSpend;
+            int64_t moreDough = S.taxFund - total;
+            S.totalFunds = (int)(S.totalFunds - (int)(-moreDough));    // spend(int) -> setFunds(int)
+            return;
+        }
+        if (yum > total) {
+            int64_t moreDough = S.taxFund - total;
+            S.totalFunds = (int)(S.totalFunds - (int)(-moreDough));
+            S.fireSpend = S.fireFund; S.policeSpend = S.policeFund; S.roadSpend = S.roadFund;
+            return;
+        }
+        S.autoBudget = 0;
+    }
+}
+
+// [LEAD] simulate.cpp:838-884 collectTax
+MPN void collect_tax(Env &e)
+{
+    const float RLevels[3] = { 0.7f, 0.9f, 1.2f }, FLevels[3] = { 1.4f, 1.2f, 0.8f };
+    S.cashFlow = 0;
+    if (!S.taxFlag) {
+        S.cityTaxAverage = 0;
+        S.policeFund = (int64_t)S.policeStationPop * 100;
+        S.fireFund = (int64_t)S.fireStationPop * 100;
+        S.roadFund = (int64_t)((S.roadTotal + (S.railTotal * 2)) * RLevels[S.gameLevel]);
+        S.taxFund = (int64_t)((((int64_t)S.totalPop * S.landValueAverage) / 120) * S.cityTax * FLevels[S.gameLevel]);
+        if (S.totalPop > 0) {
+            S.cashFlow = (int16_t)(S.taxFund - (S.policeFund + S.fireFund + S.roadFund));
+            do_budget(e);
+        } else {
+            S.roadEffect = MAX_ROAD_EFFECT;
+            S.policeEffect = MAX_POLICE_EFFECT;
+            S.fireEffect = MAX_FIRE_EFFECT;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ phase 10
+// [ALL] simulate.cpp:327-350 decTrafficMap
+MPD void dec_traffic_map(Env &e)
+{
+    for (int i = e.c.tid; i < N2; i += e.c.n) {
+        int z = e.traffic[i];
+        if (z == 0) continue;
+        if (z <= 24) e.traffic[i] = 0;
+        else if (z > 200) e.traffic[i] = (uint8_t)(z - 34);
+        else e.traffic[i] = (uint8_t)(z - 24);
+    }
+}
+
+// [ALL] simulate.cpp:356-385 decRateOfGrowthMap
+MPD void dec_rog_map(Env &e)
+{
+    for (int i = e.c.tid; i < N8; i += e.c.n) {
+        int16_t z = e.rog[i];
+        if (z == 0) continue;
+        if (z > 0) z--; else z++;
+        e.rog[i] = tclamp(z, (int16_t)-200, (int16_t)200);
+    }
+}
+
+MPD int64_t get_population(const Env &e) { return ((int64_t)S.resPop + ((int64_t)S.comPop + S.indPop) * 8L) * 20L; }
+MPD int city_class_of(int64_t p)                                    // evaluate.cpp:190-218
+{
+    int c = 0;
+    if (p > 2000) c = 1;
+    if (p > 10000) c = 2;
+    if (p > 50000) c = 3;
+    if (p > 100000) c = 4;
+    if (p > 500000) c = 5;
+    return c;
+}
+
+// [LEAD] message.cpp:77-231 sendMessages + :235-283 checkGrowth.  Messages themselves are
+// front-end callbacks; only the state they gate (growth caps, category bookkeeping) is kept.
+MPN void send_messages(Env &e)
+{
+    if ((S.cityTime & 3) == 0) {
+        int16_t category = 0;
+        int64_t thisCityPop = get_population(e);
+        if (S.cityPopLast > 0) {
+            int lastClass = city_class_of(S.cityPopLast), newClass = city_class_of(thisCityPop);
+            if (lastClass != newClass) {
+                // MESSAGE_REACHED_TOWN.. = 35..39 (text.h); only equality with categoryLast matters
+                if (newClass >= 1) category = (int16_t)(34 + newClass);
+            }
+        }
+        if (category > 0 && category != S.categoryLast) S.categoryLast = category;
+        S.cityPopLast = thisCityPop;
+    }
+    S.totalZonePop = (int16_t)(S.resZonePop + S.comZonePop + S.indZonePop);
+    switch (S.cityTime & 63) {
+    case 26: S.resCap = (S.resPop > 500 && S.stadiumPop == 0); break;
+    case 28: S.indCap = (S.indPop > 70 && S.seaportPop == 0); break;
+    case 30: S.comCap = (S.comPop > 100 && S.airportPop == 0); break;
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------ phase 11: power
+// [LEAD] power.cpp:76-156 doPowerScan stack walk (powerGridMap already cleared by ALL).
+// Literal replay: numPower counts visits AND pops, so the cut-off depends on traversal order.
+MPN void power_scan_walk(Env &e)
+{
+    int64_t maxPower = S.coalPowerPop * 700L + S.nuclearPowerPop * 2000L;
+    int64_t numPower = 0;
+    while (S.powerStackPointer > 0) {
+        int p = e.pstack[S.powerStackPointer];
+        S.powerStackPointer--;
+        int x = p / WORLD_H, y = p - x * WORLD_H;
+        int anyDir = D_INVALID, conNum;
+        do {
+            numPower++;
+            if (numPower > maxPower) return;
+            if (anyDir != D_INVALID) pos_move(x, y, anyDir);
+            pwr_set(e, x, y);
+            conNum = 0;
+            int dir = D_N;
+            while (dir < D_END && conNum < 2) {
+                int mx = x, my = y;
+                if (pos_move(mx, my, dir)) {
+                    if ((e.map[tix(mx, my)] & CONDBIT) && !pwr_get(e, mx, my)) {
+                        conNum++;
+                        anyDir = dir;
+                    }
+                }
+                dir += 2;
+            }
+            if (conNum > 1) push_power_stack(e, x, y);
+        } while (conNum);
+    }
+}
+
+// [ALL]
+MPD void do_power_scan(Env &e)
+{
+    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
+    e.c.sync();
+    if (e.c.lead()) power_scan_walk(e);
+    e.c.sync();
+}
+
+// ------------------------------------------------------------------ smoothing passes
+// [ALL] scan.cpp:551-575 smoothDitherMap, non-dither branch (donDither = 0 on this path)
+MPD void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
+{
+    for (int i = e.c.tid; i < N2; i += e.c.n) {
+        int x = i / H2, y = i - x * H2;
+        int16_t z = 0;
+        if (x > 0) z = (int16_t)(z + src[i - H2]);
+        if (x < W2 - 1) z = (int16_t)(z + src[i + H2]);
+        if (y > 0) z = (int16_t)(z + src[i - 1]);
+        if (y < H2 - 1) z = (int16_t)(z + src[i + 1]);
+        z = (int16_t)((z + src[i]) >> 2);
+        if (z > 255) z = 255;
+        dst[i] = (uint8_t)z;
+    }
+    e.c.sync();
+}
+
+// [ALL] scan.cpp:80-105 smoothStationMap (in place through a temporary copy)
+MPD void smooth_station(Env &e, int16_t *m)
+{
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.stmp[i] = m[i];
+    e.c.sync();
+    for (int i = e.c.tid; i < N8; i += e.c.n) {
+        int x = i / H8, y = i - x * H8;
+        int16_t edge = 0;
+        if (x > 0) edge = (int16_t)(edge + e.stmp[i - H8]);
+        if (x < W8 - 1) edge = (int16_t)(edge + e.stmp[i + H8]);
+        if (y > 0) edge = (int16_t)(edge + e.stmp[i - 1]);
+        if (y < H8 - 1) edge = (int16_t)(edge + e.stmp[i + 1]);
+        edge = (int16_t)(e.stmp[i] + edge / 4);
+        m[i] = (int16_t)(edge / 2);
+    }
+    e.c.sync();
+}
+
+MPD int city_center_distance(const Env &e, int x, int y)            // scan.cpp:379-396
+{
+    int xd = x > S.cityCenterX ? x - S.cityCenterX : S.cityCenterX - x;
+    int yd = y > S.cityCenterY ? y - S.cityCenterY : S.cityCenterY - y;
+    return tmin(xd + yd, 64);
+}
+
+MPD int pollution_value(int loc)                                    // scan.cpp:331-370
+{
+    if (loc < T_POWERBASE) {
+        if (loc >= T_HTRFBASE) return 75;
+        if (loc >= T_LTRFBASE) return 50;
+        if (loc < T_ROADBASE) {
+            if (loc > T_FIREBASE) return 90;
+            if (loc >= T_RADTILE) return 255;
+        }
+        return 0;
+    }
+    if (loc <= T_LASTIND) return 0;
+    if (loc < T_PORTBASE) return 50;
+    if (loc <= T_LASTPOWERPLANT) return 100;
+    return 0;
+}
+
+// block-wide integer sum of per-thread partials into e.c.red[slot] (valid after the barrier)
+MPD void coop_add(Env &e, int slot, int v)
+{
+#if defined(__CUDA_ARCH__)
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((e.c.tid & 31) == 0 && v) atomicAdd(&e.c.red[slot], v);
+#else
+    e.c.red[slot] += v;
+#endif
+}
+
+// [ALL] scan.cpp:217-322 pollutionTerrainLandValueScan (+ :454-497 smoothTerrain, non-dither)
+MPN void ptlv_scan(Env &e)
+{
+    if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; }
+    // tempMap3: +15 per natural tile (0 < tile < RUBBLE) in each 4x4 block (Byte wrap)
+    for (int i = e.c.tid; i < N4; i += e.c.n) {
+        int bx = (i / H4) * 4, by = (i % H4) * 4, cnt = 0;
+        for (int dx = 0; dx < 4; dx++)
+            for (int dy = 0; dy < 4; dy++) {
+                int loc = e.map[tix(bx + dx, by + dy)] & LOMASK;
+                if (loc && loc < T_RUBBLE) cnt++;
+            }
+        e.tmp3[i] = (uint8_t)(cnt * 15);
+    }
+    e.c.sync();
+    int lvtot = 0, lvnum = 0;
+    for (int i = e.c.tid; i < N2; i += e.c.n) {
+        int x = i / H2, y = i - x * H2, wx = x * 2, wy = y * 2;
+        int plevel = 0;
+        bool lvflag = false;
+        for (int mx = wx; mx <= wx + 1; mx++)
+            for (int my = wy; my <= wy + 1; my++) {
+                int loc = e.map[tix(mx, my)] & LOMASK;
+                if (loc) {
+                    if (loc < T_RUBBLE) continue;
+                    plevel += pollution_value(loc);
+                    if (loc >= T_ROADBASE) lvflag = true;
+                }
+            }
+        plevel = tmin(plevel, 255);
+        e.tmp1[i] = (uint8_t)plevel;
+        if (lvflag) {
+            int dis = 34 - city_center_distance(e, wx, wy) / 2;
+            dis = dis << 2;
+            dis += e.terrain[(x >> 1) * H4 + (y >> 1)];
+            dis -= e.pollution[i];
+            if (e.crime[i] > 190) dis -= 20;
+            dis = tclamp(dis, 1, 250);
+            e.landval[i] = (uint8_t)dis;
+            lvtot += dis;
+            lvnum++;
+        } else {
+            e.landval[i] = 0;
+        }
+    }
+    coop_add(e, 0, lvtot);
+    coop_add(e, 1, lvnum);
+    e.c.sync();
+    if (e.c.lead()) S.landValueAverage = e.c.red[1] > 0 ? (int16_t)(e.c.red[0] / e.c.red[1]) : (int16_t)0;
+    smooth_byte2(e, e.tmp1, e.tmp2);
+    smooth_byte2(e, e.tmp2, e.tmp1);
+    // pollution max: draws depend on the running maximum, so this is the serial lane
+    for (int i = e.c.tid; i < N2; i += e.c.n) e.pollution[i] = e.tmp1[i];
+    e.c.sync();
+    if (e.c.lead()) {
+        int pmax = 0, pnum = 0;
+        int64_t ptot = 0;
+        for (int i = 0; i < N2; i++) {
+            int z = e.tmp1[i];
+            if (z) {
+                pnum++;
+                ptot += z;
+                if (z > pmax || (z == pmax && (rnd16(e) & 3) == 0)) {
+                    pmax = z;
+                    S.pollutionMaxX = (int16_t)((i / H2) * 2);
+                    S.pollutionMaxY = (int16_t)((i % H2) * 2);
+                }
+            }
+        }
+        S.pollutionAverage = pnum ? (int16_t)(ptot / pnum) : (int16_t)0;
+    }
+    // smoothTerrain: tempMap3 -> terrainDensityMap
+    for (int i = e.c.tid; i < N4; i += e.c.n) {
+        int x = i / H4, y = i - x * H4;
+        unsigned z = 0;
+        if (x > 0) z += e.tmp3[i - H4];
+        if (x < W4 - 1) z += e.tmp3[i + H4];
+        if (y > 0) z += e.tmp3[i - 1];
+        if (y < H4 - 1) z += e.tmp3[i + 1];
+        e.terrain[i] = (uint8_t)((uint8_t)(z / 4 + e.tmp3[i]) / 2);
+    }
+    e.c.sync();
+}
+
+// [ALL] scan.cpp:403-450 crimeScan
+MPN void crime_scan(Env &e)
+{
+    smooth_station(e, e.policeSt);
+    smooth_station(e, e.policeSt);
+    smooth_station(e, e.policeSt);
+    for (int i = e.c.tid; i < N2; i += e.c.n) {
+        int x = i / H2, y = i - x * H2;
+        int z = e.landval[i];
+        if (z > 0) {
+            z = 128 - z;
+            z += e.pop[i];
+            z = tmin(z, 300);
+            z -= e.policeSt[(x >> 2) * H8 + (y >> 2)];
+            z = tclamp(z, 0, 250);
+            e.crime[i] = (uint8_t)z;
+            e.tmp2[i] = 1;
+        } else {
+            e.crime[i] = 0;
+            e.tmp2[i] = 0;
+        }
+    }
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.policeEff[i] = e.policeSt[i];
+    e.c.sync();
+    if (e.c.lead()) {
+        int64_t totz = 0;
+        int numz = 0, cmax = 0;
+        for (int i = 0; i < N2; i++) {
+            if (!e.tmp2[i]) continue;
+            int z = e.crime[i];
+            ++numz;
+            totz += z;
+            if (z > cmax || (z == cmax && (rnd16(e) & 3) == 0)) {
+                cmax = z;
+                S.crimeMaxX = (int16_t)((i / H2) * 2);
+                S.crimeMaxY = (int16_t)((i % H2) * 2);
+            }
+        }
+        S.crimeAverage = numz > 0 ? (int16_t)(totz / numz) : (int16_t)0;
+    }
+    e.c.sync();
+}
+
+MPD int population_density_of(const Env &e, int x, int y, int tile)     // scan.cpp:186-210
+{
+    if (tile == T_FREEZ) return do_free_pop(e, x, y);
+    if (tile < T_COMBASE) return res_zone_pop(tile);
+    if (tile < T_INDBASE) return com_zone_pop(tile) * 8;
+    if (tile < T_PORTBASE) return ind_zone_pop(tile) * 8;
+    return 0;
+}
+
+// [ALL] scan.cpp:126-179 populationDensityScan (+ :580-590 computeComRateMap)
+MPN void pop_density_scan(Env &e)
+{
+    if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; e.c.red[2] = 0; }
+    e.c.sync();
+    int xt = 0, yt = 0, zt = 0;
+    for (int i = e.c.tid; i < N2; i += e.c.n) {
+        int bx = (i / H2) * 2, by = (i % H2) * 2, v = 0;
+        for (int dx = 0; dx < 2; dx++)          // scan order inside the 2x2 cluster: last zone wins
+            for (int dy = 0; dy < 2; dy++) {
+                int mv = e.map[tix(bx + dx, by + dy)];
+                if (mv & ZONEBIT) {
+                    int pop = population_density_of(e, bx + dx, by + dy, mv & LOMASK) * 8;
+                    v = tmin(pop, 254);
+                    xt += bx + dx; yt += by + dy; zt++;
+                }
+            }
+        e.tmp1[i] = (uint8_t)v;
+    }
+    coop_add(e, 0, xt);
+    coop_add(e, 1, yt);
+    coop_add(e, 2, zt);
+    e.c.sync();
+    smooth_byte2(e, e.tmp1, e.tmp2);
+    smooth_byte2(e, e.tmp2, e.tmp1);
+    smooth_byte2(e, e.tmp1, e.tmp2);
+    for (int i = e.c.tid; i < N2; i += e.c.n) e.pop[i] = (uint8_t)(e.tmp2[i] * 2);
+    if (e.c.lead()) {
+        if (e.c.red[2] > 0) {
+            S.cityCenterX = (int16_t)(e.c.red[0] / e.c.red[2]);
+            S.cityCenterY = (int16_t)(e.c.red[1] / e.c.red[2]);
+        } else {
+            S.cityCenterX = WORLD_W / 2;
+            S.cityCenterY = WORLD_H / 2;
+        }
+    }
+    e.c.sync();
+    // computeComRateMap uses the NEW city centre only from the next scan on: the reference calls
+    // it before updating cityCenterX/Y (scan.cpp:166-174), so it must see the old centre.
+}
+
+// [ALL] helper so that computeComRateMap sees the centre the reference saw
+MPD void com_rate_map(Env &e, int cx, int cy)
+{
+    for (int i = e.c.tid; i < N8; i += e.c.n) {
+        int x = (i / H8) * 8, y = (i % H8) * 8;
+        int xd = x > cx ? x - cx : cx - x, yd = y > cy ? y - cy : cy - y;
+        int16_t z = (int16_t)(tmin(xd + yd, 64) / 2);
+        z = (int16_t)(z * 4);
+        e.comRate[i] = (int16_t)(64 - z);
+    }
+}
+
+// [ALL] scan.cpp:110-120 fireAnalysis
+MPD void fire_analysis(Env &e)
+{
+    smooth_station(e, e.fireSt);
+    smooth_station(e, e.fireSt);
+    smooth_station(e, e.fireSt);
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.fireEff[i] = e.fireSt[i];
+    e.c.sync();
+}
+
+// ------------------------------------------------------------------ evaluation (evaluate.cpp)
+// [LEAD] evaluate.cpp:100-124.  problemTable has PROBNUM+1 live slots because voteProblems walks
+// problem = 0..PROBNUM inclusive (:293); slot PROBNUM reads as 0 in the pinned oracle (see
+// oracle/build_ref.sh) -- it consumes a draw per visit and never votes.
+MPN void city_evaluation(Env &e)
+{
+    if (S.totalPop > 0) {
+        int16_t pt[PROBNUM + 1];
+        for (int z = 0; z <= PROBNUM; z++) pt[z] = 0;
+        // getAssessedValue :154-169
+        int64_t z = S.roadTotal * 5;
+        z += S.railTotal * 10; z += S.policeStationPop * 1000; z += S.fireStationPop * 1000;
+        z += S.hospitalPop * 400; z += S.stadiumPop * 3000; z += S.seaportPop * 5000;
+        z += S.airportPop * 10000; z += S.coalPowerPop * 3000; z += S.nuclearPowerPop * 6000;
+        S.cityAssessedValue = z * 1000;
+        // doPopNum :176-187
+        int64_t old = S.cityPop;
+        S.cityPop = get_population(e);
+        if (old == -1) old = S.cityPop;
+        S.cityPopDelta = S.cityPop - old;
+        S.cityClass = city_class_of(S.cityPop);
+        // doProblems :227-269
+        pt[0] = S.crimeAverage;
+        pt[1] = S.pollutionAverage;
+        pt[2] = (int16_t)(S.landValueAverage * 7 / 10);
+        pt[3] = (int16_t)(S.cityTax * 10);
+        {   // getTrafficAverage :305-327
+            int64_t tt = 0;
+            int16_t count = 1;
+            for (int i = 0; i < N2; i++)
+                if (e.landval[i] > 0) { tt += e.traffic[i]; count++; }
+            S.trafficAverage = d2s((double)(tt / count) * 2.4);
+            pt[4] = S.trafficAverage;
+        }
+        {   // getUnemployment :335-350
+            int16_t b = (int16_t)((S.comPop + S.indPop) * 8);
+            if (b == 0) pt[5] = 0;
+            else {
+                float r = ((float)S.resPop) / b;
+                b = f2s((r - 1) * 255);
+                pt[5] = tmin(b, (int16_t)255);
+            }
+        }
+        int16_t fireSeverity = (int16_t)tmin(S.firePop * 5, 255);
+        pt[6] = fireSeverity;
+        // voteProblems :278-299
+        for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+        int problem = 0, voteCount = 0, loopCount = 0;
+        while (voteCount < 100 && loopCount < 600) {
+            if (rnd(e, 300) < pt[problem]) {
+                S.problemVotes[problem]++;     // problem == PROBNUM never gets here (pt = 0)
+                voteCount++;
+            }
+            problem++;
+            if (problem > PROBNUM) problem = 0;
+            loopCount++;
+        }
+        bool taken[PROBNUM];
+        for (int i = 0; i < PROBNUM; i++) taken[i] = false;
+        for (int c = 0; c < PROBLEM_COMPLAINTS; c++) {
+            int maxVotes = 0, best = NUMPROBLEMS;
+            for (int i = 0; i < NUMPROBLEMS; i++)
+                if (S.problemVotes[i] > maxVotes && !taken[i]) { best = i; maxVotes = S.problemVotes[i]; }
+            S.problemOrder[c] = (int16_t)best;
+            if (best < NUMPROBLEMS) taken[best] = true;
+        }
+        // getScore :359-451 (int, float and double mixed exactly as written there)
+        int16_t last = S.cityScore;
+        int x = 0;
+        for (int i = 0; i < NUMPROBLEMS; i++) x += pt[i];
+        x = x / 3;
+        x = tmin(x, 256);
+        int sc = tclamp((256 - x) * 4, 0, 1000);
+        if (S.resCap) sc = (int)(sc * .85);
+        if (S.comCap) sc = (int)(sc * .85);
+        if (S.indCap) sc = (int)(sc * .85);
+        if (S.roadEffect < MAX_ROAD_EFFECT) sc -= (int)(MAX_ROAD_EFFECT - S.roadEffect);
+        if (S.policeEffect < MAX_POLICE_EFFECT)
+            sc = (int)(sc * (0.9 + (S.policeEffect / (10.0001 * MAX_POLICE_EFFECT))));
+        if (S.fireEffect < MAX_FIRE_EFFECT)
+            sc = (int)(sc * (0.9 + (S.fireEffect / (10.0001 * MAX_FIRE_EFFECT))));
+        if (S.resValve < -1000) sc = (int)(sc * .85);
+        if (S.comValve < -1000) sc = (int)(sc * .85);
+        if (S.indValve < -1000) sc = (int)(sc * .85);
+        float SM = 1.0f;
+        if (S.cityPop == 0 || S.cityPopDelta == 0) SM = 1.0f;
+        else if (S.cityPopDelta == S.cityPop) SM = 1.0f;
+        else if (S.cityPopDelta > 0) SM = ((float)S.cityPopDelta / S.cityPop) + 1.0f;
+        else if (S.cityPopDelta < 0) SM = 0.95f + ((float)S.cityPopDelta / (S.cityPop - S.cityPopDelta));
+        sc = (int)(sc * SM);
+        sc = sc - fireSeverity - S.cityTax;
+        float TM = (float)(S.unpoweredZoneCount + S.poweredZoneCount);
+        if (TM > 0.0f) sc = (int)(sc * (float)(S.poweredZoneCount / TM));
+        sc = tclamp(sc, 0, 1000);
+        S.cityScore = (int16_t)((S.cityScore + sc) / 2);
+        S.cityScoreDelta = (int16_t)(S.cityScore - last);
+        // doVotes :454-464
+        S.cityYes = 0;
+        for (int i = 0; i < 100; i++)
+            if (rnd(e, 1000) < S.cityScore) S.cityYes++;
+    } else {
+        // evalInit :129-147
+        S.cityPop = 0; S.cityPopDelta = 0; S.cityAssessedValue = 0; S.cityClass = 0;
+        S.cityScore = 500; S.cityScoreDelta = 0;
+        for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+        for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
+        S.cityYes = 50;
+    }
+}
+
+// ------------------------------------------------------------------ the 16-phase cycle
+// [ALL] simulate.cpp:122-268 simulate
+MPD void simulate(Env &e)
+{
+    const int16_t spdPower[3] = { 2, 4, 5 }, spdPtlv[3] = { 2, 7, 17 }, spdCrime[3] = { 1, 8, 18 };
+    const int16_t spdPop[3] = { 1, 9, 19 }, spdFire[3] = { 1, 10, 20 };
+    if (e.c.lead()) {
+        if (S.initSimLoad) S.phaseCycle = 0;
+        else S.phaseCycle &= 15;
+    }
+    e.c.sync();
+    const int phase = S.phaseCycle;
+    const int si = tclamp((int)S.simSpeed - 1, 0, 2);
+    switch (phase) {
+    case 0:
+        if (e.c.lead()) {
+            if (++S.simCycle > 1023) S.simCycle = 0;
+            if (S.doInitialEval) {
+                S.doInitialEval = 0;
+                city_evaluation(e);
+            }
+            S.cityTime++;
+            S.cityTaxAverage = (int16_t)(S.cityTaxAverage + S.cityTax);
+            if (!(S.simCycle & 1)) set_valves(e);
+            clear_census_scalars(e);
+        }
+        for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
+        break;
+    case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
+        map_scan(e, (phase - 1) * WORLD_W / 8, phase * WORLD_W / 8);
+        break;
+    case 9:
+        if (e.c.lead()) {
+            if (S.cityTime % 4 == 0) take10_census(e);
+            if (S.cityTime % 48 == 0) take120_census(e);
+            if (S.cityTime % 48 == 0) {
+                collect_tax(e);
+                city_evaluation(e);
+            }
+        }
+        break;
+    case 10:
+        if (!(S.simCycle % 5)) dec_rog_map(e);
+        dec_traffic_map(e);
+        if (e.c.lead()) send_messages(e);
+        break;
+    case 11:
+        if ((S.simCycle % spdPower[si]) == 0) {
+            do_power_scan(e);
+            if (e.c.lead()) S.newPower = 1;
+        }
+        break;
+    case 12:
+        if ((S.simCycle % spdPtlv[si]) == 0) ptlv_scan(e);
+        break;
+    case 13:
+        if ((S.simCycle % spdCrime[si]) == 0) crime_scan(e);
+        break;
+    case 14:
+        if ((S.simCycle % spdPop[si]) == 0) {
+            int cx = S.cityCenterX, cy = S.cityCenterY;
+            e.c.sync();
+            pop_density_scan(e);
+            com_rate_map(e, cx, cy);
+        }
+        break;
+    case 15:
+        if ((S.simCycle % spdFire[si]) == 0) fire_analysis(e);
+        if (e.c.lead()) do_disasters(e);
+        break;
+    }
+    e.c.sync();
+    if (e.c.lead()) S.phaseCycle = (int16_t)((phase + 1) & 15);
+    e.c.sync();
+}
+
+// [ALL] simulate.cpp:98-118 simFrame + main.cpp:403-425 simLoop(true) (heatSteps = 0)
+MPD void sim_loop(Env &e)
+{
+    bool run = false;
+    if (S.simSpeed != 0) {
+        int sc = S.speedCycle + 1;
+        if (sc > 1023) sc = 0;
+        run = !((S.simSpeed == 1 && (sc % 5) != 0) || (S.simSpeed == 2 && (sc % 3) != 0));
+        e.c.sync();
+        if (e.c.lead()) S.speedCycle = (int16_t)sc;
+        e.c.sync();
+    }
+    if (run) simulate(e);
+    if (e.c.lead()) move_objects(e);
+    e.c.sync();
+}
+
+// [ALL] simulate.cpp:276-305 doSimInit (+ :390-421 initSimMemory)
+MPD void do_sim_init(Env &e)
+{
+    if (e.c.lead()) {
+        S.phaseCycle = 0;
+        S.simCycle = 0;
+    }
+    e.c.sync();
+    if (S.initSimLoad == 2) {
+        if (e.c.lead()) {
+            // setCommonInits -> evalInit
+            S.cityYes = 0; S.cityPop = 0; S.cityPopDelta = 0; S.cityAssessedValue = 0;
+            S.cityClass = 0; S.cityScore = 500; S.cityScoreDelta = 0;
+            for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+            for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
+            S.roadEffect = MAX_ROAD_EFFECT; S.policeEffect = MAX_POLICE_EFFECT;
+            S.fireEffect = MAX_FIRE_EFFECT; S.taxFlag = 0; S.taxFund = 0;
+            S.crimeRamp = 0; S.pollutionRamp = 0; S.totalPop = 0;
+            S.resValve = 0; S.comValve = 0; S.indValve = 0;
+            S.resCap = 0; S.comCap = 0; S.indCap = 0;
+            S.externalMarket = 6.0f;
+            S.disasterEvent = 0; S.scoreType = 0;
+            S.powerStackPointer = 0;
+        }
+        for (int i = e.c.tid; i < 240; i += e.c.n) {
+            e.resHist[i] = 0; e.comHist[i] = 0; e.indHist[i] = 0;
+            e.moneyHist[i] = 128; e.crimeHist[i] = 0; e.pollutionHist[i] = 0;
+        }
+        e.c.sync();
+        do_power_scan(e);
+        if (e.c.lead()) { S.newPower = 1; S.initSimLoad = 0; }
+        e.c.sync();
+    }
+    // initSimLoad == 1 (city loaded from file) is not reachable on the gym path
+    if (e.c.lead()) { set_valves(e); clear_census_scalars(e); }
+    for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
+    e.c.sync();
+    map_scan(e, 0, WORLD_W);
+    do_power_scan(e);
+    if (e.c.lead()) S.newPower = 1;
+    e.c.sync();
+    ptlv_scan(e);
+    crime_scan(e);
+    {
+        int cx = S.cityCenterX, cy = S.cityCenterY;
+        e.c.sync();
+        pop_density_scan(e);
+        com_rate_map(e, cx, cy);
+        e.c.sync();
+    }
+    fire_analysis(e);
+    if (e.c.lead()) { S.totalPop = 1; S.doInitialEval = 1; }
+    e.c.sync();
+}
+
+// [ALL] animate.cpp:204-219 animateTiles
+MPD void animate_tiles(Env &e)
+{
+    for (int i = e.c.tid; i < NTILES; i += e.c.n) {
+        int v = e.map[i];
+        if (v & ANIMBIT) e.map[i] = (uint16_t)(e.anim[v & LOMASK] | (v & ALLBITS));
+    }
+    e.c.sync();
+}
+
+#undef S
+} // namespace mp

@@ -1,0 +1,262 @@
+// mp_state.h -- per-city state layout, accessors, RNG and the cooperative-thread context.
+//
+// One city ("env") is one contiguous block in HBM (see EnvLayout): the 120x100 uint16 tile map
+// (column-major x*100+y like the reference, allocate.cpp:75-87), the five 60x50 byte overlays,
+// the 30x25 terrain overlay, the power grid BIT-PACKED (12 000 bits), the six 15x13 short maps,
+// the history arrays, the scalar block and the sprite table, followed by per-env scratch.
+// The engine code in mp_*.h is written once against `Env` (a bundle of pointers + a thread
+// context) and compiles both for the device (one CTA per env, `Coop` = the CTA) and, for the CPU
+// test harness under tests/, for the host (`Coop` = a single thread).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "mp_tiles.h"
+
+#if defined(__CUDACC__)
+#define MPD __device__ __forceinline__
+#define MPN __device__ __noinline__
+#define MPH __host__ __device__ inline
+#else
+#define MPD inline
+#define MPN inline
+#define MPH inline
+#endif
+
+namespace mp {
+
+constexpr int WORLD_W = 120, WORLD_H = 100, NTILES = WORLD_W * WORLD_H;
+constexpr int W2 = 60, H2 = 50, N2 = W2 * H2;       // MapByte2
+constexpr int W4 = 30, H4 = 25, N4 = W4 * H4;       // MapByte4
+constexpr int W8 = 15, H8 = 13, N8 = W8 * H8;       // MapShort8
+constexpr int POWER_WORDS = NTILES / 32;            // 375
+constexpr int POWER_STACK_SIZE = NTILES / 4;        // micropolis.h:221
+constexpr int MAX_TRAFFIC_DISTANCE = 30;
+constexpr int MAX_ROAD_EFFECT = 32, MAX_POLICE_EFFECT = 1000, MAX_FIRE_EFFECT = 1000;
+constexpr int RES_VALVE_RANGE = 2000, COM_VALVE_RANGE = 1500, IND_VALVE_RANGE = 1500;
+constexpr int PROBNUM = 10, NUMPROBLEMS = 7, PROBLEM_COMPLAINTS = 4;
+constexpr int MAX_SPRITES = 48;
+
+enum : int {
+    PWRBIT = 0x8000, CONDBIT = 0x4000, BURNBIT = 0x2000, BULLBIT = 0x1000, ANIMBIT = 0x0800,
+    ZONEBIT = 0x0400, ALLBITS = 0xfc00, LOMASK = 0x03ff,
+    BLBNBIT = BULLBIT | BURNBIT, BLBNCNBIT = BULLBIT | BURNBIT | CONDBIT, BNCNBIT = BURNBIT | CONDBIT
+};
+
+enum SpriteType : int {
+    SPR_NONE = 0, SPR_TRAIN, SPR_HELICOPTER, SPR_AIRPLANE, SPR_SHIP, SPR_MONSTER, SPR_TORNADO,
+    SPR_EXPLOSION, SPR_BUS, SPR_COUNT
+};
+
+enum Dir : int { D_INVALID = 0, D_N, D_NE, D_E, D_SE, D_S, D_SW, D_W, D_NW, D_END };
+
+// reference micropolis.h:981-1018 (SimSprite); list links are slot indices, -1 = end
+struct Sprite {
+    int16_t type, frame, x, y, width, height, xOffset, yOffset, xHot, yHot;
+    int16_t origX, origY, destX, destY, count, soundCount, dir, newDir;
+    int16_t step, flag, control, turn, accel, speed;
+    int16_t next, used;
+};
+
+// Scalar state; widths follow reference micropolis.h (short / int / Quad=long / float / bool).
+struct Scalars {
+    int64_t cityTime, roadSpend, policeSpend, fireSpend, roadFund, policeFund, fireFund;
+    int64_t roadEffect, policeEffect, fireEffect, taxFund, roadValue, policeValue, fireValue;
+    int64_t cityPop, cityPopDelta, cityAssessedValue, cityPopLast, totalFunds;
+    uint32_t rng;
+    int32_t powerStackPointer, absDist, simPasses, gameLevel, cityClass, disasterEvent, scoreType,
+        scenario;
+    float roadPercent, policePercent, firePercent, externalMarket;
+    int16_t roadTotal, railTotal, firePop, resPop, comPop, indPop, totalPop, totalPopLast;
+    int16_t resZonePop, comZonePop, indZonePop, totalZonePop, hospitalPop, churchPop, faith;
+    int16_t stadiumPop, policeStationPop, fireStationPop, coalPowerPop, nuclearPowerPop;
+    int16_t seaportPop, airportPop, crimeAverage, pollutionAverage, landValueAverage, cityTax;
+    int16_t needHospital, needChurch, floodCount, cityYes, cityScore, cityScoreDelta;
+    int16_t trafficAverage, categoryLast, cityCenterX, cityCenterY, pollutionMaxX, pollutionMaxY;
+    int16_t crimeMaxX, crimeMaxY, crimeRamp, pollutionRamp, cashFlow, disasterWait, scoreWait;
+    int16_t poweredZoneCount, unpoweredZoneCount, cityTaxAverage, simCycle, phaseCycle, speedCycle;
+    int16_t resValve, comValve, indValve, spriteCycle, initSimLoad, simSpeed, trafMaxX, trafMaxY;
+    int16_t problemVotes[PROBNUM], problemOrder[PROBLEM_COMPLAINTS];
+    int16_t spriteHead, globalSprites[SPR_COUNT], curMapStackPointer;
+    uint8_t taxFlag, resCap, comCap, indCap, newPower, doInitialEval, autoBulldoze, autoBudget;
+    uint8_t enableDisasters, doAnimation, tilesAnimated, spriteOverflow;
+    int16_t curMapStack[MAX_TRAFFIC_DISTANCE + 2];   // packed x*100+y, entries 1..pointer
+};
+
+// Byte offsets of one env's block.  Every section starts 16-byte aligned so it can be moved
+// with 128-bit loads / bulk copies.
+constexpr int a16(int v) { return (v + 15) & ~15; }
+struct EnvLayout {
+    static constexpr int MAP = 0;                                   // uint16[12000]
+    static constexpr int POP = MAP + NTILES * 2;                    // uint8[3000] x5
+    static constexpr int TRAFFIC = POP + a16(N2);
+    static constexpr int POLLUTION = TRAFFIC + a16(N2);
+    static constexpr int LANDVAL = POLLUTION + a16(N2);
+    static constexpr int CRIME = LANDVAL + a16(N2);
+    static constexpr int TERRAIN = CRIME + a16(N2);                 // uint8[750]
+    static constexpr int POWER = TERRAIN + a16(N4);                 // uint32[375]
+    static constexpr int ROG = POWER + a16(POWER_WORDS * 4);        // int16[195] x6
+    static constexpr int FIREST = ROG + a16(N8 * 2);
+    static constexpr int FIREEFF = FIREST + a16(N8 * 2);
+    static constexpr int POLICEST = FIREEFF + a16(N8 * 2);
+    static constexpr int POLICEEFF = POLICEST + a16(N8 * 2);
+    static constexpr int COMRATE = POLICEEFF + a16(N8 * 2);
+    static constexpr int HIST = COMRATE + a16(N8 * 2);              // int16[6*240 + 120]
+    static constexpr int SCALARS = HIST + a16((6 * 240 + 120) * 2);
+    static constexpr int SPRITES = SCALARS + a16((int)sizeof(Scalars));
+    static constexpr int PERSISTENT_END = SPRITES + a16(MAX_SPRITES * (int)sizeof(Sprite));
+    // scratch (not part of the persistent state)
+    static constexpr int TMP1 = PERSISTENT_END;                     // uint8[3000]
+    static constexpr int TMP2 = TMP1 + a16(N2);
+    static constexpr int TMP3 = TMP2 + a16(N2);                     // uint8[750]
+    static constexpr int STMP = TMP3 + a16(N4);                     // int16[195]
+    static constexpr int PSTACK = STMP + a16(N8 * 2);               // uint16[3000]
+    static constexpr int OVERLAY = PSTACK + a16(POWER_STACK_SIZE * 2);  // tool overlay uint16[256]+mask
+    static constexpr int TOTAL = OVERLAY + 512 + 32;
+};
+
+// Thread context.  Device: the CTA that owns the env.  Host harness: one thread.
+struct Coop {
+    int tid, n;
+    int *red;       // >= 8 ints of shared scratch (device) / plain memory (host)
+    MPD void sync() const
+    {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
+    MPD bool lead() const { return tid == 0; }
+};
+
+struct Env {
+    uint16_t *map;
+    uint8_t *pop, *traffic, *pollution, *landval, *crime, *terrain;
+    uint32_t *power;
+    int16_t *rog, *fireSt, *fireEff, *policeSt, *policeEff, *comRate;
+    int16_t *resHist, *comHist, *indHist, *moneyHist, *pollutionHist, *crimeHist, *miscHist;
+    Scalars *s;
+    Sprite *spr;
+    uint8_t *tmp1, *tmp2, *tmp3;
+    int16_t *stmp;
+    uint16_t *pstack;
+    uint16_t *ovl;          // tool overlay: 256 values + 8 mask words
+    const uint16_t *anim;   // 1024-entry animation successor table
+    Coop c;
+};
+
+MPH void bind_env(Env &e, uint8_t *blk)
+{
+    typedef EnvLayout L;
+    e.map = (uint16_t *)(blk + L::MAP);
+    e.pop = blk + L::POP; e.traffic = blk + L::TRAFFIC; e.pollution = blk + L::POLLUTION;
+    e.landval = blk + L::LANDVAL; e.crime = blk + L::CRIME; e.terrain = blk + L::TERRAIN;
+    e.power = (uint32_t *)(blk + L::POWER);
+    e.rog = (int16_t *)(blk + L::ROG); e.fireSt = (int16_t *)(blk + L::FIREST);
+    e.fireEff = (int16_t *)(blk + L::FIREEFF); e.policeSt = (int16_t *)(blk + L::POLICEST);
+    e.policeEff = (int16_t *)(blk + L::POLICEEFF); e.comRate = (int16_t *)(blk + L::COMRATE);
+    int16_t *h = (int16_t *)(blk + L::HIST);
+    e.resHist = h; e.comHist = h + 240; e.indHist = h + 480; e.moneyHist = h + 720;
+    e.pollutionHist = h + 960; e.crimeHist = h + 1200; e.miscHist = h + 1440;
+    e.s = (Scalars *)(blk + L::SCALARS);
+    e.spr = (Sprite *)(blk + L::SPRITES);
+    e.tmp1 = blk + L::TMP1; e.tmp2 = blk + L::TMP2; e.tmp3 = blk + L::TMP3;
+    e.stmp = (int16_t *)(blk + L::STMP);
+    e.pstack = (uint16_t *)(blk + L::PSTACK);
+    e.ovl = (uint16_t *)(blk + L::OVERLAY);
+}
+
+// ------------------------------------------------------------------ small helpers
+template <typename T> MPD T tmin(T a, T b) { return a < b ? a : b; }
+template <typename T> MPD T tmax(T a, T b) { return a > b ? a : b; }
+template <typename T> MPD T tclamp(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+MPD int iabs(int v) { return v < 0 ? -v : v; }
+// float -> short the way x86-64 does it: truncate to int32, keep the low 16 bits
+MPD int16_t f2s(float f) { return (int16_t)(int)f; }
+MPD int16_t d2s(double f) { return (int16_t)(int)f; }
+
+MPD bool inb(int x, int y) { return x >= 0 && x < WORLD_W && y >= 0 && y < WORLD_H; }
+MPD int tix(int x, int y) { return x * WORLD_H + y; }
+
+// Map<Byte,2>/<Byte,4>/<short,8>::worldGet / worldSet (map_type.h:225-300): off-map reads 0,
+// off-map writes are dropped.
+MPD int b2get(const uint8_t *m, int wx, int wy) { return inb(wx, wy) ? m[(wx >> 1) * H2 + (wy >> 1)] : 0; }
+MPD void b2set(uint8_t *m, int wx, int wy, int v) { if (inb(wx, wy)) m[(wx >> 1) * H2 + (wy >> 1)] = (uint8_t)v; }
+MPD int s8get(const int16_t *m, int wx, int wy) { return inb(wx, wy) ? m[(wx >> 3) * H8 + (wy >> 3)] : 0; }
+MPD void s8set(int16_t *m, int wx, int wy, int v) { if (inb(wx, wy)) m[(wx >> 3) * H8 + (wy >> 3)] = (int16_t)v; }
+MPD int pwr_get(const Env &e, int x, int y)
+{
+    if (!inb(x, y)) return 0;
+    int i = tix(x, y);
+    return (e.power[i >> 5] >> (i & 31)) & 1u;
+}
+MPD void pwr_set(Env &e, int x, int y)
+{
+    if (!inb(x, y)) return;
+    int i = tix(x, y);
+    e.power[i >> 5] |= 1u << (i & 31);
+}
+// bounds-safe tile store (the reference indexes map[x][y] unchecked in a few places that are
+// in-bounds for every reachable state; an out-of-range store is dropped here)
+MPD void tset(Env &e, int x, int y, int v) { if (inb(x, y)) e.map[tix(x, y)] = (uint16_t)v; }
+MPD int tget(const Env &e, int x, int y) { return inb(x, y) ? e.map[tix(x, y)] : 0; }
+
+// ------------------------------------------------------------------ RNG (random.cpp:88-174)
+// nextRandom is an unsigned long in the reference but only bits 8..23 are observed and the LCG is
+// closed modulo 2^32, so 32 bits of state are output-equivalent.
+MPD int sim_random(Env &e)
+{
+    e.s->rng = e.s->rng * 1103515245u + 12345u;
+    return (int)((e.s->rng & 0xffff00u) >> 8);
+}
+MPD int rnd16(Env &e) { return sim_random(e) & 0xffff; }
+MPD int rnd16s(Env &e)
+{
+    int i = rnd16(e);
+    if (i > 0x7fff) i = 0x7fff - i;
+    return i;
+}
+MPD int16_t rnd(Env &e, int16_t range)
+{
+    range++;
+    int maxMultiple = 0xffff / range;
+    maxMultiple *= range;
+    int r;
+    do {
+        r = rnd16(e);
+    } while (r >= maxMultiple);
+    return (int16_t)(r % range);
+}
+MPD int16_t ernd(Env &e, int16_t limit)
+{
+    int16_t z = rnd(e, limit), x = rnd(e, limit);
+    return tmin(z, x);
+}
+MPD int random_fire(Env &e) { return (T_FIRE + (rnd16(e) & 7)) | ANIMBIT; }
+MPD int random_rubble(Env &e) { return (T_RUBBLE + (rnd16(e) & 3)) | BULLBIT; }
+
+// Position::move (position.cpp:140-214) including its two quirks: NORTH_EAST falls through to
+// EAST when blocked, SOUTH_WEST always steps then clamps and reports failure.
+MPD bool pos_move(int &x, int &y, int dir)
+{
+    switch (dir) {
+    case D_INVALID: return true;
+    case D_N: if (y > 0) { y--; return true; } break;
+    case D_NE:
+        if (x < WORLD_W - 1 && y > 0) { x++; y--; return true; }
+        // fall through
+    case D_E: if (x < WORLD_W - 1) { x++; return true; } break;
+    case D_SE: if (x < WORLD_W - 1 && y < WORLD_H - 1) { x++; y++; return true; } break;
+    case D_S: if (y < WORLD_H - 1) { y++; return true; } break;
+    case D_SW: x--; y++; break;
+    case D_W: if (x > 0) { x--; return true; } break;
+    case D_NW: if (x > 0 && y > 0) { x--; y--; return true; } break;
+    default: break;
+    }
+    if (x < 0) x = 0;
+    if (x >= WORLD_W) x = WORLD_W - 1;
+    if (y < 0) y = 0;
+    if (y >= WORLD_H) y = WORLD_H - 1;
+    return false;
+}
+MPD int rot45(int dir, int count) { return ((dir - D_N + count) & 7) + D_N; }
+
+} // namespace mp

@@ -1,0 +1,64 @@
+// host_engine.cpp -- TEST INFRASTRUCTURE ONLY (CPU CI harness; never loaded by gymcity_b200).
+//
+// Compiles the SAME engine headers the CUDA kernels are built from (gymcity_b200/csrc/mp_*.h) with
+// g++ for one host thread, behind the `mph_*` mirror of the oracle shim's ABI (oracle/ref_shim.cpp),
+// so the CPU test suite can diff the engine logic against the reference engine function by
+// function and over long rollouts without a GPU.  The product path is the CUDA library only.
+#include <stdlib.h>
+#include <string.h>
+#include "../../gymcity_b200/csrc/mp_env.h"
+#include "../../include/mp_snapshot.h"
+#include "../../gymcity_b200/csrc/mp_snapshot_io.h"
+
+using namespace mp;
+
+struct HostEnv {
+    uint8_t *blk;
+    Env e;
+    int red[8];
+    uint16_t anim[1024];
+};
+
+extern "C" {
+
+void *mph_new(void)
+{
+    HostEnv *h = new HostEnv();
+    h->blk = (uint8_t *)aligned_alloc(64, (EnvLayout::TOTAL + 63) & ~63);
+    bind_env(h->e, h->blk);
+    h->e.c.tid = 0; h->e.c.n = 1; h->e.c.red = h->red;
+    for (int i = 0; i < 1024; i++) h->anim[i] = (uint16_t)i;
+    for (int i = 0; i < kAnimPairCount; i++) h->anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
+    h->e.anim = h->anim;
+    env_construct(h->e, h->blk);
+    return h;
+}
+void mph_free(void *p) { HostEnv *h = (HostEnv *)p; free(h->blk); delete h; }
+void mph_seed(void *p, int seed) { ((HostEnv *)p)->e.s->rng = (uint32_t)seed; }
+void mph_clear_map(void *p) { clear_map(((HostEnv *)p)->e); }
+void mph_generate(void *p, int seed)
+{
+    HostEnv *h = (HostEnv *)p;
+    generate_some_city(h->e, seed, (int)h->e.s->rng);
+}
+int mph_tool(void *p, int tool, int x, int y) { return tool_down(((HostEnv *)p)->e, tool, x, y); }
+void mph_set_funds(void *p, int f) { ((HostEnv *)p)->e.s->totalFunds = f; }
+void mph_set_passes(void *p, int n) { ((HostEnv *)p)->e.s->simPasses = n; }
+void mph_sim_tick(void *p) { sim_tick(((HostEnv *)p)->e); }
+void mph_tick_engine(void *p)
+{
+    Env &e = ((HostEnv *)p)->e;
+    sim_tick(e);
+    if (e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+}
+void mph_control_sim_tick(void *p) { control_sim_tick(((HostEnv *)p)->e); }
+void mph_sim_frames(void *p, int n) { Env &e = ((HostEnv *)p)->e; for (int i = 0; i < n; i++) sim_loop(e); }
+void mph_make_monster(void *p) { make_monster(((HostEnv *)p)->e); }
+void mph_call(void *p, int fn, int a, int b) { env_call(((HostEnv *)p)->e, fn, a, b); }
+int mph_get_field(void *p, int field, void *out, int cap) { return snapshot_get_field(((HostEnv *)p)->e, field, out, cap); }
+int mph_set_field(void *p, int field, const void *in, int n) { return snapshot_set_field(((HostEnv *)p)->e, field, in, n); }
+void mph_get_scalars(void *p, mp_scalars *o) { snapshot_get_scalars(((HostEnv *)p)->e, o); }
+void mph_set_scalars(void *p, const mp_scalars *o) { snapshot_set_scalars(((HostEnv *)p)->e, o); }
+int mph_get_sprites(void *p, mp_sprite *out, int cap) { return snapshot_get_sprites(((HostEnv *)p)->e, out, cap); }
+
+} // extern "C"
