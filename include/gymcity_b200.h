@@ -68,6 +68,62 @@ int golb_step_host(golb_handle h, const int64_t *actions_host, float *reward_hos
 void *golb_ptr(golb_handle h, int which);
 int golb_step_count(golb_handle h);
 
+/* ------------------------------------------------------------------ Micropolis engine batch (mpb_*)
+ * One handle = n_envs independent Micropolis engines resident on one GPU, each in the state the
+ * reference engine has after MicropolisControl.__init__ (gym_city/envs/corecontrol.py:38-135):
+ * gameLevel 2, cityTax 10, simSpeed 3, simPasses 100, funds 2 000 000, disasters / autoBulldoze /
+ * autoBudget on.  World is 120x100 (map_type.h:73,78); coordinates are world coordinates. */
+typedef void *mpb_handle;
+
+mpb_handle mpb_create(int n_envs, int device);
+void mpb_destroy(mpb_handle h);
+const char *mpb_last_error(mpb_handle h);
+int mpb_num_envs(mpb_handle h);
+int mpb_env_stride(void);            /* bytes between consecutive env blocks in HBM            */
+int mpb_state_bytes(void);           /* bytes of persistent state per env (without scratch)     */
+void *mpb_blocks(mpb_handle h);      /* borrowed device pointer to the env blocks               */
+int mpb_sync(mpb_handle h);
+
+/* Micropolis::seedRandom per env (random.cpp:171-174); seeds_host = int32 [n_envs] HOST. */
+int mpb_seed(mpb_handle h, const int32_t *seeds_host, void *stream);
+/* engine.setFunds / setPasses / setEnableDisasters for every env (corecontrol.py:126-129,258). */
+int mpb_set_funds(mpb_handle h, int funds, void *stream);
+int mpb_set_passes(mpb_handle h, int passes, void *stream);
+int mpb_set_disasters(mpb_handle h, int enabled, void *stream);
+
+/* engine.clearMap (generate.cpp:165-174) on the envs whose mask byte is non-zero (NULL = all). */
+int mpb_clear_map(mpb_handle h, const uint8_t *mask_host, void *stream);
+/* engine.generateSomeCity(terrain_seed) (generate.cpp:92-110) followed by seedRandom(sim_seed):
+ * the reference reseeds from the wall clock inside initWillStuff, so a reproducible reset has to
+ * name both seeds.  HOST int32 [n_envs] each; mask as above. */
+int mpb_generate(mpb_handle h, const int32_t *terrain_seeds_host, const int32_t *sim_seeds_host,
+                 const uint8_t *mask_host, void *stream);
+
+/* engine.toolDown(tool, x, y) (tool.cpp:1487-1516) once per env.  tool_xy = int32 [n_envs][3]
+ * {EditingTool, x, y}; tool < 0 = no call.  results = int32 [n_envs] ToolResult (-2 no money,
+ * -1 need bulldoze, 0 failed, 1 ok; micropolis.h:387-392), may be NULL. */
+int mpb_tool(mpb_handle h, const int32_t *tool_xy_dev, int32_t *results_dev, void *stream);
+int mpb_tool_host(mpb_handle h, const int32_t *tool_xy_host, int32_t *results_host, void *stream);
+
+/* n x simLoop(true) (main.cpp:403-425). */
+int mpb_sim_frames(mpb_handle h, int n, void *stream);
+/* C++ simTick (main.cpp:435-443); animate != 0 adds tickEngine's animateTiles
+ * (micropolisgtkengine.py:542-552). */
+int mpb_sim_tick(mpb_handle h, int animate, void *stream);
+/* MicropolisControl.simTick (corecontrol.py:148-152): tickEngine() + engine.simTick(). */
+int mpb_control_sim_tick(mpb_handle h, void *stream);
+/* One engine function on every env (ids = enum Fn in csrc/mp_env.h, same as the oracle shim's
+ * FN_*): injection tests run a single scan / census / disaster function and diff its outputs. */
+int mpb_call(mpb_handle h, int fn, int a, int b, void *stream);
+
+/* State access for one env (HOST buffers; field ids = enum mp_field in mp_snapshot.h).  These
+ * stand in for the reference's getTile / getPowerGrid / get*MapBuffer getters (stubs.cpp:353-733). */
+int mpb_get_field(mpb_handle h, int env, int field, void *out_host, int cap);
+int mpb_set_field(mpb_handle h, int env, int field, const void *in_host, int nbytes);
+int mpb_get_scalars(mpb_handle h, int env, mp_scalars *out);
+int mpb_set_scalars(mpb_handle h, int env, const mp_scalars *in);
+int mpb_get_sprites(mpb_handle h, int env, mp_sprite *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif
