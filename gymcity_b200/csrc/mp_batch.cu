@@ -13,6 +13,7 @@
 
 #include "../../include/gymcity_b200.h"
 #include "mp_env.h"
+#include "mp_gym.h"
 #include "mp_snapshot_io.h"
 
 using namespace mp;
@@ -31,6 +32,18 @@ struct MpBatch {
     uint8_t *host_blk;        // pinned, one env block
     int32_t *host_i32;        // pinned staging [n_envs * 4]
     char err[256];
+    // gym layer (mpb_env_*)
+    int configured, shadow_stride;
+    GymCfg cfg;
+    uint8_t *shadow;          // [n_envs * shadow_stride]
+    float *obs;               // [n_envs, 32, W, H]
+    float *reward;            // [n_envs]
+    uint8_t *done;            // [n_envs]
+    int64_t *act_dev;         // [n_envs]
+    int64_t *h_act;           // pinned
+    float *h_reward;          // pinned
+    uint8_t *h_done;          // pinned
+    uint8_t *host_shadow;     // pinned, one env
 };
 
 __device__ __forceinline__ void bind_device_env(Env &e, uint8_t *blocks, const uint16_t *anim, int *red)
@@ -116,6 +129,81 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
     }
 }
 
+__device__ __forceinline__ void bind_device_gym(Gym &gy, uint8_t *shadow, int stride, const GymCfg *cfg)
+{
+    bind_gym(gy, shadow + (size_t)blockIdx.x * stride, cfg);
+}
+
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+                     const int32_t *terrain_seeds, const int32_t *sim_seeds, const uint8_t *mask, int terrain)
+{
+    __shared__ int red[8];
+    if (mask && !mask[blockIdx.x]) return;
+    Env e;
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[blockIdx.x] : 0, terrain ? sim_seeds[blockIdx.x] : 0);
+}
+
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_reset_finish(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+                      const uint8_t *mask, float *obs, float *reward, uint8_t *done)
+{
+    __shared__ int red[8];
+    if (mask && !mask[blockIdx.x]) return;
+    Env e;
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
+    gym_reset_finish(e, gy, obs + blockIdx.x * on, reward + blockIdx.x, done + blockIdx.x);
+}
+
+// TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
+__global__ void __launch_bounds__(32)
+k_mp_env_action(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+                const int64_t *actions, int static_build, int full, int32_t *ok)
+{
+    __shared__ int red[8];
+    Env e;
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    if (threadIdx.x == 0) {
+        int r = gym_apply_action(e, gy, actions[blockIdx.x], static_build != 0, full != 0);
+        if (ok) ok[blockIdx.x] = r;
+    }
+}
+
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_step(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+              const int64_t *actions, int static_build, float *obs, float *reward, uint8_t *done)
+{
+    __shared__ int red[8];
+    Env e;
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
+    gym_step(e, gy, actions[blockIdx.x], static_build != 0, obs + blockIdx.x * on, reward + blockIdx.x,
+             done + blockIdx.x);
+}
+
+__global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Gym gy;
+    bind_gym(gy, const_cast<uint8_t *>(shadow) + (size_t)i * stride, &cfg);
+    const GymScalars &g = *gy.g;
+    double *o = out + (size_t)i * MPB_ENV_NUM_COUNTERS;
+    o[0] = g.num_plants; o[1] = g.num_roads; o[2] = g.n_struct_tiles; o[3] = g.total_traffic;
+    o[4] = g.num_step; o[5] = g.tilemap_error; o[6] = g.reward; o[7] = g.done; o[8] = g.curr_funds;
+    for (int k = 0; k < GYM_NUM_METRICS; k++) o[9 + k] = g.metrics[k];
+}
+
 int fail(MpBatch *b, const char *what, cudaError_t e)
 {
     snprintf(b->err, sizeof(b->err), "%s: %s", what, cudaGetErrorString(e));
@@ -172,8 +260,13 @@ void mpb_destroy(mpb_handle h)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
+    cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
     if (b->host_blk) cudaFreeHost(b->host_blk);
     if (b->host_i32) cudaFreeHost(b->host_i32);
+    if (b->h_act) cudaFreeHost(b->h_act);
+    if (b->h_reward) cudaFreeHost(b->h_reward);
+    if (b->h_done) cudaFreeHost(b->h_done);
+    if (b->host_shadow) cudaFreeHost(b->host_shadow);
     free(b);
 }
 
@@ -389,6 +482,208 @@ int mpb_get_sprites(mpb_handle h, int env, mp_sprite *out, int cap)
     Env e;
     if (fetch_env(b, env, e)) return -1;
     return snapshot_get_sprites(e, out, cap);
+}
+
+
+// ------------------------------------------------------------------ gym layer (mpb_env_*)
+int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools, const int8_t *tool_zone,
+                      const int8_t *tool_engine, int max_step, const double *trg, const double *weight)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || W < 1 || H < 1 || W > 120 || H > 100 || num_tools < 1 || num_tools > GYM_MAX_TOOLS
+        || !tool_zone || !tool_engine || !trg || !weight) {
+        if (b) snprintf(b->err, sizeof(b->err), "mpb_env_configure: bad arguments");
+        return -1;
+    }
+    cudaSetDevice(b->device);
+    cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
+    b->shadow = NULL; b->obs = NULL; b->reward = NULL; b->done = NULL; b->act_dev = NULL;
+    GymCfg &c = b->cfg;
+    memset(&c, 0, sizeof(c));
+    c.W = W; c.H = H; c.xs = xs; c.ys = ys; c.num_tools = num_tools; c.max_step = max_step;
+    c.init_funds = 2000000;
+    for (int i = 0; i < num_tools; i++) { c.tool_zone[i] = tool_zone[i]; c.tool_engine[i] = tool_engine[i]; }
+    for (int i = 0; i < GYM_NUM_METRICS; i++) { c.trg[i] = trg[i]; c.weight[i] = weight[i]; }
+    b->shadow_stride = (gym_shadow_bytes(W, H) + 127) & ~127;
+    size_t on = (size_t)GYM_OBS_CHANNELS * W * H;
+    CK(cudaMalloc(&b->shadow, (size_t)b->n_envs * b->shadow_stride));
+    CK(cudaMalloc(&b->obs, (size_t)b->n_envs * on * 4));
+    CK(cudaMalloc(&b->reward, (size_t)b->n_envs * 4));
+    CK(cudaMalloc(&b->done, b->n_envs));
+    CK(cudaMalloc(&b->act_dev, (size_t)b->n_envs * 8));
+    if (!b->h_act) {
+        CK(cudaMallocHost(&b->h_act, (size_t)b->n_envs * 8));
+        CK(cudaMallocHost(&b->h_reward, (size_t)b->n_envs * 4));
+        CK(cudaMallocHost(&b->h_done, b->n_envs));
+    }
+    if (b->host_shadow) cudaFreeHost(b->host_shadow);
+    CK(cudaMallocHost(&b->host_shadow, b->shadow_stride));
+    CK(cudaMemset(b->shadow, 0, (size_t)b->n_envs * b->shadow_stride));
+    CK(cudaMemset(b->obs, 0, (size_t)b->n_envs * on * 4));
+    CK(cudaMemset(b->reward, 0, (size_t)b->n_envs * 4));
+    CK(cudaMemset(b->done, 0, b->n_envs));
+    b->configured = 1;
+    // MicropolisControl.__init__ builds an empty TileMap (tilemap.py:185 setEmpty)
+    k_mp_env_reset_begin<<<b->n_envs, MP_THREADS>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg,
+                                                   NULL, NULL, NULL, 0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+#define NEED_CFG() do { if (!b || !b->configured) { if (b) snprintf(b->err, sizeof(b->err), "mpb_env_configure not called"); return -1; } cudaSetDevice(b->device); } while (0)
+
+int mpb_env_set_targets(mpb_handle h, const double *trg, const double *weight)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    for (int i = 0; i < GYM_NUM_METRICS; i++) {
+        if (trg) b->cfg.trg[i] = trg[i];
+        if (weight) b->cfg.weight[i] = weight[i];
+    }
+    return 0;
+}
+
+int mpb_env_set_max_step(mpb_handle h, int max_step)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    b->cfg.max_step = max_step;
+    return 0;
+}
+
+int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_host,
+                        const int32_t *sim_seeds_host, const uint8_t *mask_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (terrain && (!terrain_seeds_host || !sim_seeds_host)) return -1;
+    if (upload_mask(b, mask_host, st)) return -1;
+    if (terrain) {
+        memcpy(b->host_i32, terrain_seeds_host, (size_t)b->n_envs * 4);
+        memcpy(b->host_i32 + b->n_envs, sim_seeds_host, (size_t)b->n_envs * 4);
+        CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
+    }
+    k_mp_env_reset_begin<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride,
+        b->cfg, b->i32_a, b->i32_b, mask_host ? b->mask : NULL, terrain);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (upload_mask(b, mask_host, st)) return -1;
+    k_mp_env_reset_finish<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride,
+        b->cfg, mask_host ? b->mask : NULL, b->obs, b->reward, b->done);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
+                   int32_t *ok_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!actions_host) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
+    CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
+    k_mp_env_action<<<b->n_envs, 32, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg,
+                                             b->act_dev, static_build, full_tools, b->i32_b);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ok_host) memcpy(ok_host, b->host_i32, (size_t)b->n_envs * 4);
+    return 0;
+}
+
+int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!actions_dev) return -1;
+    k_mp_env_step<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->shadow,
+        b->shadow_stride, b->cfg, actions_dev, static_build, b->obs, b->reward, b->done);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int mpb_env_step_host(mpb_handle h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                      void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!actions_host || !reward_host || !done_host) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
+    CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
+    if (mpb_env_step(h, b->act_dev, 0, stream)) return -1;
+    CK(cudaMemcpyAsync(b->h_reward, b->reward, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b->h_done, b->done, b->n_envs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(reward_host, b->h_reward, (size_t)b->n_envs * 4);
+    memcpy(done_host, b->h_done, b->n_envs);
+    return 0;
+}
+
+int mpb_env_get_counters(mpb_handle h, double *out_host)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!out_host) return -1;
+    double *dev = NULL;
+    size_t bytes = (size_t)b->n_envs * MPB_ENV_NUM_COUNTERS * sizeof(double);
+    CK(cudaMalloc(&dev, bytes));
+    k_mp_env_counters<<<(b->n_envs + 127) / 128, 128>>>(b->shadow, b->shadow_stride, b->cfg, b->n_envs, dev);
+    cudaError_t e = cudaMemcpy(out_host, dev, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(b, "mpb_env_get_counters", e);
+    return 0;
+}
+
+void *mpb_env_ptr(mpb_handle h, int which)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !b->configured) return NULL;
+    switch (which) {
+    case MPB_ENV_OBS: return b->obs;
+    case MPB_ENV_REWARD: return b->reward;
+    case MPB_ENV_DONE: return b->done;
+    default: return NULL;
+    }
+}
+
+int mpb_env_get_shadow(mpb_handle h, int env, uint8_t *zone_out, uint8_t *static_out, int16_t *center_out,
+                       double *counters_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (env < 0 || env >= b->n_envs) return -1;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(b->host_shadow, b->shadow + (size_t)env * b->shadow_stride, b->shadow_stride,
+                  cudaMemcpyDeviceToHost));
+    Gym gy;
+    bind_gym(gy, b->host_shadow, &b->cfg);
+    int n = b->cfg.W * b->cfg.H;
+    if (zone_out) memcpy(zone_out, gy.zone, n);
+    if (static_out) memcpy(static_out, gy.stat, n);
+    if (center_out) memcpy(center_out, gy.center, (size_t)n * 2);
+    if (counters_out) {
+        const GymScalars &g = *gy.g;
+        double v[MPB_ENV_NUM_COUNTERS] = { (double)g.num_plants, (double)g.num_roads, (double)g.n_struct_tiles,
+            (double)g.total_traffic, (double)g.num_step, (double)g.tilemap_error, g.reward, (double)g.done,
+            (double)g.curr_funds, g.metrics[0], g.metrics[1], g.metrics[2], g.metrics[3], g.metrics[4],
+            g.metrics[5] };
+        memcpy(counters_out, v, sizeof(v));
+    }
+    return 0;
 }
 
 } // extern "C"

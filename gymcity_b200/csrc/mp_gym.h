@@ -1,0 +1,358 @@
+// mp_gym.h -- the gym layer of one env on the device: the TileMap shadow map with its
+// clear-before-build action preprocessing (gym_city/envs/tilemap.py), the MicropolisControl
+// window / tool tables (gym_city/envs/corecontrol.py) and MicropolisEnv's step / observation /
+// reward (gym_city/envs/env.py).  Shared by mp_batch.cu and the CPU harness.
+//
+// The shadow map stores one zone id per window cell; the 22 one-hot feature planes the reference
+// keeps (zoneMap[:-1]) are a pure function of that id (every write goes through
+// zoneMap[:, x, y] = zoneCols[zone], tilemap.py:499-500), so they are expanded only when the
+// observation is written.  Road-network labels (tilemap.py:201-330) are bookkeeping that never
+// reaches the observation, reward or info and are not kept.
+#pragma once
+#include "mp_env.h"
+#include "mp_gym_tables.h"
+
+namespace mp {
+
+enum : int { Z_POLICE = 5, Z_FIRE = 6, Z_AIRPORT = 7, Z_NUCLEAR = 8, Z_COAL = 9, Z_ROAD = 10, Z_RUBBLE = 14,
+             Z_WATER = 16, Z_LAND = 17, Z_FOREST = 18 };
+constexpr uint32_t F_PLANT = (1u << Z_NUCLEAR) | (1u << Z_COAL);
+constexpr uint32_t F_ROAD = 1u << Z_ROAD;
+constexpr uint32_t F_NATURAL = (1u << Z_LAND) | (1u << Z_WATER) | (1u << Z_RUBBLE) | (1u << Z_FOREST);
+constexpr int GYM_MAX_TOOLS = 20, GYM_NUM_METRICS = 6, GYM_OBS_CHANNELS = 32;
+
+struct GymCfg {
+    int32_t W, H, xs, ys, num_tools, max_step;
+    int8_t tool_zone[GYM_MAX_TOOLS];     // agent tool -> TileMap zone id; -1 = 'Nil', -2 = 'Clear'
+    int8_t tool_engine[GYM_MAX_TOOLS];   // agent tool -> engine EditingTool
+    double trg[GYM_NUM_METRICS], weight[GYM_NUM_METRICS];
+    int32_t init_funds;
+};
+
+struct GymScalars {
+    int32_t num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error;
+    double metrics[GYM_NUM_METRICS], last_metrics[GYM_NUM_METRICS];
+    double reward;
+    int32_t done, curr_funds;
+};
+
+struct Gym {
+    uint8_t *zone, *stat;       // [W*H] index x*H + y
+    int16_t *center;            // [W*H] cx*128 + cy, -1 = None
+    GymScalars *g;
+    const GymCfg *cfg;
+};
+
+MPH int gym_shadow_bytes(int W, int H) { return a16(W * H) * 2 + a16(W * H * 2) + a16((int)sizeof(GymScalars)); }
+MPH void bind_gym(Gym &gy, uint8_t *blk, const GymCfg *cfg)
+{
+    int n = cfg->W * cfg->H;
+    gy.zone = blk;
+    gy.stat = blk + a16(n);
+    gy.center = (int16_t *)(blk + 2 * a16(n));
+    gy.g = (GymScalars *)(blk + 2 * a16(n) + a16(n * 2));
+    gy.cfg = cfg;
+}
+
+#define CFG (*gy.cfg)
+#define G (*gy.g)
+
+MPD int gym_cell(const Gym &gy, int x, int y) { return x * CFG.H + y; }
+// MicropolisControl.getTile (corecontrol.py:302-305): engine.getTile(x + MAP_XS, y + MAP_YS) & 1023
+MPD int gym_get_tile(const Env &e, const Gym &gy, int x, int y) { return tget(e, x + CFG.xs, y + CFG.ys) & 1023; }
+MPD int gym_zone_of_tile(Gym &gy, int tile)
+{
+    int z = kTileZone[tile];
+    if (z == 255) {          // zoneSize[...] raises KeyError in the reference (Flood/Radioactive/Trash/Lightning)
+        G.tilemap_error = 1;
+        z = Z_RUBBLE;
+    }
+    return z;
+}
+
+// [LEAD] tilemap.py:467-541 updateTile.  zone < 0: re-read from the map.  static_build: -1 None, 0, 1.
+MPN void gym_update_tile(Env &e, Gym &gy, int x, int y, int zone, int center, int static_build)
+{
+    const int c = gym_cell(gy, x, y);
+    const uint32_t was = kZoneFeatures[gy.zone[c]];
+    if (zone < 0) {
+        zone = gym_zone_of_tile(gy, gym_get_tile(e, gy, x, y));
+        center = (kZoneSize[zone] != 1) ? gy.center[c] : (x * 128 + y);
+        if (static_build == 0) gy.stat[c] = 0;
+    } else {
+        gy.stat[c] = (static_build == 1 && zone != Z_LAND && zone != Z_RUBBLE && zone != Z_WATER) ? 1 : 0;
+    }
+    gy.zone[c] = (uint8_t)zone;
+    gy.center[c] = (int16_t)center;
+    const uint32_t is = kZoneFeatures[zone];
+    if ((was & F_NATURAL) && !(is & F_NATURAL)) G.n_struct_tiles++;
+    if (!(was & F_NATURAL) && (is & F_NATURAL)) G.n_struct_tiles--;
+    if ((was & F_ROAD) && !(is & F_ROAD)) G.num_roads--;
+    else if (!(was & F_ROAD) && (is & F_ROAD)) G.num_roads++;
+    if ((was & F_PLANT) && !(is & F_PLANT)) G.num_plants--;
+    else if (!(was & F_PLANT) && (is & F_PLANT)) G.num_plants++;
+}
+
+// [LEAD] tilemap.py:410-447 clearTile: Water, Land, Clear on the recorded centre, then re-read the
+// old zone's footprint.
+MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
+{
+    const int c = gym_cell(gy, x, y);
+    const int old_zone = gy.zone[c];
+    int cnt = gy.center[c];
+    if (cnt < 0) cnt = x * 128 + y;
+    if (gy.stat[c] == 1 && !static_build) return;
+    int xc = cnt >> 7, yc = cnt & 127;
+    tool_down(e, TOOL_WATER, xc + CFG.xs, yc + CFG.ys);
+    tool_down(e, TOOL_LAND, xc + CFG.xs, yc + CFG.ys);
+    tool_down(e, TOOL_BULLDOZER, xc + CFG.xs, yc + CFG.ys);
+    const int size = kZoneSize[old_zone];
+    if (size == 1) {
+        if (xc < CFG.W && yc < CFG.H) gym_update_tile(e, gy, xc, yc, -1, -1, 0);
+        return;
+    }
+    if (size == 6) { xc -= 1; yc -= 1; }
+    int x0 = tmax(0, xc - 1), y0 = tmax(0, yc - 1);
+    int x1 = tmin(xc - 1 + size, (int)CFG.W), y1 = tmin(yc - 1 + size, (int)CFG.H);
+    for (int i = x0; i < x1; i++)
+        for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, -1, -1, 0);
+}
+
+// [LEAD] tilemap.py:391-408 clearPatch
+MPD int gym_clear_patch(Env &e, Gym &gy, int x, int y, int size, bool static_build)
+{
+    if (size == 1 && !(!static_build && gy.stat[gym_cell(gy, x, y)] == 1)) {
+        gym_clear_tile(e, gy, x, y, static_build);
+        return 1;
+    }
+    int x0 = tmax(x - 1, 0), x1 = tmin(x - 1 + size, (int)CFG.W);
+    int y0 = tmax(y - 1, 0), y1 = tmin(y - 1 + size, (int)CFG.H);
+    for (int i = x0; i < x1; i++)
+        for (int j = y0; j < y1; j++) {
+            if (gy.stat[gym_cell(gy, i, j)] == 1) return 0;
+            gym_clear_tile(e, gy, i, j, static_build);
+        }
+    return 1;
+}
+
+// [LEAD] tilemap.py:450-479 addZone: the zone recorded is the one the MAP now shows at (x, y)
+MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
+{
+    int zone = gym_zone_of_tile(gy, gym_get_tile(e, gy, x, y));
+    int size = kZoneSize[zone];
+    int center = (size == 6) ? (x + 1) * 128 + (y + 1) : x * 128 + y;
+    if (size == 1) {
+        gym_update_tile(e, gy, x, y, zone, center, static_build ? 1 : 0);
+        return;
+    }
+    int x0 = tmax(0, x - 1), y0 = tmax(0, y - 1);
+    int x1 = tmin(x - 1 + size, (int)CFG.W), y1 = tmin(y - 1 + size, (int)CFG.H);
+    for (int i = x0; i < x1; i++)
+        for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
+}
+
+// The full agent tool list (corecontrol.py:85-106) as (TileMap zone id, engine EditingTool);
+// zone -1 = 'Nil', -2 = 'Clear'.  Set-up builds (powerPuzzle, env.py:253-262) use tool NAMES that
+// need not be in the env's own tool list, so they are addressed through this table.
+#if defined(__CUDACC__)
+#define MP_GYM_TABLE static __device__ const
+#else
+#define MP_GYM_TABLE static const
+#endif
+MP_GYM_TABLE int8_t kFullToolZone[GYM_MAX_TOOLS] = { 0, 1, 2, 6, 5, -2, 13, 11, 10, 4, 12, 3, 9, 8, 7, 15, 16, 17, 18, -1 };
+MP_GYM_TABLE int8_t kFullToolEngine[GYM_MAX_TOOLS] = { 0, 1, 2, 3, 4, 7, 6, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 0 };
+
+// [LEAD] tilemap.py:345-377 addZoneBot for the tool recorded as `zone` and applied as `engine_tool`.
+MPN bool gym_add_zone_bot(Env &e, Gym &gy, int x, int y, int zone, int engine_tool, bool static_build)
+{
+    if (zone == -1) return true;                              // 'Nil'
+    const int c = gym_cell(gy, x, y);
+    const int old_zone = gy.zone[c];
+    if (zone >= 0 && kZoneCompat[zone] != 0
+        && (((kZoneCompat[zone] >> old_zone) & 1u) || ((kCompositeOf[old_zone] >> zone) & 1u)) && zone != Z_WATER) {
+        if (gy.stat[c] == 1) static_build = true;
+    }
+    if (!static_build && gy.stat[c] == 1) return false;
+    if (zone == -2) zone = Z_LAND;                            // 'Clear' is recorded as 'Land'
+    int result;
+    if (kZoneCompat[zone] != 0 && ((kZoneCompat[zone] >> old_zone) & 1u)) result = 1;   // clearForZone :382-389
+    else result = gym_clear_patch(e, gy, x, y, kZoneSize[zone], static_build);
+    if (result == 1) {
+        result = tool_down(e, engine_tool, x + CFG.xs, y + CFG.ys);
+        if (result == 1) gym_add_zone(e, gy, x, y, static_build);
+    }
+    return result == 1;
+}
+
+// [LEAD] one decoded action through addZoneBot; full != 0 decodes against the full agent tool list
+MPD int gym_apply_action(Env &e, Gym &gy, long long a, bool static_build, bool full)
+{
+    if (a < 0) return 0;
+    const int n = CFG.W * CFG.H;
+    int z = (int)(a / n), rem = (int)(a - (long long)z * n);
+    int x = rem / CFG.H, y = rem - x * CFG.H;
+    if (full) {
+        if (z >= GYM_MAX_TOOLS) return 0;
+        return gym_add_zone_bot(e, gy, x, y, kFullToolZone[z], kFullToolEngine[z], static_build);
+    }
+    if (z >= CFG.num_tools) return 0;
+    return gym_add_zone_bot(e, gy, x, y, CFG.tool_zone[z], CFG.tool_engine[z], static_build);
+}
+
+// [ALL] TileMap.setEmpty (tilemap.py:327-343)
+MPD void gym_set_empty(Env &e, Gym &gy)
+{
+    const int n = CFG.W * CFG.H;
+    for (int i = e.c.tid; i < n; i += e.c.n) { gy.zone[i] = Z_LAND; gy.stat[i] = 0; gy.center[i] = -1; }
+    if (e.c.lead()) { G.num_roads = 0; G.num_plants = 0; }
+    e.c.sync();
+}
+
+// [ALL] MicropolisControl.updateMap (corecontrol.py:193-203): every window cell re-read with
+// zone given, centre (i, j), static_build None
+MPD void gym_update_map(Env &e, Gym &gy)
+{
+    if (e.c.lead())
+        for (int i = 0; i < CFG.W; i++)
+            for (int j = 0; j < CFG.H; j++)
+                gym_update_tile(e, gy, i, j, gym_zone_of_tile(gy, gym_get_tile(e, gy, i, j)), i * 128 + j, -1);
+    e.c.sync();
+}
+
+// [LEAD] env.py:426-440 get_city_metrics
+MPD void gym_city_metrics(const Env &e, Gym &gy, double *m)
+{
+    m[0] = e.s->resPop; m[1] = e.s->comPop; m[2] = e.s->indPop;
+    m[3] = G.total_traffic; m[4] = G.num_plants; m[5] = e.s->cityYes;
+}
+
+MPD int dsign(double v) { return (v > 0) - (v < 0); }
+MPD double dabs(double v) { return v < 0 ? -v : v; }
+
+// [LEAD] env.py:345-387 getReward
+MPD double gym_reward(const Gym &gy)
+{
+    double reward = 0;
+    for (int k = 0; k < GYM_NUM_METRICS; k++) {
+        double last = G.last_metrics[k], trg_change = CFG.trg[k] - last, change = G.metrics[k] - last, r;
+        if (dsign(change) != dsign(trg_change)) r = -dabs(change);
+        else if (dabs(change) < dabs(trg_change)) r = dabs(change);
+        else r = dabs(trg_change) - dabs(trg_change - change);
+        reward += r * CFG.weight[k];
+    }
+    return reward;
+}
+
+// [ALL] env.py:301-343 getState/observation + corecontrol.py:215-239 getDensityMaps: writes the
+// (32, W, H) float32 observation and refreshes total_traffic.  Channel order: SURVEY appendix A.3.
+MPD void gym_observe(Env &e, Gym &gy, float *obs)
+{
+    const int W = CFG.W, H = CFG.H, n = W * H;
+    if (e.c.lead()) e.c.red[3] = 0;
+    e.c.sync();
+    const Scalars &s = *e.s;
+    float sc[6];
+    sc[0] = (float)s.resPop; sc[1] = (float)s.comPop; sc[2] = (float)s.indPop;
+    sc[3] = (float)s.resValve / (float)RES_VALVE_RANGE;        // utilities.cpp:416-424 getDemands
+    sc[4] = (float)s.comValve / (float)COM_VALVE_RANGE;
+    sc[5] = (float)s.indValve / (float)IND_VALVE_RANGE;
+    int tsum = 0;
+    for (int idx = e.c.tid; idx < GYM_OBS_CHANNELS * n; idx += e.c.n) {
+        int p = idx / n, cell = idx - p * n, i = cell / H, j = cell - i * H;
+        float v;
+        if (p < kNumFeatures) {
+            v = (float)((kZoneFeatures[gy.zone[cell]] >> p) & 1u);
+        } else if (p == 22) {
+            v = (float)pwr_get(e, j + CFG.xs, i + CFG.ys);
+        } else if (p == 23 || p == 24) {
+            // cluster (x = j' + MAP_XS/2, y = i' + MAP_YS/2) fills rows 2i'..2i'+1, cols 2j'..2j'+1
+            int i2 = i >> 1, j2 = j >> 1;
+            v = 0.0f;
+            if (i2 < W / 2 && j2 < H / 2) {
+                int cx = j2 + CFG.xs / 2, cy = i2 + CFG.ys / 2;
+                if (cx >= 0 && cx < W2 && cy >= 0 && cy < H2) {
+                    const uint8_t *m = (p == 23) ? e.pop : e.traffic;
+                    int d = m[cx * H2 + cy];
+                    v = (float)d;
+                    if (p == 24 && !(i & 1) && !(j & 1)) tsum += d;
+                }
+            }
+        } else if (p < 31) {
+            v = sc[p - 25];
+        } else {
+            v = (float)gy.stat[cell];
+        }
+        obs[idx] = v;
+    }
+    coop_add(e, 3, tsum);
+    e.c.sync();
+    if (e.c.lead()) G.total_traffic = e.c.red[3];
+    e.c.sync();
+}
+
+// [ALL] MicropolisEnv.step (env.py:448-462) + postact (:464-540) for one env.
+// action < 0: no agent action (Nil).  Observation, reward and done are written for this env.
+MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *obs, float *reward_out,
+                  uint8_t *done_out)
+{
+    if (e.c.lead()) {
+        if (action >= 0) {
+            int n = CFG.W * CFG.H;
+            int z = (int)(action / n), rem = (int)(action - (long long)z * n);
+            int x = rem / CFG.H, y = rem - x * CFG.H;
+            if (z < CFG.num_tools)                                                    // takeAction
+                gym_add_zone_bot(e, gy, x, y, CFG.tool_zone[z], CFG.tool_engine[z], static_build);
+        }
+        e.s->totalFunds = CFG.init_funds;                       // micro.setFunds(init_funds)
+    }
+    e.c.sync();
+    control_sim_tick(e);                                        // micro.simTick()
+    gym_observe(e, gy, obs);                                    // getState()
+    if (e.c.lead()) {
+        for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
+        gym_city_metrics(e, gy, G.metrics);
+        G.reward = gym_reward(gy);
+        G.curr_funds = (int32_t)e.s->totalFunds;
+        G.done = (e.s->totalFunds < 0 || G.num_step >= CFG.max_step) ? 1 : 0;
+        G.num_step++;
+        *reward_out = (float)G.reward;
+        *done_out = (uint8_t)G.done;
+    }
+    e.c.sync();
+}
+
+// [ALL] MicropolisEnv.reset, first half (env.py:264-274): clearMap (+ newMap) and num_step = 0.
+// terrain: 0 = empty_start (clearMap only), 1 = generateSomeCity(terrain_seed) + seedRandom(sim_seed).
+MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim_seed)
+{
+    gym_set_empty(e, gy);
+    clear_map(e);
+    gym_update_map(e, gy);
+    if (terrain) {
+        generate_some_city(e, terrain_seed, sim_seed);
+        gym_update_map(e, gy);
+    }
+    if (e.c.lead()) G.num_step = 0;
+    e.c.sync();
+}
+
+// [ALL] MicropolisEnv.reset, second half (env.py:279-292): simTick, metrics, funds, reward, state
+MPD void gym_reset_finish(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
+{
+    control_sim_tick(e);
+    if (e.c.lead()) {
+        gym_city_metrics(e, gy, G.metrics);                     // uses the previous total_traffic
+        for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
+        e.s->totalFunds = CFG.init_funds;
+        G.reward = gym_reward(gy);
+        G.done = 0;
+        *reward_out = (float)G.reward;
+        *done_out = 0;
+    }
+    e.c.sync();
+    gym_observe(e, gy, obs);
+}
+
+#undef CFG
+#undef G
+} // namespace mp

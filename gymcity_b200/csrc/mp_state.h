@@ -84,6 +84,9 @@ struct Scalars {
 
 // Byte offsets of one env's block.  Every section starts 16-byte aligned so it can be moved
 // with 128-bit loads / bulk copies.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr int a16(int v) { return (v + 15) & ~15; }
 struct EnvLayout {
     static constexpr int MAP = 0;                                   // uint16[12000]

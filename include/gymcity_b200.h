@@ -124,6 +124,56 @@ int mpb_get_scalars(mpb_handle h, int env, mp_scalars *out);
 int mpb_set_scalars(mpb_handle h, int env, const mp_scalars *in);
 int mpb_get_sprites(mpb_handle h, int env, mp_sprite *out, int cap);
 
+/* ------------------------------------------------------------------ gym layer on the batch (mpb_env_*)
+ * MicropolisEnv / MicropolisControl / TileMap for every env of the handle, on the device:
+ * gym_city/envs/env.py:448-540 (step/postact), :264-292 (reset), :301-343 (observation),
+ * :345-387 (reward); corecontrol.py:215-239 (density maps), :296-338 (tools, window offset);
+ * tilemap.py:345-541 (addZoneBot, clear-before-build, shadow map).
+ *
+ * mpb_env_configure: W x H build window at world offset (xs, ys) (reference: 16, 8,
+ * corecontrol.py:58-59); num_tools agent tools with tool_zone[i] = TileMap zone id the tool is
+ * recorded as (-1 'Nil', -2 'Clear') and tool_engine[i] = engine EditingTool; episode length
+ * max_step; reward targets / weights in the order res_pop, com_pop, ind_pop, traffic, num_plants,
+ * mayor_rating (env.py:31-56).  Leaves every env with an empty shadow map. */
+enum mpb_env_buffer {
+    MPB_ENV_OBS = 0,     /* float32 [n_envs, 32, W, H], channel order of env.py:315-332            */
+    MPB_ENV_REWARD,      /* float32 [n_envs]                                                     */
+    MPB_ENV_DONE         /* uint8 [n_envs]                                                       */
+};
+#define MPB_ENV_NUM_COUNTERS 15
+int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools, const int8_t *tool_zone,
+                      const int8_t *tool_engine, int max_step, const double *trg, const double *weight);
+int mpb_env_set_targets(mpb_handle h, const double *trg, const double *weight);   /* env.py:419-424 */
+int mpb_env_set_max_step(mpb_handle h, int max_step);
+/* reset, first half (env.py:264-274): TileMap.setEmpty + engine.clearMap + updateMap and, when
+ * terrain != 0, engine.generateSomeCity(terrain_seed) + seedRandom(sim_seed) + updateMap.  Set-up
+ * builds (powerPuzzle / randomStaticStart) go through mpb_env_action before the second half. */
+int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_host,
+                        const int32_t *sim_seeds_host, const uint8_t *mask_host, void *stream);
+/* reset, second half (env.py:279-292): simTick, metrics, setFunds, reward, observation. */
+int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
+/* MicropolisControl.takeAction without a tick: actions_host = int64 [n_envs] flat action index
+ * i = z*W*H + x*H + y (env.py:209-219), < 0 = none; full_tools != 0 decodes z against the full
+ * 20-tool agent list (corecontrol.py:85-106) whatever the env's own list is (powerPuzzle builds
+ * Residential / NuclearPowerPlant in a Wire-only env); ok_host = int32 [n_envs] tool success. */
+int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
+                   int32_t *ok_host, void *stream);
+/* MicropolisEnv.step for every env: one fused launch (action, setFunds, 2 x simPasses simFrames +
+ * animateTiles, observation, reward, done).  actions_dev = int64 [n_envs] DEVICE pointer. */
+int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, void *stream);
+/* Same end to end with HOST buffers: H2D actions, step, D2H reward + done, sync. */
+int mpb_env_step_host(mpb_handle h, const int64_t *actions_host, float *reward_host, uint8_t *done_host,
+                      void *stream);
+void *mpb_env_ptr(mpb_handle h, int which);
+/* Counters of every env in one call: double [n_envs][MPB_ENV_NUM_COUNTERS] HOST, fields as in
+ * mpb_env_get_shadow. */
+int mpb_env_get_counters(mpb_handle h, double *out_host);
+/* Shadow map of one env (HOST buffers, any may be NULL): zone id / static flag per cell [W*H]
+ * (index x*H + y), recorded centre cx*128+cy or -1, and counters {num_plants, num_roads,
+ * n_struct_tiles, total_traffic, num_step, tilemap_error, reward, done, funds, metrics[6]}. */
+int mpb_env_get_shadow(mpb_handle h, int env, uint8_t *zone_out, uint8_t *static_out, int16_t *center_out,
+                       double *counters_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,3 +28,65 @@ def build_host_engine():
 class HostEngine(EngineBase):
     def __init__(self):
         super().__init__(C.CDLL(build_host_engine()), "mph_")
+
+
+import numpy as np  # noqa: E402
+
+from oracle.ref_gym import AGENT_TOOLS, ENGINE_TOOLS  # noqa: E402
+
+ZONES = ['Residential', 'Commercial', 'Industrial', 'Seaport', 'Stadium', 'PoliceDept', 'FireDept', 'Airport',
+         'NuclearPowerPlant', 'CoalPowerPlant', 'Road', 'Rail', 'Park', 'Wire', 'Rubble', 'Net', 'Water', 'Land',
+         'Forest', 'Church', 'Hospital', 'Fire', 'RoadWire', 'RailWire', 'Bridge', 'RoadRail', 'WaterWire', 'Radar',
+         'RailBridge']
+TRG = [500, 50, 50, 2000, 14, 100]
+WEIGHT = [1, 1, 1, 1, 0, 0]
+
+
+def tool_tables(tools):
+    tz = [(-1 if t == 'Nil' else (-2 if t == 'Clear' else ZONES.index(t))) for t in tools]
+    te = [(0 if t == 'Nil' else ENGINE_TOOLS.index(t)) for t in tools]
+    return np.array(tz, np.int8), np.array(te, np.int8)
+
+
+class HostGym(HostEngine):
+    """One env of the gym layer on the CPU harness (mph_env_*)."""
+
+    def configure(self, W, H, max_step, power_puzzle=False, xs=16, ys=8):
+        L = self._lib
+        self.W, self.H = W, H
+        tools = ['Wire'] if power_puzzle else AGENT_TOOLS
+        tz, te = tool_tables(tools)
+        trg, wt = np.array(TRG, np.float64), np.array(WEIGHT, np.float64)
+        L.mph_env_configure.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.mph_env_configure(self._h, W, H, xs, ys, len(tools), tz.ctypes.data, te.ctypes.data, max_step,
+                            trg.ctypes.data, wt.ctypes.data)
+        L.mph_env_reset_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.mph_env_reset_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mph_env_action.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int]
+        L.mph_env_step.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mph_env_get_shadow.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        self.obs = np.zeros((32, W, H), np.float32)
+        self.rew = np.zeros(1, np.float32)
+        self.done = np.zeros(1, np.uint8)
+
+    def reset_begin(self, terrain, tseed=0, sseed=0):
+        self._lib.mph_env_reset_begin(self._h, int(terrain), int(tseed), int(sseed))
+
+    def reset_finish(self):
+        self._lib.mph_env_reset_finish(self._h, self.obs.ctypes.data, self.rew.ctypes.data, self.done.ctypes.data)
+        return self.obs.copy()
+
+    def action(self, a, static_build=False, full=False):
+        return self._lib.mph_env_action(self._h, int(a), int(static_build), int(full))
+
+    def step(self, a, static_build=False):
+        self._lib.mph_env_step(self._h, int(a), int(static_build), self.obs.ctypes.data, self.rew.ctypes.data,
+                               self.done.ctypes.data)
+        return self.obs.copy(), float(self.rew[0]), bool(self.done[0])
+
+    def shadow(self):
+        n = self.W * self.H
+        z, s, c, k = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int16), np.zeros(15)
+        self._lib.mph_env_get_shadow(self._h, z.ctypes.data, s.ctypes.data, c.ctypes.data, k.ctypes.data)
+        return z.reshape(self.W, self.H), s.reshape(self.W, self.H), c.reshape(self.W, self.H), k

@@ -1,0 +1,113 @@
+"""CPU: the gym layer.  (1) oracle/ref_gym.RefTileMap against the reference's own TileMap class
+imported by path (only where /root/reference exists); (2) the device gym-layer code (CPU harness)
+against the oracle gym layer over the reference engine: observation, reward, done, shadow map."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from oracle.ref_engine import RefEngine, diff_snapshots, ref_available
+from oracle.ref_gym import RefControl, RefEnv, RefTileMap
+from tests.host_engine import HostGym
+
+pytestmark = pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+REF_TILEMAP = "/root/reference/gym_city/envs/tilemap.py"
+
+
+def _reference_tilemap_cls():
+    gym = types.ModuleType("gym")
+    gym.spaces = types.ModuleType("gym.spaces")
+    sys.modules.setdefault("gym", gym)
+    sys.modules.setdefault("gym.spaces", gym.spaces)
+    spec = importlib.util.spec_from_file_location("ref_tilemap", REF_TILEMAP)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+
+    class Adapter(m.TileMap):
+        def __init__(self, micro, X, Y):
+            micro.env = types.SimpleNamespace(num_step=0)
+            super().__init__(micro, X, Y, paint=False)
+    return Adapter, m
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TILEMAP), reason="reference tree not present")
+@pytest.mark.parametrize("seed,size", [(0, 16), (1, 12), (2, 24)])
+def test_ref_tilemap_restatement_matches_reference_class(seed, size):
+    Adapter, m = _reference_tilemap_cls()
+    for i in range(1024):
+        from oracle.ref_gym import zone_from_int
+        assert zone_from_int(i) == m.zoneFromInt(i)
+    engines = [RefEngine(), RefEngine()]
+    ctl = [RefControl(engines[0], size, size, tilemap_cls=RefTileMap),
+           RefControl(engines[1], size, size, tilemap_cls=Adapter)]
+    for e in engines:
+        e.clearMap()
+        e.seed(seed)
+        sc = e.scalars()
+        sc.enableDisasters = 0          # floods make the reference class raise KeyError
+        e.set_scalars(sc)
+    for c in ctl:
+        c.clearMap()
+    rng = np.random.default_rng(seed)
+    for t in range(400):
+        a = [int(rng.integers(0, 20)), int(rng.integers(0, size)), int(rng.integers(0, size))]
+        sb = bool(rng.random() < 0.25)
+        for c in ctl:
+            c.takeAction(a, sb)
+            c.engine.setFunds(2000000)
+            if t % 3 == 0:
+                c.simTick()
+        a_, b_ = ctl[0].map, ctl[1].map
+        assert np.array_equal(a_.zoneMap, b_.zoneMap), t
+        assert np.array_equal(a_.static_builds, b_.static_builds), t
+        assert (a_.num_plants, a_.num_roads, a_.n_struct_tiles) == (b_.num_plants, b_.num_roads, b_.n_struct_tiles)
+        ca = [[a_.centers[x][y] for y in range(size)] for x in range(size)]
+        cb = [[b_.centers[x][y] for y in range(size)] for x in range(size)]
+        assert ca == cb, t
+    assert not diff_snapshots(engines[0].snapshot(), engines[1].snapshot())
+
+
+def _rollout(seed, steps, size, terrain, static_p, xs=16, ys=8):
+    r = RefEngine()
+    env = RefEnv(r, size, max_step=steps - 3, empty_start=not terrain, xs=xs, ys=ys)
+    W, H = env.MAP_X, env.MAP_Y
+    h = HostGym()
+    h.configure(W, H, steps - 3, xs=xs, ys=ys)
+    rng = np.random.default_rng(seed)
+    env.reset_begin(1000 + seed, seed)
+    h.reset_begin(terrain, 1000 + seed, seed)
+    if not terrain:
+        r.seed(seed)
+        h.seed(seed)
+    o0, o1 = env.reset_finish(), h.reset_finish()
+    assert np.array_equal(o0.astype(np.float32), o1)
+    done_seen = False
+    for t in range(steps):
+        a = int(rng.integers(0, env.num_tools * W * H)) if rng.random() > 0.05 else -1
+        sb = bool(rng.random() < static_p)
+        o0, r0, d0, _ = env.step(a, sb)
+        o1, r1, d1 = h.step(a, sb)
+        assert np.array_equal(o0.astype(np.float32), o1), (t, np.argwhere(o0.astype(np.float32) != o1)[:4])
+        assert r0 == r1 and d0 == d1, (t, r0, r1, d0, d1)
+        done_seen |= d0
+        z, s, c, k = h.shadow()
+        assert np.array_equal(z, env.micro.map.zoneMap[-1]) and np.array_equal(s, env.micro.map.static_builds[0])
+        assert int(k[0]) == env.micro.map.num_plants and int(k[1]) == env.micro.map.num_roads
+        assert int(k[3]) == env.micro.total_traffic and int(k[5]) == env.micro.map.tilemap_error
+    assert not diff_snapshots(r.snapshot(), h.snapshot())
+    assert done_seen                      # max_step reached: done = num_step >= max_step (env.py:517-520)
+    return env
+
+
+@pytest.mark.parametrize("seed,size,terrain,static_p", [(0, 16, True, 0.0), (1, 16, False, 0.3),
+                                                       (2, 32, True, 0.1), (3, (20, 12), False, 0.2)])
+def test_device_gym_layer_matches_oracle(seed, size, terrain, static_p):
+    _rollout(seed, 120, size, terrain, static_p)
+
+
+def test_full_world_window_at_origin():
+    """BASELINE config 4 addressing: 120x100 window at offset (0,0)."""
+    _rollout(5, 12, (120, 100), True, 0.0, xs=0, ys=0)

@@ -1,0 +1,137 @@
+"""GPU parity for the gym layer: gymcity_b200.MicropolisEnv (mpb_env_* kernels) against the oracle
+gym layer over the reference engine -- observation (32,W,H), reward, done, shadow map, engine state."""
+import numpy as np
+import pytest
+
+from oracle.ref_engine import RefEngine, diff_snapshots, ref_available
+from oracle.ref_gym import AGENT_TOOLS, RefEnv
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")]
+
+
+def _batch(n, size, terrain, max_step, seeds, power_puzzle=False, xs=16, ys=8):
+    from gymcity_b200.micropolis_env import MicropolisEnv
+    env = MicropolisEnv(num_envs=n)
+    env.setMapSize(size, max_step=max_step, empty_start=not terrain, power_puzzle=power_puzzle, MAP_XS=xs, MAP_YS=ys)
+    refs = [RefEnv(RefEngine(), size, max_step=max_step, empty_start=not terrain, power_puzzle=power_puzzle,
+                   xs=xs, ys=ys) for _ in range(n)]
+    m = env.micro
+    if terrain:
+        m.newMap(seeds + 1000, seeds)
+    else:
+        m.clearMap()
+        m.engine.seed(seeds)
+    for i, r in enumerate(refs):
+        r.reset_begin(int(seeds[i]) + 1000, int(seeds[i]))
+        if not terrain:
+            r.micro.engine.seed(int(seeds[i]))
+    return env, refs
+
+
+def _finish(env, refs):
+    m = env.micro
+    m._ck(m._L.mpb_env_reset_finish(m._h, None, m.engine._stream()))
+    obs = m.obs.cpu().numpy()
+    for i, r in enumerate(refs):
+        assert np.array_equal(r.reset_finish().astype(np.float32), obs[i]), i
+
+
+def _compare_step(env, refs, acts, sb, t):
+    import torch
+    obs, rew, done, _ = env.step(torch.from_numpy(acts), static_build=sb)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy().reshape(-1), done.cpu().numpy()
+    for i, r in enumerate(refs):
+        o, rr, d, _ = r.step(int(acts[i]), sb)
+        assert np.array_equal(o.astype(np.float32), obs[i]), (t, i, np.argwhere(o.astype(np.float32) != obs[i])[:4])
+        assert rr == rew[i] and d == bool(done[i]), (t, i, rr, rew[i], d, done[i])
+
+
+@pytest.mark.parametrize("size,terrain,n,steps", [(16, True, 6, 80), (16, False, 4, 60), (32, True, 3, 40),
+                                                   ((20, 12), False, 3, 40)])
+def test_step_matches_oracle(size, terrain, n, steps):
+    seeds = np.arange(n) + 5
+    env, refs = _batch(n, size, terrain, steps - 5, seeds)
+    _finish(env, refs)
+    W, H = refs[0].MAP_X, refs[0].MAP_Y
+    rng = np.random.default_rng(1)
+    for t in range(steps):
+        acts = rng.integers(0, 20 * W * H, n)
+        acts[rng.random(n) < 0.05] = -1
+        _compare_step(env, refs, acts.astype(np.int64), bool(rng.random() < 0.2), t)
+    ctr = env.micro.counters()
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+        z, s, c, k = env.micro.map._shadow(i)
+        assert np.array_equal(z, r.micro.map.zoneMap[-1]) and np.array_equal(s, r.micro.map.static_builds[0])
+        assert int(ctr[i, 0]) == r.micro.map.num_plants and int(ctr[i, 3]) == r.micro.total_traffic
+    env.close()
+
+
+def test_power_puzzle_variant():
+    """BASELINE config 3 shape: 32x32, Wire-only action space, 5 static Residential + 1 static Nuclear."""
+    n, size = 4, 32
+    seeds = np.arange(n) + 20
+    env, refs = _batch(n, size, True, 50, seeds, power_puzzle=True)
+    rng = np.random.default_rng(3)
+    res, nuke = AGENT_TOOLS.index('Residential'), AGENT_TOOLS.index('NuclearPowerPlant')
+    for k in range(9):
+        xs, ys = rng.integers(0, size, n), rng.integers(0, size, n)
+        tool = res if k < 5 else nuke
+        env.micro.apply_actions(env.micro._flat(tool, xs, ys), True, full_tools=True)
+        for i, r in enumerate(refs):
+            r.micro.map.addZoneBot(int(xs[i]), int(ys[i]), AGENT_TOOLS[tool], static_build=True)
+    _finish(env, refs)
+    assert env.action_space.n == size * size
+    for t in range(30):
+        acts = rng.integers(0, size * size, n).astype(np.int64)
+        _compare_step(env, refs, acts, False, t)
+    env.close()
+
+
+def test_full_world_window():
+    """BASELINE config 4 addressing: 120x100 window at offset (0, 0)."""
+    n = 2
+    seeds = np.arange(n) + 30
+    env, refs = _batch(n, (120, 100), True, 100, seeds, xs=0, ys=0)
+    _finish(env, refs)
+    rng = np.random.default_rng(4)
+    for t in range(6):
+        acts = rng.integers(0, 20 * 12000, n).astype(np.int64)
+        _compare_step(env, refs, acts, False, t)
+    env.close()
+
+
+def test_vec_env_auto_reset_and_sharding_invariance():
+    """done -> auto reset (subproc_vec_env.py:16-21); per-env seeds derive from the GLOBAL env index so
+    a shard [4:8) of an 8-env batch equals envs 4..7 of the full batch."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    full = MicropolisVecEnv(8, 16, seed=3, max_step=4, empty_start=False)
+    shard = MicropolisVecEnv(4, 16, seed=3, max_step=4, empty_start=False, env_offset=4)
+    o_full, o_shard = full.reset(), shard.reset()
+    assert torch.equal(o_full[4:], o_shard)
+    rng = np.random.default_rng(0)
+    for t in range(11):
+        a = rng.integers(0, 20 * 256, 8)
+        of, rf, df, _ = full.step(torch.from_numpy(a))
+        os_, rs, ds, _ = shard.step(torch.from_numpy(a[4:]))
+        assert torch.equal(of[4:], os_) and torch.equal(rf[4:], rs) and torch.equal(df[4:], ds)
+        assert bool(df.all().item()) == (t % 5 == 4), (t, df)
+    full.close()
+    shard.close()
+
+
+def test_step_host_end_to_end():
+    from gymcity_b200.micropolis_env import MicropolisEnv
+    n = 64
+    env = MicropolisEnv(num_envs=n)
+    env.seed(1)
+    env.setMapSize(16, max_step=100, empty_start=False)
+    env.reset()
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 20 * 256, n).astype(np.int64)
+    rew, done = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    env.step_host(a, rew, done)
+    assert np.array_equal(rew, env.micro.reward.cpu().numpy().reshape(-1))
+    assert not done.any()
+    env.close()
