@@ -20,7 +20,9 @@ using namespace mp;
 
 namespace {
 
-constexpr int MP_THREADS = 128;
+// One warp per city; MP_EPC cities (warps) per CTA so that more than 32 cities fit on an SM.
+constexpr int MP_EPC = 2;
+constexpr int MP_THREADS = 32 * MP_EPC;
 constexpr int ENV_STRIDE = (EnvLayout::TOTAL + 127) & ~127;
 
 struct MpBatch {
@@ -46,54 +48,62 @@ struct MpBatch {
     uint8_t *host_shadow;     // pinned, one env
 };
 
+__device__ __forceinline__ int device_env_index() { return blockIdx.x * MP_EPC + (threadIdx.x >> 5); }
+
 __device__ __forceinline__ void bind_device_env(Env &e, uint8_t *blocks, const uint16_t *anim, int *red)
 {
-    bind_env(e, blocks + (size_t)blockIdx.x * ENV_STRIDE);
+    bind_env(e, blocks + (size_t)device_env_index() * ENV_STRIDE);
     e.anim = anim;
-    e.c.tid = threadIdx.x;
-    e.c.n = blockDim.x;
-    e.c.red = red;
+    e.c.tid = threadIdx.x & 31;
+    e.c.n = 32;
+    e.c.red = red + (threadIdx.x >> 5) * 8;
 }
 
-__global__ void __launch_bounds__(MP_THREADS) k_mp_construct(uint8_t *blocks, const uint16_t *anim)
+#define MP_ENV_GUARD() const int env = device_env_index(); if (env >= n_envs) return; const int lane = threadIdx.x & 31; (void)lane
+
+__global__ void __launch_bounds__(MP_THREADS) k_mp_construct(uint8_t *blocks, const uint16_t *anim, int n_envs)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
-    env_construct(e, blocks + (size_t)blockIdx.x * ENV_STRIDE);
+    env_construct(e, blocks + (size_t)device_env_index() * ENV_STRIDE);
 }
 
 // mode 0: clearMap; mode 1: generateSomeCity(terrain_seed) then seedRandom(sim_seed)
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_reset(uint8_t *blocks, const uint16_t *anim, const int32_t *terrain_seeds,
+k_mp_reset(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *terrain_seeds,
            const int32_t *sim_seeds, const uint8_t *mask, int mode)
 {
-    __shared__ int red[8];
-    if (mask && !mask[blockIdx.x]) return;
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) return;
     Env e;
     bind_device_env(e, blocks, anim, red);
     if (mode == 0) clear_map(e);
-    else generate_some_city(e, terrain_seeds[blockIdx.x], sim_seeds[blockIdx.x]);
+    else generate_some_city(e, terrain_seeds[env], sim_seeds[env]);
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_tool(uint8_t *blocks, const uint16_t *anim, const int32_t *txy, int32_t *results)
+k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy, int32_t *results)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
-    if (threadIdx.x == 0) {
-        const int32_t *a = txy + (size_t)blockIdx.x * 3;
+    if (lane == 0) {
+        const int32_t *a = txy + (size_t)env * 3;
         int r = (a[0] < 0) ? (int)TR_FAILED : tool_down(e, a[0], a[1], a[2]);
-        if (results) results[blockIdx.x] = r;
+        if (results) results[env] = r;
     }
 }
 
 // mode 0: n x simLoop; mode 1: MicropolisControl.simTick (2 x simPasses frames + animateTiles)
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_tick(uint8_t *blocks, const uint16_t *anim, int mode, int n)
+k_mp_tick(uint8_t *blocks, const uint16_t *anim, int n_envs, int mode, int n)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
     if (mode == 0) {
@@ -107,9 +117,10 @@ k_mp_tick(uint8_t *blocks, const uint16_t *anim, int mode, int n)
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_call(uint8_t *blocks, const uint16_t *anim, int fn, int a, int b)
+k_mp_call(uint8_t *blocks, const uint16_t *anim, int n_envs, int fn, int a, int b)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
     env_call(e, fn, a, b);
@@ -131,64 +142,67 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
 
 __device__ __forceinline__ void bind_device_gym(Gym &gy, uint8_t *shadow, int stride, const GymCfg *cfg)
 {
-    bind_gym(gy, shadow + (size_t)blockIdx.x * stride, cfg);
+    bind_gym(gy, shadow + (size_t)device_env_index() * stride, cfg);
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
                      const int32_t *terrain_seeds, const int32_t *sim_seeds, const uint8_t *mask, int terrain)
 {
-    __shared__ int red[8];
-    if (mask && !mask[blockIdx.x]) return;
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) return;
     Env e;
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
-    gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[blockIdx.x] : 0, terrain ? sim_seeds[blockIdx.x] : 0);
+    gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[env] : 0, terrain ? sim_seeds[env] : 0);
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_env_reset_finish(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+k_mp_env_reset_finish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
                       const uint8_t *mask, float *obs, float *reward, uint8_t *done)
 {
-    __shared__ int red[8];
-    if (mask && !mask[blockIdx.x]) return;
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) return;
     Env e;
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
-    gym_reset_finish(e, gy, obs + blockIdx.x * on, reward + blockIdx.x, done + blockIdx.x);
+    gym_reset_finish(e, gy, obs + env * on, reward + env, done + env);
 }
 
 // TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
-__global__ void __launch_bounds__(32)
-k_mp_env_action(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
                 const int64_t *actions, int static_build, int full, int32_t *ok)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
-    if (threadIdx.x == 0) {
-        int r = gym_apply_action(e, gy, actions[blockIdx.x], static_build != 0, full != 0);
-        if (ok) ok[blockIdx.x] = r;
+    if (lane == 0) {
+        int r = gym_apply_action(e, gy, actions[env], static_build != 0, full != 0);
+        if (ok) ok[env] = r;
     }
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_env_step(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg,
+k_mp_env_step(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
               const int64_t *actions, int static_build, float *obs, float *reward, uint8_t *done)
 {
-    __shared__ int red[8];
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
-    gym_step(e, gy, actions[blockIdx.x], static_build != 0, obs + blockIdx.x * on, reward + blockIdx.x,
-             done + blockIdx.x);
+    gym_step(e, gy, actions[env], static_build != 0, obs + env * on, reward + env, done + env);
 }
 
 __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
@@ -203,6 +217,8 @@ __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg,
     o[4] = g.num_step; o[5] = g.tilemap_error; o[6] = g.reward; o[7] = g.done; o[8] = g.curr_funds;
     for (int k = 0; k < GYM_NUM_METRICS; k++) o[9 + k] = g.metrics[k];
 }
+
+#define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
 
 int fail(MpBatch *b, const char *what, cudaError_t e)
 {
@@ -249,7 +265,7 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMallocHost(&b->host_i32, (size_t)n_envs * 16) == cudaSuccess;
     if (!ok) { mpb_destroy(b); return NULL; }
     cudaMemcpy(b->anim, anim, sizeof(anim), cudaMemcpyHostToDevice);
-    k_mp_construct<<<n_envs, MP_THREADS>>>(b->blocks, b->anim);
+    k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS>>>(b->blocks, b->anim, n_envs);
     if (cudaDeviceSynchronize() != cudaSuccess) { mpb_destroy(b); return NULL; }
     return b;
 }
@@ -332,7 +348,7 @@ int mpb_clear_map(mpb_handle h, const uint8_t *mask_host, void *stream)
     cudaSetDevice(b->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
-    k_mp_reset<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, NULL, NULL, mask_host ? b->mask : NULL, 0);
+    k_mp_reset<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, NULL, NULL, mask_host ? b->mask : NULL, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -350,7 +366,7 @@ int mpb_generate(mpb_handle h, const int32_t *terrain_seeds_host, const int32_t 
     memcpy(b->host_i32 + b->n_envs, sim_seeds_host, (size_t)b->n_envs * 4);
     CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
-    k_mp_reset<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->i32_a, b->i32_b,
+    k_mp_reset<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->i32_a, b->i32_b,
                                                 mask_host ? b->mask : NULL, 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -362,7 +378,7 @@ int mpb_tool(mpb_handle h, const int32_t *tool_xy_dev, int32_t *results_dev, voi
     MpBatch *b = (MpBatch *)h;
     if (!b || !tool_xy_dev) return -1;
     cudaSetDevice(b->device);
-    k_mp_tool<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, tool_xy_dev, results_dev);
+    k_mp_tool<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, tool_xy_dev, results_dev);
     CK(cudaGetLastError());
     return 0;
 }
@@ -387,7 +403,7 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b || n < 0) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, 0, n);
+    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, n);
     CK(cudaGetLastError());
     return 0;
 }
@@ -397,7 +413,7 @@ int mpb_control_sim_tick(mpb_handle h, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, 1, 0);
+    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 1, 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -407,7 +423,7 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, animate ? 3 : 2, 0);
+    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, animate ? 3 : 2, 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -417,7 +433,7 @@ int mpb_call(mpb_handle h, int fn, int a, int bb, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_call<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, fn, a, bb);
+    k_mp_call<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, fn, a, bb);
     CK(cudaGetLastError());
     return 0;
 }
@@ -524,7 +540,7 @@ int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools,
     CK(cudaMemset(b->done, 0, b->n_envs));
     b->configured = 1;
     // MicropolisControl.__init__ builds an empty TileMap (tilemap.py:185 setEmpty)
-    k_mp_env_reset_begin<<<b->n_envs, MP_THREADS>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                    NULL, NULL, NULL, 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -566,7 +582,7 @@ int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_
         CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
     }
-    k_mp_env_reset_begin<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride,
+    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
         b->cfg, b->i32_a, b->i32_b, mask_host ? b->mask : NULL, terrain);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -579,7 +595,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     NEED_CFG();
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
-    k_mp_env_reset_finish<<<b->n_envs, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride,
+    k_mp_env_reset_finish<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
         b->cfg, mask_host ? b->mask : NULL, b->obs, b->reward, b->done);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -595,7 +611,7 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
     cudaStream_t st = (cudaStream_t)stream;
     memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
     CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
-    k_mp_env_action<<<b->n_envs, 32, 0, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_action<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                              b->act_dev, static_build, full_tools, b->i32_b);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
@@ -609,7 +625,7 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!actions_dev) return -1;
-    k_mp_env_step<<<b->n_envs, MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->shadow,
+    k_mp_env_step<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, b->shadow,
         b->shadow_stride, b->cfg, actions_dev, static_build, b->obs, b->reward, b->done);
     CK(cudaGetLastError());
     return 0;

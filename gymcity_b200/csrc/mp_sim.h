@@ -923,7 +923,7 @@ MPD void map_scan(Env &e, int x1, int x2)
 {
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
 #if defined(__CUDA_ARCH__)
-    if (e.c.tid < 32) {
+    {
         const int lane = e.c.tid;
         for (int base = i0; base < i1; base += 32) {
             int idx = base + lane;
@@ -1240,7 +1240,7 @@ MPD void coop_add(Env &e, int slot, int v)
 {
 #if defined(__CUDA_ARCH__)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((e.c.tid & 31) == 0 && v) atomicAdd(&e.c.red[slot], v);
+    if (e.c.tid == 0) e.c.red[slot] += v;
 #else
     e.c.red[slot] += v;
 #endif

@@ -117,14 +117,16 @@ struct EnvLayout {
     static constexpr int TOTAL = OVERLAY + 512 + 32;
 };
 
-// Thread context.  Device: the CTA that owns the env.  Host harness: one thread.
+// Thread context.  Device: the WARP that owns the env (tid = lane, n = 32; a barrier is a
+// __syncwarp, so the warps of a CTA -- one env each -- never wait on one another).  Host harness:
+// one thread.
 struct Coop {
     int tid, n;
-    int *red;       // >= 8 ints of shared scratch (device) / plain memory (host)
+    int *red;       // >= 8 ints of shared scratch per env (device) / plain memory (host)
     MPD void sync() const
     {
 #if defined(__CUDA_ARCH__)
-        __syncthreads();
+        __syncwarp();
 #endif
     }
     MPD bool lead() const { return tid == 0; }
