@@ -34,6 +34,8 @@ struct MpBatch {
     uint8_t *host_blk;        // pinned, one env block
     int32_t *host_i32;        // pinned staging [n_envs * 4]
     char err[256];
+    int passes;               // host copy of simPasses (corecontrol.py:129 sets 100)
+    int frames_per_launch;    // simFrames per k_mp_frames launch (phase lockstep across the batch)
     // gym layer (mpb_env_*)
     int configured, shadow_stride;
     GymCfg cfg;
@@ -98,21 +100,28 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
     }
 }
 
-// mode 0: n x simLoop; mode 1: MicropolisControl.simTick (2 x simPasses frames + animateTiles)
+// `count` simFrames (simLoop(true), main.cpp:403-425) for every env, frames [first, first + count) of
+// a simTick of simPasses frames.  All envs of the batch run the same frames in the same launch, so
+// every warp on the GPU is in (nearly) the same simulation phase and executes the same code: the
+// engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
+// per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
+// animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_tick(uint8_t *blocks, const uint16_t *anim, int n_envs, int mode, int n)
+k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
+            int respect_passes)
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
-    if (mode == 0) {
-        for (int i = 0; i < n; i++) sim_loop(e);
-    } else if (mode == 1) {
-        control_sim_tick(e);
+    if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+    if (respect_passes) {
+        if (!e.s->simSpeed) return;
+        int last = first + count;
+        if (last > e.s->simPasses) last = e.s->simPasses;
+        for (int i = first; i < last; i++) sim_loop(e);
     } else {
-        sim_tick(e);
-        if (mode == 3 && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+        for (int i = 0; i < count; i++) sim_loop(e);
     }
 }
 
@@ -159,21 +168,6 @@ k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t 
     gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[env] : 0, terrain ? sim_seeds[env] : 0);
 }
 
-__global__ void __launch_bounds__(MP_THREADS)
-k_mp_env_reset_finish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-                      const uint8_t *mask, float *obs, float *reward, uint8_t *done)
-{
-    __shared__ int red[8 * MP_EPC];
-    MP_ENV_GUARD();
-    if (mask && !mask[env]) return;
-    Env e;
-    bind_device_env(e, blocks, anim, red);
-    Gym gy;
-    bind_device_gym(gy, shadow, stride, &cfg);
-    const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
-    gym_reset_finish(e, gy, obs + env * on, reward + env, done + env);
-}
-
 // TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
@@ -191,9 +185,10 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
     }
 }
 
+// MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
-k_mp_env_step(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-              const int64_t *actions, int static_build, float *obs, float *reward, uint8_t *done)
+k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
+             const int64_t *actions, int static_build)
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
@@ -201,8 +196,24 @@ k_mp_env_step(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
+    if (lane == 0) gym_step_pre(e, gy, actions[env], static_build != 0);
+}
+
+// MicropolisEnv.step, part 3 (env.py:468-540): observation, metrics, reward, done
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
+              float *obs, float *reward, uint8_t *done, int is_reset, const uint8_t *mask)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) return;
+    Env e;
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
     const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
-    gym_step(e, gy, actions[env], static_build != 0, obs + env * on, reward + env, done + env);
+    if (is_reset) gym_reset_post(e, gy, obs + env * on, reward + env, done + env);
+    else gym_step_post(e, gy, obs + env * on, reward + env, done + env);
 }
 
 __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
@@ -219,6 +230,27 @@ __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg,
 }
 
 #define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
+
+// C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
+int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before)
+{
+    const int F = b->frames_per_launch, P = b->passes;
+    if (P <= 0) {
+        if (animate_before) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1);
+        return 0;
+    }
+    for (int f = 0; f < P; f += F)
+        k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
+                                                      animate_before && f == 0, 1);
+    return 0;
+}
+// MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
+int launch_control_sim_tick(MpBatch *b, cudaStream_t st)
+{
+    launch_sim_tick(b, st, 0);
+    launch_sim_tick(b, st, 1);
+    return 0;
+}
 
 int fail(MpBatch *b, const char *what, cudaError_t e)
 {
@@ -253,6 +285,9 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaSetDevice(device);
     MpBatch *b = (MpBatch *)calloc(1, sizeof(MpBatch));
     b->n_envs = n_envs; b->device = device;
+    b->passes = 100;
+    b->frames_per_launch = 4;
+    if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
@@ -289,6 +324,13 @@ void mpb_destroy(mpb_handle h)
 const char *mpb_last_error(mpb_handle h) { return h ? ((MpBatch *)h)->err : "null handle"; }
 int mpb_num_envs(mpb_handle h) { return h ? ((MpBatch *)h)->n_envs : -1; }
 int mpb_env_stride(void) { return ENV_STRIDE; }
+int mpb_launches_per_tick(mpb_handle h)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b) return -1;
+    int per = b->passes > 0 ? (b->passes + b->frames_per_launch - 1) / b->frames_per_launch : 0;
+    return 2 * per + (b->passes > 0 ? 0 : 1);
+}
 int mpb_state_bytes(void) { return EnvLayout::PERSISTENT_END; }
 void *mpb_blocks(mpb_handle h) { return h ? ((MpBatch *)h)->blocks : NULL; }
 
@@ -324,6 +366,7 @@ int mpb_set_passes(mpb_handle h, int passes, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
+    b->passes = passes;
     return set_all(b, 2, passes, (cudaStream_t)stream);
 }
 int mpb_set_disasters(mpb_handle h, int enabled, void *stream)
@@ -403,7 +446,10 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b || n < 0) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, n);
+    const int F = b->frames_per_launch;
+    for (int f = 0; f < n; f += F)
+        k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0,
+                                                                        (n - f < F) ? n - f : F, 0, 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -413,7 +459,7 @@ int mpb_control_sim_tick(mpb_handle h, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 1, 0);
+    launch_control_sim_tick(b, (cudaStream_t)stream);
     CK(cudaGetLastError());
     return 0;
 }
@@ -423,7 +469,8 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_tick<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, animate ? 3 : 2, 0);
+    launch_sim_tick(b, (cudaStream_t)stream, 0);
+    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1);
     CK(cudaGetLastError());
     return 0;
 }
@@ -595,8 +642,9 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     NEED_CFG();
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
-    k_mp_env_reset_finish<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
-        b->cfg, mask_host ? b->mask : NULL, b->obs, b->reward, b->done);
+    launch_control_sim_tick(b, st);
+    k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -625,8 +673,12 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!actions_dev) return -1;
-    k_mp_env_step<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, b->shadow,
-        b->shadow_stride, b->cfg, actions_dev, static_build, b->obs, b->reward, b->done);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_mp_env_pre<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                   actions_dev, static_build);
+    launch_control_sim_tick(b, st);
+    k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                    b->obs, b->reward, b->done, 0, NULL);
     CK(cudaGetLastError());
     return 0;
 }

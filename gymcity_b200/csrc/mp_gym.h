@@ -290,23 +290,17 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
     e.c.sync();
 }
 
-// [ALL] MicropolisEnv.step (env.py:448-462) + postact (:464-540) for one env.
-// action < 0: no agent action (Nil).  Observation, reward and done are written for this env.
-MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *obs, float *reward_out,
-                  uint8_t *done_out)
+// [LEAD] MicropolisEnv.step part 1 (env.py:448-466): takeAction + micro.setFunds(init_funds).
+// action < 0: no agent action.
+MPD void gym_step_pre(Env &e, Gym &gy, long long action, bool static_build)
 {
-    if (e.c.lead()) {
-        if (action >= 0) {
-            int n = CFG.W * CFG.H;
-            int z = (int)(action / n), rem = (int)(action - (long long)z * n);
-            int x = rem / CFG.H, y = rem - x * CFG.H;
-            if (z < CFG.num_tools)                                                    // takeAction
-                gym_add_zone_bot(e, gy, x, y, CFG.tool_zone[z], CFG.tool_engine[z], static_build);
-        }
-        e.s->totalFunds = CFG.init_funds;                       // micro.setFunds(init_funds)
-    }
-    e.c.sync();
-    control_sim_tick(e);                                        // micro.simTick()
+    gym_apply_action(e, gy, action, static_build, false);       // takeAction
+    e.s->totalFunds = CFG.init_funds;                           // micro.setFunds(init_funds)
+}
+
+// [ALL] MicropolisEnv.postact after micro.simTick() (env.py:468-540): state, metrics, reward, done
+MPD void gym_step_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
+{
     gym_observe(e, gy, obs);                                    // getState()
     if (e.c.lead()) {
         for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
@@ -319,6 +313,16 @@ MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *o
         *done_out = (uint8_t)G.done;
     }
     e.c.sync();
+}
+
+// [ALL] the whole step for one env (CPU harness; the CUDA path splits it into launches)
+MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *obs, float *reward_out,
+                  uint8_t *done_out)
+{
+    if (e.c.lead()) gym_step_pre(e, gy, action, static_build);
+    e.c.sync();
+    control_sim_tick(e);                                        // micro.simTick()
+    gym_step_post(e, gy, obs, reward_out, done_out);
 }
 
 // [ALL] MicropolisEnv.reset, first half (env.py:264-274): clearMap (+ newMap) and num_step = 0.
@@ -336,10 +340,9 @@ MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim
     e.c.sync();
 }
 
-// [ALL] MicropolisEnv.reset, second half (env.py:279-292): simTick, metrics, funds, reward, state
-MPD void gym_reset_finish(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
+// [ALL] MicropolisEnv.reset after micro.simTick() (env.py:280-292): metrics, funds, reward, state
+MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
 {
-    control_sim_tick(e);
     if (e.c.lead()) {
         gym_city_metrics(e, gy, G.metrics);                     // uses the previous total_traffic
         for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
@@ -351,6 +354,13 @@ MPD void gym_reset_finish(Env &e, Gym &gy, float *obs, float *reward_out, uint8_
     }
     e.c.sync();
     gym_observe(e, gy, obs);
+}
+
+// [ALL] MicropolisEnv.reset, second half (env.py:279-292) for one env (CPU harness)
+MPD void gym_reset_finish(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
+{
+    control_sim_tick(e);
+    gym_reset_post(e, gy, obs, reward_out, done_out);
 }
 
 #undef CFG

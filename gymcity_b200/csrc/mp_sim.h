@@ -1632,7 +1632,7 @@ MPD void simulate(Env &e)
 }
 
 // [ALL] simulate.cpp:98-118 simFrame + main.cpp:403-425 simLoop(true) (heatSteps = 0)
-MPD void sim_loop(Env &e)
+MPN void sim_loop(Env &e)
 {
     bool run = false;
     if (S.simSpeed != 0) {
