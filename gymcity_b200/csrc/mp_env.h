@@ -25,7 +25,7 @@ MPD void env_construct(Env &e, uint8_t *blk)
         S.simPasses = 100; S.enableDisasters = 1; S.doAnimation = 1;
         S.roadPercent = 1.0f; S.policePercent = 1.0f; S.firePercent = 1.0f; S.externalMarket = 4.0f;
         S.spriteHead = -1;
-        for (int i = 0; i < SPR_COUNT; i++) S.globalSprites[i] = -1;
+        MP_NOUNROLL for (int i = 0; i < SPR_COUNT; i++) S.globalSprites[i] = -1;
     }
     e.c.sync();
 }
@@ -35,7 +35,7 @@ MPD void env_construct(Env &e, uint8_t *blk)
 MPD void init_will_stuff(Env &e)
 {
     if (e.c.lead()) {
-        for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) e.spr[i].frame = 0;   // destroyAllSprites
+        MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) e.spr[i].frame = 0;   // destroyAllSprites
         S.roadEffect = MAX_ROAD_EFFECT; S.policeEffect = MAX_POLICE_EFFECT; S.fireEffect = MAX_FIRE_EFFECT;
         S.cityScore = 500; S.cityPop = -1;
         S.roadFund = 0; S.policeFund = 0; S.fireFund = 0;
@@ -82,7 +82,7 @@ MPD void sim_tick(Env &e)
 {
     if (S.simSpeed) {
         const int n = S.simPasses;
-        for (int i = 0; i < n; i++) sim_loop(e);
+        MP_NOUNROLL for (int i = 0; i < n; i++) sim_loop(e);
     }
 }
 
@@ -151,9 +151,9 @@ MPD void env_call(Env &e, int fn, int a, int b)
     case FN_GENERATE_TRAIN: if (lead) generate_train(e, a, b); break;
     case FN_MAKE_MELTDOWN:
         if (lead)
-            for (int x = 0; x < WORLD_W - 1; x++) {
+            MP_NOUNROLL for (int x = 0; x < WORLD_W - 1; x++) {
                 bool done = false;
-                for (int y = 0; y < WORLD_H - 1; y++)
+                MP_NOUNROLL for (int y = 0; y < WORLD_H - 1; y++)
                     if ((e.map[tix(x, y)] & LOMASK) == T_NUCLEAR) { do_meltdown(e, x, y); done = true; break; }
                 if (done) break;
             }

@@ -114,8 +114,8 @@ MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
     if (size == 6) { xc -= 1; yc -= 1; }
     int x0 = tmax(0, xc - 1), y0 = tmax(0, yc - 1);
     int x1 = tmin(xc - 1 + size, (int)CFG.W), y1 = tmin(yc - 1 + size, (int)CFG.H);
-    for (int i = x0; i < x1; i++)
-        for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, -1, -1, 0);
+    MP_NOUNROLL for (int i = x0; i < x1; i++)
+        MP_NOUNROLL for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, -1, -1, 0);
 }
 
 // [LEAD] tilemap.py:391-408 clearPatch
@@ -127,8 +127,8 @@ MPD int gym_clear_patch(Env &e, Gym &gy, int x, int y, int size, bool static_bui
     }
     int x0 = tmax(x - 1, 0), x1 = tmin(x - 1 + size, (int)CFG.W);
     int y0 = tmax(y - 1, 0), y1 = tmin(y - 1 + size, (int)CFG.H);
-    for (int i = x0; i < x1; i++)
-        for (int j = y0; j < y1; j++) {
+    MP_NOUNROLL for (int i = x0; i < x1; i++)
+        MP_NOUNROLL for (int j = y0; j < y1; j++) {
             if (gy.stat[gym_cell(gy, i, j)] == 1) return 0;
             gym_clear_tile(e, gy, i, j, static_build);
         }
@@ -147,8 +147,8 @@ MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
     }
     int x0 = tmax(0, x - 1), y0 = tmax(0, y - 1);
     int x1 = tmin(x - 1 + size, (int)CFG.W), y1 = tmin(y - 1 + size, (int)CFG.H);
-    for (int i = x0; i < x1; i++)
-        for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
+    MP_NOUNROLL for (int i = x0; i < x1; i++)
+        MP_NOUNROLL for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
 }
 
 // The full agent tool list (corecontrol.py:85-106) as (TileMap zone id, engine EditingTool);
@@ -213,8 +213,8 @@ MPD void gym_set_empty(Env &e, Gym &gy)
 MPD void gym_update_map(Env &e, Gym &gy)
 {
     if (e.c.lead())
-        for (int i = 0; i < CFG.W; i++)
-            for (int j = 0; j < CFG.H; j++)
+        MP_NOUNROLL for (int i = 0; i < CFG.W; i++)
+            MP_NOUNROLL for (int j = 0; j < CFG.H; j++)
                 gym_update_tile(e, gy, i, j, gym_zone_of_tile(gy, gym_get_tile(e, gy, i, j)), i * 128 + j, -1);
     e.c.sync();
 }
@@ -233,7 +233,7 @@ MPD double dabs(double v) { return v < 0 ? -v : v; }
 MPD double gym_reward(const Gym &gy)
 {
     double reward = 0;
-    for (int k = 0; k < GYM_NUM_METRICS; k++) {
+    MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) {
         double last = G.last_metrics[k], trg_change = CFG.trg[k] - last, change = G.metrics[k] - last, r;
         if (dsign(change) != dsign(trg_change)) r = -dabs(change);
         else if (dabs(change) < dabs(trg_change)) r = dabs(change);
@@ -303,7 +303,7 @@ MPD void gym_step_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *
 {
     gym_observe(e, gy, obs);                                    // getState()
     if (e.c.lead()) {
-        for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
+        MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
         gym_city_metrics(e, gy, G.metrics);
         G.reward = gym_reward(gy);
         G.curr_funds = (int32_t)e.s->totalFunds;
@@ -345,7 +345,7 @@ MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t 
 {
     if (e.c.lead()) {
         gym_city_metrics(e, gy, G.metrics);                     // uses the previous total_traffic
-        for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
+        MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
         e.s->totalFunds = CFG.init_funds;
         G.reward = gym_reward(gy);
         G.done = 0;

@@ -129,7 +129,7 @@ MPD bool find_perimeter_road(Env &e, int &x, int &y)
 {
     const int8_t px[12] = { -1, 0, 1, 2, 2, 2, 1, 0, -1, -2, -2, -2 };
     const int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
-    for (int z = 0; z < 12; z++) {
+    MP_NOUNROLL for (int z = 0; z < 12; z++) {
         int tx = x + px[z], ty = y + py[z];
         if (inb(tx, ty) && road_test(e.map[tix(tx, ty)])) {
             x = tx; y = ty;
@@ -154,7 +154,7 @@ MPD int tile_toward(const Env &e, int x, int y, int dir, int dflt)   // traffic.
 MPD int try_go(Env &e, int x, int y, int dirLast)
 {
     int dirs[4], dir = D_N, count = 0;
-    for (int i = 0; i < 4; i++) {
+    MP_NOUNROLL for (int i = 0; i < 4; i++) {
         if (dir != dirLast && road_test(tile_toward(e, x, y, dir, T_DIRT))) {
             dirs[i] = dir;
             count++;
@@ -165,7 +165,7 @@ MPD int try_go(Env &e, int x, int y, int dirLast)
     }
     if (count == 0) return D_INVALID;
     if (count == 1) {
-        for (int i = 0; i < 4; i++) if (dirs[i] != D_INVALID) return dirs[i];
+        MP_NOUNROLL for (int i = 0; i < 4; i++) if (dirs[i] != D_INVALID) return dirs[i];
     }
     int i = rnd16(e) & 3;
     while (dirs[i] == D_INVALID) i = (i + 1) & 3;
@@ -189,7 +189,7 @@ MPD bool drive_done(const Env &e, int x, int y, int dest)
 MPD bool try_drive(Env &e, int x, int y, int dest)
 {
     int dirLast = D_INVALID;
-    for (int16_t dist = 0; dist < MAX_TRAFFIC_DISTANCE; dist++) {
+    MP_NOUNROLL for (int16_t dist = 0; dist < MAX_TRAFFIC_DISTANCE; dist++) {
         int dir = try_go(e, x, y, dirLast);
         if (dir != D_INVALID) {
             pos_move(x, y, dir);
@@ -270,14 +270,14 @@ MPD int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:2
 // [LEAD] zone.cpp:315-352 zonePlop
 MPN bool zone_plop(Env &e, int x, int y, int base)
 {
-    for (int z = 0; z < 9; z++) {
+    MP_NOUNROLL for (int z = 0; z < 9; z++) {
         int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
         if (inb(xx, yy)) {
             int t = e.map[tix(xx, yy)] & LOMASK;
             if (t >= T_FLOOD && t < T_ROADBASE) return false;
         }
     }
-    for (int z = 0; z < 9; z++) {
+    MP_NOUNROLL for (int z = 0; z < 9; z++) {
         int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
         if (inb(xx, yy)) e.map[tix(xx, yy)] = (uint16_t)(base + BNCNBIT);
         base++;
@@ -290,8 +290,8 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
 MPD int16_t do_free_pop(const Env &e, int x, int y)                // zone.cpp:360-377
 {
     int16_t count = 0;
-    for (int xx = x - 1; xx <= x + 1; xx++)
-        for (int yy = y - 1; yy <= y + 1; yy++)
+    MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
+        MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
             if (inb(xx, yy)) {
                 int t = e.map[tix(xx, yy)] & LOMASK;
                 if (t >= T_LHTHR && t <= T_HHTHR) count++;
@@ -309,7 +309,7 @@ MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:4
     int16_t z = (int16_t)(e.map[tix(x, y)] & LOMASK);
     if (z && (z < T_RESBASE || z > T_RESBASE + 8)) return -1;
     int16_t score = 1;
-    for (z = 0; z < 4; z++) {
+    MP_NOUNROLL for (z = 0; z < 4; z++) {
         int xx = x + dx[z], yy = y + dy[z];
         if (inb(xx, yy) && e.map[tix(xx, yy)] != T_DIRT && (e.map[tix(xx, yy)] & LOMASK) <= T_LASTROAD)
             score++;
@@ -322,7 +322,7 @@ MPD void build_house(Env &e, int x, int y, int value)
 {
     const int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
     int16_t best = 0, hscore = 0;
-    for (int16_t z = 1; z < 9; z++) {
+    MP_NOUNROLL for (int16_t z = 1; z < 9; z++) {
         int xx = x + zx[z], yy = y + zy[z];
         if (inb(xx, yy)) {
             int16_t score = eval_lot(e, xx, yy);
@@ -390,16 +390,16 @@ MPD void do_res_out(Env &e, int x, int y, int pop, int value)
     if (pop == 16) {
         inc_rate_of_growth(e, x, y, -8);
         e.map[tix(x, y)] = (uint16_t)(T_FREEZ | BLBNCNBIT | ZONEBIT);
-        for (int xx = x - 1; xx <= x + 1; xx++)
-            for (int yy = y - 1; yy <= y + 1; yy++)
+        MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
+            MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) != T_FREEZ)
                     e.map[tix(xx, yy)] = (uint16_t)(T_LHTHR + value + rnd(e, 2) + BLBNCNBIT);
     }
     if (pop < 16) {
         inc_rate_of_growth(e, x, y, -1);
         int z = 0;
-        for (int xx = x - 1; xx <= x + 1; xx++)
-            for (int yy = y - 1; yy <= y + 1; yy++) {
+        MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
+            MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++) {
                 if (inb(xx, yy)) {
                     int loc = e.map[tix(xx, yy)] & LOMASK;
                     if (loc >= T_LHTHR && loc <= T_HHTHR) {
@@ -562,8 +562,8 @@ MPN void do_industrial(Env &e, int x, int y, bool zonePower)
 MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
 {
     int tile = zCent - 2 - zSize;
-    for (int yy = -1; yy < zSize - 1; yy++)
-        for (int xx = -1; xx < zSize - 1; xx++) {
+    MP_NOUNROLL for (int yy = -1; yy < zSize - 1; yy++)
+        MP_NOUNROLL for (int xx = -1; xx < zSize - 1; xx++) {
             int ax = x + xx, ay = y + yy;
             tile++;
             if (inb(ax, ay)) {
@@ -600,9 +600,9 @@ MPN void do_meltdown(Env &e, int x, int y)
     make_explosion(e, x - 1, y + 2);
     make_explosion(e, x + 2, y - 1);
     make_explosion(e, x + 2, y + 2);
-    for (int xx = x - 1; xx < x + 3; xx++)
-        for (int yy = y - 1; yy < y + 3; yy++) tset(e, xx, yy, random_fire(e));
-    for (int z = 0; z < 200; z++) {
+    MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++)
+        MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++) tset(e, xx, yy, random_fire(e));
+    MP_NOUNROLL for (int z = 0; z < 200; z++) {
         int xx = x - 20 + rnd(e, 40);
         int yy = y - 15 + rnd(e, 30);
         if (!inb(xx, yy)) continue;
@@ -624,7 +624,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
         push_power_stack(e, x, y);
         const int16_t sm[4] = { T_COALSMOKE1, T_COALSMOKE2, T_COALSMOKE3, T_COALSMOKE4 };
         const int8_t dx[4] = { 1, 2, 1, 2 }, dy[4] = { -1, -1, 0, 0 };
-        for (int i = 0; i < 4; i++)
+        MP_NOUNROLL for (int i = 0; i < 4; i++)
             tset(e, x + dx[i], y + dy[i], sm[i] | ANIMBIT | CONDBIT | PWRBIT | BURNBIT);
         return;
     }
@@ -655,8 +655,8 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
         if (!(S.cityTime & 15)) repair_zone(e, x, y, T_STADIUM, 4);
         if (powerOn && ((S.cityTime + x + y) & 31) == 0) {
             int z = T_FULLSTADIUM - 5;
-            for (int yy = y - 1; yy < y + 3; yy++)
-                for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
+            MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
+                MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
             e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
             tset(e, x + 1, y, T_FOOTBALLGAME1 + ANIMBIT);
             tset(e, x + 1, y + 1, T_FOOTBALLGAME2 + ANIMBIT);
@@ -666,8 +666,8 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
         S.stadiumPop++;
         if (((S.cityTime + x + y) & 7) == 0) {
             int z = T_STADIUM - 5;
-            for (int yy = y - 1; yy < y + 3; yy++)
-                for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
+            MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
+                MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
             e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
         }
         return;
@@ -716,8 +716,8 @@ MPD void fire_zone(Env &e, int x, int y, int ch)
     s8set(e.rog, x, y, v);
     ch &= LOMASK;
     int xymax = ch < T_PORTBASE ? 2 : (ch == T_AIRPORT ? 5 : 4);
-    for (int dx = -1; dx < xymax; dx++)
-        for (int dy = -1; dy < xymax; dy++) {
+    MP_NOUNROLL for (int dx = -1; dx < xymax; dx++)
+        MP_NOUNROLL for (int dy = -1; dy < xymax; dy++) {
             int xx = x + dx, yy = y + dy;
             if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map[tix(xx, yy)] |= BULLBIT;
         }
@@ -727,7 +727,7 @@ MPD void fire_zone(Env &e, int x, int y, int ch)
 MPN void do_fire(Env &e, int x, int y)
 {
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
-    for (int z = 0; z < 4; z++) {
+    MP_NOUNROLL for (int z = 0; z < 4; z++) {
         if ((rnd16(e) & 7) == 0) {
             int xx = x + dx[z], yy = y + dy[z];
             if (inb(xx, yy)) {
@@ -756,7 +756,7 @@ MPN void do_flood(Env &e, int x, int y)
 {
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     if (S.floodCount > 0) {
-        for (int z = 0; z < 4; z++) {
+        MP_NOUNROLL for (int z = 0; z < 4; z++) {
             if ((rnd16(e) & 7) == 0) {
                 int xx = x + dx[z], yy = y + dy[z];
                 if (inb(xx, yy)) {
@@ -789,7 +789,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
         T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT, T_RIVER };
     if (tile == T_BRWV) {
         if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
-            for (int z = 0; z < 7; z++) {
+            MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + VDx[z], yy = y + VDy[z];
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (VBRTAB[z] & LOMASK))
                     e.map[tix(xx, yy)] = (uint16_t)VBRTAB2[z];
@@ -798,7 +798,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
     }
     if (tile == T_BRWH) {
         if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
-            for (int z = 0; z < 7; z++) {
+            MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + HDx[z], yy = y + HDy[z];
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (HBRTAB[z] & LOMASK))
                     e.map[tix(xx, yy)] = (uint16_t)HBRTAB2[z];
@@ -808,7 +808,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
     if (boat_distance(e, x, y) < 300 || !(rnd16(e) & 7)) {
         if (tile & 1) {
             if (x < WORLD_W - 1 && e.map[tix(x + 1, y)] == T_CHANNEL) {
-                for (int z = 0; z < 7; z++) {
+                MP_NOUNROLL for (int z = 0; z < 7; z++) {
                     int xx = x + VDx[z], yy = y + VDy[z];
                     if (inb(xx, yy)) {
                         int m = e.map[tix(xx, yy)];
@@ -820,7 +820,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
             return false;
         } else {
             if (y > 0 && e.map[tix(x, y - 1)] == T_CHANNEL) {
-                for (int z = 0; z < 7; z++) {
+                MP_NOUNROLL for (int z = 0; z < 7; z++) {
                     int xx = x + HDx[z], yy = y + HDy[z];
                     if (inb(xx, yy)) {
                         int m = e.map[tix(xx, yy)];
@@ -915,26 +915,55 @@ MPD void scan_tile(Env &e, int idx)
 }
 
 // [ALL] mapScan(x1, x2).  The scan order is linear memory order (x outer, y inner over the
-// column-major map).  Device: warp 0 looks at 32 tiles at a time (one 64-byte row of the packed
-// uint16 map), a ballot finds the tiles the reference would not skip, and lane 0 processes them
-// one by one in order; after each processed tile the ballot is re-taken for the tiles behind it
-// because processing may have changed them (fire spread, zonePlop, ...).
+// column-major map).  Device: each lane looks at 8 consecutive tiles with one 128-bit load (256
+// tiles = 512 contiguous bytes per warp round), builds an 8-bit "the reference would not skip
+// this tile" mask, a ballot finds the first lane with work, and lane 0 processes that tile.  After
+// each processed tile every lane reloads its 8 tiles (L1 hits) and masks off what is already
+// behind the scan position, because processing may have changed tiles ahead of it (fire spread,
+// zonePlop, repairZone, ...).
+MPD unsigned active8(const uint16_t *map, int idx0, int lo, int hi)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 q = *reinterpret_cast<const uint4 *>(map + idx0);
+    const unsigned w[4] = { q.x, q.y, q.z, q.w };
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if ((w[k] & 0x3ffu) >= (unsigned)T_FLOOD) m |= 1u << (2 * k);
+        if (((w[k] >> 16) & 0x3ffu) >= (unsigned)T_FLOOD) m |= 2u << (2 * k);
+    }
+    // keep only tiles in [lo, hi)
+    int a = lo - idx0, b = hi - idx0;
+    if (a > 0) m &= (a >= 8) ? 0u : (0xffu << a);
+    if (b < 8) m &= (b <= 0) ? 0u : (0xffu >> (8 - b));
+    return m;
+#else
+    (void)map; (void)idx0; (void)lo; (void)hi;
+    return 0;
+#endif
+}
+
 MPD void map_scan(Env &e, int x1, int x2)
 {
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
 #if defined(__CUDA_ARCH__)
     {
         const int lane = e.c.tid;
-        for (int base = i0; base < i1; base += 32) {
-            int idx = base + lane;
-            bool ok = idx < i1;
-            unsigned m = __ballot_sync(0xffffffffu, ok && tile_is_active(e.map[ok ? idx : i0]));
-            while (m) {
-                int b = __ffs(m) - 1;
-                if (lane == 0) scan_tile(e, base + b);
+        MP_NOUNROLL for (int base = i0 & ~7; base < i1; base += 256) {
+            const int idx0 = base + lane * 8;
+            const bool ok = idx0 < i1;                  // NTILES is a multiple of 8: the load stays in the map
+            int pos = i0;                               // first tile not yet passed by the scan
+            unsigned m = ok ? active8(e.map, idx0, pos, i1) : 0u;
+            unsigned any = __ballot_sync(0xffffffffu, m != 0);
+            while (any) {
+                const int L = __ffs(any) - 1;
+                const unsigned mL = __shfl_sync(0xffffffffu, m, L);
+                const int t = base + L * 8 + (__ffs(mL) - 1);
+                if (lane == 0) scan_tile(e, t);
                 __syncwarp();
-                unsigned hi = (b == 31) ? 0u : (0xffffffffu << (b + 1));
-                m = __ballot_sync(0xffffffffu, ok && tile_is_active(e.map[ok ? idx : i0])) & hi;
+                pos = t + 1;
+                m = ok ? active8(e.map, idx0, pos, i1) : 0u;
+                any = __ballot_sync(0xffffffffu, m != 0);
             }
         }
     }
@@ -949,7 +978,7 @@ MPD void map_scan(Env &e, int x1, int x2)
 // [LEAD] simulate.cpp:712-780 take10Census
 MPN void take10_census(Env &e)
 {
-    for (int x = 118; x >= 0; x--) {
+    MP_NOUNROLL for (int x = 118; x >= 0; x--) {
         e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
         e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
         e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
@@ -976,7 +1005,7 @@ MPN void take10_census(Env &e)
 // [LEAD] simulate.cpp:784-826 take120Census
 MPN void take120_census(Env &e)
 {
-    for (int x = 238; x >= 120; x--) {
+    MP_NOUNROLL for (int x = 238; x >= 120; x--) {
         e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
         e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
         e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
@@ -1029,7 +1058,7 @@ MPN void do_budget(Env &e)
         S.fireValue = 0; S.policeValue = 0; S.roadValue = 0;
         S.firePercent = 1.0f; S.policePercent = 1.0f; S.roadPercent = 1.0f;
     }
-    for (;;) {
+    MP_NOUNROLL for (;;) {
         if (!S.autoBudget) {
             // showBudgetWindowAndStartWaiting is a front-end callback (no state)
             S.fireSpend = S.fireValue; S.policeSpend = S.policeValue; S.roadSpend = S.roadValue;
@@ -1071,16 +1100,27 @@ MPN void collect_tax(Env &e)
 }
 
 // ------------------------------------------------------------------ phase 10
-// [ALL] simulate.cpp:327-350 decTrafficMap
+// [ALL] simulate.cpp:327-350 decTrafficMap (four cells per 32-bit word on the device)
+MPD uint8_t dec_traffic_cell(int z)
+{
+    if (z == 0) return 0;
+    if (z <= 24) return 0;
+    return (uint8_t)(z > 200 ? z - 34 : z - 24);
+}
 MPD void dec_traffic_map(Env &e)
 {
-    for (int i = e.c.tid; i < N2; i += e.c.n) {
-        int z = e.traffic[i];
-        if (z == 0) continue;
-        if (z <= 24) e.traffic[i] = 0;
-        else if (z > 200) e.traffic[i] = (uint8_t)(z - 34);
-        else e.traffic[i] = (uint8_t)(z - 24);
+#if defined(__CUDA_ARCH__)
+    uint32_t *w = reinterpret_cast<uint32_t *>(e.traffic);
+    for (int i = e.c.tid; i < N2 / 4; i += e.c.n) {
+        uint32_t v = w[i];
+        if (v == 0) continue;
+        uint32_t r = dec_traffic_cell(v & 0xff) | (dec_traffic_cell((v >> 8) & 0xff) << 8)
+            | (dec_traffic_cell((v >> 16) & 0xff) << 16) | ((uint32_t)dec_traffic_cell(v >> 24) << 24);
+        w[i] = r;
     }
+#else
+    for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic[i] = dec_traffic_cell(e.traffic[i]);
+#endif
 }
 
 // [ALL] simulate.cpp:356-385 decRateOfGrowthMap
@@ -1239,7 +1279,7 @@ MPD int pollution_value(int loc)                                    // scan.cpp:
 MPD void coop_add(Env &e, int slot, int v)
 {
 #if defined(__CUDA_ARCH__)
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    MP_NOUNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (e.c.tid == 0) e.c.red[slot] += v;
 #else
     e.c.red[slot] += v;
@@ -1253,8 +1293,8 @@ MPN void ptlv_scan(Env &e)
     // tempMap3: +15 per natural tile (0 < tile < RUBBLE) in each 4x4 block (Byte wrap)
     for (int i = e.c.tid; i < N4; i += e.c.n) {
         int bx = (i / H4) * 4, by = (i % H4) * 4, cnt = 0;
-        for (int dx = 0; dx < 4; dx++)
-            for (int dy = 0; dy < 4; dy++) {
+        MP_NOUNROLL for (int dx = 0; dx < 4; dx++)
+            MP_NOUNROLL for (int dy = 0; dy < 4; dy++) {
                 int loc = e.map[tix(bx + dx, by + dy)] & LOMASK;
                 if (loc && loc < T_RUBBLE) cnt++;
             }
@@ -1266,8 +1306,8 @@ MPN void ptlv_scan(Env &e)
         int x = i / H2, y = i - x * H2, wx = x * 2, wy = y * 2;
         int plevel = 0;
         bool lvflag = false;
-        for (int mx = wx; mx <= wx + 1; mx++)
-            for (int my = wy; my <= wy + 1; my++) {
+        MP_NOUNROLL for (int mx = wx; mx <= wx + 1; mx++)
+            MP_NOUNROLL for (int my = wy; my <= wy + 1; my++) {
                 int loc = e.map[tix(mx, my)] & LOMASK;
                 if (loc) {
                     if (loc < T_RUBBLE) continue;
@@ -1303,7 +1343,7 @@ MPN void ptlv_scan(Env &e)
     if (e.c.lead()) {
         int pmax = 0, pnum = 0;
         int64_t ptot = 0;
-        for (int i = 0; i < N2; i++) {
+        MP_NOUNROLL for (int i = 0; i < N2; i++) {
             int z = e.tmp1[i];
             if (z) {
                 pnum++;
@@ -1357,7 +1397,7 @@ MPN void crime_scan(Env &e)
     if (e.c.lead()) {
         int64_t totz = 0;
         int numz = 0, cmax = 0;
-        for (int i = 0; i < N2; i++) {
+        MP_NOUNROLL for (int i = 0; i < N2; i++) {
             if (!e.tmp2[i]) continue;
             int z = e.crime[i];
             ++numz;
@@ -1390,8 +1430,8 @@ MPN void pop_density_scan(Env &e)
     int xt = 0, yt = 0, zt = 0;
     for (int i = e.c.tid; i < N2; i += e.c.n) {
         int bx = (i / H2) * 2, by = (i % H2) * 2, v = 0;
-        for (int dx = 0; dx < 2; dx++)          // scan order inside the 2x2 cluster: last zone wins
-            for (int dy = 0; dy < 2; dy++) {
+        MP_NOUNROLL for (int dx = 0; dx < 2; dx++)          // scan order inside the 2x2 cluster: last zone wins
+            MP_NOUNROLL for (int dy = 0; dy < 2; dy++) {
                 int mv = e.map[tix(bx + dx, by + dy)];
                 if (mv & ZONEBIT) {
                     int pop = population_density_of(e, bx + dx, by + dy, mv & LOMASK) * 8;
@@ -1453,7 +1493,7 @@ MPN void city_evaluation(Env &e)
 {
     if (S.totalPop > 0) {
         int16_t pt[PROBNUM + 1];
-        for (int z = 0; z <= PROBNUM; z++) pt[z] = 0;
+        MP_NOUNROLL for (int z = 0; z <= PROBNUM; z++) pt[z] = 0;
         // getAssessedValue :154-169
         int64_t z = S.roadTotal * 5;
         z += S.railTotal * 10; z += S.policeStationPop * 1000; z += S.fireStationPop * 1000;
@@ -1474,7 +1514,7 @@ MPN void city_evaluation(Env &e)
         {   // getTrafficAverage :305-327
             int64_t tt = 0;
             int16_t count = 1;
-            for (int i = 0; i < N2; i++)
+            MP_NOUNROLL for (int i = 0; i < N2; i++)
                 if (e.landval[i] > 0) { tt += e.traffic[i]; count++; }
             S.trafficAverage = d2s((double)(tt / count) * 2.4);
             pt[4] = S.trafficAverage;
@@ -1491,7 +1531,7 @@ MPN void city_evaluation(Env &e)
         int16_t fireSeverity = (int16_t)tmin(S.firePop * 5, 255);
         pt[6] = fireSeverity;
         // voteProblems :278-299
-        for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+        MP_NOUNROLL for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
         int problem = 0, voteCount = 0, loopCount = 0;
         while (voteCount < 100 && loopCount < 600) {
             if (rnd(e, 300) < pt[problem]) {
@@ -1503,10 +1543,10 @@ MPN void city_evaluation(Env &e)
             loopCount++;
         }
         bool taken[PROBNUM];
-        for (int i = 0; i < PROBNUM; i++) taken[i] = false;
-        for (int c = 0; c < PROBLEM_COMPLAINTS; c++) {
+        MP_NOUNROLL for (int i = 0; i < PROBNUM; i++) taken[i] = false;
+        MP_NOUNROLL for (int c = 0; c < PROBLEM_COMPLAINTS; c++) {
             int maxVotes = 0, best = NUMPROBLEMS;
-            for (int i = 0; i < NUMPROBLEMS; i++)
+            MP_NOUNROLL for (int i = 0; i < NUMPROBLEMS; i++)
                 if (S.problemVotes[i] > maxVotes && !taken[i]) { best = i; maxVotes = S.problemVotes[i]; }
             S.problemOrder[c] = (int16_t)best;
             if (best < NUMPROBLEMS) taken[best] = true;
@@ -1514,7 +1554,7 @@ MPN void city_evaluation(Env &e)
         // getScore :359-451 (int, float and double mixed exactly as written there)
         int16_t last = S.cityScore;
         int x = 0;
-        for (int i = 0; i < NUMPROBLEMS; i++) x += pt[i];
+        MP_NOUNROLL for (int i = 0; i < NUMPROBLEMS; i++) x += pt[i];
         x = x / 3;
         x = tmin(x, 256);
         int sc = tclamp((256 - x) * 4, 0, 1000);
@@ -1543,14 +1583,14 @@ MPN void city_evaluation(Env &e)
         S.cityScoreDelta = (int16_t)(S.cityScore - last);
         // doVotes :454-464
         S.cityYes = 0;
-        for (int i = 0; i < 100; i++)
+        MP_NOUNROLL for (int i = 0; i < 100; i++)
             if (rnd(e, 1000) < S.cityScore) S.cityYes++;
     } else {
         // evalInit :129-147
         S.cityPop = 0; S.cityPopDelta = 0; S.cityAssessedValue = 0; S.cityClass = 0;
         S.cityScore = 500; S.cityScoreDelta = 0;
-        for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
-        for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
+        MP_NOUNROLL for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+        MP_NOUNROLL for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
         S.cityYes = 50;
     }
 }
@@ -1661,8 +1701,8 @@ MPD void do_sim_init(Env &e)
             // setCommonInits -> evalInit
             S.cityYes = 0; S.cityPop = 0; S.cityPopDelta = 0; S.cityAssessedValue = 0;
             S.cityClass = 0; S.cityScore = 500; S.cityScoreDelta = 0;
-            for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
-            for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
+            MP_NOUNROLL for (int i = 0; i < PROBNUM; i++) S.problemVotes[i] = 0;
+            MP_NOUNROLL for (int i = 0; i < PROBLEM_COMPLAINTS; i++) S.problemOrder[i] = NUMPROBLEMS;
             S.roadEffect = MAX_ROAD_EFFECT; S.policeEffect = MAX_POLICE_EFFECT;
             S.fireEffect = MAX_FIRE_EFFECT; S.taxFlag = 0; S.taxFund = 0;
             S.crimeRamp = 0; S.pollutionRamp = 0; S.totalPop = 0;

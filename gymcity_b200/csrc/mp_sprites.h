@@ -90,7 +90,7 @@ MPN void init_sprite(Env &e, int si, int x, int y)
 MPN int new_sprite(Env &e, int type, int x, int y)
 {
     int si = -1;
-    for (int i = 0; i < MAX_SPRITES; i++)
+    MP_NOUNROLL for (int i = 0; i < MAX_SPRITES; i++)
         if (!e.spr[i].used) { si = i; break; }
     if (si < 0) { S.spriteOverflow = 1; return -1; }
     e.spr[si].used = 1;
@@ -107,7 +107,7 @@ MPD void destroy_sprite(Env &e, int si)
     if (S.globalSprites[e.spr[si].type] == si) S.globalSprites[e.spr[si].type] = -1;
     if (S.spriteHead == si) S.spriteHead = e.spr[si].next;
     else
-        for (int p = S.spriteHead; p >= 0; p = e.spr[p].next)
+        MP_NOUNROLL for (int p = S.spriteHead; p >= 0; p = e.spr[p].next)
             if (e.spr[p].next == si) { e.spr[p].next = e.spr[si].next; break; }
     e.spr[si].used = 0;
 }
@@ -130,7 +130,7 @@ MPN void make_explosion(Env &e, int x, int y)                  // sprite.cpp:201
 MPD int boat_distance(Env &e, int x, int y)                    // simulate.cpp:1253-1273
 {
     int dist = 99999, mx = x * 16 + 8, my = y * 16 + 8;
-    for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) {
+    MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) {
         const Sprite &sp = e.spr[i];
         if (sp.type == SPR_SHIP && sp.frame != 0) {
             int d = iabs(sp.x + sp.xHot - mx) + iabs(sp.y + sp.yHot - my);
@@ -206,8 +206,8 @@ MPD void start_fire_in_zone(Env &e, int x, int y, int ch)
     s8set(e.rog, x, y, v);
     ch &= LOMASK;
     int xymax = ch < T_PORTBASE ? 2 : (ch == T_AIRPORT ? 5 : 4);
-    for (int dx = -1; dx < xymax; dx++)
-        for (int dy = -1; dy < xymax; dy++) {
+    MP_NOUNROLL for (int dx = -1; dx < xymax; dx++)
+        MP_NOUNROLL for (int dy = -1; dy < xymax; dy++) {
             int xx = x + dx, yy = y + dy;
             if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map[tix(xx, yy)] |= BULLBIT;
         }
@@ -259,7 +259,7 @@ MPN void do_train(Env &e, int si)
     sp.y = (int16_t)(sp.y + Dy[sp.dir]);
     if ((S.spriteCycle & 3) == 0) {
         int16_t dir = (int16_t)(rnd16(e) & 3);
-        for (int16_t z = dir; z < dir + 4; z++) {
+        MP_NOUNROLL for (int16_t z = dir; z < dir + 4; z++) {
             int16_t dir2 = z & 3;
             if (sp.dir != 4 && dir2 == ((sp.dir + 2) & 3)) continue;
             int16_t c = get_char(e, sp.x + Cx[dir2] + 48, sp.y + Cy[dir2]);
@@ -334,7 +334,7 @@ MPN void do_airplane(Env &e, int si)
     }
     if (S.enableDisasters) {
         bool explode = false;
-        for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
+        MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
             if (e.spr[s].frame == 0 || s == si) continue;
             if ((e.spr[s].type == SPR_HELICOPTER || e.spr[s].type == SPR_AIRPLANE)
                 && sprite_collision(e.spr[si], e.spr[s])) {
@@ -373,7 +373,7 @@ MPN void do_ship(Env &e, int si)
             return;
         }
         int16_t tem = (int16_t)(rnd16(e) & 7), pem;
-        for (pem = tem; pem < (tem + 8); pem++) {
+        MP_NOUNROLL for (pem = tem; pem < (tem + 8); pem++) {
             z = (int16_t)((pem & 7) + 1);
             if (z == sp.dir) continue;
             x = (int16_t)(((sp.x + (48 - 1)) >> 4) + BDx[z]);
@@ -401,7 +401,7 @@ MPN void do_ship(Env &e, int si)
         }
     }
     if (sprite_not_in_bounds(sp)) { sp.frame = 0; return; }
-    for (z = 0; z < 8; z++) {
+    MP_NOUNROLL for (z = 0; z < 8; z++) {
         if (t == clr[z]) break;
         if (z == 7) {
             explode_sprite(e, si);
@@ -412,7 +412,7 @@ MPN void do_ship(Env &e, int si)
 
 MPD void hit_vehicles(Env &e, int si)                          // shared by monster and tornado
 {
-    for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
+    MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
         int ty = e.spr[s].type;
         if (e.spr[s].frame != 0
             && (ty == SPR_AIRPLANE || ty == SPR_HELICOPTER || ty == SPR_SHIP || ty == SPR_TRAIN)
@@ -553,7 +553,7 @@ MPN void move_objects(Env &e)
 {
     if (!S.simSpeed) return;
     S.spriteCycle++;
-    for (int si = S.spriteHead; si >= 0;) {
+    MP_NOUNROLL for (int si = S.spriteHead; si >= 0;) {
         if (e.spr[si].frame > 0) {
             switch (e.spr[si].type) {
             case SPR_TRAIN: do_train(e, si); break;
@@ -584,19 +584,19 @@ MPN void generate_train(Env &e, int x, int y)                  // sprite.cpp:183
 MPN void generate_ship(Env &e)                                 // sprite.cpp:1854-1898
 {
     if (!(rnd16(e) & 3))
-        for (int x = 4; x < WORLD_W - 2; x++)
+        MP_NOUNROLL for (int x = 4; x < WORLD_W - 2; x++)
             if (e.map[tix(x, 0)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, (x << 4) - 47, 0); return; }
     if (!(rnd16(e) & 3))
-        for (int y = 1; y < WORLD_H - 2; y++)
+        MP_NOUNROLL for (int y = 1; y < WORLD_H - 2; y++)
             if (e.map[tix(0, y)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, -47, y << 4); return; }
     if (!(rnd16(e) & 3))
-        for (int x = 4; x < WORLD_W - 2; x++)
+        MP_NOUNROLL for (int x = 4; x < WORLD_W - 2; x++)
             if (e.map[tix(x, WORLD_H - 1)] == T_CHANNEL) {
                 make_sprite(e, SPR_SHIP, (x << 4) - 47, (WORLD_H - 1) << 4);
                 return;
             }
     if (!(rnd16(e) & 3))
-        for (int y = 1; y < WORLD_H - 2; y++)
+        MP_NOUNROLL for (int y = 1; y < WORLD_H - 2; y++)
             if (e.map[tix(WORLD_W - 1, y)] == T_CHANNEL) {
                 make_sprite(e, SPR_SHIP, ((WORLD_W - 1) << 4) - 47, y << 4);
                 return;
@@ -625,7 +625,7 @@ MPN void make_monster(Env &e)
         e.spr[si].destY = (int16_t)(S.pollutionMaxY << 4);
         return;
     }
-    for (int z = 0; z < 300; z++) {
+    MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 20) + 10, y = rnd(e, WORLD_H - 10) + 5;
         int v = e.map[tix(x, y)];
         if (v == T_RIVER || v == T_RIVER + BULLBIT) {
@@ -657,7 +657,7 @@ MPD bool vulnerable(int tem)                                   // disasters.cpp:
 MPN void make_earthquake(Env &e)
 {
     int strength = rnd(e, 700) + 300;
-    for (int16_t z = 0; z < strength; z++) {
+    MP_NOUNROLL for (int16_t z = 0; z < strength; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
         if (vulnerable(e.map[tix(x, y)])) {
             if ((z & 0x3) != 0) e.map[tix(x, y)] = (uint16_t)random_rubble(e);
@@ -681,11 +681,11 @@ MPN void set_fire(Env &e)
 MPN void make_flood(Env &e)
 {
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
-    for (int z = 0; z < 300; z++) {
+    MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
         int c = e.map[tix(x, y)] & LOMASK;
         if (c > T_CHANNEL && c <= T_WATER_HIGH) {
-            for (int t = 0; t < 4; t++) {
+            MP_NOUNROLL for (int t = 0; t < 4; t++) {
                 int xx = x + dx[t], yy = y + dy[t];
                 if (inb(xx, yy)) {
                     int16_t cc = (int16_t)e.map[tix(xx, yy)];

@@ -16,10 +16,14 @@
 #define MPD __device__ __forceinline__
 #define MPN __device__ __noinline__
 #define MPH __host__ __device__ inline
+// The serial lane is latency bound and its code footprint is what hurts (the engine is ~10x the SM
+// instruction caches): keep its loops rolled.
+#define MP_NOUNROLL _Pragma("unroll 1")
 #else
 #define MPD inline
 #define MPN inline
 #define MPH inline
+#define MP_NOUNROLL
 #endif
 
 namespace mp {

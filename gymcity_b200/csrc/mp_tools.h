@@ -26,7 +26,7 @@ struct Fx {                 // one tool call's pending effects
     MPD Fx(Env &env, int x, int y) : e(env), ox(x - 5), oy(y - 5), cost(0)
     {
         uint32_t *m = (uint32_t *)(e.ovl + 256);
-        for (int i = 0; i < 8; i++) m[i] = 0;
+        MP_NOUNROLL for (int i = 0; i < 8; i++) m[i] = 0;
     }
     MPD int slot(int x, int y) const
     {
@@ -53,7 +53,7 @@ struct Fx {                 // one tool call's pending effects
     {
         e.s->totalFunds = (int)(e.s->totalFunds - cost);
         const uint32_t *m = (const uint32_t *)(e.ovl + 256);
-        for (int s = 0; s < 256; s++)
+        MP_NOUNROLL for (int s = 0; s < 256; s++)
             if ((m[s >> 5] >> (s & 31)) & 1u) e.map[tix(ox + (s >> 4), oy + (s & 15))] = e.ovl[s];
     }
 };
@@ -81,7 +81,7 @@ MPN void fix_single(Fx &fx, int x, int y)
     int adj = 0;
     int tile = neutralize_road(fx.tile(x, y));
     if (tile >= T_ROADS && tile <= T_INTERSECTION) {
-        for (int k = 0; k < 4; k++) {
+        MP_NOUNROLL for (int k = 0; k < 4; k++) {
             bool vert = (k == 0 || k == 2);
             int nx = x + (k == 1) - (k == 3), ny = y - (k == 0) + (k == 2);
             bool in = (k == 0) ? y > 0 : (k == 1) ? x < WORLD_W - 1 : (k == 2) ? y < WORLD_H - 1 : x > 0;
@@ -101,7 +101,7 @@ MPN void fix_single(Fx &fx, int x, int y)
         return;
     }
     if (tile >= T_LHRAIL && tile <= T_LVRAIL10) {
-        for (int k = 0; k < 4; k++) {
+        MP_NOUNROLL for (int k = 0; k < 4; k++) {
             bool vert = (k == 0 || k == 2);
             int nx = x + (k == 1) - (k == 3), ny = y - (k == 0) + (k == 2);
             bool in = (k == 0) ? y > 0 : (k == 1) ? x < WORLD_W - 1 : (k == 2) ? y < WORLD_H - 1 : x > 0;
@@ -116,7 +116,7 @@ MPN void fix_single(Fx &fx, int x, int y)
         return;
     }
     if (tile >= T_LHPOWER && tile <= T_LVPOWER10) {
-        for (int k = 0; k < 4; k++) {
+        MP_NOUNROLL for (int k = 0; k < 4; k++) {
             bool vert = (k == 0 || k == 2);
             int nx = x + (k == 1) - (k == 3), ny = y - (k == 0) + (k == 2);
             bool in = (k == 0) ? y > 0 : (k == 1) ? x < WORLD_W - 1 : (k == 2) ? y < WORLD_H - 1 : x > 0;
@@ -258,7 +258,7 @@ MPN int lay_wire(Fx &fx, int x, int y)                             // connect.cp
     case T_RIVER: case T_REDGE: case T_CHANNEL: {
         cost = 25;
         bool done = false;
-        for (int k = 0; k < 4 && !done; k++) {
+        MP_NOUNROLL for (int k = 0; k < 4 && !done; k++) {
             bool horiz = k < 2;
             int nx = x + (k == 0) - (k == 1), ny = y + (k == 2) - (k == 3);
             bool in = (k == 0) ? x < WORLD_W - 1 : (k == 1) ? x > 0 : (k == 2) ? y < WORLD_H - 1 : y > 0;
@@ -324,7 +324,7 @@ MPD int check_big_zone(int id, int &dh, int &dv)
 {
     dh = 0; dv = 0;
     const int base4[4] = { T_POWERPLANT, T_PORT, T_NUCLEAR, T_STADIUM };
-    for (int k = 0; k < 4; k++) {
+    MP_NOUNROLL for (int k = 0; k < 4; k++) {
         int d = id - base4[k];
         if (d == 0) return 4;
         if (d == 1) { dh = -1; return 4; }
@@ -351,8 +351,8 @@ MPD int check_size(int t)                                          // tool.cpp:3
 MPD void put_rubble(Fx &fx, int x, int y, int size)                // tool.cpp:910-924
 {
     Env &e = fx.e;
-    for (int xx = x; xx < x + size; xx++)
-        for (int yy = y; yy < y + size; yy++)
+    MP_NOUNROLL for (int xx = x; xx < x + size; xx++)
+        MP_NOUNROLL for (int yy = y; yy < y + size; yy++)
             if (inb(xx, yy)) {
                 int t = fx.tile(xx, yy);
                 if (t != T_RADTILE && t != T_DIRT) {
@@ -386,8 +386,8 @@ MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, b
     x--; y--;
     if (x < 0 || x + size > WORLD_W) return TR_FAILED;
     if (y < 0 || y + size > WORLD_H) return TR_FAILED;
-    for (int dy = 0; dy < size; dy++)
-        for (int dx = 0; dx < size; dx++) {
+    MP_NOUNROLL for (int dy = 0; dy < size; dy++)
+        MP_NOUNROLL for (int dx = 0; dx < size; dx++) {
             int t = fx.tile(x + dx, y + dy);
             if (t == T_DIRT) continue;
             if (!S.autoBulldoze) return TR_NEED_BULLDOZE;
@@ -396,8 +396,8 @@ MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, b
             fx.cost += 1;
         }
     fx.cost += toolCost;
-    for (int dy = 0; dy < size; dy++)
-        for (int dx = 0; dx < size; dx++) {
+    MP_NOUNROLL for (int dy = 0; dy < size; dy++)
+        MP_NOUNROLL for (int dx = 0; dx < size; dx++) {
             int v = base | BNCNBIT;
             if (dx == 1) {
                 if (dy == 1) v |= ZONEBIT;
@@ -406,10 +406,10 @@ MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, b
             fx.set(x + dx, y + dy, v);
             base++;
         }
-    for (int c = 0; c < size; c++) connect_tile(fx, x + c, y - 1, CC_FIX);
-    for (int c = 0; c < size; c++) connect_tile(fx, x - 1, y + c, CC_FIX);
-    for (int c = 0; c < size; c++) connect_tile(fx, x + c, y + size, CC_FIX);
-    for (int c = 0; c < size; c++) connect_tile(fx, x + size, y + c, CC_FIX);
+    MP_NOUNROLL for (int c = 0; c < size; c++) connect_tile(fx, x + c, y - 1, CC_FIX);
+    MP_NOUNROLL for (int c = 0; c < size; c++) connect_tile(fx, x - 1, y + c, CC_FIX);
+    MP_NOUNROLL for (int c = 0; c < size; c++) connect_tile(fx, x + c, y + size, CC_FIX);
+    MP_NOUNROLL for (int c = 0; c < size; c++) connect_tile(fx, x + size, y + c, CC_FIX);
     return TR_OK;
 }
 
@@ -420,7 +420,7 @@ MPD void smooth_trees_at_fx(Fx &fx, int x, int y, bool preserve)
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     if (!is_tree(fx.value(x, y))) return;
     int bits = 0;
-    for (int z = 0; z < 4; z++) {
+    MP_NOUNROLL for (int z = 0; z < 4; z++) {
         bits <<= 1;
         int xx = x + dx[z], yy = y + dy[z];
         if (inb(xx, yy) && is_tree(fx.value(xx, yy))) bits++;
@@ -511,7 +511,7 @@ MPN int tool_down(Env &e, int tool, int x, int y)
             if (v == T_DIRT) {
                 fx.set(x, y, T_WOODS | BLBNBIT);
                 const int8_t dx[8] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dy[8] = { -1, -1, -1, 0, 0, 1, 1, 1 };
-                for (int i = 0; i < 8; i++)
+                MP_NOUNROLL for (int i = 0; i < 8; i++)
                     if (inb(x + dx[i], y + dy[i])) smooth_trees_at_fx(fx, x + dx[i], y + dy[i], true);
                 result = TR_OK;
             } else {
@@ -546,8 +546,8 @@ MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.c
 MPN void plop_b_river(Env &e, int px, int py)
 {
     const int8_t lo[9] = { 3, 2, 1, 0, 0, 0, 1, 2, 3 };    // first non-empty column of each row
-    for (int x = 0; x < 9; x++)
-        for (int y = 0; y < 9; y++) {
+    MP_NOUNROLL for (int x = 0; x < 9; x++)
+        MP_NOUNROLL for (int y = 0; y < 9; y++) {
             int l = lo[y], h = 8 - l, ch = 0;
             if (x >= l && x <= h) ch = (x == l || x == h || y == 0 || y == 8) ? T_REDGE : T_RIVER;
             if (x == 4 && y == 4) ch = T_CHANNEL;
@@ -559,8 +559,8 @@ MPN void plop_b_river(Env &e, int px, int py)
 MPN void plop_s_river(Env &e, int px, int py)
 {
     const int8_t lo[6] = { 2, 1, 0, 0, 1, 2 };
-    for (int x = 0; x < 6; x++)
-        for (int y = 0; y < 6; y++) {
+    MP_NOUNROLL for (int x = 0; x < 6; x++)
+        MP_NOUNROLL for (int y = 0; y < 6; y++) {
             int l = lo[y], h = 5 - l, ch = 0;
             if (x >= l && x <= h) ch = (x == l || x == h || y == 0 || y == 5) ? T_REDGE : T_RIVER;
             put_on_map(e, ch, px + x, py + y);
@@ -589,11 +589,11 @@ MPN void smooth_river(Env &e)                                      // generate.c
     const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
         19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
         5 | BULLBIT, 2 };
-    for (int x = 0; x < WORLD_W; x++)
-        for (int y = 0; y < WORLD_H; y++)
+    MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
+        MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
             if (e.map[tix(x, y)] == T_REDGE) {
                 int bits = 0;
-                for (int z = 0; z < 4; z++) {
+                MP_NOUNROLL for (int z = 0; z < 4; z++) {
                     bits <<= 1;
                     int xx = x + dx[z], yy = y + dy[z];
                     if (inb(xx, yy)) {
@@ -611,11 +611,11 @@ MPN void smooth_trees(Env &e)                                      // generate.c
 {
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
-    for (int x = 0; x < WORLD_W; x++)
-        for (int y = 0; y < WORLD_H; y++)
+    MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
+        MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
             if (is_tree(e.map[tix(x, y)])) {
                 int bits = 0;
-                for (int z = 0; z < 4; z++) {
+                MP_NOUNROLL for (int z = 0; z < 4; z++) {
                     bits <<= 1;
                     int xx = x + dx[z], yy = y + dy[z];
                     if (inb(xx, yy) && is_tree(e.map[tix(xx, yy)])) bits++;
@@ -633,7 +633,7 @@ MPN void smooth_trees(Env &e)                                      // generate.c
 MPN void do_trees(Env &e)                                          // generate.cpp:330-348 (+ :299-324)
 {
     int16_t amount = (int16_t)(rnd(e, 100) + 50);          // terrainTreeLevel = -1
-    for (int16_t i = 0; i < amount; i++) {
+    MP_NOUNROLL for (int16_t i = 0; i < amount; i++) {
         int16_t xloc = rnd(e, WORLD_W - 1), yloc = rnd(e, WORLD_H - 1);
         int16_t numTrees = (int16_t)(rnd(e, 150) + 50);
         int tx = xloc, ty = yloc;
@@ -651,10 +651,10 @@ MPN void do_trees(Env &e)                                          // generate.c
 
 MPN void make_naked_island(Env &e)                                 // generate.cpp:193-231
 {
-    for (int x = 0; x < WORLD_W; x++)
-        for (int y = 0; y < WORLD_H; y++)
+    MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
+        MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
             e.map[tix(x, y)] = (x < 5 || x >= WORLD_W - 5 || y < 5 || y >= WORLD_H - 5) ? T_RIVER : T_DIRT;
-    for (int x = 0; x < WORLD_W - 5; x += 2) {
+    MP_NOUNROLL for (int x = 0; x < WORLD_W - 5; x += 2) {
         int my = ernd(e, 18);
         plop_b_river(e, x, my);
         my = (WORLD_H - 10) - ernd(e, 18);
@@ -662,7 +662,7 @@ MPN void make_naked_island(Env &e)                                 // generate.c
         plop_s_river(e, x, 0);
         plop_s_river(e, x, WORLD_H - 6);
     }
-    for (int y = 0; y < WORLD_H - 5; y += 2) {
+    MP_NOUNROLL for (int y = 0; y < WORLD_H - 5; y += 2) {
         int mx = ernd(e, 18);
         plop_b_river(e, mx, y);
         mx = (WORLD_W - 10) - ernd(e, 18);
@@ -683,7 +683,7 @@ MPN void generate_map(Env &e, int seed)
         do_trees(e);
         return;
     }
-    for (int i = 0; i < NTILES; i++) e.map[i] = T_DIRT;
+    MP_NOUNROLL for (int i = 0; i < NTILES; i++) e.map[i] = T_DIRT;
     {
         int xs = 40 + rnd(e, WORLD_W - 80), ys = 33 + rnd(e, WORLD_H - 67);
         // doRivers generate.cpp:478-495
