@@ -124,6 +124,8 @@ def run_ours(args):
     def step_dev(i):
         m._ck(m._L.mpb_env_step(m._h, acts[i].data_ptr(), 0, sp))
 
+    for i in range(args.age_steps):                 # untimed build-up: cities reach their random-action steady state
+        step_dev(i % (W + 2 * K + 2))
     for i in range(W):
         step_dev(i)
     torch.cuda.synchronize(dev)
@@ -214,6 +216,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--age-steps", type=int, default=40,
+                    help="untimed env-ticks before the warm-up so the random-action cities are in steady state")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,6 +29,7 @@ def _newer(target, deps):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    extra = os.environ.get("MPB_NVCC_EXTRA", "").split()      # e.g. -DMP_PROFILE_SPLIT for profiling builds
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     inc = os.path.join(HERE, "..", "include")
@@ -39,7 +40,7 @@ def build(force=False, verbose=False):
     procs = []
     for s in srcs:
         o = s[:-3] + ".o"
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", s, "-o", o]
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + extra + ["-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((subprocess.Popen(cmd), cmd))

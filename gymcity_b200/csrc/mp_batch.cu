@@ -111,18 +111,29 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
             int respect_passes)
 {
     __shared__ int red[8 * MP_EPC];
+    // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
+    // lane touches on almost every instruction: it lives in shared memory for the whole launch
+    __shared__ __align__(16) uint32_t s_scal[MP_EPC][(sizeof(Scalars) + 3) / 4];
     MP_ENV_GUARD();
     Env e;
     bind_device_env(e, blocks, anim, red);
+    Scalars *gs = e.s;
+    uint32_t *sw = s_scal[threadIdx.x >> 5];
+    for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
+    __syncwarp();
+    e.s = reinterpret_cast<Scalars *>(sw);
     if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     if (respect_passes) {
-        if (!e.s->simSpeed) return;
-        int last = first + count;
-        if (last > e.s->simPasses) last = e.s->simPasses;
-        for (int i = first; i < last; i++) sim_loop(e);
+        if (e.s->simSpeed) {
+            int last = first + count;
+            if (last > e.s->simPasses) last = e.s->simPasses;
+            for (int i = first; i < last; i++) sim_loop(e);
+        }
     } else {
         for (int i = 0; i < count; i++) sim_loop(e);
     }
+    __syncwarp();
+    for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
 }
 
 __global__ void __launch_bounds__(MP_THREADS)

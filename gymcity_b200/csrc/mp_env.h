@@ -56,6 +56,7 @@ MPD void init_will_stuff(Env &e)
 MPD void clear_map(Env &e)
 {
     for (int i = e.c.tid; i < NTILES; i += e.c.n) e.map[i] = T_DIRT;
+    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.act[i] = 0;
     e.c.sync();
 }
 
@@ -64,6 +65,7 @@ MPD void generate_some_city(Env &e, int terrain_seed, int sim_seed)
 {
     if (e.c.lead()) generate_map(e, terrain_seed);
     e.c.sync();
+    rebuild_active(e);              // the terrain generator writes tiles in bulk
     if (e.c.lead()) {
         S.scenario = 0; S.cityTime = 0; S.initSimLoad = 2; S.doInitialEval = 0;
     }
@@ -129,8 +131,8 @@ MPD void env_call(Env &e, int fn, int a, int b)
         if (lead) clear_census_scalars(e);
         for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
         break;
-    case FN_TAKE10: if (lead) take10_census(e); break;
-    case FN_TAKE120: if (lead) take120_census(e); break;
+    case FN_TAKE10: take10_census(e); break;
+    case FN_TAKE120: take120_census(e); break;
     case FN_COLLECT_TAX: if (lead) collect_tax(e); break;
     case FN_CITY_EVAL: if (lead) city_evaluation(e); break;
     case FN_SEND_MESSAGES: if (lead) send_messages(e); break;

@@ -104,11 +104,11 @@ MPD void push_power_stack(Env &e, int x, int y)          // power.cpp:163-169
 }
 
 // [LEAD] zone.cpp:419-437 setZonePower
-MPD bool set_zone_power(Env &e, int x, int y)
+MPP bool set_zone_power(Env &e, int x, int y)
 {
     int v = e.map[tix(x, y)], t = v & LOMASK;
     if (t == T_NUCLEAR || t == T_POWERPLANT || pwr_get(e, x, y)) {
-        e.map[tix(x, y)] = (uint16_t)(v | PWRBIT);
+        e.map[tix(x, y)] = (uint16_t)(v | PWRBIT);          // status bit only: activity unchanged
         return true;
     }
     e.map[tix(x, y)] = (uint16_t)(v & ~PWRBIT);
@@ -279,7 +279,7 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
     }
     MP_NOUNROLL for (int z = 0; z < 9; z++) {
         int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
-        if (inb(xx, yy)) e.map[tix(xx, yy)] = (uint16_t)(base + BNCNBIT);
+        if (inb(xx, yy)) mset(e, tix(xx, yy), (uint16_t)(base + BNCNBIT));
         base++;
     }
     set_zone_power(e, x, y);
@@ -334,7 +334,7 @@ MPD void build_house(Env &e, int x, int y, int value)
     }
     if (best) {
         int xx = x + zx[best], yy = y + zy[best];
-        if (inb(xx, yy)) e.map[tix(xx, yy)] = (uint16_t)(T_HOUSE + BLBNCNBIT + rnd(e, 2) + value * 3);
+        if (inb(xx, yy)) mset(e, tix(xx, yy), (uint16_t)(T_HOUSE + BLBNCNBIT + rnd(e, 2) + value * 3));
     }
 }
 
@@ -389,11 +389,11 @@ MPD void do_res_out(Env &e, int x, int y, int pop, int value)
     }
     if (pop == 16) {
         inc_rate_of_growth(e, x, y, -8);
-        e.map[tix(x, y)] = (uint16_t)(T_FREEZ | BLBNCNBIT | ZONEBIT);
+        mset(e, tix(x, y), (uint16_t)(T_FREEZ | BLBNCNBIT | ZONEBIT));
         MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
             MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) != T_FREEZ)
-                    e.map[tix(xx, yy)] = (uint16_t)(T_LHTHR + value + rnd(e, 2) + BLBNCNBIT);
+                    mset(e, tix(xx, yy), (uint16_t)(T_LHTHR + value + rnd(e, 2) + BLBNCNBIT));
     }
     if (pop < 16) {
         inc_rate_of_growth(e, x, y, -1);
@@ -403,7 +403,7 @@ MPD void do_res_out(Env &e, int x, int y, int pop, int value)
                 if (inb(xx, yy)) {
                     int loc = e.map[tix(xx, yy)] & LOMASK;
                     if (loc >= T_LHTHR && loc <= T_HHTHR) {
-                        e.map[tix(xx, yy)] = (uint16_t)(brdr[z] + BLBNCNBIT + T_FREEZ - 4);
+                        mset(e, tix(xx, yy), (uint16_t)(brdr[z] + BLBNCNBIT + T_FREEZ - 4));
                         return;
                     }
                 }
@@ -516,10 +516,10 @@ MPD void set_smoke(Env &e, int x, int y, bool zonePower)
     if (!inb(xx, yy)) return;
     if (zonePower) {
         if ((e.map[tix(xx, yy)] & LOMASK) == aniTabC[z])
-            e.map[tix(xx, yy)] = (uint16_t)((ANIMBIT | CONDBIT | BURNBIT) | (T_SMOKEBASE + aniTabB[z]));
+            mset(e, tix(xx, yy), (uint16_t)((ANIMBIT | CONDBIT | BURNBIT) | (T_SMOKEBASE + aniTabB[z])));
     } else {
         if ((e.map[tix(xx, yy)] & LOMASK) > aniTabC[z])
-            e.map[tix(xx, yy)] = (uint16_t)((CONDBIT | BURNBIT) | aniTabD[z]);
+            mset(e, tix(xx, yy), (uint16_t)((CONDBIT | BURNBIT) | aniTabD[z]));
     }
 }
 
@@ -571,7 +571,7 @@ MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
                 if (mv & ZONEBIT) continue;
                 if (mv & ANIMBIT) continue;
                 int mt = mv & LOMASK;
-                if (mt < T_RUBBLE || mt >= T_ROADBASE) e.map[tix(ax, ay)] = (uint16_t)(tile | CONDBIT | BURNBIT);
+                if (mt < T_RUBBLE || mt >= T_ROADBASE) mset(e, tix(ax, ay), (uint16_t)(tile | CONDBIT | BURNBIT));
             }
         }
 }
@@ -608,7 +608,7 @@ MPN void do_meltdown(Env &e, int x, int y)
         if (!inb(xx, yy)) continue;
         int t = e.map[tix(xx, yy)];
         if (t & ZONEBIT) continue;
-        if ((t & BURNBIT) || t == T_DIRT) e.map[tix(xx, yy)] = T_RADTILE;
+        if ((t & BURNBIT) || t == T_DIRT) mset(e, tix(xx, yy), T_RADTILE);
     }
 }
 
@@ -696,7 +696,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 }
 
 // [LEAD] zone.cpp:79-120 doZone
-MPD void do_zone(Env &e, int x, int y)
+MPP void do_zone(Env &e, int x, int y)
 {
     bool pw = set_zone_power(e, x, y);
     if (pw) S.poweredZoneCount++; else S.unpoweredZoneCount++;
@@ -737,7 +737,7 @@ MPN void do_fire(Env &e, int x, int y)
                     fire_zone(e, xx, yy, c);
                     if ((c & LOMASK) > T_IZB) make_explosion_at(e, xx * 16 + 8, yy * 16 + 8);
                 }
-                e.map[tix(xx, yy)] = (uint16_t)random_fire(e);
+                mset(e, tix(xx, yy), (uint16_t)random_fire(e));
             }
         }
     }
@@ -748,7 +748,7 @@ MPN void do_fire(Env &e, int x, int y)
         if (z > 20) rate = 2;
         if (z > 100) rate = 1;
     }
-    if (rnd(e, rate) == 0) e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+    if (rnd(e, rate) == 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
 }
 
 // [LEAD] disasters.cpp:375-405 doFlood
@@ -763,13 +763,13 @@ MPN void do_flood(Env &e, int x, int y)
                     int c = e.map[tix(xx, yy)], t = c & LOMASK;
                     if ((c & BURNBIT) == BURNBIT || c == T_DIRT || (t >= T_WOODS5 && t < T_FLOOD)) {
                         if ((c & ZONEBIT) == ZONEBIT) fire_zone(e, xx, yy, c);
-                        e.map[tix(xx, yy)] = (uint16_t)(T_FLOOD + rnd(e, 2));
+                        mset(e, tix(xx, yy), (uint16_t)(T_FLOOD + rnd(e, 2)));
                     }
                 }
             }
         }
     } else if ((rnd16(e) & 15) == 0) {
-        e.map[tix(x, y)] = T_DIRT;
+        mset(e, tix(x, y), T_DIRT);
     }
 }
 
@@ -792,7 +792,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
             MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + VDx[z], yy = y + VDy[z];
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (VBRTAB[z] & LOMASK))
-                    e.map[tix(xx, yy)] = (uint16_t)VBRTAB2[z];
+                    mset(e, tix(xx, yy), (uint16_t)VBRTAB2[z]);
             }
         return true;
     }
@@ -801,7 +801,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
             MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + HDx[z], yy = y + HDy[z];
                 if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (HBRTAB[z] & LOMASK))
-                    e.map[tix(xx, yy)] = (uint16_t)HBRTAB2[z];
+                    mset(e, tix(xx, yy), (uint16_t)HBRTAB2[z]);
             }
         return true;
     }
@@ -812,7 +812,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
                     int xx = x + VDx[z], yy = y + VDy[z];
                     if (inb(xx, yy)) {
                         int m = e.map[tix(xx, yy)];
-                        if (m == T_CHANNEL || ((m & 15) == (VBRTAB2[z] & 15))) e.map[tix(xx, yy)] = (uint16_t)VBRTAB[z];
+                        if (m == T_CHANNEL || ((m & 15) == (VBRTAB2[z] & 15))) mset(e, tix(xx, yy), (uint16_t)VBRTAB[z]);
                     }
                 }
                 return true;
@@ -824,7 +824,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
                     int xx = x + HDx[z], yy = y + HDy[z];
                     if (inb(xx, yy)) {
                         int m = e.map[tix(xx, yy)];
-                        if (((m & 15) == (HBRTAB2[z] & 15)) || m == T_CHANNEL) e.map[tix(xx, yy)] = (uint16_t)HBRTAB[z];
+                        if (((m & 15) == (HBRTAB2[z] & 15)) || m == T_CHANNEL) mset(e, tix(xx, yy), (uint16_t)HBRTAB[z]);
                     }
                 }
                 return true;
@@ -836,7 +836,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
 }
 
 // [LEAD] simulate.cpp:1048-1111 doRoad
-MPD void do_road(Env &e, int x, int y)
+MPP void do_road(Env &e, int x, int y)
 {
     const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
     S.roadTotal++;
@@ -845,8 +845,8 @@ MPD void do_road(Env &e, int x, int y)
         if ((rnd16(e) & 511) == 0) {
             if (!(mv & CONDBIT)) {
                 if (S.roadEffect < (rnd16(e) & 31)) {
-                    if ((tile & 15) < 2 || (tile & 15) == 15) e.map[tix(x, y)] = T_RIVER;
-                    else e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+                    if ((tile & 15) < 2 || (tile & 15) == 15) mset(e, tix(x, y), T_RIVER);
+                    else mset(e, tix(x, y), (uint16_t)random_rubble(e));
                     return;
                 }
             }
@@ -866,12 +866,12 @@ MPD void do_road(Env &e, int x, int y)
         int16_t z = (int16_t)(((tile - T_ROADBASE) & 15) + densityTable[td]);
         z |= mv & (ALLBITS - ANIMBIT);
         if (td > 0) z |= ANIMBIT;
-        e.map[tix(x, y)] = (uint16_t)z;
+        mset(e, tix(x, y), (uint16_t)z);
     }
 }
 
 // [LEAD] simulate.cpp:1005-1037 doRail
-MPD void do_rail(Env &e, int x, int y)
+MPP void do_rail(Env &e, int x, int y)
 {
     S.railTotal++;
     generate_train(e, x, y);
@@ -881,8 +881,8 @@ MPD void do_rail(Env &e, int x, int y)
             if (!(cv & CONDBIT)) {
                 if (S.roadEffect < (rnd16(e) & 31)) {
                     int t = cv & LOMASK;
-                    if (t < T_RAILBASE + 2) e.map[tix(x, y)] = T_RIVER;
-                    else e.map[tix(x, y)] = (uint16_t)random_rubble(e);
+                    if (t < T_RAILBASE + 2) mset(e, tix(x, y), T_RIVER);
+                    else mset(e, tix(x, y), (uint16_t)random_rubble(e));
                 }
             }
         }
@@ -890,10 +890,9 @@ MPD void do_rail(Env &e, int x, int y)
 }
 
 // ------------------------------------------------------------------ map scan
-MPD bool tile_is_active(int v) { return (v & LOMASK) >= T_FLOOD; }   // simulate.cpp:937-945
 
 // [LEAD] simulate.cpp:929-997 body of mapScan for one tile
-MPD void scan_tile(Env &e, int idx)
+MPP void scan_tile(Env &e, int idx)
 {
     int mv = e.map[idx], tile = mv & LOMASK;
     int x = idx / WORLD_H, y = idx - x * WORLD_H;
@@ -904,85 +903,108 @@ MPD void scan_tile(Env &e, int idx)
             return;
         }
         if (tile < T_RADTILE) do_flood(e, x, y);
-        else if ((rnd16(e) & 4095) == 0) e.map[idx] = T_DIRT;        // doRadTile :1040-1045
+        else if ((rnd16(e) & 4095) == 0) mset(e, idx, T_DIRT);        // doRadTile :1040-1045
         return;
     }
     if (S.newPower && (mv & CONDBIT)) set_zone_power(e, x, y);
     if (tile >= T_ROADBASE && tile < T_POWERBASE) { do_road(e, x, y); return; }
     if (mv & ZONEBIT) { do_zone(e, x, y); return; }
     if (tile >= T_RAILBASE && tile < T_RESBASE) { do_rail(e, x, y); return; }
-    if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) e.map[idx] = (uint16_t)random_rubble(e);
+    if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) mset(e, idx, (uint16_t)random_rubble(e));
 }
 
 // [ALL] mapScan(x1, x2).  The scan order is linear memory order (x outer, y inner over the
-// column-major map).  Device: each lane looks at 8 consecutive tiles with one 128-bit load (256
-// tiles = 512 contiguous bytes per warp round), builds an 8-bit "the reference would not skip
-// this tile" mask, a ballot finds the first lane with work, and lane 0 processes that tile.  After
-// each processed tile every lane reloads its 8 tiles (L1 hits) and masks off what is already
-// behind the scan position, because processing may have changed tiles ahead of it (fire spread,
-// zonePlop, repairZone, ...).
-MPD unsigned active8(const uint16_t *map, int idx0, int lo, int hi)
-{
-#if defined(__CUDA_ARCH__)
-    const uint4 q = *reinterpret_cast<const uint4 *>(map + idx0);
-    const unsigned w[4] = { q.x, q.y, q.z, q.w };
-    unsigned m = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if ((w[k] & 0x3ffu) >= (unsigned)T_FLOOD) m |= 1u << (2 * k);
-        if (((w[k] >> 16) & 0x3ffu) >= (unsigned)T_FLOOD) m |= 2u << (2 * k);
-    }
-    // keep only tiles in [lo, hi)
-    int a = lo - idx0, b = hi - idx0;
-    if (a > 0) m &= (a >= 8) ? 0u : (0xffu << a);
-    if (b < 8) m &= (b <= 0) ? 0u : (0xffu >> (8 - b));
-    return m;
-#else
-    (void)map; (void)idx0; (void)lo; (void)hi;
-    return 0;
-#endif
-}
-
-MPD void map_scan(Env &e, int x1, int x2)
+// column-major map), and the reference skips every tile whose id is below FLOOD
+// (simulate.cpp:937-945) -- on a 16x16 build window that is ~98% of the 12 000 tiles.  The active-tile
+// bitmap (Env::act, maintained by mset) turns the scan into "find the next set bit": each lane
+// loads one 32-tile word of the range, a ballot finds the first word with work, lane 0 processes
+// that tile, and the words are re-read (L1 hits) because processing may have activated tiles ahead
+// of the scan position (fire spread, zonePlop, repairZone ...).  Tiles activated BEHIND the scan
+// position are not visited, exactly as in the reference's single forward sweep.
+MPP void map_scan(Env &e, int x1, int x2)
 {
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
+    const int w0 = i0 >> 5, w1 = (i1 - 1) >> 5;
+    int pos = i0;                                   // first tile not yet passed by the scan
 #if defined(__CUDA_ARCH__)
-    {
-        const int lane = e.c.tid;
-        MP_NOUNROLL for (int base = i0 & ~7; base < i1; base += 256) {
-            const int idx0 = base + lane * 8;
-            const bool ok = idx0 < i1;                  // NTILES is a multiple of 8: the load stays in the map
-            int pos = i0;                               // first tile not yet passed by the scan
-            unsigned m = ok ? active8(e.map, idx0, pos, i1) : 0u;
-            unsigned any = __ballot_sync(0xffffffffu, m != 0);
-            while (any) {
-                const int L = __ffs(any) - 1;
-                const unsigned mL = __shfl_sync(0xffffffffu, m, L);
-                const int t = base + L * 8 + (__ffs(mL) - 1);
-                if (lane == 0) scan_tile(e, t);
-                __syncwarp();
-                pos = t + 1;
-                m = ok ? active8(e.map, idx0, pos, i1) : 0u;
-                any = __ballot_sync(0xffffffffu, m != 0);
-            }
+    const int lane = e.c.tid;
+    MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
+        const int w = wb + lane;
+        for (;;) {
+            uint32_t m = (w <= w1) ? e.act[w] : 0u;
+            // keep tiles in [pos, i1)
+            const int lo = pos - w * 32, hi = i1 - w * 32;
+            if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
+            if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
+            const unsigned any = __ballot_sync(0xffffffffu, m != 0);
+            if (!any) break;
+            const int L = __ffs(any) - 1;
+            const uint32_t mL = __shfl_sync(0xffffffffu, m, L);
+            const int t = (wb + L) * 32 + (__ffs(mL) - 1);
+            if (lane == 0) scan_tile(e, t);
+            __syncwarp();
+            pos = t + 1;
         }
     }
 #else
-    for (int idx = i0; idx < i1; idx++)
-        if (tile_is_active(e.map[idx])) scan_tile(e, idx);
+    for (int w = w0; w <= w1; w++) {
+        for (;;) {
+            uint32_t m = e.act[w];
+            const int lo = pos - w * 32, hi = i1 - w * 32;
+            if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
+            if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
+            if (!m) break;
+            int b = 0;
+            while (!((m >> b) & 1u)) b++;
+            const int t = w * 32 + b;
+            scan_tile(e, t);
+            pos = t + 1;
+        }
+    }
 #endif
     e.c.sync();
 }
 
 // ------------------------------------------------------------------ phase 9: census, tax
-// [LEAD] simulate.cpp:712-780 take10Census
+// [ALL] history scroll shared by take10Census / take120Census: hist[x + 1] = hist[x] for x = hi..lo
+// on all six graphs at once (read everything, barrier, write).
+MPD void scroll_history(Env &e, int lo, int hi)
+{
+    int16_t *h[6] = { e.resHist, e.comHist, e.indHist, e.crimeHist, e.pollutionHist, e.moneyHist };
+    const int n = hi - lo + 1;                       // <= 119 entries per graph: 4 per lane
+    int16_t v[6][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int x = lo + e.c.tid + k * e.c.n;
+#pragma unroll
+        for (int g = 0; g < 6; g++) v[g][k] = (x <= hi) ? h[g][x] : (int16_t)0;
+    }
+    e.c.sync();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int x = lo + e.c.tid + k * e.c.n;
+        if (x <= hi) {
+#pragma unroll
+            for (int g = 0; g < 6; g++) h[g][x + 1] = v[g][k];
+        }
+    }
+    (void)n;
+    e.c.sync();
+}
+
+// [ALL] simulate.cpp:712-780 take10Census
 MPN void take10_census(Env &e)
 {
-    MP_NOUNROLL for (int x = 118; x >= 0; x--) {
+#if defined(__CUDA_ARCH__)
+    scroll_history(e, 0, 118);
+#else
+    for (int x = 118; x >= 0; x--) {
         e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
         e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
         e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
     }
+#endif
+    if (!e.c.lead()) return;
     e.resHist[0] = (int16_t)(S.resPop / 8);
     e.comHist[0] = S.comPop;
     e.indHist[0] = S.indPop;
@@ -1002,14 +1024,19 @@ MPN void take10_census(Env &e)
     if (S.churchPop == faithfulPop) S.needChurch = 0;
 }
 
-// [LEAD] simulate.cpp:784-826 take120Census
+// [ALL] simulate.cpp:784-826 take120Census
 MPN void take120_census(Env &e)
 {
-    MP_NOUNROLL for (int x = 238; x >= 120; x--) {
+#if defined(__CUDA_ARCH__)
+    scroll_history(e, 120, 238);
+#else
+    for (int x = 238; x >= 120; x--) {
         e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
         e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
         e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
     }
+#endif
+    if (!e.c.lead()) return;
     e.resHist[120] = (int16_t)(S.resPop / 8);
     e.comHist[120] = S.comPop;
     e.indHist[120] = S.indPop;
@@ -1107,16 +1134,32 @@ MPD uint8_t dec_traffic_cell(int z)
     if (z <= 24) return 0;
     return (uint8_t)(z > 200 ? z - 34 : z - 24);
 }
-MPD void dec_traffic_map(Env &e)
+MPD uint32_t dec_traffic_word(uint32_t v)
+{
+    if (v == 0) return 0;
+    return dec_traffic_cell(v & 0xff) | (dec_traffic_cell((v >> 8) & 0xff) << 8)
+        | (dec_traffic_cell((v >> 16) & 0xff) << 16) | ((uint32_t)dec_traffic_cell(v >> 24) << 24);
+}
+MPP void dec_traffic_map(Env &e)
 {
 #if defined(__CUDA_ARCH__)
-    uint32_t *w = reinterpret_cast<uint32_t *>(e.traffic);
-    for (int i = e.c.tid; i < N2 / 4; i += e.c.n) {
-        uint32_t v = w[i];
-        if (v == 0) continue;
-        uint32_t r = dec_traffic_cell(v & 0xff) | (dec_traffic_cell((v >> 8) & 0xff) << 8)
-            | (dec_traffic_cell((v >> 16) & 0xff) << 16) | ((uint32_t)dec_traffic_cell(v >> 24) << 24);
-        w[i] = r;
+    // 3000 cells (+8 zero pad bytes) = 188 uint4; all six loads of a lane are issued before any use
+    uint4 *q = reinterpret_cast<uint4 *>(e.traffic);
+    uint4 v[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int i = e.c.tid + k * 32;
+        v[k] = (i < 188) ? q[i] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        int i = e.c.tid + k * 32;
+        if (i < 188 && (v[k].x | v[k].y | v[k].z | v[k].w)) {
+            uint4 r;
+            r.x = dec_traffic_word(v[k].x); r.y = dec_traffic_word(v[k].y);
+            r.z = dec_traffic_word(v[k].z); r.w = dec_traffic_word(v[k].w);
+            q[i] = r;
+        }
     }
 #else
     for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic[i] = dec_traffic_cell(e.traffic[i]);
@@ -1124,7 +1167,7 @@ MPD void dec_traffic_map(Env &e)
 }
 
 // [ALL] simulate.cpp:356-385 decRateOfGrowthMap
-MPD void dec_rog_map(Env &e)
+MPP void dec_rog_map(Env &e)
 {
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int16_t z = e.rog[i];
@@ -1207,7 +1250,7 @@ MPN void power_scan_walk(Env &e)
 }
 
 // [ALL]
-MPD void do_power_scan(Env &e)
+MPP void do_power_scan(Env &e)
 {
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
     e.c.sync();
@@ -1476,7 +1519,7 @@ MPD void com_rate_map(Env &e, int cx, int cy)
 }
 
 // [ALL] scan.cpp:110-120 fireAnalysis
-MPD void fire_analysis(Env &e)
+MPP void fire_analysis(Env &e)
 {
     smooth_station(e, e.fireSt);
     smooth_station(e, e.fireSt);
@@ -1597,7 +1640,7 @@ MPN void city_evaluation(Env &e)
 
 // ------------------------------------------------------------------ the 16-phase cycle
 // [ALL] simulate.cpp:122-268 simulate
-MPD void simulate(Env &e)
+MPP void simulate(Env &e)
 {
     const int16_t spdPower[3] = { 2, 4, 5 }, spdPtlv[3] = { 2, 7, 17 }, spdCrime[3] = { 1, 8, 18 };
     const int16_t spdPop[3] = { 1, 9, 19 }, spdFire[3] = { 1, 10, 20 };
@@ -1608,6 +1651,8 @@ MPD void simulate(Env &e)
     e.c.sync();
     const int phase = S.phaseCycle;
     const int si = tclamp((int)S.simSpeed - 1, 0, 2);
+    const int cyc = S.simCycle;
+    const int ct = (int)(S.cityTime % 48);          // cityTime >= 0; one 64-bit remainder per frame
     switch (phase) {
     case 0:
         if (e.c.lead()) {
@@ -1627,34 +1672,32 @@ MPD void simulate(Env &e)
         map_scan(e, (phase - 1) * WORLD_W / 8, phase * WORLD_W / 8);
         break;
     case 9:
-        if (e.c.lead()) {
-            if (S.cityTime % 4 == 0) take10_census(e);
-            if (S.cityTime % 48 == 0) take120_census(e);
-            if (S.cityTime % 48 == 0) {
-                collect_tax(e);
-                city_evaluation(e);
-            }
+        if ((ct & 3) == 0) { take10_census(e); e.c.sync(); }       // 48 = 4 * 12
+        if (ct == 0) { take120_census(e); e.c.sync(); }
+        if (e.c.lead() && ct == 0) {
+            collect_tax(e);
+            city_evaluation(e);
         }
         break;
     case 10:
-        if (!(S.simCycle % 5)) dec_rog_map(e);
+        if (!(cyc % 5)) dec_rog_map(e);
         dec_traffic_map(e);
         if (e.c.lead()) send_messages(e);
         break;
     case 11:
-        if ((S.simCycle % spdPower[si]) == 0) {
+        if ((si == 2 ? cyc % 5 : cyc % spdPower[si]) == 0) {
             do_power_scan(e);
             if (e.c.lead()) S.newPower = 1;
         }
         break;
     case 12:
-        if ((S.simCycle % spdPtlv[si]) == 0) ptlv_scan(e);
+        if ((si == 2 ? cyc % 17 : cyc % spdPtlv[si]) == 0) ptlv_scan(e);
         break;
     case 13:
-        if ((S.simCycle % spdCrime[si]) == 0) crime_scan(e);
+        if ((si == 2 ? cyc % 18 : cyc % spdCrime[si]) == 0) crime_scan(e);
         break;
     case 14:
-        if ((S.simCycle % spdPop[si]) == 0) {
+        if ((si == 2 ? cyc % 19 : cyc % spdPop[si]) == 0) {
             int cx = S.cityCenterX, cy = S.cityCenterY;
             e.c.sync();
             pop_density_scan(e);
@@ -1662,7 +1705,7 @@ MPD void simulate(Env &e)
         }
         break;
     case 15:
-        if ((S.simCycle % spdFire[si]) == 0) fire_analysis(e);
+        if ((si == 2 ? cyc % 20 : cyc % spdFire[si]) == 0) fire_analysis(e);
         if (e.c.lead()) do_disasters(e);
         break;
     }
@@ -1743,12 +1786,22 @@ MPD void do_sim_init(Env &e)
     e.c.sync();
 }
 
-// [ALL] animate.cpp:204-219 animateTiles
-MPD void animate_tiles(Env &e)
+// [ALL] animate.cpp:204-219 animateTiles.  Each lane owns whole 32-tile words of the active
+// bitmap so that it can refresh them without a race.
+MPP void animate_tiles(Env &e)
 {
-    for (int i = e.c.tid; i < NTILES; i += e.c.n) {
-        int v = e.map[i];
-        if (v & ANIMBIT) e.map[i] = (uint16_t)(e.anim[v & LOMASK] | (v & ALLBITS));
+    MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
+        uint32_t m = 0;
+        MP_NOUNROLL for (int b = 0; b < 32; b++) {
+            const int i = w * 32 + b;
+            int v = e.map[i];
+            if (v & ANIMBIT) {
+                v = e.anim[v & LOMASK] | (v & ALLBITS);
+                e.map[i] = (uint16_t)v;
+            }
+            if (tile_is_active(v)) m |= 1u << b;
+        }
+        e.act[w] = m;
     }
     e.c.sync();
 }

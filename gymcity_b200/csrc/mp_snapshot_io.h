@@ -78,6 +78,13 @@ inline int snapshot_set_field(Env &e, int field, const void *in, int nbytes)
     void *p = snapshot_field_ptr(e, field, &n);
     if (!p || nbytes != n) return -1;
     memcpy(p, in, n);
+    if (field == MPF_MAP) {            // keep the derived active-tile bitmap in step
+        for (int w = 0; w < POWER_WORDS; w++) {
+            uint32_t m = 0;
+            for (int b = 0; b < 32; b++) if (tile_is_active(e.map[w * 32 + b])) m |= 1u << b;
+            e.act[w] = m;
+        }
+    }
     return 0;
 }
 

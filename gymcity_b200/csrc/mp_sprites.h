@@ -222,7 +222,7 @@ MPN void destroy_map_tile(Env &e, int ox, int oy)
     int16_t t = z & LOMASK;
     if (t >= T_TREEBASE) {
         if (!(z & BURNBIT)) {
-            if (t >= T_ROADBASE && t <= T_LASTROAD) e.map[tix(x, y)] = T_RIVER;
+            if (t >= T_ROADBASE && t <= T_LASTROAD) mset(e, tix(x, y), T_RIVER);
             return;
         }
         if (z & ZONEBIT) {
@@ -230,8 +230,8 @@ MPN void destroy_map_tile(Env &e, int ox, int oy)
             if (t > T_RZB) make_explosion_at(e, ox, oy);
         }
         bool wet = t == T_HPOWER || t == T_VPOWER || t == T_HRAIL || t == T_VRAIL || t == T_BRWH || t == T_BRWV;
-        if (wet) e.map[tix(x, y)] = T_RIVER;
-        else e.map[tix(x, y)] = (uint16_t)((S.doAnimation ? (int)T_TINYEXP : (T_LASTTINYEXP - 3)) | BULLBIT | ANIMBIT);
+        if (wet) mset(e, tix(x, y), T_RIVER);
+        else mset(e, tix(x, y), (uint16_t)((S.doAnimation ? (int)T_TINYEXP : (T_LASTTINYEXP - 3)) | BULLBIT | ANIMBIT));
     }
 }
 
@@ -243,7 +243,7 @@ MPD void start_fire(Env &e, int x, int y)
     int z = e.map[tix(x, y)], t = z & LOMASK;
     if (!(z & BURNBIT) && t != T_DIRT) return;
     if (z & ZONEBIT) return;
-    e.map[tix(x, y)] = (uint16_t)random_fire(e);
+    mset(e, tix(x, y), (uint16_t)random_fire(e));
 }
 
 // ------------------------------------------------------------------ per-type movement
@@ -660,8 +660,8 @@ MPN void make_earthquake(Env &e)
     MP_NOUNROLL for (int16_t z = 0; z < strength; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
         if (vulnerable(e.map[tix(x, y)])) {
-            if ((z & 0x3) != 0) e.map[tix(x, y)] = (uint16_t)random_rubble(e);
-            else e.map[tix(x, y)] = (uint16_t)random_fire(e);
+            if ((z & 0x3) != 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
+            else mset(e, tix(x, y), (uint16_t)random_fire(e));
         }
     }
 }
@@ -673,7 +673,7 @@ MPN void set_fire(Env &e)
     int16_t z = (int16_t)e.map[tix(x, y)];
     if ((z & ZONEBIT) == 0) {
         z = z & LOMASK;
-        if (z > T_LHTHR && z < T_LASTZONE) e.map[tix(x, y)] = (uint16_t)random_fire(e);
+        if (z > T_LHTHR && z < T_LASTZONE) mset(e, tix(x, y), (uint16_t)random_fire(e));
     }
 }
 
@@ -690,7 +690,7 @@ MPN void make_flood(Env &e)
                 if (inb(xx, yy)) {
                     int16_t cc = (int16_t)e.map[tix(xx, yy)];
                     if (cc == T_DIRT || (cc & (BULLBIT | BURNBIT)) == (BULLBIT | BURNBIT)) {
-                        e.map[tix(xx, yy)] = T_FLOOD;
+                        mset(e, tix(xx, yy), T_FLOOD);
                         S.floodCount = 30;
                         return;
                     }

@@ -19,7 +19,15 @@
 // The serial lane is latency bound and its code footprint is what hurts (the engine is ~10x the SM
 // instruction caches): keep its loops rolled.
 #define MP_NOUNROLL _Pragma("unroll 1")
+// MPP: inlined in the product build, out of line when profiling (-DMP_PROFILE_SPLIT) so that ncu's
+// SASS samples can be attributed per engine function (tools/ncu_by_function.py).
+#if defined(MP_PROFILE_SPLIT)
+#define MPP __device__ __noinline__
 #else
+#define MPP __device__ __forceinline__
+#endif
+#else
+#define MPP inline
 #define MPD inline
 #define MPN inline
 #define MPH inline
@@ -85,6 +93,7 @@ struct Scalars {
     uint8_t enableDisasters, doAnimation, tilesAnimated, spriteOverflow;
     int16_t curMapStack[MAX_TRAFFIC_DISTANCE + 2];   // packed x*100+y, entries 1..pointer
 };
+static_assert(sizeof(Scalars) % 8 == 0, "Scalars is copied to shared memory word by word");
 
 // Byte offsets of one env's block.  Every section starts 16-byte aligned so it can be moved
 // with 128-bit loads / bulk copies.
@@ -118,7 +127,9 @@ struct EnvLayout {
     static constexpr int STMP = TMP3 + a16(N4);                     // int16[195]
     static constexpr int PSTACK = STMP + a16(N8 * 2);               // uint16[3000]
     static constexpr int OVERLAY = PSTACK + a16(POWER_STACK_SIZE * 2);  // tool overlay uint16[256]+mask
-    static constexpr int TOTAL = OVERLAY + 512 + 32;
+    // derived: one bit per tile, set iff mapScan would not skip it (tile id >= FLOOD)
+    static constexpr int ACTIVE = OVERLAY + 512 + 32;
+    static constexpr int TOTAL = ACTIVE + a16((POWER_WORDS + 1) * 4);
 };
 
 // Thread context.  Device: the WARP that owns the env (tid = lane, n = 32; a barrier is a
@@ -148,6 +159,7 @@ struct Env {
     int16_t *stmp;
     uint16_t *pstack;
     uint16_t *ovl;          // tool overlay: 256 values + 8 mask words
+    uint32_t *act;          // active-tile bitmap (derived from map, kept in step by mset)
     const uint16_t *anim;   // 1024-entry animation successor table
     Coop c;
 };
@@ -171,6 +183,7 @@ MPH void bind_env(Env &e, uint8_t *blk)
     e.stmp = (int16_t *)(blk + L::STMP);
     e.pstack = (uint16_t *)(blk + L::PSTACK);
     e.ovl = (uint16_t *)(blk + L::OVERLAY);
+    e.act = (uint32_t *)(blk + L::ACTIVE);
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -203,9 +216,31 @@ MPD void pwr_set(Env &e, int x, int y)
     int i = tix(x, y);
     e.power[i >> 5] |= 1u << (i & 31);
 }
+// Every tile store on the serial lane goes through mset so that the active-tile bitmap (bit set iff
+// tile id >= FLOOD, i.e. mapScan would look at the tile, simulate.cpp:937-945) never goes stale.
+// Stores that only flip status bits (|= BULLBIT, PWRBIT ...) leave the id and so the bit alone.
+MPH bool tile_is_active(int v) { return (v & LOMASK) >= T_FLOOD; }
+MPD void mset(Env &e, int idx, int v)
+{
+    e.map[idx] = (uint16_t)v;
+    const uint32_t bit = 1u << (idx & 31), w = e.act[idx >> 5];
+    const uint32_t nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
+    if (nw != w) e.act[idx >> 5] = nw;
+}
+// [ALL] recompute the whole bitmap from the map (after bulk writes: clearMap, terrain, animateTiles)
+MPD void rebuild_active(Env &e)
+{
+    for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++)
+            if (tile_is_active(e.map[w * 32 + b])) m |= 1u << b;
+        e.act[w] = m;
+    }
+    e.c.sync();
+}
 // bounds-safe tile store (the reference indexes map[x][y] unchecked in a few places that are
 // in-bounds for every reachable state; an out-of-range store is dropped here)
-MPD void tset(Env &e, int x, int y, int v) { if (inb(x, y)) e.map[tix(x, y)] = (uint16_t)v; }
+MPD void tset(Env &e, int x, int y, int v) { if (inb(x, y)) mset(e, tix(x, y), v); }
 MPD int tget(const Env &e, int x, int y) { return inb(x, y) ? e.map[tix(x, y)] : 0; }
 
 // ------------------------------------------------------------------ RNG (random.cpp:88-174)

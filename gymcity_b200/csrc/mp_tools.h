@@ -54,7 +54,7 @@ struct Fx {                 // one tool call's pending effects
         e.s->totalFunds = (int)(e.s->totalFunds - cost);
         const uint32_t *m = (const uint32_t *)(e.ovl + 256);
         MP_NOUNROLL for (int s = 0; s < 256; s++)
-            if ((m[s >> 5] >> (s & 31)) & 1u) e.map[tix(ox + (s >> 4), oy + (s & 15))] = e.ovl[s];
+            if ((m[s >> 5] >> (s & 31)) & 1u) mset(e, tix(ox + (s >> 4), oy + (s & 15)), e.ovl[s]);
     }
 };
 
@@ -539,7 +539,7 @@ MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.c
         if (temp == T_RIVER && ch != T_CHANNEL) return;
         if (temp == T_CHANNEL) return;
     }
-    e.map[tix(x, y)] = (uint16_t)ch;
+    mset(e, tix(x, y), (uint16_t)ch);
 }
 
 // generate.cpp:604-626 plopBRiver: 9x9 disc, REDGE rim, RIVER body, CHANNEL centre
@@ -603,7 +603,7 @@ MPN void smooth_river(Env &e)                                      // generate.c
                 }
                 int16_t temp = REdTab[bits & 15];
                 if (temp != T_RIVER && rnd(e, 1)) temp++;
-                e.map[tix(x, y)] = (uint16_t)temp;
+                mset(e, tix(x, y), (uint16_t)temp);
             }
 }
 
@@ -623,9 +623,9 @@ MPN void smooth_trees(Env &e)                                      // generate.c
                 int temp = treeTable[bits & 15];
                 if (temp) {
                     if (temp != T_WOODS && ((x + y) & 1)) temp -= 8;
-                    e.map[tix(x, y)] = (uint16_t)(temp | BLBNBIT);
+                    mset(e, tix(x, y), (uint16_t)(temp | BLBNBIT));
                 } else {
-                    e.map[tix(x, y)] = (uint16_t)temp;
+                    mset(e, tix(x, y), (uint16_t)temp);
                 }
             }
 }
@@ -641,7 +641,7 @@ MPN void do_trees(Env &e)                                          // generate.c
             int dir = D_N + rnd(e, 7);
             pos_move(tx, ty, dir);
             if (!inb(tx, ty)) break;
-            if ((e.map[tix(tx, ty)] & LOMASK) == T_DIRT) e.map[tix(tx, ty)] = (uint16_t)(T_WOODS | BLBNBIT);
+            if ((e.map[tix(tx, ty)] & LOMASK) == T_DIRT) mset(e, tix(tx, ty), (uint16_t)(T_WOODS | BLBNBIT));
             numTrees--;
         }
     }
@@ -653,7 +653,7 @@ MPN void make_naked_island(Env &e)                                 // generate.c
 {
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
         MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
-            e.map[tix(x, y)] = (x < 5 || x >= WORLD_W - 5 || y < 5 || y >= WORLD_H - 5) ? T_RIVER : T_DIRT;
+            mset(e, tix(x, y), (x < 5 || x >= WORLD_W - 5 || y < 5 || y >= WORLD_H - 5) ? T_RIVER : T_DIRT);
     MP_NOUNROLL for (int x = 0; x < WORLD_W - 5; x += 2) {
         int my = ernd(e, 18);
         plop_b_river(e, x, my);
@@ -683,7 +683,7 @@ MPN void generate_map(Env &e, int seed)
         do_trees(e);
         return;
     }
-    MP_NOUNROLL for (int i = 0; i < NTILES; i++) e.map[i] = T_DIRT;
+    MP_NOUNROLL for (int i = 0; i < NTILES; i++) mset(e, i, T_DIRT);
     {
         int xs = 40 + rnd(e, WORLD_W - 80), ys = 33 + rnd(e, WORLD_H - 67);
         // doRivers generate.cpp:478-495
