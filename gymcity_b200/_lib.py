@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgymcity_b200.so")
+LIB_PATH = os.environ.get("GYMCITY_B200_LIB", os.path.join(HERE, "libgymcity_b200.so"))   # override: perf variants
 
 _lib = None
 

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libgymcity_b200.so")
+LIB = os.environ.get("GYMCITY_B200_LIB", os.path.join(HERE, "libgymcity_b200.so"))
 SOURCES = ["gol.cu", "dlpack_export.cu", "mp_batch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in srcs:
-        o = s[:-3] + ".o"
+        o = s[:-3] + os.environ.get("MPB_OBJ_SUFFIX", "") + ".o"
         cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "-shared"] + extra + ["-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

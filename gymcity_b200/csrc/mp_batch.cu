@@ -36,6 +36,11 @@ struct MpBatch {
     char err[256];
     int passes;               // host copy of simPasses (corecontrol.py:129 sets 100)
     int frames_per_launch;    // simFrames per k_mp_frames launch (phase lockstep across the batch)
+    unsigned long long *cycles;   // [n_envs] SM cycles each env spent in k_mp_frames since the last read (profiling)
+    unsigned int *cost;       // [n_envs] cycles of the current step (schedule key for the next one)
+    int *perm;                // [n_envs] env ids, most expensive first
+    unsigned int *hist;       // [SCHED_BUCKETS + 1]
+    int use_sched;
     // gym layer (mpb_env_*)
     int configured, shadow_stride;
     GymCfg cfg;
@@ -106,17 +111,24 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
 // per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
-__global__ void __launch_bounds__(MP_THREADS)
+__global__ void __launch_bounds__(MP_THREADS, 24)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
-            int respect_passes)
+            int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm)
 {
+    const long long t_begin = clock64();
     __shared__ int red[8 * MP_EPC];
     // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
     // lane touches on almost every instruction: it lives in shared memory for the whole launch
     __shared__ __align__(16) uint32_t s_scal[MP_EPC][(sizeof(Scalars) + 3) / 4];
-    MP_ENV_GUARD();
+    // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
+    // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
+    const int slot = device_env_index();
+    if (slot >= n_envs) return;
+    const int env = perm ? perm[slot] : slot;
+    const int lane = threadIdx.x & 31;
     Env e;
-    bind_device_env(e, blocks, anim, red);
+    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
     Scalars *gs = e.s;
     uint32_t *sw = s_scal[threadIdx.x >> 5];
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
@@ -134,6 +146,11 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     }
     __syncwarp();
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
+    if (lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
+        if (cycles) cycles[env] += dt;
+        if (cost) cost[env] += (unsigned int)(dt >> 8);
+    }
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
@@ -158,6 +175,43 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
     case 3: s->enableDisasters = (uint8_t)v; break;
     default: break;
     }
+}
+
+constexpr int SCHED_BUCKETS = 1024;
+__device__ __forceinline__ int sched_bucket(unsigned int cost)      // cost = cycles >> 8 of one step
+{
+    unsigned int k = cost >> 9;                                      // 2^17 cycles per bucket
+    return SCHED_BUCKETS - 1 - (int)(k < (unsigned)SCHED_BUCKETS ? k : SCHED_BUCKETS - 1);   // expensive first
+}
+__global__ void k_mp_sched_identity(int *perm, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = i;
+}
+__global__ void k_mp_sched_hist(const unsigned int *cost, int n, unsigned int *hist)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&hist[sched_bucket(cost[i])], 1u);
+}
+__global__ void k_mp_sched_scan(unsigned int *hist)                  // exclusive prefix sum, one warp
+{
+    unsigned int carry = 0;
+    for (int base = 0; base < SCHED_BUCKETS; base += 32) {
+        unsigned int v = hist[base + threadIdx.x], x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)threadIdx.x >= o) x += y;
+        }
+        hist[base + threadIdx.x] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+}
+__global__ void k_mp_sched_scatter(unsigned int *cost, int n, unsigned int *hist, int *perm)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    perm[atomicAdd(&hist[sched_bucket(cost[i])], 1u)] = i;
+    cost[i] = 0;
 }
 
 __device__ __forceinline__ void bind_device_gym(Gym &gy, uint8_t *shadow, int stride, const GymCfg *cfg)
@@ -242,17 +296,30 @@ __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg,
 
 #define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
 
+// Rebuild the heavy-first order from the cycles the step that just ended cost each env
+// (bucket sort, most expensive bucket first), then clear the costs for the next step.
+int rebuild_schedule(MpBatch *b, cudaStream_t st)
+{
+    if (!b->use_sched) return 0;
+    cudaMemsetAsync(b->hist, 0, (SCHED_BUCKETS + 1) * 4, st);
+    k_mp_sched_hist<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->n_envs, b->hist);
+    k_mp_sched_scan<<<1, 32, 0, st>>>(b->hist);
+    k_mp_sched_scatter<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->n_envs, b->hist, b->perm);
+    return 0;
+}
+
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
 int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before)
 {
     const int F = b->frames_per_launch, P = b->passes;
     if (P <= 0) {
-        if (animate_before) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1);
+        if (animate_before) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL);
         return 0;
     }
     for (int f = 0; f < P; f += F)
         k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                                                      animate_before && f == 0, 1);
+                                                      animate_before && f == 0, 1, b->cycles, b->cost,
+                                                      b->use_sched ? b->perm : NULL);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
@@ -297,7 +364,10 @@ mpb_handle mpb_create(int n_envs, int device)
     MpBatch *b = (MpBatch *)calloc(1, sizeof(MpBatch));
     b->n_envs = n_envs; b->device = device;
     b->passes = 100;
-    b->frames_per_launch = 4;
+    b->frames_per_launch = 25;
+#if defined(MP_DENSE_BATCH)
+    if (const char *bm = getenv("MPB_BATCH_MIN")) { int v = atoi(bm); cudaMemcpyToSymbol(g_mp_batch_min, &v, sizeof(int)); }
+#endif
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
@@ -307,10 +377,19 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->i32_a, (size_t)n_envs * 16) == cudaSuccess
         && cudaMalloc(&b->i32_b, (size_t)n_envs * 16) == cudaSuccess
         && cudaMalloc(&b->mask, n_envs) == cudaSuccess
+        && cudaMalloc(&b->cycles, (size_t)n_envs * 8) == cudaSuccess
+        && cudaMalloc(&b->cost, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->hist, (SCHED_BUCKETS + 1) * 4) == cudaSuccess
         && cudaMallocHost(&b->host_blk, ENV_STRIDE) == cudaSuccess
         && cudaMallocHost(&b->host_i32, (size_t)n_envs * 16) == cudaSuccess;
     if (!ok) { mpb_destroy(b); return NULL; }
     cudaMemcpy(b->anim, anim, sizeof(anim), cudaMemcpyHostToDevice);
+    cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
+    cudaMemset(b->cost, 0, (size_t)n_envs * 4);
+    b->use_sched = 1;
+    if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
+    k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
     k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS>>>(b->blocks, b->anim, n_envs);
     if (cudaDeviceSynchronize() != cudaSuccess) { mpb_destroy(b); return NULL; }
     return b;
@@ -321,6 +400,7 @@ void mpb_destroy(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return;
     cudaSetDevice(b->device);
+    cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
     cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
     if (b->host_blk) cudaFreeHost(b->host_blk);
@@ -460,7 +540,8 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     const int F = b->frames_per_launch;
     for (int f = 0; f < n; f += F)
         k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0,
-                                                                        (n - f < F) ? n - f : F, 0, 0);
+                                                                        (n - f < F) ? n - f : F, 0, 0, b->cycles,
+                                                                        b->cost, b->use_sched ? b->perm : NULL);
     CK(cudaGetLastError());
     return 0;
 }
@@ -481,7 +562,7 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     if (!b) return -1;
     cudaSetDevice(b->device);
     launch_sim_tick(b, (cudaStream_t)stream, 0);
-    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1);
+    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL);
     CK(cudaGetLastError());
     return 0;
 }
@@ -493,6 +574,17 @@ int mpb_call(mpb_handle h, int fn, int a, int bb, void *stream)
     cudaSetDevice(b->device);
     k_mp_call<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, fn, a, bb);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int mpb_read_cycles(mpb_handle h, unsigned long long *out_host)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !out_host) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_host, b->cycles, (size_t)b->n_envs * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(b->cycles, 0, (size_t)b->n_envs * 8));
     return 0;
 }
 
@@ -690,6 +782,7 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     launch_control_sim_tick(b, st);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                     b->obs, b->reward, b->done, 0, NULL);
+    rebuild_schedule(b, st);
     CK(cudaGetLastError());
     return 0;
 }

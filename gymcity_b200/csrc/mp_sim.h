@@ -696,7 +696,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 }
 
 // [LEAD] zone.cpp:79-120 doZone
-MPP void do_zone(Env &e, int x, int y)
+MPQ void do_zone(Env &e, int x, int y)
 {
     bool pw = set_zone_power(e, x, y);
     if (pw) S.poweredZoneCount++; else S.unpoweredZoneCount++;
@@ -836,7 +836,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
 }
 
 // [LEAD] simulate.cpp:1048-1111 doRoad
-MPP void do_road(Env &e, int x, int y)
+MPQ void do_road(Env &e, int x, int y)
 {
     const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
     S.roadTotal++;
@@ -871,7 +871,7 @@ MPP void do_road(Env &e, int x, int y)
 }
 
 // [LEAD] simulate.cpp:1005-1037 doRail
-MPP void do_rail(Env &e, int x, int y)
+MPQ void do_rail(Env &e, int x, int y)
 {
     S.railTotal++;
     generate_train(e, x, y);
@@ -921,6 +921,120 @@ MPP void scan_tile(Env &e, int idx)
 // that tile, and the words are re-read (L1 hits) because processing may have activated tiles ahead
 // of the scan position (fire spread, zonePlop, repairZone ...).  Tiles activated BEHIND the scan
 // position are not visited, exactly as in the reference's single forward sweep.
+// Tile classes for the warp-parallel part of the scan.  Most tiles the scan visits are cheap and
+// touch nothing but themselves: building tiles that are not the zone centre (at most a
+// setZonePower), plain roads (census + traffic art), receding flood water, radioactive waste,
+// fire that does not spread this time, tiny explosions turning to rubble.  They need at most ONE
+// draw each, so a whole 32-tile word is processed at once: lane b takes tile b, the draws are
+// handed out in scan order by LCG jump-ahead, and the batch stops in front of the first tile that
+// needs the serial lane (zones, bridges, rails, spreading fire, active flooding).
+enum : int { TK_SERIAL = 0, TK_INERT, TK_ROAD, TK_FLOOD0, TK_RAD, TK_FIRE, TK_TINYEXP };
+
+MPD int tile_kind(const Env &e, int v)
+{
+    const int t = v & LOMASK;
+    if (t < T_ROADBASE) {
+        if (t >= T_FIREBASE) return TK_FIRE;
+        if (t < T_RADTILE) return S.floodCount > 0 ? (int)TK_SERIAL : (int)TK_FLOOD0;
+        return TK_RAD;          // 52..55: doRadTile
+    }
+    if (t < T_POWERBASE) {
+        if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16) || !(v & BURNBIT)) return TK_SERIAL;   // decay draw / bridge
+        return TK_ROAD;
+    }
+    if (v & ZONEBIT) return TK_SERIAL;
+    if (t >= T_RAILBASE && t < T_RESBASE) return TK_SERIAL;     // doRail: conditional draw
+    if (t >= T_SOMETINYEXP && t <= T_LASTTINYEXP) return TK_TINYEXP;
+    return TK_INERT;
+}
+
+#if defined(__CUDACC__) && defined(MP_DENSE_BATCH)
+// EXPERIMENTAL (off by default, -DMP_DENSE_BATCH): lane-parallel processing of dense 32-tile words.
+// Bit-exact (GPU suite passes with it on) but its call site in the sparse scan loop costs ~12% on
+// typical cities, see profiles/r01_notes.md.
+// tunable (MPB_BATCH_MIN): minimum number of unscanned active tiles in a word for the lane-parallel path
+__device__ int g_mp_batch_min = 8;
+#define MP_BATCH_MIN g_mp_batch_min
+#endif
+#if defined(__CUDA_ARCH__) && defined(MP_DENSE_BATCH)
+// [ALL lanes] one dense 32-tile word: lane b takes tile b of word `wi` (bits of mL, already limited
+// to the unscanned part of the range).  Returns the scan position after the batch: either the tile
+// the batch had to stop in front of (the caller gives it to the serial lane) or the next word.
+// Out of line on purpose: it is the rare path and must not bloat the sparse scan loop.
+MPN int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
+{
+    const int lane = e.c.tid;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool mine = (mL >> lane) & 1u;
+    const int t = wi * 32 + lane;
+    int v = mine ? e.map[t] : 0;
+    const int kind = mine ? tile_kind(e, v) : (int)TK_INERT;
+    const unsigned serial = __ballot_sync(0xffffffffu, mine && kind == TK_SERIAL);
+    int stop = serial ? __ffs(serial) - 1 : 32;             // batch = my tiles below `stop`
+    const bool draws = mine && lane < stop && kind >= TK_FLOOD0;
+    const unsigned dmask = __ballot_sync(0xffffffffu, draws);
+    int r = 0;
+    if (draws) {
+        uint32_t x = S.rng;
+        const int k = __popc(dmask & lt);
+        MP_NOUNROLL for (int q = 0; q <= k; q++) x = x * 1103515245u + 12345u;
+        r = (int)((x & 0xffff00u) >> 8) & 0xffff;
+    }
+    // a fire tile whose draw says "spread" (1 in 4) goes to the serial lane: the batch ends there
+    const unsigned spread = __ballot_sync(0xffffffffu, draws && kind == TK_FIRE && !(r & 3));
+    if (spread) stop = min(stop, __ffs(spread) - 1);
+    const bool batch = mine && lane < stop;
+    bool still = true, heavy = false;
+    if (batch) {
+        if (kind <= TK_ROAD) {
+            if (S.newPower && (v & CONDBIT)) {              // setZonePower (zone.cpp:419-437)
+                const int id = v & LOMASK;
+                const bool on = id == T_NUCLEAR || id == T_POWERPLANT || ((e.power[t >> 5] >> (t & 31)) & 1u);
+                const int nv = on ? (v | PWRBIT) : (v & ~PWRBIT);
+                if (nv != v) { v = nv; e.map[t] = (uint16_t)v; }
+            }
+            if (kind == TK_ROAD) {                          // doRoad (simulate.cpp:1048-1111)
+                const int tile = v & LOMASK;
+                int tden = tile < T_LTRFBASE ? 0 : (tile < T_HTRFBASE ? 1 : 2);
+                heavy = tden == 2;
+                const int tx = t / WORLD_H, ty = t - tx * WORLD_H;
+                int td = e.traffic[(tx >> 1) * H2 + (ty >> 1)] >> 6;
+                if (td > 1) td--;
+                if (tden != td) {
+                    int z = ((tile - T_ROADBASE) & 15) + (td == 0 ? (int)T_ROADBASE : (td == 1 ? (int)T_LTRFBASE : (int)T_HTRFBASE));
+                    z |= v & (ALLBITS - ANIMBIT);
+                    if (td > 0) z |= ANIMBIT;
+                    e.map[t] = (uint16_t)z;
+                }
+            }
+        } else if (kind == TK_FLOOD0) {                     // doFlood, floodCount == 0
+            if ((r & 15) == 0) { e.map[t] = T_DIRT; still = false; }
+        } else if (kind == TK_RAD) {                        // doRadTile
+            if ((r & 4095) == 0) { e.map[t] = T_DIRT; still = false; }
+        } else if (kind == TK_TINYEXP) {                    // tiny explosion -> rubble
+            e.map[t] = (uint16_t)((T_RUBBLE + (r & 3)) | BULLBIT);
+            still = false;
+        }                                                   // TK_FIRE without spread: firePop++ only
+    }
+    const unsigned gone = __ballot_sync(0xffffffffu, batch && !still);
+    const int roads = __popc(__ballot_sync(0xffffffffu, batch && kind == TK_ROAD))
+        + __popc(__ballot_sync(0xffffffffu, batch && heavy));
+    const int fires = __popc(__ballot_sync(0xffffffffu, batch && kind == TK_FIRE));
+    if (lane == 0) {
+        if (gone) e.act[wi] &= ~gone;
+        if (roads) S.roadTotal = (int16_t)(S.roadTotal + roads);
+        if (fires) S.firePop = (int16_t)(S.firePop + fires);
+        const int nd = __popc(dmask & (stop >= 32 ? 0xffffffffu : ((1u << stop) - 1u)));
+        uint32_t x = S.rng;
+        MP_NOUNROLL for (int q = 0; q < nd; q++) x = x * 1103515245u + 12345u;
+        S.rng = x;
+    }
+    __syncwarp();
+    serial_next = stop < 32 && ((mL >> stop) & 1u);
+    return serial_next ? wi * 32 + stop : (wi + 1) * 32;
+}
+#endif
+
 MPP void map_scan(Env &e, int x1, int x2)
 {
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
@@ -939,11 +1053,19 @@ MPP void map_scan(Env &e, int x1, int x2)
             const unsigned any = __ballot_sync(0xffffffffu, m != 0);
             if (!any) break;
             const int L = __ffs(any) - 1;
-            const uint32_t mL = __shfl_sync(0xffffffffu, m, L);
-            const int t = (wb + L) * 32 + (__ffs(mL) - 1);
-            if (lane == 0) scan_tile(e, t);
+            const uint32_t mL = __shfl_sync(0xffffffffu, m, L);     // the word being worked on
+            int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
+#if defined(MP_DENSE_BATCH)
+            if (__popc(mL) >= MP_BATCH_MIN) {
+                // dense word (flood / radiation / fire fields, road grids, rows of buildings)
+                bool serial_next;
+                t1 = scan_word_batch(e, wb + L, mL, serial_next);
+                if (!serial_next) { pos = t1; continue; }
+            }
+#endif
+            if (lane == 0) scan_tile(e, t1);
             __syncwarp();
-            pos = t + 1;
+            pos = t1 + 1;
         }
     }
 #else
@@ -1134,16 +1256,11 @@ MPD uint8_t dec_traffic_cell(int z)
     if (z <= 24) return 0;
     return (uint8_t)(z > 200 ? z - 34 : z - 24);
 }
-MPD uint32_t dec_traffic_word(uint32_t v)
-{
-    if (v == 0) return 0;
-    return dec_traffic_cell(v & 0xff) | (dec_traffic_cell((v >> 8) & 0xff) << 8)
-        | (dec_traffic_cell((v >> 16) & 0xff) << 16) | ((uint32_t)dec_traffic_cell(v >> 24) << 24);
-}
-MPP void dec_traffic_map(Env &e)
+MPN void dec_traffic_map(Env &e)
 {
 #if defined(__CUDA_ARCH__)
-    // 3000 cells (+8 zero pad bytes) = 188 uint4; all six loads of a lane are issued before any use
+    // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit lane with byte-SIMD:
+    // z - (z > 200 ? 34 : 24) saturated at 0 is exactly the reference's three-way rule.
     uint4 *q = reinterpret_cast<uint4 *>(e.traffic);
     uint4 v[6];
 #pragma unroll
@@ -1156,8 +1273,10 @@ MPP void dec_traffic_map(Env &e)
         int i = e.c.tid + k * 32;
         if (i < 188 && (v[k].x | v[k].y | v[k].z | v[k].w)) {
             uint4 r;
-            r.x = dec_traffic_word(v[k].x); r.y = dec_traffic_word(v[k].y);
-            r.z = dec_traffic_word(v[k].z); r.w = dec_traffic_word(v[k].w);
+            r.x = __vsubus4(v[k].x, (__vcmpgtu4(v[k].x, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+            r.y = __vsubus4(v[k].y, (__vcmpgtu4(v[k].y, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+            r.z = __vsubus4(v[k].z, (__vcmpgtu4(v[k].z, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+            r.w = __vsubus4(v[k].w, (__vcmpgtu4(v[k].w, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
             q[i] = r;
         }
     }
@@ -1167,7 +1286,7 @@ MPP void dec_traffic_map(Env &e)
 }
 
 // [ALL] simulate.cpp:356-385 decRateOfGrowthMap
-MPP void dec_rog_map(Env &e)
+MPN void dec_rog_map(Env &e)
 {
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int16_t z = e.rog[i];
@@ -1250,7 +1369,7 @@ MPN void power_scan_walk(Env &e)
 }
 
 // [ALL]
-MPP void do_power_scan(Env &e)
+MPN void do_power_scan(Env &e)
 {
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
     e.c.sync();
@@ -1260,7 +1379,7 @@ MPP void do_power_scan(Env &e)
 
 // ------------------------------------------------------------------ smoothing passes
 // [ALL] scan.cpp:551-575 smoothDitherMap, non-dither branch (donDither = 0 on this path)
-MPD void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
+MPN void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
 {
     for (int i = e.c.tid; i < N2; i += e.c.n) {
         int x = i / H2, y = i - x * H2;
@@ -1277,7 +1396,7 @@ MPD void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
 }
 
 // [ALL] scan.cpp:80-105 smoothStationMap (in place through a temporary copy)
-MPD void smooth_station(Env &e, int16_t *m)
+MPN void smooth_station(Env &e, int16_t *m)
 {
     for (int i = e.c.tid; i < N8; i += e.c.n) e.stmp[i] = m[i];
     e.c.sync();
@@ -1507,7 +1626,7 @@ MPN void pop_density_scan(Env &e)
 }
 
 // [ALL] helper so that computeComRateMap sees the centre the reference saw
-MPD void com_rate_map(Env &e, int cx, int cy)
+MPN void com_rate_map(Env &e, int cx, int cy)
 {
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int x = (i / H8) * 8, y = (i % H8) * 8;
@@ -1519,7 +1638,7 @@ MPD void com_rate_map(Env &e, int cx, int cy)
 }
 
 // [ALL] scan.cpp:110-120 fireAnalysis
-MPP void fire_analysis(Env &e)
+MPN void fire_analysis(Env &e)
 {
     smooth_station(e, e.fireSt);
     smooth_station(e, e.fireSt);
@@ -1727,7 +1846,10 @@ MPN void sim_loop(Env &e)
         e.c.sync();
     }
     if (run) simulate(e);
-    if (e.c.lead()) move_objects(e);
+    if (e.c.lead()) {
+        if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }      // moveObjects with an empty list
+        else move_objects(e);
+    }
     e.c.sync();
 }
 
@@ -1788,7 +1910,7 @@ MPD void do_sim_init(Env &e)
 
 // [ALL] animate.cpp:204-219 animateTiles.  Each lane owns whole 32-tile words of the active
 // bitmap so that it can refresh them without a race.
-MPP void animate_tiles(Env &e)
+MPN void animate_tiles(Env &e)
 {
     MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
         uint32_t m = 0;

@@ -26,7 +26,14 @@
 #else
 #define MPP __device__ __forceinline__
 #endif
+// MPQ: per-tile dispatch targets; out of line unless -DMP_INLINE_TILE
+#if defined(MP_INLINE_TILE)
+#define MPQ __device__ __forceinline__
 #else
+#define MPQ __device__ __noinline__
+#endif
+#else
+#define MPQ inline
 #define MPP inline
 #define MPD inline
 #define MPN inline

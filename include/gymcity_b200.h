@@ -84,6 +84,9 @@ int mpb_env_stride(void);            /* bytes between consecutive env blocks in 
 int mpb_state_bytes(void);           /* bytes of persistent state per env (without scratch)     */
 void *mpb_blocks(mpb_handle h);      /* borrowed device pointer to the env blocks               */
 int mpb_sync(mpb_handle h);
+/* Profiling: SM cycles each env's warp spent simulating since the last call (uint64 [n_envs] HOST);
+ * max / mean shows the load imbalance a launch has to wait out. */
+int mpb_read_cycles(mpb_handle h, unsigned long long *out_host);
 
 /* Micropolis::seedRandom per env (random.cpp:171-174); seeds_host = int32 [n_envs] HOST. */
 int mpb_seed(mpb_handle h, const int32_t *seeds_host, void *stream);
