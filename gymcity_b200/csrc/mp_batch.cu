@@ -111,7 +111,7 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
 // per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
-__global__ void __launch_bounds__(MP_THREADS, 24)
+__global__ void __launch_bounds__(MP_THREADS, 16)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm)
 {

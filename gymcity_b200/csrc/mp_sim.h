@@ -257,7 +257,7 @@ MPD void inc_rate_of_growth(Env &e, int x, int y, int amount)      // zone.cpp:3
     s8set(e.rog, x, y, v);
 }
 
-MPD int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:271-293
+MPN int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:271-293
 {
     int16_t lv = (int16_t)b2get(e.landval, x, y);
     lv = (int16_t)(lv - b2get(e.pollution, x, y));
@@ -318,7 +318,7 @@ MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:4
 }
 
 // [LEAD] zone.cpp:444-484 buildHouse
-MPD void build_house(Env &e, int x, int y, int value)
+MPN void build_house(Env &e, int x, int y, int value)
 {
     const int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
     int16_t best = 0, hscore = 0;
@@ -355,7 +355,7 @@ MPD void ind_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:1
 }
 
 // [LEAD] zone.cpp:596-630 doResIn
-MPD void do_res_in(Env &e, int x, int y, int pop, int value)
+MPN void do_res_in(Env &e, int x, int y, int pop, int value)
 {
     if (b2get(e.pollution, x, y) > 128) return;
     int t = e.map[tix(x, y)] & LOMASK;
@@ -378,7 +378,7 @@ MPD void do_res_in(Env &e, int x, int y, int pop, int value)
 }
 
 // [LEAD] zone.cpp:639-704 doResOut
-MPD void do_res_out(Env &e, int x, int y, int pop, int value)
+MPN void do_res_out(Env &e, int x, int y, int pop, int value)
 {
     const int8_t brdr[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
     if (!pop) return;
@@ -413,7 +413,7 @@ MPD void do_res_out(Env &e, int x, int y, int pop, int value)
 }
 
 // [LEAD] zone.cpp:240-264 makeHospital
-MPD void make_hospital(Env &e, int x, int y)
+MPN void make_hospital(Env &e, int x, int y)
 {
     if (S.needHospital > 0) {
         zone_plop(e, x, y, T_HOSPITAL - 4);
@@ -501,7 +501,7 @@ MPN void do_commercial(Env &e, int x, int y, bool zonePower)
 }
 
 // [LEAD] zone.cpp:187-232 setSmoke
-MPD void set_smoke(Env &e, int x, int y, bool zonePower)
+MPN void set_smoke(Env &e, int x, int y, bool zonePower)
 {
     const uint8_t aniThis[8] = { 1, 0, 1, 1, 0, 0, 1, 1 };
     const int8_t dx1[8] = { -1, 0, 1, 0, 0, 0, 0, 1 }, dy1[8] = { -1, 0, -1, -1, 0, 0, -1, -1 };
@@ -577,7 +577,7 @@ MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
 }
 
 // [LEAD] zone.cpp:127-180 doHospitalChurch
-MPD void do_hospital_church(Env &e, int x, int y)
+MPN void do_hospital_church(Env &e, int x, int y)
 {
     int t = e.map[tix(x, y)] & LOMASK;
     if (t == T_HOSPITAL) {
@@ -710,7 +710,7 @@ MPQ void do_zone(Env &e, int x, int y)
 
 // ------------------------------------------------------------------ fire / flood / radiation
 // [LEAD] simulate.cpp:1336-1381 fireZone (also disasters.cpp doFlood)
-MPD void fire_zone(Env &e, int x, int y, int ch)
+MPN void fire_zone(Env &e, int x, int y, int ch)
 {
     int v = tclamp(s8get(e.rog, x, y) - 20, -200, 200);
     s8set(e.rog, x, y, v);
@@ -1771,7 +1771,6 @@ MPP void simulate(Env &e)
     const int phase = S.phaseCycle;
     const int si = tclamp((int)S.simSpeed - 1, 0, 2);
     const int cyc = S.simCycle;
-    const int ct = (int)(S.cityTime % 48);          // cityTime >= 0; one 64-bit remainder per frame
     switch (phase) {
     case 0:
         if (e.c.lead()) {
@@ -1790,7 +1789,8 @@ MPP void simulate(Env &e)
     case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
         map_scan(e, (phase - 1) * WORLD_W / 8, phase * WORLD_W / 8);
         break;
-    case 9:
+    case 9: {
+        const int ct = (int)((uint32_t)S.cityTime % 48u);  // cityTime >= 0 and far below 2^32 on any rollout
         if ((ct & 3) == 0) { take10_census(e); e.c.sync(); }       // 48 = 4 * 12
         if (ct == 0) { take120_census(e); e.c.sync(); }
         if (e.c.lead() && ct == 0) {
@@ -1798,6 +1798,7 @@ MPP void simulate(Env &e)
             city_evaluation(e);
         }
         break;
+    }
     case 10:
         if (!(cyc % 5)) dec_rog_map(e);
         dec_traffic_map(e);
@@ -1837,10 +1838,11 @@ MPP void simulate(Env &e)
 MPN void sim_loop(Env &e)
 {
     bool run = false;
-    if (S.simSpeed != 0) {
+    const int speed = S.simSpeed;
+    if (speed != 0) {
         int sc = S.speedCycle + 1;
         if (sc > 1023) sc = 0;
-        run = !((S.simSpeed == 1 && (sc % 5) != 0) || (S.simSpeed == 2 && (sc % 3) != 0));
+        run = speed >= 3 || !((speed == 1 && (sc % 5) != 0) || (speed == 2 && (sc % 3) != 0));
         e.c.sync();
         if (e.c.lead()) S.speedCycle = (int16_t)sc;
         e.c.sync();

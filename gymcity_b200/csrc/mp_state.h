@@ -265,16 +265,22 @@ MPD int rnd16s(Env &e)
     if (i > 0x7fff) i = 0x7fff - i;
     return i;
 }
+// getRandom(range): the rejection loop lives out of line once; the inline wrapper only folds the
+// (almost always constant) range into the two numbers the loop needs.
+MPN int16_t rnd_reject(Env &e, int range1, int maxMultiple)
+{
+    int r;
+    do {
+        r = rnd16(e);
+    } while (r >= maxMultiple);
+    return (int16_t)(r % range1);
+}
 MPD int16_t rnd(Env &e, int16_t range)
 {
     range++;
     int maxMultiple = 0xffff / range;
     maxMultiple *= range;
-    int r;
-    do {
-        r = rnd16(e);
-    } while (r >= maxMultiple);
-    return (int16_t)(r % range);
+    return rnd_reject(e, range, maxMultiple);
 }
 MPD int16_t ernd(Env &e, int16_t limit)
 {
