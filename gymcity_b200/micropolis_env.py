@@ -40,14 +40,7 @@ MPB_ENV_OBS, MPB_ENV_REWARD, MPB_ENV_DONE = 0, 1, 2
 METRICS = ['res_pop', 'com_pop', 'ind_pop', 'traffic', 'num_plants', 'mayor_rating']
 
 
-def _mix(*vals):
-    """splitmix-style hash of integers -> 31-bit seed (host side, deterministic)."""
-    h = 0x9e3779b97f4a7c15
-    for v in vals:
-        h ^= (int(v) + 0x9e3779b97f4a7c15 + ((h << 6) & 0xffffffffffffffff) + (h >> 2)) & 0xffffffffffffffff
-        h = (h * 0xbf58476d1ce4e5b9) & 0xffffffffffffffff
-        h ^= h >> 31
-    return int(h & 0x7fffffff)
+from .sharding import mix as _mix  # noqa: E402
 
 
 class _ShadowMap:
