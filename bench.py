@@ -118,7 +118,7 @@ def run_ours(args):
     g.manual_seed(args.seed * 1000 + rank)
     acts = torch.randint(0, nA, (W + 2 * K + 2, E), device=dev, dtype=torch.int64, generator=g)
     stream = torch.cuda.current_stream(dev)
-    launches_per_step = 2 + int(m._L.mpb_launches_per_tick(m._h))
+    launches_per_step = int(m._L.mpb_launches_per_env_step(m._h))
     sp = m.engine._stream()
 
     def step_dev(i):
@@ -187,7 +187,7 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16/uint16 (+fp32 valves)", "data": "synthetic",
             "config": workload(args), "gpu_launches": K * launches_per_step,
-            "kernels": "k_mp_env_pre + %d x k_mp_frames + k_mp_env_post per step" % (launches_per_step - 2),
+            "kernels": "per env group: k_mp_env_pre + %d x k_mp_frames + k_mp_env_post; + 3 scheduling kernels" % int(m._L.mpb_launches_per_tick(m._h)),
             "sim_frames_per_s": world * E * K * 200 / (total_ms / 1000.0),
             "e2e": {"value": world * E * K / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * 5,

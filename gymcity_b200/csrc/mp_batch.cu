@@ -41,6 +41,11 @@ struct MpBatch {
     int *perm;                // [n_envs] env ids, most expensive first
     unsigned int *hist;       // [SCHED_BUCKETS + 1]
     int use_sched;
+    // env groups on their own streams: while one group's launch drains its slowest envs the other
+    // groups' launches keep the SMs busy (the per-env dependency chain is the only real one)
+    int groups;
+    cudaStream_t gstream[8];
+    cudaEvent_t ev_start, ev_done[8];
     // gym layer (mpb_env_*)
     int configured, shadow_stride;
     GymCfg cfg;
@@ -113,7 +118,8 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
 __global__ void __launch_bounds__(MP_THREADS, 16)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
-            int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm)
+            int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
+            int goff)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_EPC];
@@ -122,7 +128,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     __shared__ __align__(16) uint32_t s_scal[MP_EPC][(sizeof(Scalars) + 3) / 4];
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
-    const int slot = device_env_index();
+    const int slot = device_env_index() * gstride + goff;
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
@@ -253,29 +259,39 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-             const int64_t *actions, int static_build)
+             const int64_t *actions, int static_build, const int *perm, int gstride, int goff)
 {
     __shared__ int red[8 * MP_EPC];
-    MP_ENV_GUARD();
+    const int slot = device_env_index() * gstride + goff;
+    if (slot >= n_envs) return;
+    const int env = perm ? perm[slot] : slot;
+    const int lane = threadIdx.x & 31;
     Env e;
-    bind_device_env(e, blocks, anim, red);
+    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
     Gym gy;
-    bind_device_gym(gy, shadow, stride, &cfg);
+    bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     if (lane == 0) gym_step_pre(e, gy, actions[env], static_build != 0);
 }
 
 // MicropolisEnv.step, part 3 (env.py:468-540): observation, metrics, reward, done
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-              float *obs, float *reward, uint8_t *done, int is_reset, const uint8_t *mask)
+              float *obs, float *reward, uint8_t *done, int is_reset, const uint8_t *mask, const int *perm,
+              int gstride, int goff)
 {
     __shared__ int red[8 * MP_EPC];
-    MP_ENV_GUARD();
+    const int slot = device_env_index() * gstride + goff;
+    if (slot >= n_envs) return;
+    const int env = perm ? perm[slot] : slot;
+    const int lane = threadIdx.x & 31;
+    (void)lane;
     if (mask && !mask[env]) return;
     Env e;
-    bind_device_env(e, blocks, anim, red);
+    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
     Gym gy;
-    bind_device_gym(gy, shadow, stride, &cfg);
+    bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
     if (is_reset) gym_reset_post(e, gy, obs + env * on, reward + env, done + env);
     else gym_step_post(e, gy, obs + env * on, reward + env, done + env);
@@ -309,24 +325,29 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
-int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before)
+#define MP_GRID_G(b, G, g) ((((b)->n_envs - (g) + (G) - 1) / (G) + MP_EPC - 1) / MP_EPC)
+
+int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, int G = 1, int g = 0)
 {
     const int F = b->frames_per_launch, P = b->passes;
+    const int *perm = b->use_sched ? b->perm : NULL;
+    const int grid = MP_GRID_G(b, G, g);
+    if (grid <= 0) return 0;
     if (P <= 0) {
-        if (animate_before) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL);
+        if (animate_before)
+            k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm, G, g);
         return 0;
     }
     for (int f = 0; f < P; f += F)
-        k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                                                      animate_before && f == 0, 1, b->cycles, b->cost,
-                                                      b->use_sched ? b->perm : NULL);
+        k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
+                                                 animate_before && f == 0, 1, b->cycles, b->cost, perm, G, g);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
-int launch_control_sim_tick(MpBatch *b, cudaStream_t st)
+int launch_control_sim_tick(MpBatch *b, cudaStream_t st, int G = 1, int g = 0)
 {
-    launch_sim_tick(b, st, 0);
-    launch_sim_tick(b, st, 1);
+    launch_sim_tick(b, st, 0, G, g);
+    launch_sim_tick(b, st, 1, G, g);
     return 0;
 }
 
@@ -365,9 +386,6 @@ mpb_handle mpb_create(int n_envs, int device)
     b->n_envs = n_envs; b->device = device;
     b->passes = 100;
     b->frames_per_launch = 25;
-#if defined(MP_DENSE_BATCH)
-    if (const char *bm = getenv("MPB_BATCH_MIN")) { int v = atoi(bm); cudaMemcpyToSymbol(g_mp_batch_min, &v, sizeof(int)); }
-#endif
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
@@ -388,6 +406,10 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
     b->use_sched = 1;
+    b->groups = 4;
+    if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
+    for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&b->ev_done[g], cudaEventDisableTiming); }
+    cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
     k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS>>>(b->blocks, b->anim, n_envs);
@@ -400,6 +422,8 @@ void mpb_destroy(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return;
     cudaSetDevice(b->device);
+    for (int g = 0; g < 8; g++) { if (b->gstream[g]) cudaStreamDestroy(b->gstream[g]); if (b->ev_done[g]) cudaEventDestroy(b->ev_done[g]); }
+    if (b->ev_start) cudaEventDestroy(b->ev_start);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
     cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
@@ -421,6 +445,12 @@ int mpb_launches_per_tick(mpb_handle h)
     if (!b) return -1;
     int per = b->passes > 0 ? (b->passes + b->frames_per_launch - 1) / b->frames_per_launch : 0;
     return 2 * per + (b->passes > 0 ? 0 : 1);
+}
+int mpb_launches_per_env_step(mpb_handle h)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b) return -1;
+    return b->groups * (2 + mpb_launches_per_tick(h)) + (b->use_sched ? 3 : 0);
 }
 int mpb_state_bytes(void) { return EnvLayout::PERSISTENT_END; }
 void *mpb_blocks(mpb_handle h) { return h ? ((MpBatch *)h)->blocks : NULL; }
@@ -541,7 +571,7 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     for (int f = 0; f < n; f += F)
         k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0,
                                                                         (n - f < F) ? n - f : F, 0, 0, b->cycles,
-                                                                        b->cost, b->use_sched ? b->perm : NULL);
+                                                                        b->cost, b->use_sched ? b->perm : NULL, 1, 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -562,7 +592,7 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     if (!b) return -1;
     cudaSetDevice(b->device);
     launch_sim_tick(b, (cudaStream_t)stream, 0);
-    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL);
+    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -747,7 +777,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     if (upload_mask(b, mask_host, st)) return -1;
     launch_control_sim_tick(b, st);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL);
+                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -777,11 +807,24 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     NEED_CFG();
     if (!actions_dev) return -1;
     cudaStream_t st = (cudaStream_t)stream;
-    k_mp_env_pre<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                   actions_dev, static_build);
-    launch_control_sim_tick(b, st);
-    k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                    b->obs, b->reward, b->done, 0, NULL);
+    const int G = b->groups;
+    const int *perm = b->use_sched ? b->perm : NULL;
+    if (G > 1) cudaEventRecord(b->ev_start, st);
+    for (int g = 0; g < G; g++) {
+        cudaStream_t gs = G > 1 ? b->gstream[g] : st;
+        const int grid = MP_GRID_G(b, G, g);
+        if (grid <= 0) continue;
+        if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
+        k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                 actions_dev, static_build, perm, G, g);
+        launch_control_sim_tick(b, gs, G, g);
+        k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                  b->obs, b->reward, b->done, 0, NULL, perm, G, g);
+        if (G > 1) {
+            cudaEventRecord(b->ev_done[g], gs);
+            cudaStreamWaitEvent(st, b->ev_done[g], 0);
+        }
+    }
     rebuild_schedule(b, st);
     CK(cudaGetLastError());
     return 0;

@@ -56,7 +56,7 @@ MPD void init_will_stuff(Env &e)
 MPD void clear_map(Env &e)
 {
     for (int i = e.c.tid; i < NTILES; i += e.c.n) e.map[i] = T_DIRT;
-    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.act[i] = 0;
+    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) { e.act[i] = 0; e.need[i] = 0; }
     e.c.sync();
 }
 
@@ -113,7 +113,7 @@ MPD void env_call(Env &e, int fn, int a, int b)
     const bool lead = e.c.lead();
     switch (fn) {
     case FN_MAP_SCAN: map_scan(e, a, b); break;
-    case FN_POWER_SCAN: do_power_scan(e); break;
+    case FN_POWER_SCAN: do_power_scan(e, false); break;
     case FN_PTLV_SCAN: ptlv_scan(e); break;
     case FN_CRIME_SCAN: crime_scan(e); break;
     case FN_POP_DENSITY_SCAN: {

@@ -283,7 +283,7 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
         base++;
     }
     set_zone_power(e, x, y);
-    e.map[tix(x, y)] |= ZONEBIT + BULLBIT;
+    mset(e, tix(x, y), e.map[tix(x, y)] | (ZONEBIT + BULLBIT));
     return true;
 }
 
@@ -657,7 +657,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
             int z = T_FULLSTADIUM - 5;
             MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
                 MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
-            e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
+            mset(e, tix(x, y), e.map[tix(x, y)] | ZONEBIT | PWRBIT);
             tset(e, x + 1, y, T_FOOTBALLGAME1 + ANIMBIT);
             tset(e, x + 1, y + 1, T_FOOTBALLGAME2 + ANIMBIT);
         }
@@ -668,7 +668,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
             int z = T_STADIUM - 5;
             MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
                 MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
-            e.map[tix(x, y)] |= ZONEBIT | PWRBIT;
+            mset(e, tix(x, y), e.map[tix(x, y)] | ZONEBIT | PWRBIT);
         }
         return;
     case T_AIRPORT:
@@ -910,7 +910,9 @@ MPP void scan_tile(Env &e, int idx)
     if (tile >= T_ROADBASE && tile < T_POWERBASE) { do_road(e, x, y); return; }
     if (mv & ZONEBIT) { do_zone(e, x, y); return; }
     if (tile >= T_RAILBASE && tile < T_RESBASE) { do_rail(e, x, y); return; }
-    if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) mset(e, idx, (uint16_t)random_rubble(e));
+    if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) { mset(e, idx, (uint16_t)random_rubble(e)); return; }
+    // a building tile that is no centre: setZonePower above was all there is to do, and it is done
+    e.need[idx >> 5] &= ~(1u << (idx & 31));
 }
 
 // [ALL] mapScan(x1, x2).  The scan order is linear memory order (x outer, y inner over the
@@ -921,22 +923,33 @@ MPP void scan_tile(Env &e, int idx)
 // that tile, and the words are re-read (L1 hits) because processing may have activated tiles ahead
 // of the scan position (fire spread, zonePlop, repairZone ...).  Tiles activated BEHIND the scan
 // position are not visited, exactly as in the reference's single forward sweep.
-// Tile classes for the warp-parallel part of the scan.  Most tiles the scan visits are cheap and
-// touch nothing but themselves: building tiles that are not the zone centre (at most a
-// setZonePower), plain roads (census + traffic art), receding flood water, radioactive waste,
-// fire that does not spread this time, tiny explosions turning to rubble.  They need at most ONE
-// draw each, so a whole 32-tile word is processed at once: lane b takes tile b, the draws are
-// handed out in scan order by LCG jump-ahead, and the batch stops in front of the first tile that
-// needs the serial lane (zones, bridges, rails, spreading fire, active flooding).
-enum : int { TK_SERIAL = 0, TK_INERT, TK_ROAD, TK_FLOOD0, TK_RAD, TK_FIRE, TK_TINYEXP };
+#define MP_DENSE_RANGE_MIN 96       // tiles needing a visit in one scan range before the batching scan is used
+
+// ---- dense scan -------------------------------------------------------------------------------
+// A flood, a meltdown or a forest fire turns hundreds to thousands of tiles of one city active; on
+// the serial lane such a city costs 10x the average and the whole batch waits for it at the end of
+// every step (tools/imbalance.py: max/mean = 10).  Most of those tiles are cheap and touch nothing
+// but themselves, so when a scan range holds many tiles that need a visit the words are processed
+// 32 tiles at a time: lane b takes tile b, the draws are handed out in scan order by LCG
+// jump-ahead, and the batch stops in front of the first tile that really needs the serial lane:
+//   * building tile that is no centre: at most a setZonePower          (no draw)
+//   * plain road: census + traffic art                                  (no draw)
+//   * receding flood (floodCount == 0), radioactive waste, tiny explosion, fire that does not
+//     spread this time                                                   (1 draw each)
+//   * ACTIVE flooding (floodCount > 0): 4 draws; the tile is a no-op unless one of them hits
+//     (1 in 8) on a neighbour that can still be flooded -- in the interior of a flood field no
+//     neighbour can, so whole words of flood water are retired at once   (4 draws)
+//   * everything else (zones, bridges, rails, spreading fire / flood): serial lane.
+enum : int { TK_SERIAL = 0, TK_INERT, TK_ROAD, TK_FLOOD0, TK_RAD, TK_FIRE, TK_TINYEXP, TK_FLOODA };
 
 MPD int tile_kind(const Env &e, int v)
 {
     const int t = v & LOMASK;
+    const bool flooding = S.floodCount > 0;
     if (t < T_ROADBASE) {
         if (t >= T_FIREBASE) return TK_FIRE;
-        if (t < T_RADTILE) return S.floodCount > 0 ? (int)TK_SERIAL : (int)TK_FLOOD0;
-        return TK_RAD;          // 52..55: doRadTile
+        if (t < T_RADTILE) return flooding ? (int)TK_FLOODA : (int)TK_FLOOD0;
+        return flooding ? (int)TK_SERIAL : (int)TK_RAD;          // a tile that turns to DIRT could be flooded by a later lane
     }
     if (t < T_POWERBASE) {
         if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16) || !(v & BURNBIT)) return TK_SERIAL;   // decay draw / bridge
@@ -944,45 +957,62 @@ MPD int tile_kind(const Env &e, int v)
     }
     if (v & ZONEBIT) return TK_SERIAL;
     if (t >= T_RAILBASE && t < T_RESBASE) return TK_SERIAL;     // doRail: conditional draw
-    if (t >= T_SOMETINYEXP && t <= T_LASTTINYEXP) return TK_TINYEXP;
+    if (t >= T_SOMETINYEXP && t <= T_LASTTINYEXP) return flooding ? (int)TK_SERIAL : (int)TK_TINYEXP;
     return TK_INERT;
 }
 
-#if defined(__CUDACC__) && defined(MP_DENSE_BATCH)
-// EXPERIMENTAL (off by default, -DMP_DENSE_BATCH): lane-parallel processing of dense 32-tile words.
-// Bit-exact (GPU suite passes with it on) but its call site in the sparse scan loop costs ~12% on
-// typical cities, see profiles/r01_notes.md.
-// tunable (MPB_BATCH_MIN): minimum number of unscanned active tiles in a word for the lane-parallel path
-__device__ int g_mp_batch_min = 8;
-#define MP_BATCH_MIN g_mp_batch_min
-#endif
-#if defined(__CUDA_ARCH__) && defined(MP_DENSE_BATCH)
-// [ALL lanes] one dense 32-tile word: lane b takes tile b of word `wi` (bits of mL, already limited
-// to the unscanned part of the range).  Returns the scan position after the batch: either the tile
-// the batch had to stop in front of (the caller gives it to the serial lane) or the next word.
-// Out of line on purpose: it is the rare path and must not bloat the sparse scan loop.
-MPN int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
+#if defined(__CUDA_ARCH__)
+MPD uint32_t lcg_jump(uint32_t x, int n)
+{
+    MP_NOUNROLL for (int q = 0; q < n; q++) x = x * 1103515245u + 12345u;
+    return x;
+}
+MPD int lcg_r16(uint32_t x) { return (int)((x & 0xffff00u) >> 8) & 0xffff; }
+
+// [ALL lanes] one 32-tile word: lane b takes tile b of word `wi` (bits of mL, already limited to the
+// unscanned part of the range).  Returns the scan position after the batch; serial_next says whether
+// the tile at that position is the one the batch had to stop in front of.
+MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
 {
     const int lane = e.c.tid;
-    const unsigned lt = (1u << lane) - 1u;
     const bool mine = (mL >> lane) & 1u;
     const int t = wi * 32 + lane;
     int v = mine ? e.map[t] : 0;
     const int kind = mine ? tile_kind(e, v) : (int)TK_INERT;
     const unsigned serial = __ballot_sync(0xffffffffu, mine && kind == TK_SERIAL);
     int stop = serial ? __ffs(serial) - 1 : 32;             // batch = my tiles below `stop`
-    const bool draws = mine && lane < stop && kind >= TK_FLOOD0;
-    const unsigned dmask = __ballot_sync(0xffffffffu, draws);
-    int r = 0;
-    if (draws) {
-        uint32_t x = S.rng;
-        const int k = __popc(dmask & lt);
-        MP_NOUNROLL for (int q = 0; q <= k; q++) x = x * 1103515245u + 12345u;
-        r = (int)((x & 0xffff00u) >> 8) & 0xffff;
+    // draws per tile and their rank in scan order (exclusive prefix sum over the lanes)
+    const int nd = (mine && lane < stop) ? (kind == TK_FLOODA ? 4 : (kind >= TK_FLOOD0 ? 1 : 0)) : 0;
+    int pre = nd;
+    MP_NOUNROLL for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
     }
-    // a fire tile whose draw says "spread" (1 in 4) goes to the serial lane: the batch ends there
-    const unsigned spread = __ballot_sync(0xffffffffu, draws && kind == TK_FIRE && !(r & 3));
-    if (spread) stop = min(stop, __ffs(spread) - 1);
+    pre -= nd;
+    int r = 0;
+    bool must_serial = false;
+    if (nd) {
+        uint32_t x = lcg_jump(S.rng, pre + 1);
+        r = lcg_r16(x);
+        if (kind == TK_FIRE) {
+            must_serial = !(r & 3);                         // 1 in 4: doFire, which draws on
+        } else if (kind == TK_FLOODA) {                     // doFlood, floodCount > 0 (disasters.cpp:382-400)
+            const int tx = t / WORLD_H, ty = t - tx * WORLD_H;
+            MP_NOUNROLL for (int z = 0; z < 4; z++) {
+                if ((r & 7) == 0) {
+                    const int xx = tx + (z == 1) - (z == 3), yy = ty - (z == 0) + (z == 2);
+                    if (inb(xx, yy)) {
+                        const int c = e.map[tix(xx, yy)], ct = c & LOMASK;
+                        if ((c & BURNBIT) == BURNBIT || c == T_DIRT || (ct >= T_WOODS5 && ct < T_FLOOD)) must_serial = true;
+                    }
+                }
+                x = x * 1103515245u + 12345u;
+                r = lcg_r16(x);
+            }
+        }
+    }
+    const unsigned ms = __ballot_sync(0xffffffffu, must_serial);
+    if (ms) stop = min(stop, __ffs(ms) - 1);
     const bool batch = mine && lane < stop;
     bool still = true, heavy = false;
     if (batch) {
@@ -1014,24 +1044,57 @@ MPN int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
         } else if (kind == TK_TINYEXP) {                    // tiny explosion -> rubble
             e.map[t] = (uint16_t)((T_RUBBLE + (r & 3)) | BULLBIT);
             still = false;
-        }                                                   // TK_FIRE without spread: firePop++ only
+        }                                                   // TK_FIRE (no spread): firePop++; TK_FLOODA: no-op
     }
     const unsigned gone = __ballot_sync(0xffffffffu, batch && !still);
+    const unsigned inert_done = __ballot_sync(0xffffffffu, batch && kind == TK_INERT);
     const int roads = __popc(__ballot_sync(0xffffffffu, batch && kind == TK_ROAD))
         + __popc(__ballot_sync(0xffffffffu, batch && heavy));
     const int fires = __popc(__ballot_sync(0xffffffffu, batch && kind == TK_FIRE));
+    // draws consumed by the batch = prefix of the lane it stopped at (or the word total)
+    const int total = __shfl_sync(0xffffffffu, pre + nd, 31);
+    const int used = stop < 32 ? __shfl_sync(0xffffffffu, pre, stop) : total;
     if (lane == 0) {
         if (gone) e.act[wi] &= ~gone;
+        if (gone | inert_done) e.need[wi] &= ~(gone | inert_done);
         if (roads) S.roadTotal = (int16_t)(S.roadTotal + roads);
         if (fires) S.firePop = (int16_t)(S.firePop + fires);
-        const int nd = __popc(dmask & (stop >= 32 ? 0xffffffffu : ((1u << stop) - 1u)));
-        uint32_t x = S.rng;
-        MP_NOUNROLL for (int q = 0; q < nd; q++) x = x * 1103515245u + 12345u;
-        S.rng = x;
+        S.rng = lcg_jump(S.rng, used);
     }
     __syncwarp();
     serial_next = stop < 32 && ((mL >> stop) & 1u);
     return serial_next ? wi * 32 + stop : (wi + 1) * 32;
+}
+
+// [ALL] the whole mapScan range with word batching (see above).  Out of line and entered only when
+// the range is dense, so the common sparse loop below carries none of this.
+MPN void map_scan_dense(Env &e, int i0, int i1)
+{
+    const int w0 = i0 >> 5, w1 = (i1 - 1) >> 5;
+    const int lane = e.c.tid;
+    int pos = i0;
+    MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
+        const int w = wb + lane;
+        for (;;) {
+            uint32_t m = (w <= w1) ? e.need[w] : 0u;
+            const int lo = pos - w * 32, hi = i1 - w * 32;
+            if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
+            if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
+            const unsigned any = __ballot_sync(0xffffffffu, m != 0);
+            if (!any) break;
+            const int L = __ffs(any) - 1;
+            const uint32_t mL = __shfl_sync(0xffffffffu, m, L);
+            int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
+            if (__popc(mL) >= 4) {
+                bool serial_next;
+                t1 = scan_word_batch(e, wb + L, mL, serial_next);
+                if (!serial_next) { pos = t1; continue; }
+            }
+            if (lane == 0) scan_tile(e, t1);
+            __syncwarp();
+            pos = t1 + 1;
+        }
+    }
 }
 #endif
 
@@ -1042,10 +1105,20 @@ MPP void map_scan(Env &e, int x1, int x2)
     int pos = i0;                                   // first tile not yet passed by the scan
 #if defined(__CUDA_ARCH__)
     const int lane = e.c.tid;
+    {   // dense range (flood / radiation / fire field)?  then the batching scan takes it
+        int cnt = 0;
+        MP_NOUNROLL for (int w = w0 + lane; w <= w1; w += 32) cnt += __popc(e.need[w]);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (cnt >= MP_DENSE_RANGE_MIN) {
+            map_scan_dense(e, i0, i1);
+            e.c.sync();
+            return;
+        }
+    }
     MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
         const int w = wb + lane;
         for (;;) {
-            uint32_t m = (w <= w1) ? e.act[w] : 0u;
+            uint32_t m = (w <= w1) ? e.need[w] : 0u;
             // keep tiles in [pos, i1)
             const int lo = pos - w * 32, hi = i1 - w * 32;
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
@@ -1054,15 +1127,7 @@ MPP void map_scan(Env &e, int x1, int x2)
             if (!any) break;
             const int L = __ffs(any) - 1;
             const uint32_t mL = __shfl_sync(0xffffffffu, m, L);     // the word being worked on
-            int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
-#if defined(MP_DENSE_BATCH)
-            if (__popc(mL) >= MP_BATCH_MIN) {
-                // dense word (flood / radiation / fire fields, road grids, rows of buildings)
-                bool serial_next;
-                t1 = scan_word_batch(e, wb + L, mL, serial_next);
-                if (!serial_next) { pos = t1; continue; }
-            }
-#endif
+            const int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
             if (lane == 0) scan_tile(e, t1);
             __syncwarp();
             pos = t1 + 1;
@@ -1071,7 +1136,7 @@ MPP void map_scan(Env &e, int x1, int x2)
 #else
     for (int w = w0; w <= w1; w++) {
         for (;;) {
-            uint32_t m = e.act[w];
+            uint32_t m = e.need[w];
             const int lo = pos - w * 32, hi = i1 - w * 32;
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
             if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
@@ -1369,12 +1434,18 @@ MPN void power_scan_walk(Env &e)
 }
 
 // [ALL]
-MPN void do_power_scan(Env &e)
+// set_new_power: every caller in the reference sets newPower = true right after doPowerScan
+// (simulate.cpp:226, 289, 418); it is folded in here so that refresh_need sees the new value.
+MPN void do_power_scan(Env &e, bool set_new_power = true)
 {
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
     e.c.sync();
-    if (e.c.lead()) power_scan_walk(e);
+    if (e.c.lead()) {
+        power_scan_walk(e);
+        if (set_new_power) S.newPower = 1;
+    }
     e.c.sync();
+    refresh_need(e);        // inert building tiles must be revisited where PWRBIT no longer matches
 }
 
 // ------------------------------------------------------------------ smoothing passes
@@ -1448,6 +1519,78 @@ MPD void coop_add(Env &e, int slot, int v)
 #endif
 }
 
+// [ALL] The reference's running-maximum sweeps (scan.cpp:283-303 pollution, :417-437 crime):
+//   for each cell in order: if (z > max || (z == max && (getRandom16() & 3) == 0)) { max = z; site = cell; }
+// Which cells draw depends only on the values (a cell draws iff it equals the maximum of
+// everything before it), so 32 cells are handled at once: exclusive prefix maximum across the
+// lanes, draws handed out in cell order by LCG jump-ahead, the last winning lane sets the site.
+// `vals`: one byte per cell, `valid`: optional per-cell flag (crime counts only cells with land
+// value), returns the winning cell index or -1; *count / *total are the census sums.
+MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool nonzero_only, int *count, int *total)
+{
+#if defined(__CUDA_ARCH__)
+    const int lane = e.c.tid;
+    const unsigned lt = (1u << lane) - 1u;
+    int vmax = 0, site = -1, cnt = 0, tot = 0;
+    uint32_t rng = S.rng;
+    MP_NOUNROLL for (int base = 0; base < N2; base += 32) {
+        const int i = base + lane;
+        const bool in = i < N2;
+        const int z = in ? vals[i] : 0;
+        const bool live = in && (valid ? valid[i] != 0 : true) && (!nonzero_only || z != 0);
+        const unsigned lm = __ballot_sync(0xffffffffu, live);
+        if (!lm) continue;
+        cnt += live ? 1 : 0;
+        tot += live ? z : 0;
+        // exclusive prefix maximum over live lanes, seeded with the running maximum
+        int pm = live ? z : -1;
+        MP_NOUNROLL for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, pm, o);
+            if (lane >= o) pm = max(pm, y);
+        }
+        const int incl = pm;                                   // inclusive max of lanes <= me
+        int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        excl = lane == 0 ? -1 : excl;
+        const int before = max(vmax, excl);
+        const bool greater = live && z > before;
+        const bool tie = live && z == before;
+        const unsigned tm = __ballot_sync(0xffffffffu, tie);
+        bool win = greater;
+        if (tm) {
+            if (tie) {
+                uint32_t x = rng;
+                const int k = __popc(tm & lt);
+                MP_NOUNROLL for (int q = 0; q <= k; q++) x = x * 1103515245u + 12345u;
+                win = ((((x & 0xffff00u) >> 8) & 0xffff) & 3) == 0;
+            }
+            const int nd = __popc(tm);
+            MP_NOUNROLL for (int q = 0; q < nd; q++) rng = rng * 1103515245u + 12345u;
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, win);
+        if (wm) site = base + (31 - __clz(wm));
+        vmax = max(vmax, __shfl_sync(0xffffffffu, incl, 31));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    }
+    if (lane == 0) S.rng = rng;
+    __syncwarp();
+    *count = cnt; *total = tot;
+    return site;
+#else
+    int vmax = 0, site = -1, cnt = 0, tot = 0;
+    for (int i = 0; i < N2; i++) {
+        const int z = vals[i];
+        if ((valid && !valid[i]) || (nonzero_only && !z)) continue;
+        cnt++; tot += z;
+        if (z > vmax || (z == vmax && (rnd16(e) & 3) == 0)) { vmax = z; site = i; }
+    }
+    *count = cnt; *total = tot;
+    return site;
+#endif
+}
+
 // [ALL] scan.cpp:217-322 pollutionTerrainLandValueScan (+ :454-497 smoothTerrain, non-dither)
 MPN void ptlv_scan(Env &e)
 {
@@ -1502,22 +1645,16 @@ MPN void ptlv_scan(Env &e)
     // pollution max: draws depend on the running maximum, so this is the serial lane
     for (int i = e.c.tid; i < N2; i += e.c.n) e.pollution[i] = e.tmp1[i];
     e.c.sync();
-    if (e.c.lead()) {
-        int pmax = 0, pnum = 0;
-        int64_t ptot = 0;
-        MP_NOUNROLL for (int i = 0; i < N2; i++) {
-            int z = e.tmp1[i];
-            if (z) {
-                pnum++;
-                ptot += z;
-                if (z > pmax || (z == pmax && (rnd16(e) & 3) == 0)) {
-                    pmax = z;
-                    S.pollutionMaxX = (int16_t)((i / H2) * 2);
-                    S.pollutionMaxY = (int16_t)((i % H2) * 2);
-                }
+    {
+        int pnum, ptot;
+        const int site = tie_max_scan(e, e.tmp1, nullptr, true, &pnum, &ptot);
+        if (e.c.lead()) {
+            if (site >= 0) {
+                S.pollutionMaxX = (int16_t)((site / H2) * 2);
+                S.pollutionMaxY = (int16_t)((site % H2) * 2);
             }
+            S.pollutionAverage = pnum ? (int16_t)(ptot / pnum) : (int16_t)0;
         }
-        S.pollutionAverage = pnum ? (int16_t)(ptot / pnum) : (int16_t)0;
     }
     // smoothTerrain: tempMap3 -> terrainDensityMap
     for (int i = e.c.tid; i < N4; i += e.c.n) {
@@ -1556,21 +1693,16 @@ MPN void crime_scan(Env &e)
     }
     for (int i = e.c.tid; i < N8; i += e.c.n) e.policeEff[i] = e.policeSt[i];
     e.c.sync();
-    if (e.c.lead()) {
-        int64_t totz = 0;
-        int numz = 0, cmax = 0;
-        MP_NOUNROLL for (int i = 0; i < N2; i++) {
-            if (!e.tmp2[i]) continue;
-            int z = e.crime[i];
-            ++numz;
-            totz += z;
-            if (z > cmax || (z == cmax && (rnd16(e) & 3) == 0)) {
-                cmax = z;
-                S.crimeMaxX = (int16_t)((i / H2) * 2);
-                S.crimeMaxY = (int16_t)((i % H2) * 2);
+    {
+        int numz, totz;
+        const int site = tie_max_scan(e, e.crime, e.tmp2, false, &numz, &totz);
+        if (e.c.lead()) {
+            if (site >= 0) {
+                S.crimeMaxX = (int16_t)((site / H2) * 2);
+                S.crimeMaxY = (int16_t)((site % H2) * 2);
             }
+            S.crimeAverage = numz > 0 ? (int16_t)(totz / numz) : (int16_t)0;
         }
-        S.crimeAverage = numz > 0 ? (int16_t)(totz / numz) : (int16_t)0;
     }
     e.c.sync();
 }
@@ -1915,7 +2047,7 @@ MPD void do_sim_init(Env &e)
 MPN void animate_tiles(Env &e)
 {
     MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = 0;
+        uint32_t m = 0, nd = 0;
         MP_NOUNROLL for (int b = 0; b < 32; b++) {
             const int i = w * 32 + b;
             int v = e.map[i];
@@ -1924,8 +2056,10 @@ MPN void animate_tiles(Env &e)
                 e.map[i] = (uint16_t)v;
             }
             if (tile_is_active(v)) m |= 1u << b;
+            if (tile_needs_visit(e, i, v)) nd |= 1u << b;
         }
         e.act[w] = m;
+        e.need[w] = nd;
     }
     e.c.sync();
 }

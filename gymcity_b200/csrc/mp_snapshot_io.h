@@ -59,6 +59,32 @@ inline int snapshot_get_field(Env &e, int field, void *out, int cap)
     return n;
 }
 
+inline void snapshot_rebuild_bitmaps(Env &e)
+{
+    for (int w = 0; w < POWER_WORDS; w++) {
+        uint32_t m = 0, nd = 0;
+        for (int b = 0; b < 32; b++) {
+            const int idx = w * 32 + b, v = e.map[idx];
+            if (!tile_is_active(v)) continue;
+            m |= 1u << b;
+            const int t = v & LOMASK;
+            const bool inert = t >= T_POWERBASE && !(v & ZONEBIT) && !(t >= T_RAILBASE && t < T_RESBASE)
+                && !(t >= T_SOMETINYEXP && t <= T_LASTTINYEXP);
+            bool need = true;
+            if (inert) {
+                if (!(v & CONDBIT) || !e.s->newPower) need = false;
+                else {
+                    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power[idx >> 5] >> (idx & 31)) & 1u);
+                    need = ((v & PWRBIT) != 0) != want;
+                }
+            }
+            if (need) nd |= 1u << b;
+        }
+        e.act[w] = m;
+        e.need[w] = nd;
+    }
+}
+
 inline int snapshot_set_field(Env &e, int field, const void *in, int nbytes)
 {
     if (field == MPF_POWER_GRID) {
@@ -66,6 +92,7 @@ inline int snapshot_set_field(Env &e, int field, const void *in, int nbytes)
         const uint8_t *s = (const uint8_t *)in;
         for (int i = 0; i < POWER_WORDS; i++) e.power[i] = 0;
         for (int i = 0; i < NTILES; i++) if (s[i]) e.power[i >> 5] |= 1u << (i & 31);
+        snapshot_rebuild_bitmaps(e);
         return 0;
     }
     if (field == MPF_POWER_STACK) {
@@ -78,13 +105,7 @@ inline int snapshot_set_field(Env &e, int field, const void *in, int nbytes)
     void *p = snapshot_field_ptr(e, field, &n);
     if (!p || nbytes != n) return -1;
     memcpy(p, in, n);
-    if (field == MPF_MAP) {            // keep the derived active-tile bitmap in step
-        for (int w = 0; w < POWER_WORDS; w++) {
-            uint32_t m = 0;
-            for (int b = 0; b < 32; b++) if (tile_is_active(e.map[w * 32 + b])) m |= 1u << b;
-            e.act[w] = m;
-        }
-    }
+    if (field == MPF_MAP) snapshot_rebuild_bitmaps(e);      // keep the derived bitmaps in step
     return 0;
 }
 
@@ -143,6 +164,7 @@ inline void snapshot_set_scalars(Env &e, const mp_scalars *o)
     for (int i = 0; i < MP_PROBLEM_COMPLAINTS; i++) s.problemOrder[i] = (int16_t)o->problemOrder[i];
     s.roadPercent = o->roadPercent; s.policePercent = o->policePercent;
     s.firePercent = o->firePercent; s.externalMarket = o->externalMarket;
+    snapshot_rebuild_bitmaps(e);            // newPower may have changed
 }
 
 inline int snapshot_get_sprites(Env &e, mp_sprite *out, int cap)

@@ -136,7 +136,9 @@ struct EnvLayout {
     static constexpr int OVERLAY = PSTACK + a16(POWER_STACK_SIZE * 2);  // tool overlay uint16[256]+mask
     // derived: one bit per tile, set iff mapScan would not skip it (tile id >= FLOOD)
     static constexpr int ACTIVE = OVERLAY + 512 + 32;
-    static constexpr int TOTAL = ACTIVE + a16((POWER_WORDS + 1) * 4);
+    // derived: subset of ACTIVE the scan really has to visit (see tile_needs_visit)
+    static constexpr int NEED = ACTIVE + a16((POWER_WORDS + 1) * 4);
+    static constexpr int TOTAL = NEED + a16((POWER_WORDS + 1) * 4);
 };
 
 // Thread context.  Device: the WARP that owns the env (tid = lane, n = 32; a barrier is a
@@ -167,6 +169,7 @@ struct Env {
     uint16_t *pstack;
     uint16_t *ovl;          // tool overlay: 256 values + 8 mask words
     uint32_t *act;          // active-tile bitmap (derived from map, kept in step by mset)
+    uint32_t *need;         // tiles mapScan must visit: act minus building tiles whose PWRBIT is already right
     const uint16_t *anim;   // 1024-entry animation successor table
     Coop c;
 };
@@ -191,6 +194,7 @@ MPH void bind_env(Env &e, uint8_t *blk)
     e.pstack = (uint16_t *)(blk + L::PSTACK);
     e.ovl = (uint16_t *)(blk + L::OVERLAY);
     e.act = (uint32_t *)(blk + L::ACTIVE);
+    e.need = (uint32_t *)(blk + L::NEED);
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -223,25 +227,70 @@ MPD void pwr_set(Env &e, int x, int y)
     int i = tix(x, y);
     e.power[i >> 5] |= 1u << (i & 31);
 }
-// Every tile store on the serial lane goes through mset so that the active-tile bitmap (bit set iff
-// tile id >= FLOOD, i.e. mapScan would look at the tile, simulate.cpp:937-945) never goes stale.
-// Stores that only flip status bits (|= BULLBIT, PWRBIT ...) leave the id and so the bit alone.
+// Every tile store on the serial lane goes through mset so that the two derived bitmaps never go
+// stale.  `act`: bit set iff tile id >= FLOOD, i.e. the reference's mapScan would look at the tile
+// (simulate.cpp:937-945).  `need` (what the scan iterates): act minus the tiles whose visit is
+// provably a no-op -- building tiles that are not a zone centre, road, rail or tiny explosion do
+// nothing in mapScan except `if (newPower && CONDBIT) setZonePower` (simulate.cpp:966-968), which
+// changes nothing when PWRBIT already agrees with the power grid.  No draw, no census: skipping
+// such a visit is exact.  The bit comes back whenever the tile is rewritten (mset) or the power
+// grid is rebuilt (refresh_need after doPowerScan).
 MPH bool tile_is_active(int v) { return (v & LOMASK) >= T_FLOOD; }
+MPD bool tile_is_inert_kind(int v)
+{
+    const int t = v & LOMASK;
+    return t >= T_POWERBASE && !(v & ZONEBIT) && !(t >= T_RAILBASE && t < T_RESBASE)
+        && !(t >= T_SOMETINYEXP && t <= T_LASTTINYEXP);
+}
+MPD bool tile_needs_visit(const Env &e, int idx, int v)
+{
+    if (!tile_is_active(v)) return false;
+    if (!tile_is_inert_kind(v)) return true;
+    if (!(v & CONDBIT) || !e.s->newPower) return false;
+    const int t = v & LOMASK;
+    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power[idx >> 5] >> (idx & 31)) & 1u);
+    return ((v & PWRBIT) != 0) != want;
+}
 MPD void mset(Env &e, int idx, int v)
 {
     e.map[idx] = (uint16_t)v;
-    const uint32_t bit = 1u << (idx & 31), w = e.act[idx >> 5];
-    const uint32_t nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
+    const uint32_t bit = 1u << (idx & 31);
+    const uint32_t w = e.act[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
     if (nw != w) e.act[idx >> 5] = nw;
+    const uint32_t n = e.need[idx >> 5], nn = tile_needs_visit(e, idx, v) ? (n | bit) : (n & ~bit);
+    if (nn != n) e.need[idx >> 5] = nn;
 }
-// [ALL] recompute the whole bitmap from the map (after bulk writes: clearMap, terrain, animateTiles)
+// [ALL] recompute both bitmaps from the map (after bulk writes: clearMap, terrain, state upload)
 MPD void rebuild_active(Env &e)
 {
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = 0;
-        for (int b = 0; b < 32; b++)
-            if (tile_is_active(e.map[w * 32 + b])) m |= 1u << b;
+        uint32_t m = 0, nd = 0;
+        for (int b = 0; b < 32; b++) {
+            const int v = e.map[w * 32 + b];
+            if (tile_is_active(v)) m |= 1u << b;
+            if (tile_needs_visit(e, w * 32 + b, v)) nd |= 1u << b;
+        }
         e.act[w] = m;
+        e.need[w] = nd;
+    }
+    e.c.sync();
+}
+// [ALL] the power grid (or newPower) changed: recompute `need` for the active tiles
+MPD void refresh_need(Env &e)
+{
+    for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
+        uint32_t m = e.act[w], nd = 0;
+        while (m) {
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs(m) - 1;
+#else
+            int b = 0;
+            while (!((m >> b) & 1u)) b++;
+#endif
+            m &= m - 1;
+            if (tile_needs_visit(e, w * 32 + b, e.map[w * 32 + b])) nd |= 1u << b;
+        }
+        e.need[w] = nd;
     }
     e.c.sync();
 }

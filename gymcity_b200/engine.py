@@ -82,7 +82,7 @@ def _bind(L):
     sig = {
         "mpb_create": (vp, [i32, i32]), "mpb_destroy": (None, [vp]),
         "mpb_last_error": (C.c_char_p, [vp]), "mpb_num_envs": (i32, [vp]),
-        "mpb_env_stride": (i32, []), "mpb_launches_per_tick": (i32, [vp]), "mpb_state_bytes": (i32, []), "mpb_blocks": (vp, [vp]),
+        "mpb_env_stride": (i32, []), "mpb_launches_per_tick": (i32, [vp]), "mpb_launches_per_env_step": (i32, [vp]), "mpb_state_bytes": (i32, []), "mpb_blocks": (vp, [vp]),
         "mpb_sync": (i32, [vp]), "mpb_read_cycles": (i32, [vp, vp]), "mpb_seed": (i32, [vp, vp, vp]),
         "mpb_set_funds": (i32, [vp, i32, vp]), "mpb_set_passes": (i32, [vp, i32, vp]),
         "mpb_set_disasters": (i32, [vp, i32, vp]),

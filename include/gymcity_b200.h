@@ -79,7 +79,8 @@ mpb_handle mpb_create(int n_envs, int device);
 void mpb_destroy(mpb_handle h);
 const char *mpb_last_error(mpb_handle h);
 int mpb_num_envs(mpb_handle h);
-int mpb_launches_per_tick(mpb_handle h);   /* kernel launches one MicropolisControl.simTick takes */
+int mpb_launches_per_tick(mpb_handle h);
+int mpb_launches_per_env_step(mpb_handle h);   /* kernel launches one mpb_env_step enqueues */   /* kernel launches one MicropolisControl.simTick takes */
 int mpb_env_stride(void);            /* bytes between consecutive env blocks in HBM            */
 int mpb_state_bytes(void);           /* bytes of persistent state per env (without scratch)     */
 void *mpb_blocks(mpb_handle h);      /* borrowed device pointer to the env blocks               */
