@@ -269,6 +269,8 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
     Env e;
     bind_env(e, blocks + (size_t)env * ENV_STRIDE);
     e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
+    __shared__ __align__(16) uint16_t s_ovl[MP_EPC][272];      // the tool overlay (256 values + mask) on chip
+    e.ovl = s_ovl[threadIdx.x >> 5];
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     if (lane == 0) gym_step_pre(e, gy, actions[env], static_build != 0);

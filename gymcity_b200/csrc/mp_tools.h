@@ -53,8 +53,20 @@ struct Fx {                 // one tool call's pending effects
     {
         e.s->totalFunds = (int)(e.s->totalFunds - cost);
         const uint32_t *m = (const uint32_t *)(e.ovl + 256);
-        MP_NOUNROLL for (int s = 0; s < 256; s++)
-            if ((m[s >> 5] >> (s & 31)) & 1u) mset(e, tix(ox + (s >> 4), oy + (s & 15)), e.ovl[s]);
+        MP_NOUNROLL for (int w = 0; w < 8; w++) {
+            uint32_t bits = m[w];
+            while (bits) {                  // only the slots that were written
+                int b = 0;
+#if defined(__CUDA_ARCH__)
+                b = __ffs(bits) - 1;
+#else
+                while (!((bits >> b) & 1u)) b++;
+#endif
+                bits &= bits - 1;
+                const int s = w * 32 + b;
+                mset(e, tix(ox + (s >> 4), oy + (s & 15)), e.ovl[s]);
+            }
+        }
     }
 };
 
