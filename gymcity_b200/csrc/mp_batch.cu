@@ -62,13 +62,21 @@ struct MpBatch {
 
 __device__ __forceinline__ int device_env_index() { return blockIdx.x * MP_EPC + (threadIdx.x >> 5); }
 
+// One Env per warp, in shared memory (see Coop).  Lane 0 fills it in; every lane then uses it.
+#define MP_SHARED_ENV() __shared__ Env s_env[MP_EPC]; Env &e = s_env[threadIdx.x >> 5]
+
+__device__ __forceinline__ void bind_env_of(Env &e, uint8_t *blocks, int env, const uint16_t *anim, int *red)
+{
+    if ((threadIdx.x & 31) == 0) {
+        bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+        e.anim = anim;
+        e.c.red = red + (threadIdx.x >> 5) * 8;
+    }
+    __syncwarp();
+}
 __device__ __forceinline__ void bind_device_env(Env &e, uint8_t *blocks, const uint16_t *anim, int *red)
 {
-    bind_env(e, blocks + (size_t)device_env_index() * ENV_STRIDE);
-    e.anim = anim;
-    e.c.tid = threadIdx.x & 31;
-    e.c.n = 32;
-    e.c.red = red + (threadIdx.x >> 5) * 8;
+    bind_env_of(e, blocks, device_env_index(), anim, red);
 }
 
 #define MP_ENV_GUARD() const int env = device_env_index(); if (env >= n_envs) return; const int lane = threadIdx.x & 31; (void)lane
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_construct(uint8_t *blocks, co
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     env_construct(e, blocks + (size_t)device_env_index() * ENV_STRIDE);
 }
@@ -90,7 +98,7 @@ k_mp_reset(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *ter
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     if (mask && !mask[env]) return;
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     if (mode == 0) clear_map(e);
     else generate_some_city(e, terrain_seeds[env], sim_seeds[env]);
@@ -101,7 +109,7 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     if (lane == 0) {
         const int32_t *a = txy + (size_t)env * 3;
@@ -132,14 +140,14 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
-    Env e;
-    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
-    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
+    MP_SHARED_ENV();
+    bind_env_of(e, blocks, env, anim, red);
     Scalars *gs = e.s;
     uint32_t *sw = s_scal[threadIdx.x >> 5];
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
     __syncwarp();
-    e.s = reinterpret_cast<Scalars *>(sw);
+    if (lane == 0) e.s = reinterpret_cast<Scalars *>(sw);
+    __syncwarp();
     if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     if (respect_passes) {
         if (e.s->simSpeed) {
@@ -164,7 +172,7 @@ k_mp_call(uint8_t *blocks, const uint16_t *anim, int n_envs, int fn, int a, int 
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     env_call(e, fn, a, b);
 }
@@ -232,7 +240,7 @@ k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t 
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     if (mask && !mask[env]) return;
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
@@ -246,7 +254,7 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
-    Env e;
+    MP_SHARED_ENV();
     bind_device_env(e, blocks, anim, red);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
@@ -266,11 +274,11 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
-    Env e;
-    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
-    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
+    MP_SHARED_ENV();
+    bind_env_of(e, blocks, env, anim, red);
     __shared__ __align__(16) uint16_t s_ovl[MP_EPC][272];      // the tool overlay (256 values + mask) on chip
-    e.ovl = s_ovl[threadIdx.x >> 5];
+    if (lane == 0) e.ovl = s_ovl[threadIdx.x >> 5];
+    __syncwarp();
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     if (lane == 0) gym_step_pre(e, gy, actions[env], static_build != 0);
@@ -289,9 +297,8 @@ k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     const int lane = threadIdx.x & 31;
     (void)lane;
     if (mask && !mask[env]) return;
-    Env e;
-    bind_env(e, blocks + (size_t)env * ENV_STRIDE);
-    e.anim = anim; e.c.tid = lane; e.c.n = 32; e.c.red = red + (threadIdx.x >> 5) * 8;
+    MP_SHARED_ENV();
+    bind_env_of(e, blocks, env, anim, red);
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;

@@ -1513,7 +1513,7 @@ MPD void coop_add(Env &e, int slot, int v)
 {
 #if defined(__CUDA_ARCH__)
     MP_NOUNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (e.c.tid == 0) e.c.red[slot] += v;
+    if (e.c.lead()) e.c.red[slot] += v;
 #else
     e.c.red[slot] += v;
 #endif
@@ -1890,17 +1890,25 @@ MPN void city_evaluation(Env &e)
 }
 
 // ------------------------------------------------------------------ the 16-phase cycle
-// [ALL] simulate.cpp:122-268 simulate
-MPP void simulate(Env &e)
+// value of lane 0 for every lane
+MPD int coop_bcast(Env &e, int v)
 {
-    const int16_t spdPower[3] = { 2, 4, 5 }, spdPtlv[3] = { 2, 7, 17 }, spdCrime[3] = { 1, 8, 18 };
-    const int16_t spdPop[3] = { 1, 9, 19 }, spdFire[3] = { 1, 10, 20 };
-    if (e.c.lead()) {
-        if (S.initSimLoad) S.phaseCycle = 0;
-        else S.phaseCycle &= 15;
-    }
-    e.c.sync();
-    const int phase = S.phaseCycle;
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(0xffffffffu, v, 0);
+#else
+    (void)e;
+    return v;
+#endif
+}
+// scan periods by speed index (simulate.cpp:124-135); si == 2 (simSpeed 3) is the gym path
+MPD bool scan_due(int cyc, int si, int slow, int mid, int fast)
+{
+    return si == 2 ? (cyc % fast) == 0 : (si == 1 ? (cyc % mid) == 0 : (cyc % slow) == 0);
+}
+
+// [ALL] one phase of simulate() (simulate.cpp:122-268).  `phase` is uniform across the lanes.
+MPD void simulate_phase(Env &e, int phase)
+{
     const int si = tclamp((int)S.simSpeed - 1, 0, 2);
     const int cyc = S.simCycle;
     switch (phase) {
@@ -1937,19 +1945,16 @@ MPP void simulate(Env &e)
         if (e.c.lead()) send_messages(e);
         break;
     case 11:
-        if ((si == 2 ? cyc % 5 : cyc % spdPower[si]) == 0) {
-            do_power_scan(e);
-            if (e.c.lead()) S.newPower = 1;
-        }
+        if (scan_due(cyc, si, 2, 4, 5)) do_power_scan(e);          // sets newPower (see do_power_scan)
         break;
     case 12:
-        if ((si == 2 ? cyc % 17 : cyc % spdPtlv[si]) == 0) ptlv_scan(e);
+        if (scan_due(cyc, si, 2, 7, 17)) ptlv_scan(e);
         break;
     case 13:
-        if ((si == 2 ? cyc % 18 : cyc % spdCrime[si]) == 0) crime_scan(e);
+        if (scan_due(cyc, si, 1, 8, 18)) crime_scan(e);
         break;
     case 14:
-        if ((si == 2 ? cyc % 19 : cyc % spdPop[si]) == 0) {
+        if (scan_due(cyc, si, 1, 9, 19)) {
             int cx = S.cityCenterX, cy = S.cityCenterY;
             e.c.sync();
             pop_density_scan(e);
@@ -1957,30 +1962,46 @@ MPP void simulate(Env &e)
         }
         break;
     case 15:
-        if ((si == 2 ? cyc % 20 : cyc % spdFire[si]) == 0) fire_analysis(e);
+        if (scan_due(cyc, si, 1, 10, 20)) fire_analysis(e);
         if (e.c.lead()) do_disasters(e);
         break;
     }
+}
+
+// [ALL] simulate.cpp:122-268 simulate
+MPP void simulate(Env &e)
+{
+    const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
+    e.c.sync();
+    simulate_phase(e, phase);
     e.c.sync();
     if (e.c.lead()) S.phaseCycle = (int16_t)((phase + 1) & 15);
     e.c.sync();
 }
 
-// [ALL] simulate.cpp:98-118 simFrame + main.cpp:403-425 simLoop(true) (heatSteps = 0)
+// [ALL] simulate.cpp:98-118 simFrame + main.cpp:403-425 simLoop(true) (heatSteps = 0).
+// One barrier per frame: the lead lane owns speedCycle / phaseCycle / spriteCycle, every lane
+// reads the phase before the lead moves it on.
 MPN void sim_loop(Env &e)
 {
-    bool run = false;
-    const int speed = S.simSpeed;
-    if (speed != 0) {
-        int sc = S.speedCycle + 1;
-        if (sc > 1023) sc = 0;
-        run = speed >= 3 || !((speed == 1 && (sc % 5) != 0) || (speed == 2 && (sc % 3) != 0));
-        e.c.sync();
-        if (e.c.lead()) S.speedCycle = (int16_t)sc;
+    const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
+    int run = 0;
+    if (e.c.lead()) {
+        const int speed = S.simSpeed;
+        if (speed != 0) {
+            int sc = S.speedCycle + 1;
+            if (sc > 1023) sc = 0;
+            S.speedCycle = (int16_t)sc;
+            run = speed >= 3 || !((speed == 1 && (sc % 5) != 0) || (speed == 2 && (sc % 3) != 0));
+        }
+    }
+    run = coop_bcast(e, run);
+    if (run) {
+        simulate_phase(e, phase);
         e.c.sync();
     }
-    if (run) simulate(e);
     if (e.c.lead()) {
+        if (run) S.phaseCycle = (int16_t)((phase + 1) & 15);
         if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }      // moveObjects with an empty list
         else move_objects(e);
     }

@@ -143,9 +143,26 @@ struct EnvLayout {
 
 // Thread context.  Device: the WARP that owns the env (tid = lane, n = 32; a barrier is a
 // __syncwarp, so the warps of a CTA -- one env each -- never wait on one another).  Host harness:
-// one thread.
+// one thread.  Nothing in it (or in Env) differs between the lanes of a warp -- `tid` reads the
+// lane id from the hardware -- so one Env per warp lives in SHARED memory instead of one copy per
+// thread in local memory (30 pointers x 64 threads x 16 CTAs would not even fit the L1).
+struct LaneId {
+    MPD operator int() const
+    {
+#if defined(__CUDA_ARCH__)
+        return (int)(threadIdx.x & 31u);
+#else
+        return 0;
+#endif
+    }
+};
 struct Coop {
-    int tid, n;
+    LaneId tid;
+#if defined(__CUDACC__)
+    static constexpr int n = 32;
+#else
+    static constexpr int n = 1;
+#endif
     int *red;       // >= 8 ints of shared scratch per env (device) / plain memory (host)
     MPD void sync() const
     {
@@ -153,7 +170,7 @@ struct Coop {
         __syncwarp();
 #endif
     }
-    MPD bool lead() const { return tid == 0; }
+    MPD bool lead() const { return (int)tid == 0; }
 };
 
 struct Env {

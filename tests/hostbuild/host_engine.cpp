@@ -31,7 +31,7 @@ void *mph_new(void)
     h->shadow = nullptr;
     h->blk = (uint8_t *)aligned_alloc(64, (EnvLayout::TOTAL + 63) & ~63);
     bind_env(h->e, h->blk);
-    h->e.c.tid = 0; h->e.c.n = 1; h->e.c.red = h->red;
+    h->e.c.red = h->red;
     for (int i = 0; i < 1024; i++) h->anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) h->anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
     h->e.anim = h->anim;
