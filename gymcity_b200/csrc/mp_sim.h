@@ -1611,15 +1611,22 @@ MPN void ptlv_scan(Env &e)
         int x = i / H2, y = i - x * H2, wx = x * 2, wy = y * 2;
         int plevel = 0;
         bool lvflag = false;
-        MP_NOUNROLL for (int mx = wx; mx <= wx + 1; mx++)
-            MP_NOUNROLL for (int my = wy; my <= wy + 1; my++) {
-                int loc = e.map[tix(mx, my)] & LOMASK;
-                if (loc) {
-                    if (loc < T_RUBBLE) continue;
-                    plevel += pollution_value(loc);
-                    if (loc >= T_ROADBASE) lvflag = true;
+        // only tiles at or above FLOOD pollute or carry land value (getPollutionValue is 0 below
+        // RADTILE, the flag needs ROADBASE), i.e. only tiles of the active bitmap; wy is even, so
+        // the two tiles of a column are one aligned bit pair
+        const int t0 = tix(wx, wy), t1 = t0 + WORLD_H;
+        const unsigned pair = ((e.act[t0 >> 5] >> (t0 & 31)) & 3u) | (((e.act[t1 >> 5] >> (t1 & 31)) & 3u) << 2);
+        if (pair) {
+            MP_NOUNROLL for (int mx = wx; mx <= wx + 1; mx++)
+                MP_NOUNROLL for (int my = wy; my <= wy + 1; my++) {
+                    int loc = e.map[tix(mx, my)] & LOMASK;
+                    if (loc) {
+                        if (loc < T_RUBBLE) continue;
+                        plevel += pollution_value(loc);
+                        if (loc >= T_ROADBASE) lvflag = true;
+                    }
                 }
-            }
+        }
         plevel = tmin(plevel, 255);
         e.tmp1[i] = (uint8_t)plevel;
         if (lvflag) {
@@ -1722,18 +1729,36 @@ MPN void pop_density_scan(Env &e)
     if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; e.c.red[2] = 0; }
     e.c.sync();
     int xt = 0, yt = 0, zt = 0;
-    for (int i = e.c.tid; i < N2; i += e.c.n) {
-        int bx = (i / H2) * 2, by = (i % H2) * 2, v = 0;
-        MP_NOUNROLL for (int dx = 0; dx < 2; dx++)          // scan order inside the 2x2 cluster: last zone wins
-            MP_NOUNROLL for (int dy = 0; dy < 2; dy++) {
-                int mv = e.map[tix(bx + dx, by + dy)];
-                if (mv & ZONEBIT) {
-                    int pop = population_density_of(e, bx + dx, by + dy, mv & LOMASK) * 8;
-                    v = tmin(pop, 254);
-                    xt += bx + dx; yt += by + dy; zt++;
+    // zone centres are active tiles: walk the active bitmap instead of all 12 000 tiles
+    for (int i = e.c.tid; i < N2 / 4; i += e.c.n) reinterpret_cast<uint32_t *>(e.tmp1)[i] = 0;
+    e.c.sync();
+    for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
+        uint32_t m = e.act[w];
+        while (m) {
+            int b = 0;
+#if defined(__CUDA_ARCH__)
+            b = __ffs(m) - 1;
+#else
+            while (!((m >> b) & 1u)) b++;
+#endif
+            m &= m - 1;
+            const int idx = w * 32 + b, mv = e.map[idx];
+            if (!(mv & ZONEBIT)) continue;
+            const int x = idx / WORLD_H, y = idx - x * WORLD_H;
+            xt += x; yt += y; zt++;
+            // "last zone in scan order wins" inside a 2x2 cluster (tempMap1.worldSet overwrites)
+            bool later = false;
+            const int bx = x & ~1, by = y & ~1;
+            MP_NOUNROLL for (int dx = 0; dx < 2; dx++)
+                MP_NOUNROLL for (int dy = 0; dy < 2; dy++) {
+                    const int o = tix(bx + dx, by + dy);
+                    if (o > idx && (e.map[o] & ZONEBIT)) later = true;
                 }
+            if (!later) {
+                int pop = population_density_of(e, x, y, mv & LOMASK) * 8;
+                e.tmp1[(x >> 1) * H2 + (y >> 1)] = (uint8_t)tmin(pop, 254);
             }
-        e.tmp1[i] = (uint8_t)v;
+        }
     }
     coop_add(e, 0, xt);
     coop_add(e, 1, yt);
