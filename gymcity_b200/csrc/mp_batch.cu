@@ -394,7 +394,7 @@ mpb_handle mpb_create(int n_envs, int device)
     MpBatch *b = (MpBatch *)calloc(1, sizeof(MpBatch));
     b->n_envs = n_envs; b->device = device;
     b->passes = 100;
-    b->frames_per_launch = 25;
+    b->frames_per_launch = 13;
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
@@ -415,7 +415,7 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
     b->use_sched = 1;
-    b->groups = 4;
+    b->groups = 8;
     if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&b->ev_done[g], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming);
