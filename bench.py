@@ -35,32 +35,47 @@ def workload(args):
 
 
 class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (one long-running
+    `nvidia-smi -lms 100` child, stopped by PID)."""
+
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.reasons, self.stop_flag, self.max_mhz = gpu, [], set(), False, None
+        self.gpu, self.samples, self.reasons, self.max_mhz, self.proc = gpu, [], set(), None, None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [t.strip() for t in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [t.strip() for t in line.strip().split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                except ValueError:
+                    continue
                 for n, v in zip(names, f[2:6]):
                     if v.lower().startswith("active"):
                         self.reasons.add(n)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
 
     def result(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "window": "warm-up + timed region + e2e region"}
 
 
 def cpu_reference(seconds):
@@ -126,12 +141,12 @@ def run_ours(args):
 
     for i in range(args.age_steps):                 # untimed build-up: cities reach their random-action steady state
         step_dev(i % (W + 2 * K + 2))
-    for i in range(W):
-        step_dev(i)
-    torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        step_dev(i)
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -158,7 +173,8 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     if rank == 0:
-        sampler.stop_flag = True
+        sampler.stop()
+        sampler.join(timeout=2)
     t = torch.tensor([total_ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -20,8 +20,9 @@ using namespace mp;
 
 namespace {
 
-// One warp per city; MP_EPC cities (warps) per CTA so that more than 32 cities fit on an SM.
-constexpr int MP_EPC = 2;
+// One warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's slot is released the
+// moment its city is done instead of waiting for the slower of two (32 CTAs x 64 registers fill the SM).
+constexpr int MP_EPC = 1;
 constexpr int MP_THREADS = 32 * MP_EPC;
 constexpr int ENV_STRIDE = (EnvLayout::TOTAL + 127) & ~127;
 
@@ -124,10 +125,10 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
 // per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
-__global__ void __launch_bounds__(MP_THREADS, 16)
+__global__ void __launch_bounds__(MP_THREADS, 32 / MP_EPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff)
+            int goff, int gcount)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_EPC];
@@ -136,6 +137,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     __shared__ __align__(16) uint32_t s_scal[MP_EPC][(sizeof(Scalars) + 3) / 4];
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
+    if (device_env_index() >= gcount) return;
     const int slot = device_env_index() * gstride + goff;
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
@@ -267,9 +269,10 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-             const int64_t *actions, int static_build, const int *perm, int gstride, int goff)
+             const int64_t *actions, int static_build, const int *perm, int gstride, int goff, int gcount)
 {
     __shared__ int red[8 * MP_EPC];
+    if (device_env_index() >= gcount) return;
     const int slot = device_env_index() * gstride + goff;
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
@@ -288,9 +291,10 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
               float *obs, float *reward, uint8_t *done, int is_reset, const uint8_t *mask, const int *perm,
-              int gstride, int goff)
+              int gstride, int goff, int gcount)
 {
     __shared__ int red[8 * MP_EPC];
+    if (device_env_index() >= gcount) return;
     const int slot = device_env_index() * gstride + goff;
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
@@ -334,22 +338,47 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
-#define MP_GRID_G(b, G, g) ((((b)->n_envs - (g) + (G) - 1) / (G) + MP_EPC - 1) / MP_EPC)
+// Env groups (each on its own stream).  Group 0 holds the `heavy` most expensive envs of the last
+// step (flood / fire fields, 5-10x the mean): isolated there they stretch only their own launches,
+// while the other groups -- the remaining envs dealt out round robin in cost order -- have tight
+// cost distributions and short launch tails.  A group is (offset, stride, count) into the
+// heavy-first permutation.
+struct GroupGeom { int off, stride, count; };
+GroupGeom group_geom(const MpBatch *b, int G, int g)
+{
+    GroupGeom q;
+    if (G <= 1) { q.off = 0; q.stride = 1; q.count = b->n_envs; return q; }
+    int heavy = b->use_sched ? b->n_envs / 64 : 0;                 // ~1.5 % of the batch
+    if (heavy < 1 || G < 3) heavy = 0;
+    if (heavy == 0) { q.off = g; q.stride = G; q.count = (b->n_envs - g + G - 1) / G; return q; }
+    if (g == 0) { q.off = 0; q.stride = 1; q.count = heavy; return q; }
+    q.off = heavy + (g - 1); q.stride = G - 1;
+    q.count = (b->n_envs - q.off + q.stride - 1) / q.stride;
+    if (q.count < 0) q.count = 0;
+    return q;
+}
+#define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
 
 int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, int G = 1, int g = 0)
 {
-    const int F = b->frames_per_launch, P = b->passes;
+    const int P = b->passes;
     const int *perm = b->use_sched ? b->perm : NULL;
-    const int grid = MP_GRID_G(b, G, g);
+    const GroupGeom q = group_geom(b, G, g);
+    // the heavy group is not kept in phase lockstep: with few, very uneven envs every launch would
+    // wait for ITS slowest member (a different env each time), so it runs a whole simTick per launch
+    const int F = (G > 1 && g == 0 && q.stride == 1) ? (P > 0 ? P : 1) : b->frames_per_launch;
+    const int grid = MP_GRID_N(q.count);
     if (grid <= 0) return 0;
     if (P <= 0) {
         if (animate_before)
-            k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm, G, g);
+            k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm,
+                                                     q.stride, q.off, q.count);
         return 0;
     }
     for (int f = 0; f < P; f += F)
         k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                                                 animate_before && f == 0, 1, b->cycles, b->cost, perm, G, g);
+                                                 animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off,
+                                                 q.count);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
@@ -417,8 +446,8 @@ mpb_handle mpb_create(int n_envs, int device)
     b->use_sched = 1;
     b->groups = 8;
     if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
-    for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreateWithFlags(&b->ev_done[g], cudaEventDisableTiming); }
-    cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming);
+    for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
+    cudaEventCreate(&b->ev_start);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
     k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS>>>(b->blocks, b->anim, n_envs);
@@ -459,7 +488,15 @@ int mpb_launches_per_env_step(mpb_handle h)
 {
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
-    return b->groups * (2 + mpb_launches_per_tick(h)) + (b->use_sched ? 3 : 0);
+    int total = b->use_sched ? 4 : 0;                       // memset + 3 scheduling kernels
+    for (int g = 0; g < b->groups; g++) {
+        const GroupGeom q = group_geom(b, b->groups, g);
+        if (q.count <= 0) continue;
+        const int F = (b->groups > 1 && g == 0 && q.stride == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
+        const int per = b->passes > 0 ? (b->passes + F - 1) / F : 1;
+        total += 2 + 2 * per;
+    }
+    return total;
 }
 int mpb_state_bytes(void) { return EnvLayout::PERSISTENT_END; }
 void *mpb_blocks(mpb_handle h) { return h ? ((MpBatch *)h)->blocks : NULL; }
@@ -580,7 +617,7 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     for (int f = 0; f < n; f += F)
         k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0,
                                                                         (n - f < F) ? n - f : F, 0, 0, b->cycles,
-                                                                        b->cost, b->use_sched ? b->perm : NULL, 1, 0);
+                                                                        b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     return 0;
 }
@@ -601,7 +638,7 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     if (!b) return -1;
     cudaSetDevice(b->device);
     launch_sim_tick(b, (cudaStream_t)stream, 0);
-    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0);
+    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     return 0;
 }
@@ -625,6 +662,20 @@ int mpb_read_cycles(mpb_handle h, unsigned long long *out_host)
     CK(cudaMemcpy(out_host, b->cycles, (size_t)b->n_envs * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemset(b->cycles, 0, (size_t)b->n_envs * 8));
     return 0;
+}
+
+int mpb_group_times(mpb_handle h, float *ms_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !ms_out) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    for (int g = 0; g < b->groups; g++) {
+        ms_out[g] = -1.0f;
+        if (b->groups > 1) cudaEventElapsedTime(&ms_out[g], b->ev_start, b->ev_done[g]);
+    }
+    cudaGetLastError();
+    return b->groups;
 }
 
 int mpb_sync(mpb_handle h)
@@ -786,7 +837,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     if (upload_mask(b, mask_host, st)) return -1;
     launch_control_sim_tick(b, st);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0);
+                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -821,14 +872,15 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     if (G > 1) cudaEventRecord(b->ev_start, st);
     for (int g = 0; g < G; g++) {
         cudaStream_t gs = G > 1 ? b->gstream[g] : st;
-        const int grid = MP_GRID_G(b, G, g);
+        const GroupGeom q = group_geom(b, G, g);
+        const int grid = MP_GRID_N(q.count);
         if (grid <= 0) continue;
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
         k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                 actions_dev, static_build, perm, G, g);
+                                                 actions_dev, static_build, perm, q.stride, q.off, q.count);
         launch_control_sim_tick(b, gs, G, g);
         k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                  b->obs, b->reward, b->done, 0, NULL, perm, G, g);
+                                                  b->obs, b->reward, b->done, 0, NULL, perm, q.stride, q.off, q.count);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);

@@ -1404,33 +1404,37 @@ MPN void send_messages(Env &e)
 // Literal replay: numPower counts visits AND pops, so the cut-off depends on traversal order.
 MPN void power_scan_walk(Env &e)
 {
-    int64_t maxPower = S.coalPowerPop * 700L + S.nuclearPowerPop * 2000L;
-    int64_t numPower = 0;
-    while (S.powerStackPointer > 0) {
-        int p = e.pstack[S.powerStackPointer];
-        S.powerStackPointer--;
-        int x = p / WORLD_H, y = p - x * WORLD_H;
-        int anyDir = D_INVALID, conNum;
+    const int maxPower = S.coalPowerPop * 700 + S.nuclearPowerPop * 2000;     // <= 32767 * 2000 < 2^31
+    int numPower = 0, sp = S.powerStackPointer;
+    // index form of Position::move for the four cardinal directions (N, E, S, W)
+    while (sp > 0) {
+        int p = e.pstack[sp];
+        sp--;
+        int step = 0, conNum;
         do {
             numPower++;
-            if (numPower > maxPower) return;
-            if (anyDir != D_INVALID) pos_move(x, y, anyDir);
-            pwr_set(e, x, y);
+            if (numPower > maxPower) { S.powerStackPointer = sp; return; }
+            p += step;
+            e.power[p >> 5] |= 1u << (p & 31);
+            const int x = p / WORLD_H, y = p - x * WORLD_H;
             conNum = 0;
-            int dir = D_N;
-            while (dir < D_END && conNum < 2) {
-                int mx = x, my = y;
-                if (pos_move(mx, my, dir)) {
-                    if ((e.map[tix(mx, my)] & CONDBIT) && !pwr_get(e, mx, my)) {
-                        conNum++;
-                        anyDir = dir;
-                    }
-                }
-                dir += 2;
+#define MP_PW_TRY(cond, off)                                                                          \
+            if (conNum < 2 && (cond)) {                                                                   \
+                const int q = p + (off);                                                                  \
+                if ((e.map[q] & CONDBIT) && !((e.power[q >> 5] >> (q & 31)) & 1u)) { conNum++; step = (off); } \
             }
-            if (conNum > 1) push_power_stack(e, x, y);
+            MP_PW_TRY(y > 0, -1)
+            MP_PW_TRY(x < WORLD_W - 1, WORLD_H)
+            MP_PW_TRY(y < WORLD_H - 1, 1)
+            MP_PW_TRY(x > 0, -WORLD_H)
+#undef MP_PW_TRY
+            if (conNum > 1 && sp < POWER_STACK_SIZE - 2) {
+                sp++;
+                e.pstack[sp] = (uint16_t)p;
+            }
         } while (conNum);
     }
+    S.powerStackPointer = sp;
 }
 
 // [ALL]
@@ -2088,23 +2092,30 @@ MPD void do_sim_init(Env &e)
     e.c.sync();
 }
 
-// [ALL] animate.cpp:204-219 animateTiles.  Each lane owns whole 32-tile words of the active
-// bitmap so that it can refresh them without a race.
+// [ALL] animate.cpp:204-219 animateTiles.  Every tile whose animation successor differs from itself
+// has an id >= FIRE, so animated tiles are a subset of the active bitmap: each lane walks the set
+// bits of the words it owns (and refreshes `need` for the tiles it changes; the id stays >= FIRE so
+// `act` does not change).
 MPN void animate_tiles(Env &e)
 {
     MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = 0, nd = 0;
-        MP_NOUNROLL for (int b = 0; b < 32; b++) {
+        uint32_t m = e.act[w], nd = e.need[w];
+        while (m) {
+            int b = 0;
+#if defined(__CUDA_ARCH__)
+            b = __ffs(m) - 1;
+#else
+            while (!((m >> b) & 1u)) b++;
+#endif
+            m &= m - 1;
             const int i = w * 32 + b;
             int v = e.map[i];
-            if (v & ANIMBIT) {
-                v = e.anim[v & LOMASK] | (v & ALLBITS);
-                e.map[i] = (uint16_t)v;
-            }
-            if (tile_is_active(v)) m |= 1u << b;
-            if (tile_needs_visit(e, i, v)) nd |= 1u << b;
+            if (!(v & ANIMBIT)) continue;
+            const int nv = e.anim[v & LOMASK] | (v & ALLBITS);
+            if (nv == v) continue;
+            e.map[i] = (uint16_t)nv;
+            nd = tile_needs_visit(e, i, nv) ? (nd | (1u << b)) : (nd & ~(1u << b));
         }
-        e.act[w] = m;
         e.need[w] = nd;
     }
     e.c.sync();

@@ -83,7 +83,7 @@ def _bind(L):
         "mpb_create": (vp, [i32, i32]), "mpb_destroy": (None, [vp]),
         "mpb_last_error": (C.c_char_p, [vp]), "mpb_num_envs": (i32, [vp]),
         "mpb_env_stride": (i32, []), "mpb_launches_per_tick": (i32, [vp]), "mpb_launches_per_env_step": (i32, [vp]), "mpb_state_bytes": (i32, []), "mpb_blocks": (vp, [vp]),
-        "mpb_sync": (i32, [vp]), "mpb_read_cycles": (i32, [vp, vp]), "mpb_seed": (i32, [vp, vp, vp]),
+        "mpb_sync": (i32, [vp]), "mpb_read_cycles": (i32, [vp, vp]), "mpb_group_times": (i32, [vp, vp]), "mpb_seed": (i32, [vp, vp, vp]),
         "mpb_set_funds": (i32, [vp, i32, vp]), "mpb_set_passes": (i32, [vp, i32, vp]),
         "mpb_set_disasters": (i32, [vp, i32, vp]),
         "mpb_clear_map": (i32, [vp, vp, vp]), "mpb_generate": (i32, [vp, vp, vp, vp, vp]),
@@ -176,6 +176,11 @@ class EngineBatch:
     def controlSimTick(self): self._ck(self._L.mpb_control_sim_tick(self._h, self._stream()))
     def call(self, fn, a=0, b=0): self._ck(self._L.mpb_call(self._h, FN[fn], int(a), int(b), self._stream()))
     def sync(self): self._ck(self._L.mpb_sync(self._h))
+
+    def group_times(self):
+        out = np.zeros(8, np.float32)
+        g = self._ck(self._L.mpb_group_times(self._h, out.ctypes.data))
+        return out[:g]
 
     def read_cycles(self):
         out = np.zeros(self.n, np.uint64)

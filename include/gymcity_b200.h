@@ -88,6 +88,9 @@ int mpb_sync(mpb_handle h);
 /* Profiling: SM cycles each env's warp spent simulating since the last call (uint64 [n_envs] HOST);
  * max / mean shows the load imbalance a launch has to wait out. */
 int mpb_read_cycles(mpb_handle h, unsigned long long *out_host);
+/* Profiling: milliseconds from the start of the last mpb_env_step to the end of each env group's
+ * work (float [8] HOST); returns the number of groups. */
+int mpb_group_times(mpb_handle h, float *ms_out);
 
 /* Micropolis::seedRandom per env (random.cpp:171-174); seeds_host = int32 [n_envs] HOST. */
 int mpb_seed(mpb_handle h, const int32_t *seeds_host, void *stream);
