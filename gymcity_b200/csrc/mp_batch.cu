@@ -37,6 +37,7 @@ struct MpBatch {
     char err[256];
     int passes;               // host copy of simPasses (corecontrol.py:129 sets 100)
     int frames_per_launch;    // simFrames per k_mp_frames launch (phase lockstep across the batch)
+    int fepc, heavy_fepc;     // envs per CTA of k_mp_frames (frame lockstep inside the CTA), for the heavy group
     unsigned long long *cycles;   // [n_envs] SM cycles each env spent in k_mp_frames since the last read (profiling)
     unsigned int *cost;       // [n_envs] cycles of the current step (schedule key for the next one)
     int *perm;                // [n_envs] env ids, most expensive first
@@ -125,41 +126,53 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
 // per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
-__global__ void __launch_bounds__(MP_THREADS, 32 / MP_EPC)
+// MP_FEPC = envs (warps) per CTA.  MP_FEPC > 1 adds a CTA barrier per frame: the warps of a CTA run
+// the same frame -- the same simulation phase, hence the same code -- at the same time, so an SM's
+// instruction caches hold 32 / MP_FEPC phases' worth of code instead of up to 32 (no_instruction was
+// 42 % of all stall samples with free-running warps; profiles/r01_notes.md).  The heavy-first order
+// puts envs of similar cost next to each other, which keeps the barrier waits short.
+template <int MP_FEPC>
+__global__ void __launch_bounds__(32 * MP_FEPC, 32 / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount)
+            int goff, int gcount, int split_barrier)
 {
     const long long t_begin = clock64();
-    __shared__ int red[8 * MP_EPC];
+    __shared__ int red[8 * MP_FEPC];
     // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
     // lane touches on almost every instruction: it lives in shared memory for the whole launch
-    __shared__ __align__(16) uint32_t s_scal[MP_EPC][(sizeof(Scalars) + 3) / 4];
+    __shared__ __align__(16) uint32_t s_scal[MP_FEPC][(sizeof(Scalars) + 3) / 4];
+    __shared__ Env s_env[MP_FEPC];
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
-    if (device_env_index() >= gcount) return;
-    const int slot = device_env_index() * gstride + goff;
-    if (slot >= n_envs) return;
-    const int env = perm ? perm[slot] : slot;
+    const int widx = blockIdx.x * MP_FEPC + (threadIdx.x >> 5);
+    const int slot = widx * gstride + goff;
+    const bool live = widx < gcount && slot < n_envs;
+    if (MP_FEPC == 1 && !live) return;
     const int lane = threadIdx.x & 31;
-    MP_SHARED_ENV();
-    bind_env_of(e, blocks, env, anim, red);
-    Scalars *gs = e.s;
+    Env &e = s_env[threadIdx.x >> 5];
+    int env = 0;
+    Scalars *gs = NULL;
     uint32_t *sw = s_scal[threadIdx.x >> 5];
-    for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
-    __syncwarp();
-    if (lane == 0) e.s = reinterpret_cast<Scalars *>(sw);
-    __syncwarp();
-    if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
-    if (respect_passes) {
-        if (e.s->simSpeed) {
-            int last = first + count;
-            if (last > e.s->simPasses) last = e.s->simPasses;
-            for (int i = first; i < last; i++) sim_loop(e);
-        }
-    } else {
-        for (int i = 0; i < count; i++) sim_loop(e);
+    if (live) {
+        env = perm ? perm[slot] : slot;
+        bind_env_of(e, blocks, env, anim, red);
+        gs = e.s;
+        for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
+        __syncwarp();
+        if (lane == 0) e.s = reinterpret_cast<Scalars *>(sw);
+        __syncwarp();
+        if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     }
+    MP_NOUNROLL for (int i = 0; i < count; i++) {
+        const bool go = live && (!respect_passes || (e.s->simSpeed && first + i < e.s->simPasses));
+        int ran = 0;
+        if (go) ran = sim_loop_head(e);
+        if (MP_FEPC > 1 && split_barrier) __syncthreads();
+        if (go) sim_loop_tail(e, ran);
+        if (MP_FEPC > 1) __syncthreads();
+    }
+    if (!live) return;
     __syncwarp();
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
     if (lane == 0) {
@@ -337,6 +350,25 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
     return 0;
 }
 
+
+int g_split_barrier = 0;
+// k_mp_frames with `epc` envs per CTA (1, 8 or 16)
+void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, const uint16_t *anim, int n_envs, int first,
+                   int count, int animate_before, int respect_passes, unsigned long long *cycles, unsigned int *cost,
+                   const int *perm, int gstride, int goff, int gcount)
+{
+    if (count_envs <= 0) return;
+    if (epc >= 16)
+        k_mp_frames<16><<<(count_envs + 15) / 16, 512, 0, st>>>(blocks, anim, n_envs, first, count, animate_before,
+                                                                respect_passes, cycles, cost, perm, gstride, goff, gcount, g_split_barrier);
+    else if (epc >= 8)
+        k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(blocks, anim, n_envs, first, count, animate_before,
+                                                             respect_passes, cycles, cost, perm, gstride, goff, gcount, g_split_barrier);
+    else
+        k_mp_frames<1><<<count_envs, 32, 0, st>>>(blocks, anim, n_envs, first, count, animate_before, respect_passes,
+                                                  cycles, cost, perm, gstride, goff, gcount, 0);
+}
+
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
 // Env groups (each on its own stream).  Group 0 holds the `heavy` most expensive envs of the last
 // step (flood / fire fields, 5-10x the mean): isolated there they stretch only their own launches,
@@ -367,18 +399,18 @@ int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, int G = 1, 
     // the heavy group is not kept in phase lockstep: with few, very uneven envs every launch would
     // wait for ITS slowest member (a different env each time), so it runs a whole simTick per launch
     const int F = (G > 1 && g == 0 && q.stride == 1) ? (P > 0 ? P : 1) : b->frames_per_launch;
-    const int grid = MP_GRID_N(q.count);
-    if (grid <= 0) return 0;
+    const bool heavy_group = (G > 1 && g == 0 && q.stride == 1);
+    const int epc = heavy_group ? b->heavy_fepc : b->fepc;
+    if (q.count <= 0) return 0;
     if (P <= 0) {
         if (animate_before)
-            k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm,
-                                                     q.stride, q.off, q.count);
+            launch_frames(epc, q.count, st, b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm, q.stride,
+                          q.off, q.count);
         return 0;
     }
     for (int f = 0; f < P; f += F)
-        k_mp_frames<<<grid, MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                                                 animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off,
-                                                 q.count);
+        launch_frames(epc, q.count, st, b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
+                      animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off, q.count);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
@@ -423,8 +455,13 @@ mpb_handle mpb_create(int n_envs, int device)
     MpBatch *b = (MpBatch *)calloc(1, sizeof(MpBatch));
     b->n_envs = n_envs; b->device = device;
     b->passes = 100;
-    b->frames_per_launch = 13;
+    b->frames_per_launch = 34;
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
+    b->fepc = 16;
+    b->heavy_fepc = 16;
+    if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
+    if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
+    if (const char *fp = getenv("MPB_SPLIT_BARRIER")) g_split_barrier = atoi(fp);
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
@@ -444,7 +481,7 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
     b->use_sched = 1;
-    b->groups = 8;
+    b->groups = 4;
     if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
     cudaEventCreate(&b->ev_start);
@@ -615,9 +652,8 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     cudaSetDevice(b->device);
     const int F = b->frames_per_launch;
     for (int f = 0; f < n; f += F)
-        k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0,
-                                                                        (n - f < F) ? n - f : F, 0, 0, b->cycles,
-                                                                        b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
+        launch_frames(b->fepc, b->n_envs, (cudaStream_t)stream, b->blocks, b->anim, b->n_envs, 0, (n - f < F) ? n - f : F, 0,
+                      0, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     return 0;
 }
@@ -638,7 +674,9 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     if (!b) return -1;
     cudaSetDevice(b->device);
     launch_sim_tick(b, (cudaStream_t)stream, 0);
-    if (animate) k_mp_frames<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
+    if (animate)
+        launch_frames(b->fepc, b->n_envs, (cudaStream_t)stream, b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost,
+                      b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     return 0;
 }

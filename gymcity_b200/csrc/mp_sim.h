@@ -2011,7 +2011,10 @@ MPP void simulate(Env &e)
 // [ALL] simulate.cpp:98-118 simFrame + main.cpp:403-425 simLoop(true) (heatSteps = 0).
 // One barrier per frame: the lead lane owns speedCycle / phaseCycle / spriteCycle, every lane
 // reads the phase before the lead moves it on.
-MPN void sim_loop(Env &e)
+// The frame comes in two halves so that a CTA of several envs can put a barrier between the
+// simulation phase and the sprite pass (each half then runs the same code in every warp).
+// Returns phase + 1 if the phase was simulated, 0 if the speed divider skipped it.
+MPN int sim_loop_head(Env &e)
 {
     const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
     int run = 0;
@@ -2029,12 +2032,21 @@ MPN void sim_loop(Env &e)
         simulate_phase(e, phase);
         e.c.sync();
     }
+    return run ? phase + 1 : 0;
+}
+MPN void sim_loop_tail(Env &e, int ran)
+{
     if (e.c.lead()) {
-        if (run) S.phaseCycle = (int16_t)((phase + 1) & 15);
+        if (ran) S.phaseCycle = (int16_t)(ran & 15);
         if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }      // moveObjects with an empty list
         else move_objects(e);
     }
     e.c.sync();
+}
+MPD void sim_loop(Env &e)
+{
+    const int ran = sim_loop_head(e);
+    sim_loop_tail(e, ran);
 }
 
 // [ALL] simulate.cpp:276-305 doSimInit (+ :390-421 initSimMemory)

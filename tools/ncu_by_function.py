@@ -22,17 +22,25 @@ def main(src_csv, dis_txt, kern):
         if m and labels and labels[-1][1] is None:
             labels[-1][1] = int(m.group(1), 16)
     labels = [l for l in labels if l[1] is not None]
-    rows = list(csv.reader(open(src_csv)))
-    h = rows[1]
-    ia, isamp, iex = h.index('Address'), h.index('# Samples'), h.index('Instructions Executed')
-    stall_cols = [i for i, n in enumerate(h) if n.startswith('stall_')]
-    data = []
-    for r in rows[2:]:
+    # the CSV holds one table per profiled launch ("Kernel Name" row, header row, SASS rows): launches
+    # of the wanted kernel are summed
+    data, h, want = [], None, False
+    for r in csv.reader(open(src_csv)):
+        if r and r[0] == 'Kernel Name':
+            want = kern in r[1]
+            continue
+        if r and r[0] == 'Address':
+            h = r
+            ia, isamp, iex = h.index('Address'), h.index('# Samples'), h.index('Instructions Executed')
+            stall_cols = [i for i, n in enumerate(h) if n.startswith('stall_') and 'Not Issued' not in n]
+            continue
+        if not want or h is None:
+            continue
         try:
-            data.append((int(r[ia], 16), int(r[isamp]), int(r[iex]), r))
+            data.append((int(r[ia], 16), int(r[isamp]), int(r[iex]), {h[i]: r[i] for i in stall_cols}))
         except Exception:
             pass
-    base = data[0][0]
+    base = min(d[0] for d in data)
     agg = {}
     for a, s, x, r in data:
         o = a - base
@@ -45,13 +53,13 @@ def main(src_csv, dis_txt, kern):
         d = agg.setdefault(name, [0, 0, {}])
         d[0] += s
         d[1] += x
-        for i in stall_cols:
+        for k, v in r.items():
             try:
-                v = int(r[i])
+                v = int(v)
             except Exception:
                 v = 0
             if v:
-                d[2][h[i]] = d[2].get(h[i], 0) + v
+                d[2][k] = d[2].get(k, 0) + v
     ts, tx = sum(d[0] for d in agg.values()), sum(d[1] for d in agg.values())
     print("total samples %d  warp-instructions %d" % (ts, tx))
     for n, d in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
