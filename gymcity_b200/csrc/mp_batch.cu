@@ -131,11 +131,14 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // instruction caches hold 32 / MP_FEPC phases' worth of code instead of up to 32 (no_instruction was
 // 42 % of all stall samples with free-running warps; profiles/r01_notes.md).  The heavy-first order
 // puts envs of similar cost next to each other, which keeps the barrier waits short.
+#ifndef MP_FWARPS
+#define MP_FWARPS 32          // resident warps per SM the frame kernel is compiled for (register budget)
+#endif
 template <int MP_FEPC>
-__global__ void __launch_bounds__(32 * MP_FEPC, 32 / MP_FEPC)
+__global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int split_barrier)
+            int goff, int gcount, int split_barrier, unsigned int *prof, int prof_off)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_FEPC];
@@ -164,21 +167,26 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         __syncwarp();
         if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     }
+    const long long t_loop = clock64();
+    unsigned int busy = 0;
     MP_NOUNROLL for (int i = 0; i < count; i++) {
         const bool go = live && (!respect_passes || (e.s->simSpeed && first + i < e.s->simPasses));
         int ran = 0;
+        const unsigned int t0 = (unsigned int)clock64();
         if (go) ran = sim_loop_head(e);
-        if (MP_FEPC > 1 && split_barrier) __syncthreads();
         if (go) sim_loop_tail(e, ran);
-        if (MP_FEPC > 1) __syncthreads();
+        const unsigned int dt = (unsigned int)clock64() - t0;          // this env's own time, barrier waits excluded
+        busy += dt;
+        if (prof && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
+        if (MP_FEPC > 1 && (split_barrier <= 1 || ((i + 1) % split_barrier) == 0)) __syncthreads();
     }
     if (!live) return;
     __syncwarp();
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
     if (lane == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - t_begin);
-        if (cycles) cycles[env] += dt;
-        if (cost) cost[env] += (unsigned int)(dt >> 8);
+        busy += (unsigned int)(t_loop - t_begin);                       // state load, animateTiles
+        if (cycles) cycles[env] += busy;
+        if (cost) cost[env] += busy >> 8;
     }
 }
 
@@ -209,7 +217,7 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
 constexpr int SCHED_BUCKETS = 1024;
 __device__ __forceinline__ int sched_bucket(unsigned int cost)      // cost = cycles >> 8 of one step
 {
-    unsigned int k = cost >> 9;                                      // 2^17 cycles per bucket
+    unsigned int k = cost >> 5;                                      // 2^13 busy cycles per bucket (mean env: ~300)
     return SCHED_BUCKETS - 1 - (int)(k < (unsigned)SCHED_BUCKETS ? k : SCHED_BUCKETS - 1);   // expensive first
 }
 __global__ void k_mp_sched_identity(int *perm, int n)
@@ -352,21 +360,20 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 
 
 int g_split_barrier = 0;
-// k_mp_frames with `epc` envs per CTA (1, 8 or 16)
+unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
+// k_mp_frames with `epc` envs per CTA (1, 8 or 16); prof_off = frame offset of this simTick in the
+// per-frame profile rows (0 for the first simTick of an env-step, 100 for the second)
 void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, const uint16_t *anim, int n_envs, int first,
                    int count, int animate_before, int respect_passes, unsigned long long *cycles, unsigned int *cost,
-                   const int *perm, int gstride, int goff, int gcount)
+                   const int *perm, int gstride, int goff, int gcount, int prof_off = 0)
 {
     if (count_envs <= 0) return;
-    if (epc >= 16)
-        k_mp_frames<16><<<(count_envs + 15) / 16, 512, 0, st>>>(blocks, anim, n_envs, first, count, animate_before,
-                                                                respect_passes, cycles, cost, perm, gstride, goff, gcount, g_split_barrier);
-    else if (epc >= 8)
-        k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(blocks, anim, n_envs, first, count, animate_before,
-                                                             respect_passes, cycles, cost, perm, gstride, goff, gcount, g_split_barrier);
-    else
-        k_mp_frames<1><<<count_envs, 32, 0, st>>>(blocks, anim, n_envs, first, count, animate_before, respect_passes,
-                                                  cycles, cost, perm, gstride, goff, gcount, 0);
+#define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
+                       gcount, g_split_barrier, g_prof, prof_off
+    if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, 0, st>>>(MP_FRAMES_ARGS);
+    else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
+    else k_mp_frames<1><<<count_envs, 32, 0, st>>>(MP_FRAMES_ARGS);
+#undef MP_FRAMES_ARGS
 }
 
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
@@ -410,7 +417,8 @@ int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, int G = 1, 
     }
     for (int f = 0; f < P; f += F)
         launch_frames(epc, q.count, st, b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                      animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off, q.count);
+                      animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off, q.count,
+                      animate_before ? P : 0);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
@@ -714,6 +722,30 @@ int mpb_group_times(mpb_handle h, float *ms_out)
     }
     cudaGetLastError();
     return b->groups;
+}
+
+int mpb_read_schedule(mpb_handle h, int *perm_out_host)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !perm_out_host) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(perm_out_host, b->perm, (size_t)b->n_envs * sizeof(int), cudaMemcpyDeviceToHost));
+    return b->groups;
+}
+
+int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    const size_t bytes = (size_t)b->n_envs * 256 * sizeof(unsigned int);
+    if (out_host && g_prof) CK(cudaMemcpy(out_host, g_prof, bytes, cudaMemcpyDeviceToHost));
+    if (enable && !g_prof) { CK(cudaMalloc(&g_prof, bytes)); }
+    if (enable) CK(cudaMemset(g_prof, 0, bytes));
+    if (!enable && g_prof) { cudaFree(g_prof); g_prof = NULL; }
+    return 0;
 }
 
 int mpb_sync(mpb_handle h)

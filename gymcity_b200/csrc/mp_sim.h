@@ -902,8 +902,25 @@ MPP void scan_tile(Env &e, int idx)
             if (!(rnd16(e) & 3)) do_fire(e, x, y);
             return;
         }
-        if (tile < T_RADTILE) do_flood(e, x, y);
-        else if ((rnd16(e) & 4095) == 0) mset(e, idx, T_DIRT);        // doRadTile :1040-1045
+        if (tile < T_RADTILE) {
+            // doFlood (disasters.cpp:375-405) without the call when nothing happens: a receding flood
+            // tile is one draw (1 in 16 dries up), an advancing one is four draws of which each spreads
+            // 1 in 8 -- 59 % of the visits spread nowhere, and then the four draws are all there is
+            if (S.floodCount > 0) {
+                uint32_t r = S.rng;
+                bool hit = false;
+                MP_NOUNROLL for (int z = 0; z < 4; z++) {
+                    r = r * 1103515245u + 12345u;
+                    hit |= (r & 0x700u) == 0;                          // (draw >> 8) & 7 == 0
+                }
+                if (hit) do_flood(e, x, y);                            // replays the draws from S.rng
+                else S.rng = r;
+            } else if ((rnd16(e) & 15) == 0) {
+                mset(e, idx, T_DIRT);
+            }
+        } else if ((rnd16(e) & 4095) == 0) {
+            mset(e, idx, T_DIRT);                                      // doRadTile :1040-1045
+        }
         return;
     }
     if (S.newPower && (mv & CONDBIT)) set_zone_power(e, x, y);
@@ -923,7 +940,12 @@ MPP void scan_tile(Env &e, int idx)
 // that tile, and the words are re-read (L1 hits) because processing may have activated tiles ahead
 // of the scan position (fire spread, zonePlop, repairZone ...).  Tiles activated BEHIND the scan
 // position are not visited, exactly as in the reference's single forward sweep.
+#ifndef MP_DENSE_RANGE_MIN
 #define MP_DENSE_RANGE_MIN 96       // tiles needing a visit in one scan range before the batching scan is used
+#endif
+#ifndef MP_DENSE_WORD_MIN
+#define MP_DENSE_WORD_MIN 4         // tiles needing a visit in one 32-tile word before the word is batched
+#endif
 
 // ---- dense scan -------------------------------------------------------------------------------
 // A flood, a meltdown or a forest fire turns hundreds to thousands of tiles of one city active; on
@@ -962,9 +984,26 @@ MPD int tile_kind(const Env &e, int v)
 }
 
 #if defined(__CUDA_ARCH__)
+// n steps of the engine's LCG (random.cpp:88-100) in O(log n): step^(2^j) is the affine map
+// x -> A_j x + C_j with A_{j+1} = A_j^2, C_{j+1} = (A_j + 1) C_j; n < 256.
+struct LcgPow { uint32_t a[8], c[8]; };
+__host__ __device__ constexpr LcgPow lcg_pow_table()
+{
+    LcgPow t = {};
+    uint32_t a = 1103515245u, c = 12345u;
+    for (int j = 0; j < 8; j++) {
+        t.a[j] = a; t.c[j] = c;
+        c = (a + 1u) * c;
+        a = a * a;
+    }
+    return t;
+}
 MPD uint32_t lcg_jump(uint32_t x, int n)
 {
-    MP_NOUNROLL for (int q = 0; q < n; q++) x = x * 1103515245u + 12345u;
+    constexpr LcgPow t = lcg_pow_table();
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if ((n >> j) & 1) x = x * t.a[j] + t.c[j];
     return x;
 }
 MPD int lcg_r16(uint32_t x) { return (int)((x & 0xffff00u) >> 8) & 0xffff; }
@@ -1085,7 +1124,7 @@ MPN void map_scan_dense(Env &e, int i0, int i1)
             const int L = __ffs(any) - 1;
             const uint32_t mL = __shfl_sync(0xffffffffu, m, L);
             int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
-            if (__popc(mL) >= 4) {
+            if (__popc(mL) >= MP_DENSE_WORD_MIN) {
                 bool serial_next;
                 t1 = scan_word_batch(e, wb + L, mL, serial_next);
                 if (!serial_next) { pos = t1; continue; }
@@ -1105,9 +1144,16 @@ MPP void map_scan(Env &e, int x1, int x2)
     int pos = i0;                                   // first tile not yet passed by the scan
 #if defined(__CUDA_ARCH__)
     const int lane = e.c.tid;
-    {   // dense range (flood / radiation / fire field)?  then the batching scan takes it
-        int cnt = 0;
-        MP_NOUNROLL for (int w = w0 + lane; w <= w1; w += 32) cnt += __popc(e.need[w]);
+    {   // one look at the strip's words (<= 64): nothing to visit (the usual case outside the build
+        // window) ends the phase here; a dense range (flood / radiation / fire field) goes to the
+        // batching scan
+        const int wa = w0 + lane, wb2 = w0 + 32 + lane;
+        uint32_t a = (wa <= w1) ? e.need[wa] : 0u, b = (wb2 <= w1) ? e.need[wb2] : 0u;
+        if (wa == w0) a &= 0xffffffffu << (i0 & 31);
+        if (wa == w1 && (i1 & 31)) a &= 0xffffffffu >> (32 - (i1 & 31));
+        if (wb2 == w1 && (i1 & 31)) b &= 0xffffffffu >> (32 - (i1 & 31));
+        if (!__any_sync(0xffffffffu, (a | b) != 0)) return;
+        int cnt = __popc(a) + __popc(b);
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (cnt >= MP_DENSE_RANGE_MIN) {
             map_scan_dense(e, i0, i1);
@@ -1125,12 +1171,24 @@ MPP void map_scan(Env &e, int x1, int x2)
             if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
             const unsigned any = __ballot_sync(0xffffffffu, m != 0);
             if (!any) break;
-            const int L = __ffs(any) - 1;
-            const uint32_t mL = __shfl_sync(0xffffffffu, m, L);     // the word being worked on
-            const int t1 = (wb + L) * 32 + (__ffs(mL) - 1);
-            if (lane == 0) scan_tile(e, t1);
+            const int wi = wb + __ffs(any) - 1;             // first word with work: the serial lane takes all of it
+            if (lane == 0) {
+                const int hiw = i1 - wi * 32;
+                const uint32_t top = hiw < 32 ? (0xffffffffu >> (32 - hiw)) : 0xffffffffu;
+                int p = pos - wi * 32;                      // bits below p are behind the scan
+                if (p < 0) p = 0;
+                for (;;) {
+                    // re-read: the visit may have activated tiles ahead of the scan position
+                    const uint32_t mm = e.need[wi] & top & (0xffffffffu << p);
+                    if (!mm) break;
+                    const int bit = __ffs(mm) - 1;
+                    scan_tile(e, wi * 32 + bit);
+                    if (bit == 31) break;
+                    p = bit + 1;
+                }
+            }
             __syncwarp();
-            pos = t1 + 1;
+            pos = (wi + 1) * 32;
         }
     }
 #else

@@ -83,7 +83,7 @@ def _bind(L):
         "mpb_create": (vp, [i32, i32]), "mpb_destroy": (None, [vp]),
         "mpb_last_error": (C.c_char_p, [vp]), "mpb_num_envs": (i32, [vp]),
         "mpb_env_stride": (i32, []), "mpb_launches_per_tick": (i32, [vp]), "mpb_launches_per_env_step": (i32, [vp]), "mpb_state_bytes": (i32, []), "mpb_blocks": (vp, [vp]),
-        "mpb_sync": (i32, [vp]), "mpb_read_cycles": (i32, [vp, vp]), "mpb_group_times": (i32, [vp, vp]), "mpb_seed": (i32, [vp, vp, vp]),
+        "mpb_sync": (i32, [vp]), "mpb_read_cycles": (i32, [vp, vp]), "mpb_group_times": (i32, [vp, vp]), "mpb_frame_profile": (i32, [vp, i32, vp]), "mpb_read_schedule": (i32, [vp, vp]), "mpb_seed": (i32, [vp, vp, vp]),
         "mpb_set_funds": (i32, [vp, i32, vp]), "mpb_set_passes": (i32, [vp, i32, vp]),
         "mpb_set_disasters": (i32, [vp, i32, vp]),
         "mpb_clear_map": (i32, [vp, vp, vp]), "mpb_generate": (i32, [vp, vp, vp, vp, vp]),
@@ -181,6 +181,16 @@ class EngineBatch:
         out = np.zeros(8, np.float32)
         g = self._ck(self._L.mpb_group_times(self._h, out.ctypes.data))
         return out[:g]
+
+    def frame_profile(self, enable=True, read=False):
+        out = np.zeros((self.n, 256), np.uint32) if read else None
+        self._ck(self._L.mpb_frame_profile(self._h, int(enable), out.ctypes.data if read else None))
+        return out
+
+    def read_schedule(self):
+        out = np.zeros(self.n, np.int32)
+        g = self._ck(self._L.mpb_read_schedule(self._h, out.ctypes.data))
+        return out, g
 
     def read_cycles(self):
         out = np.zeros(self.n, np.uint64)

@@ -91,6 +91,13 @@ int mpb_read_cycles(mpb_handle h, unsigned long long *out_host);
 /* Profiling: milliseconds from the start of the last mpb_env_step to the end of each env group's
  * work (float [8] HOST); returns the number of groups. */
 int mpb_group_times(mpb_handle h, float *ms_out);
+/* Profiling: per-env per-frame SM cycles of the next env-steps (uint32 [n_envs][256] HOST, frames 0..199 of
+ * an env-step used): enable != 0 starts / clears the recording, out_host (may be NULL) receives what was
+ * recorded so far, enable == 0 stops and frees it.  One batch per process at a time. */
+int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host);
+/* Profiling: the heavy-first env order the NEXT env-step's launches use (int32 [n_envs] HOST); returns the
+ * number of env groups. */
+int mpb_read_schedule(mpb_handle h, int *perm_out_host);
 
 /* Micropolis::seedRandom per env (random.cpp:171-174); seeds_host = int32 [n_envs] HOST. */
 int mpb_seed(mpb_handle h, const int32_t *seeds_host, void *stream);
