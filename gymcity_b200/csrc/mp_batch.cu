@@ -138,7 +138,7 @@ template <int MP_FEPC>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int split_barrier, unsigned int *prof, int prof_off)
+            int goff, int gcount, int skew, unsigned int *prof, int prof_off)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_FEPC];
@@ -167,9 +167,31 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         __syncwarp();
         if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     }
+    // Frame lockstep with bounded skew: a warp may start frame i once every warp of the CTA has
+    // finished frame i - skew - 1 (skew = 0 is a barrier per frame).  One mbarrier per frame in a ring
+    // of 8: lane 0 of every warp arrives after its frame, everybody polls the parity of the frame it
+    // depends on.  A slot is reused for frame g + 8 only by warps that have passed the wait for frame
+    // g + 8 - skew - 1 >= g, so the phase being waited for cannot be overtaken (skew <= 7).
+    __shared__ __align__(8) unsigned long long s_bar[8];
+    if (MP_FEPC > 1) {
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 8; k++)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[k])), "r"(MP_FEPC));
+        }
+        __syncthreads();
+    }
     const long long t_loop = clock64();
     unsigned int busy = 0;
     MP_NOUNROLL for (int i = 0; i < count; i++) {
+        if (MP_FEPC > 1 && i > skew) {
+            const int dep = i - skew - 1;
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[dep & 7]), parity = (dep >> 3) & 1;
+            unsigned done;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            } while (!done);
+        }
         const bool go = live && (!respect_passes || (e.s->simSpeed && first + i < e.s->simPasses));
         int ran = 0;
         const unsigned int t0 = (unsigned int)clock64();
@@ -178,7 +200,14 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         const unsigned int dt = (unsigned int)clock64() - t0;          // this env's own time, barrier waits excluded
         busy += dt;
         if (prof && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
-        if (MP_FEPC > 1 && (split_barrier <= 1 || ((i + 1) % split_barrier) == 0)) __syncthreads();
+        if (MP_FEPC > 1) {
+            __syncwarp();
+            if (lane == 0) {
+                unsigned long long st;
+                asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((unsigned)__cvta_generic_to_shared(&s_bar[i & 7])) : "memory");
+                (void)st;
+            }
+        }
     }
     if (!live) return;
     __syncwarp();
@@ -359,7 +388,8 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 
-int g_split_barrier = 0;
+int g_pad_smem = 0;               // experiment: dynamic shared memory per CTA (limits CTAs per SM)
+int g_skew = 0;                   // frames a warp may run ahead of the slowest warp of its CTA (0..7)
 unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
 // k_mp_frames with `epc` envs per CTA (1, 8 or 16); prof_off = frame offset of this simTick in the
 // per-frame profile rows (0 for the first simTick of an env-step, 100 for the second)
@@ -369,8 +399,8 @@ void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, co
 {
     if (count_envs <= 0) return;
 #define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
-                       gcount, g_split_barrier, g_prof, prof_off
-    if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, 0, st>>>(MP_FRAMES_ARGS);
+                       gcount, g_skew, g_prof, prof_off
+    if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
     else k_mp_frames<1><<<count_envs, 32, 0, st>>>(MP_FRAMES_ARGS);
 #undef MP_FRAMES_ARGS
@@ -469,7 +499,15 @@ mpb_handle mpb_create(int n_envs, int device)
     b->heavy_fepc = 16;
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
-    if (const char *fp = getenv("MPB_SPLIT_BARRIER")) g_split_barrier = atoi(fp);
+    if (const char *fp = getenv("MPB_CARVEOUT")) {           // experiment: shared-memory share of the L1 (percent)
+        cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
+        cudaFuncSetAttribute(k_mp_frames<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
+    }
+    if (const char *fp = getenv("MPB_PAD_SMEM")) {
+        g_pad_smem = atoi(fp);
+        cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_pad_smem);
+    }
+    if (const char *fp = getenv("MPB_SKEW")) { int v = atoi(fp); g_skew = v < 0 ? 0 : (v > 7 ? 7 : v); }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
@@ -489,7 +527,7 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
     b->use_sched = 1;
-    b->groups = 4;
+    b->groups = 3;
     if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
     cudaEventCreate(&b->ev_start);

@@ -268,7 +268,11 @@ MPD bool tile_needs_visit(const Env &e, int idx, int v)
     const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power[idx >> 5] >> (idx & 31)) & 1u);
     return ((v & PWRBIT) != 0) != want;
 }
+#if defined(MP_MSET_NOINLINE)
+MPN void mset(Env &e, int idx, int v)
+#else
 MPD void mset(Env &e, int idx, int v)
+#endif
 {
     e.map[idx] = (uint16_t)v;
     const uint32_t bit = 1u << (idx & 31);
