@@ -24,13 +24,35 @@ if ROOT not in sys.path:
 
 METRIC = "Micropolis env-ticks/sec"
 UNIT = "env-ticks/s"
-B_TICK_16 = 161533          # algorithmic bytes per env-tick at 16x16
+B_STATE = 57722             # S1, S3-S8 as the reference stores them
+
+
+def b_tick(W, H):
+    """Algorithmic bytes per env-tick: state + shadow read and written once, observation
+    written once, 9 bytes of action / reward / done."""
+    return 2 * (B_STATE + 26 * W * H) + 32 * W * H * 4 + 9
+
+
+# BASELINE.json configs as bench workloads.  "mp16" is the headline (config 5's per-GPU share, and config
+# 1's setup batched); the others are reported on request (--workload) and are otherwise parity-test cases.
+WORKLOADS = {
+    "mp16": dict(size=16, envs=32768, xs=16, ys=8, puzzle=False,
+                 text="MicropolisEnv 16x16 window @ (16,8), terrain path, uniform random actions"),
+    "mp32puzzle": dict(size=32, envs=8192, xs=16, ys=8, puzzle=True,
+                       text="MicropolisEnv 32x32 power puzzle (5 static Residential + 1 static Nuclear, Wire-only "
+                            "actions), terrain path"),
+    "mp120": dict(size=(120, 100), envs=2048, xs=0, ys=0, puzzle=False,
+                  text="Full 120x100 world window @ (0,0), terrain path, uniform random actions over all 20 tools"),
+}
 
 
 def workload(args):
-    return {"workload": "MicropolisEnv 16x16 window @ (16,8), terrain path, uniform random actions, "
-                        "%d envs/GPU, env-tick = action + setFunds + 200 simFrames + animateTiles + obs/reward" % args.envs,
-            "envs_per_gpu": args.envs, "map": "16x16 window of the 120x100 world", "sim_frames_per_tick": 200,
+    w = WORKLOADS[args.workload]
+    W, H = (w["size"], w["size"]) if isinstance(w["size"], int) else w["size"]
+    return {"workload": "%s, %d envs/GPU, env-tick = action + setFunds + 200 simFrames + animateTiles + obs/reward"
+                        % (w["text"], args.envs),
+            "name": args.workload, "envs_per_gpu": args.envs, "map": "%dx%d window of the 120x100 world" % (W, H),
+            "sim_frames_per_tick": 200,
             "l2": "state working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (args.envs * 95e3 / 1e9)}
 
 
@@ -78,13 +100,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(s), "window": "warm-up + timed region + e2e region"}
 
 
-def cpu_reference(seconds):
+def cpu_reference(seconds, name="mp16"):
     from oracle import cpu_bench
-    rate, procs, steps, wall = cpu_bench.run(seconds=seconds)
+    w = WORKLOADS[name]
+    W, H = (w["size"], w["size"]) if isinstance(w["size"], int) else w["size"]
+    rate, procs, steps, wall = cpu_bench.run(seconds=seconds, win=W, win_h=H, xs=w["xs"], ys=w["ys"])
     return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
             "sample": "%d env-ticks over %d processes (one reference engine each, pinned one per core), %.1f s "
-                      "busy each, 16x16 window, terrain path, uniform random tool + Water/Land/Clear per tick, "
-                      "C++ loop (oracle/ref_shim.cpp mpref_bench_rollout)" % (steps, procs, seconds)}
+                      "busy each, %dx%d window, terrain path, uniform random tool + Water/Land/Clear per tick, "
+                      "C++ loop (oracle/ref_shim.cpp mpref_bench_rollout)" % (steps, procs, seconds, W, H)}
 
 
 def run_reference(args):
@@ -93,7 +117,7 @@ def run_reference(args):
         return
     per = max(2.0, min(20.0, 4.0 * max(1, args.steps) / 10))
     t0 = time.perf_counter()
-    cb = cpu_reference(per)
+    cb = cpu_reference(per, args.workload)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16/uint16 (+fp32 valves)", "data": "synthetic",
@@ -121,11 +145,13 @@ def run_ours(args):
     # the reference-engine baseline runs first on rank 0 (host cores only), before the GPU is busy
     cb = None
     if rank == 0 and not args.no_cpu_baseline:
-        cb = cpu_reference(args.cpu_seconds)
+        cb = cpu_reference(args.cpu_seconds, args.workload)
 
+    wl = WORKLOADS[args.workload]
     env = MicropolisEnv(num_envs=E, device=local, env_offset=rank * E)
     env.seed(args.seed)
-    env.setMapSize(16, max_step=10 ** 9, empty_start=False)
+    env.setMapSize(wl["size"], max_step=10 ** 9, empty_start=False, power_puzzle=wl["puzzle"], MAP_XS=wl["xs"],
+                   MAP_YS=wl["ys"])
     env.reset()
     m = env.micro
     nA = env.action_space.n
@@ -189,10 +215,11 @@ def run_ours(args):
         except Exception:
             peak = 6650.0
         avg_kernel_s = (sum(kern_ms) / K) / 1000.0
-        achieved = B_TICK_16 * E / avg_kernel_s / 1e9
+        B = b_tick(env.MAP_X, env.MAP_Y)
+        achieved = B * E / avg_kernel_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.workload == "mp16":
             try:
                 tj = json.load(open(tp))
                 traffic = tj.get("dram_bytes_per_env_tick") * E if tj.get("dram_bytes_per_env_tick") else None
@@ -208,10 +235,10 @@ def run_ours(args):
             "e2e": {"value": world * E * K / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * 5,
                     "note": "mpb_env_step_host: int64 actions H2D from pinned memory, fused step, float32 reward + "
-                            "uint8 done D2H; the (N,32,16,16) fp32 observation stays in HBM for the learner (DLPack)"},
+                            "uint8 done D2H; the (N,32,W,H) fp32 observation stays in HBM for the learner (DLPack)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_tick": B_TICK_16,
+                         "algorithmic_bytes_per_env_tick": B,
                          "note": "the tick is latency/issue bound on the RNG-ordered serial lane, not HBM bound "
                                  "(SURVEY 8d): frac is expected to be a few percent"},
             "cpu_baseline": cb, "clocks": sampler.result(), "reward_checksum": checksum,
@@ -222,19 +249,100 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_gol(args):
+    """BASELINE config 2: 1-player Game of Life 16x16 torus, N batched envs, uniform random toggle per tick
+    (multi_env.py:170-232).  Reported on request (--workload gol16); a different metric from the headline."""
+    import numpy as np
+    import torch
+    from gymcity_b200 import GoLMultiEnv
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N, K, W = args.envs, args.steps, max(3, args.warmup)
+    w = 16
+    env = GoLMultiEnv()
+    env.configure(map_width=w, num_proc=N, max_step=10 ** 9, device=local)
+    rng = np.random.default_rng(args.seed)
+    env.set_state((rng.random((N, w, w)) < 0.2).astype(np.uint8))
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed)
+    acts = torch.randint(0, w * w, (64, N), device=dev, dtype=torch.int64, generator=g)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    inner = 1
+    for i in range(W):
+        env.step(acts[i % 64])
+    torch.cuda.synchronize(dev)
+    ms = []
+    for i in range(K):
+        flush.zero_()                                                 # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        env.step(acts[i % 64])
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1))
+    total_ms = sum(ms)
+    acts_h = acts.cpu().numpy()
+    rew_h = np.zeros(N, np.float32)
+    env.step_host(acts_h[0], rew_h)
+    t0 = time.perf_counter()
+    for i in range(K):
+        env.step_host(acts_h[i % 64], rew_h)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    try:
+        peak, src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        peak, src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+    B = 32 + 32 + 8 + 4 + 4 + 1 + w * w * 4           # packed rows r/w, int64 action, reward, pop, done, fp32 state plane
+    achieved = B * N / (total_ms / K / 1000.0) / 1e9
+    # CPU baseline: the numpy restatement of world_pytorch.py (oracle/gol_oracle.py), one core, bounded sample
+    from oracle import gol_oracle as go
+    n_cpu = min(N, 4096)
+    st = (rng.random((n_cpu, w, w)) < 0.2).astype(np.uint8)
+    t1 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t1 < 3.0:
+        st, _, _ = go.multi_step(st, rng.integers(0, w * w, n_cpu), w * w * 2 / 3, w * w * 2 / 3, 10 ** 9, n_cpu)
+        reps += 1
+    cpu_rate = reps * n_cpu / (time.perf_counter() - t1)
+    line = {"metric": "Game of Life env-ticks/sec", "value": N * K / (total_ms / 1000.0), "unit": UNIT, "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-packed rows", "data": "synthetic",
+            "config": {"workload": "1-player Game of Life 16x16 torus, %d batched envs, uniform random toggle per tick" % N,
+                       "name": "gol16", "envs_per_gpu": N, "l2": "256 MB buffer written between timed steps (L2 flush)"},
+            "gpu_launches": K, "kernels": "k_gol_step (one launch per env-tick of the whole batch)",
+            "e2e": {"value": N * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 4,
+                    "note": "golb_step_host: int64 actions H2D, step, float32 rewards D2H; the (N,2,16,16) fp32 "
+                            "observation stays in HBM (DLPack)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": src, "algorithmic_bytes_per_env_tick": B},
+            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d numpy steps of %d boards (oracle/gol_oracle.py multi_step)" % (reps, n_cpu)}}
+    print(json.dumps(line), flush=True)
+    env.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=32768, help="envs per GPU")
+    ap.add_argument("--workload", default="mp16", choices=sorted(WORKLOADS) + ["gol16"])
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--age-steps", type=int, default=40,
                     help="untimed env-ticks before the warm-up so the random-action cities are in steady state")
     args = ap.parse_args()
+    if args.workload == "gol16":
+        args.envs = args.envs or 4096
+        return run_gol(args)
+    if args.envs is None:
+        args.envs = WORKLOADS[args.workload]["envs"]
     if args.impl == "reference":
         run_reference(args)
     else:

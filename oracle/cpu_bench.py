@@ -16,7 +16,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(idx, seconds, win, terrain):
+def _worker(idx, seconds, win, terrain, win_h=None, xs=16, ys=8):
     try:
         os.sched_setaffinity(0, {idx % (os.cpu_count() or 1)})
     except Exception:
@@ -29,22 +29,23 @@ def _worker(idx, seconds, win, terrain):
     else:
         r.clearMap()
     r.seed(idx)
-    r.bench_rollout(50, win, win, 16, 8, act_seed=idx)          # warm-up
+    win_h = win_h or win
+    r.bench_rollout(50, win, win_h, xs, ys, act_seed=idx)       # warm-up
     steps, busy = 0, 0.0
     t_end = time.perf_counter() + seconds
     while time.perf_counter() < t_end:
-        secs, _ = r.bench_rollout(250, win, win, 16, 8, act_seed=idx * 7919 + steps)
+        secs, _ = r.bench_rollout(250, win, win_h, xs, ys, act_seed=idx * 7919 + steps)
         steps += 250
         busy += secs
     print(json.dumps({"steps": steps, "busy": busy}), flush=True)
 
 
-def run(seconds=8.0, procs=None, win=16, terrain=True):
+def run(seconds=8.0, procs=None, win=16, terrain=True, win_h=None, xs=16, ys=8):
     """Returns (env_ticks_per_s_total, procs, total_steps, wall_seconds)."""
     procs = procs or (os.cpu_count() or 1)
     t0 = time.perf_counter()
     ps = [subprocess.Popen([sys.executable, "-m", "oracle.cpu_bench", "--worker", str(i), str(seconds), str(win),
-                            str(int(terrain))], cwd=ROOT, stdout=subprocess.PIPE, text=True)
+                            str(int(terrain)), str(win_h or win), str(xs), str(ys)], cwd=ROOT, stdout=subprocess.PIPE, text=True)
           for i in range(procs)]
     res = []
     for p in ps:
@@ -59,6 +60,7 @@ def run(seconds=8.0, procs=None, win=16, terrain=True):
 
 if __name__ == "__main__":
     if len(sys.argv) >= 6 and sys.argv[1] == "--worker":
-        _worker(int(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), bool(int(sys.argv[5])))
+        extra = [int(a) for a in sys.argv[6:9]]
+        _worker(int(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), bool(int(sys.argv[5])), *extra)
     else:
         print(run(seconds=float(sys.argv[1]) if len(sys.argv) > 1 else 3.0))

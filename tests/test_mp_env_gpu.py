@@ -135,3 +135,22 @@ def test_step_host_end_to_end():
     assert np.array_equal(rew, env.micro.reward.cpu().numpy().reshape(-1))
     assert not done.any()
     env.close()
+
+
+def test_1000_tick_seeded_rollout_bit_exact():
+    """The north-star parity bar: 1000 env-ticks (200 000 simFrames) of seeded random actions, tile map,
+    power map, pollution / land value / crime / density maps, population and RCI demand bit-exact against
+    the reference engine, checked every 100 ticks and at the end (observation and reward every tick)."""
+    n, size, steps = 4, 16, 1000
+    seeds = np.arange(n) + 31
+    env, refs = _batch(n, size, True, 10 ** 9, seeds)
+    _finish(env, refs)
+    rng = np.random.default_rng(7)
+    for t in range(steps):
+        acts = rng.integers(0, 20 * size * size, n).astype(np.int64)
+        _compare_step(env, refs, acts, False, t)
+        if (t + 1) % 100 == 0:
+            for i, r in enumerate(refs):
+                d = diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+                assert not d, (t, i, d)
+    env.close()
