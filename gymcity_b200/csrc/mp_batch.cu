@@ -173,18 +173,29 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     // depends on.  A slot is reused for frame g + 8 only by warps that have passed the wait for frame
     // g + 8 - skew - 1 >= g, so the phase being waited for cannot be overtaken (skew <= 7).
     __shared__ __align__(8) unsigned long long s_bar[8];
+    __shared__ int s_ph0;
     if (MP_FEPC > 1) {
         if (threadIdx.x == 0) {
             for (int k = 0; k < 8; k++)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[k])), "r"(MP_FEPC));
         }
+        if (threadIdx.x == 0) s_ph0 = live ? (e.s->initSimLoad ? 0 : (e.s->phaseCycle & 15)) : 0;
         __syncthreads();
     }
+    const int scan_block = skew >> 8;
+    skew &= 255;
     const long long t_loop = clock64();
     unsigned int busy = 0;
     MP_NOUNROLL for (int i = 0; i < count; i++) {
-        if (MP_FEPC > 1 && i > skew) {
-            const int dep = i - skew - 1;
+        // The eight map-scan phases (1..8) run the same code, so they need no lockstep among themselves:
+        // a frame in that block waits only for the frame that ended phase 0.  The block decision uses the
+        // CTA's nominal phase (warp 0's env) so that every warp waits on the same frames.
+        int dep = i - skew - 1;
+        if (scan_block) {
+            const int ph = (s_ph0 + i) & 15;
+            if (ph >= 1 && ph <= 8 && i - ph < dep) dep = i - ph;
+        }
+        if (MP_FEPC > 1 && dep >= 0) {
             const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[dep & 7]), parity = (dep >> 3) & 1;
             unsigned done;
             do {
@@ -388,6 +399,7 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 
+int g_scan_block = 1;             // map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
 int g_pad_smem = 0;               // experiment: dynamic shared memory per CTA (limits CTAs per SM)
 int g_skew = 0;                   // frames a warp may run ahead of the slowest warp of its CTA (0..7)
 unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
@@ -399,8 +411,9 @@ void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, co
 {
     if (count_envs <= 0) return;
 #define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
-                       gcount, g_skew, g_prof, prof_off
-    if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
+                       gcount, g_skew | (g_scan_block << 8), g_prof, prof_off
+    if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 0, st>>>(MP_FRAMES_ARGS);
+    else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
     else k_mp_frames<1><<<count_envs, 32, 0, st>>>(MP_FRAMES_ARGS);
 #undef MP_FRAMES_ARGS
@@ -493,16 +506,17 @@ mpb_handle mpb_create(int n_envs, int device)
     MpBatch *b = (MpBatch *)calloc(1, sizeof(MpBatch));
     b->n_envs = n_envs; b->device = device;
     b->passes = 100;
-    b->frames_per_launch = 34;
+    b->frames_per_launch = 50;
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
-    b->fepc = 16;
-    b->heavy_fepc = 16;
+    b->fepc = 32;
+    b->heavy_fepc = 32;
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
     if (const char *fp = getenv("MPB_CARVEOUT")) {           // experiment: shared-memory share of the L1 (percent)
         cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
         cudaFuncSetAttribute(k_mp_frames<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
     }
+    if (const char *fp = getenv("MPB_SCAN_BLOCK")) g_scan_block = atoi(fp) != 0;
     if (const char *fp = getenv("MPB_PAD_SMEM")) {
         g_pad_smem = atoi(fp);
         cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_pad_smem);
