@@ -132,9 +132,27 @@ k_gol_step(uint32_t *__restrict__ rows, const int64_t *__restrict__ actions,
             p = s;
         }
     }
+    if (SHFL && w == 16 && obs) {
+        // 16x16 boards: a warp holds two boards.  Instead of every lane writing its own row (four 16-byte
+        // stores 64 bytes apart from their neighbours'), the rows are redistributed by shuffle so that
+        // each store instruction writes 16 consecutive float4 per board: chunk c = k * 16 + j of a board's
+        // 1 KB state plane is quarter (j & 3) of row (k * 4 + j / 4).
+        const int lane = threadIdx.x & 31, j = lane & 15, half = lane & 16;
+        float4 *o = reinterpret_cast<float4 *>(obs + ((size_t)env * 2 + 1) * 256);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t r = __shfl_sync(0xffffffffu, nxt, half + k * 4 + (j >> 2)) >> ((j & 3) * 4);
+            float4 v;
+            v.x = (float)(r & 1u);
+            v.y = (float)((r >> 1) & 1u);
+            v.z = (float)((r >> 2) & 1u);
+            v.w = (float)((r >> 3) & 1u);
+            if (live) __stcs(&o[k * 16 + j], v);
+        }
+    }
     if (!live) return;
     rows[(size_t)env * w + x] = nxt;
-    if (obs) {
+    if (obs && !(SHFL && w == 16)) {
         // multi_env.py:235-240: obs = cat(scalar plane, state); plane 0 is written at set_params
         float4 *o = reinterpret_cast<float4 *>(obs + ((size_t)env * 2 + 1) * w * w + (size_t)x * w);
         if ((w & 3) == 0) {
