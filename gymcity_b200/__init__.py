@@ -13,4 +13,7 @@ def __getattr__(name):
     if name in ("MicropolisEnv", "MicropolisControl", "MicropolisVecEnv"):
         from . import micropolis_env
         return getattr(micropolis_env, name)
+    if name == "Extinguisher":
+        from . import wrappers
+        return wrappers.Extinguisher
     raise AttributeError(name)

@@ -327,6 +327,32 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
     }
 }
 
+// Extinguisher wrapper (wrappers.py:10-160): init_age_array / one extinction event per env
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_track_ages(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    MP_SHARED_ENV();
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    gym_init_age_array(e, gy);
+}
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_extinguish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg, int type,
+                    int n_dels, const int32_t *rnd, const uint8_t *mask, int32_t *dels_out)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) { if (lane == 0) dels_out[env] = 0; return; }
+    MP_SHARED_ENV();
+    bind_device_env(e, blocks, anim, red);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    if (lane == 0) dels_out[env] = gym_extinguish(e, gy, type, n_dels, rnd + (size_t)env * (n_dels + 2));
+}
+
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
@@ -980,6 +1006,53 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
     CK(cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (ok_host) memcpy(ok_host, b->host_i32, (size_t)b->n_envs * 4);
+    return 0;
+}
+
+int mpb_env_track_ages(mpb_handle h, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    cudaStream_t st = (cudaStream_t)stream;
+    k_mp_env_track_ages<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
+                       int32_t *dels_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (type < 0 || type > 3 || n_dels < 0 || !rnd_host) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rb = (size_t)b->n_envs * (n_dels + 2) * sizeof(int32_t);
+    int32_t *rnd_dev = NULL;
+    CK(cudaMalloc(&rnd_dev, rb));
+    CK(cudaMemcpyAsync(rnd_dev, rnd_host, rb, cudaMemcpyHostToDevice, st));
+    if (upload_mask(b, mask_host, st)) { cudaFree(rnd_dev); return -1; }
+    k_mp_env_extinguish<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                          type, n_dels, rnd_dev, mask_host ? b->mask : NULL, b->i32_b);
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st);
+    if (le == cudaSuccess) le = cudaStreamSynchronize(st);
+    cudaFree(rnd_dev);
+    if (le != cudaSuccess) return fail(b, "mpb_env_extinguish", le);
+    if (dels_host) memcpy(dels_host, b->host_i32, (size_t)b->n_envs * 4);
+    return 0;
+}
+
+int mpb_env_get_ages(mpb_handle h, int env, int32_t *age_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (env < 0 || env >= b->n_envs || !age_out) return -1;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(b->host_shadow, b->shadow + (size_t)env * b->shadow_stride, b->shadow_stride, cudaMemcpyDeviceToHost));
+    Gym gy;
+    bind_gym(gy, b->host_shadow, &b->cfg);
+    memcpy(age_out, gy.age, (size_t)b->cfg.W * b->cfg.H * 4);
     return 0;
 }
 

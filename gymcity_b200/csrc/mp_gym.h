@@ -34,16 +34,21 @@ struct GymScalars {
     double metrics[GYM_NUM_METRICS], last_metrics[GYM_NUM_METRICS];
     double reward;
     int32_t done, curr_funds;
+    int32_t track_ages, pad_;   // TileMap.track_ages (tilemap.py:201-206), set by the Extinguisher wrapper
 };
 
 struct Gym {
     uint8_t *zone, *stat;       // [W*H] index x*H + y
     int16_t *center;            // [W*H] cx*128 + cy, -1 = None
+    int32_t *age;               // [W*H] TileMap.age_order: num_step of the build, -1 = nothing built
     GymScalars *g;
     const GymCfg *cfg;
 };
 
-MPH int gym_shadow_bytes(int W, int H) { return a16(W * H) * 2 + a16(W * H * 2) + a16((int)sizeof(GymScalars)); }
+MPH int gym_shadow_bytes(int W, int H)
+{
+    return a16(W * H) * 2 + a16(W * H * 2) + a16((int)sizeof(GymScalars)) + a16(W * H * 4);
+}
 MPH void bind_gym(Gym &gy, uint8_t *blk, const GymCfg *cfg)
 {
     int n = cfg->W * cfg->H;
@@ -51,6 +56,7 @@ MPH void bind_gym(Gym &gy, uint8_t *blk, const GymCfg *cfg)
     gy.stat = blk + a16(n);
     gy.center = (int16_t *)(blk + 2 * a16(n));
     gy.g = (GymScalars *)(blk + 2 * a16(n) + a16(n * 2));
+    gy.age = (int32_t *)(blk + 2 * a16(n) + a16(n * 2) + a16((int)sizeof(GymScalars)));
     gy.cfg = cfg;
 }
 
@@ -87,6 +93,7 @@ MPN void gym_update_tile(Env &e, Gym &gy, int x, int y, int zone, int center, in
     const uint32_t is = kZoneFeatures[zone];
     if ((was & F_NATURAL) && !(is & F_NATURAL)) G.n_struct_tiles++;
     if (!(was & F_NATURAL) && (is & F_NATURAL)) G.n_struct_tiles--;
+    if (G.track_ages && (is & F_NATURAL)) gy.age[c] = -1;          // tilemap.py:521-523
     if ((was & F_ROAD) && !(is & F_ROAD)) G.num_roads--;
     else if (!(was & F_ROAD) && (is & F_ROAD)) G.num_roads++;
     if ((was & F_PLANT) && !(is & F_PLANT)) G.num_plants--;
@@ -143,12 +150,16 @@ MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
     int center = (size == 6) ? (x + 1) * 128 + (y + 1) : x * 128 + y;
     if (size == 1) {
         gym_update_tile(e, gy, x, y, zone, center, static_build ? 1 : 0);
+        if (G.track_ages) gy.age[gym_cell(gy, x, y)] = G.num_step;      // :467-468 (also after a 'Land' build)
         return;
     }
     int x0 = tmax(0, x - 1), y0 = tmax(0, y - 1);
     int x1 = tmin(x - 1 + size, (int)CFG.W), y1 = tmin(y - 1 + size, (int)CFG.H);
     MP_NOUNROLL for (int i = x0; i < x1; i++)
-        MP_NOUNROLL for (int j = y0; j < y1; j++) gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
+        MP_NOUNROLL for (int j = y0; j < y1; j++) {
+            gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
+            if (G.track_ages) gy.age[gym_cell(gy, i, j)] = G.num_step;  // :478-479
+        }
 }
 
 // The full agent tool list (corecontrol.py:85-106) as (TileMap zone id, engine EditingTool);
@@ -197,6 +208,81 @@ MPD int gym_apply_action(Env &e, Gym &gy, long long a, bool static_build, bool f
     }
     if (z >= CFG.num_tools) return 0;
     return gym_add_zone_bot(e, gy, x, y, CFG.tool_zone[z], CFG.tool_engine[z], static_build);
+}
+
+// ---- Extinguisher wrapper (gym_city/wrappers.py:10-160) -----------------------------------------
+// [ALL] TileMap.init_age_array (tilemap.py:201-206)
+MPD void gym_init_age_array(Env &e, Gym &gy)
+{
+    const int n = CFG.W * CFG.H;
+    for (int i = e.c.tid; i < n; i += e.c.n) gy.age[i] = -1;
+    if (e.c.lead()) G.track_ages = 1;
+    e.c.sync();
+}
+// micro.doBotTool(x, y, 'Clear', static_build=True)
+MPD void gym_extinct_clear(Env &e, Gym &gy, int x, int y) { gym_add_zone_bot(e, gy, x, y, -2, TOOL_BULLDOZER, true); }
+
+enum : int { XT_AGE = 0, XT_SPATIAL = 1, XT_RANDOM = 2, XT_MONSTER = 3 };
+
+// [LEAD] Extinguisher.extinguish (wrappers.py:42-55).  rnd: n_dels + 2 non-negative integers drawn by
+// the host wrapper (the reference draws from numpy's global stream, which cannot be replayed):
+// XT_RANDOM uses rnd[i] % (number of aged cells) for deletion i, XT_SPATIAL rnd[0] % W, rnd[1] % H as
+// the centre.  Returns the number of deletions (curr_dels).
+MPN int gym_extinguish(Env &e, Gym &gy, int type, int n_dels, const int32_t *rnd)
+{
+    const int W = CFG.W, H = CFG.H, n = W * H;
+    int dels = 0;
+    if (type == XT_MONSTER) { make_monster(e); return 0; }                       // engine.makeMonster()
+    if (type == XT_AGE) {                                                        // elderCleanse :118-141
+        MP_NOUNROLL for (int i = 0; i < n_dels; i++) {
+            int youngest = -1, live = 0;
+            MP_NOUNROLL for (int c = 0; c < n; c++) { const int a = gy.age[c]; youngest = tmax(youngest, a); live += a > -1; }
+            if (!live) break;
+            // ages += (ages < 0) * 2 * youngest; argmin (first minimum in flat order).  With youngest == 0
+            // an unbuilt cell (-1) wins, as in the reference.
+            int best = 0, bestv = 0x7fffffff;
+            MP_NOUNROLL for (int c = 0; c < n; c++) {
+                int a = gy.age[c];
+                if (a < 0) a += 2 * youngest;
+                if (a < bestv) { bestv = a; best = c; }
+            }
+            gym_extinct_clear(e, gy, best / H, best - (best / H) * H);
+            dels++;
+        }
+        e.s->totalFunds = CFG.init_funds;                                       // :140
+        return dels;
+    }
+    if (type == XT_RANDOM) {                                                     // ranDemolish :88-104
+        MP_NOUNROLL for (int i = 0; i < n_dels; i++) {
+            int live = 0;
+            MP_NOUNROLL for (int c = 0; c < n; c++) live += gy.age[c] > -1;
+            if (!live) break;
+            int k = (int)((uint32_t)rnd[i] % (uint32_t)live), pick = -1;
+            MP_NOUNROLL for (int c = 0; c < n; c++)
+                if (gy.age[c] > -1 && k-- == 0) { pick = c; break; }
+            gym_extinct_clear(e, gy, pick / H, pick - (pick / H) * H);
+            dels++;
+        }
+        return dels;
+    }
+    // localWipe :57-67 + clear_border :69-86 (the y bound tests MAP_X, as in the reference)
+    const int x = (int)((uint32_t)rnd[0] % (uint32_t)W), y = (int)((uint32_t)rnd[1] % (uint32_t)H);
+    const int rmax = tmax(tmax(x, W - x < 0 ? x - W : W - x), tmax(y, H - y < 0 ? y - H : H - y));
+    MP_NOUNROLL for (int r = 0; r < rmax; r++) {
+        bool full = false;
+        MP_NOUNROLL for (int xi = x - r; xi < x + r && !full; xi++) {
+            if (xi < 0 || xi >= W) continue;
+            MP_NOUNROLL for (int yi = y - r; yi < y + r; yi++) {
+                if (yi < 0 || yi >= W || yi >= H) continue;
+                if (gy.age[gym_cell(gy, xi, yi)] > 0) {
+                    gym_extinct_clear(e, gy, xi, yi);
+                    if (++dels == n_dels) { full = true; break; }
+                }
+            }
+        }
+        if (dels >= n_dels) break;
+    }
+    return dels;
 }
 
 // [ALL] TileMap.setEmpty (tilemap.py:327-343)

@@ -132,6 +132,8 @@ class MicropolisControl:
             "mpb_env_action": (i32, [vp, vp, i32, i32, vp, vp]), "mpb_env_get_counters": (i32, [vp, vp]), "mpb_env_step": (i32, [vp, vp, i32, vp]),
             "mpb_env_step_host": (i32, [vp, vp, vp, vp, vp]), "mpb_env_ptr": (vp, [vp, i32]),
             "mpb_env_get_shadow": (i32, [vp, i32, vp, vp, vp, vp]),
+            "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+            "mpb_env_get_ages": (i32, [vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

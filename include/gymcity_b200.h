@@ -173,6 +173,21 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
  * Residential / NuclearPowerPlant in a Wire-only env); ok_host = int32 [n_envs] tool success. */
 int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
                    int32_t *ok_host, void *stream);
+
+/* Extinguisher wrapper (gym_city/wrappers.py:10-160).
+ * mpb_env_track_ages: TileMap.init_age_array (tilemap.py:201-206) for every env: from now on the shadow
+ *   map records the num_step of every build (age_order) and -1 for natural cells.
+ * mpb_env_extinguish: one extinction event per env (mask_host: uint8 [n_envs] or NULL = all).
+ *   type 0 'age' (elderCleanse: the n_dels oldest cells are cleared, then setFunds), 1 'spatial'
+ *   (localWipe around a random centre), 2 'random' (ranDemolish), 3 'Monster' (engine.makeMonster()).
+ *   rnd_host: int32 [n_envs][n_dels + 2], non-negative draws of the caller's RNG (the reference uses
+ *   numpy's global stream): 'random' picks aged cell number rnd[i] % count for deletion i, 'spatial'
+ *   uses (rnd[0] % W, rnd[1] % H) as the centre.  dels_host (may be NULL): deletions made, int32 [n_envs].
+ * mpb_env_get_ages: age_order of one env, int32 [W*H] HOST. */
+int mpb_env_track_ages(mpb_handle h, void *stream);
+int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
+                       int32_t *dels_host, void *stream);
+int mpb_env_get_ages(mpb_handle h, int env, int32_t *age_out);
 /* MicropolisEnv.step for every env: one fused launch (action, setFunds, 2 x simPasses simFrames +
  * animateTiles, observation, reward, done).  actions_dev = int64 [n_envs] DEVICE pointer. */
 int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, void *stream);

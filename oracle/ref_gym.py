@@ -88,7 +88,12 @@ class RefTileMap:
         self.static_builds = np.zeros((1, MAP_X, MAP_Y), dtype=int)
         self.centers = np.full((MAP_X, MAP_Y), None)
         self.n_struct_tiles = 0
+        self.track_ages = False
         self.setEmpty()
+
+    def init_age_array(self):                                       # tilemap.py:201-206
+        self.track_ages = True
+        self.age_order = np.full((self.MAP_X, self.MAP_Y), -1, dtype=int)
 
     def setEmpty(self):                                             # tilemap.py:327-343
         self.num_roads = 0
@@ -175,12 +180,16 @@ class RefTileMap:
         center = (x + 1, y + 1) if zone_size == 6 else (x, y)
         if zone_size == 1:
             self.updateTile(x, y, zone, center, static_build)
+            if self.track_ages:
+                self.age_order[x][y] = self.micro.env.num_step         # :467-468
             return
         x0, y0 = max(0, x - 1), max(0, y - 1)
         x1, y1 = min(x - 1 + zone_size, self.MAP_X), min(y - 1 + zone_size, self.MAP_Y)
         for i in range(x0, x1):
             for j in range(y0, y1):
                 self.updateTile(i, j, zone, center, static_build)
+                if self.track_ages:
+                    self.age_order[i][j] = self.micro.env.num_step     # :478-479
 
     def _flags(self, x, y):
         zi = self.zoneInts
@@ -210,6 +219,8 @@ class RefTileMap:
             self.n_struct_tiles += 1
         if not was_natural and is_natural:
             self.n_struct_tiles -= 1
+        if self.track_ages and is_natural:
+            self.age_order[x][y] = -1                                  # :521-523
         if was_road and not is_road:
             self.num_roads -= 1
         elif not was_road and is_road:
@@ -238,6 +249,9 @@ class RefControl:
 
     def simTick(self):                                              # :148-152
         self.engine.controlSimTick()
+
+    def doBotTool(self, x, y, tool, static_build=False):            # :270-272 (PADDING = 0)
+        return self.map.addZoneBot(x, y, tool, static_build=static_build)
 
     def doSimTool(self, x, y, tool):                                # :296-301, 307-311
         return self.engine.toolDown(self.engineTools.index(tool), x + self.MAP_XS, y + self.MAP_YS)
@@ -291,6 +305,7 @@ class RefEnv:
         self.max_step = self.MAP_X * self.MAP_Y if max_step is None else max_step
         self.empty_start = empty_start
         self.micro = RefControl(engine, self.MAP_X, self.MAP_Y, power_puzzle, xs, ys, tilemap_cls)
+        self.micro.env = self                                       # TileMap reads micro.env.num_step for ages
         self.city_trgs = {'res_pop': 500, 'com_pop': 50, 'ind_pop': 50, 'traffic': 2000, 'num_plants': 14,
                           'mayor_rating': 100}
         self.weights = {'res_pop': 1, 'com_pop': 1, 'ind_pop': 1, 'traffic': 1, 'num_plants': 0,
@@ -367,3 +382,79 @@ class RefEnv:
         terminal = (funds < 0 or self.num_step >= self.max_step)
         self.num_step += 1
         return self.state, reward, terminal, {}
+
+
+class RefExtinguisher:
+    """gym_city/wrappers.py:10-141 Extinguisher around a RefEnv.  The reference draws from numpy's global
+    RNG (localWipe's centre, ranDemolish's np.random.choice); here the caller passes the draws
+    (`rnd`: n_dels + 2 non-negative ints per event) so that both sides of a parity test use the same
+    ones: ranDemolish takes aged cell number rnd[i] % count, localWipe the centre (rnd[0] % MAP_X,
+    rnd[1] % MAP_Y)."""
+    TYPES = ('age', 'spatial', 'random', 'Monster')
+
+    def __init__(self, env, extinction_type=None, extinction_prob=0.1, xt_dels=25):
+        self.env = env
+        self.set_extinction_type(extinction_type, extinction_prob, xt_dels)
+
+    def set_extinction_type(self, extinction_type, extinction_prob, extinction_dels):   # :24-33
+        self.extinction_type, self.extinction_prob, self.n_dels = extinction_type, extinction_prob, extinction_dels
+        self.extinction_interval = -1 if extinction_prob == 0 else 1 / extinction_prob
+        self.env.micro.map.init_age_array()
+
+    def step(self, a, rnd=None, static_build=False):                # :35-40
+        out = self.env.step(a, static_build)
+        dels = None
+        if self.env.num_step % self.extinction_interval == 0:
+            dels = self.extinguish(self.extinction_type, rnd)
+        return out, dels
+
+    def extinguish(self, extinction_type='age', rnd=None):          # :42-55
+        env, m = self.env, self.env.micro
+        if extinction_type == 'Monster':
+            m.engine.makeMonster()
+            return 0
+        ages = lambda: m.map.age_order
+        curr_dels = 0
+        if extinction_type == 'age':                                # elderCleanse :118-141
+            for i in range(self.n_dels):
+                a = ages().flatten()
+                youngest = np.max(a)
+                if len(np.where(a > -1)[0]) == 0:
+                    break
+                a = np.copy(a)
+                a += (a < 0) * 2 * youngest
+                x, y = np.unravel_index(np.argmin(a), ages().shape)
+                m.doBotTool(int(x), int(y), 'Clear', static_build=True)
+                curr_dels += 1
+            m.engine.setFunds(m.init_funds)
+        elif extinction_type == 'random':                           # ranDemolish :88-104
+            for i in range(self.n_dels):
+                a = ages().flatten()
+                age_is = np.where(a > -1)[0]
+                if len(age_is) == 0:
+                    break
+                age_i = age_is[int(rnd[i]) % len(age_is)]
+                x, y = np.unravel_index(age_i, ages().shape)
+                m.doBotTool(int(x), int(y), 'Clear', static_build=True)
+                curr_dels += 1
+        elif extinction_type == 'spatial':                          # localWipe :57-67, clear_border :69-86
+            x, y = int(rnd[0]) % env.MAP_X, int(rnd[1]) % env.MAP_Y
+            for r in range(0, max(x, abs(env.MAP_X - x), y, abs(env.MAP_Y - y))):
+                done = False
+                for x_i in range(x - r, x + r):
+                    if x_i < 0 or x_i >= env.MAP_X:
+                        continue
+                    for y_i in range(y - r, y + r):
+                        if y_i < 0 or y_i >= env.MAP_X or y_i >= env.MAP_Y:
+                            continue
+                        if ages()[x_i, y_i] > 0:
+                            m.doBotTool(x_i, y_i, 'Clear', static_build=True)
+                            curr_dels += 1
+                            if curr_dels == self.n_dels:
+                                done = True
+                                break
+                    if done:
+                        break
+                if curr_dels >= self.n_dels:
+                    break
+        return curr_dels

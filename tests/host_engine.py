@@ -85,6 +85,22 @@ class HostGym(HostEngine):
                                self.done.ctypes.data)
         return self.obs.copy(), float(self.rew[0]), bool(self.done[0])
 
+    def track_ages(self):
+        self._lib.mph_env_track_ages.argtypes = [C.c_void_p]
+        self._lib.mph_env_track_ages(self._h)
+
+    def extinguish(self, type_id, n_dels, rnd):
+        r = np.ascontiguousarray(rnd, np.int32)
+        assert r.size >= n_dels + 2
+        self._lib.mph_env_extinguish.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        return self._lib.mph_env_extinguish(self._h, int(type_id), int(n_dels), r.ctypes.data)
+
+    def ages(self):
+        out = np.zeros(self.W * self.H, np.int32)
+        self._lib.mph_env_get_ages.argtypes = [C.c_void_p, C.c_void_p]
+        self._lib.mph_env_get_ages(self._h, out.ctypes.data)
+        return out.reshape(self.W, self.H)
+
     def shadow(self):
         n = self.W * self.H
         z, s, c, k = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int16), np.zeros(15)

@@ -117,4 +117,17 @@ void mph_env_get_shadow(void *p, uint8_t *zone, uint8_t *stat, int16_t *center, 
     memcpy(counters, v, sizeof(v));
 }
 
+// Extinguisher wrapper (wrappers.py) on the harness
+void mph_env_track_ages(void *p) { HostEnv *h = (HostEnv *)p; gym_init_age_array(h->e, h->gy); }
+int mph_env_extinguish(void *p, int type, int n_dels, const int32_t *rnd)
+{
+    HostEnv *h = (HostEnv *)p;
+    return gym_extinguish(h->e, h->gy, type, n_dels, rnd);
+}
+void mph_env_get_ages(void *p, int32_t *out)
+{
+    HostEnv *h = (HostEnv *)p;
+    memcpy(out, h->gy.age, (size_t)h->cfg.W * h->cfg.H * 4);
+}
+
 } // extern "C"

@@ -50,12 +50,15 @@ def test_ref_tilemap_restatement_matches_reference_class(seed, size):
         sc.enableDisasters = 0          # floods make the reference class raise KeyError
         e.set_scalars(sc)
     for c in ctl:
+        c.env = types.SimpleNamespace(num_step=0)
         c.clearMap()
+        c.map.init_age_array()              # Extinguisher's age tracking (tilemap.py:201-206)
     rng = np.random.default_rng(seed)
     for t in range(400):
         a = [int(rng.integers(0, 20)), int(rng.integers(0, size)), int(rng.integers(0, size))]
         sb = bool(rng.random() < 0.25)
         for c in ctl:
+            c.env.num_step = t
             c.takeAction(a, sb)
             c.engine.setFunds(2000000)
             if t % 3 == 0:
@@ -63,6 +66,7 @@ def test_ref_tilemap_restatement_matches_reference_class(seed, size):
         a_, b_ = ctl[0].map, ctl[1].map
         assert np.array_equal(a_.zoneMap, b_.zoneMap), t
         assert np.array_equal(a_.static_builds, b_.static_builds), t
+        assert np.array_equal(a_.age_order, b_.age_order), t
         assert (a_.num_plants, a_.num_roads, a_.n_struct_tiles) == (b_.num_plants, b_.num_roads, b_.n_struct_tiles)
         ca = [[a_.centers[x][y] for y in range(size)] for x in range(size)]
         cb = [[b_.centers[x][y] for y in range(size)] for x in range(size)]
