@@ -13,6 +13,9 @@ def __getattr__(name):
     if name in ("MicropolisEnv", "MicropolisControl", "MicropolisVecEnv"):
         from . import micropolis_env
         return getattr(micropolis_env, name)
+    if name in ("make_vec_envs", "RolloutStorage", "BatchedVecEnv"):
+        from . import envs
+        return getattr(envs, name)
     if name == "Extinguisher":
         from . import wrappers
         return wrappers.Extinguisher

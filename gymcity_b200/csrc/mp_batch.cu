@@ -53,6 +53,7 @@ struct MpBatch {
     GymCfg cfg;
     uint8_t *shadow;          // [n_envs * shadow_stride]
     float *obs;               // [n_envs, 32, W, H]
+    float *obs_out;           // where the next observations go: `obs` or a caller's buffer (mpb_env_set_obs_buffer)
     float *reward;            // [n_envs]
     uint8_t *done;            // [n_envs]
     int64_t *act_dev;         // [n_envs]
@@ -924,6 +925,7 @@ int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools,
     CK(cudaMallocHost(&b->host_shadow, b->shadow_stride));
     CK(cudaMemset(b->shadow, 0, (size_t)b->n_envs * b->shadow_stride));
     CK(cudaMemset(b->obs, 0, (size_t)b->n_envs * on * 4));
+    b->obs_out = b->obs;
     CK(cudaMemset(b->reward, 0, (size_t)b->n_envs * 4));
     CK(cudaMemset(b->done, 0, b->n_envs));
     b->configured = 1;
@@ -985,7 +987,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     if (upload_mask(b, mask_host, st)) return -1;
     launch_control_sim_tick(b, st);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                    b->obs, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
+                                                    b->obs_out, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -1006,6 +1008,14 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
     CK(cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (ok_host) memcpy(ok_host, b->host_i32, (size_t)b->n_envs * 4);
+    return 0;
+}
+
+int mpb_env_set_obs_buffer(mpb_handle h, float *obs_dev)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    b->obs_out = obs_dev ? obs_dev : b->obs;
     return 0;
 }
 
@@ -1075,7 +1085,7 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
                                                  actions_dev, static_build, perm, q.stride, q.off, q.count);
         launch_control_sim_tick(b, gs, G, g);
         k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                  b->obs, b->reward, b->done, 0, NULL, perm, q.stride, q.off, q.count);
+                                                  b->obs_out, b->reward, b->done, 0, NULL, perm, q.stride, q.off, q.count);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);

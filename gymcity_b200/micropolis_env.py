@@ -133,7 +133,7 @@ class MicropolisControl:
             "mpb_env_step_host": (i32, [vp, vp, vp, vp, vp]), "mpb_env_ptr": (vp, [vp, i32]),
             "mpb_env_get_shadow": (i32, [vp, i32, vp, vp, vp, vp]),
             "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
-            "mpb_env_get_ages": (i32, [vp, i32, vp]),
+            "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -284,7 +284,11 @@ class MicropolisEnv:
         if self._single():
             return (m.obs[0].cpu().numpy().astype(np.float64), float(m.reward[0, 0].item()),
                     bool(m.done[0].item()), {})
-        return m.obs, m.reward, m.done.bool(), [{} for _ in range(self.num_envs)]
+        return self._cur_obs(), m.reward, m.done.bool(), [{} for _ in range(self.num_envs)]
+
+    def _cur_obs(self):
+        obs = getattr(self, "_obs_out", None)
+        return self.micro.obs if obs is None else obs
 
     def _episode_seeds(self, which):
         g = np.arange(self.num_envs) + self.env_offset
@@ -358,16 +362,32 @@ class MicropolisEnv:
             self.last_city_metrics = self.city_metrics
             self.state = m.obs[0].cpu().numpy().astype(np.float64)
             return self.state
-        return m.obs
+        return self._cur_obs()
 
     def _random_static_start(self):                         # env.py:228-241
         num_static = int(self.MAP_X * self.MAP_Y / 10)
         k = int(self.np_random.integers(0, num_static + 1)) if num_static > 0 else 0
         return [(self.np_random.integers(0, self.action_space.n, self.num_envs), True) for _ in range(k)]
 
-    def step(self, a, static_build=False):                  # env.py:448-540
+    def set_obs_buffer(self, out=None):
+        """Observations of the following steps / resets go to `out` (float32 CUDA tensor (N,32,W,H),
+        contiguous -- e.g. RolloutStorage.obs[step + 1]) instead of the env's own buffer; None restores it."""
+        m = self.micro
+        if out is None:
+            m._ck(m._L.mpb_env_set_obs_buffer(m._h, None))
+            self._obs_out = None
+            return
+        import torch
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+        assert tuple(out.shape) == (self.num_envs, 32, self.MAP_X, self.MAP_Y) and out.device.index == self.device
+        m._ck(m._L.mpb_env_set_obs_buffer(m._h, out.data_ptr()))
+        self._obs_out = out
+
+    def step(self, a, static_build=False, out=None):         # env.py:448-540
         import torch
         m = self.micro
+        if out is not None or getattr(self, "_obs_out", None) is not None:
+            self.set_obs_buffer(out)
         if torch.is_tensor(a):
             act = a.reshape(-1).to(device="cuda:%d" % self.device, dtype=torch.int64).contiguous()
         else:
@@ -421,8 +441,8 @@ class MicropolisVecEnv(MicropolisEnv):
         self.seed(seed)
         self.setMapSize(size, **kwargs)
 
-    def step(self, a, static_build=False):
-        obs, reward, done, infos = super().step(a, static_build)
+    def step(self, a, static_build=False, out=None):
+        obs, reward, done, infos = super().step(a, static_build, out=out)
         if self.num_envs == 1:
             if done:
                 obs = self.reset()
@@ -432,5 +452,5 @@ class MicropolisVecEnv(MicropolisEnv):
             done = done.clone()
             reward = reward.clone()
             self.reset(mask=mask)
-            obs = self.micro.obs
+            obs = self._cur_obs()
         return obs, reward, done, infos

@@ -174,6 +174,12 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
 int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
                    int32_t *ok_host, void *stream);
 
+/* Where mpb_env_step / mpb_env_step_host / mpb_env_reset_finish write the observations from now on:
+ * float32 [n_envs, 32, W, H] DEVICE memory of the caller -- e.g. RolloutStorage.obs[step + 1]
+ * (storage.py:84-94), which saves the learner's copy of the batch of observations -- or NULL for the
+ * library's own buffer (MPB_ENV_OBS).  The caller keeps the buffer alive until the step has finished. */
+int mpb_env_set_obs_buffer(mpb_handle h, float *obs_dev);
+
 /* Extinguisher wrapper (gym_city/wrappers.py:10-160).
  * mpb_env_track_ages: TileMap.init_age_array (tilemap.py:201-206) for every env: from now on the shadow
  *   map records the num_step of every build (age_order) and -1 for natural cells.

@@ -1,0 +1,96 @@
+"""Vec-env adapter + rollout storage (envs.py:270-444, storage.py:9-110 of the reference): storage
+arithmetic on the CPU; on the GPU the observation kernel writing straight into RolloutStorage.obs."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from gymcity_b200 import spaces
+from gymcity_b200.envs import RolloutStorage
+
+
+def test_rollout_storage_returns_and_bookkeeping():
+    T, N = 5, 3
+    rs = RolloutStorage(T, N, (2, 4, 4), spaces.Discrete(7), 8)
+    g = torch.Generator().manual_seed(0)
+    for t in range(T):
+        slot = rs.next_obs()
+        obs = torch.rand(N, 2, 4, 4, generator=g)
+        if t % 2:
+            slot.copy_(obs)                                   # "the env wrote it already"
+            obs = slot
+        rs.insert(obs, torch.zeros(N, 8), torch.randint(0, 7, (N, 1), generator=g), torch.rand(N, 1, generator=g),
+                  torch.rand(N, 1, generator=g), torch.rand(N, 1, generator=g),
+                  (torch.rand(N, 1, generator=g) > 0.3).float())
+        assert torch.equal(rs.obs[t + 1], obs)
+    assert rs.step == 0 and rs.actions.dtype == torch.long
+    nv, gamma, tau = torch.rand(N, 1, generator=g), 0.97, 0.9
+    rs.compute_returns(nv, False, gamma, tau)
+    ret = nv.clone()
+    for t in reversed(range(T)):
+        ret = ret * gamma * rs.masks[t + 1] + rs.rewards[t]
+        assert torch.allclose(rs.returns[t], ret)
+    rs.compute_returns(nv, True, gamma, tau)
+    gae, nxt = torch.zeros(N, 1), nv
+    for t in reversed(range(T)):
+        delta = rs.rewards[t] + gamma * nxt * rs.masks[t + 1] - rs.value_preds[t]
+        gae = delta + gamma * tau * rs.masks[t + 1] * gae
+        assert torch.allclose(rs.returns[t], gae + rs.value_preds[t])
+        nxt = rs.value_preds[t]
+    last = rs.obs[-1].clone()
+    rs.after_update()
+    assert torch.equal(rs.obs[0], last)
+
+
+@pytest.mark.gpu
+def test_make_vec_envs_writes_observations_into_rollout_storage():
+    from gymcity_b200.envs import make_vec_envs
+    N, T = 6, 4
+    args = types.SimpleNamespace(map_width=16, max_step=6, random_terrain=True, power_puzzle=False)
+    dev = torch.device("cuda", 0)
+    a = make_vec_envs('MicropolisEnv-v0', 3, N, 0.99, None, False, dev, True, args=args)
+    b = make_vec_envs('MicropolisEnv-v0', 3, N, 0.99, None, False, dev, True, args=args)
+    assert a.observation_space.shape == (32, 16, 16) and a.action_space.n == 20 * 256
+    rs = RolloutStorage(T, N, a.observation_space.shape, a.action_space, 1, device=dev)
+    o_a, o_b = a.reset(), b.reset()
+    assert torch.equal(o_a, o_b)
+    rs.obs[0].copy_(o_a)
+    rng = np.random.default_rng(0)
+    resets = 0
+    for it in range(3):
+        for t in range(T):
+            act = torch.from_numpy(rng.integers(0, 20 * 256, (N, 1))).to(dev)
+            obs, rew, done, infos = a.step(act, out=rs.next_obs())
+            obs_b, rew_b, done_b, _ = b.step(act)
+            assert obs.data_ptr() == rs.next_obs().data_ptr()            # written in place
+            assert torch.equal(obs, obs_b) and torch.equal(rew, rew_b) and np.array_equal(done, done_b)
+            assert rew.shape == (N, 1) and done.shape == (N,) and len(infos) == N
+            resets += int(done.any())
+            masks = torch.from_numpy(1.0 - done.astype(np.float32)).reshape(N, 1).to(dev)
+            rs.insert(obs, torch.zeros(N, 1, device=dev), act, torch.zeros(N, 1, device=dev), torch.zeros(N, 1, device=dev),
+                      rew, masks)
+            assert torch.equal(rs.obs[t + 1], obs_b)
+        rs.after_update()
+    assert resets >= 1                                                   # max_step = 6: the auto-reset path ran
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_make_vec_envs_extinction_and_gol():
+    from gymcity_b200.envs import make_vec_envs
+    dev = torch.device("cuda", 0)
+    args = types.SimpleNamespace(map_width=16, max_step=100, random_terrain=True, extinction_type='age',
+                                 extinction_prob=0.5)
+    v = make_vec_envs('MicropolisEnv-v0', 1, 4, 0.99, None, False, dev, True, args=args)
+    v.reset()
+    rng = np.random.default_rng(1)
+    for t in range(4):
+        v.step(torch.from_numpy(rng.integers(0, 20 * 256, (4, 1))).to(dev))
+    assert int((v.env.ages(0) > -1).sum()) == 0                          # an event fired on the last step
+    v.close()
+    gargs = types.SimpleNamespace(map_width=16, max_step=20, num_proc=64, prob_life=20)
+    gol = make_vec_envs('GoLMultiEnv-v0', 0, 1, 0.99, None, False, dev, True, args=gargs)
+    obs = gol.reset()
+    assert tuple(obs.shape) == (64, 2, 16, 16)
+    gol.close()
