@@ -37,6 +37,7 @@ struct MpBatch {
     char err[256];
     int passes;               // host copy of simPasses (corecontrol.py:129 sets 100)
     int frames_per_launch;    // simFrames per k_mp_frames launch (phase lockstep across the batch)
+    int heavy_div;            // the n_envs / heavy_div most expensive envs form the heavy group (0: none)
     int fepc, heavy_fepc;     // envs per CTA of k_mp_frames (frame lockstep inside the CTA), for the heavy group
     unsigned long long *cycles;   // [n_envs] SM cycles each env spent in k_mp_frames since the last read (profiling)
     unsigned int *cost;       // [n_envs] cycles of the current step (schedule key for the next one)
@@ -139,7 +140,7 @@ template <int MP_FEPC>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int skew, unsigned int *prof, int prof_off)
+            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_FEPC];
@@ -168,42 +169,22 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         __syncwarp();
         if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     }
-    // Frame lockstep with bounded skew: a warp may start frame i once every warp of the CTA has
-    // finished frame i - skew - 1 (skew = 0 is a barrier per frame).  One mbarrier per frame in a ring
-    // of 8: lane 0 of every warp arrives after its frame, everybody polls the parity of the frame it
-    // depends on.  A slot is reused for frame g + 8 only by warps that have passed the wait for frame
-    // g + 8 - skew - 1 >= g, so the phase being waited for cannot be overtaken (skew <= 7).
-    __shared__ __align__(8) unsigned long long s_bar[8];
+    // Frame lockstep: a CTA barrier after every frame keeps the warps of the CTA in the same simulation
+    // phase, i.e. in the same code.  The eight map-scan phases (1..8) run the same code, so they need no
+    // lockstep among themselves: with scan_block the barrier is skipped after phases 1..7.  The decision
+    // uses the CTA's nominal phase (warp 0's env at the start of the launch), so every warp -- also one
+    // whose env was reset to another phase -- executes the same barriers.  (A bounded-skew variant over an
+    // mbarrier ring, warps running up to 7 frames ahead, was 3-17 % slower and its polling loop was 59 %
+    // of the issued instructions: profiles/r01_notes.md.)
     __shared__ int s_ph0;
     if (MP_FEPC > 1) {
-        if (threadIdx.x == 0) {
-            for (int k = 0; k < 8; k++)
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar[k])), "r"(MP_FEPC));
-        }
         if (threadIdx.x == 0) s_ph0 = live ? (e.s->initSimLoad ? 0 : (e.s->phaseCycle & 15)) : 0;
         __syncthreads();
     }
-    const int scan_block = skew >> 8;
-    skew &= 255;
+    const int ph0 = MP_FEPC > 1 ? s_ph0 : 0;
     const long long t_loop = clock64();
     unsigned int busy = 0;
     MP_NOUNROLL for (int i = 0; i < count; i++) {
-        // The eight map-scan phases (1..8) run the same code, so they need no lockstep among themselves:
-        // a frame in that block waits only for the frame that ended phase 0.  The block decision uses the
-        // CTA's nominal phase (warp 0's env) so that every warp waits on the same frames.
-        int dep = i - skew - 1;
-        if (scan_block) {
-            const int ph = (s_ph0 + i) & 15;
-            if (ph >= 1 && ph <= 8 && i - ph < dep) dep = i - ph;
-        }
-        if (MP_FEPC > 1 && dep >= 0) {
-            const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[dep & 7]), parity = (dep >> 3) & 1;
-            unsigned done;
-            do {
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            } while (!done);
-        }
         const bool go = live && (!respect_passes || (e.s->simSpeed && first + i < e.s->simPasses));
         int ran = 0;
         const unsigned int t0 = (unsigned int)clock64();
@@ -213,12 +194,8 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         busy += dt;
         if (prof && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
         if (MP_FEPC > 1) {
-            __syncwarp();
-            if (lane == 0) {
-                unsigned long long st;
-                asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"((unsigned)__cvta_generic_to_shared(&s_bar[i & 7])) : "memory");
-                (void)st;
-            }
+            const int ph = (ph0 + i) & 15;
+            if (!(scan_block && ph >= 1 && ph <= 7)) __syncthreads();
         }
     }
     if (!live) return;
@@ -428,7 +405,6 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 
 int g_scan_block = 1;             // map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
 int g_pad_smem = 0;               // experiment: dynamic shared memory per CTA (limits CTAs per SM)
-int g_skew = 0;                   // frames a warp may run ahead of the slowest warp of its CTA (0..7)
 unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
 // k_mp_frames with `epc` envs per CTA (1, 8 or 16); prof_off = frame offset of this simTick in the
 // per-frame profile rows (0 for the first simTick of an env-step, 100 for the second)
@@ -438,7 +414,7 @@ void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, co
 {
     if (count_envs <= 0) return;
 #define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
-                       gcount, g_skew | (g_scan_block << 8), g_prof, prof_off
+                       gcount, g_scan_block, g_prof, prof_off
     if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 0, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
@@ -457,7 +433,7 @@ GroupGeom group_geom(const MpBatch *b, int G, int g)
 {
     GroupGeom q;
     if (G <= 1) { q.off = 0; q.stride = 1; q.count = b->n_envs; return q; }
-    int heavy = b->use_sched ? b->n_envs / 64 : 0;                 // ~1.5 % of the batch
+    int heavy = b->use_sched && b->heavy_div > 0 ? b->n_envs / b->heavy_div : 0;   // ~1.5 % of the batch
     if (heavy < 1 || G < 3) heavy = 0;
     if (heavy == 0) { q.off = g; q.stride = G; q.count = (b->n_envs - g + G - 1) / G; return q; }
     if (g == 0) { q.off = 0; q.stride = 1; q.count = heavy; return q; }
@@ -535,6 +511,8 @@ mpb_handle mpb_create(int n_envs, int device)
     b->passes = 100;
     b->frames_per_launch = 50;
     if (const char *fp = getenv("MPB_FRAMES_PER_LAUNCH")) { int v = atoi(fp); if (v > 0) b->frames_per_launch = v; }
+    b->heavy_div = 64;
+    if (const char *fp = getenv("MPB_HEAVY_DIV")) b->heavy_div = atoi(fp);
     b->fepc = 32;
     b->heavy_fepc = 32;
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
@@ -548,7 +526,6 @@ mpb_handle mpb_create(int n_envs, int device)
         g_pad_smem = atoi(fp);
         cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_pad_smem);
     }
-    if (const char *fp = getenv("MPB_SKEW")) { int v = atoi(fp); g_skew = v < 0 ? 0 : (v > 7 ? 7 : v); }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];

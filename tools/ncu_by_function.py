@@ -1,18 +1,19 @@
 """Attribute an ncu source-page CSV (SASS view) of one kernel to the device functions inside it,
-using nvdisasm's labels of the same cubin.  usage: ncu_by_function.py src.csv dis.txt kernel_substr"""
+using nvdisasm's labels of the same cubin.  usage: ncu_by_function.py src.csv dis.txt kernel_substr [section_substr]"""
 import csv
 import re
 import sys
 
 
-def main(src_csv, dis_txt, kern):
+def main(src_csv, dis_txt, kern, sect=None):
+    sect = sect or kern          # mangled-name substring of the cubin section (template instantiations)
     labels, sec, off = [], None, 0
     for l in open(dis_txt):
         m = re.match(r'\s*\.section\s+\.text\.(\S+?),', l)
         if m:
             sec = m.group(1)
             continue
-        if not sec or kern not in sec:
+        if not sec or sect not in sec:
             continue
         m = re.match(r'^(\$?[_a-zA-Z][\w\$]*):\s*$', l)
         if m and not m.group(1).startswith('.L'):
@@ -69,4 +70,4 @@ def main(src_csv, dis_txt, kern):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
