@@ -141,6 +141,12 @@ class EngineBase:
     def generate(self, s): self._f("generate")(self._h, int(s))
     def toolDown(self, tool, x, y): return self._f("tool")(self._h, int(tool), int(x), int(y))
     def setFunds(self, v): self._f("set_funds")(self._h, int(v))
+
+    def loadFileDir(self, path):
+        fn = self._f("load_file_dir")
+        fn.argtypes = [C.c_void_p, C.c_char_p]
+        fn.restype = C.c_int
+        return bool(fn(self._h, str(path).encode()))
     def setPasses(self, v): self._f("set_passes")(self._h, int(v))
     def simTick(self): self._f("sim_tick")(self._h)
     def tickEngine(self): self._f("tick_engine")(self._h)

@@ -69,6 +69,10 @@ int mpref_tool(void *h, int tool, int x, int y)
 
 void mpref_set_funds(void *h, int funds) { ((Micropolis *)h)->setFunds(funds); }
 
+// fileio.cpp:203-247 loadFileDir: the seven history arrays and the map of a .cty file, nothing else
+// (loadFile's scalar decoding reads 8-byte longs from 4-byte fields on LP64 and is not used).
+int mpref_load_file_dir(void *h, const char *path) { return ((Micropolis *)h)->loadFileDir(path, NULL) ? 1 : 0; }
+
 void mpref_set_passes(void *h, int passes) { ((Micropolis *)h)->setPasses(passes); }
 
 void mpref_sim_tick(void *h) { ((Micropolis *)h)->simTick(); }
