@@ -10,7 +10,7 @@ def __getattr__(name):
     if name in ("GoLMultiEnv", "GameOfLifeEnv"):
         from . import gol_env
         return getattr(gol_env, name)
-    if name in ("MicropolisEnv", "MicropolisControl", "MicropolisVecEnv"):
+    if name in ("MicropolisEnv", "MicropolisControl", "MicropolisVecEnv", "MicropolisPaintEnv"):
         from . import micropolis_env
         return getattr(micropolis_env, name)
     if name in ("make_vec_envs", "RolloutStorage", "BatchedVecEnv"):

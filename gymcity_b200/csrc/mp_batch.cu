@@ -305,6 +305,27 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
     }
 }
 
+// MicropolisPaintEnv.step, part 1 (paintenv.py:43-52): one tool per window cell, then setFunds
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_pre_paint(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
+                   const uint8_t *actions, const int *perm, int gstride, int goff, int gcount)
+{
+    __shared__ int red[8 * MP_EPC];
+    if (device_env_index() >= gcount) return;
+    const int slot = device_env_index() * gstride + goff;
+    if (slot >= n_envs) return;
+    const int env = perm ? perm[slot] : slot;
+    const int lane = threadIdx.x & 31;
+    MP_SHARED_ENV();
+    bind_env_of(e, blocks, env, anim, red);
+    Gym gy;
+    bind_gym(gy, shadow + (size_t)env * stride, &cfg);
+    if (lane == 0) {
+        gym_paint_action(e, gy, actions + (size_t)env * cfg.W * cfg.H);
+        e.s->totalFunds = cfg.init_funds;
+    }
+}
+
 // Extinguisher wrapper (wrappers.py:10-160): init_age_array / one extinction event per env
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_track_ages(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg)
@@ -1043,12 +1064,26 @@ int mpb_env_get_ages(mpb_handle h, int env, int32_t *age_out)
     return 0;
 }
 
+static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build, cudaStream_t st);
+
 int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, void *stream)
 {
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!actions_dev) return -1;
-    cudaStream_t st = (cudaStream_t)stream;
+    return env_step_impl(b, actions_dev, NULL, static_build, (cudaStream_t)stream);
+}
+
+int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!tools_dev) return -1;
+    return env_step_impl(b, NULL, tools_dev, 0, (cudaStream_t)stream);
+}
+
+static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build, cudaStream_t st)
+{
     const int G = b->groups;
     const int *perm = b->use_sched ? b->perm : NULL;
     if (G > 1) cudaEventRecord(b->ev_start, st);
@@ -1058,8 +1093,12 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
         const int grid = MP_GRID_N(q.count);
         if (grid <= 0) continue;
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
-        k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                 actions_dev, static_build, perm, q.stride, q.off, q.count);
+        if (paint_dev)
+            k_mp_env_pre_paint<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
+                                                           b->cfg, paint_dev, perm, q.stride, q.off, q.count);
+        else
+            k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                     actions_dev, static_build, perm, q.stride, q.off, q.count);
         launch_control_sim_tick(b, gs, G, g);
         k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                   b->obs_out, b->reward, b->done, 0, NULL, perm, q.stride, q.off, q.count);

@@ -34,20 +34,22 @@ struct GymScalars {
     double metrics[GYM_NUM_METRICS], last_metrics[GYM_NUM_METRICS];
     double reward;
     int32_t done, curr_funds;
-    int32_t track_ages, pad_;   // TileMap.track_ages (tilemap.py:201-206), set by the Extinguisher wrapper
+    int32_t track_ages;         // TileMap.track_ages (tilemap.py:201-206), set by the Extinguisher wrapper
+    int32_t paint;              // TileMap.paint (tilemap.py:74-81): MicropolisPaintEnv's one-build-per-tile-per-step rule
 };
 
 struct Gym {
     uint8_t *zone, *stat;       // [W*H] index x*H + y
     int16_t *center;            // [W*H] cx*128 + cy, -1 = None
     int32_t *age;               // [W*H] TileMap.age_order: num_step of the build, -1 = nothing built
+    uint8_t *acted;             // [W*H] TileMap.acted: built on during this paint step
     GymScalars *g;
     const GymCfg *cfg;
 };
 
 MPH int gym_shadow_bytes(int W, int H)
 {
-    return a16(W * H) * 2 + a16(W * H * 2) + a16((int)sizeof(GymScalars)) + a16(W * H * 4);
+    return a16(W * H) * 3 + a16(W * H * 2) + a16((int)sizeof(GymScalars)) + a16(W * H * 4);
 }
 MPH void bind_gym(Gym &gy, uint8_t *blk, const GymCfg *cfg)
 {
@@ -57,6 +59,7 @@ MPH void bind_gym(Gym &gy, uint8_t *blk, const GymCfg *cfg)
     gy.center = (int16_t *)(blk + 2 * a16(n));
     gy.g = (GymScalars *)(blk + 2 * a16(n) + a16(n * 2));
     gy.age = (int32_t *)(blk + 2 * a16(n) + a16(n * 2) + a16((int)sizeof(GymScalars)));
+    gy.acted = blk + 2 * a16(n) + a16(n * 2) + a16((int)sizeof(GymScalars)) + a16(n * 4);
     gy.cfg = cfg;
 }
 
@@ -167,6 +170,7 @@ MPD int gym_clear_patch(Env &e, Gym &gy, int x, int y, int size, bool static_bui
     MP_NOUNROLL for (int i = x0; i < x1; i++)
         MP_NOUNROLL for (int j = y0; j < y1; j++) {
             if (gy.stat[gym_cell(gy, i, j)] == 1) return 0;
+            if (G.paint && gy.acted[gym_cell(gy, i, j)] == 1) return 0;     // built this turn: not overwritten (:402-404)
             gym_clear_tile(e, gy, i, j, static_build);
         }
     return 1;
@@ -180,6 +184,7 @@ MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
     int center = (size == 6) ? (x + 1) * 128 + (y + 1) : x * 128 + y;
     if (size == 1) {
         gym_update_tile(e, gy, x, y, zone, center, static_build ? 1 : 0);
+        if (G.paint) gy.acted[gym_cell(gy, x, y)] = 1;                   // :465-466
         if (G.track_ages) gy.age[gym_cell(gy, x, y)] = G.num_step;      // :467-468 (also after a 'Land' build)
         return;
     }
@@ -188,6 +193,7 @@ MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
     MP_NOUNROLL for (int i = x0; i < x1; i++)
         MP_NOUNROLL for (int j = y0; j < y1; j++) {
             gym_update_tile(e, gy, i, j, zone, center, static_build ? 1 : 0);
+            if (G.paint) gy.acted[gym_cell(gy, i, j)] = 1;               // :476-477
             if (G.track_ages) gy.age[gym_cell(gy, i, j)] = G.num_step;  // :478-479
         }
 }
@@ -238,6 +244,24 @@ MPD int gym_apply_action(Env &e, Gym &gy, long long a, bool static_build, bool f
     }
     if (z >= CFG.num_tools) return 0;
     return gym_add_zone_bot(e, gy, x, y, CFG.tool_zone[z], CFG.tool_engine[z], static_build);
+}
+
+// ---- MicropolisPaintEnv (gym_city/envs/paintenv.py, paintcontrol.py) --------------------------
+// [LEAD] MicropolisPaintControl.takeAction (paintcontrol.py:45-70): one tool per window cell, row by
+// row, a cell is skipped if an earlier build of this step already covers it; the last column is never
+// reached (the loop breaks at j >= MAP_Y - 1), as in the reference.  a: tool index per cell [W*H].
+MPN void gym_paint_action(Env &e, Gym &gy, const uint8_t *a)
+{
+    const int W = CFG.W, H = CFG.H;
+    G.paint = 1;                    // the acted rule applies to the builds of this action only
+    MP_NOUNROLL for (int i = 0; i < W; i++)
+        MP_NOUNROLL for (int j = 0; j < H - 1; j++) {
+            const int c = gym_cell(gy, i, j), t = a[c];
+            if (t >= CFG.num_tools || gy.acted[c]) continue;
+            gym_add_zone_bot(e, gy, i, j, CFG.tool_zone[t], CFG.tool_engine[t], false);
+        }
+    MP_NOUNROLL for (int c = 0; c < W * H; c++) gy.acted[c] = 0;
+    G.paint = 0;
 }
 
 // ---- Extinguisher wrapper (gym_city/wrappers.py:10-160) -----------------------------------------

@@ -134,6 +134,7 @@ class MicropolisControl:
             "mpb_env_get_shadow": (i32, [vp, i32, vp, vp, vp, vp]),
             "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
             "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
+            "mpb_env_step_paint": (i32, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -451,6 +452,36 @@ class MicropolisVecEnv(MicropolisEnv):
             mask = done.cpu().numpy()
             done = done.clone()
             reward = reward.clone()
+            self.reset(mask=mask)
+            obs = self._cur_obs()
+        return obs, reward, done, infos
+
+
+class MicropolisPaintEnv(MicropolisVecEnv):
+    """gym_city/envs/paintenv.py: the agent names a tool for EVERY window cell each step.  Batched:
+    step(a) takes (N, W, H) tool indices (uint8 / integer tensor or array); the action space is the
+    reference's Box(0, num_tools - 1, (W, H))."""
+
+    def setMapSize(self, size, **kwargs):
+        super().setMapSize(size, **kwargs)
+        hi = np.full((self.MAP_X, self.MAP_Y), self.num_tools - 1)
+        self.action_space = spaces.Box(np.zeros_like(hi), hi, dtype=np.int64)     # paintenv.py:36-39
+
+    def step(self, a, static_build=False, out=None):
+        import torch
+        m = self.micro
+        dev = "cuda:%d" % self.device
+        if not torch.is_tensor(a):
+            a = torch.as_tensor(np.asarray(a))
+        t = a.to(device=dev).reshape(self.num_envs, self.MAP_X * self.MAP_Y).to(torch.uint8).contiguous()
+        if out is not None or getattr(self, "_obs_out", None) is not None:
+            self.set_obs_buffer(out)
+        m._ck(m._L.mpb_env_step_paint(m._h, t.data_ptr(), m.engine._stream()))
+        self.num_step += 1
+        obs, reward, done, infos = self._out()
+        if self.num_envs > 1 and self.auto_reset and bool(done.any().item()):
+            mask = done.cpu().numpy()
+            done, reward = done.clone(), reward.clone()
             self.reset(mask=mask)
             obs = self._cur_obs()
         return obs, reward, done, infos

@@ -174,6 +174,13 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
 int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
                    int32_t *ok_host, void *stream);
 
+/* MicropolisPaintEnv.step (gym_city/envs/paintenv.py:43-52, paintcontrol.py:45-70): one tool per window
+ * cell.  tools_dev: uint8 [n_envs][W*H] DEVICE, index into the env's tool list at cell x*H + y.  Cells are
+ * visited row by row (the last column is never reached, as in the reference); a cell an earlier build of
+ * the same step covers is skipped and is not cleared by later builds (TileMap.acted, tilemap.py:402-404).
+ * Then setFunds, MicropolisControl.simTick, observation / reward / done exactly as mpb_env_step. */
+int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream);
+
 /* Where mpb_env_step / mpb_env_step_host / mpb_env_reset_finish write the observations from now on:
  * float32 [n_envs, 32, W, H] DEVICE memory of the caller -- e.g. RolloutStorage.obs[step + 1]
  * (storage.py:84-94), which saves the learner's copy of the batch of observations -- or NULL for the

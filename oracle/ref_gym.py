@@ -89,6 +89,8 @@ class RefTileMap:
         self.centers = np.full((MAP_X, MAP_Y), None)
         self.n_struct_tiles = 0
         self.track_ages = False
+        self.paint = False                 # tilemap.py:74-81 (MicropolisPaintControl passes paint=True)
+        self.acted = np.zeros((MAP_X, MAP_Y))
         self.setEmpty()
 
     def init_age_array(self):                                       # tilemap.py:201-206
@@ -140,6 +142,8 @@ class RefTileMap:
             for j in range(y0, y1):
                 if self.static_builds[0][i][j] == 1:
                     return 0
+                if self.paint and self.acted[i][j] == 1:           # :402-404
+                    return 0
                 self.clearTile(i, j, static_build=static_build)
         return 1
 
@@ -180,6 +184,8 @@ class RefTileMap:
         center = (x + 1, y + 1) if zone_size == 6 else (x, y)
         if zone_size == 1:
             self.updateTile(x, y, zone, center, static_build)
+            if self.paint:
+                self.acted[x, y] = 1                                   # :465-466
             if self.track_ages:
                 self.age_order[x][y] = self.micro.env.num_step         # :467-468
             return
@@ -188,6 +194,8 @@ class RefTileMap:
         for i in range(x0, x1):
             for j in range(y0, y1):
                 self.updateTile(i, j, zone, center, static_build)
+                if self.paint:
+                    self.acted[i, j] = 1                               # :476-477
                 if self.track_ages:
                     self.age_order[i][j] = self.micro.env.num_step     # :478-479
 
@@ -458,3 +466,30 @@ class RefExtinguisher:
                 if curr_dels >= self.n_dels:
                     break
         return curr_dels
+
+
+class RefPaintEnv(RefEnv):
+    """gym_city/envs/paintenv.py:20-53 + paintcontrol.py:36-70 around the oracle control: step(a) with a (W, H)
+    array of tool indices, one doBotTool per cell (the last column is never reached), cells an earlier build
+    of the same step covers are skipped.  The TileMap's paint rule is switched on for the action only (setup
+    builds of the reference happen with it on, which differs for static cells only, and those refuse
+    non-static builds anyway)."""
+
+    def step(self, a, static_build=False):
+        m = self.micro
+        a = np.asarray(a)
+        m.map.paint = True
+        i = 0
+        while i in range(self.MAP_X):
+            j = 0
+            while j in range(self.MAP_Y):
+                if j >= self.MAP_Y - 1 or i >= self.MAP_X:
+                    break
+                tool = m.tools[int(a[i][j])]
+                if m.map.acted[i, j] == 0:
+                    m.doBotTool(i, j, tool, static_build=False)
+                j += 1
+            i += 1
+        m.map.acted.fill(0)
+        m.map.paint = False
+        return RefEnv.step(self, -1, static_build)          # postact (env.py:468-540); the reward is recomputed there

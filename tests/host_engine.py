@@ -85,6 +85,14 @@ class HostGym(HostEngine):
                                self.done.ctypes.data)
         return self.obs.copy(), float(self.rew[0]), bool(self.done[0])
 
+    def step_paint(self, tools):
+        t = np.ascontiguousarray(tools, np.uint8).reshape(-1)
+        assert t.size == self.W * self.H
+        self._lib.mph_env_step_paint.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        self._lib.mph_env_step_paint(self._h, t.ctypes.data, self.obs.ctypes.data, self.rew.ctypes.data,
+                                     self.done.ctypes.data)
+        return self.obs.copy(), float(self.rew[0]), bool(self.done[0])
+
     def track_ages(self):
         self._lib.mph_env_track_ages.argtypes = [C.c_void_p]
         self._lib.mph_env_track_ages(self._h)

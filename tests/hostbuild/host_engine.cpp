@@ -117,6 +117,16 @@ void mph_env_get_shadow(void *p, uint8_t *zone, uint8_t *stat, int16_t *center, 
     memcpy(counters, v, sizeof(v));
 }
 
+// MicropolisPaintEnv.step on the harness
+void mph_env_step_paint(void *p, const uint8_t *tools, float *obs, float *reward, uint8_t *done)
+{
+    HostEnv *h = (HostEnv *)p;
+    gym_paint_action(h->e, h->gy, tools);
+    h->e.s->totalFunds = h->cfg.init_funds;
+    control_sim_tick(h->e);
+    gym_step_post(h->e, h->gy, obs, reward, done);
+}
+
 // Extinguisher wrapper (wrappers.py) on the harness
 void mph_env_track_ages(void *p) { HostEnv *h = (HostEnv *)p; gym_init_age_array(h->e, h->gy); }
 int mph_env_extinguish(void *p, int type, int n_dels, const int32_t *rnd)
