@@ -391,7 +391,7 @@ k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     bind_env_of(e, blocks, env, anim, red);
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
-    const size_t on = (size_t)GYM_OBS_CHANNELS * cfg.W * cfg.H;
+    const size_t on = (size_t)gym_obs_channels(cfg) * cfg.W * cfg.H;
     if (is_reset) gym_reset_post(e, gy, obs + env * on, reward + env, done + env);
     else gym_step_post(e, gy, obs + env * on, reward + env, done + env);
 }
@@ -1007,6 +1007,23 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
     CK(cudaStreamSynchronize(st));
     if (ok_host) memcpy(ok_host, b->host_i32, (size_t)b->n_envs * 4);
     return 0;
+}
+
+int mpb_env_set_poet(mpb_handle h, int enable, const double *param_ranges)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (enable && !param_ranges) return -1;
+    b->cfg.poet = enable ? 1 : 0;
+    for (int i = 0; i < GYM_NUM_METRICS; i++) b->cfg.param_range[i] = enable ? param_ranges[i] : 0.0;
+    const size_t on = (size_t)gym_obs_channels(b->cfg) * b->cfg.W * b->cfg.H;
+    CK(cudaDeviceSynchronize());
+    cudaFree(b->obs);
+    b->obs = NULL;
+    CK(cudaMalloc(&b->obs, (size_t)b->n_envs * on * 4));
+    CK(cudaMemset(b->obs, 0, (size_t)b->n_envs * on * 4));
+    b->obs_out = b->obs;
+    return gym_obs_channels(b->cfg);
 }
 
 int mpb_env_set_obs_buffer(mpb_handle h, float *obs_dev)

@@ -27,7 +27,12 @@ struct GymCfg {
     int8_t tool_engine[GYM_MAX_TOOLS];   // agent tool -> engine EditingTool
     double trg[GYM_NUM_METRICS], weight[GYM_NUM_METRICS];
     int32_t init_funds;
+    // MicropolisEnv(poet=True) (env.py:301-313): populations divided by their parameter ranges and six more
+    // scalar planes, the targets divided by theirs: 38 observation planes instead of 32
+    int32_t poet;
+    double param_range[GYM_NUM_METRICS];
 };
+MPH int gym_obs_channels(const GymCfg &c) { return c.poet ? GYM_OBS_CHANNELS + GYM_NUM_METRICS : GYM_OBS_CHANNELS; }
 
 struct GymScalars {
     int32_t num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error;
@@ -391,11 +396,18 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
     if (e.c.lead()) e.c.red[3] = 0;
     e.c.sync();
     const Scalars &s = *e.s;
-    float sc[6];
+    float sc[6 + GYM_NUM_METRICS];
     sc[0] = (float)s.resPop; sc[1] = (float)s.comPop; sc[2] = (float)s.indPop;
     sc[3] = (float)s.resValve / (float)RES_VALVE_RANGE;        // utilities.cpp:416-424 getDemands
     sc[4] = (float)s.comValve / (float)COM_VALVE_RANGE;
     sc[5] = (float)s.indValve / (float)IND_VALVE_RANGE;
+    const int nsc = CFG.poet ? 6 + GYM_NUM_METRICS : 6;
+    if (CFG.poet) {                                            // env.py:306-312 (Python floats: double division)
+        sc[0] = (float)((double)s.resPop / CFG.param_range[0]);
+        sc[1] = (float)((double)s.comPop / CFG.param_range[1]);
+        sc[2] = (float)((double)s.indPop / CFG.param_range[2]);
+        MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) sc[6 + k] = (float)(CFG.trg[k] / CFG.param_range[k]);
+    }
     int tsum = 0;
     // one window cell per lane and iteration: every plane's store is coalesced across the lanes, and
     // the per-cell inputs (zone id, power bit, the two half-resolution densities) are read once
@@ -419,9 +431,8 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
         }
         o[23 * n] = vp;
         o[24 * n] = vt;
-#pragma unroll
-        for (int k = 0; k < 6; k++) o[(25 + k) * n] = sc[k];
-        o[31 * n] = (float)gy.stat[cell];
+        MP_NOUNROLL for (int k = 0; k < nsc; k++) o[(25 + k) * n] = sc[k];
+        o[(25 + nsc) * n] = (float)gy.stat[cell];
     }
     coop_add(e, 3, tsum);
     e.c.sync();

@@ -20,7 +20,7 @@ class BatchedVecEnv:
         self.venv = self.env = env
         self.device = device
         self.num_envs = env.num_envs
-        self.observation_space = spaces.Box(0, 1, (32, env.MAP_X, env.MAP_Y), dtype=np.float32)
+        self.observation_space = spaces.Box(-1, 1, (env.micro.obs_channels, env.MAP_X, env.MAP_Y), dtype=np.float32)
         self.action_space = env.action_space
         self._pending = None
 
@@ -76,6 +76,7 @@ def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, add_timestep, d
     env = MicropolisVecEnv(num_processes, g('map_width', 20), device=dev_index, seed=seed,
                            max_step=g('max_step', None), empty_start=not g('random_terrain', True),
                            power_puzzle=bool(g('power_puzzle', False)), random_builds=bool(g('random_builds', False)),
+                           poet=bool(g('poet', False)),
                            env_offset=g('env_offset', 0))
     if g('extinction_type') is not None:                    # envs.py:255-257
         from .wrappers import Extinguisher

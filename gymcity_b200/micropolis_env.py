@@ -119,9 +119,17 @@ class MicropolisControl:
         n, W, H = self.num_envs, self.MAP_X, self.MAP_Y
         P = lambda w: self._L.mpb_env_ptr(self._h, w)
         dev = self.engine.device
+        self.obs_channels = 32
         self.obs = device_tensor(P(MPB_ENV_OBS), "float32", (n, 32, W, H), dev)
         self.reward = device_tensor(P(MPB_ENV_REWARD), "float32", (n, 1), dev)
         self.done = device_tensor(P(MPB_ENV_DONE), "uint8", (n,), dev)
+
+    def set_poet(self, param_ranges):
+        """env.py:301-313 poet observation: 38 planes (pops / ranges, targets / ranges); rebinds self.obs."""
+        r = np.ascontiguousarray(param_ranges, np.float64)
+        self.obs_channels = self._ck(self._L.mpb_env_set_poet(self._h, 1, r.ctypes.data))
+        self.obs = device_tensor(self._L.mpb_env_ptr(self._h, MPB_ENV_OBS), "float32",
+                                 (self.num_envs, self.obs_channels, self.MAP_X, self.MAP_Y), self.engine.device)
 
     def _bind(self):
         L, vp, i32 = self._L, C.c_void_p, C.c_int
@@ -134,7 +142,7 @@ class MicropolisControl:
             "mpb_env_get_shadow": (i32, [vp, i32, vp, vp, vp, vp]),
             "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
             "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
-            "mpb_env_step_paint": (i32, [vp, vp, vp]),
+            "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -243,8 +251,6 @@ class MicropolisEnv:
         """env.py:100-139 (setMapSize / pre_gui / post_gui) with the same keyword arguments."""
         if record:
             raise NotImplementedError
-        if poet:
-            raise NotImplementedError("poet target planes (env.py:307-313) are not on this path yet")
         if num_envs is not None:
             self.num_envs = int(num_envs)
         if device is not None:
@@ -267,6 +273,9 @@ class MicropolisEnv:
         self.initFunds = self.micro.init_funds
         self.num_tools, self.num_zones = self.micro.num_tools, self.micro.num_zones
         self.num_obs_channels = NUM_FEATURES + 6 + 3 + 1
+        if poet:                                               # env.py:157-158, 305-312
+            self.micro.set_poet(self.param_ranges)
+            self.num_obs_channels += len(self.city_trgs)
         self.action_space = spaces.Discrete(self.num_tools * self.MAP_X * self.MAP_Y)
         self.observation_space = spaces.Box(-1, 1, (self.num_obs_channels, self.MAP_X, self.MAP_Y), dtype=float)
         self.intsToActions = _IntsToActions(self.num_tools, self.MAP_X, self.MAP_Y)
@@ -380,7 +389,8 @@ class MicropolisEnv:
             return
         import torch
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
-        assert tuple(out.shape) == (self.num_envs, 32, self.MAP_X, self.MAP_Y) and out.device.index == self.device
+        assert tuple(out.shape) == (self.num_envs, self.micro.obs_channels, self.MAP_X, self.MAP_Y)
+        assert out.device.index == self.device
         m._ck(m._L.mpb_env_set_obs_buffer(m._h, out.data_ptr()))
         self._obs_out = out
 

@@ -151,7 +151,7 @@ int mpb_get_sprites(mpb_handle h, int env, mp_sprite *out, int cap);
  * max_step; reward targets / weights in the order res_pop, com_pop, ind_pop, traffic, num_plants,
  * mayor_rating (env.py:31-56).  Leaves every env with an empty shadow map. */
 enum mpb_env_buffer {
-    MPB_ENV_OBS = 0,     /* float32 [n_envs, 32, W, H], channel order of env.py:315-332            */
+    MPB_ENV_OBS = 0,     /* float32 [n_envs, 32 (38 with poet), W, H], channel order of env.py:315-332 */
     MPB_ENV_REWARD,      /* float32 [n_envs]                                                     */
     MPB_ENV_DONE         /* uint8 [n_envs]                                                       */
 };
@@ -180,6 +180,12 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
  * the same step covers is skipped and is not cleared by later builds (TileMap.acted, tilemap.py:402-404).
  * Then setFunds, MicropolisControl.simTick, observation / reward / done exactly as mpb_env_step. */
 int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream);
+
+/* MicropolisEnv(poet=True) observation (env.py:301-313): the three population planes are divided by their
+ * parameter ranges and six planes are added, target k divided by param_ranges[k] (double [6]), before the
+ * static-build plane: 38 planes instead of 32.  Reallocates MPB_ENV_OBS (fetch the pointer again) and
+ * returns the number of planes; enable == 0 restores the 32-plane layout. */
+int mpb_env_set_poet(mpb_handle h, int enable, const double *param_ranges);
 
 /* Where mpb_env_step / mpb_env_step_host / mpb_env_reset_finish write the observations from now on:
  * float32 [n_envs, 32, W, H] DEVICE memory of the caller -- e.g. RolloutStorage.obs[step + 1]

@@ -320,6 +320,8 @@ class RefEnv:
                         'mayor_rating': 0}
         self.num_tools = self.micro.num_tools
         self.num_step = 0
+        self.poet = False
+        self.param_ranges = [750, 100, 100, 2000, 100, 100]         # env.py:39-48 param_bounds, ub - lb
         self.city_metrics = self.get_city_metrics()
         self.last_city_metrics = self.city_metrics
 
@@ -353,9 +355,16 @@ class RefEnv:
         f = np.float32
         scalars = [s.resPop, s.comPop, s.indPop, float(f(s.resValve) / f(2000)), float(f(s.comValve) / f(1500)),
                    float(f(s.indValve) / f(1500))]
+        if getattr(self, 'poet', False):                            # env.py:305-312
+            for j in range(3):
+                scalars[j] = scalars[j] / self.param_ranges[j]
+            trg_metrics = [v for k, v in self.city_trgs.items()]
+            for i in range(len(trg_metrics)):
+                trg_metrics[i] = trg_metrics[i] / self.param_ranges[i]
+            scalars += trg_metrics
         state = self.micro.map.getMapState()
         density = self.micro.getDensityMaps()
-        layers = np.zeros((6, self.MAP_X, self.MAP_Y))
+        layers = np.zeros((len(scalars), self.MAP_X, self.MAP_Y))
         for i, v in enumerate(scalars):
             layers[i].fill(v)
         return np.concatenate((state, density, layers, self.micro.map.static_builds), 0)

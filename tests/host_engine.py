@@ -85,6 +85,16 @@ class HostGym(HostEngine):
                                self.done.ctypes.data)
         return self.obs.copy(), float(self.rew[0]), bool(self.done[0])
 
+    def set_poet(self, ranges, trg=None):
+        r = np.ascontiguousarray(ranges, np.float64)
+        self._lib.mph_env_set_poet.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self._lib.mph_env_set_poet(self._h, 1, r.ctypes.data)
+        if trg is not None:
+            t = np.ascontiguousarray(trg, np.float64)
+            self._lib.mph_env_set_targets.argtypes = [C.c_void_p, C.c_void_p]
+            self._lib.mph_env_set_targets(self._h, t.ctypes.data)
+        self.obs = np.zeros((38, self.W, self.H), np.float32)
+
     def step_paint(self, tools):
         t = np.ascontiguousarray(tools, np.uint8).reshape(-1)
         assert t.size == self.W * self.H

@@ -117,6 +117,18 @@ void mph_env_get_shadow(void *p, uint8_t *zone, uint8_t *stat, int16_t *center, 
     memcpy(counters, v, sizeof(v));
 }
 
+void mph_env_set_poet(void *p, int enable, const double *ranges)
+{
+    HostEnv *h = (HostEnv *)p;
+    h->cfg.poet = enable ? 1 : 0;
+    for (int i = 0; i < GYM_NUM_METRICS; i++) h->cfg.param_range[i] = enable ? ranges[i] : 0.0;
+}
+void mph_env_set_targets(void *p, const double *trg)
+{
+    HostEnv *h = (HostEnv *)p;
+    for (int i = 0; i < GYM_NUM_METRICS; i++) h->cfg.trg[i] = trg[i];
+}
+
 // MicropolisPaintEnv.step on the harness
 void mph_env_step_paint(void *p, const uint8_t *tools, float *obs, float *reward, uint8_t *done)
 {

@@ -115,3 +115,28 @@ def test_device_gym_layer_matches_oracle(seed, size, terrain, static_p):
 def test_full_world_window_at_origin():
     """BASELINE config 4 addressing: 120x100 window at offset (0,0)."""
     _rollout(5, 12, (120, 100), True, 0.0, xs=0, ys=0)
+
+
+def test_poet_observation_planes():
+    """MicropolisEnv(poet=True) (env.py:301-313): 38 planes, pops / ranges and targets / ranges."""
+    seed, size = 7, 16
+    r = RefEngine()
+    env = RefEnv(r, size, max_step=10 ** 6, empty_start=False)
+    env.poet = True
+    env.city_trgs = {'res_pop': 320, 'com_pop': 77, 'ind_pop': 13, 'traffic': 900, 'num_plants': 3, 'mayor_rating': 61}
+    h = HostGym()
+    h.configure(size, size, 10 ** 6)
+    h.set_poet(env.param_ranges, [env.city_trgs[k] for k in ('res_pop', 'com_pop', 'ind_pop', 'traffic', 'num_plants',
+                                                              'mayor_rating')])
+    env.reset_begin(1000 + seed, seed)
+    h.reset_begin(True, 1000 + seed, seed)
+    o0, o1 = env.reset_finish(), h.reset_finish()
+    assert o0.shape == (38, size, size) and np.array_equal(o0.astype(np.float32), o1)
+    rng = np.random.default_rng(seed)
+    for t in range(60):
+        a = int(rng.integers(0, 20 * size * size))
+        o0, r0, d0, _ = env.step(a)
+        o1, r1, d1 = h.step(a)
+        assert np.array_equal(o0.astype(np.float32), o1), (t, np.argwhere(o0.astype(np.float32) != o1)[:4])
+        assert r0 == r1
+    assert float(o1[31, 0, 0]) == np.float32(320 / 750) and float(o1[36, 3, 3]) == np.float32(61 / 100)

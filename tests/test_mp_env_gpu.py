@@ -154,3 +154,36 @@ def test_1000_tick_seeded_rollout_bit_exact():
                 d = diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
                 assert not d, (t, i, d)
     env.close()
+
+
+def test_poet_observation_on_gpu():
+    """MicropolisEnv.setMapSize(poet=True) (env.py:157-158, 301-313) against the oracle: 38 planes."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisEnv
+    n, size = 3, 16
+    seeds = np.arange(n) + 70
+    env = MicropolisEnv(num_envs=n)
+    env.setMapSize(size, max_step=10 ** 6, empty_start=False, poet=True)
+    env.set_params({'res_pop': 320, 'com_pop': 77, 'ind_pop': 13, 'traffic': 900, 'num_plants': 3, 'mayor_rating': 61})
+    assert env.observation_space.shape == (38, size, size)
+    refs = [RefEnv(RefEngine(), size, max_step=10 ** 6, empty_start=False) for _ in range(n)]
+    m = env.micro
+    m.newMap(seeds + 1000, seeds)
+    for i, r in enumerate(refs):
+        r.poet = True
+        r.city_trgs = dict(env.city_trgs)
+        r.reset_begin(int(seeds[i]) + 1000, int(seeds[i]))
+    m._ck(m._L.mpb_env_reset_finish(m._h, None, m.engine._stream()))
+    for i, r in enumerate(refs):
+        assert np.array_equal(r.reset_finish().astype(np.float32), m.obs[i].cpu().numpy())
+    rng = np.random.default_rng(2)
+    for t in range(25):
+        acts = rng.integers(0, 20 * size * size, n).astype(np.int64)
+        obs, rew, done, _ = env.step(torch.from_numpy(acts))
+        assert tuple(obs.shape) == (n, 38, size, size)
+        obs = obs.cpu().numpy()
+        for i, r in enumerate(refs):
+            o, rr, d, _ = r.step(int(acts[i]))
+            assert np.array_equal(o.astype(np.float32), obs[i]), (t, i)
+            assert rr == float(rew[i, 0].item())
+    env.close()
