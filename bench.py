@@ -297,6 +297,11 @@ def run_gol(args):
         peak, src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
     B = 32 + 32 + 8 + 4 + 4 + 1 + w * w * 4           # packed rows r/w, int64 action, reward, pop, done, fp32 state plane
     achieved = B * N / (total_ms / K / 1000.0) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gol_traffic.json")))["dram_bytes_per_env_tick"] * N
+    except Exception:
+        pass
     # CPU baseline: the numpy restatement of world_pytorch.py (oracle/gol_oracle.py), one core, bounded sample
     from oracle import gol_oracle as go
     n_cpu = min(N, 4096)
@@ -317,7 +322,7 @@ def run_gol(args):
                     "note": "golb_step_host: int64 actions H2D, step, float32 rewards D2H; the (N,2,16,16) fp32 "
                             "observation stays in HBM (DLPack)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": src, "algorithmic_bytes_per_env_tick": B},
+                         "traffic": traffic, "peak_source": src, "algorithmic_bytes_per_env_tick": B},
             "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": "%d numpy steps of %d boards (oracle/gol_oracle.py multi_step)" % (reps, n_cpu)}}
     print(json.dumps(line), flush=True)
