@@ -136,14 +136,19 @@ MPD void env_call(Env &e, int fn, int a, int b)
     case FN_COLLECT_TAX: if (lead) collect_tax(e); break;
     case FN_CITY_EVAL: if (lead) city_evaluation(e); break;
     case FN_SEND_MESSAGES: if (lead) send_messages(e); break;
-    case FN_DO_DISASTERS: if (lead) do_disasters(e); break;
+    case FN_DO_DISASTERS: {
+        int quake = 0;
+        if (lead) quake = do_disasters(e, true);
+        if (coop_bcast(e, quake)) make_earthquake_coop(e);
+        break;
+    }
     case FN_MOVE_OBJECTS: if (lead) move_objects(e); break;
     case FN_ANIMATE: animate_tiles(e); break;
     case FN_SIMULATE: simulate(e); break;
     case FN_DO_SIM_INIT: do_sim_init(e); break;
     case FN_MAKE_FLOOD: if (lead) make_flood(e); break;
     case FN_MAKE_TORNADO: if (lead) make_tornado(e); break;
-    case FN_MAKE_EARTHQUAKE: if (lead) make_earthquake(e); break;
+    case FN_MAKE_EARTHQUAKE: make_earthquake_coop(e); break;
     case FN_MAKE_MONSTER: if (lead) make_monster(e); break;
     case FN_SET_FIRE: if (lead) set_fire(e); break;
     case FN_MAKE_EXPLOSION: if (lead) make_explosion(e, a, b); break;

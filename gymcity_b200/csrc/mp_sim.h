@@ -15,7 +15,8 @@ namespace mp {
 
 MPN void city_evaluation(Env &e);                       // mp_eval part below
 MPN void move_objects(Env &e);                          // mp_sprites.h
-MPN void do_disasters(Env &e);                          // mp_sprites.h
+MPN int do_disasters(Env &e, bool defer_quake);         // mp_sprites.h
+MPN void make_earthquake_coop(Env &e);                  // mp_sprites.h
 MPN void make_explosion_at(Env &e, int x, int y);       // mp_sprites.h
 MPN void make_explosion(Env &e, int x, int y);          // mp_sprites.h
 MPN void generate_train(Env &e, int x, int y);          // mp_sprites.h
@@ -2050,7 +2051,11 @@ MPD void simulate_phase(Env &e, int phase)
         break;
     case 15:
         if (scan_due(cyc, si, 1, 10, 20)) fire_analysis(e);
-        if (e.c.lead()) do_disasters(e);
+        {   // an earthquake (300-1000 random tile probes) is handed to all lanes instead of the serial lane
+            int quake = 0;
+            if (e.c.lead()) quake = do_disasters(e, true);
+            if (coop_bcast(e, quake)) make_earthquake_coop(e);
+        }
         break;
     }
 }

@@ -666,6 +666,54 @@ MPN void make_earthquake(Env &e)
     }
 }
 
+// [ALL] makeEarthquake with the probes spread over the lanes.  An iteration draws x = getRandom(119) and
+// y = getRandom(99) -- two LCG steps unless a draw is rejected (16 resp. 36 of 65536 values) -- and does
+// nothing unless the tile is vulnerable (a non-centre building tile: ~0.5 % of a gym city's world).  So
+// 32 iterations are evaluated at once, lane k on draws 2k+1 and 2k+2 after the current state (jump-ahead);
+// the iterations in front of the first lane that sees a rejected draw or a vulnerable tile are no-ops
+// and are committed as 2 draws each, that one iteration is replayed by the serial lane, and so on.
+MPN void make_earthquake_coop(Env &e)
+{
+#if defined(__CUDA_ARCH__)
+    int strength = 0;
+    if (e.c.lead()) strength = rnd(e, 700) + 300;
+    strength = coop_bcast(e, strength);
+    e.c.sync();
+    const int lane = e.c.tid;
+    int z = 0;
+    while (z < strength) {
+        const uint32_t rng = S.rng;
+        const int nb = tmin(32, strength - z);
+        uint32_t x0 = lcg_jump(rng, 2 * lane + 1);
+        const int r1 = lcg_r16(x0);
+        x0 = x0 * 1103515245u + 12345u;
+        const int r2 = lcg_r16(x0);
+        bool special = false;
+        if (lane < nb) {
+            special = r1 >= 65520 || r2 >= 65500;           // getRandom's rejection: (0xffff / range) * range
+            if (!special) special = vulnerable(e.map[tix(r1 % WORLD_W, r2 % WORLD_H)]);
+        }
+        const unsigned sm = __ballot_sync(0xffffffffu, special);
+        const int first = sm ? __ffs(sm) - 1 : nb;
+        e.c.sync();
+        if (e.c.lead()) {
+            S.rng = lcg_jump(rng, 2 * first);
+            if (first < nb) {                               // the literal iteration z + first
+                const int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
+                if (vulnerable(e.map[tix(x, y)])) {
+                    if (((z + first) & 0x3) != 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
+                    else mset(e, tix(x, y), (uint16_t)random_fire(e));
+                }
+            }
+        }
+        z += first + (first < nb ? 1 : 0);
+        e.c.sync();
+    }
+#else
+    make_earthquake(e);
+#endif
+}
+
 // [LEAD] disasters.cpp:273-290 setFire
 MPN void set_fire(Env &e)
 {
@@ -702,11 +750,12 @@ MPN void make_flood(Env &e)
 
 // [LEAD] disasters.cpp:82-144 doDisasters (scenario == SC_NONE on this path, so
 // disasterEvent never leaves SC_NONE and scenarioDisaster is unreachable)
-MPN void do_disasters(Env &e)
+// defer_quake: return 1 instead of running makeEarthquake (the caller runs make_earthquake_coop on all lanes)
+MPN int do_disasters(Env &e, bool defer_quake)
 {
     const int16_t chance[3] = { 10 * 48, 5 * 48, 60 };
     if (S.floodCount) S.floodCount--;
-    if (!S.enableDisasters) return;
+    if (!S.enableDisasters) return 0;
     int lvl = S.gameLevel;
     if (lvl > 2) lvl = 0;
     if (!rnd(e, chance[lvl])) {
@@ -715,12 +764,16 @@ MPN void do_disasters(Env &e)
         case 2: case 3: make_flood(e); break;
         case 4: break;
         case 5: make_tornado(e); break;
-        case 6: make_earthquake(e); break;
+        case 6:
+            if (defer_quake) return 1;
+            make_earthquake(e);
+            break;
         case 7: case 8:
             if (S.pollutionAverage > 60) make_monster(e);
             break;
         }
     }
+    return 0;
 }
 
 #undef S
