@@ -1461,10 +1461,13 @@ MPN void send_messages(Env &e)
 // ------------------------------------------------------------------ phase 11: power
 // [LEAD] power.cpp:76-156 doPowerScan stack walk (powerGridMap already cleared by ALL).
 // Literal replay: numPower counts visits AND pops, so the cut-off depends on traversal order.
-MPN void power_scan_walk(Env &e)
+// Returns true if the walk stayed well clear of the capacity cut-off (the result then does not depend
+// on how many duplicate plant entries the stack held).
+MPN bool power_scan_walk(Env &e)
 {
     const int maxPower = S.coalPowerPop * 700 + S.nuclearPowerPop * 2000;     // <= 32767 * 2000 < 2^31
     int numPower = 0, sp = S.powerStackPointer;
+    const bool no_seeds = sp <= 0;                // nothing to walk from: the grid stays empty
     // index form of Position::move for the four cardinal directions (N, E, S, W)
     while (sp > 0) {
         int p = e.pstack[sp];
@@ -1472,7 +1475,7 @@ MPN void power_scan_walk(Env &e)
         int step = 0, conNum;
         do {
             numPower++;
-            if (numPower > maxPower) { S.powerStackPointer = sp; return; }
+            if (numPower > maxPower) { S.powerStackPointer = sp; return false; }
             p += step;
             e.power[p >> 5] |= 1u << (p & 31);
             const int x = p / WORLD_H, y = p - x * WORLD_H;
@@ -1494,6 +1497,7 @@ MPN void power_scan_walk(Env &e)
         } while (conNum);
     }
     S.powerStackPointer = sp;
+    return no_seeds || numPower + 256 < maxPower;
 }
 
 // [ALL]
@@ -1501,10 +1505,22 @@ MPN void power_scan_walk(Env &e)
 // (simulate.cpp:226, 289, 418); it is folded in here so that refresh_need sees the new value.
 MPN void do_power_scan(Env &e, bool set_new_power = true)
 {
+    // Memo (Scalars::powerQuiet / powerPure): nothing conductive has changed since a scan whose seeds were
+    // all current plants, so the walk would rebuild the grid it already has; only its side effects remain --
+    // the drained stack and newPower.
+    e.c.sync();
+    if (S.powerQuiet && S.powerPure && S.newPower) {
+        e.c.sync();
+        if (e.c.lead()) S.powerStackPointer = 0;
+        e.c.sync();
+        return;
+    }
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
     e.c.sync();
     if (e.c.lead()) {
-        power_scan_walk(e);
+        const bool headroom = power_scan_walk(e);
+        S.powerPure = (S.powerQuiet && headroom) ? 1 : 0;
+        S.powerQuiet = headroom ? 1 : 0;          // a cut-off walk can leave seeds on the stack for the next scan
         if (set_new_power) S.newPower = 1;
     }
     e.c.sync();

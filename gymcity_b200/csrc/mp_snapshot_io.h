@@ -42,6 +42,7 @@ inline int snapshot_get_field(Env &e, int field, void *out, int cap)
         for (int i = 0; i < NTILES; i++) o[i] = (e.power[i >> 5] >> (i & 31)) & 1u;
         return NTILES;
     }
+    e.s->powerQuiet = 0; e.s->powerPure = 0;
     if (field == MPF_POWER_STACK) {
         int n = POWER_STACK_SIZE * 4;
         if (cap < n) return -1;
@@ -61,6 +62,7 @@ inline int snapshot_get_field(Env &e, int field, void *out, int cap)
 
 inline void snapshot_rebuild_bitmaps(Env &e)
 {
+    e.s->powerQuiet = 0; e.s->powerPure = 0;    // state written from outside: the next power scan runs
     for (int w = 0; w < POWER_WORDS; w++) {
         uint32_t m = 0, nd = 0;
         for (int b = 0; b < 32; b++) {

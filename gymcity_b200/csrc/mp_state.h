@@ -98,6 +98,13 @@ struct Scalars {
     int16_t spriteHead, globalSprites[SPR_COUNT], curMapStackPointer;
     uint8_t taxFlag, resCap, comCap, indCap, newPower, doInitialEval, autoBulldoze, autoBudget;
     uint8_t enableDisasters, doAnimation, tilesAnimated, spriteOverflow;
+    // derived, not part of the reference state -- memo for doPowerScan.  The grid a scan produces is a
+    // function of the map's conductive layout and of the seeds pushed since the previous scan (plant
+    // centres, including stale ones of plants removed meanwhile).  powerQuiet: no write has flipped a
+    // tile's CONDBIT since the last scan (cleared by mset and by bulk map / state writes).  powerPure: the
+    // last scan followed a quiet interval (all its seeds were current plants) and stayed clear of the
+    // capacity cut-off.  A scan that finds both set would recompute the grid it already has.
+    uint8_t powerQuiet, powerPure, pad_[6];
     int16_t curMapStack[MAX_TRAFFIC_DISTANCE + 2];   // packed x*100+y, entries 1..pointer
 };
 static_assert(sizeof(Scalars) % 8 == 0, "Scalars is copied to shared memory word by word");
@@ -274,6 +281,7 @@ MPN void mset(Env &e, int idx, int v)
 MPD void mset(Env &e, int idx, int v)
 #endif
 {
+    if ((e.map[idx] ^ v) & CONDBIT) e.s->powerQuiet = 0;
     e.map[idx] = (uint16_t)v;
     const uint32_t bit = 1u << (idx & 31);
     const uint32_t w = e.act[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
@@ -284,6 +292,7 @@ MPD void mset(Env &e, int idx, int v)
 // [ALL] recompute both bitmaps from the map (after bulk writes: clearMap, terrain, state upload)
 MPD void rebuild_active(Env &e)
 {
+    if (e.c.lead()) { e.s->powerQuiet = 0; e.s->powerPure = 0; }
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
         uint32_t m = 0, nd = 0;
         for (int b = 0; b < 32; b++) {
