@@ -184,12 +184,32 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     const int ph0 = MP_FEPC > 1 ? s_ph0 : 0;
     const long long t_loop = clock64();
     unsigned int busy = 0;
+    // frames this env runs in this launch, and the gym path's common case kept in registers: at simSpeed 3
+    // every frame simulates, so speedCycle and phaseCycle are plain counters (written back after the loop)
+    int nrun = 0;
+    bool fast = false;
+    int phase = 0, sc = 0;
+    if (live) {
+        nrun = count;
+        if (respect_passes) nrun = e.s->simSpeed ? min(count, max(0, (int)e.s->simPasses - first)) : 0;
+        fast = e.s->simSpeed == 3 && !e.s->initSimLoad;
+        phase = e.s->phaseCycle & 15;
+        sc = e.s->speedCycle;
+    }
     MP_NOUNROLL for (int i = 0; i < count; i++) {
-        const bool go = live && (!respect_passes || (e.s->simSpeed && first + i < e.s->simPasses));
-        int ran = 0;
+        const bool go = i < nrun;
         const unsigned int t0 = (unsigned int)clock64();
-        if (go) ran = sim_loop_head(e);
-        if (go) sim_loop_tail(e, ran);
+        if (go) {
+            if (fast) {
+                sim_phase(e, phase);
+                phase = (phase + 1) & 15;
+                sc = (sc + 1) & 1023;                                  // simFrame: if (++speedCycle > 1023) speedCycle = 0
+                sim_sprites(e);
+            } else {
+                const int ran = sim_loop_head(e);
+                sim_loop_tail(e, ran);
+            }
+        }
         const unsigned int dt = (unsigned int)clock64() - t0;          // this env's own time, barrier waits excluded
         busy += dt;
         if (prof && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
@@ -199,6 +219,10 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         }
     }
     if (!live) return;
+    if (fast && lane == 0 && nrun > 0) {
+        e.s->phaseCycle = (int16_t)phase;
+        e.s->speedCycle = (int16_t)sc;
+    }
     __syncwarp();
     for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
     if (lane == 0) {

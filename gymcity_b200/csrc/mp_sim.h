@@ -2093,6 +2093,21 @@ MPP void simulate(Env &e)
 // The frame comes in two halves so that a CTA of several envs can put a barrier between the
 // simulation phase and the sprite pass (each half then runs the same code in every warp).
 // Returns phase + 1 if the phase was simulated, 0 if the speed divider skipped it.
+// [ALL] one simulation phase + its closing barrier, out of line once (the frame loops call it)
+MPN void sim_phase(Env &e, int phase)
+{
+    simulate_phase(e, phase);
+    e.c.sync();
+}
+// [LEAD-guarded inside] the sprite pass of a frame (moveObjects; an empty list only counts the cycle)
+MPD void sim_sprites(Env &e)
+{
+    if (e.c.lead()) {
+        if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }
+        else move_objects(e);
+    }
+    e.c.sync();
+}
 MPN int sim_loop_head(Env &e)
 {
     const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
@@ -2107,10 +2122,7 @@ MPN int sim_loop_head(Env &e)
         }
     }
     run = coop_bcast(e, run);
-    if (run) {
-        simulate_phase(e, phase);
-        e.c.sync();
-    }
+    if (run) sim_phase(e, phase);
     return run ? phase + 1 : 0;
 }
 MPN void sim_loop_tail(Env &e, int ran)
