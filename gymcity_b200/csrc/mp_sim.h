@@ -1545,6 +1545,55 @@ MPN void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
     e.c.sync();
 }
 
+// Sparse form of the same pass.  The half-resolution maps of a gym city are zero outside the few dozen
+// cells around the build window, and smoothing zeros gives zeros: `box` = {x0, x1, y0, y1} (inclusive)
+// bounds every non-zero cell of src; the pass zero-fills dst, computes only the box grown by one cell,
+// and grows `box` for the next pass.  An empty box (x0 > x1) means src is all zero.
+struct CellBox { int x0, x1, y0, y1; };
+MPD void zero_byte2(Env &e, uint8_t *m)
+{
+    uint4 *q = reinterpret_cast<uint4 *>(m);                    // 3000 bytes + padding = 188 uint4
+    for (int i = e.c.tid; i < (N2 + 15) / 16; i += e.c.n) q[i] = make_uint4(0, 0, 0, 0);
+}
+MPD void smooth_byte2_box(Env &e, const uint8_t *src, uint8_t *dst, CellBox &box)
+{
+    zero_byte2(e, dst);
+    e.c.sync();
+    if (box.x0 > box.x1) return;
+    box.x0 = tmax(box.x0 - 1, 0); box.x1 = tmin(box.x1 + 1, W2 - 1);
+    box.y0 = tmax(box.y0 - 1, 0); box.y1 = tmin(box.y1 + 1, H2 - 1);
+    const int bh = box.y1 - box.y0 + 1, cells = (box.x1 - box.x0 + 1) * bh;
+    for (int k = e.c.tid; k < cells; k += e.c.n) {
+        const int cx = k / bh, x = box.x0 + cx, y = box.y0 + (k - cx * bh), i = x * H2 + y;
+        int z = 0;
+        if (x > 0) z += src[i - H2];
+        if (x < W2 - 1) z += src[i + H2];
+        if (y > 0) z += src[i - 1];
+        if (y < H2 - 1) z += src[i + 1];
+        z = (z + src[i]) >> 2;
+        dst[i] = (uint8_t)tmin(z, 255);
+    }
+    e.c.sync();
+}
+// bounding box of the cells a lane has seen -> the group's box
+MPD void box_add(CellBox &b, int x, int y)
+{
+    b.x0 = tmin(b.x0, x); b.x1 = tmax(b.x1, x); b.y0 = tmin(b.y0, y); b.y1 = tmax(b.y1, y);
+}
+MPD void box_reduce(Env &e, CellBox &b)
+{
+#if defined(__CUDA_ARCH__)
+    for (int o = 16; o > 0; o >>= 1) {
+        b.x0 = min(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, o));
+        b.x1 = max(b.x1, __shfl_xor_sync(0xffffffffu, b.x1, o));
+        b.y0 = min(b.y0, __shfl_xor_sync(0xffffffffu, b.y0, o));
+        b.y1 = max(b.y1, __shfl_xor_sync(0xffffffffu, b.y1, o));
+    }
+#else
+    (void)e; (void)b;
+#endif
+}
+
 // [ALL] scan.cpp:80-105 smoothStationMap (in place through a temporary copy)
 MPN void smooth_station(Env &e, int16_t *m)
 {
@@ -1686,6 +1735,7 @@ MPN void ptlv_scan(Env &e)
     }
     e.c.sync();
     int lvtot = 0, lvnum = 0;
+    CellBox pbox = { W2, -1, H2, -1 };               // cells with pollution sources
     for (int i = e.c.tid; i < N2; i += e.c.n) {
         int x = i / H2, y = i - x * H2, wx = x * 2, wy = y * 2;
         int plevel = 0;
@@ -1708,6 +1758,7 @@ MPN void ptlv_scan(Env &e)
         }
         plevel = tmin(plevel, 255);
         e.tmp1[i] = (uint8_t)plevel;
+        if (plevel) box_add(pbox, x, y);
         if (lvflag) {
             int dis = 34 - city_center_distance(e, wx, wy) / 2;
             dis = dis << 2;
@@ -1726,10 +1777,16 @@ MPN void ptlv_scan(Env &e)
     coop_add(e, 1, lvnum);
     e.c.sync();
     if (e.c.lead()) S.landValueAverage = e.c.red[1] > 0 ? (int16_t)(e.c.red[0] / e.c.red[1]) : (int16_t)0;
-    smooth_byte2(e, e.tmp1, e.tmp2);
-    smooth_byte2(e, e.tmp2, e.tmp1);
+    box_reduce(e, pbox);
+    smooth_byte2_box(e, e.tmp1, e.tmp2, pbox);
+    smooth_byte2_box(e, e.tmp2, e.tmp1, pbox);
     // pollution max: draws depend on the running maximum, so this is the serial lane
-    for (int i = e.c.tid; i < N2; i += e.c.n) e.pollution[i] = e.tmp1[i];
+    {
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp1);
+        uint4 *o = reinterpret_cast<uint4 *>(e.pollution);
+        for (int i = e.c.tid; i < N2 / 16; i += e.c.n) o[i] = q[i];
+        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pollution[i] = e.tmp1[i];
+    }
     e.c.sync();
     {
         int pnum, ptot;
@@ -1808,8 +1865,9 @@ MPN void pop_density_scan(Env &e)
     if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; e.c.red[2] = 0; }
     e.c.sync();
     int xt = 0, yt = 0, zt = 0;
+    CellBox box = { W2, -1, H2, -1 };
     // zone centres are active tiles: walk the active bitmap instead of all 12 000 tiles
-    for (int i = e.c.tid; i < N2 / 4; i += e.c.n) reinterpret_cast<uint32_t *>(e.tmp1)[i] = 0;
+    zero_byte2(e, e.tmp1);
     e.c.sync();
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
         uint32_t m = e.act[w];
@@ -1836,6 +1894,7 @@ MPN void pop_density_scan(Env &e)
             if (!later) {
                 int pop = population_density_of(e, x, y, mv & LOMASK) * 8;
                 e.tmp1[(x >> 1) * H2 + (y >> 1)] = (uint8_t)tmin(pop, 254);
+                if (pop) box_add(box, x >> 1, y >> 1);
             }
         }
     }
@@ -1843,10 +1902,21 @@ MPN void pop_density_scan(Env &e)
     coop_add(e, 1, yt);
     coop_add(e, 2, zt);
     e.c.sync();
-    smooth_byte2(e, e.tmp1, e.tmp2);
-    smooth_byte2(e, e.tmp2, e.tmp1);
-    smooth_byte2(e, e.tmp1, e.tmp2);
-    for (int i = e.c.tid; i < N2; i += e.c.n) e.pop[i] = (uint8_t)(e.tmp2[i] * 2);
+    box_reduce(e, box);
+    smooth_byte2_box(e, e.tmp1, e.tmp2, box);
+    smooth_byte2_box(e, e.tmp2, e.tmp1, box);
+    smooth_byte2_box(e, e.tmp1, e.tmp2, box);
+    {   // populationDensityMap = tempMap2 * 2 (Byte wrap), 16 cells per 128-bit word
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp2);
+        uint4 *o = reinterpret_cast<uint4 *>(e.pop);
+        for (int i = e.c.tid; i < N2 / 16; i += e.c.n) {
+            uint4 v = q[i];
+            v.x = (v.x & 0x7f7f7f7fu) << 1; v.y = (v.y & 0x7f7f7f7fu) << 1;
+            v.z = (v.z & 0x7f7f7f7fu) << 1; v.w = (v.w & 0x7f7f7f7fu) << 1;
+            o[i] = v;
+        }
+        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pop[i] = (uint8_t)(e.tmp2[i] * 2);
+    }
     if (e.c.lead()) {
         if (e.c.red[2] > 0) {
             S.cityCenterX = (int16_t)(e.c.red[0] / e.c.red[2]);

@@ -33,6 +33,9 @@
 #define MPQ __device__ __noinline__
 #endif
 #else
+// host harness: the 128-bit vector type the device code moves cells with
+struct uint4 { unsigned int x, y, z, w; };
+inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { uint4 v = { x, y, z, w }; return v; }
 #define MPQ inline
 #define MPP inline
 #define MPD inline
