@@ -284,7 +284,9 @@ MPN void mset(Env &e, int idx, int v)
 MPD void mset(Env &e, int idx, int v)
 #endif
 {
-    if ((e.map[idx] ^ v) & CONDBIT) e.s->powerQuiet = 0;
+    const int old = e.map[idx];
+    if (old == (int)(uint16_t)v) return;                 // repairZone, smoke and traffic art mostly rewrite what is there
+    if ((old ^ v) & CONDBIT) e.s->powerQuiet = 0;
     e.map[idx] = (uint16_t)v;
     const uint32_t bit = 1u << (idx & 31);
     const uint32_t w = e.act[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
@@ -349,20 +351,20 @@ MPD int rnd16s(Env &e)
 }
 // getRandom(range): the rejection loop lives out of line once; the inline wrapper only folds the
 // (almost always constant) range into the two numbers the loop needs.
-MPN int16_t rnd_reject(Env &e, int range1, int maxMultiple)
+MPN int rnd_reject(Env &e, int maxMultiple)
 {
     int r;
     do {
         r = rnd16(e);
     } while (r >= maxMultiple);
-    return (int16_t)(r % range1);
+    return r;
 }
+// the modulo stays in the inlined wrapper: with a literal range it folds to a multiply
 MPD int16_t rnd(Env &e, int16_t range)
 {
-    range++;
-    int maxMultiple = 0xffff / range;
-    maxMultiple *= range;
-    return rnd_reject(e, range, maxMultiple);
+    const int range1 = range + 1;
+    const int maxMultiple = (0xffff / range1) * range1;
+    return (int16_t)(rnd_reject(e, maxMultiple) % range1);
 }
 MPD int16_t ernd(Env &e, int16_t limit)
 {
