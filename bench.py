@@ -230,7 +230,8 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16/uint16 (+fp32 valves)", "data": "synthetic",
             "config": workload(args), "gpu_launches": K * launches_per_step,
-            "kernels": "per env group: k_mp_env_pre + %d x k_mp_frames + k_mp_env_post; + 3 scheduling kernels" % int(m._L.mpb_launches_per_tick(m._h)),
+            "kernels": "per env group: k_mp_env_pre + k_mp_frames<32> launches of %d frames (32 envs per CTA, frame "
+                       "lockstep) + k_mp_env_post; + memset + 3 scheduling kernels" % int(os.environ.get("MPB_FRAMES_PER_LAUNCH", 50)),
             "sim_frames_per_s": world * E * K * 200 / (total_ms / 1000.0),
             "e2e": {"value": world * E * K / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * 5,
@@ -239,8 +240,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_tick": B,
-                         "note": "the tick is latency/issue bound on the RNG-ordered serial lane, not HBM bound "
-                                 "(SURVEY 8d): frac is expected to be a few percent"},
+                         "note": "the tick is not HBM bound (SURVEY 8d: a few percent expected): ~300 KB of branchy SASS "
+                                 "run by one lane per warp is bound by instruction supply -- ncu: GPC-level L1.5 "
+                                 "instruction cache (gcc) requests at 55-65 % of peak, issue slots 30 % busy, DRAM 2 % "
+                                 "(profiles/r01_k_mp_frames_ncu_full.txt, profiles/r01_notes.md)"},
             "cpu_baseline": cb, "clocks": sampler.result(), "reward_checksum": checksum,
         }
         print(json.dumps(line), flush=True)
