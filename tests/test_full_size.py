@@ -1,0 +1,85 @@
+"""BASELINE.json's batch sizes on the GPU.  The small parity tests run one CTA of a handful of envs; the
+scheduler (heavy-first permutation, heavy env group, 32-env CTAs in frame lockstep, env groups on
+streams) only comes into play with thousands of envs.  Property used: an env's trajectory depends on its
+global index, its seeds and its actions only -- so env i of a full-size batch must equal the same env
+stepped in a two-env batch at env_offset = i, bit for bit, and (terrain path) the reference engine driven
+by the oracle gym layer with the same seeds."""
+import numpy as np
+import pytest
+
+from oracle.ref_engine import RefEngine, diff_snapshots, ref_available
+from oracle.ref_gym import RefEnv
+
+pytestmark = pytest.mark.gpu
+
+
+def _probe_indices(n):
+    return sorted({0, 1, 31, 32, 33, n // 64 - 1, n // 64, n // 3 + 5, n // 2, n - 2})
+
+
+@pytest.mark.parametrize("size,n,xs,ys,steps", [(16, 32768, 16, 8, 6), ((120, 100), 2048, 0, 0, 3)])
+def test_full_batch_envs_equal_small_batches_and_reference(size, n, xs, ys, steps):
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    from gymcity_b200.sharding import mix
+    kw = dict(seed=5, max_step=10 ** 6, empty_start=False, MAP_XS=xs, MAP_YS=ys)
+    big = MicropolisVecEnv(n, size, **kw)
+    W, H = big.MAP_X, big.MAP_Y
+    idx = _probe_indices(n)
+    small = [MicropolisVecEnv(2, size, env_offset=i, **kw) for i in idx]
+    refs = []
+    if ref_available():
+        for i in idx[:3]:
+            r = RefEnv(RefEngine(), size, max_step=10 ** 6, empty_start=False, xs=xs, ys=ys)
+            r.reset_begin(int(np.int32(mix(5, i, 0, 0))), int(np.int32(mix(5, i, 0, 1))))
+            refs.append((i, r, r.reset_finish()))
+    ob = big.reset()
+    for k, i in enumerate(idx):
+        assert torch.equal(ob[i], small[k].reset()[0]), i
+    for i, r, o0 in refs:
+        assert np.array_equal(o0.astype(np.float32), ob[i].cpu().numpy()), i
+    rng = np.random.default_rng(9)
+    nA = 20 * W * H
+    for t in range(steps):
+        a = rng.integers(0, nA, n)
+        ob, rb, db, _ = big.step(torch.from_numpy(a))
+        for k, i in enumerate(idx):
+            os_, rs, ds, _ = small[k].step(torch.from_numpy(a[i:i + 2]))
+            assert torch.equal(ob[i], os_[0]) and torch.equal(rb[i], rs[0]) and torch.equal(db[i], ds[0]), (t, i)
+        for i, r, _ in refs:
+            o, rr, d, _ = r.step(int(a[i]))
+            assert np.array_equal(o.astype(np.float32), ob[i].cpu().numpy()) and rr == float(rb[i, 0].item()), (t, i)
+    for k, i in enumerate(idx):
+        assert not diff_snapshots(big.micro.engine.snapshot(i), small[k].micro.engine.snapshot(0)), i
+    for i, r, _ in refs:
+        assert not diff_snapshots(r.micro.engine.snapshot(), big.micro.engine.snapshot(i)), i
+    # every env advanced by the same number of steps
+    ctr = big.micro.counters()
+    assert int(ctr[:, 4].min()) == steps == int(ctr[:, 4].max())
+    big.close()
+    for s in small:
+        s.close()
+
+
+def test_power_puzzle_8192_envs_is_deterministic_and_well_formed():
+    """BASELINE config 3: 32x32, 8192 envs, Wire-only actions over 5 static Residential + 1 static Nuclear."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    n, size = 8192, 32
+    out = []
+    for rep in range(2):
+        env = MicropolisVecEnv(n, size, seed=11, max_step=10 ** 6, empty_start=False, power_puzzle=True)
+        assert env.action_space.n == size * size
+        env.reset()
+        rng = np.random.default_rng(4)
+        for t in range(4):
+            obs, rew, done, _ = env.step(torch.from_numpy(rng.integers(0, size * size, n)))
+        ctr = env.micro.counters()
+        out.append((obs.sum(dim=(2, 3)).cpu().numpy(), rew.cpu().numpy().copy(), ctr.copy()))
+        static_cells = obs[:, 31].sum(dim=(1, 2)).cpu().numpy()
+        # static builds never shrink below one zone and never exceed 5 x 9 + 16 cells
+        assert static_cells.min() >= 9 and static_cells.max() <= 5 * 9 + 16
+        assert int(ctr[:, 0].max()) <= 16                                        # num_plants counts cells: one 4x4 plant
+        env.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
