@@ -17,7 +17,7 @@ def _probe_indices(n):
     return sorted({0, 1, 31, 32, 33, n // 64 - 1, n // 64, n // 3 + 5, n // 2, n - 2})
 
 
-@pytest.mark.parametrize("size,n,xs,ys,steps", [(16, 32768, 16, 8, 6), ((120, 100), 2048, 0, 0, 3)])
+@pytest.mark.parametrize("size,n,xs,ys,steps", [(16, 32768, 16, 8, 45), ((120, 100), 2048, 0, 0, 8)])
 def test_full_batch_envs_equal_small_batches_and_reference(size, n, xs, ys, steps):
     import torch
     from gymcity_b200.micropolis_env import MicropolisVecEnv
@@ -83,3 +83,41 @@ def test_power_puzzle_8192_envs_is_deterministic_and_well_formed():
         env.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert np.array_equal(out[0][2], out[1][2])
+
+
+def test_results_do_not_depend_on_the_schedule(monkeypatch):
+    """Every env of a 32768-env batch, 45 aged steps (flood fields, sprites, the dense scan path and the
+    heavy group are all live by then): the default schedule (3 env groups on streams, heavy-first order, 32
+    envs per CTA in frame lockstep) against the plainest one (one group, index order, one free-running warp
+    per CTA) -- observations, rewards, dones and bookkeeping counters of ALL envs must be identical."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    n, steps = 32768, 45
+
+    def run(envvars):
+        for k, v in envvars.items():
+            monkeypatch.setenv(k, v)
+        env = MicropolisVecEnv(n, 16, seed=21, max_step=10 ** 6, empty_start=False)
+        env.reset()
+        rng = np.random.default_rng(3)
+        rsum = torch.zeros(n, 1, device="cuda")
+        snaps = []
+        for t in range(steps):
+            obs, rew, done, _ = env.step(torch.from_numpy(rng.integers(0, 20 * 256, n)))
+            rsum += rew
+            if t % 15 == 14:
+                snaps.append((obs.clone(), done.clone()))
+        ctr = env.micro.counters()
+        maps = [env.micro.engine.get(i, "MPF_MAP").copy() for i in (0, 777, n - 1)]
+        env.close()
+        for k in envvars:
+            monkeypatch.delenv(k)
+        return snaps, rsum, ctr, maps
+
+    a = run({})
+    b = run({"MPB_GROUPS": "1", "MPB_FEPC": "1", "MPB_HEAVY_FEPC": "1", "MPB_SCHED": "0"})
+    for (oa, da), (ob, db) in zip(a[0], b[0]):
+        assert torch.equal(oa, ob) and torch.equal(da, db)
+    assert torch.equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for ma, mb in zip(a[3], b[3]):
+        assert np.array_equal(ma, mb)
