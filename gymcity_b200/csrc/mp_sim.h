@@ -1500,6 +1500,81 @@ MPN bool power_scan_walk(Env &e)
     return no_seeds || numPower + 256 < maxPower;
 }
 
+#if defined(__CUDA_ARCH__)
+// [ALL] doPowerScan as a lane-parallel flood fill over bitmaps, for the case in which the literal walk's
+// only order-dependent feature -- the numPower cut-off -- cannot trigger.  numPower counts one step per
+// newly powered tile plus one per pop, and a tile is pushed at most three times (once per neighbour it
+// still has to leave through), so numPower <= 4 T + sp for T conductive tiles and sp seeds; with
+// 4 T + sp + 256 < maxPower the walk powers exactly the conductive tiles 4-connected to a seed, which is
+// what the fixpoint below computes.  Returns false (nothing done) when that bound does not hold or the
+// grid is too small to be worth it; the caller then runs the literal walk.
+//   C (conductive bitmap, scratch in tmp1) is built from the active bitmap; P = Env::power.
+//   Tile i's neighbours are i -/+ 1 (same column: y -/+ 1, not across a column end) and i -/+ 100.
+MPN bool power_scan_parallel(Env &e)
+{
+    const int lane = e.c.tid;
+    uint32_t *C = reinterpret_cast<uint32_t *>(e.tmp1);
+    int T = 0, wlo = POWER_WORDS, whi = -1;
+    MP_NOUNROLL for (int w = lane; w < POWER_WORDS; w += 32) {
+        uint32_t a = e.act[w], c = 0;
+        while (a) {
+            const int b = __ffs(a) - 1;
+            a &= a - 1;
+            if (e.map[w * 32 + b] & CONDBIT) c |= 1u << b;
+        }
+        C[w] = c;
+        if (c) { T += __popc(c); wlo = min(wlo, w); whi = max(whi, w); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        T += __shfl_xor_sync(0xffffffffu, T, o);
+        wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+        whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+    }
+    const int sp = S.powerStackPointer;
+    const int maxPower = S.coalPowerPop * 700 + S.nuclearPowerPop * 2000;
+    if (T < 24 || 4 * T + sp + 256 >= maxPower) return false;
+    e.c.sync();
+    if (lane == 0)
+        MP_NOUNROLL for (int k = 1; k <= sp; k++) {
+            const int p = e.pstack[k];
+            e.power[p >> 5] |= 1u << (p & 31);
+            wlo = min(wlo, p >> 5); whi = max(whi, p >> 5);
+        }
+    wlo = __shfl_sync(0xffffffffu, wlo, 0);
+    whi = __shfl_sync(0xffffffffu, whi, 0);
+    e.c.sync();
+    for (;;) {
+        bool changed = false;
+        MP_NOUNROLL for (int w = wlo + lane; w <= whi; w += 32) {
+            const uint32_t c = C[w];
+            if (!c) continue;
+            uint32_t p = e.power[w];
+            // column ends inside this word: bit b with (w * 32 + b) % 100 == 0 has no upper neighbour, == 99 no lower
+            const int r = (w * 32) % WORLD_H;
+            const int b0 = (WORLD_H - r) % WORLD_H, b99 = WORLD_H - 1 - r;
+            const uint32_t y0 = b0 < 32 ? 1u << b0 : 0u, y99 = b99 < 32 ? 1u << b99 : 0u;
+            const uint32_t pm1 = w > 0 ? e.power[w - 1] : 0u, pp1 = w < POWER_WORDS - 1 ? e.power[w + 1] : 0u;
+            const uint32_t pm3 = w >= 3 ? e.power[w - 3] : 0u, pm4 = w >= 4 ? e.power[w - 4] : 0u;
+            const uint32_t pp3 = w + 3 < POWER_WORDS ? e.power[w + 3] : 0u, pp4 = w + 4 < POWER_WORDS ? e.power[w + 4] : 0u;
+            uint32_t reach = ((((p << 1) | (pm1 >> 31)) & ~y0) | (((p >> 1) | (pp1 << 31)) & ~y99)
+                              | (pm3 << 4) | (pm4 >> 28) | (pp3 >> 4) | (pp4 << 28));
+            uint32_t add = reach & c & ~p;
+            while (add) {                                   // run up and down the columns inside the word
+                p |= add;
+                add = (((p << 1) & ~y0) | ((p >> 1) & ~y99)) & c & ~p;
+                changed = true;
+            }
+            e.power[w] = p;
+        }
+        e.c.sync();
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    if (lane == 0) S.powerStackPointer = 0;
+    e.c.sync();
+    return true;
+}
+#endif
+
 // [ALL]
 // set_new_power: every caller in the reference sets newPower = true right after doPowerScan
 // (simulate.cpp:226, 289, 418); it is folded in here so that refresh_need sees the new value.
@@ -1517,8 +1592,12 @@ MPN void do_power_scan(Env &e, bool set_new_power = true)
     }
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
     e.c.sync();
+    bool filled = false;
+#if defined(__CUDA_ARCH__)
+    if (S.powerStackPointer > 0) filled = power_scan_parallel(e);
+#endif
     if (e.c.lead()) {
-        const bool headroom = power_scan_walk(e);
+        const bool headroom = filled ? true : power_scan_walk(e);
         S.powerPure = (S.powerQuiet && headroom) ? 1 : 0;
         S.powerQuiet = headroom ? 1 : 0;          // a cut-off walk can leave seeds on the stack for the next scan
         if (set_new_power) S.newPower = 1;

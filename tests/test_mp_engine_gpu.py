@@ -163,3 +163,60 @@ def test_single_functions_injected_state():
             r.call(fn)
         _check(b, refs, fn)
     b.close()
+
+
+def test_power_scan_paths_match_reference():
+    """doPowerScan's three device paths -- bitmap flood fill (large grid, ample capacity), literal walk
+    (small grid, or capacity too close: one coal plant feeding > 160 conductive tiles) and the memo (nothing
+    conductive changed between scans) -- against the reference engine: power grid, PWRBIT of every tile and
+    the zone power census after full simulation cycles."""
+    TOOL_WIRE, TOOL_RES, TOOL_COAL, TOOL_NUKE, TOOL_DOZE = 6, 0, 13, 14, 7
+    layouts = []
+    # 0: nuclear plant + a long serpentine of wire with zones hanging off it (fill path)
+    a = [(TOOL_NUKE, 20, 20)]
+    for row in range(6):
+        y = 26 + 4 * row
+        a += [(TOOL_WIRE, x, y) for x in range(18, 60)]
+        a += [(TOOL_WIRE, 59 if row % 2 == 0 else 18, y + k) for k in range(1, 4)]
+        a += [(TOOL_RES, x, y + 2) for x in range(22, 56, 8)]
+    a += [(TOOL_WIRE, 20, y) for y in range(23, 27)]
+    layouts.append(a)
+    # 1: coal plant + ~200 wire tiles: 4 T + seeds + 256 >= 700, the literal walk (and its cut-off margin)
+    a = [(TOOL_COAL, 30, 30)]
+    a += [(TOOL_WIRE, x, 34) for x in range(10, 110)] + [(TOOL_WIRE, x, 36) for x in range(10, 110)]
+    a += [(TOOL_WIRE, 10, 35), (TOOL_WIRE, 30, 33), (TOOL_WIRE, 30, 32)]
+    layouts.append(a)
+    # 2: small grid (below the fill threshold)
+    layouts.append([(TOOL_COAL, 40, 40)] + [(TOOL_WIRE, x, 44) for x in range(38, 50)] + [(TOOL_RES, 50, 46)])
+    n = len(layouts)
+    b, refs = _mk(n)
+    # a live simulation (generateSomeCity; a clearMap-only engine does not tick, SURVEY 0.5) on bare ground
+    b.generate(np.arange(n) + 50, np.arange(n) + 3)
+    bare = np.zeros(12000, np.uint16)
+    for i, r in enumerate(refs):
+        r.generate(i + 50)
+        r.seed(i + 3)
+        r.set("MPF_MAP", bare)
+        b.set(i, "MPF_MAP", bare)
+    for k in range(max(len(a) for a in layouts)):
+        t = np.array([a[k][0] if k < len(a) else -1 for a in layouts])
+        x = np.array([a[k][1] if k < len(a) else 0 for a in layouts])
+        y = np.array([a[k][2] if k < len(a) else 0 for a in layouts])
+        b.toolDown(t, x, y)
+        for i, r in enumerate(refs):
+            if t[i] >= 0:
+                r.toolDown(int(t[i]), int(x[i]), int(y[i]))
+    for rep in range(4):                     # 4 x 200 frames = 50 simulation cycles: 10 power scans, most of them memo hits
+        b.setFunds(2000000)
+        b.controlSimTick()
+        for r in refs:
+            r.setFunds(2000000)
+            r.controlSimTick()
+        _check(b, refs, "power rep %d" % rep)
+        if rep == 1:                         # cut the grid in the middle: the memo must notice
+            b.toolDown(np.full(n, TOOL_DOZE), np.array([40, 60, 44]), np.array([26, 34, 44]))
+            for r, (x, y) in zip(refs, [(40, 26), (60, 34), (44, 44)]):
+                r.toolDown(TOOL_DOZE, x, y)
+    pw = [int(b.get(i, "MPF_POWER_GRID").sum()) for i in range(n)]
+    assert pw[0] > 150 and pw[1] > 50 and pw[2] > 10, pw
+    b.close()
