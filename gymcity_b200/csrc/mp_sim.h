@@ -1733,14 +1733,17 @@ MPD void coop_add(Env &e, int slot, int v)
 // lanes, draws handed out in cell order by LCG jump-ahead, the last winning lane sets the site.
 // `vals`: one byte per cell, `valid`: optional per-cell flag (crime counts only cells with land
 // value), returns the winning cell index or -1; *count / *total are the census sums.
-MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool nonzero_only, int *count, int *total)
+// [lo, hi): cell range that can hold live cells (everything outside is known to be dead); chunks keep their
+// alignment to multiples of 32 so that the order of the draws is the full scan's.
+MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool nonzero_only, int *count, int *total,
+                     int lo = 0, int hi = N2)
 {
 #if defined(__CUDA_ARCH__)
     const int lane = e.c.tid;
     const unsigned lt = (1u << lane) - 1u;
     int vmax = 0, site = -1, cnt = 0, tot = 0;
     uint32_t rng = S.rng;
-    MP_NOUNROLL for (int base = 0; base < N2; base += 32) {
+    MP_NOUNROLL for (int base = lo & ~31; base < hi; base += 32) {
         const int i = base + lane;
         const bool in = i < N2;
         const int z = in ? vals[i] : 0;
@@ -1869,7 +1872,8 @@ MPN void ptlv_scan(Env &e)
     e.c.sync();
     {
         int pnum, ptot;
-        const int site = tie_max_scan(e, e.tmp1, nullptr, true, &pnum, &ptot);
+        const int p_lo = pbox.x0 > pbox.x1 ? 0 : pbox.x0 * H2, p_hi = pbox.x0 > pbox.x1 ? 0 : (pbox.x1 + 1) * H2;
+        const int site = tie_max_scan(e, e.tmp1, nullptr, true, &pnum, &ptot, p_lo, p_hi);
         if (e.c.lead()) {
             if (site >= 0) {
                 S.pollutionMaxX = (int16_t)((site / H2) * 2);
@@ -1897,7 +1901,30 @@ MPN void crime_scan(Env &e)
     smooth_station(e, e.policeSt);
     smooth_station(e, e.policeSt);
     smooth_station(e, e.policeSt);
-    for (int i = e.c.tid; i < N2; i += e.c.n) {
+    // Only cells with land value have crime (everything else is zeroed), and land value exists only where
+    // something is built: find the columns of the half-resolution map that hold any (128-bit loads, 16 cells
+    // each), zero the two output maps, and visit only those columns.
+    int c0 = W2, c1 = -1;
+    {
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.landval);
+        for (int j = e.c.tid; j < (N2 + 15) / 16; j += e.c.n) {
+            const uint4 v = q[j];
+            uint32_t any = v.x | v.y | v.z | v.w;
+            if (j == (N2 + 15) / 16 - 1) any = v.x | v.y;        // the last word pair is padding (3000 = 187 * 16 + 8)
+            if (any) { c0 = tmin(c0, (j * 16) / H2); c1 = tmax(c1, tmin((j * 16 + 15) / H2, W2 - 1)); }
+        }
+#if defined(__CUDA_ARCH__)
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
+            c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        }
+#endif
+    }
+    zero_byte2(e, e.crime);
+    zero_byte2(e, e.tmp2);
+    e.c.sync();
+    const int i_lo = c0 * H2, i_hi = (c1 + 1) * H2;                 // empty: i_lo > i_hi
+    for (int i = i_lo + e.c.tid; i < i_hi; i += e.c.n) {
         int x = i / H2, y = i - x * H2;
         int z = e.landval[i];
         if (z > 0) {
@@ -1908,16 +1935,13 @@ MPN void crime_scan(Env &e)
             z = tclamp(z, 0, 250);
             e.crime[i] = (uint8_t)z;
             e.tmp2[i] = 1;
-        } else {
-            e.crime[i] = 0;
-            e.tmp2[i] = 0;
         }
     }
     for (int i = e.c.tid; i < N8; i += e.c.n) e.policeEff[i] = e.policeSt[i];
     e.c.sync();
     {
         int numz, totz;
-        const int site = tie_max_scan(e, e.crime, e.tmp2, false, &numz, &totz);
+        const int site = tie_max_scan(e, e.crime, e.tmp2, false, &numz, &totz, tmin(i_lo, i_hi), i_hi);
         if (e.c.lead()) {
             if (site >= 0) {
                 S.crimeMaxX = (int16_t)((site / H2) * 2);

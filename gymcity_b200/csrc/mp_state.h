@@ -103,8 +103,9 @@ struct Scalars {
     uint8_t enableDisasters, doAnimation, tilesAnimated, spriteOverflow;
     // derived, not part of the reference state -- memo for doPowerScan.  The grid a scan produces is a
     // function of the map's conductive layout and of the seeds pushed since the previous scan (plant
-    // centres, including stale ones of plants removed meanwhile).  powerQuiet: no write has flipped a
-    // tile's CONDBIT since the last scan (cleared by mset and by bulk map / state writes).  powerPure: the
+    // centres, including stale ones of plants removed meanwhile).  powerQuiet: no write since the last scan has
+    // flipped the CONDBIT of a tile that is powered, touches a powered tile or is a plant centre (mset) and no
+    // bulk map / state write happened.  powerPure: the
     // last scan followed a quiet interval (all its seeds were current plants) and stayed clear of the
     // capacity cut-off.  A scan that finds both set would recompute the grid it already has.
     uint8_t powerQuiet, powerPure, pad_[6];
@@ -286,7 +287,23 @@ MPD void mset(Env &e, int idx, int v)
 {
     const int old = e.map[idx];
     if (old == (int)(uint16_t)v) return;                 // repairZone, smoke and traffic art mostly rewrite what is there
-    if ((old ^ v) & CONDBIT) e.s->powerQuiet = 0;
+    if ((old ^ v) & CONDBIT) {
+        // Does the flip touch the powered grid?  A tile that stops conducting matters if it was powered; a
+        // tile that starts conducting matters if it is a plant centre (a new seed) or touches a powered tile
+        // (anything joined to the grid later is joined through such a tile, whose own write is then caught).
+        bool matters;
+        if (v & CONDBIT) {
+            const int t = v & LOMASK, x = idx / WORLD_H, y = idx - x * WORLD_H;
+            matters = t == T_POWERPLANT || t == T_NUCLEAR;
+            if (y > 0) matters |= ((e.power[(idx - 1) >> 5] >> ((idx - 1) & 31)) & 1u) != 0;
+            if (y < WORLD_H - 1) matters |= ((e.power[(idx + 1) >> 5] >> ((idx + 1) & 31)) & 1u) != 0;
+            if (x > 0) matters |= ((e.power[(idx - WORLD_H) >> 5] >> ((idx - WORLD_H) & 31)) & 1u) != 0;
+            if (x < WORLD_W - 1) matters |= ((e.power[(idx + WORLD_H) >> 5] >> ((idx + WORLD_H) & 31)) & 1u) != 0;
+        } else {
+            matters = ((e.power[idx >> 5] >> (idx & 31)) & 1u) != 0;
+        }
+        if (matters) e.s->powerQuiet = 0;
+    }
     e.map[idx] = (uint16_t)v;
     const uint32_t bit = 1u << (idx & 31);
     const uint32_t w = e.act[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
