@@ -23,11 +23,9 @@ enum EditingTool : int {
 struct Fx {                 // one tool call's pending effects
     Env &e;
     int ox, oy, cost;
-    MPD Fx(Env &env, int x, int y) : e(env), ox(x - 5), oy(y - 5), cost(0)
-    {
-        uint32_t *m = (uint32_t *)(e.ovl + 256);
-        MP_NOUNROLL for (int i = 0; i < 8; i++) m[i] = 0;
-    }
+    bool any;               // something has been written: until then reads go straight to the map and the
+                            // presence mask is not even cleared (most clear-before-build calls fail early)
+    MPD Fx(Env &env, int x, int y) : e(env), ox(x - 5), oy(y - 5), cost(0), any(false) {}
     MPD int slot(int x, int y) const
     {
         int dx = x - ox, dy = y - oy;
@@ -35,6 +33,7 @@ struct Fx {                 // one tool call's pending effects
     }
     MPD int value(int x, int y) const
     {
+        if (!any) return tget(e, x, y);
         int s = slot(x, y);
         const uint32_t *m = (const uint32_t *)(e.ovl + 256);
         if (s >= 0 && ((m[s >> 5] >> (s & 31)) & 1u)) return e.ovl[s];
@@ -46,12 +45,17 @@ struct Fx {                 // one tool call's pending effects
         int s = slot(x, y);
         if (s < 0 || !inb(x, y)) return;
         uint32_t *m = (uint32_t *)(e.ovl + 256);
+        if (!any) {
+            MP_NOUNROLL for (int i = 0; i < 8; i++) m[i] = 0;
+            any = true;
+        }
         m[s >> 5] |= 1u << (s & 31);
         e.ovl[s] = (uint16_t)v;
     }
     MPD void apply()            // ToolEffects::modifyWorld (tool.cpp:113-137)
     {
         e.s->totalFunds = (int)(e.s->totalFunds - cost);
+        if (!any) return;
         const uint32_t *m = (const uint32_t *)(e.ovl + 256);
         MP_NOUNROLL for (int w = 0; w < 8; w++) {
             uint32_t bits = m[w];
