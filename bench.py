@@ -53,6 +53,8 @@ def workload(args):
                         % (w["text"], args.envs),
             "name": args.workload, "envs_per_gpu": args.envs, "map": "%dx%d window of the 120x100 world" % (W, H),
             "sim_frames_per_tick": 200,
+            "rollout_buffer": ("obs[%d, E, 32, W, H] written in place (mpb_env_set_obs_buffer)" % (args.rollout_steps + 1))
+            if getattr(args, "rollout_steps", 0) > 0 else None,
             "l2": "state working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (args.envs * 95e3 / 1e9)}
 
 
@@ -162,7 +164,18 @@ def run_ours(args):
     launches_per_step = int(m._L.mpb_launches_per_env_step(m._h))
     sp = m.engine._stream()
 
+    # BASELINE config 5's consumer: an A2C rollout buffer obs[T + 1, E, 32, W, H] (storage.py:13-15, --num-steps 5)
+    # filled in place -- the observation kernel writes step t's batch straight into slot (t mod T) + 1
+    rollout = None
+    if args.rollout_steps > 0:
+        rollout = torch.zeros(args.rollout_steps + 1, E, m.obs_channels, env.MAP_X, env.MAP_Y, device=dev)
+    nstep = [0]
+
     def step_dev(i):
+        if rollout is not None:
+            slot = rollout[nstep[0] % args.rollout_steps + 1]
+            m._ck(m._L.mpb_env_set_obs_buffer(m._h, slot.data_ptr()))
+            nstep[0] += 1
         m._ck(m._L.mpb_env_step(m._h, acts[i].data_ptr(), 0, sp))
 
     for i in range(args.age_steps):                 # untimed build-up: cities reach their random-action steady state
@@ -343,6 +356,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout-steps", type=int, default=0,
+                    help="> 0: observations go straight into an A2C rollout buffer obs[T+1, E, 32, W, H] (config 5)")
     ap.add_argument("--age-steps", type=int, default=40,
                     help="untimed env-ticks before the warm-up so the random-action cities are in steady state")
     args = ap.parse_args()
