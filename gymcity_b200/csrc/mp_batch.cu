@@ -140,7 +140,7 @@ template <int MP_FEPC>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off)
+            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off, const uint8_t *mask)
 {
     const long long t_begin = clock64();
     __shared__ int red[8 * MP_FEPC];
@@ -152,15 +152,18 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
     const int widx = blockIdx.x * MP_FEPC + (threadIdx.x >> 5);
     const int slot = widx * gstride + goff;
-    const bool live = widx < gcount && slot < n_envs;
+    bool live = widx < gcount && slot < n_envs;
+    int env = 0;
+    if (live) {
+        env = perm ? perm[slot] : slot;
+        if (mask && !mask[env]) live = false;             // masked step (mpb_env_step_masked): this env sits it out
+    }
     if (MP_FEPC == 1 && !live) return;
     const int lane = threadIdx.x & 31;
     Env &e = s_env[threadIdx.x >> 5];
-    int env = 0;
     Scalars *gs = NULL;
     uint32_t *sw = s_scal[threadIdx.x >> 5];
     if (live) {
-        env = perm ? perm[slot] : slot;
         bind_env_of(e, blocks, env, anim, red);
         gs = e.s;
         for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
@@ -379,13 +382,15 @@ k_mp_env_extinguish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-             const int64_t *actions, int static_build, const int *perm, int gstride, int goff, int gcount)
+             const int64_t *actions, int static_build, const int *perm, int gstride, int goff, int gcount,
+             const uint8_t *mask)
 {
     __shared__ int red[8 * MP_EPC];
     if (device_env_index() >= gcount) return;
     const int slot = device_env_index() * gstride + goff;
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
+    if (mask && !mask[env]) return;
     const int lane = threadIdx.x & 31;
     MP_SHARED_ENV();
     bind_env_of(e, blocks, env, anim, red);
@@ -448,6 +453,7 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 
+const uint8_t *g_step_mask = NULL;  // device mask of the envs that take part in the current masked env-step
 int g_scan_block = 1;             // map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
 int g_pad_smem = 0;               // experiment: dynamic shared memory per CTA (limits CTAs per SM)
 unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
@@ -459,7 +465,7 @@ void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, co
 {
     if (count_envs <= 0) return;
 #define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
-                       gcount, g_scan_block, g_prof, prof_off
+                       gcount, g_scan_block, g_prof, prof_off, g_step_mask
     if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 0, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
     else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
@@ -1115,6 +1121,23 @@ int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, voi
     return env_step_impl(b, actions_dev, NULL, static_build, (cudaStream_t)stream);
 }
 
+int mpb_env_step_masked(mpb_handle h, const int64_t *actions_host, int static_build, const uint8_t *mask_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!actions_host || !mask_host) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
+    CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
+    if (upload_mask(b, mask_host, st)) return -1;
+    g_step_mask = b->mask;
+    const int rc = env_step_impl(b, b->act_dev, NULL, static_build, st);
+    g_step_mask = NULL;
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream)
 {
     MpBatch *b = (MpBatch *)h;
@@ -1139,10 +1162,10 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
                                                            b->cfg, paint_dev, perm, q.stride, q.off, q.count);
         else
             k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                     actions_dev, static_build, perm, q.stride, q.off, q.count);
+                                                     actions_dev, static_build, perm, q.stride, q.off, q.count, g_step_mask);
         launch_control_sim_tick(b, gs, G, g);
         k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                  b->obs_out, b->reward, b->done, 0, NULL, perm, q.stride, q.off, q.count);
+                                                  b->obs_out, b->reward, b->done, 0, g_step_mask, perm, q.stride, q.off, q.count);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);

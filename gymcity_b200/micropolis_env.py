@@ -143,6 +143,7 @@ class MicropolisControl:
             "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
             "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
             "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
+            "mpb_env_step_masked": (i32, [vp, vp, i32, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -343,7 +344,7 @@ class MicropolisEnv:
             flat[~need] = -1
             m.apply_actions(flat, True, full_tools=True)
 
-    def reset(self, mask=None, setup_actions=None):
+    def reset(self, mask=None, setup_actions=None, static_start=None):
         """env.py:264-292.  `mask` (N,) selects the envs to reset (None = all).  `setup_actions` is an
         optional list of (flat_action (N,), static_build) applied between clearMap/newMap and the first
         simTick -- the hook the reference uses for powerPuzzle / randomStaticStart (env.py:275-278)."""
@@ -355,8 +356,6 @@ class MicropolisEnv:
         self.num_step = 0
         if self.power_puzzle and setup_actions is None:
             self.powerPuzzle(mask)
-        if self.random_builds and setup_actions is None:
-            setup_actions = self._random_static_start()
         for item in (setup_actions or []):
             flat, sb = item[0], item[1]
             full = item[2] if len(item) > 2 else False
@@ -364,6 +363,8 @@ class MicropolisEnv:
             if mask is not None:
                 flat[~np.asarray(mask, bool)] = -1
             m.apply_actions(flat, sb, full_tools=full)
+        if self.random_builds or static_start is not None:
+            self._random_static_start(mask, *(static_start or ()))
         mk, p = EngineBatch._mask(mask, self.num_envs)
         m._ck(m._L.mpb_env_reset_finish(m._h, p, m.engine._stream()))
         self.num_episode += 1
@@ -374,10 +375,26 @@ class MicropolisEnv:
             return self.state
         return self._cur_obs()
 
-    def _random_static_start(self):                         # env.py:228-241
+    def _random_static_start(self, mask=None, ks=None, actions=None):   # env.py:228-241
+        """randomStaticStart: every env being reset takes its own number k of FULL env steps (random action
+        with static_build=True, simulation tick, num_step + 1) before the reset's closing simTick; the
+        envs that are done with theirs, and the ones not being reset, sit the step out
+        (mpb_env_step_masked).  ks (N,) / actions (max k, N): the draws, for tests; by default k ~
+        U{0..W*H/10} and uniform actions from the env's generator."""
+        m, n = self.micro, self.num_envs
         num_static = int(self.MAP_X * self.MAP_Y / 10)
-        k = int(self.np_random.integers(0, num_static + 1)) if num_static > 0 else 0
-        return [(self.np_random.integers(0, self.action_space.n, self.num_envs), True) for _ in range(k)]
+        m.setFunds(m.init_funds)
+        if ks is None:
+            ks = self.np_random.integers(0, num_static + 1, n) if num_static > 0 else np.zeros(n, np.int64)
+        ks = np.asarray(ks).reshape(n)
+        live = np.ones(n, bool) if mask is None else np.asarray(mask, bool).reshape(n)
+        for j in range(int(ks.max()) if n else 0):
+            a = (self.np_random.integers(0, self.action_space.n, n) if actions is None else np.asarray(actions[j])).astype(np.int64)
+            mk = np.ascontiguousarray(((j < ks) & live).astype(np.uint8))
+            if not mk.any():
+                continue
+            a = np.ascontiguousarray(a)
+            m._ck(m._L.mpb_env_step_masked(m._h, a.ctypes.data, 1, mk.ctypes.data, m.engine._stream()))
 
     def set_obs_buffer(self, out=None):
         """Observations of the following steps / resets go to `out` (float32 CUDA tensor (N,32,W,H),

@@ -174,6 +174,12 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
 int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, int full_tools,
                    int32_t *ok_host, void *stream);
 
+/* mpb_env_step for a subset of the batch: envs with mask_host[i] == 0 (uint8 [n_envs] HOST) are left
+ * untouched -- no action, no tick, no observation / reward / done update, num_step unchanged.  Actions are
+ * HOST int64 [n_envs].  Used by MicropolisEnv.randomStaticStart (env.py:228-241), where every env takes its own
+ * number of full static-build steps during reset.  Synchronises the stream before returning. */
+int mpb_env_step_masked(mpb_handle h, const int64_t *actions_host, int static_build, const uint8_t *mask_host, void *stream);
+
 /* MicropolisPaintEnv.step (gym_city/envs/paintenv.py:43-52, paintcontrol.py:45-70): one tool per window
  * cell.  tools_dev: uint8 [n_envs][W*H] DEVICE, index into the env's tool list at cell x*H + y.  Cells are
  * visited row by row (the last column is never reached, as in the reference); a cell an earlier build of

@@ -377,6 +377,11 @@ class RefEnv:
             self.micro.updateMap()
         self.num_step = 0
 
+    def random_static_start(self, k, actions):                      # env.py:228-241 with the draws passed in
+        self.micro.engine.setFunds(self.micro.init_funds)
+        for j in range(int(k)):
+            self.step(int(actions[j]), static_build=True)
+
     def reset_finish(self):                                         # env.py:279-292
         self.micro.simTick()
         self.city_metrics = self.get_city_metrics()

@@ -187,3 +187,39 @@ def test_poet_observation_on_gpu():
             assert np.array_equal(o.astype(np.float32), obs[i]), (t, i)
             assert rr == float(rew[i, 0].item())
     env.close()
+
+
+def test_random_static_start_runs_full_steps_per_env():
+    """MicropolisEnv(random_builds=True) reset (env.py:228-241, 276-278): every env takes its own number of full
+    static-build steps (action, tick, num_step + 1) before the closing simTick -- mpb_env_step_masked."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisEnv
+    n, size = 5, 16
+    ks = np.array([0, 3, 1, 5, 2])
+    rng = np.random.default_rng(8)
+    acts = rng.integers(0, 20 * size * size, (int(ks.max()), n))
+    env = MicropolisEnv(num_envs=n)
+    env.seed(9)
+    env.setMapSize(size, max_step=10 ** 6, empty_start=False, random_builds=True)
+    obs0 = env.reset(static_start=(ks, acts)).cpu().numpy()
+    from gymcity_b200.sharding import mix
+    refs = []
+    for i in range(n):
+        r = RefEnv(RefEngine(), size, max_step=10 ** 6, empty_start=False)
+        r.reset_begin(int(np.int32(mix(9, i, 0, 0))), int(np.int32(mix(9, i, 0, 1))))
+        r.random_static_start(ks[i], acts[:, i])
+        assert np.array_equal(r.reset_finish().astype(np.float32), obs0[i]), i
+        assert r.num_step == ks[i]
+        refs.append(r)
+    ctr = env.micro.counters()
+    assert np.array_equal(ctr[:, 4].astype(int), ks)                       # num_step per env
+    assert obs0[:, 31].sum() > 0                                           # static builds exist
+    for t in range(10):
+        a = rng.integers(0, 20 * size * size, n).astype(np.int64)
+        obs, rew, done, _ = env.step(torch.from_numpy(a))
+        for i, r in enumerate(refs):
+            o, rr, d, _ = r.step(int(a[i]))
+            assert np.array_equal(o.astype(np.float32), obs[i].cpu().numpy()) and rr == float(rew[i, 0].item()), (t, i)
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+    env.close()
