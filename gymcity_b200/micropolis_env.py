@@ -294,8 +294,11 @@ class MicropolisEnv:
         m = self.micro
         if self._single():
             return (m.obs[0].cpu().numpy().astype(np.float64), float(m.reward[0, 0].item()),
-                    bool(m.done[0].item()), {})
-        return self._cur_obs(), m.reward, m.done.bool(), [{} for _ in range(self.num_envs)]
+                    bool(m.done[0].item()) and bool(self.auto_reset), {})
+        done = m.done.bool()
+        if not self.auto_reset:                              # env.py:519-520: terminal = (...) and self.auto_reset
+            done = done & False
+        return self._cur_obs(), m.reward, done, [{} for _ in range(self.num_envs)]
 
     def _cur_obs(self):
         obs = getattr(self, "_obs_out", None)
