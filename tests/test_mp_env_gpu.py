@@ -223,3 +223,21 @@ def test_random_static_start_runs_full_steps_per_env():
     for i, r in enumerate(refs):
         assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
     env.close()
+
+
+def test_soak_48_envs_250_ticks():
+    """Breadth for the rare paths (earthquakes, floods, meltdowns, the lane-parallel flood fill and dense scan):
+    48 cities x 250 env-ticks of random actions against the reference engine, every observation and reward,
+    full state at the end."""
+    n, size, steps = 48, 16, 250
+    seeds = np.arange(n) + 500
+    env, refs = _batch(n, size, True, 10 ** 9, seeds)
+    _finish(env, refs)
+    rng = np.random.default_rng(77)
+    for t in range(steps):
+        acts = rng.integers(0, 20 * size * size, n).astype(np.int64)
+        _compare_step(env, refs, acts, False, t)
+    for i, r in enumerate(refs):
+        d = diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+        assert not d, (i, d[:5])
+    env.close()
