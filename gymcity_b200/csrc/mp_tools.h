@@ -148,13 +148,21 @@ MPN void fix_single(Fx &fx, int x, int y)
     }
 }
 
+// fixSingle only ever redraws a road, rail or wire tile; the test is made at the call site so that the
+// usual case (five tiles of ground, water or buildings) costs no calls
+MPD bool fix_candidate(const Fx &fx, int x, int y)
+{
+    const int t = neutralize_road(fx.tile(x, y));
+    return (t >= T_ROADS && t <= T_INTERSECTION) || (t >= T_LHRAIL && t <= T_LVRAIL10)
+        || (t >= T_LHPOWER && t <= T_LVPOWER10);
+}
 MPD void fix_zone(Fx &fx, int x, int y)                            // connect.cpp:523-545
 {
-    fix_single(fx, x, y);
-    if (y > 0) fix_single(fx, x, y - 1);
-    if (x < WORLD_W - 1) fix_single(fx, x + 1, y);
-    if (y < WORLD_H - 1) fix_single(fx, x, y + 1);
-    if (x > 0) fix_single(fx, x - 1, y);
+    if (fix_candidate(fx, x, y)) fix_single(fx, x, y);
+    if (y > 0 && fix_candidate(fx, x, y - 1)) fix_single(fx, x, y - 1);
+    if (x < WORLD_W - 1 && fix_candidate(fx, x + 1, y)) fix_single(fx, x + 1, y);
+    if (y < WORLD_H - 1 && fix_candidate(fx, x, y + 1)) fix_single(fx, x, y + 1);
+    if (x > 0 && fix_candidate(fx, x - 1, y)) fix_single(fx, x - 1, y);
 }
 
 MPD int lay_doze(Fx &fx, int x, int y)                             // connect.cpp:193-236
