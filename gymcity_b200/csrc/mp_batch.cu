@@ -1,6 +1,7 @@
-// mp_batch.cu -- batched Micropolis engine on sm_100a: one CTA per city, state resident in HBM as
-// one contiguous block per city (mp_state.h EnvLayout), kernels + the mpb_* C-ABI of
-// include/gymcity_b200.h.
+// mp_batch.cu -- batched Micropolis engine on sm_100a: one warp per city, state resident in HBM as
+// one contiguous block per city (mp_state.h EnvLayout), kernels + the mpb_* / mpb_env_* C-ABI of
+// include/gymcity_b200.h.  The frame kernel runs 32 (16 / 8 for small batches) cities per CTA in frame
+// lockstep; the other kernels (tools, reset, gym pre / post) one city per CTA.
 //
 // What this replaces in the reference: the C++ `Micropolis` engine object as the gym path drives
 // it through SWIG (gym_city/envs/corecontrol.py:36-357) -- construction, clearMap/generateMap,
@@ -20,8 +21,8 @@ using namespace mp;
 
 namespace {
 
-// One warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's slot is released the
-// moment its city is done instead of waiting for the slower of two (32 CTAs x 64 registers fill the SM).
+// Kernels other than k_mp_frames: one warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's
+// slot is released the moment its city is done instead of waiting for the slower of two.
 constexpr int MP_EPC = 1;
 constexpr int MP_THREADS = 32 * MP_EPC;
 constexpr int ENV_STRIDE = (EnvLayout::TOTAL + 127) & ~127;
@@ -125,8 +126,8 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 // `count` simFrames (simLoop(true), main.cpp:403-425) for every env, frames [first, first + count) of
 // a simTick of simPasses frames.  All envs of the batch run the same frames in the same launch, so
 // every warp on the GPU is in (nearly) the same simulation phase and executes the same code: the
-// engine's instruction footprint (~0.5 MB) is far beyond the SM instruction caches, and a launch
-// per few frames keeps the live footprint to one phase's worth (profiles/r01_icache.md).
+// engine's instruction footprint (~0.3 MB) is far beyond the SM instruction caches, and a launch
+// per few dozen frames keeps the live footprint to a few phases' worth (profiles/r01_notes.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
 // MP_FEPC = envs (warps) per CTA.  MP_FEPC > 1 adds a CTA barrier per frame: the warps of a CTA run
 // the same frame -- the same simulation phase, hence the same code -- at the same time, so an SM's
