@@ -924,7 +924,8 @@ MPP void scan_tile(Env &e, int idx)
         }
         return;
     }
-    if (S.newPower && (mv & CONDBIT)) set_zone_power(e, x, y);
+    // (a zone centre gets its setZonePower from doZone right below: the call is idempotent and draws nothing)
+    if (S.newPower && (mv & CONDBIT) && (!(mv & ZONEBIT) || tile < T_POWERBASE)) set_zone_power(e, x, y);
     if (tile >= T_ROADBASE && tile < T_POWERBASE) { do_road(e, x, y); return; }
     if (mv & ZONEBIT) { do_zone(e, x, y); return; }
     if (tile >= T_RAILBASE && tile < T_RESBASE) { do_rail(e, x, y); return; }
