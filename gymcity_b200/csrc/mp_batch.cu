@@ -67,21 +67,42 @@ struct MpBatch {
 
 __device__ __forceinline__ int device_env_index() { return blockIdx.x * MP_EPC + (threadIdx.x >> 5); }
 
-// One Env per warp, in shared memory (see Coop).  Lane 0 fills it in; every lane then uses it.
-#define MP_SHARED_ENV() __shared__ Env s_env[MP_EPC]; Env &e = s_env[threadIdx.x >> 5]
+constexpr int SCAL_WORDS = (int)((sizeof(Scalars) + 3) / 4);
+constexpr int SCAL_BYTES = SCAL_WORDS * 4;
+constexpr int MP_DYN_SMEM = MP_EPC * SCAL_BYTES;    // dynamic shared memory of the one-warp-per-env kernels
 
-__device__ __forceinline__ void bind_env_of(Env &e, uint8_t *blocks, int env, const uint16_t *anim, int *red)
+// One Env per warp, in shared memory (see Coop), together with the env's scalar block: every kernel works on
+// a shared-memory copy of the scalars (ScalPtr tells the compiler so) and writes it back when it is done.
+// Lane 0 fills the Env in; every lane then uses it.
+// The scalar copies live at the start of the kernel's DYNAMIC shared memory (mp_dyn_smem, declared in mp_state.h):
+// ScalPtr addresses them as an offset from that symbol, which is how the compiler knows they are shared memory.
+#define MP_SHARED_ENV() __shared__ Env s_env[MP_EPC]; \
+    Env &e = s_env[threadIdx.x >> 5]; uint32_t *const sw = reinterpret_cast<uint32_t *>(mp_dyn_smem) + (threadIdx.x >> 5) * SCAL_WORDS
+
+// [ALL lanes] bind the warp's Env to env `env` and stage its scalars in `sw` (shared memory)
+__device__ __forceinline__ void bind_env_of(Env &e, uint8_t *blocks, int env, const uint16_t *anim, int *red, uint32_t *sw)
 {
+    uint8_t *blk = blocks + (size_t)env * ENV_STRIDE;
+    const uint32_t *gs = reinterpret_cast<const uint32_t *>(blk + EnvLayout::SCALARS);
+    for (int i = threadIdx.x & 31; i < SCAL_WORDS; i += 32) sw[i] = gs[i];
     if ((threadIdx.x & 31) == 0) {
-        bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+        bind_env(e, blk);
+        e.s = reinterpret_cast<Scalars *>(sw);
         e.anim = anim;
         e.c.red = red + (threadIdx.x >> 5) * 8;
     }
     __syncwarp();
 }
-__device__ __forceinline__ void bind_device_env(Env &e, uint8_t *blocks, const uint16_t *anim, int *red)
+// [ALL lanes] write the staged scalars back to the env's block
+__device__ __forceinline__ void unstage_scalars(Env &e, const uint32_t *sw)
 {
-    bind_env_of(e, blocks, device_env_index(), anim, red);
+    __syncwarp();
+    uint32_t *gs = reinterpret_cast<uint32_t *>(e.base() + EnvLayout::SCALARS);
+    for (int i = threadIdx.x & 31; i < SCAL_WORDS; i += 32) gs[i] = sw[i];
+}
+__device__ __forceinline__ void bind_device_env(Env &e, uint8_t *blocks, const uint16_t *anim, int *red, uint32_t *sw)
+{
+    bind_env_of(e, blocks, device_env_index(), anim, red, sw);
 }
 
 #define MP_ENV_GUARD() const int env = device_env_index(); if (env >= n_envs) return; const int lane = threadIdx.x & 31; (void)lane
@@ -91,8 +112,9 @@ __global__ void __launch_bounds__(MP_THREADS) k_mp_construct(uint8_t *blocks, co
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     env_construct(e, blocks + (size_t)device_env_index() * ENV_STRIDE);
+    unstage_scalars(e, sw);
 }
 
 // mode 0: clearMap; mode 1: generateSomeCity(terrain_seed) then seedRandom(sim_seed)
@@ -104,9 +126,10 @@ k_mp_reset(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *ter
     MP_ENV_GUARD();
     if (mask && !mask[env]) return;
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     if (mode == 0) clear_map(e);
     else generate_some_city(e, terrain_seeds[env], sim_seeds[env]);
+    unstage_scalars(e, sw);
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
@@ -115,12 +138,13 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     if (lane == 0) {
         const int32_t *a = txy + (size_t)env * 3;
         int r = (a[0] < 0) ? (int)TR_FAILED : tool_down(e, a[0], a[1], a[2]);
         if (results) results[env] = r;
     }
+    unstage_scalars(e, sw);
 }
 
 // `count` simFrames (simLoop(true), main.cpp:403-425) for every env, frames [first, first + count) of
@@ -147,7 +171,6 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     __shared__ int red[8 * MP_FEPC];
     // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
     // lane touches on almost every instruction: it lives in shared memory for the whole launch
-    __shared__ __align__(16) uint32_t s_scal[MP_FEPC][(sizeof(Scalars) + 3) / 4];
     __shared__ Env s_env[MP_FEPC];
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
@@ -162,15 +185,9 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     if (MP_FEPC == 1 && !live) return;
     const int lane = threadIdx.x & 31;
     Env &e = s_env[threadIdx.x >> 5];
-    Scalars *gs = NULL;
-    uint32_t *sw = s_scal[threadIdx.x >> 5];
+    uint32_t *sw = reinterpret_cast<uint32_t *>(mp_dyn_smem) + (threadIdx.x >> 5) * SCAL_WORDS;
     if (live) {
-        bind_env_of(e, blocks, env, anim, red);
-        gs = e.s;
-        for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) sw[i] = reinterpret_cast<const uint32_t *>(gs)[i];
-        __syncwarp();
-        if (lane == 0) e.s = reinterpret_cast<Scalars *>(sw);
-        __syncwarp();
+        bind_env_of(e, blocks, env, anim, red, sw);
         if (animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
     }
     // Frame lockstep: a CTA barrier after every frame keeps the warps of the CTA in the same simulation
@@ -227,8 +244,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         e.s->phaseCycle = (int16_t)phase;
         e.s->speedCycle = (int16_t)sc;
     }
-    __syncwarp();
-    for (int i = lane; i < (int)((sizeof(Scalars) + 3) / 4); i += 32) reinterpret_cast<uint32_t *>(gs)[i] = sw[i];
+    unstage_scalars(e, sw);
     if (lane == 0) {
         busy += (unsigned int)(t_loop - t_begin);                       // state load, animateTiles
         if (cycles) cycles[env] += busy;
@@ -242,8 +258,9 @@ k_mp_call(uint8_t *blocks, const uint16_t *anim, int n_envs, int fn, int a, int 
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     env_call(e, fn, a, b);
+    unstage_scalars(e, sw);
 }
 
 __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t *vals, int64_t v)
@@ -310,10 +327,11 @@ k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t 
     MP_ENV_GUARD();
     if (mask && !mask[env]) return;
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[env] : 0, terrain ? sim_seeds[env] : 0);
+    unstage_scalars(e, sw);
 }
 
 // TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
@@ -324,13 +342,14 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     if (lane == 0) {
         int r = gym_apply_action(e, gy, actions[env], static_build != 0, full != 0);
         if (ok) ok[env] = r;
     }
+    unstage_scalars(e, sw);
 }
 
 // MicropolisPaintEnv.step, part 1 (paintenv.py:43-52): one tool per window cell, then setFunds
@@ -345,13 +364,14 @@ k_mp_env_pre_paint(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *s
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
     MP_SHARED_ENV();
-    bind_env_of(e, blocks, env, anim, red);
+    bind_env_of(e, blocks, env, anim, red, sw);
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     if (lane == 0) {
         gym_paint_action(e, gy, actions + (size_t)env * cfg.W * cfg.H);
         e.s->totalFunds = cfg.init_funds;
     }
+    unstage_scalars(e, sw);
 }
 
 // Extinguisher wrapper (wrappers.py:10-160): init_age_array / one extinction event per env
@@ -361,7 +381,7 @@ k_mp_env_track_ages(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     gym_init_age_array(e, gy);
@@ -374,10 +394,11 @@ k_mp_env_extinguish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *
     MP_ENV_GUARD();
     if (mask && !mask[env]) { if (lane == 0) dels_out[env] = 0; return; }
     MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red);
+    bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     if (lane == 0) dels_out[env] = gym_extinguish(e, gy, type, n_dels, rnd + (size_t)env * (n_dels + 2));
+    unstage_scalars(e, sw);
 }
 
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
@@ -394,13 +415,14 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
     if (mask && !mask[env]) return;
     const int lane = threadIdx.x & 31;
     MP_SHARED_ENV();
-    bind_env_of(e, blocks, env, anim, red);
+    bind_env_of(e, blocks, env, anim, red, sw);
     __shared__ __align__(16) uint16_t s_ovl[MP_EPC][272];      // the tool overlay (256 values + mask) on chip
     if (lane == 0) e.ovl = s_ovl[threadIdx.x >> 5];
     __syncwarp();
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     if (lane == 0) gym_step_pre(e, gy, actions[env], static_build != 0);
+    unstage_scalars(e, sw);
 }
 
 // MicropolisEnv.step, part 3 (env.py:468-540): observation, metrics, reward, done
@@ -418,12 +440,13 @@ k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     (void)lane;
     if (mask && !mask[env]) return;
     MP_SHARED_ENV();
-    bind_env_of(e, blocks, env, anim, red);
+    bind_env_of(e, blocks, env, anim, red, sw);
     Gym gy;
     bind_gym(gy, shadow + (size_t)env * stride, &cfg);
     const size_t on = (size_t)gym_obs_channels(cfg) * cfg.W * cfg.H;
     if (is_reset) gym_reset_post(e, gy, obs + env * on, reward + env, done + env);
     else gym_step_post(e, gy, obs + env * on, reward + env, done + env);
+    unstage_scalars(e, sw);
 }
 
 __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
@@ -456,7 +479,6 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 
 const uint8_t *g_step_mask = NULL;  // device mask of the envs that take part in the current masked env-step
 int g_scan_block = 1;             // map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
-int g_pad_smem = 0;               // experiment: dynamic shared memory per CTA (limits CTAs per SM)
 unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
 // k_mp_frames with `epc` envs per CTA (1, 8 or 16); prof_off = frame offset of this simTick in the
 // per-frame profile rows (0 for the first simTick of an env-step, 100 for the second)
@@ -467,10 +489,10 @@ void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, co
     if (count_envs <= 0) return;
 #define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
                        gcount, g_scan_block, g_prof, prof_off, g_step_mask
-    if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 0, st>>>(MP_FRAMES_ARGS);
-    else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, g_pad_smem, st>>>(MP_FRAMES_ARGS);
-    else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 0, st>>>(MP_FRAMES_ARGS);
-    else k_mp_frames<1><<<count_envs, 32, 0, st>>>(MP_FRAMES_ARGS);
+    if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+    else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+    else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+    else k_mp_frames<1><<<count_envs, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
 #undef MP_FRAMES_ARGS
 }
 
@@ -580,10 +602,6 @@ mpb_handle mpb_create(int n_envs, int device)
         cudaFuncSetAttribute(k_mp_frames<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
     }
     if (const char *fp = getenv("MPB_SCAN_BLOCK")) g_scan_block = atoi(fp) != 0;
-    if (const char *fp = getenv("MPB_PAD_SMEM")) {
-        g_pad_smem = atoi(fp);
-        cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_pad_smem);
-    }
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
@@ -609,7 +627,7 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaEventCreate(&b->ev_start);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
-    k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS>>>(b->blocks, b->anim, n_envs);
+    k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, n_envs);
     if (cudaDeviceSynchronize() != cudaSuccess) { mpb_destroy(b); return NULL; }
     return b;
 }
@@ -717,7 +735,7 @@ int mpb_clear_map(mpb_handle h, const uint8_t *mask_host, void *stream)
     cudaSetDevice(b->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
-    k_mp_reset<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, NULL, NULL, mask_host ? b->mask : NULL, 0);
+    k_mp_reset<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, NULL, NULL, mask_host ? b->mask : NULL, 0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -735,7 +753,7 @@ int mpb_generate(mpb_handle h, const int32_t *terrain_seeds_host, const int32_t 
     memcpy(b->host_i32 + b->n_envs, sim_seeds_host, (size_t)b->n_envs * 4);
     CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
-    k_mp_reset<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->i32_a, b->i32_b,
+    k_mp_reset<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->i32_a, b->i32_b,
                                                 mask_host ? b->mask : NULL, 1);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -747,7 +765,7 @@ int mpb_tool(mpb_handle h, const int32_t *tool_xy_dev, int32_t *results_dev, voi
     MpBatch *b = (MpBatch *)h;
     if (!b || !tool_xy_dev) return -1;
     cudaSetDevice(b->device);
-    k_mp_tool<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, tool_xy_dev, results_dev);
+    k_mp_tool<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, tool_xy_dev, results_dev);
     CK(cudaGetLastError());
     return 0;
 }
@@ -808,7 +826,7 @@ int mpb_call(mpb_handle h, int fn, int a, int bb, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    k_mp_call<<<MP_GRID(b), MP_THREADS, 0, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, fn, a, bb);
+    k_mp_call<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, (cudaStream_t)stream>>>(b->blocks, b->anim, b->n_envs, fn, a, bb);
     CK(cudaGetLastError());
     return 0;
 }
@@ -965,7 +983,7 @@ int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools,
     CK(cudaMemset(b->done, 0, b->n_envs));
     b->configured = 1;
     // MicropolisControl.__init__ builds an empty TileMap (tilemap.py:185 setEmpty)
-    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                    NULL, NULL, NULL, 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
@@ -1007,7 +1025,7 @@ int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_
         CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
     }
-    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
+    k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
         b->cfg, b->i32_a, b->i32_b, mask_host ? b->mask : NULL, terrain);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -1021,7 +1039,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
     launch_control_sim_tick(b, st);
-    k_mp_env_post<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_post<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                     b->obs_out, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -1037,7 +1055,7 @@ int mpb_env_action(mpb_handle h, const int64_t *actions_host, int static_build, 
     cudaStream_t st = (cudaStream_t)stream;
     memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
     CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
-    k_mp_env_action<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_action<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                              b->act_dev, static_build, full_tools, b->i32_b);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st));
@@ -1076,7 +1094,7 @@ int mpb_env_track_ages(mpb_handle h, void *stream)
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     cudaStream_t st = (cudaStream_t)stream;
-    k_mp_env_track_ages<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg);
+    k_mp_env_track_ages<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -1094,7 +1112,7 @@ int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_ho
     CK(cudaMalloc(&rnd_dev, rb));
     CK(cudaMemcpyAsync(rnd_dev, rnd_host, rb, cudaMemcpyHostToDevice, st));
     if (upload_mask(b, mask_host, st)) { cudaFree(rnd_dev); return -1; }
-    k_mp_env_extinguish<<<MP_GRID(b), MP_THREADS, 0, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+    k_mp_env_extinguish<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                           type, n_dels, rnd_dev, mask_host ? b->mask : NULL, b->i32_b);
     cudaError_t le = cudaGetLastError();
     if (le == cudaSuccess) le = cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st);
@@ -1165,13 +1183,13 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         if (grid <= 0) continue;
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
         if (paint_dev)
-            k_mp_env_pre_paint<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
+            k_mp_env_pre_paint<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
                                                            b->cfg, paint_dev, perm, q.stride, q.off, q.count);
         else
-            k_mp_env_pre<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+            k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q.stride, q.off, q.count, g_step_mask);
         launch_control_sim_tick(b, gs, G, g);
-        k_mp_env_post<<<grid, MP_THREADS, 0, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+        k_mp_env_post<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                   b->obs_out, b->reward, b->done, 0, g_step_mask, perm, q.stride, q.off, q.count);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);

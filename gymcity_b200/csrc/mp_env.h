@@ -16,6 +16,10 @@ MPD void env_construct(Env &e, uint8_t *blk)
 {
     uint32_t *w = (uint32_t *)blk;
     for (int i = e.c.tid; i < EnvLayout::TOTAL / 4; i += e.c.n) w[i] = 0;
+    {   // the scalar block the caller works on (the device kernels stage it in shared memory)
+        uint32_t *sw = (uint32_t *)(Scalars *)e.s;
+        for (int i = e.c.tid; i < (int)(sizeof(Scalars) / 4); i += e.c.n) sw[i] = 0;
+    }
     e.c.sync();
     if (e.c.lead()) {
         S.cityTime = 50;
@@ -35,19 +39,19 @@ MPD void env_construct(Env &e, uint8_t *blk)
 MPD void init_will_stuff(Env &e)
 {
     if (e.c.lead()) {
-        MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) e.spr[i].frame = 0;   // destroyAllSprites
+        MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr()[i].next) e.spr()[i].frame = 0;   // destroyAllSprites
         S.roadEffect = MAX_ROAD_EFFECT; S.policeEffect = MAX_POLICE_EFFECT; S.fireEffect = MAX_FIRE_EFFECT;
         S.cityScore = 500; S.cityPop = -1;
         S.roadFund = 0; S.policeFund = 0; S.fireFund = 0;
         S.disasterEvent = 0; S.taxFlag = 0;
     }
     for (int i = e.c.tid; i < N2; i += e.c.n) {
-        e.pop[i] = 0; e.traffic[i] = 0; e.pollution[i] = 0; e.landval[i] = 0; e.crime[i] = 0;
+        e.pop()[i] = 0; e.traffic()[i] = 0; e.pollution()[i] = 0; e.landval()[i] = 0; e.crime()[i] = 0;
     }
-    for (int i = e.c.tid; i < N4; i += e.c.n) e.terrain[i] = 0;
+    for (int i = e.c.tid; i < N4; i += e.c.n) e.terrain()[i] = 0;
     for (int i = e.c.tid; i < N8; i += e.c.n) {
-        e.rog[i] = 0; e.comRate[i] = 0; e.policeSt[i] = 0; e.policeEff[i] = 0; e.fireSt[i] = 0;
-        e.fireEff[i] = 0;
+        e.rog()[i] = 0; e.comRate()[i] = 0; e.policeSt()[i] = 0; e.policeEff()[i] = 0; e.fireSt()[i] = 0;
+        e.fireEff()[i] = 0;
     }
     e.c.sync();
 }
@@ -55,8 +59,8 @@ MPD void init_will_stuff(Env &e)
 // [ALL] generate.cpp:165-174 clearMap
 MPD void clear_map(Env &e)
 {
-    for (int i = e.c.tid; i < NTILES; i += e.c.n) e.map[i] = T_DIRT;
-    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) { e.act[i] = 0; e.need[i] = 0; }
+    for (int i = e.c.tid; i < NTILES; i += e.c.n) e.map()[i] = T_DIRT;
+    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) { e.act()[i] = 0; e.need()[i] = 0; }
     e.c.sync();
 }
 
@@ -129,7 +133,7 @@ MPD void env_call(Env &e, int fn, int a, int b)
     case FN_SET_VALVES: if (lead) set_valves(e); break;
     case FN_CLEAR_CENSUS:
         if (lead) clear_census_scalars(e);
-        for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
+        for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt()[i] = 0; e.policeSt()[i] = 0; }
         break;
     case FN_TAKE10: take10_census(e); break;
     case FN_TAKE120: take120_census(e); break;
@@ -161,7 +165,7 @@ MPD void env_call(Env &e, int fn, int a, int b)
             MP_NOUNROLL for (int x = 0; x < WORLD_W - 1; x++) {
                 bool done = false;
                 MP_NOUNROLL for (int y = 0; y < WORLD_H - 1; y++)
-                    if ((e.map[tix(x, y)] & LOMASK) == T_NUCLEAR) { do_meltdown(e, x, y); done = true; break; }
+                    if ((e.map()[tix(x, y)] & LOMASK) == T_NUCLEAR) { do_meltdown(e, x, y); done = true; break; }
                 if (done) break;
             }
         break;

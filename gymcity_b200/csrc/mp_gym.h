@@ -128,7 +128,7 @@ MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
     const int wx = xc + CFG.xs, wy = yc + CFG.ys;
     bool slow = true;
     if (inb(wx, wy)) {
-        const int v = e.map[tix(wx, wy)], t = v & LOMASK;
+        const int v = e.map()[tix(wx, wy)], t = v & LOMASK;
         if (v == T_DIRT) {
             slow = false;
         } else if ((v & BULLBIT) && !(v & ZONEBIT) && t >= T_TREEBASE && t <= T_LASTRUBBLE && e.s->totalFunds >= 1) {
@@ -136,7 +136,7 @@ MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
             MP_NOUNROLL for (int k = 0; k < 4; k++) {
                 const int nx = wx + (k == 1) - (k == 3), ny = wy - (k == 0) + (k == 2);
                 if (!inb(nx, ny)) continue;
-                const int nt = e.map[tix(nx, ny)] & LOMASK;
+                const int nt = e.map()[tix(nx, ny)] & LOMASK;
                 near |= nt >= T_ROADBASE && nt < T_RESBASE;
             }
             if (!near) {
@@ -423,7 +423,7 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
         if (i2 < W / 2 && j2 < H / 2) {
             const int cx = j2 + CFG.xs / 2, cy = i2 + CFG.ys / 2;
             if (cx >= 0 && cx < W2 && cy >= 0 && cy < H2) {
-                const int dp = e.pop[cx * H2 + cy], dt = e.traffic[cx * H2 + cy];
+                const int dp = e.pop()[cx * H2 + cy], dt = e.traffic()[cx * H2 + cy];
                 vp = (float)dp;
                 vt = (float)dt;
                 if (!(i & 1) && !(j & 1)) tsum += dt;

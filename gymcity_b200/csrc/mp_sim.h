@@ -37,7 +37,7 @@ MPN void set_valves(Env &e)
     const float birthRate = 0.02f, laborBaseMax = 1.3f, internalMarketDenom = 3.7f;
     const float projectedIndPopMin = 5.0f, resRatioDefault = 1.3f;
     const float resRatioMax = 2, comRatioMax = 2, indRatioMax = 2, taxTableScale = 600;
-    int16_t *mh = e.miscHist;
+    int16_t *mh = e.miscHist();
     mh[1] = f2s(S.externalMarket);
     mh[2] = S.resPop; mh[3] = S.comPop; mh[4] = S.indPop;
     mh[5] = S.resValve; mh[6] = S.comValve; mh[7] = S.indValve;
@@ -49,14 +49,14 @@ MPN void set_valves(Env &e)
     S.totalPopLast = S.totalPop;
     S.totalPop = f2s(normalizedResPop + S.comPop + S.indPop);
     float employment;
-    if (S.resPop > 0) employment = (float)(e.comHist[1] + e.indHist[1]) / normalizedResPop;
+    if (S.resPop > 0) employment = (float)(e.comHist()[1] + e.indHist()[1]) / normalizedResPop;
     else employment = 1;
     float migration = normalizedResPop * (employment - 1);
     float births = normalizedResPop * birthRate;
     float projectedResPop = normalizedResPop + migration + births;
-    float temp = (float)(e.comHist[1] + e.indHist[1]);
+    float temp = (float)(e.comHist()[1] + e.indHist()[1]);
     float laborBase;
-    if (temp > 0.0f) laborBase = (float)e.resHist[1] / temp;
+    if (temp > 0.0f) laborBase = (float)e.resHist()[1] / temp;
     else laborBase = 1;
     laborBase = tclamp(laborBase, 0.0f, laborBaseMax);
     float internalMarket = (float)(normalizedResPop + S.comPop + S.indPop) / internalMarketDenom;
@@ -100,19 +100,19 @@ MPD void push_power_stack(Env &e, int x, int y)          // power.cpp:163-169
 {
     if (S.powerStackPointer < POWER_STACK_SIZE - 2) {
         S.powerStackPointer++;
-        e.pstack[S.powerStackPointer] = (uint16_t)tix(x, y);
+        e.pstack()[S.powerStackPointer] = (uint16_t)tix(x, y);
     }
 }
 
 // [LEAD] zone.cpp:419-437 setZonePower
 MPP bool set_zone_power(Env &e, int x, int y)
 {
-    int v = e.map[tix(x, y)], t = v & LOMASK;
+    int v = e.map()[tix(x, y)], t = v & LOMASK;
     if (t == T_NUCLEAR || t == T_POWERPLANT || pwr_get(e, x, y)) {
-        e.map[tix(x, y)] = (uint16_t)(v | PWRBIT);          // status bit only: activity unchanged
+        e.map()[tix(x, y)] = (uint16_t)(v | PWRBIT);          // status bit only: activity unchanged
         return true;
     }
-    e.map[tix(x, y)] = (uint16_t)(v & ~PWRBIT);
+    e.map()[tix(x, y)] = (uint16_t)(v & ~PWRBIT);
     return false;
 }
 
@@ -132,7 +132,7 @@ MPD bool find_perimeter_road(Env &e, int &x, int &y)
     const int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
     MP_NOUNROLL for (int z = 0; z < 12; z++) {
         int tx = x + px[z], ty = y + py[z];
-        if (inb(tx, ty) && road_test(e.map[tix(tx, ty)])) {
+        if (inb(tx, ty) && road_test(e.map()[tix(tx, ty)])) {
             x = tx; y = ty;
             return true;
         }
@@ -143,10 +143,10 @@ MPD bool find_perimeter_road(Env &e, int &x, int &y)
 MPD int tile_toward(const Env &e, int x, int y, int dir, int dflt)   // traffic.cpp:383-427
 {
     switch (dir) {
-    case D_N: return y > 0 ? (e.map[tix(x, y - 1)] & LOMASK) : dflt;
-    case D_E: return x < WORLD_W - 1 ? (e.map[tix(x + 1, y)] & LOMASK) : dflt;
-    case D_S: return y < WORLD_H - 1 ? (e.map[tix(x, y + 1)] & LOMASK) : dflt;
-    case D_W: return x > 0 ? (e.map[tix(x - 1, y)] & LOMASK) : dflt;
+    case D_N: return y > 0 ? (e.map()[tix(x, y - 1)] & LOMASK) : dflt;
+    case D_E: return x < WORLD_W - 1 ? (e.map()[tix(x + 1, y)] & LOMASK) : dflt;
+    case D_S: return y < WORLD_H - 1 ? (e.map()[tix(x, y + 1)] & LOMASK) : dflt;
+    case D_W: return x > 0 ? (e.map()[tix(x - 1, y)] & LOMASK) : dflt;
     default: return dflt;
     }
 }
@@ -179,10 +179,10 @@ MPD bool drive_done(const Env &e, int x, int y, int dest)
     const int lo[3] = { T_COMBASE, T_LHTHR, T_LHTHR };
     const int hi[3] = { T_NUCLEAR, T_PORT, T_COMBASE };
     int l = lo[dest], h = hi[dest], z;
-    if (y > 0) { z = e.map[tix(x, y - 1)] & LOMASK; if (z >= l && z <= h) return true; }
-    if (x < WORLD_W - 1) { z = e.map[tix(x + 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
-    if (y < WORLD_H - 1) { z = e.map[tix(x, y + 1)] & LOMASK; if (z >= l && z <= h) return true; }
-    if (x > 0) { z = e.map[tix(x - 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (y > 0) { z = e.map()[tix(x, y - 1)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (x < WORLD_W - 1) { z = e.map()[tix(x + 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (y < WORLD_H - 1) { z = e.map()[tix(x, y + 1)] & LOMASK; if (z >= l && z <= h) return true; }
+    if (x > 0) { z = e.map()[tix(x - 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
     return false;
 }
 
@@ -219,17 +219,17 @@ MPD void add_to_traffic_density(Env &e)
         int p = S.curMapStack[S.curMapStackPointer];
         S.curMapStackPointer--;
         int x = p / WORLD_H, y = p - x * WORLD_H;
-        int t = e.map[p] & LOMASK;
+        int t = e.map()[p] & LOMASK;
         if (t >= T_ROADBASE && t < T_POWERBASE) {
-            int traffic = b2get(e.traffic, x, y) + 50;
+            int traffic = b2get(e.traffic(), x, y) + 50;
             traffic = tmin(traffic, 240);
-            b2set(e.traffic, x, y, traffic);
+            b2set(e.traffic(), x, y, traffic);
             if (traffic >= 240 && rnd(e, 5) == 0) {
                 S.trafMaxX = (int16_t)x; S.trafMaxY = (int16_t)y;
                 int sp = get_sprite(e, SPR_HELICOPTER);
-                if (sp >= 0 && e.spr[sp].control == -1) {
-                    e.spr[sp].destX = (int16_t)(S.trafMaxX * 16);
-                    e.spr[sp].destY = (int16_t)(S.trafMaxY * 16);
+                if (sp >= 0 && e.spr()[sp].control == -1) {
+                    e.spr()[sp].destX = (int16_t)(S.trafMaxX * 16);
+                    e.spr()[sp].destY = (int16_t)(S.trafMaxY * 16);
                 }
             }
         }
@@ -253,15 +253,15 @@ MPN int make_traffic(Env &e, int x, int y, int dest)
 // ------------------------------------------------------------------ zones (zone.cpp)
 MPD void inc_rate_of_growth(Env &e, int x, int y, int amount)      // zone.cpp:300-306
 {
-    int v = s8get(e.rog, x, y);
+    int v = s8get(e.rog(), x, y);
     v = tclamp(v + amount * 4, -200, 200);
-    s8set(e.rog, x, y, v);
+    s8set(e.rog(), x, y, v);
 }
 
 MPN int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:271-293
 {
-    int16_t lv = (int16_t)b2get(e.landval, x, y);
-    lv = (int16_t)(lv - b2get(e.pollution, x, y));
+    int16_t lv = (int16_t)b2get(e.landval(), x, y);
+    lv = (int16_t)(lv - b2get(e.pollution(), x, y));
     if (lv < 30) return 0;
     if (lv < 80) return 1;
     if (lv < 150) return 2;
@@ -274,7 +274,7 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
     MP_NOUNROLL for (int z = 0; z < 9; z++) {
         int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
         if (inb(xx, yy)) {
-            int t = e.map[tix(xx, yy)] & LOMASK;
+            int t = e.map()[tix(xx, yy)] & LOMASK;
             if (t >= T_FLOOD && t < T_ROADBASE) return false;
         }
     }
@@ -284,7 +284,7 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
         base++;
     }
     set_zone_power(e, x, y);
-    mset(e, tix(x, y), e.map[tix(x, y)] | (ZONEBIT + BULLBIT));
+    mset(e, tix(x, y), e.map()[tix(x, y)] | (ZONEBIT + BULLBIT));
     return true;
 }
 
@@ -294,7 +294,7 @@ MPD int16_t do_free_pop(const Env &e, int x, int y)                // zone.cpp:3
     MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
         MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
             if (inb(xx, yy)) {
-                int t = e.map[tix(xx, yy)] & LOMASK;
+                int t = e.map()[tix(xx, yy)] & LOMASK;
                 if (t >= T_LHTHR && t <= T_HHTHR) count++;
             }
     return count;
@@ -307,12 +307,12 @@ MPD int16_t ind_zone_pop(int t) { return t == T_INDCLR ? (int16_t)0 : (int16_t)(
 MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:493-517
 {
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
-    int16_t z = (int16_t)(e.map[tix(x, y)] & LOMASK);
+    int16_t z = (int16_t)(e.map()[tix(x, y)] & LOMASK);
     if (z && (z < T_RESBASE || z > T_RESBASE + 8)) return -1;
     int16_t score = 1;
     MP_NOUNROLL for (z = 0; z < 4; z++) {
         int xx = x + dx[z], yy = y + dy[z];
-        if (inb(xx, yy) && e.map[tix(xx, yy)] != T_DIRT && (e.map[tix(xx, yy)] & LOMASK) <= T_LASTROAD)
+        if (inb(xx, yy) && e.map()[tix(xx, yy)] != T_DIRT && (e.map()[tix(xx, yy)] & LOMASK) <= T_LASTROAD)
             score++;
     }
     return score;
@@ -358,15 +358,15 @@ MPD void ind_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:1
 // [LEAD] zone.cpp:596-630 doResIn
 MPN void do_res_in(Env &e, int x, int y, int pop, int value)
 {
-    if (b2get(e.pollution, x, y) > 128) return;
-    int t = e.map[tix(x, y)] & LOMASK;
+    if (b2get(e.pollution(), x, y) > 128) return;
+    int t = e.map()[tix(x, y)] & LOMASK;
     if (t == T_FREEZ) {
         if (pop < 8) {
             build_house(e, x, y, value);
             inc_rate_of_growth(e, x, y, 1);
             return;
         }
-        if (b2get(e.pop, x, y) > 64) {
+        if (b2get(e.pop(), x, y) > 64) {
             res_plop(e, x, y, 0, value);
             inc_rate_of_growth(e, x, y, 8);
         }
@@ -393,7 +393,7 @@ MPN void do_res_out(Env &e, int x, int y, int pop, int value)
         mset(e, tix(x, y), (uint16_t)(T_FREEZ | BLBNCNBIT | ZONEBIT));
         MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
             MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
-                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) != T_FREEZ)
+                if (inb(xx, yy) && (e.map()[tix(xx, yy)] & LOMASK) != T_FREEZ)
                     mset(e, tix(xx, yy), (uint16_t)(T_LHTHR + value + rnd(e, 2) + BLBNCNBIT));
     }
     if (pop < 16) {
@@ -402,7 +402,7 @@ MPN void do_res_out(Env &e, int x, int y, int pop, int value)
         MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
             MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++) {
                 if (inb(xx, yy)) {
-                    int loc = e.map[tix(xx, yy)] & LOMASK;
+                    int loc = e.map()[tix(xx, yy)] & LOMASK;
                     if (loc >= T_LHTHR && loc <= T_HHTHR) {
                         mset(e, tix(xx, yy), (uint16_t)(brdr[z] + BLBNCNBIT + T_FREEZ - 4));
                         return;
@@ -432,8 +432,8 @@ MPN void make_hospital(Env &e, int x, int y)
 MPD int16_t eval_res(const Env &e, int x, int y, int traf)         // zone.cpp:757-777
 {
     if (traf < 0) return -3000;
-    int16_t v = (int16_t)b2get(e.landval, x, y);
-    v = (int16_t)(v - b2get(e.pollution, x, y));
+    int16_t v = (int16_t)b2get(e.landval(), x, y);
+    v = (int16_t)(v - b2get(e.pollution(), x, y));
     if (v < 0) v = 0;
     else v = (int16_t)tmin(v * 32, 6000);
     return (int16_t)(v - 3000);
@@ -443,7 +443,7 @@ MPD int16_t eval_res(const Env &e, int x, int y, int traf)         // zone.cpp:7
 MPN void do_residential(Env &e, int x, int y, bool zonePower)
 {
     S.resZonePop++;
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     int16_t tpop = (t == T_FREEZ) ? do_free_pop(e, x, y) : res_zone_pop(t);
     S.resPop = (int16_t)(S.resPop + tpop);
     int16_t trf = (tpop > rnd(e, 35)) ? (int16_t)make_traffic(e, x, y, 0) : (int16_t)1;
@@ -471,7 +471,7 @@ MPN void do_residential(Env &e, int x, int y, bool zonePower)
 // [LEAD] zone.cpp:786-888 doCommercial / doComIn / doComOut
 MPN void do_commercial(Env &e, int x, int y, bool zonePower)
 {
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     S.comZonePop++;
     int16_t tpop = com_zone_pop(t);
     S.comPop = (int16_t)(S.comPop + tpop);
@@ -483,12 +483,12 @@ MPN void do_commercial(Env &e, int x, int y, bool zonePower)
         return;
     }
     if (!(rnd16(e) & 7)) {
-        int16_t locvalve = (trf < 0) ? (int16_t)-3000 : (int16_t)s8get(e.comRate, x, y);
+        int16_t locvalve = (trf < 0) ? (int16_t)-3000 : (int16_t)s8get(e.comRate(), x, y);
         int16_t zscore = (int16_t)(S.comValve + locvalve);
         if (!zonePower) zscore = -500;
         if (trf && zscore > -350 && ((int16_t)(zscore - 26380) > (int16_t)rnd16s(e))) {
             int value = land_pollution_value(e, x, y);
-            int16_t z = (int16_t)(b2get(e.landval, x, y) >> 5);
+            int16_t z = (int16_t)(b2get(e.landval(), x, y) >> 5);
             if (tpop > z) return;
             if (tpop < 5) { com_plop(e, x, y, tpop, value); inc_rate_of_growth(e, x, y, 8); }
             return;
@@ -509,17 +509,17 @@ MPN void set_smoke(Env &e, int x, int y, bool zonePower)
     const int16_t aniTabB[8] = { 0, 0, 36, 44, 0, 0, 52, 60 };
     const int16_t aniTabC[8] = { T_IND1, 0, T_IND2, T_IND4, 0, 0, T_IND6, T_IND8 };
     const int16_t aniTabD[8] = { T_IND1, 0, T_IND3, T_IND5, 0, 0, T_IND7, T_IND9 };
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     if (t < T_IZB) return;
     int z = ((t - T_IZB) >> 3) & 7;
     if (!aniThis[z]) return;
     int xx = x + dx1[z], yy = y + dy1[z];
     if (!inb(xx, yy)) return;
     if (zonePower) {
-        if ((e.map[tix(xx, yy)] & LOMASK) == aniTabC[z])
+        if ((e.map()[tix(xx, yy)] & LOMASK) == aniTabC[z])
             mset(e, tix(xx, yy), (uint16_t)((ANIMBIT | CONDBIT | BURNBIT) | (T_SMOKEBASE + aniTabB[z])));
     } else {
-        if ((e.map[tix(xx, yy)] & LOMASK) > aniTabC[z])
+        if ((e.map()[tix(xx, yy)] & LOMASK) > aniTabC[z])
             mset(e, tix(xx, yy), (uint16_t)((CONDBIT | BURNBIT) | aniTabD[z]));
     }
 }
@@ -533,7 +533,7 @@ MPD void do_ind_out(Env &e, int x, int y, int pop, int value)      // zone.cpp:9
 // [LEAD] zone.cpp:916-957 doIndustrial
 MPN void do_industrial(Env &e, int x, int y, bool zonePower)
 {
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     S.indZonePop++;
     set_smoke(e, x, y, zonePower);
     int16_t tpop = ind_zone_pop(t);
@@ -568,7 +568,7 @@ MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
             int ax = x + xx, ay = y + yy;
             tile++;
             if (inb(ax, ay)) {
-                int mv = e.map[tix(ax, ay)];
+                int mv = e.map()[tix(ax, ay)];
                 if (mv & ZONEBIT) continue;
                 if (mv & ANIMBIT) continue;
                 int mt = mv & LOMASK;
@@ -580,7 +580,7 @@ MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
 // [LEAD] zone.cpp:127-180 doHospitalChurch
 MPN void do_hospital_church(Env &e, int x, int y)
 {
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     if (t == T_HOSPITAL) {
         S.hospitalPop++;
         if (!(S.cityTime & 15)) repair_zone(e, x, y, T_HOSPITAL, 3);
@@ -607,7 +607,7 @@ MPN void do_meltdown(Env &e, int x, int y)
         int xx = x - 20 + rnd(e, 40);
         int yy = y - 15 + rnd(e, 30);
         if (!inb(xx, yy)) continue;
-        int t = e.map[tix(xx, yy)];
+        int t = e.map()[tix(xx, yy)];
         if (t & ZONEBIT) continue;
         if ((t & BURNBIT) || t == T_DIRT) mset(e, tix(xx, yy), T_RADTILE);
     }
@@ -617,7 +617,7 @@ MPN void do_meltdown(Env &e, int x, int y)
 MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 {
     const int meltdownTable[3] = { 30000, 20000, 10000 };
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     switch (t) {
     case T_POWERPLANT: {
         S.coalPowerPop++;
@@ -647,7 +647,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
         if (!powerOn) z = z / 2;
         int px = x, py = y;
         if (!find_perimeter_road(e, px, py)) z = z / 2;
-        int16_t *m = fire ? e.fireSt : e.policeSt;
+        int16_t *m = fire ? e.fireSt() : e.policeSt();
         s8set(m, px, py, s8get(m, px, py) + z);
         return;
     }
@@ -658,7 +658,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
             int z = T_FULLSTADIUM - 5;
             MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
                 MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
-            mset(e, tix(x, y), e.map[tix(x, y)] | ZONEBIT | PWRBIT);
+            mset(e, tix(x, y), e.map()[tix(x, y)] | ZONEBIT | PWRBIT);
             tset(e, x + 1, y, T_FOOTBALLGAME1 + ANIMBIT);
             tset(e, x + 1, y + 1, T_FOOTBALLGAME2 + ANIMBIT);
         }
@@ -669,7 +669,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
             int z = T_STADIUM - 5;
             MP_NOUNROLL for (int yy = y - 1; yy < y + 3; yy++)
                 MP_NOUNROLL for (int xx = x - 1; xx < x + 3; xx++) { tset(e, xx, yy, z | BNCNBIT); z++; }
-            mset(e, tix(x, y), e.map[tix(x, y)] | ZONEBIT | PWRBIT);
+            mset(e, tix(x, y), e.map()[tix(x, y)] | ZONEBIT | PWRBIT);
         }
         return;
     case T_AIRPORT:
@@ -701,7 +701,7 @@ MPQ void do_zone(Env &e, int x, int y)
 {
     bool pw = set_zone_power(e, x, y);
     if (pw) S.poweredZoneCount++; else S.unpoweredZoneCount++;
-    int t = e.map[tix(x, y)] & LOMASK;
+    int t = e.map()[tix(x, y)] & LOMASK;
     if (t > T_PORTBASE && t < T_CHURCH1BASE) { do_special_zone(e, x, y, pw); return; }
     if (t < T_HOSPITAL) { do_residential(e, x, y, pw); return; }
     if (t < T_COMBASE || (t >= T_CHURCH1BASE && t <= T_CHURCH7LAST)) { do_hospital_church(e, x, y); return; }
@@ -713,14 +713,14 @@ MPQ void do_zone(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1336-1381 fireZone (also disasters.cpp doFlood)
 MPN void fire_zone(Env &e, int x, int y, int ch)
 {
-    int v = tclamp(s8get(e.rog, x, y) - 20, -200, 200);
-    s8set(e.rog, x, y, v);
+    int v = tclamp(s8get(e.rog(), x, y) - 20, -200, 200);
+    s8set(e.rog(), x, y, v);
     ch &= LOMASK;
     int xymax = ch < T_PORTBASE ? 2 : (ch == T_AIRPORT ? 5 : 4);
     MP_NOUNROLL for (int dx = -1; dx < xymax; dx++)
         MP_NOUNROLL for (int dy = -1; dy < xymax; dy++) {
             int xx = x + dx, yy = y + dy;
-            if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map[tix(xx, yy)] |= BULLBIT;
+            if (inb(xx, yy) && (e.map()[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map()[tix(xx, yy)] |= BULLBIT;
         }
 }
 
@@ -732,7 +732,7 @@ MPN void do_fire(Env &e, int x, int y)
         if ((rnd16(e) & 7) == 0) {
             int xx = x + dx[z], yy = y + dy[z];
             if (inb(xx, yy)) {
-                int c = e.map[tix(xx, yy)];
+                int c = e.map()[tix(xx, yy)];
                 if (!(c & BURNBIT)) continue;
                 if (c & ZONEBIT) {
                     fire_zone(e, xx, yy, c);
@@ -743,7 +743,7 @@ MPN void do_fire(Env &e, int x, int y)
         }
     }
     int16_t rate = 10;
-    int z = s8get(e.fireEff, x, y);
+    int z = s8get(e.fireEff(), x, y);
     if (z > 0) {
         rate = 3;
         if (z > 20) rate = 2;
@@ -761,7 +761,7 @@ MPN void do_flood(Env &e, int x, int y)
             if ((rnd16(e) & 7) == 0) {
                 int xx = x + dx[z], yy = y + dy[z];
                 if (inb(xx, yy)) {
-                    int c = e.map[tix(xx, yy)], t = c & LOMASK;
+                    int c = e.map()[tix(xx, yy)], t = c & LOMASK;
                     if ((c & BURNBIT) == BURNBIT || c == T_DIRT || (t >= T_WOODS5 && t < T_FLOOD)) {
                         if ((c & ZONEBIT) == ZONEBIT) fire_zone(e, xx, yy, c);
                         mset(e, tix(xx, yy), (uint16_t)(T_FLOOD + rnd(e, 2)));
@@ -792,7 +792,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
         if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
             MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + VDx[z], yy = y + VDy[z];
-                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (VBRTAB[z] & LOMASK))
+                if (inb(xx, yy) && (e.map()[tix(xx, yy)] & LOMASK) == (VBRTAB[z] & LOMASK))
                     mset(e, tix(xx, yy), (uint16_t)VBRTAB2[z]);
             }
         return true;
@@ -801,18 +801,18 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
         if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
             MP_NOUNROLL for (int z = 0; z < 7; z++) {
                 int xx = x + HDx[z], yy = y + HDy[z];
-                if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) == (HBRTAB[z] & LOMASK))
+                if (inb(xx, yy) && (e.map()[tix(xx, yy)] & LOMASK) == (HBRTAB[z] & LOMASK))
                     mset(e, tix(xx, yy), (uint16_t)HBRTAB2[z]);
             }
         return true;
     }
     if (boat_distance(e, x, y) < 300 || !(rnd16(e) & 7)) {
         if (tile & 1) {
-            if (x < WORLD_W - 1 && e.map[tix(x + 1, y)] == T_CHANNEL) {
+            if (x < WORLD_W - 1 && e.map()[tix(x + 1, y)] == T_CHANNEL) {
                 MP_NOUNROLL for (int z = 0; z < 7; z++) {
                     int xx = x + VDx[z], yy = y + VDy[z];
                     if (inb(xx, yy)) {
-                        int m = e.map[tix(xx, yy)];
+                        int m = e.map()[tix(xx, yy)];
                         if (m == T_CHANNEL || ((m & 15) == (VBRTAB2[z] & 15))) mset(e, tix(xx, yy), (uint16_t)VBRTAB[z]);
                     }
                 }
@@ -820,11 +820,11 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
             }
             return false;
         } else {
-            if (y > 0 && e.map[tix(x, y - 1)] == T_CHANNEL) {
+            if (y > 0 && e.map()[tix(x, y - 1)] == T_CHANNEL) {
                 MP_NOUNROLL for (int z = 0; z < 7; z++) {
                     int xx = x + HDx[z], yy = y + HDy[z];
                     if (inb(xx, yy)) {
-                        int m = e.map[tix(xx, yy)];
+                        int m = e.map()[tix(xx, yy)];
                         if (((m & 15) == (HBRTAB2[z] & 15)) || m == T_CHANNEL) mset(e, tix(xx, yy), (uint16_t)HBRTAB[z]);
                     }
                 }
@@ -841,7 +841,7 @@ MPQ void do_road(Env &e, int x, int y)
 {
     const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
     S.roadTotal++;
-    int mv = e.map[tix(x, y)], tile = mv & LOMASK;
+    int mv = e.map()[tix(x, y)], tile = mv & LOMASK;
     if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {
         if ((rnd16(e) & 511) == 0) {
             if (!(mv & CONDBIT)) {
@@ -861,7 +861,7 @@ MPQ void do_road(Env &e, int x, int y)
     if (tile < T_LTRFBASE) tden = 0;
     else if (tile < T_HTRFBASE) tden = 1;
     else { S.roadTotal++; tden = 2; }
-    int16_t td = (int16_t)(b2get(e.traffic, x, y) >> 6);
+    int16_t td = (int16_t)(b2get(e.traffic(), x, y) >> 6);
     if (td > 1) td--;
     if (tden != td) {
         int16_t z = (int16_t)(((tile - T_ROADBASE) & 15) + densityTable[td]);
@@ -878,7 +878,7 @@ MPQ void do_rail(Env &e, int x, int y)
     generate_train(e, x, y);
     if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {
         if (!(rnd16(e) & 511)) {
-            int cv = e.map[tix(x, y)];
+            int cv = e.map()[tix(x, y)];
             if (!(cv & CONDBIT)) {
                 if (S.roadEffect < (rnd16(e) & 31)) {
                     int t = cv & LOMASK;
@@ -895,7 +895,7 @@ MPQ void do_rail(Env &e, int x, int y)
 // [LEAD] simulate.cpp:929-997 body of mapScan for one tile
 MPP void scan_tile(Env &e, int idx)
 {
-    int mv = e.map[idx], tile = mv & LOMASK;
+    int mv = e.map()[idx], tile = mv & LOMASK;
     int x = idx / WORLD_H, y = idx - x * WORLD_H;
     if (tile < T_ROADBASE) {
         if (tile >= T_FIREBASE) {
@@ -931,7 +931,7 @@ MPP void scan_tile(Env &e, int idx)
     if (tile >= T_RAILBASE && tile < T_RESBASE) { do_rail(e, x, y); return; }
     if (tile >= T_SOMETINYEXP && tile <= T_LASTTINYEXP) { mset(e, idx, (uint16_t)random_rubble(e)); return; }
     // a building tile that is no centre: setZonePower above was all there is to do, and it is done
-    e.need[idx >> 5] &= ~(1u << (idx & 31));
+    e.need()[idx >> 5] &= ~(1u << (idx & 31));
 }
 
 // [ALL] mapScan(x1, x2).  The scan order is linear memory order (x outer, y inner over the
@@ -1018,7 +1018,7 @@ MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
     const int lane = e.c.tid;
     const bool mine = (mL >> lane) & 1u;
     const int t = wi * 32 + lane;
-    int v = mine ? e.map[t] : 0;
+    int v = mine ? e.map()[t] : 0;
     const int kind = mine ? tile_kind(e, v) : (int)TK_INERT;
     const unsigned serial = __ballot_sync(0xffffffffu, mine && kind == TK_SERIAL);
     int stop = serial ? __ffs(serial) - 1 : 32;             // batch = my tiles below `stop`
@@ -1043,7 +1043,7 @@ MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
                 if ((r & 7) == 0) {
                     const int xx = tx + (z == 1) - (z == 3), yy = ty - (z == 0) + (z == 2);
                     if (inb(xx, yy)) {
-                        const int c = e.map[tix(xx, yy)], ct = c & LOMASK;
+                        const int c = e.map()[tix(xx, yy)], ct = c & LOMASK;
                         if ((c & BURNBIT) == BURNBIT || c == T_DIRT || (ct >= T_WOODS5 && ct < T_FLOOD)) must_serial = true;
                     }
                 }
@@ -1060,30 +1060,30 @@ MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
         if (kind <= TK_ROAD) {
             if (S.newPower && (v & CONDBIT)) {              // setZonePower (zone.cpp:419-437)
                 const int id = v & LOMASK;
-                const bool on = id == T_NUCLEAR || id == T_POWERPLANT || ((e.power[t >> 5] >> (t & 31)) & 1u);
+                const bool on = id == T_NUCLEAR || id == T_POWERPLANT || ((e.power()[t >> 5] >> (t & 31)) & 1u);
                 const int nv = on ? (v | PWRBIT) : (v & ~PWRBIT);
-                if (nv != v) { v = nv; e.map[t] = (uint16_t)v; }
+                if (nv != v) { v = nv; e.map()[t] = (uint16_t)v; }
             }
             if (kind == TK_ROAD) {                          // doRoad (simulate.cpp:1048-1111)
                 const int tile = v & LOMASK;
                 int tden = tile < T_LTRFBASE ? 0 : (tile < T_HTRFBASE ? 1 : 2);
                 heavy = tden == 2;
                 const int tx = t / WORLD_H, ty = t - tx * WORLD_H;
-                int td = e.traffic[(tx >> 1) * H2 + (ty >> 1)] >> 6;
+                int td = e.traffic()[(tx >> 1) * H2 + (ty >> 1)] >> 6;
                 if (td > 1) td--;
                 if (tden != td) {
                     int z = ((tile - T_ROADBASE) & 15) + (td == 0 ? (int)T_ROADBASE : (td == 1 ? (int)T_LTRFBASE : (int)T_HTRFBASE));
                     z |= v & (ALLBITS - ANIMBIT);
                     if (td > 0) z |= ANIMBIT;
-                    e.map[t] = (uint16_t)z;
+                    e.map()[t] = (uint16_t)z;
                 }
             }
         } else if (kind == TK_FLOOD0) {                     // doFlood, floodCount == 0
-            if ((r & 15) == 0) { e.map[t] = T_DIRT; still = false; }
+            if ((r & 15) == 0) { e.map()[t] = T_DIRT; still = false; }
         } else if (kind == TK_RAD) {                        // doRadTile
-            if ((r & 4095) == 0) { e.map[t] = T_DIRT; still = false; }
+            if ((r & 4095) == 0) { e.map()[t] = T_DIRT; still = false; }
         } else if (kind == TK_TINYEXP) {                    // tiny explosion -> rubble
-            e.map[t] = (uint16_t)((T_RUBBLE + (r & 3)) | BULLBIT);
+            e.map()[t] = (uint16_t)((T_RUBBLE + (r & 3)) | BULLBIT);
             still = false;
         }                                                   // TK_FIRE (no spread): firePop++; TK_FLOODA: no-op
     }
@@ -1096,8 +1096,8 @@ MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
     const int total = __shfl_sync(0xffffffffu, pre + nd, 31);
     const int used = stop < 32 ? __shfl_sync(0xffffffffu, pre, stop) : total;
     if (lane == 0) {
-        if (gone) e.act[wi] &= ~gone;
-        if (gone | inert_done) e.need[wi] &= ~(gone | inert_done);
+        if (gone) e.act()[wi] &= ~gone;
+        if (gone | inert_done) e.need()[wi] &= ~(gone | inert_done);
         if (roads) S.roadTotal = (int16_t)(S.roadTotal + roads);
         if (fires) S.firePop = (int16_t)(S.firePop + fires);
         S.rng = lcg_jump(S.rng, used);
@@ -1117,7 +1117,7 @@ MPN void map_scan_dense(Env &e, int i0, int i1)
     MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
         const int w = wb + lane;
         for (;;) {
-            uint32_t m = (w <= w1) ? e.need[w] : 0u;
+            uint32_t m = (w <= w1) ? e.need()[w] : 0u;
             const int lo = pos - w * 32, hi = i1 - w * 32;
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
             if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
@@ -1150,7 +1150,7 @@ MPP void map_scan(Env &e, int x1, int x2)
         // window) ends the phase here; a dense range (flood / radiation / fire field) goes to the
         // batching scan
         const int wa = w0 + lane, wb2 = w0 + 32 + lane;
-        uint32_t a = (wa <= w1) ? e.need[wa] : 0u, b = (wb2 <= w1) ? e.need[wb2] : 0u;
+        uint32_t a = (wa <= w1) ? e.need()[wa] : 0u, b = (wb2 <= w1) ? e.need()[wb2] : 0u;
         if (wa == w0) a &= 0xffffffffu << (i0 & 31);
         if (wa == w1 && (i1 & 31)) a &= 0xffffffffu >> (32 - (i1 & 31));
         if (wb2 == w1 && (i1 & 31)) b &= 0xffffffffu >> (32 - (i1 & 31));
@@ -1166,7 +1166,7 @@ MPP void map_scan(Env &e, int x1, int x2)
     MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
         const int w = wb + lane;
         for (;;) {
-            uint32_t m = (w <= w1) ? e.need[w] : 0u;
+            uint32_t m = (w <= w1) ? e.need()[w] : 0u;
             // keep tiles in [pos, i1)
             const int lo = pos - w * 32, hi = i1 - w * 32;
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
@@ -1181,7 +1181,7 @@ MPP void map_scan(Env &e, int x1, int x2)
                 if (p < 0) p = 0;
                 for (;;) {
                     // re-read: the visit may have activated tiles ahead of the scan position
-                    const uint32_t mm = e.need[wi] & top & (0xffffffffu << p);
+                    const uint32_t mm = e.need()[wi] & top & (0xffffffffu << p);
                     if (!mm) break;
                     const int bit = __ffs(mm) - 1;
                     scan_tile(e, wi * 32 + bit);
@@ -1196,7 +1196,7 @@ MPP void map_scan(Env &e, int x1, int x2)
 #else
     for (int w = w0; w <= w1; w++) {
         for (;;) {
-            uint32_t m = e.need[w];
+            uint32_t m = e.need()[w];
             const int lo = pos - w * 32, hi = i1 - w * 32;
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
             if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
@@ -1217,7 +1217,7 @@ MPP void map_scan(Env &e, int x1, int x2)
 // on all six graphs at once (read everything, barrier, write).
 MPD void scroll_history(Env &e, int lo, int hi)
 {
-    int16_t *h[6] = { e.resHist, e.comHist, e.indHist, e.crimeHist, e.pollutionHist, e.moneyHist };
+    int16_t *h[6] = { e.resHist(), e.comHist(), e.indHist(), e.crimeHist(), e.pollutionHist(), e.moneyHist() };
     const int n = hi - lo + 1;                       // <= 119 entries per graph: 4 per lane
     int16_t v[6][4];
 #pragma unroll
@@ -1246,21 +1246,21 @@ MPN void take10_census(Env &e)
     scroll_history(e, 0, 118);
 #else
     for (int x = 118; x >= 0; x--) {
-        e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
-        e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
-        e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
+        e.resHist()[x + 1] = e.resHist()[x]; e.comHist()[x + 1] = e.comHist()[x];
+        e.indHist()[x + 1] = e.indHist()[x]; e.crimeHist()[x + 1] = e.crimeHist()[x];
+        e.pollutionHist()[x + 1] = e.pollutionHist()[x]; e.moneyHist()[x + 1] = e.moneyHist()[x];
     }
 #endif
     if (!e.c.lead()) return;
-    e.resHist[0] = (int16_t)(S.resPop / 8);
-    e.comHist[0] = S.comPop;
-    e.indHist[0] = S.indPop;
+    e.resHist()[0] = (int16_t)(S.resPop / 8);
+    e.comHist()[0] = S.comPop;
+    e.indHist()[0] = S.indPop;
     S.crimeRamp = (int16_t)(S.crimeRamp + (S.crimeAverage - S.crimeRamp) / 4);
-    e.crimeHist[0] = tmin(S.crimeRamp, (int16_t)255);
+    e.crimeHist()[0] = tmin(S.crimeRamp, (int16_t)255);
     S.pollutionRamp = (int16_t)(S.pollutionRamp + (S.pollutionAverage - S.pollutionRamp) / 4);
-    e.pollutionHist[0] = tmin(S.pollutionRamp, (int16_t)255);
+    e.pollutionHist()[0] = tmin(S.pollutionRamp, (int16_t)255);
     int16_t x = (int16_t)((S.cashFlow / 20) + 128);
-    e.moneyHist[0] = tclamp(x, (int16_t)0, (int16_t)255);
+    e.moneyHist()[0] = tclamp(x, (int16_t)0, (int16_t)255);
     int16_t resPopScaled = (int16_t)(S.resPop >> 8);
     if (S.hospitalPop < resPopScaled) S.needHospital = 1;
     if (S.hospitalPop > resPopScaled) S.needHospital = -1;
@@ -1278,18 +1278,18 @@ MPN void take120_census(Env &e)
     scroll_history(e, 120, 238);
 #else
     for (int x = 238; x >= 120; x--) {
-        e.resHist[x + 1] = e.resHist[x]; e.comHist[x + 1] = e.comHist[x];
-        e.indHist[x + 1] = e.indHist[x]; e.crimeHist[x + 1] = e.crimeHist[x];
-        e.pollutionHist[x + 1] = e.pollutionHist[x]; e.moneyHist[x + 1] = e.moneyHist[x];
+        e.resHist()[x + 1] = e.resHist()[x]; e.comHist()[x + 1] = e.comHist()[x];
+        e.indHist()[x + 1] = e.indHist()[x]; e.crimeHist()[x + 1] = e.crimeHist()[x];
+        e.pollutionHist()[x + 1] = e.pollutionHist()[x]; e.moneyHist()[x + 1] = e.moneyHist()[x];
     }
 #endif
     if (!e.c.lead()) return;
-    e.resHist[120] = (int16_t)(S.resPop / 8);
-    e.comHist[120] = S.comPop;
-    e.indHist[120] = S.indPop;
-    e.crimeHist[120] = e.crimeHist[0];
-    e.pollutionHist[120] = e.pollutionHist[0];
-    e.moneyHist[120] = e.moneyHist[0];
+    e.resHist()[120] = (int16_t)(S.resPop / 8);
+    e.comHist()[120] = S.comPop;
+    e.indHist()[120] = S.indPop;
+    e.crimeHist()[120] = e.crimeHist()[0];
+    e.pollutionHist()[120] = e.pollutionHist()[0];
+    e.moneyHist()[120] = e.moneyHist()[0];
 }
 
 // [LEAD] budget.cpp:107-316 doBudgetNow(false)
@@ -1386,7 +1386,7 @@ MPN void dec_traffic_map(Env &e)
 #if defined(__CUDA_ARCH__)
     // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit lane with byte-SIMD:
     // z - (z > 200 ? 34 : 24) saturated at 0 is exactly the reference's three-way rule.
-    uint4 *q = reinterpret_cast<uint4 *>(e.traffic);
+    uint4 *q = reinterpret_cast<uint4 *>(e.traffic());
     uint4 v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -1406,7 +1406,7 @@ MPN void dec_traffic_map(Env &e)
         }
     }
 #else
-    for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic[i] = dec_traffic_cell(e.traffic[i]);
+    for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic()[i] = dec_traffic_cell(e.traffic()[i]);
 #endif
 }
 
@@ -1414,10 +1414,10 @@ MPN void dec_traffic_map(Env &e)
 MPN void dec_rog_map(Env &e)
 {
     for (int i = e.c.tid; i < N8; i += e.c.n) {
-        int16_t z = e.rog[i];
+        int16_t z = e.rog()[i];
         if (z == 0) continue;
         if (z > 0) z--; else z++;
-        e.rog[i] = tclamp(z, (int16_t)-200, (int16_t)200);
+        e.rog()[i] = tclamp(z, (int16_t)-200, (int16_t)200);
     }
 }
 
@@ -1471,20 +1471,20 @@ MPN bool power_scan_walk(Env &e)
     const bool no_seeds = sp <= 0;                // nothing to walk from: the grid stays empty
     // index form of Position::move for the four cardinal directions (N, E, S, W)
     while (sp > 0) {
-        int p = e.pstack[sp];
+        int p = e.pstack()[sp];
         sp--;
         int step = 0, conNum;
         do {
             numPower++;
             if (numPower > maxPower) { S.powerStackPointer = sp; return false; }
             p += step;
-            e.power[p >> 5] |= 1u << (p & 31);
+            e.power()[p >> 5] |= 1u << (p & 31);
             const int x = p / WORLD_H, y = p - x * WORLD_H;
             conNum = 0;
 #define MP_PW_TRY(cond, off)                                                                          \
             if (conNum < 2 && (cond)) {                                                                   \
                 const int q = p + (off);                                                                  \
-                if ((e.map[q] & CONDBIT) && !((e.power[q >> 5] >> (q & 31)) & 1u)) { conNum++; step = (off); } \
+                if ((e.map()[q] & CONDBIT) && !((e.power()[q >> 5] >> (q & 31)) & 1u)) { conNum++; step = (off); } \
             }
             MP_PW_TRY(y > 0, -1)
             MP_PW_TRY(x < WORLD_W - 1, WORLD_H)
@@ -1493,7 +1493,7 @@ MPN bool power_scan_walk(Env &e)
 #undef MP_PW_TRY
             if (conNum > 1 && sp < POWER_STACK_SIZE - 2) {
                 sp++;
-                e.pstack[sp] = (uint16_t)p;
+                e.pstack()[sp] = (uint16_t)p;
             }
         } while (conNum);
     }
@@ -1514,14 +1514,14 @@ MPN bool power_scan_walk(Env &e)
 MPN bool power_scan_parallel(Env &e)
 {
     const int lane = e.c.tid;
-    uint32_t *C = reinterpret_cast<uint32_t *>(e.tmp1);
+    uint32_t *C = reinterpret_cast<uint32_t *>(e.tmp1());
     int T = 0, wlo = POWER_WORDS, whi = -1;
     MP_NOUNROLL for (int w = lane; w < POWER_WORDS; w += 32) {
-        uint32_t a = e.act[w], c = 0;
+        uint32_t a = e.act()[w], c = 0;
         while (a) {
             const int b = __ffs(a) - 1;
             a &= a - 1;
-            if (e.map[w * 32 + b] & CONDBIT) c |= 1u << b;
+            if (e.map()[w * 32 + b] & CONDBIT) c |= 1u << b;
         }
         C[w] = c;
         if (c) { T += __popc(c); wlo = min(wlo, w); whi = max(whi, w); }
@@ -1537,8 +1537,8 @@ MPN bool power_scan_parallel(Env &e)
     e.c.sync();
     if (lane == 0)
         MP_NOUNROLL for (int k = 1; k <= sp; k++) {
-            const int p = e.pstack[k];
-            e.power[p >> 5] |= 1u << (p & 31);
+            const int p = e.pstack()[k];
+            e.power()[p >> 5] |= 1u << (p & 31);
             wlo = min(wlo, p >> 5); whi = max(whi, p >> 5);
         }
     wlo = __shfl_sync(0xffffffffu, wlo, 0);
@@ -1549,14 +1549,14 @@ MPN bool power_scan_parallel(Env &e)
         MP_NOUNROLL for (int w = wlo + lane; w <= whi; w += 32) {
             const uint32_t c = C[w];
             if (!c) continue;
-            uint32_t p = e.power[w];
+            uint32_t p = e.power()[w];
             // column ends inside this word: bit b with (w * 32 + b) % 100 == 0 has no upper neighbour, == 99 no lower
             const int r = (w * 32) % WORLD_H;
             const int b0 = (WORLD_H - r) % WORLD_H, b99 = WORLD_H - 1 - r;
             const uint32_t y0 = b0 < 32 ? 1u << b0 : 0u, y99 = b99 < 32 ? 1u << b99 : 0u;
-            const uint32_t pm1 = w > 0 ? e.power[w - 1] : 0u, pp1 = w < POWER_WORDS - 1 ? e.power[w + 1] : 0u;
-            const uint32_t pm3 = w >= 3 ? e.power[w - 3] : 0u, pm4 = w >= 4 ? e.power[w - 4] : 0u;
-            const uint32_t pp3 = w + 3 < POWER_WORDS ? e.power[w + 3] : 0u, pp4 = w + 4 < POWER_WORDS ? e.power[w + 4] : 0u;
+            const uint32_t pm1 = w > 0 ? e.power()[w - 1] : 0u, pp1 = w < POWER_WORDS - 1 ? e.power()[w + 1] : 0u;
+            const uint32_t pm3 = w >= 3 ? e.power()[w - 3] : 0u, pm4 = w >= 4 ? e.power()[w - 4] : 0u;
+            const uint32_t pp3 = w + 3 < POWER_WORDS ? e.power()[w + 3] : 0u, pp4 = w + 4 < POWER_WORDS ? e.power()[w + 4] : 0u;
             uint32_t reach = ((((p << 1) | (pm1 >> 31)) & ~y0) | (((p >> 1) | (pp1 << 31)) & ~y99)
                               | (pm3 << 4) | (pm4 >> 28) | (pp3 >> 4) | (pp4 << 28));
             uint32_t add = reach & c & ~p;
@@ -1565,7 +1565,7 @@ MPN bool power_scan_parallel(Env &e)
                 add = (((p << 1) & ~y0) | ((p >> 1) & ~y99)) & c & ~p;
                 changed = true;
             }
-            e.power[w] = p;
+            e.power()[w] = p;
         }
         e.c.sync();
         if (!__any_sync(0xffffffffu, changed)) break;
@@ -1591,7 +1591,7 @@ MPN void do_power_scan(Env &e, bool set_new_power = true)
         e.c.sync();
         return;
     }
-    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power[i] = 0;
+    for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power()[i] = 0;
     e.c.sync();
     bool filled = false;
 #if defined(__CUDA_ARCH__)
@@ -1677,16 +1677,16 @@ MPD void box_reduce(Env &e, CellBox &b)
 // [ALL] scan.cpp:80-105 smoothStationMap (in place through a temporary copy)
 MPN void smooth_station(Env &e, int16_t *m)
 {
-    for (int i = e.c.tid; i < N8; i += e.c.n) e.stmp[i] = m[i];
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.stmp()[i] = m[i];
     e.c.sync();
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int x = i / H8, y = i - x * H8;
         int16_t edge = 0;
-        if (x > 0) edge = (int16_t)(edge + e.stmp[i - H8]);
-        if (x < W8 - 1) edge = (int16_t)(edge + e.stmp[i + H8]);
-        if (y > 0) edge = (int16_t)(edge + e.stmp[i - 1]);
-        if (y < H8 - 1) edge = (int16_t)(edge + e.stmp[i + 1]);
-        edge = (int16_t)(e.stmp[i] + edge / 4);
+        if (x > 0) edge = (int16_t)(edge + e.stmp()[i - H8]);
+        if (x < W8 - 1) edge = (int16_t)(edge + e.stmp()[i + H8]);
+        if (y > 0) edge = (int16_t)(edge + e.stmp()[i - 1]);
+        if (y < H8 - 1) edge = (int16_t)(edge + e.stmp()[i + 1]);
+        edge = (int16_t)(e.stmp()[i] + edge / 4);
         m[i] = (int16_t)(edge / 2);
     }
     e.c.sync();
@@ -1811,10 +1811,10 @@ MPN void ptlv_scan(Env &e)
         int bx = (i / H4) * 4, by = (i % H4) * 4, cnt = 0;
         MP_NOUNROLL for (int dx = 0; dx < 4; dx++)
             MP_NOUNROLL for (int dy = 0; dy < 4; dy++) {
-                int loc = e.map[tix(bx + dx, by + dy)] & LOMASK;
+                int loc = e.map()[tix(bx + dx, by + dy)] & LOMASK;
                 if (loc && loc < T_RUBBLE) cnt++;
             }
-        e.tmp3[i] = (uint8_t)(cnt * 15);
+        e.tmp3()[i] = (uint8_t)(cnt * 15);
     }
     e.c.sync();
     int lvtot = 0, lvnum = 0;
@@ -1827,11 +1827,11 @@ MPN void ptlv_scan(Env &e)
         // RADTILE, the flag needs ROADBASE), i.e. only tiles of the active bitmap; wy is even, so
         // the two tiles of a column are one aligned bit pair
         const int t0 = tix(wx, wy), t1 = t0 + WORLD_H;
-        const unsigned pair = ((e.act[t0 >> 5] >> (t0 & 31)) & 3u) | (((e.act[t1 >> 5] >> (t1 & 31)) & 3u) << 2);
+        const unsigned pair = ((e.act()[t0 >> 5] >> (t0 & 31)) & 3u) | (((e.act()[t1 >> 5] >> (t1 & 31)) & 3u) << 2);
         if (pair) {
             MP_NOUNROLL for (int mx = wx; mx <= wx + 1; mx++)
                 MP_NOUNROLL for (int my = wy; my <= wy + 1; my++) {
-                    int loc = e.map[tix(mx, my)] & LOMASK;
+                    int loc = e.map()[tix(mx, my)] & LOMASK;
                     if (loc) {
                         if (loc < T_RUBBLE) continue;
                         plevel += pollution_value(loc);
@@ -1840,20 +1840,20 @@ MPN void ptlv_scan(Env &e)
                 }
         }
         plevel = tmin(plevel, 255);
-        e.tmp1[i] = (uint8_t)plevel;
+        e.tmp1()[i] = (uint8_t)plevel;
         if (plevel) box_add(pbox, x, y);
         if (lvflag) {
             int dis = 34 - city_center_distance(e, wx, wy) / 2;
             dis = dis << 2;
-            dis += e.terrain[(x >> 1) * H4 + (y >> 1)];
-            dis -= e.pollution[i];
-            if (e.crime[i] > 190) dis -= 20;
+            dis += e.terrain()[(x >> 1) * H4 + (y >> 1)];
+            dis -= e.pollution()[i];
+            if (e.crime()[i] > 190) dis -= 20;
             dis = tclamp(dis, 1, 250);
-            e.landval[i] = (uint8_t)dis;
+            e.landval()[i] = (uint8_t)dis;
             lvtot += dis;
             lvnum++;
         } else {
-            e.landval[i] = 0;
+            e.landval()[i] = 0;
         }
     }
     coop_add(e, 0, lvtot);
@@ -1861,20 +1861,20 @@ MPN void ptlv_scan(Env &e)
     e.c.sync();
     if (e.c.lead()) S.landValueAverage = e.c.red[1] > 0 ? (int16_t)(e.c.red[0] / e.c.red[1]) : (int16_t)0;
     box_reduce(e, pbox);
-    smooth_byte2_box(e, e.tmp1, e.tmp2, pbox);
-    smooth_byte2_box(e, e.tmp2, e.tmp1, pbox);
+    smooth_byte2_box(e, e.tmp1(), e.tmp2(), pbox);
+    smooth_byte2_box(e, e.tmp2(), e.tmp1(), pbox);
     // pollution max: draws depend on the running maximum, so this is the serial lane
     {
-        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp1);
-        uint4 *o = reinterpret_cast<uint4 *>(e.pollution);
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp1());
+        uint4 *o = reinterpret_cast<uint4 *>(e.pollution());
         for (int i = e.c.tid; i < N2 / 16; i += e.c.n) o[i] = q[i];
-        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pollution[i] = e.tmp1[i];
+        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pollution()[i] = e.tmp1()[i];
     }
     e.c.sync();
     {
         int pnum, ptot;
         const int p_lo = pbox.x0 > pbox.x1 ? 0 : pbox.x0 * H2, p_hi = pbox.x0 > pbox.x1 ? 0 : (pbox.x1 + 1) * H2;
-        const int site = tie_max_scan(e, e.tmp1, nullptr, true, &pnum, &ptot, p_lo, p_hi);
+        const int site = tie_max_scan(e, e.tmp1(), nullptr, true, &pnum, &ptot, p_lo, p_hi);
         if (e.c.lead()) {
             if (site >= 0) {
                 S.pollutionMaxX = (int16_t)((site / H2) * 2);
@@ -1887,11 +1887,11 @@ MPN void ptlv_scan(Env &e)
     for (int i = e.c.tid; i < N4; i += e.c.n) {
         int x = i / H4, y = i - x * H4;
         unsigned z = 0;
-        if (x > 0) z += e.tmp3[i - H4];
-        if (x < W4 - 1) z += e.tmp3[i + H4];
-        if (y > 0) z += e.tmp3[i - 1];
-        if (y < H4 - 1) z += e.tmp3[i + 1];
-        e.terrain[i] = (uint8_t)((uint8_t)(z / 4 + e.tmp3[i]) / 2);
+        if (x > 0) z += e.tmp3()[i - H4];
+        if (x < W4 - 1) z += e.tmp3()[i + H4];
+        if (y > 0) z += e.tmp3()[i - 1];
+        if (y < H4 - 1) z += e.tmp3()[i + 1];
+        e.terrain()[i] = (uint8_t)((uint8_t)(z / 4 + e.tmp3()[i]) / 2);
     }
     e.c.sync();
 }
@@ -1899,15 +1899,15 @@ MPN void ptlv_scan(Env &e)
 // [ALL] scan.cpp:403-450 crimeScan
 MPN void crime_scan(Env &e)
 {
-    smooth_station(e, e.policeSt);
-    smooth_station(e, e.policeSt);
-    smooth_station(e, e.policeSt);
+    smooth_station(e, e.policeSt());
+    smooth_station(e, e.policeSt());
+    smooth_station(e, e.policeSt());
     // Only cells with land value have crime (everything else is zeroed), and land value exists only where
     // something is built: find the columns of the half-resolution map that hold any (128-bit loads, 16 cells
     // each), zero the two output maps, and visit only those columns.
     int c0 = W2, c1 = -1;
     {
-        const uint4 *q = reinterpret_cast<const uint4 *>(e.landval);
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.landval());
         for (int j = e.c.tid; j < (N2 + 15) / 16; j += e.c.n) {
             const uint4 v = q[j];
             uint32_t any = v.x | v.y | v.z | v.w;
@@ -1921,28 +1921,28 @@ MPN void crime_scan(Env &e)
         }
 #endif
     }
-    zero_byte2(e, e.crime);
-    zero_byte2(e, e.tmp2);
+    zero_byte2(e, e.crime());
+    zero_byte2(e, e.tmp2());
     e.c.sync();
     const int i_lo = c0 * H2, i_hi = (c1 + 1) * H2;                 // empty: i_lo > i_hi
     for (int i = i_lo + e.c.tid; i < i_hi; i += e.c.n) {
         int x = i / H2, y = i - x * H2;
-        int z = e.landval[i];
+        int z = e.landval()[i];
         if (z > 0) {
             z = 128 - z;
-            z += e.pop[i];
+            z += e.pop()[i];
             z = tmin(z, 300);
-            z -= e.policeSt[(x >> 2) * H8 + (y >> 2)];
+            z -= e.policeSt()[(x >> 2) * H8 + (y >> 2)];
             z = tclamp(z, 0, 250);
-            e.crime[i] = (uint8_t)z;
-            e.tmp2[i] = 1;
+            e.crime()[i] = (uint8_t)z;
+            e.tmp2()[i] = 1;
         }
     }
-    for (int i = e.c.tid; i < N8; i += e.c.n) e.policeEff[i] = e.policeSt[i];
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.policeEff()[i] = e.policeSt()[i];
     e.c.sync();
     {
         int numz, totz;
-        const int site = tie_max_scan(e, e.crime, e.tmp2, false, &numz, &totz, tmin(i_lo, i_hi), i_hi);
+        const int site = tie_max_scan(e, e.crime(), e.tmp2(), false, &numz, &totz, tmin(i_lo, i_hi), i_hi);
         if (e.c.lead()) {
             if (site >= 0) {
                 S.crimeMaxX = (int16_t)((site / H2) * 2);
@@ -1971,10 +1971,10 @@ MPN void pop_density_scan(Env &e)
     int xt = 0, yt = 0, zt = 0;
     CellBox box = { W2, -1, H2, -1 };
     // zone centres are active tiles: walk the active bitmap instead of all 12 000 tiles
-    zero_byte2(e, e.tmp1);
+    zero_byte2(e, e.tmp1());
     e.c.sync();
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = e.act[w];
+        uint32_t m = e.act()[w];
         while (m) {
             int b = 0;
 #if defined(__CUDA_ARCH__)
@@ -1983,7 +1983,7 @@ MPN void pop_density_scan(Env &e)
             while (!((m >> b) & 1u)) b++;
 #endif
             m &= m - 1;
-            const int idx = w * 32 + b, mv = e.map[idx];
+            const int idx = w * 32 + b, mv = e.map()[idx];
             if (!(mv & ZONEBIT)) continue;
             const int x = idx / WORLD_H, y = idx - x * WORLD_H;
             xt += x; yt += y; zt++;
@@ -1993,11 +1993,11 @@ MPN void pop_density_scan(Env &e)
             MP_NOUNROLL for (int dx = 0; dx < 2; dx++)
                 MP_NOUNROLL for (int dy = 0; dy < 2; dy++) {
                     const int o = tix(bx + dx, by + dy);
-                    if (o > idx && (e.map[o] & ZONEBIT)) later = true;
+                    if (o > idx && (e.map()[o] & ZONEBIT)) later = true;
                 }
             if (!later) {
                 int pop = population_density_of(e, x, y, mv & LOMASK) * 8;
-                e.tmp1[(x >> 1) * H2 + (y >> 1)] = (uint8_t)tmin(pop, 254);
+                e.tmp1()[(x >> 1) * H2 + (y >> 1)] = (uint8_t)tmin(pop, 254);
                 if (pop) box_add(box, x >> 1, y >> 1);
             }
         }
@@ -2007,19 +2007,19 @@ MPN void pop_density_scan(Env &e)
     coop_add(e, 2, zt);
     e.c.sync();
     box_reduce(e, box);
-    smooth_byte2_box(e, e.tmp1, e.tmp2, box);
-    smooth_byte2_box(e, e.tmp2, e.tmp1, box);
-    smooth_byte2_box(e, e.tmp1, e.tmp2, box);
+    smooth_byte2_box(e, e.tmp1(), e.tmp2(), box);
+    smooth_byte2_box(e, e.tmp2(), e.tmp1(), box);
+    smooth_byte2_box(e, e.tmp1(), e.tmp2(), box);
     {   // populationDensityMap = tempMap2 * 2 (Byte wrap), 16 cells per 128-bit word
-        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp2);
-        uint4 *o = reinterpret_cast<uint4 *>(e.pop);
+        const uint4 *q = reinterpret_cast<const uint4 *>(e.tmp2());
+        uint4 *o = reinterpret_cast<uint4 *>(e.pop());
         for (int i = e.c.tid; i < N2 / 16; i += e.c.n) {
             uint4 v = q[i];
             v.x = (v.x & 0x7f7f7f7fu) << 1; v.y = (v.y & 0x7f7f7f7fu) << 1;
             v.z = (v.z & 0x7f7f7f7fu) << 1; v.w = (v.w & 0x7f7f7f7fu) << 1;
             o[i] = v;
         }
-        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pop[i] = (uint8_t)(e.tmp2[i] * 2);
+        for (int i = (N2 / 16) * 16 + e.c.tid; i < N2; i += e.c.n) e.pop()[i] = (uint8_t)(e.tmp2()[i] * 2);
     }
     if (e.c.lead()) {
         if (e.c.red[2] > 0) {
@@ -2043,17 +2043,17 @@ MPN void com_rate_map(Env &e, int cx, int cy)
         int xd = x > cx ? x - cx : cx - x, yd = y > cy ? y - cy : cy - y;
         int16_t z = (int16_t)(tmin(xd + yd, 64) / 2);
         z = (int16_t)(z * 4);
-        e.comRate[i] = (int16_t)(64 - z);
+        e.comRate()[i] = (int16_t)(64 - z);
     }
 }
 
 // [ALL] scan.cpp:110-120 fireAnalysis
 MPN void fire_analysis(Env &e)
 {
-    smooth_station(e, e.fireSt);
-    smooth_station(e, e.fireSt);
-    smooth_station(e, e.fireSt);
-    for (int i = e.c.tid; i < N8; i += e.c.n) e.fireEff[i] = e.fireSt[i];
+    smooth_station(e, e.fireSt());
+    smooth_station(e, e.fireSt());
+    smooth_station(e, e.fireSt());
+    for (int i = e.c.tid; i < N8; i += e.c.n) e.fireEff()[i] = e.fireSt()[i];
     e.c.sync();
 }
 
@@ -2087,7 +2087,7 @@ MPN void city_evaluation(Env &e)
             int64_t tt = 0;
             int16_t count = 1;
             MP_NOUNROLL for (int i = 0; i < N2; i++)
-                if (e.landval[i] > 0) { tt += e.traffic[i]; count++; }
+                if (e.landval()[i] > 0) { tt += e.traffic()[i]; count++; }
             S.trafficAverage = d2s((double)(tt / count) * 2.4);
             pt[4] = S.trafficAverage;
         }
@@ -2202,7 +2202,7 @@ MPD void simulate_phase(Env &e, int phase)
             if (!(S.simCycle & 1)) set_valves(e);
             clear_census_scalars(e);
         }
-        for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
+        for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt()[i] = 0; e.policeSt()[i] = 0; }
         break;
     case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
         map_scan(e, (phase - 1) * WORLD_W / 8, phase * WORLD_W / 8);
@@ -2339,8 +2339,8 @@ MPD void do_sim_init(Env &e)
             S.powerStackPointer = 0;
         }
         for (int i = e.c.tid; i < 240; i += e.c.n) {
-            e.resHist[i] = 0; e.comHist[i] = 0; e.indHist[i] = 0;
-            e.moneyHist[i] = 128; e.crimeHist[i] = 0; e.pollutionHist[i] = 0;
+            e.resHist()[i] = 0; e.comHist()[i] = 0; e.indHist()[i] = 0;
+            e.moneyHist()[i] = 128; e.crimeHist()[i] = 0; e.pollutionHist()[i] = 0;
         }
         e.c.sync();
         do_power_scan(e);
@@ -2349,7 +2349,7 @@ MPD void do_sim_init(Env &e)
     }
     // initSimLoad == 1 (city loaded from file) is not reachable on the gym path
     if (e.c.lead()) { set_valves(e); clear_census_scalars(e); }
-    for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt[i] = 0; e.policeSt[i] = 0; }
+    for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt()[i] = 0; e.policeSt()[i] = 0; }
     e.c.sync();
     map_scan(e, 0, WORLD_W);
     do_power_scan(e);
@@ -2376,7 +2376,7 @@ MPD void do_sim_init(Env &e)
 MPN void animate_tiles(Env &e)
 {
     MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = e.act[w], nd = e.need[w];
+        uint32_t m = e.act()[w], nd = e.need()[w];
         while (m) {
             int b = 0;
 #if defined(__CUDA_ARCH__)
@@ -2386,14 +2386,14 @@ MPN void animate_tiles(Env &e)
 #endif
             m &= m - 1;
             const int i = w * 32 + b;
-            int v = e.map[i];
+            int v = e.map()[i];
             if (!(v & ANIMBIT)) continue;
             const int nv = e.anim[v & LOMASK] | (v & ALLBITS);
             if (nv == v) continue;
-            e.map[i] = (uint16_t)nv;
+            e.map()[i] = (uint16_t)nv;
             nd = tile_needs_visit(e, i, nv) ? (nd | (1u << b)) : (nd & ~(1u << b));
         }
-        e.need[w] = nd;
+        e.need()[w] = nd;
     }
     e.c.sync();
 }

@@ -10,26 +10,26 @@ namespace mp {
 inline void *snapshot_field_ptr(Env &e, int field, int *nbytes)
 {
     switch (field) {
-    case MPF_MAP: *nbytes = NTILES * 2; return e.map;
-    case MPF_POP_DENSITY: *nbytes = N2; return e.pop;
-    case MPF_TRAFFIC_DENSITY: *nbytes = N2; return e.traffic;
-    case MPF_POLLUTION_DENSITY: *nbytes = N2; return e.pollution;
-    case MPF_LAND_VALUE: *nbytes = N2; return e.landval;
-    case MPF_CRIME_RATE: *nbytes = N2; return e.crime;
-    case MPF_TERRAIN_DENSITY: *nbytes = N4; return e.terrain;
-    case MPF_RATE_OF_GROWTH: *nbytes = N8 * 2; return e.rog;
-    case MPF_FIRE_STATION: *nbytes = N8 * 2; return e.fireSt;
-    case MPF_FIRE_STATION_EFFECT: *nbytes = N8 * 2; return e.fireEff;
-    case MPF_POLICE_STATION: *nbytes = N8 * 2; return e.policeSt;
-    case MPF_POLICE_STATION_EFFECT: *nbytes = N8 * 2; return e.policeEff;
-    case MPF_COM_RATE: *nbytes = N8 * 2; return e.comRate;
-    case MPF_RES_HIST: *nbytes = 480; return e.resHist;
-    case MPF_COM_HIST: *nbytes = 480; return e.comHist;
-    case MPF_IND_HIST: *nbytes = 480; return e.indHist;
-    case MPF_MONEY_HIST: *nbytes = 480; return e.moneyHist;
-    case MPF_POLLUTION_HIST: *nbytes = 480; return e.pollutionHist;
-    case MPF_CRIME_HIST: *nbytes = 480; return e.crimeHist;
-    case MPF_MISC_HIST: *nbytes = 240; return e.miscHist;
+    case MPF_MAP: *nbytes = NTILES * 2; return e.map();
+    case MPF_POP_DENSITY: *nbytes = N2; return e.pop();
+    case MPF_TRAFFIC_DENSITY: *nbytes = N2; return e.traffic();
+    case MPF_POLLUTION_DENSITY: *nbytes = N2; return e.pollution();
+    case MPF_LAND_VALUE: *nbytes = N2; return e.landval();
+    case MPF_CRIME_RATE: *nbytes = N2; return e.crime();
+    case MPF_TERRAIN_DENSITY: *nbytes = N4; return e.terrain();
+    case MPF_RATE_OF_GROWTH: *nbytes = N8 * 2; return e.rog();
+    case MPF_FIRE_STATION: *nbytes = N8 * 2; return e.fireSt();
+    case MPF_FIRE_STATION_EFFECT: *nbytes = N8 * 2; return e.fireEff();
+    case MPF_POLICE_STATION: *nbytes = N8 * 2; return e.policeSt();
+    case MPF_POLICE_STATION_EFFECT: *nbytes = N8 * 2; return e.policeEff();
+    case MPF_COM_RATE: *nbytes = N8 * 2; return e.comRate();
+    case MPF_RES_HIST: *nbytes = 480; return e.resHist();
+    case MPF_COM_HIST: *nbytes = 480; return e.comHist();
+    case MPF_IND_HIST: *nbytes = 480; return e.indHist();
+    case MPF_MONEY_HIST: *nbytes = 480; return e.moneyHist();
+    case MPF_POLLUTION_HIST: *nbytes = 480; return e.pollutionHist();
+    case MPF_CRIME_HIST: *nbytes = 480; return e.crimeHist();
+    case MPF_MISC_HIST: *nbytes = 240; return e.miscHist();
     default: *nbytes = 0; return nullptr;
     }
 }
@@ -39,7 +39,7 @@ inline int snapshot_get_field(Env &e, int field, void *out, int cap)
     if (field == MPF_POWER_GRID) {
         if (cap < NTILES) return -1;
         uint8_t *o = (uint8_t *)out;
-        for (int i = 0; i < NTILES; i++) o[i] = (e.power[i >> 5] >> (i & 31)) & 1u;
+        for (int i = 0; i < NTILES; i++) o[i] = (e.power()[i >> 5] >> (i & 31)) & 1u;
         return NTILES;
     }
     e.s->powerQuiet = 0; e.s->powerPure = 0;
@@ -48,8 +48,8 @@ inline int snapshot_get_field(Env &e, int field, void *out, int cap)
         if (cap < n) return -1;
         int16_t *o = (int16_t *)out;
         for (int i = 0; i < POWER_STACK_SIZE; i++) {
-            o[2 * i] = (int16_t)(e.pstack[i] / WORLD_H);
-            o[2 * i + 1] = (int16_t)(e.pstack[i] % WORLD_H);
+            o[2 * i] = (int16_t)(e.pstack()[i] / WORLD_H);
+            o[2 * i + 1] = (int16_t)(e.pstack()[i] % WORLD_H);
         }
         return n;
     }
@@ -66,7 +66,7 @@ inline void snapshot_rebuild_bitmaps(Env &e)
     for (int w = 0; w < POWER_WORDS; w++) {
         uint32_t m = 0, nd = 0;
         for (int b = 0; b < 32; b++) {
-            const int idx = w * 32 + b, v = e.map[idx];
+            const int idx = w * 32 + b, v = e.map()[idx];
             if (!tile_is_active(v)) continue;
             m |= 1u << b;
             const int t = v & LOMASK;
@@ -76,14 +76,14 @@ inline void snapshot_rebuild_bitmaps(Env &e)
             if (inert) {
                 if (!(v & CONDBIT) || !e.s->newPower) need = false;
                 else {
-                    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power[idx >> 5] >> (idx & 31)) & 1u);
+                    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power()[idx >> 5] >> (idx & 31)) & 1u);
                     need = ((v & PWRBIT) != 0) != want;
                 }
             }
             if (need) nd |= 1u << b;
         }
-        e.act[w] = m;
-        e.need[w] = nd;
+        e.act()[w] = m;
+        e.need()[w] = nd;
     }
 }
 
@@ -92,15 +92,15 @@ inline int snapshot_set_field(Env &e, int field, const void *in, int nbytes)
     if (field == MPF_POWER_GRID) {
         if (nbytes != NTILES) return -1;
         const uint8_t *s = (const uint8_t *)in;
-        for (int i = 0; i < POWER_WORDS; i++) e.power[i] = 0;
-        for (int i = 0; i < NTILES; i++) if (s[i]) e.power[i >> 5] |= 1u << (i & 31);
+        for (int i = 0; i < POWER_WORDS; i++) e.power()[i] = 0;
+        for (int i = 0; i < NTILES; i++) if (s[i]) e.power()[i >> 5] |= 1u << (i & 31);
         snapshot_rebuild_bitmaps(e);
         return 0;
     }
     if (field == MPF_POWER_STACK) {
         const int16_t *s = (const int16_t *)in;
         for (int i = 0; i < POWER_STACK_SIZE && (i * 4 + 4) <= nbytes; i++)
-            e.pstack[i] = (uint16_t)(s[2 * i] * WORLD_H + s[2 * i + 1]);
+            e.pstack()[i] = (uint16_t)(s[2 * i] * WORLD_H + s[2 * i + 1]);
         return 0;
     }
     int n = 0;
@@ -145,7 +145,7 @@ inline void snapshot_get_scalars(Env &e, mp_scalars *o)
 #undef X
     o->nextRandom = (int64_t)s.rng;
     int cnt = 0;
-    for (int i = s.spriteHead; i >= 0; i = e.spr[i].next) cnt++;
+    for (int i = s.spriteHead; i >= 0; i = e.spr()[i].next) cnt++;
     o->numSprites = cnt;
     for (int i = 0; i < MP_PROBNUM; i++) o->problemVotes[i] = s.problemVotes[i];
     for (int i = 0; i < MP_PROBLEM_COMPLAINTS; i++) o->problemOrder[i] = s.problemOrder[i];
@@ -172,8 +172,8 @@ inline void snapshot_set_scalars(Env &e, const mp_scalars *o)
 inline int snapshot_get_sprites(Env &e, mp_sprite *out, int cap)
 {
     int n = 0;
-    for (int i = e.s->spriteHead; i >= 0 && n < cap; i = e.spr[i].next, n++) {
-        const Sprite &s = e.spr[i];
+    for (int i = e.s->spriteHead; i >= 0 && n < cap; i = e.spr()[i].next, n++) {
+        const Sprite &s = e.spr()[i];
         mp_sprite *o = &out[n];
         o->type = s.type; o->frame = s.frame; o->x = s.x; o->y = s.y; o->width = s.width;
         o->height = s.height; o->xOffset = s.xOffset; o->yOffset = s.yOffset; o->xHot = s.xHot;

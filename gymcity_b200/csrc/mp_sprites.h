@@ -15,14 +15,14 @@ namespace mp {
 MPD int get_sprite(Env &e, int type)                         // sprite.cpp:336-344
 {
     int i = S.globalSprites[type];
-    if (i < 0 || e.spr[i].frame == 0) return -1;
+    if (i < 0 || e.spr()[i].frame == 0) return -1;
     return i;
 }
 
 // [LEAD] sprite.cpp:125-296 initSprite
 MPN void init_sprite(Env &e, int si, int x, int y)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     sp.x = (int16_t)x; sp.y = (int16_t)y; sp.frame = 0;
     sp.origX = 0; sp.origY = 0; sp.destX = 0; sp.destY = 0; sp.count = 0; sp.soundCount = 0;
     sp.dir = 0; sp.newDir = 0; sp.step = 0; sp.flag = 0; sp.control = -1; sp.turn = 0;
@@ -91,12 +91,12 @@ MPN int new_sprite(Env &e, int type, int x, int y)
 {
     int si = -1;
     MP_NOUNROLL for (int i = 0; i < MAX_SPRITES; i++)
-        if (!e.spr[i].used) { si = i; break; }
+        if (!e.spr()[i].used) { si = i; break; }
     if (si < 0) { S.spriteOverflow = 1; return -1; }
-    e.spr[si].used = 1;
-    e.spr[si].type = (int16_t)type;
+    e.spr()[si].used = 1;
+    e.spr()[si].type = (int16_t)type;
     init_sprite(e, si, x, y);
-    e.spr[si].next = S.spriteHead;
+    e.spr()[si].next = S.spriteHead;
     S.spriteHead = (int16_t)si;
     return si;
 }
@@ -104,12 +104,12 @@ MPN int new_sprite(Env &e, int type, int x, int y)
 // [LEAD] sprite.cpp:303-329 destroySprite
 MPD void destroy_sprite(Env &e, int si)
 {
-    if (S.globalSprites[e.spr[si].type] == si) S.globalSprites[e.spr[si].type] = -1;
-    if (S.spriteHead == si) S.spriteHead = e.spr[si].next;
+    if (S.globalSprites[e.spr()[si].type] == si) S.globalSprites[e.spr()[si].type] = -1;
+    if (S.spriteHead == si) S.spriteHead = e.spr()[si].next;
     else
-        MP_NOUNROLL for (int p = S.spriteHead; p >= 0; p = e.spr[p].next)
-            if (e.spr[p].next == si) { e.spr[p].next = e.spr[si].next; break; }
-    e.spr[si].used = 0;
+        MP_NOUNROLL for (int p = S.spriteHead; p >= 0; p = e.spr()[p].next)
+            if (e.spr()[p].next == si) { e.spr()[p].next = e.spr()[si].next; break; }
+    e.spr()[si].used = 0;
 }
 
 // [LEAD] sprite.cpp:352-365 makeSprite
@@ -130,8 +130,8 @@ MPN void make_explosion(Env &e, int x, int y)                  // sprite.cpp:201
 MPD int boat_distance(Env &e, int x, int y)                    // simulate.cpp:1253-1273
 {
     int dist = 99999, mx = x * 16 + 8, my = y * 16 + 8;
-    MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr[i].next) {
-        const Sprite &sp = e.spr[i];
+    MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr()[i].next) {
+        const Sprite &sp = e.spr()[i];
         if (sp.type == SPR_SHIP && sp.frame != 0) {
             int d = iabs(sp.x + sp.xHot - mx) + iabs(sp.y + sp.yHot - my);
             dist = tmin(dist, d);
@@ -144,7 +144,7 @@ MPD int16_t get_char(const Env &e, int x, int y)               // sprite.cpp:376
 {
     x >>= 4; y >>= 4;
     if (!inb(x, y)) return -1;
-    return (int16_t)(e.map[tix(x, y)] & LOMASK);
+    return (int16_t)(e.map()[tix(x, y)] & LOMASK);
 }
 
 MPD int16_t turn_to(int p, int d)                              // sprite.cpp:395-423
@@ -194,7 +194,7 @@ MPD bool sprite_collision(const Sprite &a, const Sprite &b)    // sprite.cpp:536
 
 MPD void explode_sprite(Env &e, int si)                        // sprite.cpp:1649-1688
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     sp.frame = 0;
     make_explosion_at(e, sp.x + sp.xHot, sp.y + sp.yHot);
 }
@@ -202,14 +202,14 @@ MPD void explode_sprite(Env &e, int si)                        // sprite.cpp:164
 // [LEAD] sprite.cpp:1752-1786 startFireInZone
 MPD void start_fire_in_zone(Env &e, int x, int y, int ch)
 {
-    int v = tclamp(s8get(e.rog, x, y) - 20, -200, 200);
-    s8set(e.rog, x, y, v);
+    int v = tclamp(s8get(e.rog(), x, y) - 20, -200, 200);
+    s8set(e.rog(), x, y, v);
     ch &= LOMASK;
     int xymax = ch < T_PORTBASE ? 2 : (ch == T_AIRPORT ? 5 : 4);
     MP_NOUNROLL for (int dx = -1; dx < xymax; dx++)
         MP_NOUNROLL for (int dy = -1; dy < xymax; dy++) {
             int xx = x + dx, yy = y + dy;
-            if (inb(xx, yy) && (e.map[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map[tix(xx, yy)] |= BULLBIT;
+            if (inb(xx, yy) && (e.map()[tix(xx, yy)] & LOMASK) >= T_ROADBASE) e.map()[tix(xx, yy)] |= BULLBIT;
         }
 }
 
@@ -218,7 +218,7 @@ MPN void destroy_map_tile(Env &e, int ox, int oy)
 {
     int x = (int16_t)(ox >> 4), y = (int16_t)(oy >> 4);
     if (!inb(x, y)) return;
-    int16_t z = (int16_t)e.map[tix(x, y)];
+    int16_t z = (int16_t)e.map()[tix(x, y)];
     int16_t t = z & LOMASK;
     if (t >= T_TREEBASE) {
         if (!(z & BURNBIT)) {
@@ -240,7 +240,7 @@ MPD void start_fire(Env &e, int x, int y)
 {
     x >>= 4; y >>= 4;
     if (!inb(x, y)) return;
-    int z = e.map[tix(x, y)], t = z & LOMASK;
+    int z = e.map()[tix(x, y)], t = z & LOMASK;
     if (!(z & BURNBIT) && t != T_DIRT) return;
     if (z & ZONEBIT) return;
     mset(e, tix(x, y), (uint16_t)random_fire(e));
@@ -250,7 +250,7 @@ MPD void start_fire(Env &e, int x, int y)
 // [LEAD] sprite.cpp:608-673 doTrainSprite
 MPN void do_train(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     const int16_t Cx[4] = { 0, 16, 0, -16 }, Cy[4] = { -16, 0, 16, 0 };
     const int16_t Dx[5] = { 0, 4, 0, -4, 0 }, Dy[5] = { -4, 0, 4, 0, 0 };
     const int16_t pic2[5] = { 1, 2, 1, 2, 5 };
@@ -279,7 +279,7 @@ MPN void do_train(Env &e, int si)
 // [LEAD] sprite.cpp:680-770 doCopterSprite
 MPN void do_copter(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     const int16_t CDx[9] = { 0, 0, 3, 5, 3, 0, -3, -5, -3 }, CDy[9] = { 0, -5, -3, 0, 3, 5, 3, 0, -3 };
     if (sp.soundCount > 0) sp.soundCount--;
     if (sp.control < 0) {
@@ -287,7 +287,7 @@ MPN void do_copter(Env &e, int si)
         if (sp.count == 0) {
             int s2 = get_sprite(e, SPR_MONSTER);
             if (s2 < 0) s2 = get_sprite(e, SPR_TORNADO);
-            if (s2 >= 0) { sp.destX = e.spr[s2].x; sp.destY = e.spr[s2].y; }
+            if (s2 >= 0) { sp.destX = e.spr()[s2].x; sp.destY = e.spr()[s2].y; }
             else { sp.destX = sp.origX; sp.destY = sp.origY; }
             get_dir(e, sp.x, sp.y, sp.origX, sp.origY);
             if (S.absDist < 30) { sp.frame = 0; return; }
@@ -299,7 +299,7 @@ MPN void do_copter(Env &e, int si)
     if (sp.soundCount == 0) {
         int16_t x = (int16_t)((sp.x + 48) / 16), y = (int16_t)(sp.y / 16);
         if (x >= 0 && x < WORLD_W && y >= 0 && y < WORLD_H)
-            if (b2get(e.traffic, x, y) > 170 && (rnd16(e) & 7) == 0) sp.soundCount = 200;
+            if (b2get(e.traffic(), x, y) > 170 && (rnd16(e) & 7) == 0) sp.soundCount = 200;
     }
     int16_t z = sp.frame;
     if ((S.spriteCycle & 3) == 0) {
@@ -316,43 +316,43 @@ MPN void do_airplane(Env &e, int si)
 {
     const int16_t CDx[12] = { 0, 0, 6, 8, 6, 0, -6, -8, -6, 8, 8, 8 };
     const int16_t CDy[12] = { 0, -8, -6, 0, 6, 8, 6, 0, -6, 0, 0, 0 };
-    int16_t z = e.spr[si].frame;
+    int16_t z = e.spr()[si].frame;
     if ((S.spriteCycle % 5) == 0) {
         if (z > 8) {
             z--;
             if (z < 9) z = 3;
-            e.spr[si].frame = z;
+            e.spr()[si].frame = z;
         } else {
-            int16_t d = get_dir(e, e.spr[si].x, e.spr[si].y, e.spr[si].destX, e.spr[si].destY);
+            int16_t d = get_dir(e, e.spr()[si].x, e.spr()[si].y, e.spr()[si].destX, e.spr()[si].destY);
             z = turn_to(z, d);
-            e.spr[si].frame = z;
+            e.spr()[si].frame = z;
         }
     }
     if (S.absDist < 50) {
-        e.spr[si].destX = (int16_t)(rnd(e, (WORLD_W * 16) + 100) - 50);
-        e.spr[si].destY = (int16_t)(rnd(e, (WORLD_H * 16) + 100) - 50);
+        e.spr()[si].destX = (int16_t)(rnd(e, (WORLD_W * 16) + 100) - 50);
+        e.spr()[si].destY = (int16_t)(rnd(e, (WORLD_H * 16) + 100) - 50);
     }
     if (S.enableDisasters) {
         bool explode = false;
-        MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
-            if (e.spr[s].frame == 0 || s == si) continue;
-            if ((e.spr[s].type == SPR_HELICOPTER || e.spr[s].type == SPR_AIRPLANE)
-                && sprite_collision(e.spr[si], e.spr[s])) {
+        MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr()[s].next) {
+            if (e.spr()[s].frame == 0 || s == si) continue;
+            if ((e.spr()[s].type == SPR_HELICOPTER || e.spr()[s].type == SPR_AIRPLANE)
+                && sprite_collision(e.spr()[si], e.spr()[s])) {
                 explode_sprite(e, s);
                 explode = true;
             }
         }
         if (explode) explode_sprite(e, si);
     }
-    e.spr[si].x = (int16_t)(e.spr[si].x + CDx[z]);
-    e.spr[si].y = (int16_t)(e.spr[si].y + CDy[z]);
-    if (sprite_not_in_bounds(e.spr[si])) e.spr[si].frame = 0;
+    e.spr()[si].x = (int16_t)(e.spr()[si].x + CDx[z]);
+    e.spr()[si].y = (int16_t)(e.spr()[si].y + CDy[z]);
+    if (sprite_not_in_bounds(e.spr()[si])) e.spr()[si].frame = 0;
 }
 
 // [LEAD] sprite.cpp:857-984 doShipSprite
 MPN void do_ship(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     const int16_t BDx[9] = { 0, 0, 1, 1, 1, 0, -1, -1, -1 }, BDy[9] = { 0, -1, -1, 0, 1, 1, 1, 0, -1 };
     const int16_t BPx[9] = { 0, 0, 2, 2, 2, 0, -2, -2, -2 }, BPy[9] = { 0, -2, -2, 0, 2, 2, 2, 0, -2 };
     const int16_t clr[8] = { T_RIVER, T_CHANNEL, T_POWERBASE, T_POWERBASE + 1, T_RAILBASE, T_RAILBASE + 1,
@@ -379,7 +379,7 @@ MPN void do_ship(Env &e, int si)
             x = (int16_t)(((sp.x + (48 - 1)) >> 4) + BDx[z]);
             y = (int16_t)((sp.y >> 4) + BDy[z]);
             if (inb(x, y)) {
-                t = (int16_t)(e.map[tix(x, y)] & LOMASK);
+                t = (int16_t)(e.map()[tix(x, y)] & LOMASK);
                 if (t == T_CHANNEL || t == T_BRWH || t == T_BRWV || try_other(t, sp.dir, z)) {
                     sp.newDir = z;
                     sp.frame = turn_to(sp.frame, sp.newDir);
@@ -405,18 +405,18 @@ MPN void do_ship(Env &e, int si)
         if (t == clr[z]) break;
         if (z == 7) {
             explode_sprite(e, si);
-            destroy_map_tile(e, e.spr[si].x + 48, e.spr[si].y);
+            destroy_map_tile(e, e.spr()[si].x + 48, e.spr()[si].y);
         }
     }
 }
 
 MPD void hit_vehicles(Env &e, int si)                          // shared by monster and tornado
 {
-    MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr[s].next) {
-        int ty = e.spr[s].type;
-        if (e.spr[s].frame != 0
+    MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr()[s].next) {
+        int ty = e.spr()[s].type;
+        if (e.spr()[s].frame != 0
             && (ty == SPR_AIRPLANE || ty == SPR_HELICOPTER || ty == SPR_SHIP || ty == SPR_TRAIN)
-            && sprite_collision(e.spr[si], e.spr[s]))
+            && sprite_collision(e.spr()[si], e.spr()[s]))
             explode_sprite(e, s);
     }
 }
@@ -424,7 +424,7 @@ MPD void hit_vehicles(Env &e, int si)                          // shared by mons
 // [LEAD] sprite.cpp:997-1181 doMonsterSprite
 MPN void do_monster(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     const int16_t Gx[5] = { 2, 2, -2, -2, 0 }, Gy[5] = { -2, 2, 2, -2, 0 };
     const int16_t ND1[4] = { 0, 1, 2, 3 }, ND2[4] = { 1, 2, 3, 0 };
     const int16_t nn1[4] = { 2, 5, 8, 11 }, nn2[4] = { 11, 2, 5, 8 };
@@ -505,13 +505,13 @@ MPN void do_monster(Env &e, int si)
     c = get_char(e, sp.x + sp.xHot, sp.y + sp.yHot);
     if (c == -1 || (c == T_RIVER && sp.count != 0 && sp.control == -1)) sp.frame = 0;
     hit_vehicles(e, si);
-    destroy_map_tile(e, e.spr[si].x + 48, e.spr[si].y + 16);
+    destroy_map_tile(e, e.spr()[si].x + 48, e.spr()[si].y + 16);
 }
 
 // [LEAD] sprite.cpp:1188-1248 doTornadoSprite
 MPN void do_tornado(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     const int16_t CDx[9] = { 2, 3, 2, 0, -2, -3, 0, 0, 0 }, CDy[9] = { -2, 0, 2, 3, 2, 0, 0, 0, 0 };
     int16_t z = sp.frame;
     if (z == 2) z = sp.flag ? 3 : 1;
@@ -523,7 +523,7 @@ MPN void do_tornado(Env &e, int si)
     sp.frame = z;
     hit_vehicles(e, si);
     z = rnd(e, 5);
-    Sprite &sq = e.spr[si];
+    Sprite &sq = e.spr()[si];
     sq.x = (int16_t)(sq.x + CDx[z]);
     sq.y = (int16_t)(sq.y + CDy[z]);
     if (sprite_not_in_bounds(sq)) sq.frame = 0;
@@ -534,7 +534,7 @@ MPN void do_tornado(Env &e, int si)
 // [LEAD] sprite.cpp:1255-1288 doExplosionSprite
 MPN void do_explosion(Env &e, int si)
 {
-    Sprite &sp = e.spr[si];
+    Sprite &sp = e.spr()[si];
     if ((S.spriteCycle & 1) == 0) sp.frame++;
     if (sp.frame > 6) {
         sp.frame = 0;
@@ -554,8 +554,8 @@ MPN void move_objects(Env &e)
     if (!S.simSpeed) return;
     S.spriteCycle++;
     MP_NOUNROLL for (int si = S.spriteHead; si >= 0;) {
-        if (e.spr[si].frame > 0) {
-            switch (e.spr[si].type) {
+        if (e.spr()[si].frame > 0) {
+            switch (e.spr()[si].type) {
             case SPR_TRAIN: do_train(e, si); break;
             case SPR_HELICOPTER: do_copter(e, si); break;
             case SPR_AIRPLANE: do_airplane(e, si); break;
@@ -565,10 +565,10 @@ MPN void move_objects(Env &e)
             case SPR_EXPLOSION: do_explosion(e, si); break;
             default: break;
             }
-            si = e.spr[si].next;
+            si = e.spr()[si].next;
         } else {
             int s = si;
-            si = e.spr[si].next;
+            si = e.spr()[si].next;
             destroy_sprite(e, s);
         }
     }
@@ -585,19 +585,19 @@ MPN void generate_ship(Env &e)                                 // sprite.cpp:185
 {
     if (!(rnd16(e) & 3))
         MP_NOUNROLL for (int x = 4; x < WORLD_W - 2; x++)
-            if (e.map[tix(x, 0)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, (x << 4) - 47, 0); return; }
+            if (e.map()[tix(x, 0)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, (x << 4) - 47, 0); return; }
     if (!(rnd16(e) & 3))
         MP_NOUNROLL for (int y = 1; y < WORLD_H - 2; y++)
-            if (e.map[tix(0, y)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, -47, y << 4); return; }
+            if (e.map()[tix(0, y)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, -47, y << 4); return; }
     if (!(rnd16(e) & 3))
         MP_NOUNROLL for (int x = 4; x < WORLD_W - 2; x++)
-            if (e.map[tix(x, WORLD_H - 1)] == T_CHANNEL) {
+            if (e.map()[tix(x, WORLD_H - 1)] == T_CHANNEL) {
                 make_sprite(e, SPR_SHIP, (x << 4) - 47, (WORLD_H - 1) << 4);
                 return;
             }
     if (!(rnd16(e) & 3))
         MP_NOUNROLL for (int y = 1; y < WORLD_H - 2; y++)
-            if (e.map[tix(WORLD_W - 1, y)] == T_CHANNEL) {
+            if (e.map()[tix(WORLD_W - 1, y)] == T_CHANNEL) {
                 make_sprite(e, SPR_SHIP, ((WORLD_W - 1) << 4) - 47, y << 4);
                 return;
             }
@@ -620,14 +620,14 @@ MPN void make_monster(Env &e)
 {
     int si = get_sprite(e, SPR_MONSTER);
     if (si >= 0) {
-        e.spr[si].soundCount = 1; e.spr[si].count = 1000;
-        e.spr[si].destX = (int16_t)(S.pollutionMaxX << 4);
-        e.spr[si].destY = (int16_t)(S.pollutionMaxY << 4);
+        e.spr()[si].soundCount = 1; e.spr()[si].count = 1000;
+        e.spr()[si].destX = (int16_t)(S.pollutionMaxX << 4);
+        e.spr()[si].destY = (int16_t)(S.pollutionMaxY << 4);
         return;
     }
     MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 20) + 10, y = rnd(e, WORLD_H - 10) + 5;
-        int v = e.map[tix(x, y)];
+        int v = e.map()[tix(x, y)];
         if (v == T_RIVER || v == T_RIVER + BULLBIT) {
             make_sprite(e, SPR_MONSTER, (x << 4) + 48, y << 4);
             return;
@@ -640,7 +640,7 @@ MPN void make_monster(Env &e)
 MPN void make_tornado(Env &e)
 {
     int si = get_sprite(e, SPR_TORNADO);
-    if (si >= 0) { e.spr[si].count = 200; return; }
+    if (si >= 0) { e.spr()[si].count = 200; return; }
     int16_t x = (int16_t)(rnd(e, (WORLD_W << 4) - 800) + 400);
     int16_t y = (int16_t)(rnd(e, (WORLD_H << 4) - 200) + 100);
     make_sprite(e, SPR_TORNADO, x, y);
@@ -659,7 +659,7 @@ MPN void make_earthquake(Env &e)
     int strength = rnd(e, 700) + 300;
     MP_NOUNROLL for (int16_t z = 0; z < strength; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
-        if (vulnerable(e.map[tix(x, y)])) {
+        if (vulnerable(e.map()[tix(x, y)])) {
             if ((z & 0x3) != 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
             else mset(e, tix(x, y), (uint16_t)random_fire(e));
         }
@@ -691,7 +691,7 @@ MPN void make_earthquake_coop(Env &e)
         bool special = false;
         if (lane < nb) {
             special = r1 >= 65520 || r2 >= 65500;           // getRandom's rejection: (0xffff / range) * range
-            if (!special) special = vulnerable(e.map[tix(r1 % WORLD_W, r2 % WORLD_H)]);
+            if (!special) special = vulnerable(e.map()[tix(r1 % WORLD_W, r2 % WORLD_H)]);
         }
         const unsigned sm = __ballot_sync(0xffffffffu, special);
         const int first = sm ? __ffs(sm) - 1 : nb;
@@ -700,7 +700,7 @@ MPN void make_earthquake_coop(Env &e)
             S.rng = lcg_jump(rng, 2 * first);
             if (first < nb) {                               // the literal iteration z + first
                 const int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
-                if (vulnerable(e.map[tix(x, y)])) {
+                if (vulnerable(e.map()[tix(x, y)])) {
                     if (((z + first) & 0x3) != 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
                     else mset(e, tix(x, y), (uint16_t)random_fire(e));
                 }
@@ -718,7 +718,7 @@ MPN void make_earthquake_coop(Env &e)
 MPN void set_fire(Env &e)
 {
     int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
-    int16_t z = (int16_t)e.map[tix(x, y)];
+    int16_t z = (int16_t)e.map()[tix(x, y)];
     if ((z & ZONEBIT) == 0) {
         z = z & LOMASK;
         if (z > T_LHTHR && z < T_LASTZONE) mset(e, tix(x, y), (uint16_t)random_fire(e));
@@ -731,12 +731,12 @@ MPN void make_flood(Env &e)
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
-        int c = e.map[tix(x, y)] & LOMASK;
+        int c = e.map()[tix(x, y)] & LOMASK;
         if (c > T_CHANNEL && c <= T_WATER_HIGH) {
             MP_NOUNROLL for (int t = 0; t < 4; t++) {
                 int xx = x + dx[t], yy = y + dy[t];
                 if (inb(xx, yy)) {
-                    int16_t cc = (int16_t)e.map[tix(xx, yy)];
+                    int16_t cc = (int16_t)e.map()[tix(xx, yy)];
                     if (cc == T_DIRT || (cc & (BULLBIT | BURNBIT)) == (BULLBIT | BURNBIT)) {
                         mset(e, tix(xx, yy), T_FLOOD);
                         S.floodCount = 30;

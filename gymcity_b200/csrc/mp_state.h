@@ -16,6 +16,7 @@
 #define MPD __device__ __forceinline__
 #define MPN __device__ __noinline__
 #define MPH __host__ __device__ inline
+#define MPA __host__ __device__ __forceinline__
 // The serial lane is latency bound and its code footprint is what hurts (the engine is ~10x the SM
 // instruction caches): keep its loops rolled.
 #define MP_NOUNROLL _Pragma("unroll 1")
@@ -41,6 +42,7 @@ inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned
 #define MPD inline
 #define MPN inline
 #define MPH inline
+#define MPA inline
 #define MP_NOUNROLL
 #endif
 
@@ -184,45 +186,94 @@ struct Coop {
     MPD bool lead() const { return (int)tid == 0; }
 };
 
-struct Env {
-    uint16_t *map;
-    uint8_t *pop, *traffic, *pollution, *landval, *crime, *terrain;
-    uint32_t *power;
-    int16_t *rog, *fireSt, *fireEff, *policeSt, *policeEff, *comRate;
-    int16_t *resHist, *comHist, *indHist, *moneyHist, *pollutionHist, *crimeHist, *miscHist;
-    Scalars *s;
-    Sprite *spr;
-    uint8_t *tmp1, *tmp2, *tmp3;
-    int16_t *stmp;
-    uint16_t *pstack;
-    uint16_t *ovl;          // tool overlay: 256 values + 8 mask words
-    uint32_t *act;          // active-tile bitmap (derived from map, kept in step by mset)
-    uint32_t *need;         // tiles mapScan must visit: act minus building tiles whose PWRBIT is already right
-    const uint16_t *anim;   // 1024-entry animation successor table
-    Coop c;
+// Scalars pointer.  On the device every kernel stages the env's scalar block in SHARED memory for the
+// duration of the launch (census counters, cycle counters, RNG state are touched on almost every serial
+// instruction).  The copies live in the kernel's dynamic shared memory and the pointer is kept as a byte
+// offset from that symbol, so the compiler knows the address space and emits LDS / STS with 32-bit addresses
+// instead of generic-space accesses.  Host code (snapshots, the CPU harness) holds a plain pointer.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t mp_dyn_smem[];
+#endif
+struct ScalPtr {
+    Scalars *p;                 // device: byte offset into mp_dyn_smem
+    MPA Scalars *get() const
+    {
+#if defined(__CUDA_ARCH__)
+        return reinterpret_cast<Scalars *>(mp_dyn_smem + (uint32_t)reinterpret_cast<uintptr_t>(p));
+#else
+        return p;
+#endif
+    }
+    MPA Scalars *operator->() const { return get(); }
+    MPA Scalars &operator*() const { return *get(); }
+    MPA operator Scalars *() const { return get(); }
+    MPA ScalPtr &operator=(Scalars *q)
+    {
+#if defined(__CUDA_ARCH__)
+        p = reinterpret_cast<Scalars *>((uintptr_t)(reinterpret_cast<uint8_t *>(q) - mp_dyn_smem));
+#else
+        p = q;
+#endif
+        return *this;
+    }
 };
 
+// One env = the base pointer of its block; every map is the base plus a compile-time offset (EnvLayout), so
+// a field access is one global load with an immediate offset -- no per-field pointer to fetch first.
+struct Env {
+    uint8_t *blk;
+    ScalPtr s;
+    uint16_t *ovl;          // tool overlay: 256 values + 8 mask words (block scratch, or shared memory in k_mp_env_pre)
+    const uint16_t *anim;   // 1024-entry animation successor table
+    Coop c;
+    MPA uint8_t *base() const
+    {
+        uint8_t *b = blk;
+#if defined(__CUDA_ARCH__) && !defined(MP_NO_ASSUME_GLOBAL)
+        __builtin_assume(__isGlobal(b));
+#endif
+        return b;
+    }
+    typedef EnvLayout L;
+    MPA uint16_t *map() const { return (uint16_t *)(base() + L::MAP); }
+    MPA uint8_t *pop() const { return base() + L::POP; }
+    MPA uint8_t *traffic() const { return base() + L::TRAFFIC; }
+    MPA uint8_t *pollution() const { return base() + L::POLLUTION; }
+    MPA uint8_t *landval() const { return base() + L::LANDVAL; }
+    MPA uint8_t *crime() const { return base() + L::CRIME; }
+    MPA uint8_t *terrain() const { return base() + L::TERRAIN; }
+    MPA uint32_t *power() const { return (uint32_t *)(base() + L::POWER); }
+    MPA int16_t *rog() const { return (int16_t *)(base() + L::ROG); }
+    MPA int16_t *fireSt() const { return (int16_t *)(base() + L::FIREST); }
+    MPA int16_t *fireEff() const { return (int16_t *)(base() + L::FIREEFF); }
+    MPA int16_t *policeSt() const { return (int16_t *)(base() + L::POLICEST); }
+    MPA int16_t *policeEff() const { return (int16_t *)(base() + L::POLICEEFF); }
+    MPA int16_t *comRate() const { return (int16_t *)(base() + L::COMRATE); }
+    MPA int16_t *resHist() const { return (int16_t *)(base() + L::HIST); }
+    MPA int16_t *comHist() const { return resHist() + 240; }
+    MPA int16_t *indHist() const { return resHist() + 480; }
+    MPA int16_t *moneyHist() const { return resHist() + 720; }
+    MPA int16_t *pollutionHist() const { return resHist() + 960; }
+    MPA int16_t *crimeHist() const { return resHist() + 1200; }
+    MPA int16_t *miscHist() const { return resHist() + 1440; }
+    MPA Sprite *spr() const { return (Sprite *)(base() + L::SPRITES); }
+    MPA uint8_t *tmp1() const { return base() + L::TMP1; }
+    MPA uint8_t *tmp2() const { return base() + L::TMP2; }
+    MPA uint8_t *tmp3() const { return base() + L::TMP3; }
+    MPA int16_t *stmp() const { return (int16_t *)(base() + L::STMP); }
+    MPA uint16_t *pstack() const { return (uint16_t *)(base() + L::PSTACK); }
+    MPA uint32_t *act() const { return (uint32_t *)(base() + L::ACTIVE); }      // active-tile bitmap (derived from map, kept in step by mset)
+    MPA uint32_t *need() const { return (uint32_t *)(base() + L::NEED); }       // tiles mapScan must visit: act minus building tiles whose PWRBIT is already right
+};
+
+// Scalars live in the block; the kernels re-point `s` at their shared-memory copy (stage_scalars).
 MPH void bind_env(Env &e, uint8_t *blk)
 {
-    typedef EnvLayout L;
-    e.map = (uint16_t *)(blk + L::MAP);
-    e.pop = blk + L::POP; e.traffic = blk + L::TRAFFIC; e.pollution = blk + L::POLLUTION;
-    e.landval = blk + L::LANDVAL; e.crime = blk + L::CRIME; e.terrain = blk + L::TERRAIN;
-    e.power = (uint32_t *)(blk + L::POWER);
-    e.rog = (int16_t *)(blk + L::ROG); e.fireSt = (int16_t *)(blk + L::FIREST);
-    e.fireEff = (int16_t *)(blk + L::FIREEFF); e.policeSt = (int16_t *)(blk + L::POLICEST);
-    e.policeEff = (int16_t *)(blk + L::POLICEEFF); e.comRate = (int16_t *)(blk + L::COMRATE);
-    int16_t *h = (int16_t *)(blk + L::HIST);
-    e.resHist = h; e.comHist = h + 240; e.indHist = h + 480; e.moneyHist = h + 720;
-    e.pollutionHist = h + 960; e.crimeHist = h + 1200; e.miscHist = h + 1440;
-    e.s = (Scalars *)(blk + L::SCALARS);
-    e.spr = (Sprite *)(blk + L::SPRITES);
-    e.tmp1 = blk + L::TMP1; e.tmp2 = blk + L::TMP2; e.tmp3 = blk + L::TMP3;
-    e.stmp = (int16_t *)(blk + L::STMP);
-    e.pstack = (uint16_t *)(blk + L::PSTACK);
-    e.ovl = (uint16_t *)(blk + L::OVERLAY);
-    e.act = (uint32_t *)(blk + L::ACTIVE);
-    e.need = (uint32_t *)(blk + L::NEED);
+    e.blk = blk;
+#if !defined(__CUDA_ARCH__)
+    e.s.p = (Scalars *)(blk + EnvLayout::SCALARS);      // device: the kernels point `s` at their shared-memory copy
+#endif
+    e.ovl = (uint16_t *)(blk + EnvLayout::OVERLAY);
 }
 
 // ------------------------------------------------------------------ small helpers
@@ -247,13 +298,13 @@ MPD int pwr_get(const Env &e, int x, int y)
 {
     if (!inb(x, y)) return 0;
     int i = tix(x, y);
-    return (e.power[i >> 5] >> (i & 31)) & 1u;
+    return (e.power()[i >> 5] >> (i & 31)) & 1u;
 }
 MPD void pwr_set(Env &e, int x, int y)
 {
     if (!inb(x, y)) return;
     int i = tix(x, y);
-    e.power[i >> 5] |= 1u << (i & 31);
+    e.power()[i >> 5] |= 1u << (i & 31);
 }
 // Every tile store on the serial lane goes through mset so that the two derived bitmaps never go
 // stale.  `act`: bit set iff tile id >= FLOOD, i.e. the reference's mapScan would look at the tile
@@ -276,7 +327,7 @@ MPD bool tile_needs_visit(const Env &e, int idx, int v)
     if (!tile_is_inert_kind(v)) return true;
     if (!(v & CONDBIT) || !e.s->newPower) return false;
     const int t = v & LOMASK;
-    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power[idx >> 5] >> (idx & 31)) & 1u);
+    const bool want = t == T_NUCLEAR || t == T_POWERPLANT || ((e.power()[idx >> 5] >> (idx & 31)) & 1u);
     return ((v & PWRBIT) != 0) != want;
 }
 #if defined(MP_MSET_NOINLINE)
@@ -285,7 +336,7 @@ MPN void mset(Env &e, int idx, int v)
 MPD void mset(Env &e, int idx, int v)
 #endif
 {
-    const int old = e.map[idx];
+    const int old = e.map()[idx];
     if (old == (int)(uint16_t)v) return;                 // repairZone, smoke and traffic art mostly rewrite what is there
     if ((old ^ v) & CONDBIT) {
         // Does the flip touch the powered grid?  A tile that stops conducting matters if it was powered; a
@@ -295,21 +346,21 @@ MPD void mset(Env &e, int idx, int v)
         if (v & CONDBIT) {
             const int t = v & LOMASK, x = idx / WORLD_H, y = idx - x * WORLD_H;
             matters = t == T_POWERPLANT || t == T_NUCLEAR;
-            if (y > 0) matters |= ((e.power[(idx - 1) >> 5] >> ((idx - 1) & 31)) & 1u) != 0;
-            if (y < WORLD_H - 1) matters |= ((e.power[(idx + 1) >> 5] >> ((idx + 1) & 31)) & 1u) != 0;
-            if (x > 0) matters |= ((e.power[(idx - WORLD_H) >> 5] >> ((idx - WORLD_H) & 31)) & 1u) != 0;
-            if (x < WORLD_W - 1) matters |= ((e.power[(idx + WORLD_H) >> 5] >> ((idx + WORLD_H) & 31)) & 1u) != 0;
+            if (y > 0) matters |= ((e.power()[(idx - 1) >> 5] >> ((idx - 1) & 31)) & 1u) != 0;
+            if (y < WORLD_H - 1) matters |= ((e.power()[(idx + 1) >> 5] >> ((idx + 1) & 31)) & 1u) != 0;
+            if (x > 0) matters |= ((e.power()[(idx - WORLD_H) >> 5] >> ((idx - WORLD_H) & 31)) & 1u) != 0;
+            if (x < WORLD_W - 1) matters |= ((e.power()[(idx + WORLD_H) >> 5] >> ((idx + WORLD_H) & 31)) & 1u) != 0;
         } else {
-            matters = ((e.power[idx >> 5] >> (idx & 31)) & 1u) != 0;
+            matters = ((e.power()[idx >> 5] >> (idx & 31)) & 1u) != 0;
         }
         if (matters) e.s->powerQuiet = 0;
     }
-    e.map[idx] = (uint16_t)v;
+    e.map()[idx] = (uint16_t)v;
     const uint32_t bit = 1u << (idx & 31);
-    const uint32_t w = e.act[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
-    if (nw != w) e.act[idx >> 5] = nw;
-    const uint32_t n = e.need[idx >> 5], nn = tile_needs_visit(e, idx, v) ? (n | bit) : (n & ~bit);
-    if (nn != n) e.need[idx >> 5] = nn;
+    const uint32_t w = e.act()[idx >> 5], nw = tile_is_active(v) ? (w | bit) : (w & ~bit);
+    if (nw != w) e.act()[idx >> 5] = nw;
+    const uint32_t n = e.need()[idx >> 5], nn = tile_needs_visit(e, idx, v) ? (n | bit) : (n & ~bit);
+    if (nn != n) e.need()[idx >> 5] = nn;
 }
 // [ALL] recompute both bitmaps from the map (after bulk writes: clearMap, terrain, state upload)
 MPD void rebuild_active(Env &e)
@@ -318,12 +369,12 @@ MPD void rebuild_active(Env &e)
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
         uint32_t m = 0, nd = 0;
         for (int b = 0; b < 32; b++) {
-            const int v = e.map[w * 32 + b];
+            const int v = e.map()[w * 32 + b];
             if (tile_is_active(v)) m |= 1u << b;
             if (tile_needs_visit(e, w * 32 + b, v)) nd |= 1u << b;
         }
-        e.act[w] = m;
-        e.need[w] = nd;
+        e.act()[w] = m;
+        e.need()[w] = nd;
     }
     e.c.sync();
 }
@@ -331,7 +382,7 @@ MPD void rebuild_active(Env &e)
 MPD void refresh_need(Env &e)
 {
     for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
-        uint32_t m = e.act[w], nd = 0;
+        uint32_t m = e.act()[w], nd = 0;
         while (m) {
 #if defined(__CUDA_ARCH__)
             const int b = __ffs(m) - 1;
@@ -340,16 +391,16 @@ MPD void refresh_need(Env &e)
             while (!((m >> b) & 1u)) b++;
 #endif
             m &= m - 1;
-            if (tile_needs_visit(e, w * 32 + b, e.map[w * 32 + b])) nd |= 1u << b;
+            if (tile_needs_visit(e, w * 32 + b, e.map()[w * 32 + b])) nd |= 1u << b;
         }
-        e.need[w] = nd;
+        e.need()[w] = nd;
     }
     e.c.sync();
 }
 // bounds-safe tile store (the reference indexes map[x][y] unchecked in a few places that are
 // in-bounds for every reachable state; an out-of-range store is dropped here)
 MPD void tset(Env &e, int x, int y, int v) { if (inb(x, y)) mset(e, tix(x, y), v); }
-MPD int tget(const Env &e, int x, int y) { return inb(x, y) ? e.map[tix(x, y)] : 0; }
+MPD int tget(const Env &e, int x, int y) { return inb(x, y) ? e.map()[tix(x, y)] : 0; }
 
 // ------------------------------------------------------------------ RNG (random.cpp:88-174)
 // nextRandom is an unsigned long in the reference but only bits 8..23 are observed and the LCG is

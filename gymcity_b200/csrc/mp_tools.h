@@ -557,7 +557,7 @@ MPN int tool_down(Env &e, int tool, int x, int y)
 MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.cpp:572-598
 {
     if (ch == 0 || !inb(x, y)) return;
-    int temp = e.map[tix(x, y)];
+    int temp = e.map()[tix(x, y)];
     if (temp != T_DIRT) {
         temp &= LOMASK;
         if (temp == T_RIVER && ch != T_CHANNEL) return;
@@ -615,13 +615,13 @@ MPN void smooth_river(Env &e)                                      // generate.c
         5 | BULLBIT, 2 };
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
         MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
-            if (e.map[tix(x, y)] == T_REDGE) {
+            if (e.map()[tix(x, y)] == T_REDGE) {
                 int bits = 0;
                 MP_NOUNROLL for (int z = 0; z < 4; z++) {
                     bits <<= 1;
                     int xx = x + dx[z], yy = y + dy[z];
                     if (inb(xx, yy)) {
-                        int t = e.map[tix(xx, yy)] & LOMASK;
+                        int t = e.map()[tix(xx, yy)] & LOMASK;
                         if (t != T_DIRT && (t < T_WOODS_LOW || t > T_WOODS_HIGH)) bits++;
                     }
                 }
@@ -637,12 +637,12 @@ MPN void smooth_trees(Env &e)                                      // generate.c
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
         MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
-            if (is_tree(e.map[tix(x, y)])) {
+            if (is_tree(e.map()[tix(x, y)])) {
                 int bits = 0;
                 MP_NOUNROLL for (int z = 0; z < 4; z++) {
                     bits <<= 1;
                     int xx = x + dx[z], yy = y + dy[z];
-                    if (inb(xx, yy) && is_tree(e.map[tix(xx, yy)])) bits++;
+                    if (inb(xx, yy) && is_tree(e.map()[tix(xx, yy)])) bits++;
                 }
                 int temp = treeTable[bits & 15];
                 if (temp) {
@@ -665,7 +665,7 @@ MPN void do_trees(Env &e)                                          // generate.c
             int dir = D_N + rnd(e, 7);
             pos_move(tx, ty, dir);
             if (!inb(tx, ty)) break;
-            if ((e.map[tix(tx, ty)] & LOMASK) == T_DIRT) mset(e, tix(tx, ty), (uint16_t)(T_WOODS | BLBNBIT));
+            if ((e.map()[tix(tx, ty)] & LOMASK) == T_DIRT) mset(e, tix(tx, ty), (uint16_t)(T_WOODS | BLBNBIT));
             numTrees--;
         }
     }
