@@ -203,12 +203,17 @@ __global__ void k_gol_classic_step(uint32_t *__restrict__ rows, uint32_t *__rest
     int64_t a = actions[env];
     bool del = a < 0;
     if (del) a = -a;
-    int ax = (int)(a / w), ay = (int)(a - (int64_t)ax * w);
+    // an action outside the board (intsToActions raises IndexError in the reference; host-side inputs are
+    // rejected by the Python wrapper) builds nothing here: the tick still runs
+    const bool in_range = a < (int64_t)w * w;
+    int ax = in_range ? (int)(a / w) : 0, ay = in_range ? (int)(a - (int64_t)ax * w) : 0;
     int pre = 0;
     for (int x = 0; x < w; x++) pre += __popc(r[x]);
     // build_cell: neighbours q of p=(ax,ay) whose reference to p is still live now freeze the old value
     uint32_t old = (r[ax] >> ay) & 1u;
-    for (int d = 0; d < 8; d++) {
+    // env.py:147-152: a player delete happens BEFORE reward = state.sum(); a build after it
+    if (del && in_range && old) pre--;
+    for (int d = 0; d < 8 && in_range; d++) {
         // q sees p in direction d  <=>  q + (dx,dy) = p
         int qx = (ax - dx[d] + w) % w, qy = (ay - dy[d] + w) % w;
         uint32_t bit = 1u << qy;
@@ -219,7 +224,7 @@ __global__ void k_gol_classic_step(uint32_t *__restrict__ rows, uint32_t *__rest
         // the new Cell at p has neighbours=None: all eight references are rebuilt live
         fz[ax * 8 + d] &= ~(1u << ay);
     }
-    r[ax] = del ? (r[ax] & ~(1u << ay)) : (r[ax] | (1u << ay));
+    if (in_range) r[ax] = del ? (r[ax] & ~(1u << ay)) : (r[ax] | (1u << ay));
 
     // world.py:29-56 _tick with per-direction visibility
     uint32_t nxt_rows[32];

@@ -45,6 +45,14 @@ struct MpBatch {
     int *perm;                // [n_envs] env ids, most expensive first
     unsigned int *hist;       // [SCHED_BUCKETS + 1]
     int use_sched;
+    int sms;                  // SMs of the device
+    int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
+    int qmode;                // frames run by the queue-scheduled kernel (k_mp_frames_q) when the launch has >= q_min_envs envs
+    int q_min_envs, q_max_k, q_waves, q_unit_mask, q_ctas;
+    unsigned int *prof;       // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
+    cudaError_t launch_err;   // first error of a launch enqueued by launch_frames since the last check
+    int32_t *xt_rnd; size_t xt_rnd_bytes;    // device buffer of mpb_env_extinguish's draws (grown on demand)
+    double *counters_dev;     // [n_envs * MPB_ENV_NUM_COUNTERS] staging of mpb_env_get_counters
     // env groups on their own streams: while one group's launch drains its slowest envs the other
     // groups' launches keep the SMs busy (the per-env dependency chain is the only real one)
     int groups;
@@ -252,6 +260,184 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     }
 }
 
+// ---- queue-scheduled frame kernel ----------------------------------------------------------------
+// k_mp_frames<32> keeps the 32 warps of an SM in the same simulation phase with a CTA barrier per frame, and
+// pays for it: every frame lasts as long as its slowest env (ncu r01: 42 % of all warp cycles stalled at the
+// barrier).  Here one CTA (32 warps, one per SM) owns K >> 32 envs and the warps take env-frames from a FIFO of
+// ready envs in shared memory: a warp pops an env, runs one UNIT of its frames (a run of phases that ends after a
+// phase of `unit_mask`, e.g. the eight map-scan phases), and pushes it back.  Because the queue is first in,
+// first out, every env finishes unit u before any env starts unit u + 2, so the warps of the SM are still in
+// (nearly) the same code -- the lockstep the instruction caches need -- but nobody waits: a slow env only
+// occupies the warp that runs it.  Envs flagged heavy (the first `heavy_slots` of the cost order: flood and fire
+// fields, 5-10 x the mean) are run to the end of the launch by the warp that pops them: they are the critical
+// path and must not queue behind anyone.
+//   Queue: bounded MPMC ring (tickets + per-slot sequence numbers).  At most K + 32 entries are ever in
+// flight (K envs, 32 exit sentinels pushed by the warp that retires the last env), QN >= K + 32.
+constexpr int MPQ_MAX_K = 448;      // envs per CTA the shared-memory budget allows (448 * 480 B + queue < 227 KB)
+constexpr int MPQ_QN = 512;         // ring size, power of two >= MPQ_MAX_K + 32
+
+struct QArgs {
+    uint8_t *blocks; const uint16_t *anim; int n_envs, first, count, animate_before, respect_passes;
+    unsigned long long *cycles; unsigned int *cost; const int *perm; int gstride, goff, gcount;
+    int K;                   // envs per CTA: CTA c owns ranks c, c + gridDim.x, ... (K of them)
+    int unit_mask;           // bit p: a unit ends after phase p
+    int heavy_slots;         // schedule slots below this are run to the end of the launch without re-queueing
+    unsigned int *prof; int prof_off; const uint8_t *mask;
+};
+
+__device__ __forceinline__ unsigned int q_ld(const volatile unsigned int *p) { return *p; }
+
+__global__ void __launch_bounds__(1024, 1) k_mp_frames_q(const QArgs a)
+{
+    __shared__ Env s_env[32];
+    __shared__ int red[8 * 32];
+    __shared__ int s_q[MPQ_QN];
+    __shared__ unsigned int s_seq[MPQ_QN];
+    __shared__ unsigned int s_head, s_tail, s_ndone, s_nlive;
+    const int K = a.K;
+    // dynamic shared memory: K scalar blocks, then the per-env bookkeeping
+    uint32_t *const scal = reinterpret_cast<uint32_t *>(mp_dyn_smem);
+    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)K * SCAL_BYTES);
+    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + K);
+    short *const s_fdone = reinterpret_cast<short *>(s_busy + K);
+    short *const s_nrun = s_fdone + K;
+    unsigned char *const s_sticky = reinterpret_cast<unsigned char *>(s_nrun + K);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Env &e = s_env[warp];
+    for (int i = threadIdx.x; i < MPQ_QN; i += blockDim.x) s_seq[i] = 0;
+    if (lane == 0) { e.anim = a.anim; e.c.red = red + warp * 8; }     // also for warps that stage no env below
+
+    // ---- prologue: stage the scalars of the CTA's envs, tickEngine's animateTiles, frames to run
+    for (int k = warp; k < K; k += 32) {
+        const long long t0 = clock64();
+        const int rank = blockIdx.x + k * gridDim.x;
+        const int slot = rank * a.gstride + a.goff;
+        bool live = rank < a.gcount && slot < a.n_envs;
+        int env = 0;
+        if (live) {
+            env = a.perm ? a.perm[slot] : slot;
+            if (a.mask && !a.mask[env]) live = false;
+        }
+        int nrun = 0;
+        if (live) {
+            bind_env_of(e, a.blocks, env, a.anim, red, scal + (size_t)k * SCAL_WORDS);
+            if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+            nrun = a.count;
+            if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            s_envid[k] = live ? env : -1;
+            s_nrun[k] = (short)nrun;
+            s_fdone[k] = 0;
+            s_sticky[k] = (unsigned char)(live && slot < a.heavy_slots);
+            s_busy[k] = (unsigned int)(clock64() - t0);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                   // the ready queue, in schedule (heavy-first) order
+        unsigned int base = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const bool ready = k < K && s_envid[k] >= 0 && s_nrun[k] > 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, ready);
+            if (ready) {
+                const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
+                s_q[pos] = k;
+                s_seq[pos] = pos + 1;
+            }
+            base += __popc(m);
+        }
+        if (base == 0) {                               // nothing to run: every warp takes an exit sentinel
+            s_q[lane] = -1;
+            s_seq[lane] = lane + 1;
+        }
+        if (lane == 0) { s_head = 0; s_tail = base ? base : 32; s_nlive = base; s_ndone = 0; }
+    }
+    __syncthreads();
+
+    // ---- the warps drain the queue
+    for (;;) {
+        int k = 0;
+        if (lane == 0) {
+            const unsigned int t = atomicAdd(&s_head, 1u);
+            const unsigned int slot = t & (MPQ_QN - 1);
+            while (q_ld(&s_seq[slot]) != t + 1) __nanosleep(64);
+            k = *reinterpret_cast<volatile int *>(&s_q[slot]);
+        }
+        __threadfence_block();
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k < 0) break;
+        const unsigned int t0 = (unsigned int)clock64();
+        const int env = s_envid[k];
+        if (lane == 0) {
+            bind_env(e, a.blocks + (size_t)env * ENV_STRIDE);
+            e.s = reinterpret_cast<Scalars *>(scal + (size_t)k * SCAL_WORDS);
+        }
+        __syncwarp();
+        int f = s_fdone[k];
+        const int n = s_nrun[k];
+        const bool sticky = s_sticky[k] != 0;
+        if (e.s->simSpeed == 3 && !e.s->initSimLoad) {
+            // the gym path's common case: every frame simulates, speedCycle / phaseCycle are plain counters
+            int phase = e.s->phaseCycle & 15, sc = e.s->speedCycle, ran;
+            do {
+                const unsigned int tf = (unsigned int)clock64();
+                sim_phase(e, phase);
+                ran = phase;
+                phase = (phase + 1) & 15;
+                sc = (sc + 1) & 1023;
+                sim_sprites(e);
+                if (a.prof && lane == 0) a.prof[(size_t)env * 256 + a.prof_off + a.first + f] = (unsigned int)clock64() - tf;
+                f++;
+            } while (f < n && (sticky || !((a.unit_mask >> ran) & 1)));
+            if (lane == 0) { e.s->phaseCycle = (int16_t)phase; e.s->speedCycle = (int16_t)sc; }
+        } else {
+            int ran;
+            do {
+                ran = sim_loop_head(e);
+                sim_loop_tail(e, ran);
+                f++;
+            } while (f < n && (sticky || !(ran && ((a.unit_mask >> (ran - 1)) & 1))));
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+            s_fdone[k] = (short)f;
+            s_busy[k] += (unsigned int)clock64() - t0;
+            __threadfence_block();
+            if (f < n) {
+                const unsigned int p = atomicAdd(&s_tail, 1u), slot = p & (MPQ_QN - 1);
+                *reinterpret_cast<volatile int *>(&s_q[slot]) = k;
+                __threadfence_block();
+                *reinterpret_cast<volatile unsigned int *>(&s_seq[slot]) = p + 1;
+            } else if (atomicAdd(&s_ndone, 1u) + 1 == s_nlive) {
+                for (int i = 0; i < 32; i++) {         // the last env is done: one exit sentinel per warp
+                    const unsigned int p = atomicAdd(&s_tail, 1u), slot = p & (MPQ_QN - 1);
+                    *reinterpret_cast<volatile int *>(&s_q[slot]) = -1;
+                    __threadfence_block();
+                    *reinterpret_cast<volatile unsigned int *>(&s_seq[slot]) = p + 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue: scalars back to the blocks, per-env cycle counts for the next schedule
+    for (int k = warp; k < K; k += 32) {
+        const int env = s_envid[k];
+        if (env < 0) continue;
+        uint32_t *gs = reinterpret_cast<uint32_t *>(a.blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
+        const uint32_t *sw = scal + (size_t)k * SCAL_WORDS;
+        for (int i = lane; i < SCAL_WORDS; i += 32) gs[i] = sw[i];
+        if (lane == 0) {
+            if (a.cycles) a.cycles[env] += s_busy[k];
+            if (a.cost) a.cost[env] += s_busy[k] >> 8;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_call(uint8_t *blocks, const uint16_t *anim, int n_envs, int fn, int a, int b)
 {
@@ -449,10 +635,11 @@ k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     unstage_scalars(e, sw);
 }
 
-__global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
+__global__ void k_mp_env_counters(const uint8_t *blocks, const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const Scalars *sc = (const Scalars *)(blocks + (size_t)i * ENV_STRIDE + EnvLayout::SCALARS);
     Gym gy;
     bind_gym(gy, const_cast<uint8_t *>(shadow) + (size_t)i * stride, &cfg);
     const GymScalars &g = *gy.g;
@@ -460,6 +647,7 @@ __global__ void k_mp_env_counters(const uint8_t *shadow, int stride, GymCfg cfg,
     o[0] = g.num_plants; o[1] = g.num_roads; o[2] = g.n_struct_tiles; o[3] = g.total_traffic;
     o[4] = g.num_step; o[5] = g.tilemap_error; o[6] = g.reward; o[7] = g.done; o[8] = g.curr_funds;
     for (int k = 0; k < GYM_NUM_METRICS; k++) o[9 + k] = g.metrics[k];
+    o[15] = sc->spriteOverflow;
 }
 
 #define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
@@ -477,23 +665,40 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 
-const uint8_t *g_step_mask = NULL;  // device mask of the envs that take part in the current masked env-step
-int g_scan_block = 1;             // map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
-unsigned int *g_prof = NULL;      // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
-// k_mp_frames with `epc` envs per CTA (1, 8 or 16); prof_off = frame offset of this simTick in the
-// per-frame profile rows (0 for the first simTick of an env-step, 100 for the second)
-void launch_frames(int epc, int count_envs, cudaStream_t st, uint8_t *blocks, const uint16_t *anim, int n_envs, int first,
-                   int count, int animate_before, int respect_passes, unsigned long long *cycles, unsigned int *cost,
-                   const int *perm, int gstride, int goff, int gcount, int prof_off = 0)
+// k_mp_frames with `epc` envs per CTA (1, 8, 16 or 32), or the queue-scheduled kernel (b->qmode); prof_off = frame
+// offset of this simTick in the per-frame profile rows (0 for the first simTick of an env-step, 100 for the
+// second).  `mask`: device mask of the envs that take part (NULL = all).  A launch error is recorded in the handle
+// (b->launch_err) and reported by the entry point that enqueued it.
+void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, int animate_before, int respect_passes,
+                   const int *perm, int gstride, int goff, int gcount, const uint8_t *mask, int prof_off = 0, bool heavy = false)
 {
-    if (count_envs <= 0) return;
-#define MP_FRAMES_ARGS blocks, anim, n_envs, first, count, animate_before, respect_passes, cycles, cost, perm, gstride, goff, \
-                       gcount, g_scan_block, g_prof, prof_off, g_step_mask
-    if (epc >= 32) k_mp_frames<32><<<(count_envs + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-    else if (epc >= 16) k_mp_frames<16><<<(count_envs + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-    else if (epc >= 8) k_mp_frames<8><<<(count_envs + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-    else k_mp_frames<1><<<count_envs, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+    if (gcount <= 0) return;
+    if (b->qmode && !heavy && gcount >= b->q_min_envs) {
+        // CTAs: whole waves of one CTA per SM; envs per CTA as even as possible
+        int waves = b->q_waves > 0 ? b->q_waves : 1;
+        int ctas = b->q_ctas > 0 ? b->q_ctas : b->sms * waves;
+        while ((gcount + ctas - 1) / ctas > b->q_max_k) ctas += b->q_ctas > 0 ? 1 : b->sms;
+        QArgs a;
+        a.blocks = b->blocks; a.anim = b->anim; a.n_envs = b->n_envs; a.first = first; a.count = count;
+        a.animate_before = animate_before; a.respect_passes = respect_passes; a.cycles = b->cycles; a.cost = b->cost;
+        a.perm = perm; a.gstride = gstride; a.goff = goff; a.gcount = gcount;
+        a.K = (gcount + ctas - 1) / ctas;
+        a.unit_mask = b->q_unit_mask;
+        a.heavy_slots = (b->use_sched && b->heavy_div > 0 && gstride == 1 && goff == 0) ? b->n_envs / b->heavy_div : 0;
+        a.prof = b->prof; a.prof_off = prof_off; a.mask = mask;
+        const size_t smem = (size_t)a.K * (SCAL_BYTES + 4 + 4 + 2 + 2 + 1) + 16;
+        k_mp_frames_q<<<ctas, 1024, smem, st>>>(a);
+    } else {
+#define MP_FRAMES_ARGS b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles, b->cost, perm, \
+                       gstride, goff, gcount, b->scan_block, b->prof, prof_off, mask
+        if (epc >= 32) k_mp_frames<32><<<(gcount + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+        else if (epc >= 16) k_mp_frames<16><<<(gcount + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+        else if (epc >= 8) k_mp_frames<8><<<(gcount + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+        else k_mp_frames<1><<<gcount, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
 #undef MP_FRAMES_ARGS
+    }
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
 }
 
 // C++ simTick (main.cpp:435-443) for the batch: simPasses frames in launches of frames_per_launch.
@@ -517,35 +722,36 @@ GroupGeom group_geom(const MpBatch *b, int G, int g)
     return q;
 }
 #define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
+// env groups of an env-step: the queue-scheduled kernel balances inside each SM and takes the whole batch as
+// one group; the lockstep kernel overlaps the launch tails of b->groups groups on their own streams
+int step_groups(const MpBatch *b) { return (b->qmode && b->n_envs >= b->q_min_envs) ? 1 : b->groups; }
 
-int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, int G = 1, int g = 0)
+int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8_t *mask, int G = 1, int g = 0)
 {
     const int P = b->passes;
     const int *perm = b->use_sched ? b->perm : NULL;
     const GroupGeom q = group_geom(b, G, g);
     // the heavy group is not kept in phase lockstep: with few, very uneven envs every launch would
     // wait for ITS slowest member (a different env each time), so it runs a whole simTick per launch
-    const int F = (G > 1 && g == 0 && q.stride == 1) ? (P > 0 ? P : 1) : b->frames_per_launch;
     const bool heavy_group = (G > 1 && g == 0 && q.stride == 1);
+    const int F = heavy_group ? (P > 0 ? P : 1) : b->frames_per_launch;
     const int epc = heavy_group ? b->heavy_fepc : b->fepc;
     if (q.count <= 0) return 0;
     if (P <= 0) {
         if (animate_before)
-            launch_frames(epc, q.count, st, b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost, perm, q.stride,
-                          q.off, q.count);
+            launch_frames(b, epc, st, 0, 0, 1, 1, perm, q.stride, q.off, q.count, mask, 0, heavy_group);
         return 0;
     }
     for (int f = 0; f < P; f += F)
-        launch_frames(epc, q.count, st, b->blocks, b->anim, b->n_envs, f, (P - f < F) ? P - f : F,
-                      animate_before && f == 0, 1, b->cycles, b->cost, perm, q.stride, q.off, q.count,
-                      animate_before ? P : 0);
+        launch_frames(b, epc, st, f, (P - f < F) ? P - f : F, animate_before && f == 0, 1, perm, q.stride, q.off, q.count,
+                      mask, animate_before ? P : 0, heavy_group);
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
-int launch_control_sim_tick(MpBatch *b, cudaStream_t st, int G = 1, int g = 0)
+int launch_control_sim_tick(MpBatch *b, cudaStream_t st, const uint8_t *mask, int G = 1, int g = 0)
 {
-    launch_sim_tick(b, st, 0, G, g);
-    launch_sim_tick(b, st, 1, G, g);
+    launch_sim_tick(b, st, 0, mask, G, g);
+    launch_sim_tick(b, st, 1, mask, G, g);
     return 0;
 }
 
@@ -555,6 +761,8 @@ int fail(MpBatch *b, const char *what, cudaError_t e)
     return -1;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(b, #call, e_); } while (0)
+// kernel launches enqueued through launch_frames record their error in the handle
+#define CK_LAUNCHES() do { if (b->launch_err != cudaSuccess) { cudaError_t e_ = b->launch_err; b->launch_err = cudaSuccess; return fail(b, "kernel launch", e_); } CK(cudaGetLastError()); } while (0)
 
 int fetch_env(MpBatch *b, int env, Env &e)
 {
@@ -592,8 +800,25 @@ mpb_handle mpb_create(int n_envs, int device)
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        b->sms = sms;
         b->fepc = n_envs >= sms * 32 * 4 ? 32 : (n_envs >= sms * 16 * 2 ? 16 : 8);
         b->heavy_fepc = b->fepc;
+        // queue-scheduled frames (k_mp_frames_q): one CTA per SM with K = n / SMs envs each; worth it once an SM
+        // has clearly more envs than warps.  q_unit_mask: a unit ends after the map-scan block (phase 8), the
+        // census / decay pair (10), the power scan (11) and the overlay scans + phase 0 (0).
+        b->qmode = 1;
+        b->q_min_envs = sms * 48;
+        b->q_max_k = 256;
+        b->q_waves = 1;
+        b->q_unit_mask = (1 << 8) | (1 << 10) | (1 << 11) | (1 << 0);
+        if (const char *fp = getenv("MPB_QMODE")) b->qmode = atoi(fp);
+        if (const char *fp = getenv("MPB_Q_MIN_ENVS")) b->q_min_envs = atoi(fp);
+        if (const char *fp = getenv("MPB_Q_MAX_K")) { int v = atoi(fp); if (v >= 1 && v <= MPQ_MAX_K) b->q_max_k = v; }
+        if (const char *fp = getenv("MPB_Q_WAVES")) b->q_waves = atoi(fp);
+        if (const char *fp = getenv("MPB_Q_CTAS")) b->q_ctas = atoi(fp);          // tests: a fixed number of CTAs
+        if (const char *fp = getenv("MPB_Q_UNIT_MASK")) b->q_unit_mask = (int)strtol(fp, NULL, 0);
+        cudaFuncSetAttribute(k_mp_frames_q, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MPQ_MAX_K * (SCAL_BYTES + 13) + 16);
     }
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
@@ -601,7 +826,8 @@ mpb_handle mpb_create(int n_envs, int device)
         cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
         cudaFuncSetAttribute(k_mp_frames<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
     }
-    if (const char *fp = getenv("MPB_SCAN_BLOCK")) g_scan_block = atoi(fp) != 0;
+    b->scan_block = 1;
+    if (const char *fp = getenv("MPB_SCAN_BLOCK")) b->scan_block = atoi(fp) != 0;
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
@@ -640,6 +866,7 @@ void mpb_destroy(mpb_handle h)
     for (int g = 0; g < 8; g++) { if (b->gstream[g]) cudaStreamDestroy(b->gstream[g]); if (b->ev_done[g]) cudaEventDestroy(b->ev_done[g]); }
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
+    cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
     cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
     if (b->host_blk) cudaFreeHost(b->host_blk);
@@ -666,10 +893,11 @@ int mpb_launches_per_env_step(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     int total = b->use_sched ? 4 : 0;                       // memset + 3 scheduling kernels
-    for (int g = 0; g < b->groups; g++) {
-        const GroupGeom q = group_geom(b, b->groups, g);
+    const int G = step_groups(b);
+    for (int g = 0; g < G; g++) {
+        const GroupGeom q = group_geom(b, G, g);
         if (q.count <= 0) continue;
-        const int F = (b->groups > 1 && g == 0 && q.stride == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
+        const int F = (G > 1 && g == 0 && q.stride == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
         const int per = b->passes > 0 ? (b->passes + F - 1) / F : 1;
         total += 2 + 2 * per;
     }
@@ -792,9 +1020,9 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     cudaSetDevice(b->device);
     const int F = b->frames_per_launch;
     for (int f = 0; f < n; f += F)
-        launch_frames(b->fepc, b->n_envs, (cudaStream_t)stream, b->blocks, b->anim, b->n_envs, 0, (n - f < F) ? n - f : F, 0,
-                      0, b->cycles, b->cost, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
-    CK(cudaGetLastError());
+        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, (n - f < F) ? n - f : F, 0, 0, b->use_sched ? b->perm : NULL, 1, 0,
+                      b->n_envs, NULL);
+    CK_LAUNCHES();
     return 0;
 }
 
@@ -803,8 +1031,8 @@ int mpb_control_sim_tick(mpb_handle h, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    launch_control_sim_tick(b, (cudaStream_t)stream);
-    CK(cudaGetLastError());
+    launch_control_sim_tick(b, (cudaStream_t)stream, NULL);
+    CK_LAUNCHES();
     return 0;
 }
 
@@ -813,11 +1041,10 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     cudaSetDevice(b->device);
-    launch_sim_tick(b, (cudaStream_t)stream, 0);
+    launch_sim_tick(b, (cudaStream_t)stream, 0, NULL);
     if (animate)
-        launch_frames(b->fepc, b->n_envs, (cudaStream_t)stream, b->blocks, b->anim, b->n_envs, 0, 0, 1, 1, b->cycles, b->cost,
-                      b->use_sched ? b->perm : NULL, 1, 0, b->n_envs);
-    CK(cudaGetLastError());
+        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, 0, 1, 1, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs, NULL);
+    CK_LAUNCHES();
     return 0;
 }
 
@@ -873,10 +1100,10 @@ int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host)
     cudaSetDevice(b->device);
     CK(cudaDeviceSynchronize());
     const size_t bytes = (size_t)b->n_envs * 256 * sizeof(unsigned int);
-    if (out_host && g_prof) CK(cudaMemcpy(out_host, g_prof, bytes, cudaMemcpyDeviceToHost));
-    if (enable && !g_prof) { CK(cudaMalloc(&g_prof, bytes)); }
-    if (enable) CK(cudaMemset(g_prof, 0, bytes));
-    if (!enable && g_prof) { cudaFree(g_prof); g_prof = NULL; }
+    if (out_host && b->prof) CK(cudaMemcpy(out_host, b->prof, bytes, cudaMemcpyDeviceToHost));
+    if (enable && !b->prof) { CK(cudaMalloc(&b->prof, bytes)); }
+    if (enable) CK(cudaMemset(b->prof, 0, bytes));
+    if (!enable && b->prof) { cudaFree(b->prof); b->prof = NULL; }
     return 0;
 }
 
@@ -1038,10 +1265,10 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     NEED_CFG();
     cudaStream_t st = (cudaStream_t)stream;
     if (upload_mask(b, mask_host, st)) return -1;
-    launch_control_sim_tick(b, st);
+    launch_control_sim_tick(b, st, mask_host ? b->mask : NULL);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                     b->obs_out, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
-    CK(cudaGetLastError());
+    CK_LAUNCHES();
     CK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1108,16 +1335,21 @@ int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_ho
     if (type < 0 || type > 3 || n_dels < 0 || !rnd_host) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t rb = (size_t)b->n_envs * (n_dels + 2) * sizeof(int32_t);
-    int32_t *rnd_dev = NULL;
-    CK(cudaMalloc(&rnd_dev, rb));
+    if (rb > b->xt_rnd_bytes) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(b->xt_rnd);
+        b->xt_rnd = NULL; b->xt_rnd_bytes = 0;
+        CK(cudaMalloc(&b->xt_rnd, rb));
+        b->xt_rnd_bytes = rb;
+    }
+    int32_t *rnd_dev = b->xt_rnd;
     CK(cudaMemcpyAsync(rnd_dev, rnd_host, rb, cudaMemcpyHostToDevice, st));
-    if (upload_mask(b, mask_host, st)) { cudaFree(rnd_dev); return -1; }
+    if (upload_mask(b, mask_host, st)) return -1;
     k_mp_env_extinguish<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                           type, n_dels, rnd_dev, mask_host ? b->mask : NULL, b->i32_b);
     cudaError_t le = cudaGetLastError();
     if (le == cudaSuccess) le = cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st);
     if (le == cudaSuccess) le = cudaStreamSynchronize(st);
-    cudaFree(rnd_dev);
     if (le != cudaSuccess) return fail(b, "mpb_env_extinguish", le);
     if (dels_host) memcpy(dels_host, b->host_i32, (size_t)b->n_envs * 4);
     return 0;
@@ -1136,14 +1368,15 @@ int mpb_env_get_ages(mpb_handle h, int env, int32_t *age_out)
     return 0;
 }
 
-static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build, cudaStream_t st);
+static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build,
+                         const uint8_t *mask_dev, cudaStream_t st);
 
 int mpb_env_step(mpb_handle h, const int64_t *actions_dev, int static_build, void *stream)
 {
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!actions_dev) return -1;
-    return env_step_impl(b, actions_dev, NULL, static_build, (cudaStream_t)stream);
+    return env_step_impl(b, actions_dev, NULL, static_build, NULL, (cudaStream_t)stream);
 }
 
 int mpb_env_step_masked(mpb_handle h, const int64_t *actions_host, int static_build, const uint8_t *mask_host, void *stream)
@@ -1155,9 +1388,7 @@ int mpb_env_step_masked(mpb_handle h, const int64_t *actions_host, int static_bu
     memcpy(b->h_act, actions_host, (size_t)b->n_envs * 8);
     CK(cudaMemcpyAsync(b->act_dev, b->h_act, (size_t)b->n_envs * 8, cudaMemcpyHostToDevice, st));
     if (upload_mask(b, mask_host, st)) return -1;
-    g_step_mask = b->mask;
-    const int rc = env_step_impl(b, b->act_dev, NULL, static_build, st);
-    g_step_mask = NULL;
+    const int rc = env_step_impl(b, b->act_dev, NULL, static_build, b->mask, st);
     if (rc) return rc;
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -1168,12 +1399,13 @@ int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream)
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!tools_dev) return -1;
-    return env_step_impl(b, NULL, tools_dev, 0, (cudaStream_t)stream);
+    return env_step_impl(b, NULL, tools_dev, 0, NULL, (cudaStream_t)stream);
 }
 
-static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build, cudaStream_t st)
+static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build,
+                         const uint8_t *mask_dev, cudaStream_t st)
 {
-    const int G = b->groups;
+    const int G = step_groups(b);
     const int *perm = b->use_sched ? b->perm : NULL;
     if (G > 1) cudaEventRecord(b->ev_start, st);
     for (int g = 0; g < G; g++) {
@@ -1187,17 +1419,17 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
                                                            b->cfg, paint_dev, perm, q.stride, q.off, q.count);
         else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                     actions_dev, static_build, perm, q.stride, q.off, q.count, g_step_mask);
-        launch_control_sim_tick(b, gs, G, g);
+                                                     actions_dev, static_build, perm, q.stride, q.off, q.count, mask_dev);
+        launch_control_sim_tick(b, gs, mask_dev, G, g);
         k_mp_env_post<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                  b->obs_out, b->reward, b->done, 0, g_step_mask, perm, q.stride, q.off, q.count);
+                                                  b->obs_out, b->reward, b->done, 0, mask_dev, perm, q.stride, q.off, q.count);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);
         }
     }
     rebuild_schedule(b, st);
-    CK(cudaGetLastError());
+    CK_LAUNCHES();
     return 0;
 }
 
@@ -1224,13 +1456,12 @@ int mpb_env_get_counters(mpb_handle h, double *out_host)
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     if (!out_host) return -1;
-    double *dev = NULL;
     size_t bytes = (size_t)b->n_envs * MPB_ENV_NUM_COUNTERS * sizeof(double);
-    CK(cudaMalloc(&dev, bytes));
-    k_mp_env_counters<<<(b->n_envs + 127) / 128, 128>>>(b->shadow, b->shadow_stride, b->cfg, b->n_envs, dev);
-    cudaError_t e = cudaMemcpy(out_host, dev, bytes, cudaMemcpyDeviceToHost);
-    cudaFree(dev);
-    if (e != cudaSuccess) return fail(b, "mpb_env_get_counters", e);
+    if (!b->counters_dev) CK(cudaMalloc(&b->counters_dev, bytes));
+    CK(cudaDeviceSynchronize());
+    k_mp_env_counters<<<(b->n_envs + 127) / 128, 128>>>(b->blocks, b->shadow, b->shadow_stride, b->cfg, b->n_envs, b->counters_dev);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_host, b->counters_dev, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1266,7 +1497,12 @@ int mpb_env_get_shadow(mpb_handle h, int env, uint8_t *zone_out, uint8_t *static
         double v[MPB_ENV_NUM_COUNTERS] = { (double)g.num_plants, (double)g.num_roads, (double)g.n_struct_tiles,
             (double)g.total_traffic, (double)g.num_step, (double)g.tilemap_error, g.reward, (double)g.done,
             (double)g.curr_funds, g.metrics[0], g.metrics[1], g.metrics[2], g.metrics[3], g.metrics[4],
-            g.metrics[5] };
+            g.metrics[5], 0.0 };
+        {   // sprite-table overflow flag of the engine (Scalars::spriteOverflow)
+            Env e;
+            if (fetch_env(b, env, e)) return -1;
+            v[15] = (double)e.s->spriteOverflow;
+        }
         memcpy(counters_out, v, sizeof(v));
     }
     return 0;

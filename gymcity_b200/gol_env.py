@@ -98,7 +98,13 @@ class _GolBase:
     def _actions_dev(self, a):
         import torch
         if not torch.is_tensor(a):
-            a = torch.as_tensor(np.asarray(a).reshape(-1), dtype=torch.int64)
+            a = np.asarray(a).reshape(-1)
+            # intsToActions[a] raises for an action outside the board (env.py:143, multi_env.py:182); device
+            # tensors cannot be checked without a sync -- the kernels skip the build for such an action
+            lim = self.map_width * self.map_width
+            if a.size and (np.abs(a).max() >= lim or (not self.classic and a.min() < 0)):
+                raise IndexError("action out of range for a %dx%d board" % (self.map_width, self.map_width))
+            a = torch.as_tensor(a, dtype=torch.int64)
         a = a.reshape(-1).to(device="cuda:%d" % self.device, dtype=torch.int64).contiguous()
         assert a.numel() == self.num_proc
         return a

@@ -55,7 +55,7 @@ class _ShadowMap:
     def _shadow(self, env=0):
         c = self._c
         n = c.MAP_X * c.MAP_Y
-        z, s, ce, k = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int16), np.zeros(15)
+        z, s, ce, k = np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.int16), np.zeros(16)
         c._ck(c._L.mpb_env_get_shadow(c._h, int(env), z.ctypes.data, s.ctypes.data, ce.ctypes.data, k.ctypes.data))
         shp = (c.MAP_X, c.MAP_Y)
         return z.reshape(shp), s.reshape(shp), ce.reshape(shp), k
@@ -78,7 +78,7 @@ class _ShadowMap:
     def counters(self, env=0):
         k = self._shadow(env)[3]
         names = ["num_plants", "num_roads", "n_struct_tiles", "total_traffic", "num_step", "tilemap_error",
-                 "reward", "done", "funds"] + METRICS
+                 "reward", "done", "funds"] + METRICS + ["sprite_overflow"]
         return dict(zip(names, [float(v) for v in k]))
 
 
@@ -175,9 +175,9 @@ class MicropolisControl:
         return self.apply_actions(self._flat(AGENT_TOOLS.index(tool), x, y), static_build, full_tools=True)
 
     def counters(self):
-        """(N, 15) array: num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error,
-        reward, done, funds, metrics[6] for every env."""
-        out = np.zeros((self.num_envs, 15), np.float64)
+        """(N, 16) array: num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error,
+        reward, done, funds, metrics[6], sprite_overflow for every env."""
+        out = np.zeros((self.num_envs, 16), np.float64)
         self._ck(self._L.mpb_env_get_counters(self._h, out.ctypes.data))
         return out
 

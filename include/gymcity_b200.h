@@ -155,7 +155,7 @@ enum mpb_env_buffer {
     MPB_ENV_REWARD,      /* float32 [n_envs]                                                     */
     MPB_ENV_DONE         /* uint8 [n_envs]                                                       */
 };
-#define MPB_ENV_NUM_COUNTERS 15
+#define MPB_ENV_NUM_COUNTERS 16
 int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools, const int8_t *tool_zone,
                       const int8_t *tool_engine, int max_step, const double *trg, const double *weight);
 int mpb_env_set_targets(mpb_handle h, const double *trg, const double *weight);   /* env.py:419-424 */
@@ -225,7 +225,11 @@ void *mpb_env_ptr(mpb_handle h, int which);
 int mpb_env_get_counters(mpb_handle h, double *out_host);
 /* Shadow map of one env (HOST buffers, any may be NULL): zone id / static flag per cell [W*H]
  * (index x*H + y), recorded centre cx*128+cy or -1, and counters {num_plants, num_roads,
- * n_struct_tiles, total_traffic, num_step, tilemap_error, reward, done, funds, metrics[6]}. */
+ * n_struct_tiles, total_traffic, num_step, tilemap_error, reward, done, funds, metrics[6],
+ * sprite_overflow}.  tilemap_error and sprite_overflow are sticky divergence flags: the first is raised
+ * where the reference's TileMap would have died with a KeyError (tilemap.py:488-491), the second when an
+ * env needed more than MAX_SPRITES sprites at once (the reference's list is unbounded); both must be 0 for
+ * a rollout to count as bit-exact. */
 int mpb_env_get_shadow(mpb_handle h, int env, uint8_t *zone_out, uint8_t *static_out, int16_t *center_out,
                        double *counters_out);
 

@@ -241,3 +241,57 @@ def test_soak_48_envs_250_ticks():
         d = diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
         assert not d, (i, d[:5])
     env.close()
+
+
+def test_masked_reset_leaves_other_envs_untouched():
+    """A partial reset (mpb_env_reset_begin / _finish with a mask) ticks only the envs it resets: the reference
+    keeps every env in its own worker, and a reset there advances nobody else (env.py:264-279)."""
+    import torch
+    n, size = 4, 16
+    seeds = np.arange(n) + 70
+    env, refs = _batch(n, size, True, 1000, seeds)
+    _finish(env, refs)
+    rng = np.random.default_rng(9)
+    for t in range(12):
+        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), False, t)
+    before = [env.micro.engine.snapshot(i) for i in range(n)]
+    mask = np.array([1, 0, 0, 1], bool)
+    env.micro.newMap(seeds + 2000, seeds + 500, mask=mask)
+    mk = np.ascontiguousarray(mask.astype(np.uint8))
+    env.micro._ck(env.micro._L.mpb_env_reset_finish(env.micro._h, mk.ctypes.data, env.micro.engine._stream()))
+    obs = env.micro.obs.cpu().numpy()
+    for i, r in enumerate(refs):
+        if mask[i]:
+            r.reset_begin(int(seeds[i]) + 2000, int(seeds[i]) + 500)
+            assert np.array_equal(r.reset_finish().astype(np.float32), obs[i]), i
+        else:
+            assert not diff_snapshots(before[i], env.micro.engine.snapshot(i)), i
+    for t in range(12):
+        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), False, 100 + t)
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+    env.close()
+
+
+@pytest.mark.parametrize("unit_mask", ["0x0d01", "0xffff", "0x0100"])
+def test_queue_scheduled_frames_match_oracle(unit_mask, monkeypatch):
+    """The queue-scheduled frame kernel (k_mp_frames_q), forced onto a small batch: 40 envs share one CTA's ready
+    queue (more envs than warps, so envs are re-queued and change warps), different unit boundaries."""
+    monkeypatch.setenv("MPB_QMODE", "1")
+    monkeypatch.setenv("MPB_Q_MIN_ENVS", "1")
+    monkeypatch.setenv("MPB_Q_CTAS", "1")
+    monkeypatch.setenv("MPB_Q_UNIT_MASK", unit_mask)
+    if unit_mask == "0x0100":
+        monkeypatch.setenv("MPB_HEAVY_DIV", "4")        # the 10 most expensive envs run unqueued to the end of a launch
+    n, size, steps = 40, 16, 40
+    seeds = np.arange(n) + 300
+    env, refs = _batch(n, size, True, 1000, seeds)
+    _finish(env, refs)
+    rng = np.random.default_rng(11)
+    for t in range(steps):
+        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), bool(rng.random() < 0.2), t)
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+    ctr = env.micro.counters()
+    assert not ctr[:, 5].any() and not ctr[:, 15].any()
+    env.close()
