@@ -19,6 +19,12 @@
 
 using namespace mp;
 
+// mp_simt.cu: the frames of a launch with one THREAD per env (the engine headers compiled with Coop::n = 1)
+extern "C" int mps_launch_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
+                                 int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm,
+                                 int gstride, int goff, int gcount, unsigned int *prof, int prof_off, const uint8_t *mask,
+                                 void *stream);
+
 namespace {
 
 // Kernels other than k_mp_frames: one warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's
@@ -48,7 +54,8 @@ struct MpBatch {
     int sms;                  // SMs of the device
     int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
     int qmode;                // frames run by the queue-scheduled kernel (k_mp_frames_q) when the launch has >= q_min_envs envs
-    int q_min_envs, q_max_k, q_waves, q_unit_mask, q_ctas;
+    int q_min_envs, q_max_k, q_waves, q_unit_mask, q_ctas, q_window;
+    int simt;                 // frames of the non-heavy groups run one THREAD per env (mp_simt.cu)
     unsigned int *prof;       // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
     cudaError_t launch_err;   // first error of a launch enqueued by launch_frames since the last check
     int32_t *xt_rnd; size_t xt_rnd_bytes;    // device buffer of mpb_env_extinguish's draws (grown on demand)
@@ -263,122 +270,135 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
 // ---- queue-scheduled frame kernel ----------------------------------------------------------------
 // k_mp_frames<32> keeps the 32 warps of an SM in the same simulation phase with a CTA barrier per frame, and
 // pays for it: every frame lasts as long as its slowest env (ncu r01: 42 % of all warp cycles stalled at the
-// barrier).  Here one CTA (32 warps, one per SM) owns K >> 32 envs and the warps take env-frames from a FIFO of
-// ready envs in shared memory: a warp pops an env, runs one UNIT of its frames (a run of phases that ends after a
-// phase of `unit_mask`, e.g. the eight map-scan phases), and pushes it back.  Because the queue is first in,
-// first out, every env finishes unit u before any env starts unit u + 2, so the warps of the SM are still in
-// (nearly) the same code -- the lockstep the instruction caches need -- but nobody waits: a slow env only
-// occupies the warp that runs it.  Envs flagged heavy (the first `heavy_slots` of the cost order: flood and fire
+// barrier).  Here one CTA (32 warps, one per SM) owns K >> 32 envs, keeps a WINDOW of W of them active, and the
+// warps take env-frames from a FIFO of ready window slots in shared memory: a warp pops a slot, runs one UNIT of
+// its env's frames (a run of phases that ends after a phase of `unit_mask`, e.g. the eight map-scan phases), and
+// pushes it back.  Because the queue is first in, first out, every env of the window finishes unit u before any
+// starts unit u + 2, so the warps of the SM are still in (nearly) the same code -- the lockstep the instruction
+// caches need -- but nobody waits: a slow env only occupies the warp that runs it.  An env that has run its
+// frames of the launch retires: its scalars go back to its block and the next env of the CTA's list takes the
+// slot.  W bounds the data the SM cycles through between two visits of the same env (the L1 holds the hot lines
+// of a few dozen envs, not of hundreds); K >> W means there is always a successor, so the window never drains
+// before the end of the launch.  Envs flagged heavy (the first `heavy_slots` of the cost order: flood and fire
 // fields, 5-10 x the mean) are run to the end of the launch by the warp that pops them: they are the critical
 // path and must not queue behind anyone.
-//   Queue: bounded MPMC ring (tickets + per-slot sequence numbers).  At most K + 32 entries are ever in
-// flight (K envs, 32 exit sentinels pushed by the warp that retires the last env), QN >= K + 32.
-constexpr int MPQ_MAX_K = 448;      // envs per CTA the shared-memory budget allows (448 * 480 B + queue < 227 KB)
-constexpr int MPQ_QN = 512;         // ring size, power of two >= MPQ_MAX_K + 32
+//   Queue: bounded MPMC ring (tickets + per-slot sequence numbers).  At most W + 32 entries are ever in
+// flight (W slots, 32 exit sentinels pushed by the warp that retires the last env), QN >= W + 32.
+constexpr int MPQ_MAX_W = 224;      // window slots the ring and the shared-memory budget allow
+constexpr int MPQ_QN = 256;         // ring size, power of two >= MPQ_MAX_W + 32
+constexpr int MPQ_SLOT_BYTES = SCAL_BYTES + 4 + 4 + 2 + 2 + 1;
 
 struct QArgs {
     uint8_t *blocks; const uint16_t *anim; int n_envs, first, count, animate_before, respect_passes;
     unsigned long long *cycles; unsigned int *cost; const int *perm; int gstride, goff, gcount;
     int K;                   // envs per CTA: CTA c owns ranks c, c + gridDim.x, ... (K of them)
+    int W;                   // window: envs of a CTA that are in flight at a time
     int unit_mask;           // bit p: a unit ends after phase p
     int heavy_slots;         // schedule slots below this are run to the end of the launch without re-queueing
     unsigned int *prof; int prof_off; const uint8_t *mask;
 };
 
-__device__ __forceinline__ unsigned int q_ld(const volatile unsigned int *p) { return *p; }
+struct QState {                      // shared memory of k_mp_frames_q (static part)
+    Env env[32];
+    int red[8 * 32];
+    int q[MPQ_QN];
+    unsigned int seq[MPQ_QN];
+    unsigned int head, tail, next, active;
+};
+
+__device__ __forceinline__ void q_push(QState &Q, int item)           // one lane
+{
+    const unsigned int p = atomicAdd(&Q.tail, 1u), slot = p & (MPQ_QN - 1);
+    *reinterpret_cast<volatile int *>(&Q.q[slot]) = item;
+    __threadfence_block();
+    *reinterpret_cast<volatile unsigned int *>(&Q.seq[slot]) = p + 1;
+}
+__device__ __forceinline__ int q_pop(QState &Q)                       // one lane; waits for its ticket's entry
+{
+    const unsigned int t = atomicAdd(&Q.head, 1u), slot = t & (MPQ_QN - 1);
+    while (*reinterpret_cast<volatile unsigned int *>(&Q.seq[slot]) != t + 1) __nanosleep(64);
+    return *reinterpret_cast<volatile int *>(&Q.q[slot]);
+}
 
 __global__ void __launch_bounds__(1024, 1) k_mp_frames_q(const QArgs a)
 {
-    __shared__ Env s_env[32];
-    __shared__ int red[8 * 32];
-    __shared__ int s_q[MPQ_QN];
-    __shared__ unsigned int s_seq[MPQ_QN];
-    __shared__ unsigned int s_head, s_tail, s_ndone, s_nlive;
-    const int K = a.K;
-    // dynamic shared memory: K scalar blocks, then the per-env bookkeeping
+    __shared__ QState Q;
+    const int W = a.W;
+    // dynamic shared memory: W scalar blocks, then the per-slot bookkeeping
     uint32_t *const scal = reinterpret_cast<uint32_t *>(mp_dyn_smem);
-    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)K * SCAL_BYTES);
-    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + K);
-    short *const s_fdone = reinterpret_cast<short *>(s_busy + K);
-    short *const s_nrun = s_fdone + K;
-    unsigned char *const s_sticky = reinterpret_cast<unsigned char *>(s_nrun + K);
+    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)W * SCAL_BYTES);
+    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + W);
+    short *const s_fdone = reinterpret_cast<short *>(s_busy + W);
+    short *const s_nrun = s_fdone + W;
+    unsigned char *const s_sticky = reinterpret_cast<unsigned char *>(s_nrun + W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Env &e = s_env[warp];
-    for (int i = threadIdx.x; i < MPQ_QN; i += blockDim.x) s_seq[i] = 0;
-    if (lane == 0) { e.anim = a.anim; e.c.red = red + warp * 8; }     // also for warps that stage no env below
-
-    // ---- prologue: stage the scalars of the CTA's envs, tickEngine's animateTiles, frames to run
-    for (int k = warp; k < K; k += 32) {
-        const long long t0 = clock64();
-        const int rank = blockIdx.x + k * gridDim.x;
-        const int slot = rank * a.gstride + a.goff;
-        bool live = rank < a.gcount && slot < a.n_envs;
-        int env = 0;
-        if (live) {
-            env = a.perm ? a.perm[slot] : slot;
-            if (a.mask && !a.mask[env]) live = false;
-        }
-        int nrun = 0;
-        if (live) {
-            bind_env_of(e, a.blocks, env, a.anim, red, scal + (size_t)k * SCAL_WORDS);
-            if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
-            nrun = a.count;
-            if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
-        }
-        __syncwarp();
-        if (lane == 0) {
-            s_envid[k] = live ? env : -1;
-            s_nrun[k] = (short)nrun;
-            s_fdone[k] = 0;
-            s_sticky[k] = (unsigned char)(live && slot < a.heavy_slots);
-            s_busy[k] = (unsigned int)(clock64() - t0);
-        }
-    }
+    Env &e = Q.env[warp];
+    for (int i = threadIdx.x; i < MPQ_QN; i += blockDim.x) Q.seq[i] = 0;
+    if (threadIdx.x == 0) { Q.head = 0; Q.tail = 0; Q.next = 0; Q.active = 0; }
+    if (lane == 0) { e.anim = a.anim; e.c.red = Q.red + warp * 8; }
     __syncthreads();
-    if (warp == 0) {                                   // the ready queue, in schedule (heavy-first) order
-        unsigned int base = 0;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + lane;
-            const bool ready = k < K && s_envid[k] >= 0 && s_nrun[k] > 0;
-            const unsigned int m = __ballot_sync(0xffffffffu, ready);
-            if (ready) {
-                const unsigned int pos = base + __popc(m & ((1u << lane) - 1u));
-                s_q[pos] = k;
-                s_seq[pos] = pos + 1;
+
+    // [ALL lanes of a warp] the next env of the CTA's list moves into window slot `ws`: scalars staged,
+    // tickEngine's animateTiles, frames to run in this launch.  False when the list is exhausted.
+    auto admit = [&](int ws) -> bool {
+        for (;;) {
+            const long long t0 = clock64();
+            int k = 0;
+            if (lane == 0) k = (int)atomicAdd(&Q.next, 1u);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= a.K) return false;
+            const int rank = blockIdx.x + k * gridDim.x;
+            const int slot = rank * a.gstride + a.goff;
+            if (rank >= a.gcount || slot >= a.n_envs) continue;
+            const int env = a.perm ? a.perm[slot] : slot;
+            if (a.mask && !a.mask[env]) continue;
+            uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
+            bind_env_of(e, a.blocks, env, a.anim, Q.red, sw);
+            if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+            int nrun = a.count;
+            if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
+            if (nrun <= 0) { unstage_scalars(e, sw); __syncwarp(); continue; }
+            if (lane == 0) {
+                s_envid[ws] = env;
+                s_nrun[ws] = (short)nrun;
+                s_fdone[ws] = 0;
+                s_sticky[ws] = (unsigned char)(slot < a.heavy_slots);
+                s_busy[ws] = (unsigned int)(clock64() - t0);
             }
-            base += __popc(m);
+            __syncwarp();
+            return true;
         }
-        if (base == 0) {                               // nothing to run: every warp takes an exit sentinel
-            s_q[lane] = -1;
-            s_seq[lane] = lane + 1;
+    };
+
+    for (int ws = warp; ws < W; ws += 32)
+        if (admit(ws) && lane == 0) {
+            atomicAdd(&Q.active, 1u);
+            __threadfence_block();
+            q_push(Q, ws);
         }
-        if (lane == 0) { s_head = 0; s_tail = base ? base : 32; s_nlive = base; s_ndone = 0; }
-    }
+    __syncthreads();
+    if (warp == 0 && Q.active == 0) q_push(Q, -1 - lane);      // nothing to run: every warp takes an exit sentinel
     __syncthreads();
 
     // ---- the warps drain the queue
     for (;;) {
-        int k = 0;
-        if (lane == 0) {
-            const unsigned int t = atomicAdd(&s_head, 1u);
-            const unsigned int slot = t & (MPQ_QN - 1);
-            while (q_ld(&s_seq[slot]) != t + 1) __nanosleep(64);
-            k = *reinterpret_cast<volatile int *>(&s_q[slot]);
-        }
+        int ws = 0;
+        if (lane == 0) ws = q_pop(Q);
         __threadfence_block();
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k < 0) break;
+        ws = __shfl_sync(0xffffffffu, ws, 0);
+        if (ws < 0) break;
         const unsigned int t0 = (unsigned int)clock64();
-        const int env = s_envid[k];
+        const int env = s_envid[ws];
+        uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
         if (lane == 0) {
             bind_env(e, a.blocks + (size_t)env * ENV_STRIDE);
-            e.s = reinterpret_cast<Scalars *>(scal + (size_t)k * SCAL_WORDS);
+            e.s = reinterpret_cast<Scalars *>(sw);
         }
         __syncwarp();
-        int f = s_fdone[k];
-        const int n = s_nrun[k];
-        const bool sticky = s_sticky[k] != 0;
+        int f = s_fdone[ws];
+        const int n = s_nrun[ws];
+        const bool sticky = s_sticky[ws] != 0;
         if (e.s->simSpeed == 3 && !e.s->initSimLoad) {
             // the gym path's common case: every frame simulates, speedCycle / phaseCycle are plain counters
             int phase = e.s->phaseCycle & 15, sc = e.s->speedCycle, ran;
@@ -403,38 +423,148 @@ __global__ void __launch_bounds__(1024, 1) k_mp_frames_q(const QArgs a)
         }
         __threadfence_block();
         __syncwarp();
-        if (lane == 0) {
-            s_fdone[k] = (short)f;
-            s_busy[k] += (unsigned int)clock64() - t0;
-            __threadfence_block();
-            if (f < n) {
-                const unsigned int p = atomicAdd(&s_tail, 1u), slot = p & (MPQ_QN - 1);
-                *reinterpret_cast<volatile int *>(&s_q[slot]) = k;
+        if (f < n) {                                           // back into the queue
+            if (lane == 0) {
+                s_fdone[ws] = (short)f;
+                s_busy[ws] += (unsigned int)clock64() - t0;
                 __threadfence_block();
-                *reinterpret_cast<volatile unsigned int *>(&s_seq[slot]) = p + 1;
-            } else if (atomicAdd(&s_ndone, 1u) + 1 == s_nlive) {
-                for (int i = 0; i < 32; i++) {         // the last env is done: one exit sentinel per warp
-                    const unsigned int p = atomicAdd(&s_tail, 1u), slot = p & (MPQ_QN - 1);
-                    *reinterpret_cast<volatile int *>(&s_q[slot]) = -1;
-                    __threadfence_block();
-                    *reinterpret_cast<volatile unsigned int *>(&s_seq[slot]) = p + 1;
-                }
+                q_push(Q, ws);
             }
+            continue;
+        }
+        // the env has run its frames: retire it, and let the next env of the list have the slot
+        unstage_scalars(e, sw);
+        if (lane == 0) {
+            const unsigned int busy = s_busy[ws] + ((unsigned int)clock64() - t0);
+            if (a.cycles) a.cycles[env] += busy;
+            if (a.cost) a.cost[env] += busy >> 8;
+        }
+        __syncwarp();
+        const bool more = admit(ws);
+        if (lane == 0) {
+            __threadfence_block();
+            if (more) q_push(Q, ws);
+            else if (atomicSub(&Q.active, 1u) == 1u)
+                for (int i = 0; i < 32; i++) q_push(Q, -1);    // the last env is done: one exit sentinel per warp
         }
     }
-    __syncthreads();
+}
 
-    // ---- epilogue: scalars back to the blocks, per-env cycle counts for the next schedule
-    for (int k = warp; k < K; k += 32) {
-        const int env = s_envid[k];
-        if (env < 0) continue;
-        uint32_t *gs = reinterpret_cast<uint32_t *>(a.blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
-        const uint32_t *sw = scal + (size_t)k * SCAL_WORDS;
-        for (int i = lane; i < SCAL_WORDS; i += 32) gs[i] = sw[i];
-        if (lane == 0) {
-            if (a.cycles) a.cycles[env] += s_busy[k];
-            if (a.cost) a.cost[env] += s_busy[k] >> 8;
+// ---- unit-lockstep frame kernel with dynamic balancing ---------------------------------------------
+// The queue above keeps nobody waiting but only loosely in step, and measured slower than the barrier kernel for
+// exactly that reason (profiles/r02_notes.md: the smaller the window, the freer the warps run, the slower).  This
+// kernel keeps k_mp_frames<32>'s strict lockstep -- a CTA barrier between units -- but hands the work of a unit out
+// dynamically: one CTA per SM owns K envs, works on a window of W >= 32 of them at a time, and inside a unit (a run
+// of frames that ends after a phase of `unit_mask`) the 32 warps take window slots from a shared counter, most
+// expensive env first.  A unit then lasts max(longest env, sum / 32) instead of the longest env of every warp's
+// fixed share; the barrier wait shrinks to the drain at the end of each unit.
+__global__ void __launch_bounds__(1024, 1) k_mp_frames_u(const QArgs a)
+{
+    __shared__ Env s_env[32];
+    __shared__ int red[8 * 32];
+    __shared__ unsigned int s_ctr[2];
+    __shared__ int s_ph0;
+    const int W = a.W;
+    uint32_t *const scal = reinterpret_cast<uint32_t *>(mp_dyn_smem);
+    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)W * SCAL_BYTES);
+    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + W);
+    short *const s_nrun = reinterpret_cast<short *>(s_busy + W);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Env &e = s_env[warp];
+    if (lane == 0) { e.anim = a.anim; e.c.red = red + warp * 8; }
+    for (int w0 = 0; w0 < a.K; w0 += W) {
+        const int nw = min(W, a.K - w0);
+        // ---- stage the window: scalars into shared memory, tickEngine's animateTiles, frames to run
+        for (int ws = warp; ws < nw; ws += 32) {
+            const long long t0 = clock64();
+            const int k = w0 + ws;
+            const int rank = blockIdx.x + k * gridDim.x;
+            const int slot = rank * a.gstride + a.goff;
+            bool live = rank < a.gcount && slot < a.n_envs;
+            int env = 0;
+            if (live) {
+                env = a.perm ? a.perm[slot] : slot;
+                if (a.mask && !a.mask[env]) live = false;
+            }
+            int nrun = 0;
+            if (live) {
+                bind_env_of(e, a.blocks, env, a.anim, red, scal + (size_t)ws * SCAL_WORDS);
+                if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
+                nrun = a.count;
+                if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_envid[ws] = live ? env : -1;
+                s_nrun[ws] = (short)nrun;
+                s_busy[ws] = (unsigned int)(clock64() - t0);
+                if (ws == 0) s_ph0 = live ? (e.s->initSimLoad ? 0 : (e.s->phaseCycle & 15)) : 0;
+            }
         }
+        if (threadIdx.x == 0) { s_ctr[0] = 0; s_ctr[1] = 0; }
+        __syncthreads();
+        // ---- units: [f, f + len) ends after a phase of unit_mask (the window's nominal phase: slot 0's)
+        const int ph0 = s_ph0;
+        int u = 0;
+        for (int f = 0; f < a.count; u++) {
+            int len = 1;
+            while (f + len < a.count && !((a.unit_mask >> ((ph0 + f + len - 1) & 15)) & 1)) len++;
+            unsigned int *ctr = &s_ctr[u & 1];
+            for (;;) {
+                int ws = 0;
+                if (lane == 0) ws = (int)atomicAdd(ctr, 1u);
+                ws = __shfl_sync(0xffffffffu, ws, 0);
+                if (ws >= nw) break;
+                const int env = s_envid[ws];
+                const int n = min((int)s_nrun[ws], f + len);          // this env's frames end here in this unit
+                if (env < 0 || f >= n) continue;
+                const unsigned int t0 = (unsigned int)clock64();
+                if (lane == 0) {
+                    bind_env(e, a.blocks + (size_t)env * ENV_STRIDE);
+                    e.s = reinterpret_cast<Scalars *>(scal + (size_t)ws * SCAL_WORDS);
+                }
+                __syncwarp();
+                int ff = f;
+                if (e.s->simSpeed == 3 && !e.s->initSimLoad) {
+                    // the gym path's common case: every frame simulates, speedCycle / phaseCycle are plain counters
+                    int phase = e.s->phaseCycle & 15, sc = e.s->speedCycle;
+                    do {
+                        const unsigned int tf = (unsigned int)clock64();
+                        sim_phase(e, phase);
+                        phase = (phase + 1) & 15;
+                        sc = (sc + 1) & 1023;
+                        sim_sprites(e);
+                        if (a.prof && lane == 0)
+                            a.prof[(size_t)env * 256 + a.prof_off + a.first + ff] = (unsigned int)clock64() - tf;
+                    } while (++ff < n);
+                    if (lane == 0) { e.s->phaseCycle = (int16_t)phase; e.s->speedCycle = (int16_t)sc; }
+                } else {
+                    do {
+                        const int ran = sim_loop_head(e);
+                        sim_loop_tail(e, ran);
+                    } while (++ff < n);
+                }
+                __syncwarp();
+                if (lane == 0) s_busy[ws] += (unsigned int)clock64() - t0;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_ctr[u & 1] = 0;                    // used again by the unit after the next one
+            f += len;
+        }
+        // ---- scalars back to the blocks, per-env cycle counts for the next schedule
+        for (int ws = warp; ws < nw; ws += 32) {
+            const int env = s_envid[ws];
+            if (env < 0) continue;
+            uint32_t *gs = reinterpret_cast<uint32_t *>(a.blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
+            const uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
+            for (int i = lane; i < SCAL_WORDS; i += 32) gs[i] = sw[i];
+            if (lane == 0) {
+                if (a.cycles) a.cycles[env] += s_busy[ws];
+                if (a.cost) a.cost[env] += s_busy[ws] >> 8;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -673,6 +803,12 @@ void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, i
                    const int *perm, int gstride, int goff, int gcount, const uint8_t *mask, int prof_off = 0, bool heavy = false)
 {
     if (gcount <= 0) return;
+    if (b->simt && !heavy && count > 0) {
+        const int rc = mps_launch_frames(b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles,
+                                         b->cost, perm, gstride, goff, gcount, b->prof, prof_off, mask, st);
+        if (rc != 0 && b->launch_err == cudaSuccess) b->launch_err = (cudaError_t)rc;
+        return;
+    }
     if (b->qmode && !heavy && gcount >= b->q_min_envs) {
         // CTAs: whole waves of one CTA per SM; envs per CTA as even as possible
         int waves = b->q_waves > 0 ? b->q_waves : 1;
@@ -683,11 +819,13 @@ void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, i
         a.animate_before = animate_before; a.respect_passes = respect_passes; a.cycles = b->cycles; a.cost = b->cost;
         a.perm = perm; a.gstride = gstride; a.goff = goff; a.gcount = gcount;
         a.K = (gcount + ctas - 1) / ctas;
+        a.W = a.K < b->q_window ? a.K : b->q_window;
         a.unit_mask = b->q_unit_mask;
         a.heavy_slots = (b->use_sched && b->heavy_div > 0 && gstride == 1 && goff == 0) ? b->n_envs / b->heavy_div : 0;
         a.prof = b->prof; a.prof_off = prof_off; a.mask = mask;
-        const size_t smem = (size_t)a.K * (SCAL_BYTES + 4 + 4 + 2 + 2 + 1) + 16;
-        k_mp_frames_q<<<ctas, 1024, smem, st>>>(a);
+        const size_t smem = (size_t)a.W * MPQ_SLOT_BYTES + 16;
+        if (b->qmode == 2) k_mp_frames_u<<<ctas, 1024, smem, st>>>(a);
+        else k_mp_frames_q<<<ctas, 1024, smem, st>>>(a);
     } else {
 #define MP_FRAMES_ARGS b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles, b->cost, perm, \
                        gstride, goff, gcount, b->scan_block, b->prof, prof_off, mask
@@ -724,7 +862,7 @@ GroupGeom group_geom(const MpBatch *b, int G, int g)
 #define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
 // env groups of an env-step: the queue-scheduled kernel balances inside each SM and takes the whole batch as
 // one group; the lockstep kernel overlaps the launch tails of b->groups groups on their own streams
-int step_groups(const MpBatch *b) { return (b->qmode && b->n_envs >= b->q_min_envs) ? 1 : b->groups; }
+int step_groups(const MpBatch *b) { return (b->qmode == 1 && b->n_envs >= b->q_min_envs) ? 1 : b->groups; }
 
 int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8_t *mask, int G = 1, int g = 0)
 {
@@ -808,17 +946,22 @@ mpb_handle mpb_create(int n_envs, int device)
         // census / decay pair (10), the power scan (11) and the overlay scans + phase 0 (0).
         b->qmode = 1;
         b->q_min_envs = sms * 48;
-        b->q_max_k = 256;
+        b->q_max_k = 1 << 20;
+        b->q_window = 64;
         b->q_waves = 1;
         b->q_unit_mask = (1 << 8) | (1 << 10) | (1 << 11) | (1 << 0);
         if (const char *fp = getenv("MPB_QMODE")) b->qmode = atoi(fp);
+        if (const char *fp = getenv("MPB_SIMT")) b->simt = atoi(fp);
         if (const char *fp = getenv("MPB_Q_MIN_ENVS")) b->q_min_envs = atoi(fp);
-        if (const char *fp = getenv("MPB_Q_MAX_K")) { int v = atoi(fp); if (v >= 1 && v <= MPQ_MAX_K) b->q_max_k = v; }
+        if (const char *fp = getenv("MPB_Q_MAX_K")) { int v = atoi(fp); if (v >= 1) b->q_max_k = v; }
+        if (const char *fp = getenv("MPB_Q_WINDOW")) { int v = atoi(fp); if (v >= 1 && v <= MPQ_MAX_W) b->q_window = v; }
         if (const char *fp = getenv("MPB_Q_WAVES")) b->q_waves = atoi(fp);
         if (const char *fp = getenv("MPB_Q_CTAS")) b->q_ctas = atoi(fp);          // tests: a fixed number of CTAs
         if (const char *fp = getenv("MPB_Q_UNIT_MASK")) b->q_unit_mask = (int)strtol(fp, NULL, 0);
         cudaFuncSetAttribute(k_mp_frames_q, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MPQ_MAX_K * (SCAL_BYTES + 13) + 16);
+                             MPQ_MAX_W * MPQ_SLOT_BYTES + 16);
+        cudaFuncSetAttribute(k_mp_frames_u, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MPQ_MAX_W * MPQ_SLOT_BYTES + 16);
     }
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);

@@ -896,6 +896,9 @@ MPQ void do_rail(Env &e, int x, int y)
 MPP void scan_tile(Env &e, int idx)
 {
     int mv = e.map()[idx], tile = mv & LOMASK;
+#if defined(MP_SIMT)
+    S.work += (mv & ZONEBIT) ? 8u : 1u;
+#endif
     int x = idx / WORLD_H, y = idx - x * WORLD_H;
     if (tile < T_ROADBASE) {
         if (tile >= T_FIREBASE) {
@@ -985,7 +988,7 @@ MPD int tile_kind(const Env &e, int v)
     return TK_INERT;
 }
 
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
 // n steps of the engine's LCG (random.cpp:88-100) in O(log n): step^(2^j) is the affine map
 // x -> A_j x + C_j with A_{j+1} = A_j^2, C_{j+1} = (A_j + 1) C_j; n < 256.
 struct LcgPow { uint32_t a[8], c[8]; };
@@ -1144,7 +1147,7 @@ MPP void map_scan(Env &e, int x1, int x2)
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
     const int w0 = i0 >> 5, w1 = (i1 - 1) >> 5;
     int pos = i0;                                   // first tile not yet passed by the scan
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     const int lane = e.c.tid;
     {   // one look at the strip's words (<= 64): nothing to visit (the usual case outside the build
         // window) ends the phase here; a dense range (flood / radiation / fire field) goes to the
@@ -1201,8 +1204,12 @@ MPP void map_scan(Env &e, int x1, int x2)
             if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
             if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
             if (!m) break;
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs(m) - 1;
+#else
             int b = 0;
             while (!((m >> b) & 1u)) b++;
+#endif
             const int t = w * 32 + b;
             scan_tile(e, t);
             pos = t + 1;
@@ -1242,7 +1249,7 @@ MPD void scroll_history(Env &e, int lo, int hi)
 // [ALL] simulate.cpp:712-780 take10Census
 MPN void take10_census(Env &e)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     scroll_history(e, 0, 118);
 #else
     for (int x = 118; x >= 0; x--) {
@@ -1274,7 +1281,7 @@ MPN void take10_census(Env &e)
 // [ALL] simulate.cpp:784-826 take120Census
 MPN void take120_census(Env &e)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     scroll_history(e, 120, 238);
 #else
     for (int x = 238; x >= 120; x--) {
@@ -1384,9 +1391,10 @@ MPD uint8_t dec_traffic_cell(int z)
 MPN void dec_traffic_map(Env &e)
 {
 #if defined(__CUDA_ARCH__)
-    // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit lane with byte-SIMD:
+    // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit word with byte-SIMD:
     // z - (z > 200 ? 34 : 24) saturated at 0 is exactly the reference's three-way rule.
     uint4 *q = reinterpret_cast<uint4 *>(e.traffic());
+#if MP_WARP_COOP
     uint4 v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -1405,6 +1413,18 @@ MPN void dec_traffic_map(Env &e)
             q[i] = r;
         }
     }
+#else
+    MP_NOUNROLL for (int i = 0; i < 188; i++) {
+        const uint4 v = q[i];
+        if (!(v.x | v.y | v.z | v.w)) continue;
+        uint4 r;
+        r.x = __vsubus4(v.x, (__vcmpgtu4(v.x, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+        r.y = __vsubus4(v.y, (__vcmpgtu4(v.y, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+        r.z = __vsubus4(v.z, (__vcmpgtu4(v.z, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+        r.w = __vsubus4(v.w, (__vcmpgtu4(v.w, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
+        q[i] = r;
+    }
+#endif
 #else
     for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic()[i] = dec_traffic_cell(e.traffic()[i]);
 #endif
@@ -1501,7 +1521,7 @@ MPN bool power_scan_walk(Env &e)
     return no_seeds || numPower + 256 < maxPower;
 }
 
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
 // [ALL] doPowerScan as a lane-parallel flood fill over bitmaps, for the case in which the literal walk's
 // only order-dependent feature -- the numPower cut-off -- cannot trigger.  numPower counts one step per
 // newly powered tile plus one per pop, and a tile is pushed at most three times (once per neighbour it
@@ -1594,7 +1614,7 @@ MPN void do_power_scan(Env &e, bool set_new_power = true)
     for (int i = e.c.tid; i < POWER_WORDS; i += e.c.n) e.power()[i] = 0;
     e.c.sync();
     bool filled = false;
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     if (S.powerStackPointer > 0) filled = power_scan_parallel(e);
 #endif
     if (e.c.lead()) {
@@ -1662,7 +1682,7 @@ MPD void box_add(CellBox &b, int x, int y)
 }
 MPD void box_reduce(Env &e, CellBox &b)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     for (int o = 16; o > 0; o >>= 1) {
         b.x0 = min(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, o));
         b.x1 = max(b.x1, __shfl_xor_sync(0xffffffffu, b.x1, o));
@@ -1719,7 +1739,7 @@ MPD int pollution_value(int loc)                                    // scan.cpp:
 // block-wide integer sum of per-thread partials into e.c.red[slot] (valid after the barrier)
 MPD void coop_add(Env &e, int slot, int v)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     MP_NOUNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (e.c.lead()) e.c.red[slot] += v;
 #else
@@ -1739,7 +1759,7 @@ MPD void coop_add(Env &e, int slot, int v)
 MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool nonzero_only, int *count, int *total,
                      int lo = 0, int hi = N2)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     const int lane = e.c.tid;
     const unsigned lt = (1u << lane) - 1u;
     int vmax = 0, site = -1, cnt = 0, tot = 0;
@@ -1791,7 +1811,7 @@ MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool non
     return site;
 #else
     int vmax = 0, site = -1, cnt = 0, tot = 0;
-    for (int i = 0; i < N2; i++) {
+    for (int i = lo; i < tmin(hi, N2); i++) {
         const int z = vals[i];
         if ((valid && !valid[i]) || (nonzero_only && !z)) continue;
         cnt++; tot += z;
@@ -1914,7 +1934,7 @@ MPN void crime_scan(Env &e)
             if (j == (N2 + 15) / 16 - 1) any = v.x | v.y;        // the last word pair is padding (3000 = 187 * 16 + 8)
             if (any) { c0 = tmin(c0, (j * 16) / H2); c1 = tmax(c1, tmin((j * 16 + 15) / H2, W2 - 1)); }
         }
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
         for (int o = 16; o > 0; o >>= 1) {
             c0 = min(c0, __shfl_xor_sync(0xffffffffu, c0, o));
             c1 = max(c1, __shfl_xor_sync(0xffffffffu, c1, o));
@@ -2171,7 +2191,7 @@ MPN void city_evaluation(Env &e)
 // value of lane 0 for every lane
 MPD int coop_bcast(Env &e, int v)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     return __shfl_sync(0xffffffffu, v, 0);
 #else
     (void)e;

@@ -674,7 +674,7 @@ MPN void make_earthquake(Env &e)
 // and are committed as 2 draws each, that one iteration is replayed by the serial lane, and so on.
 MPN void make_earthquake_coop(Env &e)
 {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
     int strength = 0;
     if (e.c.lead()) strength = rnd(e, 700) + 300;
     strength = coop_bcast(e, strength);

@@ -46,6 +46,15 @@ inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned
 #define MP_NOUNROLL
 #endif
 
+// MP_WARP_COOP: the code is compiled for the device with one WARP per env (lanes cooperate through shuffles,
+// ballots and warp barriers).  Otherwise one THREAD runs an env on its own: the host harness under tests/, and
+// the thread-per-env device build (-DMP_SIMT, mp_simt.cu) in which the 32 lanes of a warp run 32 different envs.
+#if defined(__CUDA_ARCH__) && !defined(MP_SIMT)
+#define MP_WARP_COOP 1
+#else
+#define MP_WARP_COOP 0
+#endif
+
 namespace mp {
 
 constexpr int WORLD_W = 120, WORLD_H = 100, NTILES = WORLD_W * WORLD_H;
@@ -110,7 +119,10 @@ struct Scalars {
     // bulk map / state write happened.  powerPure: the
     // last scan followed a quiet interval (all its seeds were current plants) and stayed clear of the
     // capacity cut-off.  A scan that finds both set would recompute the grid it already has.
-    uint8_t powerQuiet, powerPure, pad_[6];
+    uint8_t powerQuiet, powerPure, pad_[2];
+    // derived, not part of the reference state: tiles mapScan visited since the schedule was last rebuilt (zone
+    // centres count 8) -- the cost key of the thread-per-env kernel, whose lanes share one clock
+    uint32_t work;
     int16_t curMapStack[MAX_TRAFFIC_DISTANCE + 2];   // packed x*100+y, entries 1..pointer
 };
 static_assert(sizeof(Scalars) % 8 == 0, "Scalars is copied to shared memory word by word");
@@ -162,7 +174,7 @@ struct EnvLayout {
 struct LaneId {
     MPD operator int() const
     {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
         return (int)(threadIdx.x & 31u);
 #else
         return 0;
@@ -171,15 +183,15 @@ struct LaneId {
 };
 struct Coop {
     LaneId tid;
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(MP_SIMT)
     static constexpr int n = 32;
 #else
     static constexpr int n = 1;
 #endif
-    int *red;       // >= 8 ints of shared scratch per env (device) / plain memory (host)
+    int *red;       // >= 8 ints of scratch per env: shared memory (warp per env) / plain memory (thread per env, host)
     MPD void sync() const
     {
-#if defined(__CUDA_ARCH__)
+#if MP_WARP_COOP
         __syncwarp();
 #endif
     }

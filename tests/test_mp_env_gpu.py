@@ -273,16 +273,21 @@ def test_masked_reset_leaves_other_envs_untouched():
     env.close()
 
 
-@pytest.mark.parametrize("unit_mask", ["0x0d01", "0xffff", "0x0100"])
-def test_queue_scheduled_frames_match_oracle(unit_mask, monkeypatch):
-    """The queue-scheduled frame kernel (k_mp_frames_q), forced onto a small batch: 40 envs share one CTA's ready
-    queue (more envs than warps, so envs are re-queued and change warps), different unit boundaries."""
-    monkeypatch.setenv("MPB_QMODE", "1")
+@pytest.mark.parametrize("qmode", ["1", "2"])
+@pytest.mark.parametrize("unit_mask,window,heavy_div", [("0x0d01", 64, 64), ("0xffff", 12, 64), ("0x0100", 40, 4),
+                                                        ("0x0d01", 5, 8)])
+def test_queue_scheduled_frames_match_oracle(unit_mask, window, heavy_div, qmode, monkeypatch):
+    """The queue-scheduled frame kernel (k_mp_frames_q), forced onto a small batch: 40 envs share ONE CTA's ready
+    queue (envs are re-queued and change warps), with different unit boundaries, windows smaller than the env list
+    (envs retire and their successors take the slot) and smaller than the warp count, and heavy envs that run
+    unqueued to the end of a launch."""
+    monkeypatch.setenv("MPB_QMODE", qmode)          # 1: FIFO of ready envs, 2: unit lockstep with a shared work counter
+    monkeypatch.setenv("MPB_GROUPS", "1")
     monkeypatch.setenv("MPB_Q_MIN_ENVS", "1")
     monkeypatch.setenv("MPB_Q_CTAS", "1")
     monkeypatch.setenv("MPB_Q_UNIT_MASK", unit_mask)
-    if unit_mask == "0x0100":
-        monkeypatch.setenv("MPB_HEAVY_DIV", "4")        # the 10 most expensive envs run unqueued to the end of a launch
+    monkeypatch.setenv("MPB_Q_WINDOW", str(window))
+    monkeypatch.setenv("MPB_HEAVY_DIV", str(heavy_div))
     n, size, steps = 40, 16, 40
     seeds = np.arange(n) + 300
     env, refs = _batch(n, size, True, 1000, seeds)
@@ -292,6 +297,22 @@ def test_queue_scheduled_frames_match_oracle(unit_mask, monkeypatch):
         _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), bool(rng.random() < 0.2), t)
     for i, r in enumerate(refs):
         assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
-    ctr = env.micro.counters()
-    assert not ctr[:, 5].any() and not ctr[:, 15].any()
+    assert not env.micro.counters()[:, 15].any()                # no sprite-table overflow
+    env.close()
+
+
+def test_thread_per_env_frames_match_oracle(monkeypatch):
+    """The frames run one THREAD per env (mp_simt.cu: the engine headers compiled with Coop::n = 1, 32 different envs
+    in the lanes of a warp) -- same rollout as the reference, every observation and the final engine state."""
+    monkeypatch.setenv("MPB_SIMT", "1")
+    n, size, steps = 70, 16, 60
+    seeds = np.arange(n) + 500
+    env, refs = _batch(n, size, True, 1000, seeds)
+    _finish(env, refs)
+    rng = np.random.default_rng(12)
+    for t in range(steps):
+        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), bool(rng.random() < 0.2), t)
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
+    assert not env.micro.counters()[:, 15].any()
     env.close()

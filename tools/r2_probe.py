@@ -17,12 +17,11 @@ sys.path.insert(0, ROOT)
 
 DEFAULT = [
     "lockstep=MPB_QMODE:0",
-    "queue=MPB_QMODE:1",
-    "queue_k111=MPB_QMODE:1,MPB_Q_WAVES:2",
-    "queue_unit_frame=MPB_QMODE:1,MPB_Q_UNIT_MASK:0xffff",
-    "queue_unit_scan=MPB_QMODE:1,MPB_Q_UNIT_MASK:0x0100",
-    "queue_f100=MPB_QMODE:1,MPB_FRAMES_PER_LAUNCH:100",
-    "queue_f25=MPB_QMODE:1,MPB_FRAMES_PER_LAUNCH:25",
+    "simt_g3=MPB_QMODE:0,MPB_SIMT:1",
+    "simt_g1=MPB_QMODE:0,MPB_SIMT:1,MPB_GROUPS:1",
+    "simt_g3_f100=MPB_QMODE:0,MPB_SIMT:1,MPB_FRAMES_PER_LAUNCH:100",
+    "simt_g3_f25=MPB_QMODE:0,MPB_SIMT:1,MPB_FRAMES_PER_LAUNCH:25",
+    "simt_g3_h16=MPB_QMODE:0,MPB_SIMT:1,MPB_HEAVY_DIV:16",
 ]
 
 
