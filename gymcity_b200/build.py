@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("GYMCITY_B200_LIB", os.path.join(HERE, "libgymcity_b200.so"))
-SOURCES = ["gol.cu", "dlpack_export.cu", "mp_batch.cu", "mp_simt.cu"]
+SOURCES = ["gol.cu", "dlpack_export.cu", "mp_batch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-exact float: no fused multiply-add contraction, IEEE div/sqrt (setValves, collectTax,

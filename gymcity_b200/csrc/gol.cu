@@ -81,12 +81,18 @@ __device__ __forceinline__ uint32_t life_row(uint32_t up, uint32_t me, uint32_t 
 }
 
 // One thread per row.  W | 32 path: shuffle halo exchange inside the W-lane group.
+// T ticks per launch (golb_step_n): the rows stay in registers from tick to tick, tick t takes its actions from
+// actions[t * n_envs + env]; per-tick observations / rewards go to obs_seq[t] / reward_seq[t] when given, the
+// last tick's always to the handle's own buffers -- the state afterwards is that of T golb_step calls.  At
+// BASELINE's 4 096 boards one tick is ~1 us of GPU work: a launch per tick is launch-bound (14 us), T per launch
+// is not.
 template <bool SHFL>
 __global__ void __launch_bounds__(256)
 k_gol_step(uint32_t *__restrict__ rows, const int64_t *__restrict__ actions,
            float *__restrict__ obs, float *__restrict__ reward, int32_t *__restrict__ pop_out,
            uint8_t *__restrict__ done, int n_envs, int w, float trg_pop, float max_loss,
-           float denom, int terminal)
+           float denom, int step_count, int max_step, int T, float *__restrict__ obs_seq,
+           float *__restrict__ reward_seq, float scalar_plane)
 {
     extern __shared__ uint32_t s_rows[];
     const uint32_t mask = (w == 32) ? 0xffffffffu : ((1u << w) - 1u);
@@ -95,88 +101,110 @@ k_gol_step(uint32_t *__restrict__ rows, const int64_t *__restrict__ actions,
     const int x = threadIdx.x - le * w;             // row within the board
     const int env = blockIdx.x * envs_per_cta + le;
     const bool live = (le < envs_per_cta) && (env < n_envs);
+    const size_t plane = (size_t)w * w;
 
-    uint32_t me = 0;
-    if (live) {
-        me = rows[(size_t)env * w + x];
-        // multi_env.py:179,243-253: new_state = state ^ one_hot(a), a = x * W + y
-        int64_t a = actions[env];
-        int ax = (int)(a / w), ay = (int)(a - (int64_t)ax * w);
-        if (ax == x) me ^= (1u << ay);
-    }
-    uint32_t up, dn;
-    if (SHFL) {
-        // rows of one board sit in one aligned group of w lanes
-        const int lane = threadIdx.x & 31;
-        const int base = lane - x;
-        up = __shfl_sync(0xffffffffu, me, base + ((x + w - 1) & (w - 1)));
-        dn = __shfl_sync(0xffffffffu, me, base + ((x + 1) & (w - 1)));
-    } else {
-        s_rows[threadIdx.x] = me;
-        __syncthreads();
-        int xu = (x == 0) ? w - 1 : x - 1, xd = (x == w - 1) ? 0 : x + 1;
-        up = live ? s_rows[le * w + xu] : 0;
-        dn = live ? s_rows[le * w + xd] : 0;
-    }
-    uint32_t nxt = life_row(up, me, dn, w, mask);
-    int p = __popc(nxt);
-    if (SHFL) {
-        for (int o = w >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    } else {
-        __syncthreads();
-        s_rows[threadIdx.x] = (uint32_t)p;
-        __syncthreads();
-        if (live && x == 0) {
-            int s = 0;
-            for (int i = 0; i < w; i++) s += (int)s_rows[le * w + i];
-            p = s;
+    uint32_t me = live ? rows[(size_t)env * w + x] : 0u;
+    for (int t = 0; t < T; t++) {
+        if (live) {
+            // multi_env.py:179,243-253: new_state = state ^ one_hot(a), a = x * W + y
+            int64_t a = actions[(size_t)t * n_envs + env];
+            int ax = (int)(a / w), ay = (int)(a - (int64_t)ax * w);
+            if (ax == x) me ^= (1u << ay);
         }
-    }
-    if (SHFL && w == 16 && obs) {
-        // 16x16 boards: a warp holds two boards.  Instead of every lane writing its own row (four 16-byte
-        // stores 64 bytes apart from their neighbours'), the rows are redistributed by shuffle so that
-        // each store instruction writes 16 consecutive float4 per board: chunk c = k * 16 + j of a board's
-        // 1 KB state plane is quarter (j & 3) of row (k * 4 + j / 4).
-        const int lane = threadIdx.x & 31, j = lane & 15, half = lane & 16;
-        float4 *o = reinterpret_cast<float4 *>(obs + ((size_t)env * 2 + 1) * 256);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t r = __shfl_sync(0xffffffffu, nxt, half + k * 4 + (j >> 2)) >> ((j & 3) * 4);
-            float4 v;
-            v.x = (float)(r & 1u);
-            v.y = (float)((r >> 1) & 1u);
-            v.z = (float)((r >> 2) & 1u);
-            v.w = (float)((r >> 3) & 1u);
-            if (live) __stcs(&o[k * 16 + j], v);
-        }
-    }
-    if (!live) return;
-    rows[(size_t)env * w + x] = nxt;
-    if (obs && !(SHFL && w == 16)) {
-        // multi_env.py:235-240: obs = cat(scalar plane, state); plane 0 is written at set_params
-        float4 *o = reinterpret_cast<float4 *>(obs + ((size_t)env * 2 + 1) * w * w + (size_t)x * w);
-        if ((w & 3) == 0) {
-            for (int y = 0; y < w; y += 4) {
-                float4 v;
-                v.x = (float)((nxt >> y) & 1u);
-                v.y = (float)((nxt >> (y + 1)) & 1u);
-                v.z = (float)((nxt >> (y + 2)) & 1u);
-                v.w = (float)((nxt >> (y + 3)) & 1u);
-                o[y >> 2] = v;
-            }
+        uint32_t up, dn;
+        if (SHFL) {
+            // rows of one board sit in one aligned group of w lanes
+            const int lane = threadIdx.x & 31;
+            const int base = lane - x;
+            up = __shfl_sync(0xffffffffu, me, base + ((x + w - 1) & (w - 1)));
+            dn = __shfl_sync(0xffffffffu, me, base + ((x + 1) & (w - 1)));
         } else {
-            float *of = reinterpret_cast<float *>(o);
-            for (int y = 0; y < w; y++) of[y] = (float)((nxt >> y) & 1u);
+            __syncthreads();
+            s_rows[threadIdx.x] = me;
+            __syncthreads();
+            int xu = (x == 0) ? w - 1 : x - 1, xd = (x == w - 1) ? 0 : x + 1;
+            up = live ? s_rows[le * w + xu] : 0;
+            dn = live ? s_rows[le * w + xd] : 0;
         }
+        const uint32_t nxt = life_row(up, me, dn, w, mask);
+        int p = __popc(nxt);
+        if (SHFL) {
+            for (int o = w >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        } else {
+            __syncthreads();
+            s_rows[threadIdx.x] = (uint32_t)p;
+            __syncthreads();
+            if (live && x == 0) {
+                int s = 0;
+                for (int i = 0; i < w; i++) s += (int)s_rows[le * w + i];
+                p = s;
+            }
+        }
+        const bool last = t == T - 1;
+        // where this tick's observation goes: the caller's sequence buffer, and the handle's own for the last tick
+        for (int dst = 0; dst < 2; dst++) {
+            float *ob = dst == 0 ? (obs_seq ? obs_seq + (size_t)t * n_envs * 2 * plane : (float *)0)
+                                 : (last ? obs : (float *)0);
+            if (!ob) continue;
+            const bool with_plane0 = dst == 0;      // the handle's plane 0 is written at set_params; a sequence buffer gets it here
+            if (SHFL && w == 16) {
+                // 16x16 boards: a warp holds two boards.  Instead of every lane writing its own row (four 16-byte
+                // stores 64 bytes apart from their neighbours'), the rows are redistributed by shuffle so that
+                // each store instruction writes 16 consecutive float4 per board: chunk c = k * 16 + j of a board's
+                // 1 KB state plane is quarter (j & 3) of row (k * 4 + j / 4).
+                const int lane = threadIdx.x & 31, j = lane & 15, half = lane & 16;
+                float4 *o = reinterpret_cast<float4 *>(ob + ((size_t)env * 2 + 1) * 256);
+                const float4 sp = make_float4(scalar_plane, scalar_plane, scalar_plane, scalar_plane);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t r = __shfl_sync(0xffffffffu, nxt, half + k * 4 + (j >> 2)) >> ((j & 3) * 4);
+                    float4 v;
+                    v.x = (float)(r & 1u);
+                    v.y = (float)((r >> 1) & 1u);
+                    v.z = (float)((r >> 2) & 1u);
+                    v.w = (float)((r >> 3) & 1u);
+                    if (live) {
+                        __stcs(&o[k * 16 + j], v);
+                        if (with_plane0) __stcs(&o[k * 16 + j - 64], sp);
+                    }
+                }
+            } else if (live) {
+                // multi_env.py:235-240: obs = cat(scalar plane, state)
+                float4 *o = reinterpret_cast<float4 *>(ob + ((size_t)env * 2 + 1) * plane + (size_t)x * w);
+                if ((w & 3) == 0) {
+                    for (int y = 0; y < w; y += 4) {
+                        float4 v;
+                        v.x = (float)((nxt >> y) & 1u);
+                        v.y = (float)((nxt >> (y + 1)) & 1u);
+                        v.z = (float)((nxt >> (y + 2)) & 1u);
+                        v.w = (float)((nxt >> (y + 3)) & 1u);
+                        o[y >> 2] = v;
+                    }
+                } else {
+                    float *of = reinterpret_cast<float *>(o);
+                    for (int y = 0; y < w; y++) of[y] = (float)((nxt >> y) & 1u);
+                }
+                if (with_plane0) {
+                    float *o0 = ob + (size_t)env * 2 * plane + (size_t)x * w;
+                    for (int y = 0; y < w; y++) o0[y] = scalar_plane;
+                }
+            }
+        }
+        if (live && x == 0) {
+            // multi_env.py:203-212, fp32 like torch: (max_loss - |trg - pop|) * 100 / (max_loss * max_step * num_proc)
+            float loss = fabsf(__fsub_rn(trg_pop, (float)p));
+            float r = __fdiv_rn(__fmul_rn(__fsub_rn(max_loss, loss), 100.0f), denom);
+            if (reward_seq) reward_seq[(size_t)t * n_envs + env] = r;
+            if (last) {
+                reward[env] = r;
+                pop_out[env] = p;
+                // multi_env.py:213-216: terminal is all-true when step_count == max_step (checked before ++)
+                done[env] = (uint8_t)(step_count + t == max_step);
+            }
+        }
+        me = nxt;
     }
-    if (x == 0) {
-        // multi_env.py:203-212, fp32 like torch: (max_loss - |trg - pop|) * 100 / (max_loss * max_step * num_proc)
-        float loss = fabsf(__fsub_rn(trg_pop, (float)p));
-        float r = __fdiv_rn(__fmul_rn(__fsub_rn(max_loss, loss), 100.0f), denom);
-        reward[env] = r;
-        pop_out[env] = p;
-        done[env] = (uint8_t)terminal;
-    }
+    if (live) rows[(size_t)env * w + x] = me;
 }
 
 // Classic single-env world (world.py).  build_cell() replaces the Cell object at (x,y) while the
@@ -444,6 +472,24 @@ int golb_get_state(golb_handle h, uint8_t *cells_host)
     return 0;
 }
 
+static int gol_launch(GolBatch *b, const int64_t *actions_dev, int T, float *obs_seq, float *reward_seq, cudaStream_t st)
+{
+    const int w = b->width;
+    float denom = b->max_loss * (float)b->max_step;       // torch: fp32 tensor * int, twice
+    denom = denom * (float)b->n_envs;
+    int threads = (256 / w) * w, epc = threads / w;
+    int grid = (b->n_envs + epc - 1) / epc;
+    if ((32 % w) == 0)
+        k_gol_step<true><<<grid, threads, 0, st>>>(b->rows, actions_dev, b->obs, b->reward, b->pop, b->done, b->n_envs, w,
+            b->trg_pop, b->max_loss, denom, b->step_count, b->max_step, T, obs_seq, reward_seq, b->scalar_plane);
+    else
+        k_gol_step<false><<<grid, threads, threads * 4, st>>>(b->rows, actions_dev, b->obs, b->reward, b->pop, b->done,
+            b->n_envs, w, b->trg_pop, b->max_loss, denom, b->step_count, b->max_step, T, obs_seq, reward_seq, b->scalar_plane);
+    CK(cudaGetLastError());
+    b->step_count += T;
+    return 0;
+}
+
 int golb_step(golb_handle h, const int64_t *actions_dev, void *stream)
 {
     GolBatch *b = (GolBatch *)h;
@@ -455,23 +501,20 @@ int golb_step(golb_handle h, const int64_t *actions_dev, void *stream)
         k_gol_classic_step<<<(b->n_envs + 63) / 64, 64, 0, st>>>(
             b->rows, b->frozen, b->frozen_val, actions_dev, b->obs_u8, b->reward, b->pop, b->done,
             b->n_envs, w, b->max_step, b->step_count);
-    } else {
-        // multi_env.py:213-216: terminal is all-true when step_count == max_step (checked before ++)
-        int terminal = (b->step_count == b->max_step);
-        float denom = b->max_loss * (float)b->max_step;       // torch: fp32 tensor * int, twice
-        denom = denom * (float)b->n_envs;
-        int threads = (256 / w) * w, epc = threads / w;
-        int grid = (b->n_envs + epc - 1) / epc;
-        if ((32 % w) == 0)
-            k_gol_step<true><<<grid, threads, 0, st>>>(b->rows, actions_dev, b->obs, b->reward,
-                b->pop, b->done, b->n_envs, w, b->trg_pop, b->max_loss, denom, terminal);
-        else
-            k_gol_step<false><<<grid, threads, threads * 4, st>>>(b->rows, actions_dev, b->obs,
-                b->reward, b->pop, b->done, b->n_envs, w, b->trg_pop, b->max_loss, denom, terminal);
+        CK(cudaGetLastError());
+        b->step_count++;
+        return 0;
     }
-    CK(cudaGetLastError());
-    b->step_count++;
-    return 0;
+    return gol_launch(b, actions_dev, 1, NULL, NULL, st);
+}
+
+int golb_step_n(golb_handle h, const int64_t *actions_dev, int T, float *obs_seq_dev, float *reward_seq_dev, void *stream)
+{
+    GolBatch *b = (GolBatch *)h;
+    if (!b || !actions_dev || T < 1) return -1;
+    if (b->classic) { snprintf(b->err, sizeof(b->err), "golb_step_n: multi-env handles only"); return -1; }
+    cudaSetDevice(b->device);
+    return gol_launch(b, actions_dev, T, obs_seq_dev, reward_seq_dev, (cudaStream_t)stream);
 }
 
 int golb_step_host(golb_handle h, const int64_t *actions_host, float *reward_host, void *stream)

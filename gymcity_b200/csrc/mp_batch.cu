@@ -19,12 +19,6 @@
 
 using namespace mp;
 
-// mp_simt.cu: the frames of a launch with one THREAD per env (the engine headers compiled with Coop::n = 1)
-extern "C" int mps_launch_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
-                                 int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm,
-                                 int gstride, int goff, int gcount, unsigned int *prof, int prof_off, const uint8_t *mask,
-                                 void *stream);
-
 namespace {
 
 // Kernels other than k_mp_frames: one warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's
@@ -53,11 +47,13 @@ struct MpBatch {
     int use_sched;
     int sms;                  // SMs of the device
     int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
-    int qmode;                // frames run by the queue-scheduled kernel (k_mp_frames_q) when the launch has >= q_min_envs envs
-    int q_min_envs, q_max_k, q_waves, q_unit_mask, q_ctas, q_window;
-    int simt;                 // frames of the non-heavy groups run one THREAD per env (mp_simt.cu)
     unsigned int *prof;       // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
     cudaError_t launch_err;   // first error of a launch enqueued by launch_frames since the last check
+    // per-episode seeds derived on the device (gym_episode_seed) and the device-side auto-reset of mpb_env_step*
+    long long run_seed; int env_offset;
+    int auto_reset, auto_terrain;
+    int *rlist, *rcount;      // [n_envs] envs being reset by the current step, [1] how many
+    uint8_t *amask;           // [n_envs] the same as a byte mask
     int32_t *xt_rnd; size_t xt_rnd_bytes;    // device buffer of mpb_env_extinguish's draws (grown on demand)
     double *counters_dev;     // [n_envs * MPB_ENV_NUM_COUNTERS] staging of mpb_env_get_counters
     // env groups on their own streams: while one group's launch drains its slowest envs the other
@@ -180,16 +176,23 @@ template <int MP_FEPC>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off, const uint8_t *mask)
+            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off, const uint8_t *mask,
+            const int *gcount_dev)
 {
-    const long long t_begin = clock64();
     __shared__ int red[8 * MP_FEPC];
     // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
     // lane touches on almost every instruction: it lives in shared memory for the whole launch
     __shared__ Env s_env[MP_FEPC];
+    __shared__ int s_ph0;
+    // list-driven launches (device-side auto-reset: `perm` is the list of envs being reset and *gcount_dev its
+    // length, unknown to the host) use a fixed grid and walk the list; every other launch has one CTA per
+    // MP_FEPC slots and runs the loop body once
+    if (gcount_dev) gcount = *gcount_dev;
+    for (int cta = blockIdx.x; cta * MP_FEPC < gcount; cta += gridDim.x) {
+    const long long t_begin = clock64();
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
-    const int widx = blockIdx.x * MP_FEPC + (threadIdx.x >> 5);
+    const int widx = cta * MP_FEPC + (threadIdx.x >> 5);
     const int slot = widx * gstride + goff;
     bool live = widx < gcount && slot < n_envs;
     int env = 0;
@@ -197,7 +200,8 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         env = perm ? perm[slot] : slot;
         if (mask && !mask[env]) live = false;             // masked step (mpb_env_step_masked): this env sits it out
     }
-    if (MP_FEPC == 1 && !live) return;
+    if (MP_FEPC == 1 && !live) continue;
+    if (MP_FEPC > 1 && mask && !__syncthreads_or(live)) continue;      // nobody of this CTA takes part
     const int lane = threadIdx.x & 31;
     Env &e = s_env[threadIdx.x >> 5];
     uint32_t *sw = reinterpret_cast<uint32_t *>(mp_dyn_smem) + (threadIdx.x >> 5) * SCAL_WORDS;
@@ -212,7 +216,6 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     // whose env was reset to another phase -- executes the same barriers.  (A bounded-skew variant over an
     // mbarrier ring, warps running up to 7 frames ahead, was 3-17 % slower and its polling loop was 59 %
     // of the issued instructions: profiles/r01_notes.md.)
-    __shared__ int s_ph0;
     if (MP_FEPC > 1) {
         if (threadIdx.x == 0) s_ph0 = live ? (e.s->initSimLoad ? 0 : (e.s->phaseCycle & 15)) : 0;
         __syncthreads();
@@ -254,317 +257,19 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
             if (!(scan_block && ph >= 1 && ph <= 7)) __syncthreads();
         }
     }
-    if (!live) return;
-    if (fast && lane == 0 && nrun > 0) {
-        e.s->phaseCycle = (int16_t)phase;
-        e.s->speedCycle = (int16_t)sc;
-    }
-    unstage_scalars(e, sw);
-    if (lane == 0) {
-        busy += (unsigned int)(t_loop - t_begin);                       // state load, animateTiles
-        if (cycles) cycles[env] += busy;
-        if (cost) cost[env] += busy >> 8;
-    }
-}
-
-// ---- queue-scheduled frame kernel ----------------------------------------------------------------
-// k_mp_frames<32> keeps the 32 warps of an SM in the same simulation phase with a CTA barrier per frame, and
-// pays for it: every frame lasts as long as its slowest env (ncu r01: 42 % of all warp cycles stalled at the
-// barrier).  Here one CTA (32 warps, one per SM) owns K >> 32 envs, keeps a WINDOW of W of them active, and the
-// warps take env-frames from a FIFO of ready window slots in shared memory: a warp pops a slot, runs one UNIT of
-// its env's frames (a run of phases that ends after a phase of `unit_mask`, e.g. the eight map-scan phases), and
-// pushes it back.  Because the queue is first in, first out, every env of the window finishes unit u before any
-// starts unit u + 2, so the warps of the SM are still in (nearly) the same code -- the lockstep the instruction
-// caches need -- but nobody waits: a slow env only occupies the warp that runs it.  An env that has run its
-// frames of the launch retires: its scalars go back to its block and the next env of the CTA's list takes the
-// slot.  W bounds the data the SM cycles through between two visits of the same env (the L1 holds the hot lines
-// of a few dozen envs, not of hundreds); K >> W means there is always a successor, so the window never drains
-// before the end of the launch.  Envs flagged heavy (the first `heavy_slots` of the cost order: flood and fire
-// fields, 5-10 x the mean) are run to the end of the launch by the warp that pops them: they are the critical
-// path and must not queue behind anyone.
-//   Queue: bounded MPMC ring (tickets + per-slot sequence numbers).  At most W + 32 entries are ever in
-// flight (W slots, 32 exit sentinels pushed by the warp that retires the last env), QN >= W + 32.
-constexpr int MPQ_MAX_W = 224;      // window slots the ring and the shared-memory budget allow
-constexpr int MPQ_QN = 256;         // ring size, power of two >= MPQ_MAX_W + 32
-constexpr int MPQ_SLOT_BYTES = SCAL_BYTES + 4 + 4 + 2 + 2 + 1;
-
-struct QArgs {
-    uint8_t *blocks; const uint16_t *anim; int n_envs, first, count, animate_before, respect_passes;
-    unsigned long long *cycles; unsigned int *cost; const int *perm; int gstride, goff, gcount;
-    int K;                   // envs per CTA: CTA c owns ranks c, c + gridDim.x, ... (K of them)
-    int W;                   // window: envs of a CTA that are in flight at a time
-    int unit_mask;           // bit p: a unit ends after phase p
-    int heavy_slots;         // schedule slots below this are run to the end of the launch without re-queueing
-    unsigned int *prof; int prof_off; const uint8_t *mask;
-};
-
-struct QState {                      // shared memory of k_mp_frames_q (static part)
-    Env env[32];
-    int red[8 * 32];
-    int q[MPQ_QN];
-    unsigned int seq[MPQ_QN];
-    unsigned int head, tail, next, active;
-};
-
-__device__ __forceinline__ void q_push(QState &Q, int item)           // one lane
-{
-    const unsigned int p = atomicAdd(&Q.tail, 1u), slot = p & (MPQ_QN - 1);
-    *reinterpret_cast<volatile int *>(&Q.q[slot]) = item;
-    __threadfence_block();
-    *reinterpret_cast<volatile unsigned int *>(&Q.seq[slot]) = p + 1;
-}
-__device__ __forceinline__ int q_pop(QState &Q)                       // one lane; waits for its ticket's entry
-{
-    const unsigned int t = atomicAdd(&Q.head, 1u), slot = t & (MPQ_QN - 1);
-    while (*reinterpret_cast<volatile unsigned int *>(&Q.seq[slot]) != t + 1) __nanosleep(64);
-    return *reinterpret_cast<volatile int *>(&Q.q[slot]);
-}
-
-__global__ void __launch_bounds__(1024, 1) k_mp_frames_q(const QArgs a)
-{
-    __shared__ QState Q;
-    const int W = a.W;
-    // dynamic shared memory: W scalar blocks, then the per-slot bookkeeping
-    uint32_t *const scal = reinterpret_cast<uint32_t *>(mp_dyn_smem);
-    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)W * SCAL_BYTES);
-    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + W);
-    short *const s_fdone = reinterpret_cast<short *>(s_busy + W);
-    short *const s_nrun = s_fdone + W;
-    unsigned char *const s_sticky = reinterpret_cast<unsigned char *>(s_nrun + W);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Env &e = Q.env[warp];
-    for (int i = threadIdx.x; i < MPQ_QN; i += blockDim.x) Q.seq[i] = 0;
-    if (threadIdx.x == 0) { Q.head = 0; Q.tail = 0; Q.next = 0; Q.active = 0; }
-    if (lane == 0) { e.anim = a.anim; e.c.red = Q.red + warp * 8; }
-    __syncthreads();
-
-    // [ALL lanes of a warp] the next env of the CTA's list moves into window slot `ws`: scalars staged,
-    // tickEngine's animateTiles, frames to run in this launch.  False when the list is exhausted.
-    auto admit = [&](int ws) -> bool {
-        for (;;) {
-            const long long t0 = clock64();
-            int k = 0;
-            if (lane == 0) k = (int)atomicAdd(&Q.next, 1u);
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= a.K) return false;
-            const int rank = blockIdx.x + k * gridDim.x;
-            const int slot = rank * a.gstride + a.goff;
-            if (rank >= a.gcount || slot >= a.n_envs) continue;
-            const int env = a.perm ? a.perm[slot] : slot;
-            if (a.mask && !a.mask[env]) continue;
-            uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
-            bind_env_of(e, a.blocks, env, a.anim, Q.red, sw);
-            if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
-            int nrun = a.count;
-            if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
-            if (nrun <= 0) { unstage_scalars(e, sw); __syncwarp(); continue; }
-            if (lane == 0) {
-                s_envid[ws] = env;
-                s_nrun[ws] = (short)nrun;
-                s_fdone[ws] = 0;
-                s_sticky[ws] = (unsigned char)(slot < a.heavy_slots);
-                s_busy[ws] = (unsigned int)(clock64() - t0);
-            }
-            __syncwarp();
-            return true;
+    if (live) {
+        if (fast && lane == 0 && nrun > 0) {
+            e.s->phaseCycle = (int16_t)phase;
+            e.s->speedCycle = (int16_t)sc;
         }
-    };
-
-    for (int ws = warp; ws < W; ws += 32)
-        if (admit(ws) && lane == 0) {
-            atomicAdd(&Q.active, 1u);
-            __threadfence_block();
-            q_push(Q, ws);
-        }
-    __syncthreads();
-    if (warp == 0 && Q.active == 0) q_push(Q, -1 - lane);      // nothing to run: every warp takes an exit sentinel
-    __syncthreads();
-
-    // ---- the warps drain the queue
-    for (;;) {
-        int ws = 0;
-        if (lane == 0) ws = q_pop(Q);
-        __threadfence_block();
-        ws = __shfl_sync(0xffffffffu, ws, 0);
-        if (ws < 0) break;
-        const unsigned int t0 = (unsigned int)clock64();
-        const int env = s_envid[ws];
-        uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
-        if (lane == 0) {
-            bind_env(e, a.blocks + (size_t)env * ENV_STRIDE);
-            e.s = reinterpret_cast<Scalars *>(sw);
-        }
-        __syncwarp();
-        int f = s_fdone[ws];
-        const int n = s_nrun[ws];
-        const bool sticky = s_sticky[ws] != 0;
-        if (e.s->simSpeed == 3 && !e.s->initSimLoad) {
-            // the gym path's common case: every frame simulates, speedCycle / phaseCycle are plain counters
-            int phase = e.s->phaseCycle & 15, sc = e.s->speedCycle, ran;
-            do {
-                const unsigned int tf = (unsigned int)clock64();
-                sim_phase(e, phase);
-                ran = phase;
-                phase = (phase + 1) & 15;
-                sc = (sc + 1) & 1023;
-                sim_sprites(e);
-                if (a.prof && lane == 0) a.prof[(size_t)env * 256 + a.prof_off + a.first + f] = (unsigned int)clock64() - tf;
-                f++;
-            } while (f < n && (sticky || !((a.unit_mask >> ran) & 1)));
-            if (lane == 0) { e.s->phaseCycle = (int16_t)phase; e.s->speedCycle = (int16_t)sc; }
-        } else {
-            int ran;
-            do {
-                ran = sim_loop_head(e);
-                sim_loop_tail(e, ran);
-                f++;
-            } while (f < n && (sticky || !(ran && ((a.unit_mask >> (ran - 1)) & 1))));
-        }
-        __threadfence_block();
-        __syncwarp();
-        if (f < n) {                                           // back into the queue
-            if (lane == 0) {
-                s_fdone[ws] = (short)f;
-                s_busy[ws] += (unsigned int)clock64() - t0;
-                __threadfence_block();
-                q_push(Q, ws);
-            }
-            continue;
-        }
-        // the env has run its frames: retire it, and let the next env of the list have the slot
         unstage_scalars(e, sw);
         if (lane == 0) {
-            const unsigned int busy = s_busy[ws] + ((unsigned int)clock64() - t0);
-            if (a.cycles) a.cycles[env] += busy;
-            if (a.cost) a.cost[env] += busy >> 8;
-        }
-        __syncwarp();
-        const bool more = admit(ws);
-        if (lane == 0) {
-            __threadfence_block();
-            if (more) q_push(Q, ws);
-            else if (atomicSub(&Q.active, 1u) == 1u)
-                for (int i = 0; i < 32; i++) q_push(Q, -1);    // the last env is done: one exit sentinel per warp
+            busy += (unsigned int)(t_loop - t_begin);                   // state load, animateTiles
+            if (cycles) cycles[env] += busy;
+            if (cost) cost[env] += busy >> 8;
         }
     }
-}
-
-// ---- unit-lockstep frame kernel with dynamic balancing ---------------------------------------------
-// The queue above keeps nobody waiting but only loosely in step, and measured slower than the barrier kernel for
-// exactly that reason (profiles/r02_notes.md: the smaller the window, the freer the warps run, the slower).  This
-// kernel keeps k_mp_frames<32>'s strict lockstep -- a CTA barrier between units -- but hands the work of a unit out
-// dynamically: one CTA per SM owns K envs, works on a window of W >= 32 of them at a time, and inside a unit (a run
-// of frames that ends after a phase of `unit_mask`) the 32 warps take window slots from a shared counter, most
-// expensive env first.  A unit then lasts max(longest env, sum / 32) instead of the longest env of every warp's
-// fixed share; the barrier wait shrinks to the drain at the end of each unit.
-__global__ void __launch_bounds__(1024, 1) k_mp_frames_u(const QArgs a)
-{
-    __shared__ Env s_env[32];
-    __shared__ int red[8 * 32];
-    __shared__ unsigned int s_ctr[2];
-    __shared__ int s_ph0;
-    const int W = a.W;
-    uint32_t *const scal = reinterpret_cast<uint32_t *>(mp_dyn_smem);
-    int *const s_envid = reinterpret_cast<int *>(mp_dyn_smem + (size_t)W * SCAL_BYTES);
-    unsigned int *const s_busy = reinterpret_cast<unsigned int *>(s_envid + W);
-    short *const s_nrun = reinterpret_cast<short *>(s_busy + W);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Env &e = s_env[warp];
-    if (lane == 0) { e.anim = a.anim; e.c.red = red + warp * 8; }
-    for (int w0 = 0; w0 < a.K; w0 += W) {
-        const int nw = min(W, a.K - w0);
-        // ---- stage the window: scalars into shared memory, tickEngine's animateTiles, frames to run
-        for (int ws = warp; ws < nw; ws += 32) {
-            const long long t0 = clock64();
-            const int k = w0 + ws;
-            const int rank = blockIdx.x + k * gridDim.x;
-            const int slot = rank * a.gstride + a.goff;
-            bool live = rank < a.gcount && slot < a.n_envs;
-            int env = 0;
-            if (live) {
-                env = a.perm ? a.perm[slot] : slot;
-                if (a.mask && !a.mask[env]) live = false;
-            }
-            int nrun = 0;
-            if (live) {
-                bind_env_of(e, a.blocks, env, a.anim, red, scal + (size_t)ws * SCAL_WORDS);
-                if (a.animate_before && e.s->doAnimation && !e.s->tilesAnimated) animate_tiles(e);
-                nrun = a.count;
-                if (a.respect_passes) nrun = e.s->simSpeed ? min(a.count, max(0, (int)e.s->simPasses - a.first)) : 0;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                s_envid[ws] = live ? env : -1;
-                s_nrun[ws] = (short)nrun;
-                s_busy[ws] = (unsigned int)(clock64() - t0);
-                if (ws == 0) s_ph0 = live ? (e.s->initSimLoad ? 0 : (e.s->phaseCycle & 15)) : 0;
-            }
-        }
-        if (threadIdx.x == 0) { s_ctr[0] = 0; s_ctr[1] = 0; }
-        __syncthreads();
-        // ---- units: [f, f + len) ends after a phase of unit_mask (the window's nominal phase: slot 0's)
-        const int ph0 = s_ph0;
-        int u = 0;
-        for (int f = 0; f < a.count; u++) {
-            int len = 1;
-            while (f + len < a.count && !((a.unit_mask >> ((ph0 + f + len - 1) & 15)) & 1)) len++;
-            unsigned int *ctr = &s_ctr[u & 1];
-            for (;;) {
-                int ws = 0;
-                if (lane == 0) ws = (int)atomicAdd(ctr, 1u);
-                ws = __shfl_sync(0xffffffffu, ws, 0);
-                if (ws >= nw) break;
-                const int env = s_envid[ws];
-                const int n = min((int)s_nrun[ws], f + len);          // this env's frames end here in this unit
-                if (env < 0 || f >= n) continue;
-                const unsigned int t0 = (unsigned int)clock64();
-                if (lane == 0) {
-                    bind_env(e, a.blocks + (size_t)env * ENV_STRIDE);
-                    e.s = reinterpret_cast<Scalars *>(scal + (size_t)ws * SCAL_WORDS);
-                }
-                __syncwarp();
-                int ff = f;
-                if (e.s->simSpeed == 3 && !e.s->initSimLoad) {
-                    // the gym path's common case: every frame simulates, speedCycle / phaseCycle are plain counters
-                    int phase = e.s->phaseCycle & 15, sc = e.s->speedCycle;
-                    do {
-                        const unsigned int tf = (unsigned int)clock64();
-                        sim_phase(e, phase);
-                        phase = (phase + 1) & 15;
-                        sc = (sc + 1) & 1023;
-                        sim_sprites(e);
-                        if (a.prof && lane == 0)
-                            a.prof[(size_t)env * 256 + a.prof_off + a.first + ff] = (unsigned int)clock64() - tf;
-                    } while (++ff < n);
-                    if (lane == 0) { e.s->phaseCycle = (int16_t)phase; e.s->speedCycle = (int16_t)sc; }
-                } else {
-                    do {
-                        const int ran = sim_loop_head(e);
-                        sim_loop_tail(e, ran);
-                    } while (++ff < n);
-                }
-                __syncwarp();
-                if (lane == 0) s_busy[ws] += (unsigned int)clock64() - t0;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_ctr[u & 1] = 0;                    // used again by the unit after the next one
-            f += len;
-        }
-        // ---- scalars back to the blocks, per-env cycle counts for the next schedule
-        for (int ws = warp; ws < nw; ws += 32) {
-            const int env = s_envid[ws];
-            if (env < 0) continue;
-            uint32_t *gs = reinterpret_cast<uint32_t *>(a.blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
-            const uint32_t *sw = scal + (size_t)ws * SCAL_WORDS;
-            for (int i = lane; i < SCAL_WORDS; i += 32) gs[i] = sw[i];
-            if (lane == 0) {
-                if (a.cycles) a.cycles[env] += s_busy[ws];
-                if (a.cost) a.cost[env] += s_busy[ws] >> 8;
-            }
-        }
-        __syncthreads();
+    if (gcount_dev) { if (MP_FEPC > 1) __syncthreads(); else __syncwarp(); }      // the shared Env / scalars are reused
     }
 }
 
@@ -635,9 +340,11 @@ __device__ __forceinline__ void bind_device_gym(Gym &gy, uint8_t *shadow, int st
     bind_gym(gy, shadow + (size_t)device_env_index() * stride, cfg);
 }
 
+// terrain_seeds == NULL with terrain != 0: the seeds of the env's next episode are derived here (gym_episode_seed)
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-                     const int32_t *terrain_seeds, const int32_t *sim_seeds, const uint8_t *mask, int terrain)
+                     const int32_t *terrain_seeds, const int32_t *sim_seeds, const uint8_t *mask, int terrain,
+                     long long run_seed, int env_offset)
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
@@ -646,8 +353,72 @@ k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t 
     bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
-    gym_reset_begin(e, gy, terrain, terrain ? terrain_seeds[env] : 0, terrain ? sim_seeds[env] : 0);
+    int ts = 0, ss = 0;
+    if (terrain && terrain_seeds) { ts = terrain_seeds[env]; ss = sim_seeds[env]; }
+    else if (terrain) {
+        const int ep = gy.g->episode;
+        ts = gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 0);
+        ss = gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 1);
+    }
+    __syncwarp();
+    gym_reset_begin(e, gy, terrain, ts, ss);
+    if (lane == 0 && terrain && !terrain_seeds) gy.g->episode++;
     unstage_scalars(e, sw);
+}
+
+// ---- device-side auto-reset (subproc_vec_env.py:16-21: `if done: ob = env.reset()` inside the worker) ----------
+// The envs whose episode ended in the step that just ran, as a list + count + byte mask; nothing goes to the host.
+__global__ void k_mp_env_auto_list(const uint8_t *done, const uint8_t *step_mask, int n, int *list, int *count, uint8_t *amask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool r = done[i] != 0 && (!step_mask || step_mask[i] != 0);
+    amask[i] = r ? 1 : 0;
+    if (r) list[atomicAdd(count, 1)] = i;
+}
+// reset, first half, for the envs of the list (a fixed grid walks it: the host does not know its length)
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_reset_list(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg, const int *list,
+                    const int *count, int terrain, long long run_seed, int env_offset)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_SHARED_ENV();
+    const int lane = threadIdx.x & 31;
+    const int n = *count;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int env = list[k];
+        bind_env_of(e, blocks, env, anim, red, sw);
+        Gym gy;
+        bind_gym(gy, shadow + (size_t)env * stride, &cfg);
+        const int ep = gy.g->episode;
+        __syncwarp();
+        gym_reset_begin(e, gy, terrain,
+                        terrain ? gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 0) : 0,
+                        terrain ? gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 1) : 0);
+        if (lane == 0 && terrain) gy.g->episode = ep + 1;
+        unstage_scalars(e, sw);
+        __syncwarp();
+    }
+}
+// reset, second half after the tick, for the envs of the list: metrics, funds, observation; reward / done stay
+// those of the step that ended the episode
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_post_list(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg, float *obs,
+                   float *reward, uint8_t *done, const int *list, const int *count)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_SHARED_ENV();
+    const int n = *count;
+    const size_t on = (size_t)gym_obs_channels(cfg) * cfg.W * cfg.H;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int env = list[k];
+        bind_env_of(e, blocks, env, anim, red, sw);
+        Gym gy;
+        bind_gym(gy, shadow + (size_t)env * stride, &cfg);
+        gym_reset_post(e, gy, obs + env * on, reward + env, done + env, true);
+        unstage_scalars(e, sw);
+        __syncwarp();
+    }
 }
 
 // TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
@@ -765,6 +536,15 @@ k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow
     unstage_scalars(e, sw);
 }
 
+__global__ void k_mp_env_set_num_step(uint8_t *shadow, int stride, GymCfg cfg, int n, const int32_t *vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Gym gy;
+    bind_gym(gy, shadow + (size_t)i * stride, &cfg);
+    gy.g->num_step = vals[i];
+}
+
 __global__ void k_mp_env_counters(const uint8_t *blocks, const uint8_t *shadow, int stride, GymCfg cfg, int n, double *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -778,6 +558,7 @@ __global__ void k_mp_env_counters(const uint8_t *blocks, const uint8_t *shadow, 
     o[4] = g.num_step; o[5] = g.tilemap_error; o[6] = g.reward; o[7] = g.done; o[8] = g.curr_funds;
     for (int k = 0; k < GYM_NUM_METRICS; k++) o[9 + k] = g.metrics[k];
     o[15] = sc->spriteOverflow;
+    o[16] = g.episode;
 }
 
 #define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
@@ -795,7 +576,7 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 }
 
 
-// k_mp_frames with `epc` envs per CTA (1, 8, 16 or 32), or the queue-scheduled kernel (b->qmode); prof_off = frame
+// k_mp_frames with `epc` envs per CTA (1, 8, 16 or 32); prof_off = frame
 // offset of this simTick in the per-frame profile rows (0 for the first simTick of an env-step, 100 for the
 // second).  `mask`: device mask of the envs that take part (NULL = all).  A launch error is recorded in the handle
 // (b->launch_err) and reported by the entry point that enqueued it.
@@ -803,38 +584,13 @@ void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, i
                    const int *perm, int gstride, int goff, int gcount, const uint8_t *mask, int prof_off = 0, bool heavy = false)
 {
     if (gcount <= 0) return;
-    if (b->simt && !heavy && count > 0) {
-        const int rc = mps_launch_frames(b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles,
-                                         b->cost, perm, gstride, goff, gcount, b->prof, prof_off, mask, st);
-        if (rc != 0 && b->launch_err == cudaSuccess) b->launch_err = (cudaError_t)rc;
-        return;
-    }
-    if (b->qmode && !heavy && gcount >= b->q_min_envs) {
-        // CTAs: whole waves of one CTA per SM; envs per CTA as even as possible
-        int waves = b->q_waves > 0 ? b->q_waves : 1;
-        int ctas = b->q_ctas > 0 ? b->q_ctas : b->sms * waves;
-        while ((gcount + ctas - 1) / ctas > b->q_max_k) ctas += b->q_ctas > 0 ? 1 : b->sms;
-        QArgs a;
-        a.blocks = b->blocks; a.anim = b->anim; a.n_envs = b->n_envs; a.first = first; a.count = count;
-        a.animate_before = animate_before; a.respect_passes = respect_passes; a.cycles = b->cycles; a.cost = b->cost;
-        a.perm = perm; a.gstride = gstride; a.goff = goff; a.gcount = gcount;
-        a.K = (gcount + ctas - 1) / ctas;
-        a.W = a.K < b->q_window ? a.K : b->q_window;
-        a.unit_mask = b->q_unit_mask;
-        a.heavy_slots = (b->use_sched && b->heavy_div > 0 && gstride == 1 && goff == 0) ? b->n_envs / b->heavy_div : 0;
-        a.prof = b->prof; a.prof_off = prof_off; a.mask = mask;
-        const size_t smem = (size_t)a.W * MPQ_SLOT_BYTES + 16;
-        if (b->qmode == 2) k_mp_frames_u<<<ctas, 1024, smem, st>>>(a);
-        else k_mp_frames_q<<<ctas, 1024, smem, st>>>(a);
-    } else {
 #define MP_FRAMES_ARGS b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles, b->cost, perm, \
-                       gstride, goff, gcount, b->scan_block, b->prof, prof_off, mask
+                       gstride, goff, gcount, b->scan_block, b->prof, prof_off, mask, (const int *)NULL
         if (epc >= 32) k_mp_frames<32><<<(gcount + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
         else if (epc >= 16) k_mp_frames<16><<<(gcount + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
         else if (epc >= 8) k_mp_frames<8><<<(gcount + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
         else k_mp_frames<1><<<gcount, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
 #undef MP_FRAMES_ARGS
-    }
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
 }
@@ -860,9 +616,8 @@ GroupGeom group_geom(const MpBatch *b, int G, int g)
     return q;
 }
 #define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
-// env groups of an env-step: the queue-scheduled kernel balances inside each SM and takes the whole batch as
-// one group; the lockstep kernel overlaps the launch tails of b->groups groups on their own streams
-int step_groups(const MpBatch *b) { return (b->qmode == 1 && b->n_envs >= b->q_min_envs) ? 1 : b->groups; }
+// env groups of an env-step: the launch tails of b->groups groups overlap on their own streams
+int step_groups(const MpBatch *b) { return b->groups; }
 
 int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8_t *mask, int G = 1, int g = 0)
 {
@@ -891,6 +646,29 @@ int launch_control_sim_tick(MpBatch *b, cudaStream_t st, const uint8_t *mask, in
     launch_sim_tick(b, st, 0, mask, G, g);
     launch_sim_tick(b, st, 1, mask, G, g);
     return 0;
+}
+
+// The envs whose `done` flag the step just set are reset before the step returns, all on the device: list of the
+// finished envs, reset (seeds of each env's next episode derived in the kernel), MicropolisControl.simTick and the
+// reset observation for the envs of the list.  The list kernels run on a fixed grid and walk the list, so a step
+// in which no episode ended pays six empty launches (~20 us) and nothing crosses PCIe.
+void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
+{
+    const int n = b->n_envs;
+    int grid = b->sms * 32;
+    if (grid > n) grid = n;
+    cudaMemsetAsync(b->rcount, 0, 4, st);
+    k_mp_env_auto_list<<<(n + 255) / 256, 256, 0, st>>>(b->done, step_mask, n, b->rlist, b->rcount, b->amask);
+    k_mp_env_reset_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->rlist,
+                                                               b->rcount, b->auto_terrain, b->run_seed, b->env_offset);
+    const int P = b->passes;
+    for (int t = 0; t < 2; t++)                               // MicropolisControl.simTick: simTick, animateTiles, simTick
+        k_mp_frames<1><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist, 1, 0,
+                                                    0, b->scan_block, NULL, 0, NULL, b->rcount);
+    k_mp_env_post_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->obs_out,
+                                                              b->reward, b->done, b->rlist, b->rcount);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
 }
 
 int fail(MpBatch *b, const char *what, cudaError_t e)
@@ -941,27 +719,6 @@ mpb_handle mpb_create(int n_envs, int device)
         b->sms = sms;
         b->fepc = n_envs >= sms * 32 * 4 ? 32 : (n_envs >= sms * 16 * 2 ? 16 : 8);
         b->heavy_fepc = b->fepc;
-        // queue-scheduled frames (k_mp_frames_q): one CTA per SM with K = n / SMs envs each; worth it once an SM
-        // has clearly more envs than warps.  q_unit_mask: a unit ends after the map-scan block (phase 8), the
-        // census / decay pair (10), the power scan (11) and the overlay scans + phase 0 (0).
-        b->qmode = 1;
-        b->q_min_envs = sms * 48;
-        b->q_max_k = 1 << 20;
-        b->q_window = 64;
-        b->q_waves = 1;
-        b->q_unit_mask = (1 << 8) | (1 << 10) | (1 << 11) | (1 << 0);
-        if (const char *fp = getenv("MPB_QMODE")) b->qmode = atoi(fp);
-        if (const char *fp = getenv("MPB_SIMT")) b->simt = atoi(fp);
-        if (const char *fp = getenv("MPB_Q_MIN_ENVS")) b->q_min_envs = atoi(fp);
-        if (const char *fp = getenv("MPB_Q_MAX_K")) { int v = atoi(fp); if (v >= 1) b->q_max_k = v; }
-        if (const char *fp = getenv("MPB_Q_WINDOW")) { int v = atoi(fp); if (v >= 1 && v <= MPQ_MAX_W) b->q_window = v; }
-        if (const char *fp = getenv("MPB_Q_WAVES")) b->q_waves = atoi(fp);
-        if (const char *fp = getenv("MPB_Q_CTAS")) b->q_ctas = atoi(fp);          // tests: a fixed number of CTAs
-        if (const char *fp = getenv("MPB_Q_UNIT_MASK")) b->q_unit_mask = (int)strtol(fp, NULL, 0);
-        cudaFuncSetAttribute(k_mp_frames_q, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MPQ_MAX_W * MPQ_SLOT_BYTES + 16);
-        cudaFuncSetAttribute(k_mp_frames_u, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MPQ_MAX_W * MPQ_SLOT_BYTES + 16);
     }
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
@@ -983,6 +740,9 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->cost, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->hist, (SCHED_BUCKETS + 1) * 4) == cudaSuccess
+        && cudaMalloc(&b->rlist, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->rcount, 4) == cudaSuccess
+        && cudaMalloc(&b->amask, n_envs) == cudaSuccess
         && cudaMallocHost(&b->host_blk, ENV_STRIDE) == cudaSuccess
         && cudaMallocHost(&b->host_i32, (size_t)n_envs * 16) == cudaSuccess;
     if (!ok) { mpb_destroy(b); return NULL; }
@@ -1010,6 +770,7 @@ void mpb_destroy(mpb_handle h)
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
+    cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
     cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
     if (b->host_blk) cudaFreeHost(b->host_blk);
@@ -1036,6 +797,7 @@ int mpb_launches_per_env_step(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     int total = b->use_sched ? 4 : 0;                       // memset + 3 scheduling kernels
+    if (b->auto_reset) total += 6;                          // list, reset, 2 x frames, post (+ a memset node)
     const int G = step_groups(b);
     for (int g = 0; g < G; g++) {
         const GroupGeom q = group_geom(b, G, g);
@@ -1354,7 +1116,7 @@ int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools,
     b->configured = 1;
     // MicropolisControl.__init__ builds an empty TileMap (tilemap.py:185 setEmpty)
     k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                   NULL, NULL, NULL, 0);
+                                                   NULL, NULL, NULL, 0, 0, 0);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     return 0;
@@ -1381,22 +1143,54 @@ int mpb_env_set_max_step(mpb_handle h, int max_step)
     return 0;
 }
 
+int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    b->run_seed = seed; b->env_offset = env_offset;
+    return 0;
+}
+
+int mpb_env_set_num_step(mpb_handle h, const int32_t *num_step_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    if (!num_step_host) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    memcpy(b->host_i32, num_step_host, (size_t)b->n_envs * 4);
+    CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
+    k_mp_env_set_num_step<<<(b->n_envs + 127) / 128, 128, 0, st>>>(b->shadow, b->shadow_stride, b->cfg, b->n_envs, b->i32_a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    b->auto_reset = enable ? 1 : 0; b->auto_terrain = terrain ? 1 : 0;
+    return 0;
+}
+
 int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_host,
                         const int32_t *sim_seeds_host, const uint8_t *mask_host, void *stream)
 {
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     cudaStream_t st = (cudaStream_t)stream;
-    if (terrain && (!terrain_seeds_host || !sim_seeds_host)) return -1;
+    const bool host_seeds = terrain && terrain_seeds_host && sim_seeds_host;
+    if (terrain && !host_seeds && (terrain_seeds_host || sim_seeds_host)) return -1;     // both or neither
     if (upload_mask(b, mask_host, st)) return -1;
-    if (terrain) {
+    if (host_seeds) {
         memcpy(b->host_i32, terrain_seeds_host, (size_t)b->n_envs * 4);
         memcpy(b->host_i32 + b->n_envs, sim_seeds_host, (size_t)b->n_envs * 4);
         CK(cudaMemcpyAsync(b->i32_a, b->host_i32, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->i32_b, b->host_i32 + b->n_envs, (size_t)b->n_envs * 4, cudaMemcpyHostToDevice, st));
     }
     k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
-        b->cfg, b->i32_a, b->i32_b, mask_host ? b->mask : NULL, terrain);
+        b->cfg, host_seeds ? b->i32_a : NULL, host_seeds ? b->i32_b : NULL, mask_host ? b->mask : NULL, terrain,
+        b->run_seed, b->env_offset);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -1571,6 +1365,7 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             cudaStreamWaitEvent(st, b->ev_done[g], 0);
         }
     }
+    if (b->auto_reset) launch_auto_reset(b, mask_dev, st);
     rebuild_schedule(b, st);
     CK_LAUNCHES();
     return 0;
@@ -1640,7 +1435,7 @@ int mpb_env_get_shadow(mpb_handle h, int env, uint8_t *zone_out, uint8_t *static
         double v[MPB_ENV_NUM_COUNTERS] = { (double)g.num_plants, (double)g.num_roads, (double)g.n_struct_tiles,
             (double)g.total_traffic, (double)g.num_step, (double)g.tilemap_error, g.reward, (double)g.done,
             (double)g.curr_funds, g.metrics[0], g.metrics[1], g.metrics[2], g.metrics[3], g.metrics[4],
-            g.metrics[5], 0.0 };
+            g.metrics[5], 0.0, (double)g.episode };
         {   // sprite-table overflow flag of the engine (Scalars::spriteOverflow)
             Env e;
             if (fetch_env(b, env, e)) return -1;

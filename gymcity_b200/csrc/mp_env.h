@@ -67,7 +67,11 @@ MPD void clear_map(Env &e)
 // [ALL] generate.cpp:92-110 generateSomeCity(seed), then seedRandom(sim_seed)
 MPD void generate_some_city(Env &e, int terrain_seed, int sim_seed)
 {
+#if MP_WARP_COOP
+    generate_map_coop(e, terrain_seed);
+#else
     if (e.c.lead()) generate_map(e, terrain_seed);
+#endif
     e.c.sync();
     rebuild_active(e);              // the terrain generator writes tiles in bulk
     if (e.c.lead()) {

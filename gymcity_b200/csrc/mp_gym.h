@@ -41,7 +41,23 @@ struct GymScalars {
     int32_t done, curr_funds;
     int32_t track_ages;         // TileMap.track_ages (tilemap.py:201-206), set by the Extinguisher wrapper
     int32_t paint;              // TileMap.paint (tilemap.py:74-81): MicropolisPaintEnv's one-build-per-tile-per-step rule
+    int32_t episode;            // resets this env has taken with derived seeds (gym_episode_seed): the episode index of the next one
 };
+
+// Per-episode seeds: hash of (run seed, GLOBAL env index, episode index, which) -> 31 bits; which = 0 terrain seed
+// (generateSomeCity), 1 simRandom seed.  The same function as gymcity_b200/sharding.py mix(): a rollout does not
+// depend on how the envs are sharded over GPUs, nor on whether the host or the device asked for the reset.
+MPH int32_t gym_episode_seed(uint64_t seed, uint64_t global_env, uint64_t episode, uint64_t which)
+{
+    const uint64_t v[4] = { seed, global_env, episode, which };
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (int i = 0; i < 4; i++) {
+        h ^= v[i] + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        h *= 0xbf58476d1ce4e5b9ull;
+        h ^= h >> 31;
+    }
+    return (int32_t)(h & 0x7fffffffull);
+}
 
 struct Gym {
     uint8_t *zone, *stat;       // [W*H] index x*H + y
@@ -491,7 +507,9 @@ MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim
 }
 
 // [ALL] MicropolisEnv.reset after micro.simTick() (env.py:280-292): metrics, funds, reward, state
-MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
+// keep_outputs: the worker's auto-reset (subproc_vec_env.py:16-21) hands back the reset observation together with the
+// reward and done flag of the step that ended the episode
+MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out, bool keep_outputs = false)
 {
     if (e.c.lead()) {
         gym_city_metrics(e, gy, G.metrics);                     // uses the previous total_traffic
@@ -499,8 +517,10 @@ MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t 
         e.s->totalFunds = CFG.init_funds;
         G.reward = gym_reward(gy);
         G.done = 0;
-        *reward_out = (float)G.reward;
-        *done_out = 0;
+        if (!keep_outputs) {
+            *reward_out = (float)G.reward;
+            *done_out = 0;
+        }
     }
     e.c.sync();
     gym_observe(e, gy, obs);

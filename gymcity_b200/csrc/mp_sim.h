@@ -896,9 +896,6 @@ MPQ void do_rail(Env &e, int x, int y)
 MPP void scan_tile(Env &e, int idx)
 {
     int mv = e.map()[idx], tile = mv & LOMASK;
-#if defined(MP_SIMT)
-    S.work += (mv & ZONEBIT) ? 8u : 1u;
-#endif
     int x = idx / WORLD_H, y = idx - x * WORLD_H;
     if (tile < T_ROADBASE) {
         if (tile >= T_FIREBASE) {

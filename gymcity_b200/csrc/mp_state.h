@@ -47,9 +47,10 @@ inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned
 #endif
 
 // MP_WARP_COOP: the code is compiled for the device with one WARP per env (lanes cooperate through shuffles,
-// ballots and warp barriers).  Otherwise one THREAD runs an env on its own: the host harness under tests/, and
-// the thread-per-env device build (-DMP_SIMT, mp_simt.cu) in which the 32 lanes of a warp run 32 different envs.
-#if defined(__CUDA_ARCH__) && !defined(MP_SIMT)
+// ballots and warp barriers).  Otherwise one THREAD runs an env on its own: the host harness under tests/.
+// (A thread-per-env DEVICE build, 32 different envs in the lanes of a warp, is bit-exact too and 2.8x slower:
+// profiles/r02_notes.md.)
+#if defined(__CUDA_ARCH__)
 #define MP_WARP_COOP 1
 #else
 #define MP_WARP_COOP 0
@@ -119,10 +120,7 @@ struct Scalars {
     // bulk map / state write happened.  powerPure: the
     // last scan followed a quiet interval (all its seeds were current plants) and stayed clear of the
     // capacity cut-off.  A scan that finds both set would recompute the grid it already has.
-    uint8_t powerQuiet, powerPure, pad_[2];
-    // derived, not part of the reference state: tiles mapScan visited since the schedule was last rebuilt (zone
-    // centres count 8) -- the cost key of the thread-per-env kernel, whose lanes share one clock
-    uint32_t work;
+    uint8_t powerQuiet, powerPure, pad_[6];
     int16_t curMapStack[MAX_TRAFFIC_DISTANCE + 2];   // packed x*100+y, entries 1..pointer
 };
 static_assert(sizeof(Scalars) % 8 == 0, "Scalars is copied to shared memory word by word");
@@ -183,7 +181,7 @@ struct LaneId {
 };
 struct Coop {
     LaneId tid;
-#if defined(__CUDACC__) && !defined(MP_SIMT)
+#if defined(__CUDACC__)
     static constexpr int n = 32;
 #else
     static constexpr int n = 1;

@@ -739,5 +739,269 @@ MPN void generate_map(Env &e, int seed)
     do_trees(e);
 }
 
+
+#if MP_WARP_COOP
+// ------------------------------------------------------------------ terrain generator, all 32 lanes
+// The generator above is a serial program on the lead lane: ~1.5 M instructions, 36 ms per city on one lane
+// (profiles/r01_launches.csv: k_mp_env_reset_begin = 250 ms for 32 768 cities, 13 env-steps' worth).  Its draws
+// are few and its tile work is wide, so the same map is produced with the tile work spread over the warp and the
+// draws handed out in reference order by LCG jump-ahead:
+//   * a river / lake plop is 81 (36) distinct cells: one per lane, three (two) rounds;
+//   * smoothRiver's result for an edge tile depends on whether its neighbours are "land" (dirt or woods), which
+//     no rewrite of the pass changes -- every tile of a 32-tile word is computed at once, the coin flips
+//     (getRandom(1), one draw each unless the 1-in-32768 rejection hits) ranked in scan order;
+//   * a tree splash is a random walk whose path does not depend on the map: 32 steps at a time, positions by a
+//     prefix sum of the step vectors, cut in front of the first step that touches the map border (Position::move
+//     clamps and has its NORTH_EAST / SOUTH_WEST quirks there) or whose draw is rejected -- that one step is
+//     replayed by the lead lane;
+//   * smoothTrees reads the NEW value of its west and north neighbours and the OLD value of the other two: a
+//     wavefront over the anti-diagonals x + y = d.
+// Tiles are stored directly: generate_some_city rebuilds the derived bitmaps afterwards (rebuild_active).
+MPD void gen_put(Env &e, int ch, int x, int y)                      // generate.cpp:572-598 putOnMap
+{
+    if (ch == 0 || !inb(x, y)) return;
+    int temp = e.map()[tix(x, y)];
+    if (temp != T_DIRT) {
+        temp &= LOMASK;
+        if (temp == T_RIVER && ch != T_CHANNEL) return;
+        if (temp == T_CHANNEL) return;
+    }
+    e.map()[tix(x, y)] = (uint16_t)ch;
+}
+MPD void gen_plop_b(Env &e, int px, int py)                         // generate.cpp:604-626
+{
+    MP_NOUNROLL for (int c = e.c.tid; c < 81; c += 32) {
+        const int x = c / 9, y = c - x * 9;
+        const int l = y < 4 ? 3 - y : (y > 4 ? y - 5 : 0);         // first non-empty column of the row
+        const int h = 8 - l;
+        int ch = 0;
+        if (x >= l && x <= h) ch = (x == l || x == h || y == 0 || y == 8) ? T_REDGE : T_RIVER;
+        if (x == 4 && y == 4) ch = T_CHANNEL;
+        gen_put(e, ch, px + x, py + y);
+    }
+    __syncwarp();
+}
+MPD void gen_plop_s(Env &e, int px, int py)                         // generate.cpp:632-651
+{
+    MP_NOUNROLL for (int c = e.c.tid; c < 36; c += 32) {
+        const int x = c / 6, y = c - x * 6;
+        const int l = y < 2 ? 2 - y : (y > 3 ? y - 3 : 0);
+        const int h = 5 - l;
+        int ch = 0;
+        if (x >= l && x <= h) ch = (x == l || x == h || y == 0 || y == 5) ? T_REDGE : T_RIVER;
+        gen_put(e, ch, px + x, py + y);
+    }
+    __syncwarp();
+}
+MPN int gen_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big)   // generate.cpp:498-570
+{
+    const int ext = big ? 4 : 3;
+    while (inb(px + ext, py + ext)) {
+        if (big) gen_plop_b(e, px, py); else gen_plop_s(e, px, py);
+        if (e.c.lead()) {
+            if (rnd(e, 100) < 10) terrainDir = riverDir;
+            else {
+                if (rnd(e, 200) > 90) terrainDir = rot45(terrainDir, 1);
+                if (rnd(e, 200) > 90) terrainDir = rot45(terrainDir, 7);
+            }
+            pos_move(px, py, terrainDir);
+        }
+        px = coop_bcast(e, px); py = coop_bcast(e, py); terrainDir = coop_bcast(e, terrainDir);
+    }
+    return terrainDir;
+}
+
+// generate.cpp:354-395 smoothRiver for one tile (lead lane: the tile whose coin flip was rejected)
+MPD int gen_redge_value(Env &e, int idx)
+{
+    const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
+        19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
+        5 | BULLBIT, 2 };
+    const int x = idx / WORLD_H, y = idx - x * WORLD_H;
+    int bits = 0;
+    MP_NOUNROLL for (int z = 0; z < 4; z++) {
+        bits <<= 1;
+        const int xx = x + (z == 2) - (z == 0), yy = y + (z == 1) - (z == 3);
+        if (inb(xx, yy)) {
+            const int t = e.map()[tix(xx, yy)] & LOMASK;
+            if (t != T_DIRT && (t < T_WOODS_LOW || t > T_WOODS_HIGH)) bits++;
+        }
+    }
+    return REdTab[bits & 15];
+}
+MPN void gen_smooth_river(Env &e)
+{
+    const int lane = e.c.tid;
+    MP_NOUNROLL for (int base = 0; base < NTILES; base += 32) {
+        int pos = base;
+        for (;;) {
+            const int idx = base + lane;
+            const bool mine = idx >= pos && e.map()[idx] == T_REDGE;
+            if (!__any_sync(0xffffffffu, mine)) break;
+            int temp = 0;
+            if (mine) temp = gen_redge_value(e, idx);
+            const bool draws = mine && temp != T_RIVER;
+            const unsigned dm = __ballot_sync(0xffffffffu, draws);
+            int r = 0;
+            if (draws) r = lcg_r16(lcg_jump(S.rng, __popc(dm & ((1u << lane) - 1u)) + 1));
+            const unsigned rej = __ballot_sync(0xffffffffu, draws && r >= 65534);      // getRandom(1): 65534 = 0xffff / 2 * 2
+            const int stop = rej ? __ffs(rej) - 1 : 32;
+            __syncwarp();                                                               // every neighbour read is done
+            if (mine && lane < stop) e.map()[idx] = (uint16_t)(temp + (draws ? (r & 1) : 0));
+            if (lane == 0) S.rng = lcg_jump(S.rng, __popc(stop < 32 ? (dm & ((1u << stop) - 1u)) : dm));
+            __syncwarp();
+            if (stop == 32) break;
+            if (lane == 0) {                                                            // the rejected flip, literally
+                int16_t t2 = (int16_t)gen_redge_value(e, base + stop);
+                if (t2 != T_RIVER && rnd(e, 1)) t2++;
+                e.map()[base + stop] = (uint16_t)t2;
+            }
+            __syncwarp();
+            pos = base + stop + 1;
+        }
+    }
+}
+
+// generate.cpp:410-430 smoothTrees as a wavefront over the anti-diagonals
+MPN void gen_smooth_trees(Env &e)
+{
+    const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
+    const int lane = e.c.tid;
+    MP_NOUNROLL for (int d = 0; d < WORLD_W + WORLD_H - 1; d++) {
+        const int x0 = d < WORLD_H ? 0 : d - (WORLD_H - 1), x1 = d < WORLD_W ? d : WORLD_W - 1;
+        MP_NOUNROLL for (int x = x0 + lane; x <= x1; x += 32) {
+            const int y = d - x, idx = tix(x, y);
+            if (!is_tree(e.map()[idx])) continue;
+            int bits = 0;
+            if (x > 0 && is_tree(e.map()[idx - WORLD_H])) bits |= 8;
+            if (y < WORLD_H - 1 && is_tree(e.map()[idx + 1])) bits |= 4;
+            if (x < WORLD_W - 1 && is_tree(e.map()[idx + WORLD_H])) bits |= 2;
+            if (y > 0 && is_tree(e.map()[idx - 1])) bits |= 1;
+            int temp = treeTable[bits];
+            if (temp) {
+                if (temp != T_WOODS && (d & 1)) temp -= 8;
+                temp |= BLBNBIT;
+            }
+            e.map()[idx] = (uint16_t)temp;
+        }
+        __syncwarp();
+    }
+}
+
+// generate.cpp:299-348 doTrees / treeSplash
+MPN void gen_trees(Env &e)
+{
+    const int lane = e.c.tid;
+    int amount = 0;
+    if (lane == 0) amount = rnd(e, 100) + 50;
+    amount = coop_bcast(e, amount);
+    MP_NOUNROLL for (int i = 0; i < amount; i++) {
+        int tx = 0, ty = 0, numTrees = 0;
+        if (lane == 0) { tx = rnd(e, WORLD_W - 1); ty = rnd(e, WORLD_H - 1); numTrees = rnd(e, 150) + 50; }
+        tx = coop_bcast(e, tx); ty = coop_bcast(e, ty); numTrees = coop_bcast(e, numTrees);
+        while (numTrees > 0) {
+            const int n = numTrees < 32 ? numTrees : 32;
+            const int r = lcg_r16(lcg_jump(S.rng, lane + 1));
+            const int dir = r & 7;                                     // getRandom(7) = r % 8 unless r >= 65528; D_N + dir
+            // step vector of direction D_N + dir: N NE E SE S SW W NW
+            const int dx = (dir >= 1 && dir <= 3) - (dir >= 5), dy = (dir >= 3 && dir <= 5) - (dir == 0 || dir == 1 || dir == 7);
+            int sx = dx, sy = dy;
+            MP_NOUNROLL for (int o = 1; o < 32; o <<= 1) {
+                const int ax = __shfl_up_sync(0xffffffffu, sx, o), ay = __shfl_up_sync(0xffffffffu, sy, o);
+                if (lane >= o) { sx += ax; sy += ay; }
+            }
+            const int x = tx + sx, y = ty + sy;
+            const unsigned bad = __ballot_sync(0xffffffffu, lane < n && (r >= 65528 || !inb(x, y)));
+            const int stop = bad ? __ffs(bad) - 1 : n;                 // steps [0, stop) are plain moves
+            if (lane < stop && (e.map()[tix(x, y)] & LOMASK) == T_DIRT) e.map()[tix(x, y)] = (uint16_t)(T_WOODS | BLBNBIT);
+            if (stop > 0) {
+                tx = __shfl_sync(0xffffffffu, x, stop - 1);
+                ty = __shfl_sync(0xffffffffu, y, stop - 1);
+                if (lane == 0) S.rng = lcg_jump(S.rng, stop);
+            }
+            numTrees -= stop;
+            __syncwarp();
+            if (stop < n) {                                            // the step at the border / the rejected draw, literally
+                if (lane == 0) {
+                    const int d2 = D_N + rnd(e, 7);
+                    pos_move(tx, ty, d2);
+                    if ((e.map()[tix(tx, ty)] & LOMASK) == T_DIRT) e.map()[tix(tx, ty)] = (uint16_t)(T_WOODS | BLBNBIT);
+                }
+                tx = coop_bcast(e, tx); ty = coop_bcast(e, ty);
+                numTrees--;
+                __syncwarp();
+            }
+        }
+    }
+    gen_smooth_trees(e);
+    gen_smooth_trees(e);
+}
+
+// [ALL] generate.cpp:119-160 generateMap(seed), same map and same final RNG state as generate_map above
+MPN void generate_map_coop(Env &e, int seed)
+{
+    const int lane = e.c.tid;
+    int island = 0;
+    if (lane == 0) { S.rng = (uint32_t)seed; island = rnd(e, 100) < 10; }
+    island = coop_bcast(e, island);
+    if (island) {                                                      // makeNakedIsland generate.cpp:193-231
+        MP_NOUNROLL for (int i = lane; i < NTILES; i += 32) {
+            const int x = i / WORLD_H, y = i - x * WORLD_H;
+            e.map()[i] = (x < 5 || x >= WORLD_W - 5 || y < 5 || y >= WORLD_H - 5) ? T_RIVER : T_DIRT;
+        }
+        __syncwarp();
+        MP_NOUNROLL for (int x = 0; x < WORLD_W - 5; x += 2) {
+            int a = 0, b = 0;
+            if (lane == 0) { a = ernd(e, 18); b = (WORLD_H - 10) - ernd(e, 18); }
+            a = coop_bcast(e, a); b = coop_bcast(e, b);
+            gen_plop_b(e, x, a);
+            gen_plop_b(e, x, b);
+            gen_plop_s(e, x, 0);
+            gen_plop_s(e, x, WORLD_H - 6);
+        }
+        MP_NOUNROLL for (int y = 0; y < WORLD_H - 5; y += 2) {
+            int a = 0, b = 0;
+            if (lane == 0) { a = ernd(e, 18); b = (WORLD_W - 10) - ernd(e, 18); }
+            a = coop_bcast(e, a); b = coop_bcast(e, b);
+            gen_plop_b(e, a, y);
+            gen_plop_b(e, b, y);
+            gen_plop_s(e, 0, y);
+            gen_plop_s(e, WORLD_W - 6, y);
+        }
+    } else {
+        MP_NOUNROLL for (int i = lane; i < NTILES; i += 32) e.map()[i] = T_DIRT;
+        __syncwarp();
+        int xs = 0, ys = 0, riverDir = 0;
+        if (lane == 0) { xs = 40 + rnd(e, WORLD_W - 80); ys = 33 + rnd(e, WORLD_H - 67); riverDir = D_N + rnd(e, 3) * 2; }
+        xs = coop_bcast(e, xs); ys = coop_bcast(e, ys); riverDir = coop_bcast(e, riverDir);
+        gen_river(e, xs, ys, riverDir, riverDir, true);                // doRivers generate.cpp:478-495
+        riverDir = rot45(riverDir, 4);
+        const int terrainDir = gen_river(e, xs, ys, riverDir, riverDir, true);
+        if (lane == 0) riverDir = D_N + rnd(e, 3) * 2;
+        riverDir = coop_bcast(e, riverDir);
+        gen_river(e, xs, ys, riverDir, terrainDir, false);
+        int numLakes = 0;                                              // makeLakes generate.cpp:249-291
+        if (lane == 0) numLakes = rnd(e, 10);
+        numLakes = coop_bcast(e, numLakes);
+        while (numLakes > 0) {
+            int x = 0, y = 0, numPlops = 0;
+            if (lane == 0) { x = rnd(e, WORLD_W - 21) + 10; y = rnd(e, WORLD_H - 20) + 10; numPlops = rnd(e, 12) + 2; }
+            x = coop_bcast(e, x); y = coop_bcast(e, y); numPlops = coop_bcast(e, numPlops);
+            while (numPlops > 0) {
+                int oy = 0, ox = 0, small = 0;
+                if (lane == 0) { oy = rnd(e, 12) - 6; ox = rnd(e, 12) - 6; small = rnd(e, 4); }   // y offset first (see generate_map)
+                oy = coop_bcast(e, oy); ox = coop_bcast(e, ox); small = coop_bcast(e, small);
+                if (small) gen_plop_s(e, x + ox, y + oy); else gen_plop_b(e, x + ox, y + oy);
+                numPlops--;
+            }
+            numLakes--;
+        }
+    }
+    gen_smooth_river(e);
+    gen_trees(e);
+    __syncwarp();
+}
+#endif
+
 #undef S
 } // namespace mp

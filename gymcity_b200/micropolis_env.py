@@ -78,7 +78,7 @@ class _ShadowMap:
     def counters(self, env=0):
         k = self._shadow(env)[3]
         names = ["num_plants", "num_roads", "n_struct_tiles", "total_traffic", "num_step", "tilemap_error",
-                 "reward", "done", "funds"] + METRICS + ["sprite_overflow"]
+                 "reward", "done", "funds"] + METRICS + ["sprite_overflow", "episode"]
         return dict(zip(names, [float(v) for v in k]))
 
 
@@ -144,6 +144,8 @@ class MicropolisControl:
             "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
             "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
             "mpb_env_step_masked": (i32, [vp, vp, i32, vp, vp]),
+            "mpb_env_set_seed": (i32, [vp, C.c_longlong, i32]), "mpb_env_set_auto_reset": (i32, [vp, i32, i32]),
+            "mpb_env_set_num_step": (i32, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -175,9 +177,9 @@ class MicropolisControl:
         return self.apply_actions(self._flat(AGENT_TOOLS.index(tool), x, y), static_build, full_tools=True)
 
     def counters(self):
-        """(N, 16) array: num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error,
-        reward, done, funds, metrics[6], sprite_overflow for every env."""
-        out = np.zeros((self.num_envs, 16), np.float64)
+        """(N, 17) array: num_plants, num_roads, n_struct_tiles, total_traffic, num_step, tilemap_error,
+        reward, done, funds, metrics[6], sprite_overflow, episode for every env."""
+        out = np.zeros((self.num_envs, 17), np.float64)
         self._ck(self._L.mpb_env_get_counters(self._h, out.ctypes.data))
         return out
 
@@ -202,6 +204,12 @@ class MicropolisControl:
         a, b = self.engine._i32(terrain_seeds), self.engine._i32(sim_seeds)
         m, p = EngineBatch._mask(mask, self.num_envs)
         self._ck(self._L.mpb_env_reset_begin(self._h, 1, a.ctypes.data, b.ctypes.data, p, self.engine._stream()))
+
+    def newMapDerived(self, mask=None):
+        """clearMap + generateSomeCity with the seeds of each env's next episode, derived on the device from
+        (seed, global env index, episode) -- mpb_env_set_seed; sharding.mix is the same hash on the host."""
+        m, p = EngineBatch._mask(mask, self.num_envs)
+        self._ck(self._L.mpb_env_reset_begin(self._h, 1, None, None, p, self.engine._stream()))
 
     def getDensityMaps(self):                               # corecontrol.py:215-239 -> obs planes 22..24
         return self.obs[:, 22:25]
@@ -243,6 +251,8 @@ class MicropolisEnv:
     def seed(self, seed=None):                              # env.py:91-98
         self._seed = 0 if seed is None else int(seed)
         self.np_random = np.random.default_rng(self._seed)
+        if hasattr(self, 'micro'):
+            self.micro._ck(self.micro._L.mpb_env_set_seed(self.micro._h, self._seed, self.env_offset))
         return [self._seed]
 
     def setMapSize(self, size, max_step=None, rank=0, print_map=False, PADDING=0, static_builds=True,
@@ -269,6 +279,8 @@ class MicropolisEnv:
         self.micro = MicropolisControl(self, self.MAP_X, self.MAP_Y, PADDING, rank=rank,
                                        power_puzzle=power_puzzle, gui=render_gui, num_envs=self.num_envs,
                                        device=self.device, MAP_XS=MAP_XS, MAP_YS=MAP_YS, max_step=self.max_step)
+        self.micro._ck(self.micro._L.mpb_env_set_seed(self.micro._h, self._seed, self.env_offset))
+        self._device_auto_reset = False
         self.num_step = 0
         self.minFunds = 0
         self.initFunds = self.micro.init_funds
@@ -298,15 +310,18 @@ class MicropolisEnv:
         done = m.done.bool()
         if not self.auto_reset:                              # env.py:519-520: terminal = (...) and self.auto_reset
             done = done & False
-        return self._cur_obs(), m.reward, done, [{} for _ in range(self.num_envs)]
+        return self._cur_obs(), m.reward, done, _Infos(self.num_envs)
 
     def _cur_obs(self):
         obs = getattr(self, "_obs_out", None)
         return self.micro.obs if obs is None else obs
 
-    def _episode_seeds(self, which):
+    def episode_seeds(self, which, episodes=None):
+        """The seeds the device derives for the NEXT reset of every env (which = 0 terrain, 1 simulation):
+        sharding.mix(seed, global env index, episode of the env, which).  For tests and reference runs."""
+        ep = self.micro.counters()[:, 16].astype(np.int64) if episodes is None else np.broadcast_to(episodes, (self.num_envs,))
         g = np.arange(self.num_envs) + self.env_offset
-        return np.array([_mix(self._seed, int(i), self.num_episode, which) for i in g], np.int32)
+        return np.array([_mix(self._seed, int(i), int(k), which) for i, k in zip(g, ep)], np.int32)
 
     def get_param_bounds(self):
         return self.param_bounds
@@ -355,7 +370,7 @@ class MicropolisEnv:
         if self.empty_start:
             m.clearMap(mask)
         else:
-            m.newMap(self._episode_seeds(0), self._episode_seeds(1), mask)
+            m.newMapDerived(mask)                            # seeds: episode_seeds(), derived in the kernel
         self.num_step = 0
         if self.power_puzzle and setup_actions is None:
             self.powerPuzzle(mask)
@@ -399,6 +414,11 @@ class MicropolisEnv:
             a = np.ascontiguousarray(a)
             m._ck(m._L.mpb_env_step_masked(m._h, a.ctypes.data, 1, mk.ctypes.data, m.engine._stream()))
 
+    def set_num_steps(self, num_step):
+        """Per-env MicropolisEnv.num_step (N,): episodes of different envs end on different steps."""
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(num_step, np.int32), (self.num_envs,)))
+        self.micro._ck(self.micro._L.mpb_env_set_num_step(self.micro._h, a.ctypes.data, self.micro.engine._stream()))
+
     def set_obs_buffer(self, out=None):
         """Observations of the following steps / resets go to `out` (float32 CUDA tensor (N,32,W,H),
         contiguous -- e.g. RolloutStorage.obs[step + 1]) instead of the env's own buffer; None restores it."""
@@ -417,7 +437,7 @@ class MicropolisEnv:
     def step(self, a, static_build=False, out=None):         # env.py:448-540
         import torch
         m = self.micro
-        if out is not None or getattr(self, "_obs_out", None) is not None:
+        if out is not None:                                   # an explicit set_obs_buffer() stays in force otherwise
             self.set_obs_buffer(out)
         if torch.is_tensor(a):
             act = a.reshape(-1).to(device="cuda:%d" % self.device, dtype=torch.int64).contiguous()
@@ -463,6 +483,25 @@ class _IntsToActions:
         return [i // n, (i % n) // self.H, i % self.H]
 
 
+class _Infos:
+    """The per-env info dicts of a step (the reference's workers return {} each): a sequence of N empty dicts
+    that costs nothing until someone indexes it (a list of 32 768 fresh dicts per step is ~2 ms of Python)."""
+
+    def __init__(self, n):
+        self._n, self._d = n, None
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if self._d is None:
+            self._d = [{} for _ in range(self._n)]
+        return self._d[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
 class MicropolisVecEnv(MicropolisEnv):
     """The batch as the vec env (envs.py:347-375, 406-444): reset() -> obs, step(actions (N,1)) ->
     (obs, reward (N,1), done (N,), infos), with the worker's auto-reset (subproc_vec_env.py:16-21)."""
@@ -472,7 +511,24 @@ class MicropolisVecEnv(MicropolisEnv):
         self.seed(seed)
         self.setMapSize(size, **kwargs)
 
+    def setMapSize(self, size, **kwargs):
+        super().setMapSize(size, **kwargs)
+        self.set_device_auto_reset(self.num_envs > 1 and not self.power_puzzle and not self.random_builds)
+
+    def set_device_auto_reset(self, on):
+        """The worker's auto-reset (subproc_vec_env.py:16-21) inside the step, on the device: no `done.any()`
+        round trip, no host-side reset call.  Off for the variants whose reset needs host-drawn set-up builds
+        (powerPuzzle, randomStaticStart): those keep the host path below."""
+        self._device_auto_reset = bool(on)
+        self.micro._ck(self.micro._L.mpb_env_set_auto_reset(self.micro._h, int(bool(on) and self.auto_reset),
+                                                            int(not self.empty_start)))
+
     def step(self, a, static_build=False, out=None):
+        if self._device_auto_reset:
+            if not self.auto_reset:                                      # switched off after setMapSize
+                self.set_device_auto_reset(False)
+            else:
+                return super().step(a, static_build, out=out)            # done envs come back already reset
         obs, reward, done, infos = super().step(a, static_build, out=out)
         if self.num_envs == 1:
             if done:
@@ -504,11 +560,13 @@ class MicropolisPaintEnv(MicropolisVecEnv):
         if not torch.is_tensor(a):
             a = torch.as_tensor(np.asarray(a))
         t = a.to(device=dev).reshape(self.num_envs, self.MAP_X * self.MAP_Y).to(torch.uint8).contiguous()
-        if out is not None or getattr(self, "_obs_out", None) is not None:
+        if out is not None:
             self.set_obs_buffer(out)
         m._ck(m._L.mpb_env_step_paint(m._h, t.data_ptr(), m.engine._stream()))
         self.num_step += 1
         obs, reward, done, infos = self._out()
+        if self._device_auto_reset and self.auto_reset:
+            return obs, reward, done, infos
         if self.num_envs > 1 and self.auto_reset and bool(done.any().item()):
             mask = done.cpu().numpy()
             done, reward = done.clone(), reward.clone()

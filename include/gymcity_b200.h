@@ -60,6 +60,12 @@ int golb_get_state(golb_handle h, uint8_t *cells_host);
 /* GoLMultiEnv.step (multi_env.py:170-232) / GameOfLifeEnv.step (env.py:125-182):
  * actions_dev = int64 [n_envs] DEVICE pointer, flat index a = x*W + y. */
 int golb_step(golb_handle h, const int64_t *actions_dev, void *stream);
+/* T steps in ONE launch (multi-env handles): actions_dev = int64 [T, n_envs]; tick t's observation goes to
+ * obs_seq_dev[t] (float32 [T, n_envs, 2, W, W], both planes) and its reward to reward_seq_dev[t] (float32
+ * [T, n_envs]) when given (either may be NULL); the handle's own obs / reward / pop / done hold the last tick's.
+ * Same state as T golb_step calls (multi_env.py:170-232 x T).  For scripted / random-action rollouts: at 4 096
+ * boards a tick is ~1 us of GPU work and a launch per tick is launch-bound. */
+int golb_step_n(golb_handle h, const int64_t *actions_dev, int T, float *obs_seq_dev, float *reward_seq_dev, void *stream);
 
 /* Same, end to end with HOST buffers: copies actions H2D, steps, copies rewards D2H, syncs. */
 int golb_step_host(golb_handle h, const int64_t *actions_host, float *reward_host, void *stream);
@@ -155,7 +161,7 @@ enum mpb_env_buffer {
     MPB_ENV_REWARD,      /* float32 [n_envs]                                                     */
     MPB_ENV_DONE         /* uint8 [n_envs]                                                       */
 };
-#define MPB_ENV_NUM_COUNTERS 16
+#define MPB_ENV_NUM_COUNTERS 17
 int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools, const int8_t *tool_zone,
                       const int8_t *tool_engine, int max_step, const double *trg, const double *weight);
 int mpb_env_set_targets(mpb_handle h, const double *trg, const double *weight);   /* env.py:419-424 */
@@ -165,6 +171,21 @@ int mpb_env_set_max_step(mpb_handle h, int max_step);
  * builds (powerPuzzle / randomStaticStart) go through mpb_env_action before the second half. */
 int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_host,
                         const int32_t *sim_seeds_host, const uint8_t *mask_host, void *stream);
+/* Seeds derived on the device.  The reference seeds its engine from the wall clock (random.cpp:155-164); here every
+ * episode of every env has a terrain seed and a simulation seed = hash(seed, env_offset + i, episode_i, which),
+ * episode_i = the number of derived-seed resets env i has taken (counter 16).  mpb_env_reset_begin with
+ * terrain != 0 and both seed arrays NULL uses them; so does the auto-reset below.  env_offset = global index of
+ * env 0 (sharding: results do not depend on the number of GPUs). */
+int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset);
+/* The vec-env worker's auto-reset (subproc_vec_env.py:16-21: `if done: ob = env.reset()`), on the device: with
+ * enable != 0 every mpb_env_step / _step_host / _step_paint / _step_masked ends by resetting the envs whose done
+ * flag it set (terrain != 0: clearMap + generateSomeCity with the env's next derived seeds; 0: clearMap only),
+ * running the reset's simTick for them and writing their reset observation.  Reward and done stay those of the
+ * step that ended the episode.  No host round trip: the finished envs are a device-side list. */
+int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain);
+/* MicropolisEnv.num_step of every env (int32 [n_envs] HOST): episodes that end on different steps (in the reference
+ * every worker counts its own steps, env.py:448-460; randomStaticStart gives each its own offset, env.py:228-241). */
+int mpb_env_set_num_step(mpb_handle h, const int32_t *num_step_host, void *stream);
 /* reset, second half (env.py:279-292): simTick, metrics, setFunds, reward, observation. */
 int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream);
 /* MicropolisControl.takeAction without a tick: actions_host = int64 [n_envs] flat action index

@@ -33,6 +33,22 @@ def test_construct_and_terrain():
     b.close()
 
 
+def test_terrain_generator_256_seeds():
+    """generateSomeCity on all 32 lanes (generate_map_coop: plops a lane per cell, smoothRiver by word with ranked coin
+    flips, tree splashes 32 steps at a time, smoothTrees as a wavefront) against the reference generator: map, RNG
+    state and everything doSimInit derives from them.  256 seeds cover islands (1 in 10), walks along the map border
+    and rejected draws (about 1.5 per map)."""
+    n = 256
+    b, refs = _mk(n)
+    ts, ss = np.arange(n) * 7919 + 1, np.arange(n)
+    b.generate(ts, ss)
+    for i, r in enumerate(refs):
+        r.generate(int(ts[i]))
+        r.seed(int(ss[i]))
+    _check(b, refs, "generate256")
+    b.close()
+
+
 @pytest.mark.parametrize("terrain,steps,n", [(True, 120, 8), (False, 60, 4)])
 def test_random_action_rollout(terrain, steps, n):
     """BASELINE config 1 shape: 16x16 window at (16,8), uniform random tools, env-ticks of

@@ -273,46 +273,73 @@ def test_masked_reset_leaves_other_envs_untouched():
     env.close()
 
 
-@pytest.mark.parametrize("qmode", ["1", "2"])
-@pytest.mark.parametrize("unit_mask,window,heavy_div", [("0x0d01", 64, 64), ("0xffff", 12, 64), ("0x0100", 40, 4),
-                                                        ("0x0d01", 5, 8)])
-def test_queue_scheduled_frames_match_oracle(unit_mask, window, heavy_div, qmode, monkeypatch):
-    """The queue-scheduled frame kernel (k_mp_frames_q), forced onto a small batch: 40 envs share ONE CTA's ready
-    queue (envs are re-queued and change warps), with different unit boundaries, windows smaller than the env list
-    (envs retire and their successors take the slot) and smaller than the warp count, and heavy envs that run
-    unqueued to the end of a launch."""
-    monkeypatch.setenv("MPB_QMODE", qmode)          # 1: FIFO of ready envs, 2: unit lockstep with a shared work counter
-    monkeypatch.setenv("MPB_GROUPS", "1")
-    monkeypatch.setenv("MPB_Q_MIN_ENVS", "1")
-    monkeypatch.setenv("MPB_Q_CTAS", "1")
-    monkeypatch.setenv("MPB_Q_UNIT_MASK", unit_mask)
-    monkeypatch.setenv("MPB_Q_WINDOW", str(window))
-    monkeypatch.setenv("MPB_HEAVY_DIV", str(heavy_div))
-    n, size, steps = 40, 16, 40
-    seeds = np.arange(n) + 300
-    env, refs = _batch(n, size, True, 1000, seeds)
-    _finish(env, refs)
-    rng = np.random.default_rng(11)
-    for t in range(steps):
-        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), bool(rng.random() < 0.2), t)
+def test_device_auto_reset_matches_reference_workers():
+    """MicropolisVecEnv with the auto-reset inside the step (mpb_env_set_auto_reset): episodes of different envs
+    end on different steps (a masked reset up front staggers them), each finished env comes back with its reset
+    observation and the terminal step's reward / done (subproc_vec_env.py:16-21), its next episode is seeded with
+    sharding.mix(seed, global index, episode, which), and nobody else is touched -- against one reference env per
+    worker doing exactly that."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    from gymcity_b200.sharding import mix
+    n, size, max_step, seed, off = 6, 16, 7, 11, 40
+    env = MicropolisVecEnv(n, size, seed=seed, max_step=max_step, empty_start=False, env_offset=off)
+    assert env._device_auto_reset
+    refs = [RefEnv(RefEngine(), size, max_step=max_step, empty_start=False) for _ in range(n)]
+    episode = np.zeros(n, int)
+
+    def ref_reset(i):
+        refs[i].reset_begin(mix(seed, off + i, episode[i], 0), mix(seed, off + i, episode[i], 1))
+        episode[i] += 1
+        return refs[i].reset_finish().astype(np.float32)
+
+    obs = env.reset().cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(ref_reset(i), obs[i]), i
+    rng = np.random.default_rng(5)
+    n_resets, ended = 0, [[] for _ in range(n)]
+    for t in range(40):
+        if t == 3:                                           # stagger: envs 1 and 4 start a new episode now
+            mask = np.array([0, 1, 0, 0, 1, 0], bool)
+            obs = env.reset(mask=mask).cpu().numpy()
+            for i in np.flatnonzero(mask):
+                assert np.array_equal(ref_reset(i), obs[i]), i
+        acts = rng.integers(0, 20 * size * size, n).astype(np.int64)
+        obs, rew, done, infos = env.step(torch.from_numpy(acts))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy().reshape(-1), done.cpu().numpy()
+        assert len(infos) == n and infos[0] == {}
+        for i, r in enumerate(refs):
+            o, rr, d, _ = r.step(int(acts[i]), False)
+            assert rr == rew[i] and d == bool(done[i]), (t, i, rr, rew[i], d, done[i])
+            if d:
+                o = ref_reset(i)
+                n_resets += 1
+                ended[i].append(t)
+            assert np.array_equal(np.asarray(o, np.float32), obs[i]), (t, i)
+    assert n_resets >= 20 and ended[0] != ended[1] and ended[1] == ended[4]   # staggered episodes, several resets each
+    assert np.array_equal(env.micro.counters()[:, 16], episode)
     for i, r in enumerate(refs):
         assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
-    assert not env.micro.counters()[:, 15].any()                # no sprite-table overflow
     env.close()
 
 
-def test_thread_per_env_frames_match_oracle(monkeypatch):
-    """The frames run one THREAD per env (mp_simt.cu: the engine headers compiled with Coop::n = 1, 32 different envs
-    in the lanes of a warp) -- same rollout as the reference, every observation and the final engine state."""
-    monkeypatch.setenv("MPB_SIMT", "1")
-    n, size, steps = 70, 16, 60
-    seeds = np.arange(n) + 500
-    env, refs = _batch(n, size, True, 1000, seeds)
-    _finish(env, refs)
-    rng = np.random.default_rng(12)
-    for t in range(steps):
-        _compare_step(env, refs, rng.integers(0, 20 * size * size, n).astype(np.int64), bool(rng.random() < 0.2), t)
-    for i, r in enumerate(refs):
-        assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
-    assert not env.micro.counters()[:, 15].any()
+def test_sticky_obs_buffer_and_per_call_out():
+    """set_obs_buffer(X) stays in force for plain step(a) calls; step(a, out=Y) switches to Y."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    env = MicropolisVecEnv(4, 16, seed=1, max_step=50, empty_start=False)
+    env.reset()
+    dev = env.micro.obs.device
+    X, Y = torch.zeros_like(env.micro.obs), torch.zeros_like(env.micro.obs)
+    env.set_obs_buffer(X)
+    a = torch.zeros(4, dtype=torch.int64, device=dev)
+    o1, *_ = env.step(a)
+    assert o1.data_ptr() == X.data_ptr() and float(X.abs().sum()) > 0
+    o2, *_ = env.step(a)
+    assert o2.data_ptr() == X.data_ptr()
+    o3, *_ = env.step(a, out=Y)
+    assert o3.data_ptr() == Y.data_ptr() and float(Y.abs().sum()) > 0
+    env.set_obs_buffer(None)
+    o4, *_ = env.step(a)
+    assert o4.data_ptr() == env.micro.obs.data_ptr()
     env.close()

@@ -16,12 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 DEFAULT = [
-    "lockstep=MPB_QMODE:0",
-    "simt_g3=MPB_QMODE:0,MPB_SIMT:1",
-    "simt_g1=MPB_QMODE:0,MPB_SIMT:1,MPB_GROUPS:1",
-    "simt_g3_f100=MPB_QMODE:0,MPB_SIMT:1,MPB_FRAMES_PER_LAUNCH:100",
-    "simt_g3_f25=MPB_QMODE:0,MPB_SIMT:1,MPB_FRAMES_PER_LAUNCH:25",
-    "simt_g3_h16=MPB_QMODE:0,MPB_SIMT:1,MPB_HEAVY_DIV:16",
+    "default=",
+    "groups1=MPB_GROUPS:1",
+    "f25=MPB_FRAMES_PER_LAUNCH:25",
+    "f100=MPB_FRAMES_PER_LAUNCH:100",
 ]
 
 
