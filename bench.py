@@ -6,9 +6,15 @@
 
 Workload (config.workload): MicropolisEnv 16x16 build window at (16,8) in the 120x100 world, terrain
 path (simulation live), uniform random actions, E envs per GPU (weak scaling; E = 32768 = BASELINE
-config 5's per-GPU share at 8 GPUs).  One step = one env-tick for every env of the batch = one fused
-kernel launch: action through the TileMap clear-then-build logic, setFunds, 2 x 100 simFrames +
-animateTiles, observation / reward / done.
+config 5's per-GPU share at 8 GPUs), observations written in place into an A2C rollout buffer
+obs[T+1, E, 32, 16, 16].  One step = one env-tick for every env of the batch: action through the TileMap
+clear-then-build logic, setFunds, 2 x 100 simFrames + animateTiles, observation / reward / done.
+
+At N = 1 the line also carries `extra_workloads`: the headline with episodes (max_step 200, staggered, device-side
+auto-reset inside the timed region), the same through MicropolisVecEnv.step, BASELINE config 4 (120x100, 2048 envs),
+config 3 (32x32 power puzzle, 8192 envs) and config 2 (Game of Life 16x16, 4096 and 1 M boards), each with its
+roofline fraction and CPU arm.  `step_ms` gives min / median / max of the per-step times: the random-action cities
+keep ageing (no reset in the headline), so the workload drifts slowly over the timed steps.
 """
 import argparse
 import json
@@ -129,11 +135,136 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def ms_stats(ms):
+    s = sorted(ms)
+    return {"min": s[0], "median": s[len(s) // 2], "max": s[-1], "first": ms[0], "last": ms[-1], "n": len(ms)}
+
+
+def time_steps(step, K, stream, dev):
+    """K calls of step(i) timed with CUDA events on `stream`: (total ms, per-step ms list)."""
+    import torch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record(stream)
+    for i in range(K):
+        step(i)
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    return ev[0].elapsed_time(ev[K]), [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+
+
+def divergence_flags(m):
+    """Sticky per-env flags that must be understood before a rollout counts as bit-exact: sprite_overflow (an env
+    needed more sprite slots than the table has; the reference's list is unbounded) must be 0; tilemap_error
+    counts envs in which the reference's Python TileMap would have died with a KeyError (tilemap.py:488-491)."""
+    c = m.counters()
+    return {"sprite_overflow_envs": int((c[:, 15] != 0).sum()), "tilemap_error_envs": int((c[:, 5] != 0).sum())}
+
+
+def make_env(name, E, local, rank, seed, max_step=10 ** 9, vec=False):
+    from gymcity_b200.micropolis_env import MicropolisEnv, MicropolisVecEnv
+    wl = WORKLOADS[name]
+    kw = dict(max_step=max_step, empty_start=False, power_puzzle=wl["puzzle"], MAP_XS=wl["xs"], MAP_YS=wl["ys"])
+    if vec:
+        return MicropolisVecEnv(E, wl["size"], device=local, env_offset=rank * E, seed=seed, **kw)
+    env = MicropolisEnv(num_envs=E, device=local, env_offset=rank * E)
+    env.seed(seed)
+    env.setMapSize(wl["size"], **kw)
+    return env
+
+
+def run_extra_mp(name, args, local, dev, K, age, cpu_seconds):
+    """A BASELINE config other than the headline, through the same code: value, per-step times, roofline, CPU arm."""
+    import torch
+    wl = WORKLOADS[name]
+    E = wl["envs"]
+    cb = None if args.no_cpu_baseline else cpu_reference(cpu_seconds, name)
+    env = make_env(name, E, local, 0, args.seed)
+    env.reset()
+    m = env.micro
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed * 1000 + 17)
+    acts = torch.randint(0, env.action_space.n, (age + 3 + K, E), device=dev, dtype=torch.int64, generator=g)
+    sp, stream = m.engine._stream(), torch.cuda.current_stream(dev)
+    for i in range(age + 3):
+        m._ck(m._L.mpb_env_step(m._h, acts[i].data_ptr(), 0, sp))
+    torch.cuda.synchronize(dev)
+    total_ms, ms = time_steps(lambda i: m._ck(m._L.mpb_env_step(m._h, acts[age + 3 + i].data_ptr(), 0, sp)), K, stream, dev)
+    peak, _ = hbm_peak()
+    B = b_tick(env.MAP_X, env.MAP_Y)
+    achieved = B * E / (total_ms / K / 1000.0) / 1e9
+    out = {"workload": "%s, %d envs" % (wl["text"], E), "value": E * K / (total_ms / 1000.0), "unit": UNIT, "steps": K,
+           "age_steps": age, "ms_per_step": total_ms / K, "step_ms": ms_stats(ms),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "algorithmic_bytes_per_env_tick": B},
+           "cpu_baseline": cb, "flags": divergence_flags(m)}
+    env.close()
+    return out
+
+
+def run_episode_and_venv(args, local, dev, K):
+    """The headline workload the way the reference's training loop runs it: episodes of max_step = 200 env-ticks
+    (arguments.py:134), every env at its own point of its episode (num_step staggered uniformly, as the workers of a
+    SubprocVecEnv drift apart), finished envs reset inside the step on the device -- terrain generation, the
+    reset's simTick and its observation are inside the timed region.  Then the same env through the Python vec-env
+    API (MicropolisVecEnv.step: what envs.py:363-375 calls), wall clock with a device sync at both ends."""
+    import numpy as np
+    import torch
+    E, max_step = WORKLOADS["mp16"]["envs"], 200
+    env = make_env("mp16", E, local, 0, args.seed, max_step=max_step, vec=True)
+    assert env._device_auto_reset
+    env.reset()
+    env.set_num_steps((np.arange(E, dtype=np.int64) * max_step // E).astype(np.int32))
+    m = env.micro
+    g = torch.Generator(device=dev)
+    g.manual_seed(args.seed * 1000 + 29)
+    pool = 64
+    acts = torch.randint(0, env.action_space.n, (pool, E), device=dev, dtype=torch.int64, generator=g)
+    sp, stream = m.engine._stream(), torch.cuda.current_stream(dev)
+    ep0 = m.counters()[:, 16].sum()
+    for i in range(max_step + 5):                    # one full episode length: every env has been reset once, ages uniform
+        m._ck(m._L.mpb_env_step(m._h, acts[i % pool].data_ptr(), 0, sp))
+    torch.cuda.synchronize(dev)
+    ep1 = m.counters()[:, 16].sum()
+    total_ms, ms = time_steps(lambda i: m._ck(m._L.mpb_env_step(m._h, acts[i % pool].data_ptr(), 0, sp)), K, stream, dev)
+    ep2 = m.counters()[:, 16].sum()
+    import ctypes as C
+    ar_ms, ar_n = C.c_float(), C.c_int()
+    m._L.mpb_auto_reset_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    m._ck(m._L.mpb_auto_reset_time(m._h, C.byref(ar_ms), C.byref(ar_n)))
+    episode = {"workload": "mp16 with episodes: max_step 200, per-env staggered num_step, device-side auto-reset "
+                           "(terrain generation + reset tick + reset observation inside the timed region)",
+               "value": E * K / (total_ms / 1000.0), "unit": UNIT, "steps": K, "ms_per_step": total_ms / K,
+               "step_ms": ms_stats(ms), "resets_in_timed_region": int(ep2 - ep1), "resets_during_ageing": int(ep1 - ep0),
+               "auto_reset_part_of_last_step_ms": ar_ms.value, "resets_in_last_step": ar_n.value,
+               "flags": divergence_flags(m)}
+    a2 = acts.reshape(pool, E, 1)
+    for i in range(3):
+        env.step(a2[i])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(K):
+        obs, rew, done, infos = env.step(a2[i % pool])
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    venv = {"workload": "the same env through MicropolisVecEnv.step(actions (N,1) CUDA tensor) -> (obs, reward, done, "
+                        "infos), device auto-reset on; wall clock, device sync at both ends",
+            "value": E * K / dt, "unit": UNIT, "steps": K, "ms_per_step": dt * 1000.0 / K}
+    env.close()
+    return episode, venv
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from gymcity_b200.micropolis_env import MicropolisEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -149,11 +280,7 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         cb = cpu_reference(args.cpu_seconds, args.workload)
 
-    wl = WORKLOADS[args.workload]
-    env = MicropolisEnv(num_envs=E, device=local, env_offset=rank * E)
-    env.seed(args.seed)
-    env.setMapSize(wl["size"], max_step=10 ** 9, empty_start=False, power_puzzle=wl["puzzle"], MAP_XS=wl["xs"],
-                   MAP_YS=wl["ys"])
+    env = make_env(args.workload, E, local, rank, args.seed)
     env.reset()
     m = env.micro
     nA = env.action_space.n
@@ -189,16 +316,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    ev[0].record(stream)
-    for i in range(K):
-        step_dev(W + i)
-        ev[i + 1].record(stream)
-    torch.cuda.synchronize(dev)
+    total_ms, kern_ms = time_steps(lambda i: step_dev(W + i), K, stream, dev)
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[K])
-    kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
     # end to end through the host-buffer entry point: H2D actions, step, D2H reward + done, every step
     acts_host = acts[W + K: W + 2 * K].cpu().numpy()
     rew_h, done_h = np.zeros(E, np.float32), np.zeros(E, np.uint8)
@@ -219,30 +339,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0].item()), float(t[1].item())
     checksum = float(m.reward.sum().item())
+    flags = divergence_flags(m)
+    if flags["sprite_overflow_envs"]:
+        raise RuntimeError("sprite table overflow in %d envs: the rollout is not bit-exact" % flags["sprite_overflow_envs"])
+    W_, H_ = env.MAP_X, env.MAP_Y
+    env.close()
+    del rollout
+    torch.cuda.empty_cache()
 
+    line = None
     if rank == 0:
-        peaks, peak_src = None, "fallback 6650 GB/s (B200_PROFILING.md)"
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-        except Exception:
-            peak = 6650.0
+        peak, peak_src = hbm_peak()
         avg_kernel_s = (sum(kern_ms) / K) / 1000.0
-        B = b_tick(env.MAP_X, env.MAP_Y)
+        B = b_tick(W_, H_)
         achieved = B * E / avg_kernel_s / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp) and args.workload == "mp16":
-            try:
-                tj = json.load(open(tp))
-                traffic = tj.get("dram_bytes_per_env_tick") * E if tj.get("dram_bytes_per_env_tick") else None
-            except Exception:
-                traffic = None
+        for tp in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp) and args.workload == "mp16":
+                try:
+                    tj = json.load(open(tp))
+                    traffic = tj.get("dram_bytes_per_env_tick") * E if tj.get("dram_bytes_per_env_tick") else None
+                    break
+                except Exception:
+                    traffic = None
         line = {
             "metric": METRIC, "value": world * E * K / (total_ms / 1000.0), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int16/uint16 (+fp32 valves)", "data": "synthetic",
             "config": workload(args), "gpu_launches": K * launches_per_step,
+            "step_ms": ms_stats(kern_ms),
             "kernels": "per env group: k_mp_env_pre + k_mp_frames<32> launches of %d frames (32 envs per CTA, frame "
                        "lockstep) + k_mp_env_post; + memset + 3 scheduling kernels" % int(os.environ.get("MPB_FRAMES_PER_LAUNCH", 50)),
             "sim_frames_per_s": world * E * K * 200 / (total_ms / 1000.0),
@@ -254,110 +380,157 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_tick": B,
                          "note": "the tick is not HBM bound (SURVEY 8d: a few percent expected): ~300 KB of branchy SASS "
-                                 "run by one lane per warp is bound by instruction supply -- ncu: GPC-level L1.5 "
-                                 "instruction cache (gcc) requests at 55-65 % of peak, issue slots 30 % busy, DRAM 2 % "
-                                 "(profiles/r01_k_mp_frames_ncu_full.txt, profiles/r01_notes.md)"},
-            "cpu_baseline": cb, "clocks": sampler.result(), "reward_checksum": checksum,
+                                 "run by one lane per warp is bound by instruction supply and by the wait for the slowest "
+                                 "of the 32 cities of a CTA (profiles/r02_notes.md)"},
+            "cpu_baseline": cb, "clocks": sampler.result(), "reward_checksum": checksum, "flags": flags,
         }
-        print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    # BASELINE's other configs and the episode / vec-env variants of the headline, on one GPU only (the scaling runs
+    # stay what they were: one line per N, the headline workload)
+    if world == 1 and args.workload == "mp16" and not args.no_extra:
+        Kx = max(5, min(K, 20))
+        extra = {}
+        try:
+            extra["mp16_episode"], extra["mp16_venv_step"] = run_episode_and_venv(args, local, dev, Kx)
+            extra["mp120"] = run_extra_mp("mp120", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
+            extra["mp32puzzle"] = run_extra_mp("mp32puzzle", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
+            extra["gol16_4096"] = gol_measure(args, 4096, Kx, local)
+            extra["gol16_1m"] = gol_measure(args, 1 << 20, Kx, local, cpu=False)
+        except Exception as ex:                      # the headline line must not be lost to an extra
+            extra["error"] = repr(ex)
+        line["extra_workloads"] = extra
+    print(json.dumps(line), flush=True)
 
 
-def run_gol(args):
+def gol_measure(args, N, K, local, cpu=True, T=32):
     """BASELINE config 2: 1-player Game of Life 16x16 torus, N batched envs, uniform random toggle per tick
-    (multi_env.py:170-232).  Reported on request (--workload gol16); a different metric from the headline."""
+    (multi_env.py:170-232).  Two figures: one launch per tick (golb_step: what an agent that picks every action from
+    the last observation gets) and T ticks per launch (golb_step_n with the per-tick observations and rewards
+    written out: scripted / random-action rollouts).  L2 is flushed between timed launches."""
     import numpy as np
     import torch
     from gymcity_b200 import GoLMultiEnv
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    N, K, W = args.envs, args.steps, max(3, args.warmup)
     w = 16
     env = GoLMultiEnv()
     env.configure(map_width=w, num_proc=N, max_step=10 ** 9, device=local)
     rng = np.random.default_rng(args.seed)
-    env.set_state((rng.random((N, w, w)) < 0.2).astype(np.uint8))
+    env.set_state((rng.integers(0, 5, (N, w, w), dtype=np.uint8) == 0).astype(np.uint8))     # 20 % alive
     g = torch.Generator(device=dev)
     g.manual_seed(args.seed)
-    acts = torch.randint(0, w * w, (64, N), device=dev, dtype=torch.int64, generator=g)
+    acts = torch.randint(0, w * w, (T, N), device=dev, dtype=torch.int64, generator=g)
     stream = torch.cuda.current_stream(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    inner = 1
-    for i in range(W):
-        env.step(acts[i % 64])
+    Tn = T if N <= 65536 else 4                                        # obs_seq is T x N x 2 KB
+    obs_seq = torch.empty(Tn, N, 2, w, w, device=dev)
+    rew_seq = torch.empty(Tn, N, device=dev)
+    for i in range(3):
+        env.step(acts[i])
+        env.step_n(acts[:Tn], obs_seq, rew_seq)
     torch.cuda.synchronize(dev)
-    ms = []
+    ms1, msn = [], []
     for i in range(K):
-        flush.zero_()                                                 # L2 flush between timed iterations
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        env.step(acts[i % 64])
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms.append(e0.elapsed_time(e1))
-    total_ms = sum(ms)
+        for which in (0, 1):
+            flush.zero_()                                             # L2 flush between timed iterations
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if which == 0:
+                env.step(acts[i % T])
+            else:
+                env.step_n(acts[:Tn], obs_seq, rew_seq)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            (ms1 if which == 0 else msn).append(e0.elapsed_time(e1))
     acts_h = acts.cpu().numpy()
     rew_h = np.zeros(N, np.float32)
     env.step_host(acts_h[0], rew_h)
     t0 = time.perf_counter()
     for i in range(K):
-        env.step_host(acts_h[i % 64], rew_h)
+        env.step_host(acts_h[i % T], rew_h)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    try:
-        peak, src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    except Exception:
-        peak, src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
-    B = 32 + 32 + 8 + 4 + 4 + 1 + w * w * 4           # packed rows r/w, int64 action, reward, pop, done, fp32 state plane
-    achieved = B * N / (total_ms / K / 1000.0) / 1e9
+    peak, src = hbm_peak()
+    B1 = 32 + 32 + 8 + 4 + 4 + 1 + w * w * 4          # packed rows r/w, int64 action, reward, pop, done, fp32 state plane
+    Bn = 8 + 4 + 2 * w * w * 4                        # per tick of a T-tick launch: action, reward, both fp32 planes
+    a1 = B1 * N / (sum(ms1) / K / 1000.0) / 1e9
+    an = Bn * N * Tn / (sum(msn) / K / 1000.0) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gol_traffic.json")))["dram_bytes_per_env_tick"] * N
     except Exception:
         pass
-    # CPU baseline: the numpy restatement of world_pytorch.py (oracle/gol_oracle.py), one core, bounded sample
-    from oracle import gol_oracle as go
-    n_cpu = min(N, 4096)
-    st = (rng.random((n_cpu, w, w)) < 0.2).astype(np.uint8)
-    t1 = time.perf_counter()
-    reps = 0
-    while time.perf_counter() - t1 < 3.0:
-        st, _, _ = go.multi_step(st, rng.integers(0, w * w, n_cpu), w * w * 2 / 3, w * w * 2 / 3, 10 ** 9, n_cpu)
-        reps += 1
-    cpu_rate = reps * n_cpu / (time.perf_counter() - t1)
-    line = {"metric": "Game of Life env-ticks/sec", "value": N * K / (total_ms / 1000.0), "unit": UNIT, "n_gpus": 1,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 bit-packed rows", "data": "synthetic",
-            "config": {"workload": "1-player Game of Life 16x16 torus, %d batched envs, uniform random toggle per tick" % N,
-                       "name": "gol16", "envs_per_gpu": N, "l2": "256 MB buffer written between timed steps (L2 flush)"},
-            "gpu_launches": K, "kernels": "k_gol_step (one launch per env-tick of the whole batch)",
-            "e2e": {"value": N * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 4,
-                    "note": "golb_step_host: int64 actions H2D, step, float32 rewards D2H; the (N,2,16,16) fp32 "
-                            "observation stays in HBM (DLPack)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": src, "algorithmic_bytes_per_env_tick": B},
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": "%d numpy steps of %d boards (oracle/gol_oracle.py multi_step)" % (reps, n_cpu)}}
-    print(json.dumps(line), flush=True)
+    cbl = None
+    if cpu and not args.no_cpu_baseline:
+        # CPU baseline: the reference's own torch pipeline (world_pytorch.World with cuda=False) restated in
+        # oracle/gol_oracle.py TorchWorldPort, all of torch's CPU threads, bounded sample
+        from oracle import gol_oracle as go
+        n_cpu = min(N, 4096)
+        tw = go.TorchWorldPort((rng.random((n_cpu, w, w)) < 0.2).astype(np.uint8))
+        t1 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t1 < 3.0:
+            tw.step(rng.integers(0, w * w, n_cpu), w * w * 2 / 3, w * w * 2 / 3, 10 ** 9)
+            reps += 1
+        cbl = {"value": reps * n_cpu / (time.perf_counter() - t1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d steps of %d boards through oracle/gol_oracle.py TorchWorldPort (the reference's torch ops: circular "
+                         "pad, Conv2d 3x3, round, GoLU; torch CPU threads = cores)" % (reps, n_cpu)}
+    out = {"workload": "1-player Game of Life 16x16 torus, %d batched envs, uniform random toggle per tick" % N,
+           "unit": UNIT, "steps": K, "l2": "256 MB buffer written between timed launches (L2 flush)",
+           "per_launch_1_tick": {"value": N * K / (sum(ms1) / 1000.0), "ms_per_launch": sum(ms1) / K, "step_ms": ms_stats(ms1),
+                                 "roofline": {"bound": "hbm", "achieved": a1, "peak": peak, "unit": "GB/s", "frac": a1 / peak,
+                                              "traffic": traffic, "algorithmic_bytes_per_env_tick": B1}},
+           "per_launch_T_ticks": {"T": Tn, "value": N * Tn * K / (sum(msn) / 1000.0), "ms_per_launch": sum(msn) / K,
+                                  "step_ms": ms_stats(msn),
+                                  "roofline": {"bound": "hbm", "achieved": an, "peak": peak, "unit": "GB/s", "frac": an / peak,
+                                               "algorithmic_bytes_per_env_tick": Bn},
+                                  "note": "golb_step_n: T ticks per launch, every tick's observation (both planes) and reward written out"},
+           "e2e": {"value": N * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N * 8, "d2h_bytes_per_step": N * 4},
+           "cpu_baseline": cbl}
+    out["value"] = out["per_launch_T_ticks"]["value"]
     env.close()
+    del obs_seq, rew_seq, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gol(args):
+    """--workload gol16: the Game-of-Life figures as a line of their own (a different metric from the headline)."""
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K = args.steps
+    r = gol_measure(args, args.envs, K, local)
+    one = r["per_launch_1_tick"]
+    line = {"metric": "Game of Life env-ticks/sec", "value": r["per_launch_T_ticks"]["value"], "unit": UNIT, "n_gpus": 1,
+            "steps": K, "warmup": max(3, args.warmup), "ms_per_step": r["per_launch_T_ticks"]["ms_per_launch"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-packed rows",
+            "data": "synthetic", "config": {"workload": r["workload"], "name": "gol16", "envs_per_gpu": args.envs, "l2": r["l2"]},
+            "gpu_launches": K, "kernels": "k_gol_step (T ticks per launch)", "e2e": r["e2e"],
+            "roofline": r["per_launch_T_ticks"]["roofline"], "per_launch_1_tick": one, "per_launch_T_ticks": r["per_launch_T_ticks"],
+            "cpu_baseline": r["cpu_baseline"]}
+    print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mp16", choices=sorted(WORKLOADS) + ["gol16"])
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--rollout-steps", type=int, default=0,
-                    help="> 0: observations go straight into an A2C rollout buffer obs[T+1, E, 32, W, H] (config 5)")
+    ap.add_argument("--rollout-steps", type=int, default=5,
+                    help="> 0: observations go straight into an A2C rollout buffer obs[T+1, E, 32, W, H] (config 5: "
+                         "--num-steps 5); 0: into the library's own buffer")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip extra_workloads (BASELINE configs 2-4 and the episode / vec-env variants; N = 1 only)")
     ap.add_argument("--age-steps", type=int, default=40,
                     help="untimed env-ticks before the warm-up so the random-action cities are in steady state")
     args = ap.parse_args()

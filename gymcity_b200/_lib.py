@@ -35,6 +35,7 @@ def lib():
         "golb_get_state": (i32, [vp, vp]),
         "golb_step": (i32, [vp, vp, vp]),
         "golb_step_host": (i32, [vp, vp, vp, vp]),
+        "golb_step_n": (i32, [vp, vp, i32, vp, vp, vp]),
         "golb_ptr": (vp, [vp, i32]),
         "golb_step_count": (i32, [vp]),
     }

@@ -43,7 +43,7 @@ struct MpBatch {
     unsigned long long *cycles;   // [n_envs] SM cycles each env spent in k_mp_frames since the last read (profiling)
     unsigned int *cost;       // [n_envs] cycles of the current step (schedule key for the next one)
     int *perm;                // [n_envs] env ids, most expensive first
-    unsigned int *hist;       // [SCHED_BUCKETS + 1]
+    unsigned int *hist;       // [SCHED_NB + 1]
     int use_sched;
     int sms;                  // SMs of the device
     int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
@@ -60,7 +60,7 @@ struct MpBatch {
     // groups' launches keep the SMs busy (the per-env dependency chain is the only real one)
     int groups;
     cudaStream_t gstream[8];
-    cudaEvent_t ev_start, ev_done[8];
+    cudaEvent_t ev_start, ev_done[8], ev_ar0, ev_ar1;     // ev_ar*: around the auto-reset part of the last step
     // gym layer (mpb_env_*)
     int configured, shadow_stride;
     GymCfg cfg;
@@ -298,40 +298,67 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
     }
 }
 
+// Schedule key: (phase class, cost bucket).  Envs of one k_mp_frames CTA run in frame lockstep, which only works when
+// they are in the same phase of the 16-phase cycle: an env that was reset (or stepped under a mask) on another step is
+// half a cycle away from its neighbours (200 frames per env-step = 8 mod 16) -- its map-scan block would meet the
+// others' census / power-scan frames and every frame would cost the maximum of the two (measured: episodes of 200
+// steps with staggered resets ran at 34 ms per step instead of 20).  So the order is by phase class first, and by cost,
+// most expensive first, inside a class; only the CTAs at the <= 15 class boundaries are mixed.
 constexpr int SCHED_BUCKETS = 1024;
-__device__ __forceinline__ int sched_bucket(unsigned int cost)      // cost = cycles >> 8 of one step
+constexpr int SCHED_CLASSES = 16;
+constexpr int SCHED_NB = SCHED_BUCKETS * SCHED_CLASSES;
+__device__ __forceinline__ int sched_bucket(unsigned int cost, int phase)      // cost = cycles >> 8 of one step
 {
     unsigned int k = cost >> 5;                                      // 2^13 busy cycles per bucket (mean env: ~300)
-    return SCHED_BUCKETS - 1 - (int)(k < (unsigned)SCHED_BUCKETS ? k : SCHED_BUCKETS - 1);   // expensive first
+    return (phase & 15) * SCHED_BUCKETS + SCHED_BUCKETS - 1 - (int)(k < (unsigned)SCHED_BUCKETS ? k : SCHED_BUCKETS - 1);   // expensive first
+}
+__device__ __forceinline__ int env_phase(const uint8_t *blocks, int env)
+{
+    const Scalars *sc = reinterpret_cast<const Scalars *>(blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
+    return sc->initSimLoad ? 0 : (sc->phaseCycle & 15);
 }
 __global__ void k_mp_sched_identity(int *perm, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) perm[i] = i;
 }
-__global__ void k_mp_sched_hist(const unsigned int *cost, int n, unsigned int *hist)
+__global__ void k_mp_sched_hist(const unsigned int *cost, const uint8_t *blocks, int n, unsigned int *hist)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&hist[sched_bucket(cost[i])], 1u);
+    if (i < n) atomicAdd(&hist[sched_bucket(cost[i], env_phase(blocks, i))], 1u);
 }
-__global__ void k_mp_sched_scan(unsigned int *hist)                  // exclusive prefix sum, one warp
+__global__ void __launch_bounds__(1024) k_mp_sched_scan(unsigned int *hist)     // exclusive prefix sum, one CTA of 1024
 {
-    unsigned int carry = 0;
-    for (int base = 0; base < SCHED_BUCKETS; base += 32) {
-        unsigned int v = hist[base + threadIdx.x], x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((int)threadIdx.x >= o) x += y;
-        }
-        hist[base + threadIdx.x] = carry + x - v;
-        carry += __shfl_sync(0xffffffffu, x, 31);
+    __shared__ unsigned int wsum[32];
+    constexpr int PER = SCHED_NB / 1024;
+    unsigned int v[PER], tot = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { v[k] = hist[threadIdx.x * PER + k]; tot += v[k]; }
+    unsigned int x = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)(threadIdx.x & 31) >= o) x += y;
     }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int w = wsum[threadIdx.x], z = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, z, o);
+            if ((int)threadIdx.x >= o) z += y;
+        }
+        wsum[threadIdx.x] = z - w;
+    }
+    __syncthreads();
+    unsigned int run = wsum[threadIdx.x >> 5] + x - tot;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { hist[threadIdx.x * PER + k] = run; run += v[k]; }
 }
-__global__ void k_mp_sched_scatter(unsigned int *cost, int n, unsigned int *hist, int *perm)
+__global__ void k_mp_sched_scatter(unsigned int *cost, const uint8_t *blocks, int n, unsigned int *hist, int *perm)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    perm[atomicAdd(&hist[sched_bucket(cost[i])], 1u)] = i;
+    perm[atomicAdd(&hist[sched_bucket(cost[i], env_phase(blocks, i))], 1u)] = i;
     cost[i] = 0;
 }
 
@@ -568,10 +595,10 @@ __global__ void k_mp_env_counters(const uint8_t *blocks, const uint8_t *shadow, 
 int rebuild_schedule(MpBatch *b, cudaStream_t st)
 {
     if (!b->use_sched) return 0;
-    cudaMemsetAsync(b->hist, 0, (SCHED_BUCKETS + 1) * 4, st);
-    k_mp_sched_hist<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->n_envs, b->hist);
-    k_mp_sched_scan<<<1, 32, 0, st>>>(b->hist);
-    k_mp_sched_scatter<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->n_envs, b->hist, b->perm);
+    cudaMemsetAsync(b->hist, 0, (SCHED_NB + 1) * 4, st);
+    k_mp_sched_hist<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, b->n_envs, b->hist);
+    k_mp_sched_scan<<<1, 1024, 0, st>>>(b->hist);
+    k_mp_sched_scatter<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, b->n_envs, b->hist, b->perm);
     return 0;
 }
 
@@ -657,6 +684,7 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
     const int n = b->n_envs;
     int grid = b->sms * 32;
     if (grid > n) grid = n;
+    cudaEventRecord(b->ev_ar0, st);
     cudaMemsetAsync(b->rcount, 0, 4, st);
     k_mp_env_auto_list<<<(n + 255) / 256, 256, 0, st>>>(b->done, step_mask, n, b->rlist, b->rcount, b->amask);
     k_mp_env_reset_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->rlist,
@@ -667,6 +695,7 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
                                                     0, b->scan_block, NULL, 0, NULL, b->rcount);
     k_mp_env_post_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->obs_out,
                                                               b->reward, b->done, b->rlist, b->rcount);
+    cudaEventRecord(b->ev_ar1, st);
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
 }
@@ -739,7 +768,7 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->cycles, (size_t)n_envs * 8) == cudaSuccess
         && cudaMalloc(&b->cost, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
-        && cudaMalloc(&b->hist, (SCHED_BUCKETS + 1) * 4) == cudaSuccess
+        && cudaMalloc(&b->hist, (SCHED_NB + 1) * 4) == cudaSuccess
         && cudaMalloc(&b->rlist, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->rcount, 4) == cudaSuccess
         && cudaMalloc(&b->amask, n_envs) == cudaSuccess
@@ -754,6 +783,7 @@ mpb_handle mpb_create(int n_envs, int device)
     if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
     cudaEventCreate(&b->ev_start);
+    cudaEventCreate(&b->ev_ar0); cudaEventCreate(&b->ev_ar1);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
     k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, n_envs);
@@ -768,6 +798,8 @@ void mpb_destroy(mpb_handle h)
     cudaSetDevice(b->device);
     for (int g = 0; g < 8; g++) { if (b->gstream[g]) cudaStreamDestroy(b->gstream[g]); if (b->ev_done[g]) cudaEventDestroy(b->ev_done[g]); }
     if (b->ev_start) cudaEventDestroy(b->ev_start);
+    if (b->ev_ar0) cudaEventDestroy(b->ev_ar0);
+    if (b->ev_ar1) cudaEventDestroy(b->ev_ar1);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
@@ -986,6 +1018,18 @@ int mpb_group_times(mpb_handle h, float *ms_out)
     }
     cudaGetLastError();
     return b->groups;
+}
+
+int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !ms_out) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    *ms_out = -1.0f;
+    if (cudaEventElapsedTime(ms_out, b->ev_ar0, b->ev_ar1) != cudaSuccess) { cudaGetLastError(); *ms_out = -1.0f; }
+    if (n_reset_out) CK(cudaMemcpy(n_reset_out, b->rcount, 4, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int mpb_read_schedule(mpb_handle h, int *perm_out_host)
@@ -1344,6 +1388,9 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
 {
     const int G = step_groups(b);
     const int *perm = b->use_sched ? b->perm : NULL;
+    // the order of this step: by the phase each env is in NOW (resets between steps move envs to another phase
+    // class) and by what the previous step cost it
+    rebuild_schedule(b, st);
     if (G > 1) cudaEventRecord(b->ev_start, st);
     for (int g = 0; g < G; g++) {
         cudaStream_t gs = G > 1 ? b->gstream[g] : st;
@@ -1366,7 +1413,6 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         }
     }
     if (b->auto_reset) launch_auto_reset(b, mask_dev, st);
-    rebuild_schedule(b, st);
     CK_LAUNCHES();
     return 0;
 }

@@ -156,6 +156,21 @@ class GoLMultiEnv(_GolBase):
         self.step_count += 1
         return self._obs, self._reward, self._done.bool(), [{}]
 
+    def step_n(self, actions, obs_seq=None, reward_seq=None):
+        """T steps in one launch (golb_step_n) for scripted / random-action rollouts: actions (T, N) int64 CUDA
+        tensor; obs_seq (T, N, 2, W, W) / reward_seq (T, N) float32 CUDA tensors receive every tick's observation /
+        reward when given.  Returns what the T-th step() would have."""
+        import torch
+        a = actions.to(device="cuda:%d" % self.device, dtype=torch.int64).contiguous()
+        T = a.shape[0]
+        assert a.dim() == 2 and a.shape[1] == self.num_proc
+        for t, shape in ((obs_seq, (T, self.num_proc, 2, self.map_width, self.map_width)), (reward_seq, (T, self.num_proc))):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape)
+        self._ck(self._L.golb_step_n(self._h, a.data_ptr(), T, obs_seq.data_ptr() if obs_seq is not None else None,
+                                     reward_seq.data_ptr() if reward_seq is not None else None, _stream_ptr(self.device)))
+        self.step_count += T
+        return self._obs, self._reward, self._done.bool(), [{}]
+
     def step_host(self, actions_np, reward_out):
         """End-to-end call with HOST buffers (int64 actions in, float32 rewards out)."""
         self._ck(self._L.golb_step_host(self._h, actions_np.ctypes.data, reward_out.ctypes.data,

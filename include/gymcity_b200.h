@@ -101,6 +101,8 @@ int mpb_group_times(mpb_handle h, float *ms_out);
  * an env-step used): enable != 0 starts / clears the recording, out_host (may be NULL) receives what was
  * recorded so far, enable == 0 stops and frees it.  One batch per process at a time. */
 int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host);
+/* Profiling: device time (ms) of the auto-reset part of the last env step and how many envs it reset. */
+int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out);
 /* Profiling: the heavy-first env order the NEXT env-step's launches use (int32 [n_envs] HOST); returns the
  * number of env groups. */
 int mpb_read_schedule(mpb_handle h, int *perm_out_host);

@@ -100,3 +100,62 @@ def classic_step(world, a, max_step, step_count):
     world.tick()
     terminal = (step_count == max_step) or raw < 2
     return world.state(), float(raw * 100 / (max_step * w * w)), terminal
+
+
+class TorchWorldPort:
+    """world_pytorch.py:6-135 + multi_env.py:170-232 restated with the reference's own torch ops on the CPU (all of
+    torch's threads): circular pad by four torch.cat, Conv2d(1, 1, 3) with weights [[1,1,1],[1,9,1],[1,1,1]], round,
+    the piecewise GoLU activation, population by sum, fp32 reward.  bench.py's CPU baseline for the Game-of-Life
+    workload (the reference's own CPU path is exactly this module with cuda=False).  Checked against tick_torus
+    in tests/test_gol_oracle.py."""
+
+    def __init__(self, state):
+        import torch
+        self.torch = torch
+        self.state = torch.as_tensor(np.asarray(state), dtype=torch.float32).unsqueeze(1).contiguous()   # (N, 1, W, W)
+        self.weight = torch.tensor([[[[1, 1, 1], [1, 9, 1], [1, 1, 1]]]], dtype=torch.float32)
+        n, _, w, _ = self.state.shape
+        self.n, self.w = n, w
+
+    @staticmethod
+    def _pad_circular(torch, x, pad):                                  # world_pytorch.py:6-19
+        x = torch.cat([x, x[:, :, 0:pad, :]], dim=2)
+        x = torch.cat([x, x[:, :, :, 0:pad]], dim=3)
+        x = torch.cat([x[:, :, -2 * pad:-pad, :], x], dim=2)
+        x = torch.cat([x[:, :, :, -2 * pad:-pad], x], dim=3)
+        return x
+
+    def _golu(self, x):                                                # world_pytorch.py:110-135
+        x_out = x.clone().fill_(0).float()
+        ded_0 = (x >= 2).float()
+        bth_0 = ded_0 * (x < 3).float()
+        x_out = x_out + (bth_0 * (x - 2).float())
+        ded_1 = (x >= 3).float()
+        bth_1 = ded_1 * (x < 4).float()
+        x_out = x_out + abs(bth_1 * (x - 4).float())
+        alv_0 = (x >= 10).float()
+        lif_0 = alv_0 * (x < 11).float()
+        x_out = x_out + (lif_0 * (x - 10).float())
+        alv_1 = (x >= 11).float()
+        lif_1 = alv_1 * (x < 12).float()
+        x_out = x_out + lif_1
+        alv_2 = (x >= 12).float()
+        lif_2 = alv_2 * (x < 13).float()
+        x_out = x_out + abs(lif_2 * (x - 13).float())
+        return x_out
+
+    def step(self, actions, trg_pop, max_loss, max_step):
+        torch = self.torch
+        with torch.no_grad():
+            a = torch.as_tensor(np.asarray(actions), dtype=torch.int64)
+            onehot = torch.zeros(self.n, self.w * self.w)
+            onehot.scatter_(1, a.reshape(-1, 1), 1.0)                   # multi_env.py:243-253 act_to_build
+            st = ((self.state.long() ^ onehot.reshape(self.n, 1, self.w, self.w).long())).float()   # :179
+            x = self._pad_circular(torch, st, 1)
+            x = torch.nn.functional.conv2d(x, self.weight)
+            x = x.round()
+            self.state = self._golu(x)
+            pop = self.state.sum(dim=(1, 2, 3))                         # :199-204
+            loss = abs(trg_pop - pop)
+            reward = (max_loss - loss) * 100 / (max_loss * max_step * self.n)
+        return self.state, reward, pop

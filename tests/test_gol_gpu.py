@@ -136,3 +136,28 @@ def test_step_host_end_to_end():
     st, orew, _ = go.multi_step(init, a, w * w * 2 / 3, w * w * 2 / 3, 200, n)
     assert np.array_equal(rew, orew) and np.array_equal(env.get_state(), st)
     env.close()
+
+
+@pytest.mark.parametrize("n,w,T", [(4096, 16, 33), (100, 8, 7), (77, 32, 5), (50, 12, 9)])
+def test_step_n_equals_n_steps(n, w, T):
+    """golb_step_n: T ticks in one launch leave the same state / reward / pop / done as T golb_step calls, and the
+    per-tick observation and reward sequences are those of the single steps (both planes)."""
+    import torch
+    rng = np.random.default_rng(n * 3 + w)
+    init = (rng.random((n, w, w)) < 0.25).astype(np.uint8)
+    acts = torch.from_numpy(rng.integers(0, w * w, (T, n))).cuda()
+    a, b = _multi(n, w, max_step=T - 2), _multi(n, w, max_step=T - 2)
+    a.set_state(init); b.set_state(init)
+    obs_seq = torch.full((T, n, 2, w, w), -1.0, device="cuda")
+    rew_seq = torch.full((T, n), -1.0, device="cuda")
+    ob, rb, db, _ = b.step_n(acts, obs_seq, rew_seq)
+    for t in range(T):
+        oa, ra, da, _ = a.step(acts[t])
+        assert torch.equal(oa, obs_seq[t]), t
+        assert torch.equal(ra.reshape(-1), rew_seq[t]), t
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    assert np.array_equal(a.get_state(), b.get_state()) and torch.equal(a.get_pop(), b.get_pop())
+    assert a.step_count == b.step_count == T
+    oa, ra, da, _ = a.step(acts[0]); ob, rb, db, _ = b.step_n(acts[:1])
+    assert torch.equal(oa, ob) and torch.equal(da, db)
+    a.close(); b.close()

@@ -46,3 +46,18 @@ def test_known_patterns():
     for _ in range(4):
         s = go.tick_torus(s)
     assert np.array_equal(s, np.roll(np.roll(g, 1, 0), 1, 1))
+
+
+def test_torch_world_port_matches_bit_oracle():
+    """The torch-CPU restatement of world_pytorch.World used as bench.py's Game-of-Life CPU baseline."""
+    rng = np.random.default_rng(3)
+    n, w = 64, 16
+    st = (rng.random((n, w, w)) < 0.3).astype(np.uint8)
+    tw = go.TorchWorldPort(st)
+    for t in range(20):
+        a = rng.integers(0, w * w, n)
+        st, rew, pop = go.multi_step(st, a, w * w * 2 / 3, w * w * 2 / 3, 200, n)
+        s2, r2, p2 = tw.step(a, w * w * 2 / 3, w * w * 2 / 3, 200)
+        assert np.array_equal(s2[:, 0].numpy().astype(np.uint8), st), t
+        assert np.array_equal(p2.numpy().astype(np.int64), pop)
+        assert np.allclose(r2.numpy(), rew, rtol=1e-6)

@@ -140,3 +140,87 @@ def test_poet_observation_planes():
         assert np.array_equal(o0.astype(np.float32), o1), (t, np.argwhere(o0.astype(np.float32) != o1)[:4])
         assert r0 == r1
     assert float(o1[31, 0, 0]) == np.float32(320 / 750) and float(o1[36, 3, 3]) == np.float32(61 / 100)
+
+
+# ---- the restated env / control arithmetic against the reference's own functions, lifted out of its files ------
+REF_ENV = "/root/reference/gym_city/envs/env.py"
+REF_CONTROL = "/root/reference/gym_city/envs/corecontrol.py"
+
+
+def _lift(path, class_name, names):
+    """The named methods of `class_name` in the reference file `path`, compiled on their own (the modules import gtk /
+    the SWIG engine at the top and cannot be imported here) into a bare class."""
+    import ast
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == class_name)
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(f.name for f in fns) == sorted(names), [f.name for f in fns]
+    mod = ast.Module(body=[ast.ClassDef(name="Lifted", bases=[], keywords=[], body=fns, decorator_list=[])], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"np": np, "print": lambda *a, **k: None}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["Lifted"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ENV), reason="reference tree not present")
+def test_ref_env_reward_and_action_map_match_reference_functions():
+    """RefEnv.getReward / decode against MicropolisEnv.getReward / mapIntsToActions (env.py:209-219, 345-387)."""
+    L = _lift(REF_ENV, "MicropolisEnv", ["getReward", "mapIntsToActions"])
+    rng = np.random.default_rng(0)
+    env = RefEnv(RefEngine(), 16, max_step=10)
+    ref = L()
+    ref.city_trgs, ref.weights = dict(env.city_trgs), dict(env.weights)
+    for k in range(4000):
+        scale = [1, 10, 1000][k % 3]
+        last = {m: int(rng.integers(-scale, 3 * scale)) for m in env.city_trgs}
+        cur = {m: (last[m] if rng.random() < 0.3 else int(rng.integers(-scale, 3 * scale))) for m in env.city_trgs}
+        if k % 7 == 0:                                       # exactly on / beyond the target
+            m = list(env.city_trgs)[k % 6]
+            cur[m] = env.city_trgs[m] + int(rng.integers(-1, 2))
+        env.last_city_metrics = ref.last_city_metrics = last
+        env.city_metrics = ref.city_metrics = cur
+        assert env.getReward() == ref.getReward(), (last, cur)
+    for T, W, H in [(20, 16, 16), (1, 32, 32), (20, 20, 12)]:
+        ref = L()
+        ref.num_tools, ref.MAP_X, ref.MAP_Y = T, W, H
+        ref.intsToActions, ref.actionsToInts = {}, np.zeros((T, W, H), int)
+        ref.mapIntsToActions()
+        e = RefEnv(RefEngine(), (W, H), max_step=10, power_puzzle=(T == 1))
+        assert e.num_tools == T
+        for i in range(T * W * H):
+            assert e.decode(i) == ref.intsToActions[i] and ref.actionsToInts[tuple(e.decode(i))] == i
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CONTROL), reason="reference tree not present")
+@pytest.mark.parametrize("W,H,xs,ys", [(16, 16, 16, 8), (32, 32, 16, 8), (120, 100, 0, 0), (20, 12, 30, 40)])
+def test_ref_control_density_maps_match_reference_functions(W, H, xs, ys):
+    """RefControl.getDensityMaps against MicropolisControl.getDensityMaps / fillDensityMap (corecontrol.py:205-239)
+    run over the same engine state: the swapped x / y offsets (MAP_YS added to the row index), the half-resolution
+    lookups and total_traffic."""
+    L = _lift(REF_CONTROL, "MicropolisControl", ["fillDensityMap", "getDensityMaps"])
+    r = RefEngine()
+    r.generate(77)
+    r.seed(7)
+    rng = np.random.default_rng(W + H)
+    r.set("MPF_TRAFFIC_DENSITY", rng.integers(0, 256, 3000).astype(np.uint8))
+    r.set("MPF_POP_DENSITY", rng.integers(0, 256, 3000).astype(np.uint8))
+    pw = (rng.random(12000) < 0.3).astype(np.uint8)
+    r.set("MPF_POWER_GRID", pw)
+    traffic = np.asarray(r.get("MPF_TRAFFIC_DENSITY")).reshape(60, 50)
+    pop = np.asarray(r.get("MPF_POP_DENSITY")).reshape(60, 50)
+    power = np.asarray(r.get("MPF_POWER_GRID")).reshape(120, 100)
+
+    class Eng:                                                 # stubs.cpp:382-505: Map::get / worldGet, 0 off the map
+        @staticmethod
+        def getTrafficDensity(x, y): return int(traffic[x, y]) if 0 <= x < 60 and 0 <= y < 50 else 0
+        @staticmethod
+        def getPopulationDensity(x, y): return int(pop[x, y]) if 0 <= x < 60 and 0 <= y < 50 else 0
+        @staticmethod
+        def getPowerGrid(x, y): return int(power[x, y]) if 0 <= x < 120 and 0 <= y < 100 else 0
+    ref = L()
+    ref.engine, ref.MAP_X, ref.MAP_Y, ref.MAP_XS, ref.MAP_YS = Eng, W, H, xs, ys
+    want = ref.getDensityMaps()
+    ctl = RefControl(r, W, H, xs=xs, ys=ys)
+    got = ctl.getDensityMaps()
+    assert np.array_equal(want, got)
+    assert ctl.total_traffic == ref.total_traffic
