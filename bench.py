@@ -304,6 +304,10 @@ def run_ours(args):
             m._ck(m._L.mpb_env_set_obs_buffer(m._h, slot.data_ptr()))
             nstep[0] += 1
         m._ck(m._L.mpb_env_step(m._h, acts[i].data_ptr(), 0, sp))
+        if args.allreduce_stats:
+            from gymcity_b200 import sharding
+            stats[0] = sharding.all_reduce_stats(sharding.step_stats(m.reward, m.done))
+    stats = [None]
 
     for i in range(args.age_steps):                 # untimed build-up: cities reach their random-action steady state
         step_dev(i % (W + 2 * K + 2))
@@ -365,9 +369,12 @@ def run_ours(args):
                     traffic = None
         line = {
             "metric": METRIC, "value": world * E * K / (total_ms / 1000.0), "unit": UNIT, "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "strong" if args.total_envs > 0 else "weak",
             "vs_baseline": None, "dtype": "int16/uint16 (+fp32 valves)", "data": "synthetic",
             "config": workload(args), "gpu_launches": K * launches_per_step,
+            "collective": ("all-reduce of 3 doubles per step (sum reward, n done, n envs)" if args.allreduce_stats
+                           else "none on the tick path (NCCL: barrier + max of the timings only)"),
             "step_ms": ms_stats(kern_ms),
             "kernels": "per env group: k_mp_env_pre + k_mp_frames<32> launches of %d frames (32 envs per CTA, frame "
                        "lockstep) + k_mp_env_post; + memset + 3 scheduling kernels" % int(os.environ.get("MPB_FRAMES_PER_LAUNCH", 50)),
@@ -529,6 +536,11 @@ def main():
     ap.add_argument("--rollout-steps", type=int, default=5,
                     help="> 0: observations go straight into an A2C rollout buffer obs[T+1, E, 32, W, H] (config 5: "
                          "--num-steps 5); 0: into the library's own buffer")
+    ap.add_argument("--total-envs", type=int, default=0,
+                    help="> 0: STRONG scaling -- this many envs in total, split evenly over the N GPUs (config 5: 262144)")
+    ap.add_argument("--allreduce-stats", action="store_true",
+                    help="add the one optional collective of the tick path to every timed step: an all-reduce of "
+                         "[sum reward, n done, n envs] over the ranks (sharding.all_reduce_stats)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip extra_workloads (BASELINE configs 2-4 and the episode / vec-env variants; N = 1 only)")
     ap.add_argument("--age-steps", type=int, default=40,
@@ -539,6 +551,8 @@ def main():
         return run_gol(args)
     if args.envs is None:
         args.envs = WORKLOADS[args.workload]["envs"]
+    if args.total_envs > 0:
+        args.envs = args.total_envs // max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -54,5 +54,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_coverage():
+    """The -DMP_COVERAGE variant (csrc/mp_cov.h) next to the product library: test infrastructure for
+    tests/test_coverage_gpu.py, never loaded unless GYMCITY_B200_LIB names it."""
+    global LIB
+    keep, env_keep = LIB, {k: os.environ.get(k) for k in ("MPB_NVCC_EXTRA", "MPB_OBJ_SUFFIX")}
+    LIB = os.path.join(HERE, "libgymcity_b200_cov.so")
+    os.environ["MPB_NVCC_EXTRA"] = "-DMP_COVERAGE"
+    os.environ["MPB_OBJ_SUFFIX"] = "_cov"
+    try:
+        return build()
+    finally:
+        LIB = keep
+        for k, v in env_keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--coverage" in sys.argv:
+        print(build_coverage())

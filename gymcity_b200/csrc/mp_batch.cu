@@ -19,6 +19,10 @@
 
 using namespace mp;
 
+#if defined(MP_COVERAGE)
+__device__ unsigned long long mp_cov_bits[mp::COV_WORDS];      // function-hit bitmap of the coverage build (mp_cov.h)
+#endif
+
 namespace {
 
 // Kernels other than k_mp_frames: one warp per city, MP_EPC cities (warps) per CTA.  One per CTA: a CTA's
@@ -1030,6 +1034,28 @@ int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out)
     if (cudaEventElapsedTime(ms_out, b->ev_ar0, b->ev_ar1) != cudaSuccess) { cudaGetLastError(); *ms_out = -1.0f; }
     if (n_reset_out) CK(cudaMemcpy(n_reset_out, b->rcount, 4, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// Function-hit coverage (-DMP_COVERAGE builds; mp_cov.h): copies the bitmap (one bit per engine / gym function, set
+// when any env entered it since the library was loaded) and returns the number of functions; -1 in a product build.
+int mpb_coverage(unsigned long long *bits_out, int cap_words)
+{
+#if defined(MP_COVERAGE)
+    if (!bits_out || cap_words < COV_WORDS) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(bits_out, mp_cov_bits, sizeof(unsigned long long) * COV_WORDS) != cudaSuccess) return -1;
+    return COV_COUNT;
+#else
+    (void)bits_out; (void)cap_words;
+    return -1;
+#endif
+}
+const char *mpb_coverage_name(int id)
+{
+#define MP_COV_NAME(n) #n,
+    static const char *const names[] = { MP_COV_LIST(MP_COV_NAME) };
+#undef MP_COV_NAME
+    return (id >= 0 && id < COV_COUNT) ? names[id] : "";
 }
 
 int mpb_read_schedule(mpb_handle h, int *perm_out_host)

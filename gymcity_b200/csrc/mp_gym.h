@@ -92,6 +92,7 @@ MPD int gym_cell(const Gym &gy, int x, int y) { return x * CFG.H + y; }
 MPD int gym_get_tile(const Env &e, const Gym &gy, int x, int y) { return tget(e, x + CFG.xs, y + CFG.ys) & 1023; }
 MPD int gym_zone_of_tile(Gym &gy, int tile)
 {
+    MP_COV(gym_zone_of_tile);
     int z = kTileZone[tile];
     if (z == 255) {          // zoneSize[...] raises KeyError in the reference (Flood/Radioactive/Trash/Lightning)
         G.tilemap_error = 1;
@@ -103,6 +104,7 @@ MPD int gym_zone_of_tile(Gym &gy, int tile)
 // [LEAD] tilemap.py:467-541 updateTile.  zone < 0: re-read from the map.  static_build: -1 None, 0, 1.
 MPN void gym_update_tile(Env &e, Gym &gy, int x, int y, int zone, int center, int static_build)
 {
+    MP_COV(gym_update_tile);
     const int c = gym_cell(gy, x, y);
     const uint32_t was = kZoneFeatures[gy.zone[c]];
     if (zone < 0) {
@@ -128,6 +130,7 @@ MPN void gym_update_tile(Env &e, Gym &gy, int x, int y, int zone, int center, in
 // old zone's footprint.
 MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
 {
+    MP_COV(gym_clear_tile);
     const int c = gym_cell(gy, x, y);
     const int old_zone = gy.zone[c];
     int cnt = gy.center[c];
@@ -182,6 +185,7 @@ MPN void gym_clear_tile(Env &e, Gym &gy, int x, int y, bool static_build)
 // [LEAD] tilemap.py:391-408 clearPatch
 MPD int gym_clear_patch(Env &e, Gym &gy, int x, int y, int size, bool static_build)
 {
+    MP_COV(gym_clear_patch);
     if (size == 1 && !(!static_build && gy.stat[gym_cell(gy, x, y)] == 1)) {
         gym_clear_tile(e, gy, x, y, static_build);
         return 1;
@@ -200,6 +204,7 @@ MPD int gym_clear_patch(Env &e, Gym &gy, int x, int y, int size, bool static_bui
 // [LEAD] tilemap.py:450-479 addZone: the zone recorded is the one the MAP now shows at (x, y)
 MPD void gym_add_zone(Env &e, Gym &gy, int x, int y, bool static_build)
 {
+    MP_COV(gym_add_zone);
     int zone = gym_zone_of_tile(gy, gym_get_tile(e, gy, x, y));
     int size = kZoneSize[zone];
     int center = (size == 6) ? (x + 1) * 128 + (y + 1) : x * 128 + y;
@@ -233,6 +238,7 @@ MP_GYM_TABLE int8_t kFullToolEngine[GYM_MAX_TOOLS] = { 0, 1, 2, 3, 4, 7, 6, 8, 9
 // [LEAD] tilemap.py:345-377 addZoneBot for the tool recorded as `zone` and applied as `engine_tool`.
 MPN bool gym_add_zone_bot(Env &e, Gym &gy, int x, int y, int zone, int engine_tool, bool static_build)
 {
+    MP_COV(gym_add_zone_bot);
     if (zone == -1) return true;                              // 'Nil'
     const int c = gym_cell(gy, x, y);
     const int old_zone = gy.zone[c];
@@ -255,6 +261,7 @@ MPN bool gym_add_zone_bot(Env &e, Gym &gy, int x, int y, int zone, int engine_to
 // [LEAD] one decoded action through addZoneBot; full != 0 decodes against the full agent tool list
 MPD int gym_apply_action(Env &e, Gym &gy, long long a, bool static_build, bool full)
 {
+    MP_COV(gym_apply_action);
     if (a < 0) return 0;
     const int n = CFG.W * CFG.H;
     int z = (int)(a / n), rem = (int)(a - (long long)z * n);
@@ -273,6 +280,7 @@ MPD int gym_apply_action(Env &e, Gym &gy, long long a, bool static_build, bool f
 // reached (the loop breaks at j >= MAP_Y - 1), as in the reference.  a: tool index per cell [W*H].
 MPN void gym_paint_action(Env &e, Gym &gy, const uint8_t *a)
 {
+    MP_COV(gym_paint_action);
     const int W = CFG.W, H = CFG.H;
     G.paint = 1;                    // the acted rule applies to the builds of this action only
     MP_NOUNROLL for (int i = 0; i < W; i++)
@@ -289,6 +297,7 @@ MPN void gym_paint_action(Env &e, Gym &gy, const uint8_t *a)
 // [ALL] TileMap.init_age_array (tilemap.py:201-206)
 MPD void gym_init_age_array(Env &e, Gym &gy)
 {
+    MP_COV(gym_init_age_array);
     const int n = CFG.W * CFG.H;
     for (int i = e.c.tid; i < n; i += e.c.n) gy.age[i] = -1;
     if (e.c.lead()) G.track_ages = 1;
@@ -305,6 +314,7 @@ enum : int { XT_AGE = 0, XT_SPATIAL = 1, XT_RANDOM = 2, XT_MONSTER = 3 };
 // the centre.  Returns the number of deletions (curr_dels).
 MPN int gym_extinguish(Env &e, Gym &gy, int type, int n_dels, const int32_t *rnd)
 {
+    MP_COV(gym_extinguish);
     const int W = CFG.W, H = CFG.H, n = W * H;
     int dels = 0;
     if (type == XT_MONSTER) { make_monster(e); return 0; }                       // engine.makeMonster()
@@ -363,6 +373,7 @@ MPN int gym_extinguish(Env &e, Gym &gy, int type, int n_dels, const int32_t *rnd
 // [ALL] TileMap.setEmpty (tilemap.py:327-343)
 MPD void gym_set_empty(Env &e, Gym &gy)
 {
+    MP_COV(gym_set_empty);
     const int n = CFG.W * CFG.H;
     for (int i = e.c.tid; i < n; i += e.c.n) { gy.zone[i] = Z_LAND; gy.stat[i] = 0; gy.center[i] = -1; }
     if (e.c.lead()) { G.num_roads = 0; G.num_plants = 0; }
@@ -373,6 +384,7 @@ MPD void gym_set_empty(Env &e, Gym &gy)
 // zone given, centre (i, j), static_build None
 MPD void gym_update_map(Env &e, Gym &gy)
 {
+    MP_COV(gym_update_map);
     if (e.c.lead())
         MP_NOUNROLL for (int i = 0; i < CFG.W; i++)
             MP_NOUNROLL for (int j = 0; j < CFG.H; j++)
@@ -383,6 +395,7 @@ MPD void gym_update_map(Env &e, Gym &gy)
 // [LEAD] env.py:426-440 get_city_metrics
 MPD void gym_city_metrics(const Env &e, Gym &gy, double *m)
 {
+    MP_COV(gym_city_metrics);
     m[0] = e.s->resPop; m[1] = e.s->comPop; m[2] = e.s->indPop;
     m[3] = G.total_traffic; m[4] = G.num_plants; m[5] = e.s->cityYes;
 }
@@ -393,6 +406,7 @@ MPD double dabs(double v) { return v < 0 ? -v : v; }
 // [LEAD] env.py:345-387 getReward
 MPD double gym_reward(const Gym &gy)
 {
+    MP_COV(gym_reward);
     double reward = 0;
     MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) {
         double last = G.last_metrics[k], trg_change = CFG.trg[k] - last, change = G.metrics[k] - last, r;
@@ -408,6 +422,7 @@ MPD double gym_reward(const Gym &gy)
 // (32, W, H) float32 observation and refreshes total_traffic.  Channel order: SURVEY appendix A.3.
 MPD void gym_observe(Env &e, Gym &gy, float *obs)
 {
+    MP_COV(gym_observe);
     const int W = CFG.W, H = CFG.H, n = W * H;
     if (e.c.lead()) e.c.red[3] = 0;
     e.c.sync();
@@ -460,6 +475,7 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
 // action < 0: no agent action.
 MPD void gym_step_pre(Env &e, Gym &gy, long long action, bool static_build)
 {
+    MP_COV(gym_step_pre);
     gym_apply_action(e, gy, action, static_build, false);       // takeAction
     e.s->totalFunds = CFG.init_funds;                           // micro.setFunds(init_funds)
 }
@@ -467,6 +483,7 @@ MPD void gym_step_pre(Env &e, Gym &gy, long long action, bool static_build)
 // [ALL] MicropolisEnv.postact after micro.simTick() (env.py:468-540): state, metrics, reward, done
 MPD void gym_step_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
 {
+    MP_COV(gym_step_post);
     gym_observe(e, gy, obs);                                    // getState()
     if (e.c.lead()) {
         MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
@@ -485,6 +502,7 @@ MPD void gym_step_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *
 MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *obs, float *reward_out,
                   uint8_t *done_out)
 {
+    MP_COV(gym_step);
     if (e.c.lead()) gym_step_pre(e, gy, action, static_build);
     e.c.sync();
     control_sim_tick(e);                                        // micro.simTick()
@@ -495,6 +513,7 @@ MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *o
 // terrain: 0 = empty_start (clearMap only), 1 = generateSomeCity(terrain_seed) + seedRandom(sim_seed).
 MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim_seed)
 {
+    MP_COV(gym_reset_begin);
     gym_set_empty(e, gy);
     clear_map(e);
     gym_update_map(e, gy);
@@ -511,6 +530,7 @@ MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim
 // reward and done flag of the step that ended the episode
 MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out, bool keep_outputs = false)
 {
+    MP_COV(gym_reset_post);
     if (e.c.lead()) {
         gym_city_metrics(e, gy, G.metrics);                     // uses the previous total_traffic
         MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) G.last_metrics[k] = G.metrics[k];
@@ -529,6 +549,7 @@ MPD void gym_reset_post(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t 
 // [ALL] MicropolisEnv.reset, second half (env.py:279-292) for one env (CPU harness)
 MPD void gym_reset_finish(Env &e, Gym &gy, float *obs, float *reward_out, uint8_t *done_out)
 {
+    MP_COV(gym_reset_finish);
     control_sim_tick(e);
     gym_reset_post(e, gy, obs, reward_out, done_out);
 }

@@ -31,6 +31,7 @@ MPD int boat_distance(Env &e, int x, int y);            // mp_sprites.h
 // `resRatio = min(indRatio, ...)` slip at :644.
 MPN void set_valves(Env &e)
 {
+    MP_COV(set_valves);
     const int16_t taxTable[21] = { 200, 150, 120, 100, 80, 50, 30, 0, -10, -40, -100,
         -150, -200, -250, -300, -350, -400, -450, -500, -550, -600 };
     const float extMarketParamTable[3] = { 1.2f, 1.1f, 0.98f };
@@ -88,6 +89,7 @@ MPN void set_valves(Env &e)
 // [LEAD] simulate.cpp:674-703 clearCensus, scalar part (the two station maps are cleared by ALL)
 MPD void clear_census_scalars(Env &e)
 {
+    MP_COV(clear_census_scalars);
     S.poweredZoneCount = 0; S.unpoweredZoneCount = 0; S.firePop = 0; S.roadTotal = 0;
     S.railTotal = 0; S.resPop = 0; S.comPop = 0; S.indPop = 0; S.resZonePop = 0;
     S.comZonePop = 0; S.indZonePop = 0; S.hospitalPop = 0; S.churchPop = 0;
@@ -98,6 +100,7 @@ MPD void clear_census_scalars(Env &e)
 // ------------------------------------------------------------------ power stack / zone power
 MPD void push_power_stack(Env &e, int x, int y)          // power.cpp:163-169
 {
+    MP_COV(push_power_stack);
     if (S.powerStackPointer < POWER_STACK_SIZE - 2) {
         S.powerStackPointer++;
         e.pstack()[S.powerStackPointer] = (uint16_t)tix(x, y);
@@ -107,6 +110,7 @@ MPD void push_power_stack(Env &e, int x, int y)          // power.cpp:163-169
 // [LEAD] zone.cpp:419-437 setZonePower
 MPP bool set_zone_power(Env &e, int x, int y)
 {
+    MP_COV(set_zone_power);
     int v = e.map()[tix(x, y)], t = v & LOMASK;
     if (t == T_NUCLEAR || t == T_POWERPLANT || pwr_get(e, x, y)) {
         e.map()[tix(x, y)] = (uint16_t)(v | PWRBIT);          // status bit only: activity unchanged
@@ -119,6 +123,7 @@ MPP bool set_zone_power(Env &e, int x, int y)
 // ------------------------------------------------------------------ traffic (traffic.cpp)
 MPD bool road_test(int mv)                                // traffic.cpp:489-503
 {
+    MP_COV(road_test);
     int t = mv & LOMASK;
     if (t < T_ROADBASE || t > T_LASTRAIL) return false;
     if (t >= T_POWERBASE && t < T_LASTPOWER) return false;
@@ -128,6 +133,7 @@ MPD bool road_test(int mv)                                // traffic.cpp:489-503
 // [LEAD] traffic.cpp:227-249 findPerimeterRoad
 MPD bool find_perimeter_road(Env &e, int &x, int &y)
 {
+    MP_COV(find_perimeter_road);
     const int8_t px[12] = { -1, 0, 1, 2, 2, 2, 1, 0, -1, -2, -2, -2 };
     const int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
     MP_NOUNROLL for (int z = 0; z < 12; z++) {
@@ -142,6 +148,7 @@ MPD bool find_perimeter_road(Env &e, int &x, int &y)
 
 MPD int tile_toward(const Env &e, int x, int y, int dir, int dflt)   // traffic.cpp:383-427
 {
+    MP_COV(tile_toward);
     switch (dir) {
     case D_N: return y > 0 ? (e.map()[tix(x, y - 1)] & LOMASK) : dflt;
     case D_E: return x < WORLD_W - 1 ? (e.map()[tix(x + 1, y)] & LOMASK) : dflt;
@@ -154,6 +161,7 @@ MPD int tile_toward(const Env &e, int x, int y, int dir, int dflt)   // traffic.
 // [LEAD] traffic.cpp:333-376 tryGo
 MPD int try_go(Env &e, int x, int y, int dirLast)
 {
+    MP_COV(try_go);
     int dirs[4], dir = D_N, count = 0;
     MP_NOUNROLL for (int i = 0; i < 4; i++) {
         if (dir != dirLast && road_test(tile_toward(e, x, y, dir, T_DIRT))) {
@@ -176,6 +184,7 @@ MPD int try_go(Env &e, int x, int y, int dirLast)
 // [LEAD] traffic.cpp:436-480 driveDone
 MPD bool drive_done(const Env &e, int x, int y, int dest)
 {
+    MP_COV(drive_done);
     const int lo[3] = { T_COMBASE, T_LHTHR, T_LHTHR };
     const int hi[3] = { T_NUCLEAR, T_PORT, T_COMBASE };
     int l = lo[dest], h = hi[dest], z;
@@ -189,6 +198,7 @@ MPD bool drive_done(const Env &e, int x, int y, int dest)
 // [LEAD] traffic.cpp:287-323 tryDrive
 MPD bool try_drive(Env &e, int x, int y, int dest)
 {
+    MP_COV(try_drive);
     int dirLast = D_INVALID;
     MP_NOUNROLL for (int16_t dist = 0; dist < MAX_TRAFFIC_DISTANCE; dist++) {
         int dir = try_go(e, x, y, dirLast);
@@ -215,6 +225,7 @@ MPD bool try_drive(Env &e, int x, int y, int dest)
 // [LEAD] traffic.cpp:164-201 addToTrafficDensityMap
 MPD void add_to_traffic_density(Env &e)
 {
+    MP_COV(add_to_traffic_density);
     while (S.curMapStackPointer > 0) {
         int p = S.curMapStack[S.curMapStackPointer];
         S.curMapStackPointer--;
@@ -239,6 +250,7 @@ MPD void add_to_traffic_density(Env &e)
 // [LEAD] traffic.cpp:126-156 makeTraffic: 1 = trip found, 0 = no trip, -1 = no road at all
 MPN int make_traffic(Env &e, int x, int y, int dest)
 {
+    MP_COV(make_traffic);
     S.curMapStackPointer = 0;
     if (find_perimeter_road(e, x, y)) {
         if (try_drive(e, x, y, dest)) {
@@ -253,6 +265,7 @@ MPN int make_traffic(Env &e, int x, int y, int dest)
 // ------------------------------------------------------------------ zones (zone.cpp)
 MPD void inc_rate_of_growth(Env &e, int x, int y, int amount)      // zone.cpp:300-306
 {
+    MP_COV(inc_rate_of_growth);
     int v = s8get(e.rog(), x, y);
     v = tclamp(v + amount * 4, -200, 200);
     s8set(e.rog(), x, y, v);
@@ -260,6 +273,7 @@ MPD void inc_rate_of_growth(Env &e, int x, int y, int amount)      // zone.cpp:3
 
 MPN int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:271-293
 {
+    MP_COV(land_pollution_value);
     int16_t lv = (int16_t)b2get(e.landval(), x, y);
     lv = (int16_t)(lv - b2get(e.pollution(), x, y));
     if (lv < 30) return 0;
@@ -271,6 +285,7 @@ MPN int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:2
 // [LEAD] zone.cpp:315-352 zonePlop
 MPN bool zone_plop(Env &e, int x, int y, int base)
 {
+    MP_COV(zone_plop);
     MP_NOUNROLL for (int z = 0; z < 9; z++) {
         int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
         if (inb(xx, yy)) {
@@ -290,6 +305,7 @@ MPN bool zone_plop(Env &e, int x, int y, int base)
 
 MPD int16_t do_free_pop(const Env &e, int x, int y)                // zone.cpp:360-377
 {
+    MP_COV(do_free_pop);
     int16_t count = 0;
     MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
         MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
@@ -306,6 +322,7 @@ MPD int16_t ind_zone_pop(int t) { return t == T_INDCLR ? (int16_t)0 : (int16_t)(
 
 MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:493-517
 {
+    MP_COV(eval_lot);
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     int16_t z = (int16_t)(e.map()[tix(x, y)] & LOMASK);
     if (z && (z < T_RESBASE || z > T_RESBASE + 8)) return -1;
@@ -321,6 +338,7 @@ MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:4
 // [LEAD] zone.cpp:444-484 buildHouse
 MPN void build_house(Env &e, int x, int y, int value)
 {
+    MP_COV(build_house);
     const int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
     int16_t best = 0, hscore = 0;
     MP_NOUNROLL for (int16_t z = 1; z < 9; z++) {
@@ -341,16 +359,19 @@ MPN void build_house(Env &e, int x, int y, int value)
 
 MPD void res_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:741-747
 {
+    MP_COV(res_plop);
     int16_t base = (int16_t)(((value * 4 + den) * 9) + T_RZB - 4);
     zone_plop(e, x, y, base);
 }
 MPD void com_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:900-906
 {
+    MP_COV(com_plop);
     int16_t base = (int16_t)(((value * 5) + den) * 9 + T_CZB - 4);
     zone_plop(e, x, y, base);
 }
 MPD void ind_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:1005-1009
 {
+    MP_COV(ind_plop);
     int16_t base = (int16_t)(((value * 4) + den) * 9 + T_IND1);
     zone_plop(e, x, y, base);
 }
@@ -358,6 +379,7 @@ MPD void ind_plop(Env &e, int x, int y, int den, int value)        // zone.cpp:1
 // [LEAD] zone.cpp:596-630 doResIn
 MPN void do_res_in(Env &e, int x, int y, int pop, int value)
 {
+    MP_COV(do_res_in);
     if (b2get(e.pollution(), x, y) > 128) return;
     int t = e.map()[tix(x, y)] & LOMASK;
     if (t == T_FREEZ) {
@@ -381,6 +403,7 @@ MPN void do_res_in(Env &e, int x, int y, int pop, int value)
 // [LEAD] zone.cpp:639-704 doResOut
 MPN void do_res_out(Env &e, int x, int y, int pop, int value)
 {
+    MP_COV(do_res_out);
     const int8_t brdr[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
     if (!pop) return;
     if (pop > 16) {
@@ -416,6 +439,7 @@ MPN void do_res_out(Env &e, int x, int y, int pop, int value)
 // [LEAD] zone.cpp:240-264 makeHospital
 MPN void make_hospital(Env &e, int x, int y)
 {
+    MP_COV(make_hospital);
     if (S.needHospital > 0) {
         zone_plop(e, x, y, T_HOSPITAL - 4);
         S.needHospital = 0;
@@ -431,6 +455,7 @@ MPN void make_hospital(Env &e, int x, int y)
 
 MPD int16_t eval_res(const Env &e, int x, int y, int traf)         // zone.cpp:757-777
 {
+    MP_COV(eval_res);
     if (traf < 0) return -3000;
     int16_t v = (int16_t)b2get(e.landval(), x, y);
     v = (int16_t)(v - b2get(e.pollution(), x, y));
@@ -442,6 +467,7 @@ MPD int16_t eval_res(const Env &e, int x, int y, int traf)         // zone.cpp:7
 // [LEAD] zone.cpp:526-587 doResidential
 MPN void do_residential(Env &e, int x, int y, bool zonePower)
 {
+    MP_COV(do_residential);
     S.resZonePop++;
     int t = e.map()[tix(x, y)] & LOMASK;
     int16_t tpop = (t == T_FREEZ) ? do_free_pop(e, x, y) : res_zone_pop(t);
@@ -471,6 +497,7 @@ MPN void do_residential(Env &e, int x, int y, bool zonePower)
 // [LEAD] zone.cpp:786-888 doCommercial / doComIn / doComOut
 MPN void do_commercial(Env &e, int x, int y, bool zonePower)
 {
+    MP_COV(do_commercial);
     int t = e.map()[tix(x, y)] & LOMASK;
     S.comZonePop++;
     int16_t tpop = com_zone_pop(t);
@@ -504,6 +531,7 @@ MPN void do_commercial(Env &e, int x, int y, bool zonePower)
 // [LEAD] zone.cpp:187-232 setSmoke
 MPN void set_smoke(Env &e, int x, int y, bool zonePower)
 {
+    MP_COV(set_smoke);
     const uint8_t aniThis[8] = { 1, 0, 1, 1, 0, 0, 1, 1 };
     const int8_t dx1[8] = { -1, 0, 1, 0, 0, 0, 0, 1 }, dy1[8] = { -1, 0, -1, -1, 0, 0, -1, -1 };
     const int16_t aniTabB[8] = { 0, 0, 36, 44, 0, 0, 52, 60 };
@@ -526,6 +554,7 @@ MPN void set_smoke(Env &e, int x, int y, bool zonePower)
 
 MPD void do_ind_out(Env &e, int x, int y, int pop, int value)      // zone.cpp:969-981
 {
+    MP_COV(do_ind_out);
     if (pop > 1) { ind_plop(e, x, y, pop - 2, value); inc_rate_of_growth(e, x, y, -8); return; }
     if (pop == 1) { zone_plop(e, x, y, T_INDBASE); inc_rate_of_growth(e, x, y, -8); }
 }
@@ -533,6 +562,7 @@ MPD void do_ind_out(Env &e, int x, int y, int pop, int value)      // zone.cpp:9
 // [LEAD] zone.cpp:916-957 doIndustrial
 MPN void do_industrial(Env &e, int x, int y, bool zonePower)
 {
+    MP_COV(do_industrial);
     int t = e.map()[tix(x, y)] & LOMASK;
     S.indZonePop++;
     set_smoke(e, x, y, zonePower);
@@ -562,6 +592,7 @@ MPN void do_industrial(Env &e, int x, int y, bool zonePower)
 // [LEAD] simulate.cpp:1390-1421 repairZone
 MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
 {
+    MP_COV(repair_zone);
     int tile = zCent - 2 - zSize;
     MP_NOUNROLL for (int yy = -1; yy < zSize - 1; yy++)
         MP_NOUNROLL for (int xx = -1; xx < zSize - 1; xx++) {
@@ -580,6 +611,7 @@ MPN void repair_zone(Env &e, int x, int y, int zCent, int zSize)
 // [LEAD] zone.cpp:127-180 doHospitalChurch
 MPN void do_hospital_church(Env &e, int x, int y)
 {
+    MP_COV(do_hospital_church);
     int t = e.map()[tix(x, y)] & LOMASK;
     if (t == T_HOSPITAL) {
         S.hospitalPop++;
@@ -597,6 +629,7 @@ MPN void do_hospital_church(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1652-1705 doMeltdown
 MPN void do_meltdown(Env &e, int x, int y)
 {
+    MP_COV(do_meltdown);
     make_explosion(e, x - 1, y - 1);
     make_explosion(e, x - 1, y + 2);
     make_explosion(e, x + 2, y - 1);
@@ -616,6 +649,7 @@ MPN void do_meltdown(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1430-1585 doSpecialZone (+ drawStadium :1588, doAirport :1606, coalSmoke :1624)
 MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 {
+    MP_COV(do_special_zone);
     const int meltdownTable[3] = { 30000, 20000, 10000 };
     int t = e.map()[tix(x, y)] & LOMASK;
     switch (t) {
@@ -699,6 +733,7 @@ MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 // [LEAD] zone.cpp:79-120 doZone
 MPQ void do_zone(Env &e, int x, int y)
 {
+    MP_COV(do_zone);
     bool pw = set_zone_power(e, x, y);
     if (pw) S.poweredZoneCount++; else S.unpoweredZoneCount++;
     int t = e.map()[tix(x, y)] & LOMASK;
@@ -713,6 +748,7 @@ MPQ void do_zone(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1336-1381 fireZone (also disasters.cpp doFlood)
 MPN void fire_zone(Env &e, int x, int y, int ch)
 {
+    MP_COV(fire_zone);
     int v = tclamp(s8get(e.rog(), x, y) - 20, -200, 200);
     s8set(e.rog(), x, y, v);
     ch &= LOMASK;
@@ -727,6 +763,7 @@ MPN void fire_zone(Env &e, int x, int y, int ch)
 // [LEAD] simulate.cpp:1280-1327 doFire
 MPN void do_fire(Env &e, int x, int y)
 {
+    MP_COV(do_fire);
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
     MP_NOUNROLL for (int z = 0; z < 4; z++) {
         if ((rnd16(e) & 7) == 0) {
@@ -755,6 +792,7 @@ MPN void do_fire(Env &e, int x, int y)
 // [LEAD] disasters.cpp:375-405 doFlood
 MPN void do_flood(Env &e, int x, int y)
 {
+    MP_COV(do_flood);
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     if (S.floodCount > 0) {
         MP_NOUNROLL for (int z = 0; z < 4; z++) {
@@ -778,6 +816,7 @@ MPN void do_flood(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1114-1245 doBridge
 MPN bool do_bridge(Env &e, int x, int y, int tile)
 {
+    MP_COV(do_bridge);
     const int8_t HDx[7] = { -2, 2, -2, -1, 0, 1, 2 }, HDy[7] = { -1, -1, 0, 0, 0, 0, 0 };
     const int16_t HBRTAB[7] = { T_HBRDG1 | BULLBIT, T_HBRDG3 | BULLBIT, T_HBRDG0 | BULLBIT, T_RIVER,
         T_BRWH | BULLBIT, T_RIVER, T_HBRDG2 | BULLBIT };
@@ -839,6 +878,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
 // [LEAD] simulate.cpp:1048-1111 doRoad
 MPQ void do_road(Env &e, int x, int y)
 {
+    MP_COV(do_road);
     const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
     S.roadTotal++;
     int mv = e.map()[tix(x, y)], tile = mv & LOMASK;
@@ -874,6 +914,7 @@ MPQ void do_road(Env &e, int x, int y)
 // [LEAD] simulate.cpp:1005-1037 doRail
 MPQ void do_rail(Env &e, int x, int y)
 {
+    MP_COV(do_rail);
     S.railTotal++;
     generate_train(e, x, y);
     if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {
@@ -895,6 +936,7 @@ MPQ void do_rail(Env &e, int x, int y)
 // [LEAD] simulate.cpp:929-997 body of mapScan for one tile
 MPP void scan_tile(Env &e, int idx)
 {
+    MP_COV(scan_tile);
     int mv = e.map()[idx], tile = mv & LOMASK;
     int x = idx / WORLD_H, y = idx - x * WORLD_H;
     if (tile < T_ROADBASE) {
@@ -968,6 +1010,7 @@ enum : int { TK_SERIAL = 0, TK_INERT, TK_ROAD, TK_FLOOD0, TK_RAD, TK_FIRE, TK_TI
 
 MPD int tile_kind(const Env &e, int v)
 {
+    MP_COV(tile_kind);
     const int t = v & LOMASK;
     const bool flooding = S.floodCount > 0;
     if (t < T_ROADBASE) {
@@ -1002,6 +1045,7 @@ __host__ __device__ constexpr LcgPow lcg_pow_table()
 }
 MPD uint32_t lcg_jump(uint32_t x, int n)
 {
+    MP_COV(lcg_jump);
     constexpr LcgPow t = lcg_pow_table();
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -1015,6 +1059,7 @@ MPD int lcg_r16(uint32_t x) { return (int)((x & 0xffff00u) >> 8) & 0xffff; }
 // the tile at that position is the one the batch had to stop in front of.
 MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
 {
+    MP_COV(scan_word_batch);
     const int lane = e.c.tid;
     const bool mine = (mL >> lane) & 1u;
     const int t = wi * 32 + lane;
@@ -1111,6 +1156,7 @@ MPD int scan_word_batch(Env &e, int wi, uint32_t mL, bool &serial_next)
 // the range is dense, so the common sparse loop below carries none of this.
 MPN void map_scan_dense(Env &e, int i0, int i1)
 {
+    MP_COV(map_scan_dense);
     const int w0 = i0 >> 5, w1 = (i1 - 1) >> 5;
     const int lane = e.c.tid;
     int pos = i0;
@@ -1141,6 +1187,7 @@ MPN void map_scan_dense(Env &e, int i0, int i1)
 
 MPP void map_scan(Env &e, int x1, int x2)
 {
+    MP_COV(map_scan);
     const int i0 = x1 * WORLD_H, i1 = x2 * WORLD_H;
     const int w0 = i0 >> 5, w1 = (i1 - 1) >> 5;
     int pos = i0;                                   // first tile not yet passed by the scan
@@ -1221,6 +1268,7 @@ MPP void map_scan(Env &e, int x1, int x2)
 // on all six graphs at once (read everything, barrier, write).
 MPD void scroll_history(Env &e, int lo, int hi)
 {
+    MP_COV(scroll_history);
     int16_t *h[6] = { e.resHist(), e.comHist(), e.indHist(), e.crimeHist(), e.pollutionHist(), e.moneyHist() };
     const int n = hi - lo + 1;                       // <= 119 entries per graph: 4 per lane
     int16_t v[6][4];
@@ -1246,6 +1294,7 @@ MPD void scroll_history(Env &e, int lo, int hi)
 // [ALL] simulate.cpp:712-780 take10Census
 MPN void take10_census(Env &e)
 {
+    MP_COV(take10_census);
 #if MP_WARP_COOP
     scroll_history(e, 0, 118);
 #else
@@ -1278,6 +1327,7 @@ MPN void take10_census(Env &e)
 // [ALL] simulate.cpp:784-826 take120Census
 MPN void take120_census(Env &e)
 {
+    MP_COV(take120_census);
 #if MP_WARP_COOP
     scroll_history(e, 120, 238);
 #else
@@ -1299,6 +1349,7 @@ MPN void take120_census(Env &e)
 // [LEAD] budget.cpp:107-316 doBudgetNow(false)
 MPN void do_budget(Env &e)
 {
+    MP_COV(do_budget);
     int64_t fireInt = (int)(S.fireFund * S.firePercent);
     int64_t policeInt = (int)(S.policeFund * S.policePercent);
     int64_t roadInt = (int)(S.roadFund * S.roadPercent);
@@ -1358,6 +1409,7 @@ MPN void do_budget(Env &e)
 // [LEAD] simulate.cpp:838-884 collectTax
 MPN void collect_tax(Env &e)
 {
+    MP_COV(collect_tax);
     const float RLevels[3] = { 0.7f, 0.9f, 1.2f }, FLevels[3] = { 1.4f, 1.2f, 0.8f };
     S.cashFlow = 0;
     if (!S.taxFlag) {
@@ -1381,12 +1433,14 @@ MPN void collect_tax(Env &e)
 // [ALL] simulate.cpp:327-350 decTrafficMap (four cells per 32-bit word on the device)
 MPD uint8_t dec_traffic_cell(int z)
 {
+    MP_COV(dec_traffic_cell);
     if (z == 0) return 0;
     if (z <= 24) return 0;
     return (uint8_t)(z > 200 ? z - 34 : z - 24);
 }
 MPN void dec_traffic_map(Env &e)
 {
+    MP_COV(dec_traffic_map);
 #if defined(__CUDA_ARCH__)
     // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit word with byte-SIMD:
     // z - (z > 200 ? 34 : 24) saturated at 0 is exactly the reference's three-way rule.
@@ -1430,6 +1484,7 @@ MPN void dec_traffic_map(Env &e)
 // [ALL] simulate.cpp:356-385 decRateOfGrowthMap
 MPN void dec_rog_map(Env &e)
 {
+    MP_COV(dec_rog_map);
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int16_t z = e.rog()[i];
         if (z == 0) continue;
@@ -1441,6 +1496,7 @@ MPN void dec_rog_map(Env &e)
 MPD int64_t get_population(const Env &e) { return ((int64_t)S.resPop + ((int64_t)S.comPop + S.indPop) * 8L) * 20L; }
 MPD int city_class_of(int64_t p)                                    // evaluate.cpp:190-218
 {
+    MP_COV(city_class_of);
     int c = 0;
     if (p > 2000) c = 1;
     if (p > 10000) c = 2;
@@ -1454,6 +1510,7 @@ MPD int city_class_of(int64_t p)                                    // evaluate.
 // front-end callbacks; only the state they gate (growth caps, category bookkeeping) is kept.
 MPN void send_messages(Env &e)
 {
+    MP_COV(send_messages);
     if ((S.cityTime & 3) == 0) {
         int16_t category = 0;
         int64_t thisCityPop = get_population(e);
@@ -1483,6 +1540,7 @@ MPN void send_messages(Env &e)
 // on how many duplicate plant entries the stack held).
 MPN bool power_scan_walk(Env &e)
 {
+    MP_COV(power_scan_walk);
     const int maxPower = S.coalPowerPop * 700 + S.nuclearPowerPop * 2000;     // <= 32767 * 2000 < 2^31
     int numPower = 0, sp = S.powerStackPointer;
     const bool no_seeds = sp <= 0;                // nothing to walk from: the grid stays empty
@@ -1530,6 +1588,7 @@ MPN bool power_scan_walk(Env &e)
 //   Tile i's neighbours are i -/+ 1 (same column: y -/+ 1, not across a column end) and i -/+ 100.
 MPN bool power_scan_parallel(Env &e)
 {
+    MP_COV(power_scan_parallel);
     const int lane = e.c.tid;
     uint32_t *C = reinterpret_cast<uint32_t *>(e.tmp1());
     int T = 0, wlo = POWER_WORDS, whi = -1;
@@ -1598,6 +1657,7 @@ MPN bool power_scan_parallel(Env &e)
 // (simulate.cpp:226, 289, 418); it is folded in here so that refresh_need sees the new value.
 MPN void do_power_scan(Env &e, bool set_new_power = true)
 {
+    MP_COV(do_power_scan);
     // Memo (Scalars::powerQuiet / powerPure): nothing conductive has changed since a scan whose seeds were
     // all current plants, so the walk would rebuild the grid it already has; only its side effects remain --
     // the drained stack and newPower.
@@ -1625,35 +1685,21 @@ MPN void do_power_scan(Env &e, bool set_new_power = true)
 }
 
 // ------------------------------------------------------------------ smoothing passes
-// [ALL] scan.cpp:551-575 smoothDitherMap, non-dither branch (donDither = 0 on this path)
-MPN void smooth_byte2(Env &e, const uint8_t *src, uint8_t *dst)
-{
-    for (int i = e.c.tid; i < N2; i += e.c.n) {
-        int x = i / H2, y = i - x * H2;
-        int16_t z = 0;
-        if (x > 0) z = (int16_t)(z + src[i - H2]);
-        if (x < W2 - 1) z = (int16_t)(z + src[i + H2]);
-        if (y > 0) z = (int16_t)(z + src[i - 1]);
-        if (y < H2 - 1) z = (int16_t)(z + src[i + 1]);
-        z = (int16_t)((z + src[i]) >> 2);
-        if (z > 255) z = 255;
-        dst[i] = (uint8_t)z;
-    }
-    e.c.sync();
-}
-
-// Sparse form of the same pass.  The half-resolution maps of a gym city are zero outside the few dozen
+// [ALL] scan.cpp:551-575 smoothDitherMap, non-dither branch (donDither = 0 on this path): z = (sum of the four
+// neighbours + self) >> 2, capped at 255 -- in sparse form.  The half-resolution maps of a gym city are zero outside the few dozen
 // cells around the build window, and smoothing zeros gives zeros: `box` = {x0, x1, y0, y1} (inclusive)
 // bounds every non-zero cell of src; the pass zero-fills dst, computes only the box grown by one cell,
 // and grows `box` for the next pass.  An empty box (x0 > x1) means src is all zero.
 struct CellBox { int x0, x1, y0, y1; };
 MPD void zero_byte2(Env &e, uint8_t *m)
 {
+    MP_COV(zero_byte2);
     uint4 *q = reinterpret_cast<uint4 *>(m);                    // 3000 bytes + padding = 188 uint4
     for (int i = e.c.tid; i < (N2 + 15) / 16; i += e.c.n) q[i] = make_uint4(0, 0, 0, 0);
 }
 MPD void smooth_byte2_box(Env &e, const uint8_t *src, uint8_t *dst, CellBox &box)
 {
+    MP_COV(smooth_byte2_box);
     zero_byte2(e, dst);
     e.c.sync();
     if (box.x0 > box.x1) return;
@@ -1675,10 +1721,12 @@ MPD void smooth_byte2_box(Env &e, const uint8_t *src, uint8_t *dst, CellBox &box
 // bounding box of the cells a lane has seen -> the group's box
 MPD void box_add(CellBox &b, int x, int y)
 {
+    MP_COV(box_add);
     b.x0 = tmin(b.x0, x); b.x1 = tmax(b.x1, x); b.y0 = tmin(b.y0, y); b.y1 = tmax(b.y1, y);
 }
 MPD void box_reduce(Env &e, CellBox &b)
 {
+    MP_COV(box_reduce);
 #if MP_WARP_COOP
     for (int o = 16; o > 0; o >>= 1) {
         b.x0 = min(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, o));
@@ -1694,6 +1742,7 @@ MPD void box_reduce(Env &e, CellBox &b)
 // [ALL] scan.cpp:80-105 smoothStationMap (in place through a temporary copy)
 MPN void smooth_station(Env &e, int16_t *m)
 {
+    MP_COV(smooth_station);
     for (int i = e.c.tid; i < N8; i += e.c.n) e.stmp()[i] = m[i];
     e.c.sync();
     for (int i = e.c.tid; i < N8; i += e.c.n) {
@@ -1711,6 +1760,7 @@ MPN void smooth_station(Env &e, int16_t *m)
 
 MPD int city_center_distance(const Env &e, int x, int y)            // scan.cpp:379-396
 {
+    MP_COV(city_center_distance);
     int xd = x > S.cityCenterX ? x - S.cityCenterX : S.cityCenterX - x;
     int yd = y > S.cityCenterY ? y - S.cityCenterY : S.cityCenterY - y;
     return tmin(xd + yd, 64);
@@ -1718,6 +1768,7 @@ MPD int city_center_distance(const Env &e, int x, int y)            // scan.cpp:
 
 MPD int pollution_value(int loc)                                    // scan.cpp:331-370
 {
+    MP_COV(pollution_value);
     if (loc < T_POWERBASE) {
         if (loc >= T_HTRFBASE) return 75;
         if (loc >= T_LTRFBASE) return 50;
@@ -1736,6 +1787,7 @@ MPD int pollution_value(int loc)                                    // scan.cpp:
 // block-wide integer sum of per-thread partials into e.c.red[slot] (valid after the barrier)
 MPD void coop_add(Env &e, int slot, int v)
 {
+    MP_COV(coop_add);
 #if MP_WARP_COOP
     MP_NOUNROLL for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (e.c.lead()) e.c.red[slot] += v;
@@ -1756,6 +1808,7 @@ MPD void coop_add(Env &e, int slot, int v)
 MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool nonzero_only, int *count, int *total,
                      int lo = 0, int hi = N2)
 {
+    MP_COV(tie_max_scan);
 #if MP_WARP_COOP
     const int lane = e.c.tid;
     const unsigned lt = (1u << lane) - 1u;
@@ -1822,6 +1875,7 @@ MPD int tie_max_scan(Env &e, const uint8_t *vals, const uint8_t *valid, bool non
 // [ALL] scan.cpp:217-322 pollutionTerrainLandValueScan (+ :454-497 smoothTerrain, non-dither)
 MPN void ptlv_scan(Env &e)
 {
+    MP_COV(ptlv_scan);
     if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; }
     // tempMap3: +15 per natural tile (0 < tile < RUBBLE) in each 4x4 block (Byte wrap)
     for (int i = e.c.tid; i < N4; i += e.c.n) {
@@ -1916,6 +1970,7 @@ MPN void ptlv_scan(Env &e)
 // [ALL] scan.cpp:403-450 crimeScan
 MPN void crime_scan(Env &e)
 {
+    MP_COV(crime_scan);
     smooth_station(e, e.policeSt());
     smooth_station(e, e.policeSt());
     smooth_station(e, e.policeSt());
@@ -1973,6 +2028,7 @@ MPN void crime_scan(Env &e)
 
 MPD int population_density_of(const Env &e, int x, int y, int tile)     // scan.cpp:186-210
 {
+    MP_COV(population_density_of);
     if (tile == T_FREEZ) return do_free_pop(e, x, y);
     if (tile < T_COMBASE) return res_zone_pop(tile);
     if (tile < T_INDBASE) return com_zone_pop(tile) * 8;
@@ -1983,6 +2039,7 @@ MPD int population_density_of(const Env &e, int x, int y, int tile)     // scan.
 // [ALL] scan.cpp:126-179 populationDensityScan (+ :580-590 computeComRateMap)
 MPN void pop_density_scan(Env &e)
 {
+    MP_COV(pop_density_scan);
     if (e.c.lead()) { e.c.red[0] = 0; e.c.red[1] = 0; e.c.red[2] = 0; }
     e.c.sync();
     int xt = 0, yt = 0, zt = 0;
@@ -2055,6 +2112,7 @@ MPN void pop_density_scan(Env &e)
 // [ALL] helper so that computeComRateMap sees the centre the reference saw
 MPN void com_rate_map(Env &e, int cx, int cy)
 {
+    MP_COV(com_rate_map);
     for (int i = e.c.tid; i < N8; i += e.c.n) {
         int x = (i / H8) * 8, y = (i % H8) * 8;
         int xd = x > cx ? x - cx : cx - x, yd = y > cy ? y - cy : cy - y;
@@ -2067,6 +2125,7 @@ MPN void com_rate_map(Env &e, int cx, int cy)
 // [ALL] scan.cpp:110-120 fireAnalysis
 MPN void fire_analysis(Env &e)
 {
+    MP_COV(fire_analysis);
     smooth_station(e, e.fireSt());
     smooth_station(e, e.fireSt());
     smooth_station(e, e.fireSt());
@@ -2080,6 +2139,7 @@ MPN void fire_analysis(Env &e)
 // oracle/build_ref.sh) -- it consumes a draw per visit and never votes.
 MPN void city_evaluation(Env &e)
 {
+    MP_COV(city_evaluation);
     if (S.totalPop > 0) {
         int16_t pt[PROBNUM + 1];
         MP_NOUNROLL for (int z = 0; z <= PROBNUM; z++) pt[z] = 0;
@@ -2188,6 +2248,7 @@ MPN void city_evaluation(Env &e)
 // value of lane 0 for every lane
 MPD int coop_bcast(Env &e, int v)
 {
+    MP_COV(coop_bcast);
 #if MP_WARP_COOP
     return __shfl_sync(0xffffffffu, v, 0);
 #else
@@ -2198,12 +2259,14 @@ MPD int coop_bcast(Env &e, int v)
 // scan periods by speed index (simulate.cpp:124-135); si == 2 (simSpeed 3) is the gym path
 MPD bool scan_due(int cyc, int si, int slow, int mid, int fast)
 {
+    MP_COV(scan_due);
     return si == 2 ? (cyc % fast) == 0 : (si == 1 ? (cyc % mid) == 0 : (cyc % slow) == 0);
 }
 
 // [ALL] one phase of simulate() (simulate.cpp:122-268).  `phase` is uniform across the lanes.
 MPD void simulate_phase(Env &e, int phase)
 {
+    MP_COV(simulate_phase);
     const int si = tclamp((int)S.simSpeed - 1, 0, 2);
     const int cyc = S.simCycle;
     switch (phase) {
@@ -2270,6 +2333,7 @@ MPD void simulate_phase(Env &e, int phase)
 // [ALL] simulate.cpp:122-268 simulate
 MPP void simulate(Env &e)
 {
+    MP_COV(simulate);
     const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
     e.c.sync();
     simulate_phase(e, phase);
@@ -2287,12 +2351,14 @@ MPP void simulate(Env &e)
 // [ALL] one simulation phase + its closing barrier, out of line once (the frame loops call it)
 MPN void sim_phase(Env &e, int phase)
 {
+    MP_COV(sim_phase);
     simulate_phase(e, phase);
     e.c.sync();
 }
 // [LEAD-guarded inside] the sprite pass of a frame (moveObjects; an empty list only counts the cycle)
 MPD void sim_sprites(Env &e)
 {
+    MP_COV(sim_sprites);
     if (e.c.lead()) {
         if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }
         else move_objects(e);
@@ -2301,6 +2367,7 @@ MPD void sim_sprites(Env &e)
 }
 MPN int sim_loop_head(Env &e)
 {
+    MP_COV(sim_loop_head);
     const int phase = S.initSimLoad ? 0 : (S.phaseCycle & 15);
     int run = 0;
     if (e.c.lead()) {
@@ -2318,6 +2385,7 @@ MPN int sim_loop_head(Env &e)
 }
 MPN void sim_loop_tail(Env &e, int ran)
 {
+    MP_COV(sim_loop_tail);
     if (e.c.lead()) {
         if (ran) S.phaseCycle = (int16_t)(ran & 15);
         if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }      // moveObjects with an empty list
@@ -2327,6 +2395,7 @@ MPN void sim_loop_tail(Env &e, int ran)
 }
 MPD void sim_loop(Env &e)
 {
+    MP_COV(sim_loop);
     const int ran = sim_loop_head(e);
     sim_loop_tail(e, ran);
 }
@@ -2334,6 +2403,7 @@ MPD void sim_loop(Env &e)
 // [ALL] simulate.cpp:276-305 doSimInit (+ :390-421 initSimMemory)
 MPD void do_sim_init(Env &e)
 {
+    MP_COV(do_sim_init);
     if (e.c.lead()) {
         S.phaseCycle = 0;
         S.simCycle = 0;
@@ -2392,6 +2462,7 @@ MPD void do_sim_init(Env &e)
 // `act` does not change).
 MPN void animate_tiles(Env &e)
 {
+    MP_COV(animate_tiles);
     MP_NOUNROLL for (int w = e.c.tid; w < POWER_WORDS; w += e.c.n) {
         uint32_t m = e.act()[w], nd = e.need()[w];
         while (m) {

@@ -14,6 +14,7 @@ namespace mp {
 
 MPD int get_sprite(Env &e, int type)                         // sprite.cpp:336-344
 {
+    MP_COV(get_sprite);
     int i = S.globalSprites[type];
     if (i < 0 || e.spr()[i].frame == 0) return -1;
     return i;
@@ -22,6 +23,7 @@ MPD int get_sprite(Env &e, int type)                         // sprite.cpp:336-3
 // [LEAD] sprite.cpp:125-296 initSprite
 MPN void init_sprite(Env &e, int si, int x, int y)
 {
+    MP_COV(init_sprite);
     Sprite &sp = e.spr()[si];
     sp.x = (int16_t)x; sp.y = (int16_t)y; sp.frame = 0;
     sp.origX = 0; sp.origY = 0; sp.destX = 0; sp.destY = 0; sp.count = 0; sp.soundCount = 0;
@@ -89,6 +91,7 @@ MPN void init_sprite(Env &e, int si, int x, int y)
 // [LEAD] sprite.cpp:93-118 newSprite
 MPN int new_sprite(Env &e, int type, int x, int y)
 {
+    MP_COV(new_sprite);
     int si = -1;
     MP_NOUNROLL for (int i = 0; i < MAX_SPRITES; i++)
         if (!e.spr()[i].used) { si = i; break; }
@@ -104,6 +107,7 @@ MPN int new_sprite(Env &e, int type, int x, int y)
 // [LEAD] sprite.cpp:303-329 destroySprite
 MPD void destroy_sprite(Env &e, int si)
 {
+    MP_COV(destroy_sprite);
     if (S.globalSprites[e.spr()[si].type] == si) S.globalSprites[e.spr()[si].type] = -1;
     if (S.spriteHead == si) S.spriteHead = e.spr()[si].next;
     else
@@ -115,6 +119,7 @@ MPD void destroy_sprite(Env &e, int si)
 // [LEAD] sprite.cpp:352-365 makeSprite
 MPD int make_sprite(Env &e, int type, int x, int y)
 {
+    MP_COV(make_sprite);
     int si = S.globalSprites[type];
     if (si < 0) return new_sprite(e, type, x, y);
     init_sprite(e, si, x, y);
@@ -124,11 +129,13 @@ MPD int make_sprite(Env &e, int type, int x, int y)
 MPN void make_explosion_at(Env &e, int x, int y) { new_sprite(e, SPR_EXPLOSION, x - 40, y - 16); }   // sprite.cpp:2029
 MPN void make_explosion(Env &e, int x, int y)                  // sprite.cpp:2017-2022
 {
+    MP_COV(make_explosion);
     if (inb(x, y)) make_explosion_at(e, (x << 4) + 8, (y << 4) + 8);
 }
 
 MPD int boat_distance(Env &e, int x, int y)                    // simulate.cpp:1253-1273
 {
+    MP_COV(boat_distance);
     int dist = 99999, mx = x * 16 + 8, my = y * 16 + 8;
     MP_NOUNROLL for (int i = S.spriteHead; i >= 0; i = e.spr()[i].next) {
         const Sprite &sp = e.spr()[i];
@@ -142,6 +149,7 @@ MPD int boat_distance(Env &e, int x, int y)                    // simulate.cpp:1
 
 MPD int16_t get_char(const Env &e, int x, int y)               // sprite.cpp:376-386
 {
+    MP_COV(get_char);
     x >>= 4; y >>= 4;
     if (!inb(x, y)) return -1;
     return (int16_t)(e.map()[tix(x, y)] & LOMASK);
@@ -149,6 +157,7 @@ MPD int16_t get_char(const Env &e, int x, int y)               // sprite.cpp:376
 
 MPD int16_t turn_to(int p, int d)                              // sprite.cpp:395-423
 {
+    MP_COV(turn_to);
     if (p == d) return (int16_t)p;
     if (p < d) { if (d - p < 4) p++; else p--; }
     else { if (p - d < 4) p--; else p++; }
@@ -159,6 +168,7 @@ MPD int16_t turn_to(int p, int d)                              // sprite.cpp:395
 
 MPD bool try_other(int tpoo, int told, int tnew)               // sprite.cpp:426-443
 {
+    MP_COV(try_other);
     int16_t z = (int16_t)(told + 4);
     if (z > 8) z -= 8;
     if (tnew != z) return false;
@@ -167,6 +177,7 @@ MPD bool try_other(int tpoo, int told, int tnew)               // sprite.cpp:426
 
 MPD bool sprite_not_in_bounds(const Sprite &sp)                // sprite.cpp:451-457
 {
+    MP_COV(sprite_not_in_bounds);
     int x = sp.x + sp.xHot, y = sp.y + sp.yHot;
     return x < 0 || y < 0 || x >= (WORLD_W << 4) || y >= (WORLD_H << 4);
 }
@@ -174,6 +185,7 @@ MPD bool sprite_not_in_bounds(const Sprite &sp)                // sprite.cpp:451
 // sprite.cpp:471-511 getDir (sets absDist; keeps the `dispY * 2 < dispY` slip)
 MPD int16_t get_dir(Env &e, int ox, int oy, int dx_, int dy_)
 {
+    MP_COV(get_dir);
     const int16_t gd[13] = { 0, 3, 2, 1, 3, 4, 5, 7, 6, 5, 7, 8, 1 };
     int dispX = dx_ - ox, dispY = dy_ - oy, z;
     if (dispX < 0) z = dispY < 0 ? 11 : 8;
@@ -188,12 +200,14 @@ MPD int16_t get_dir(Env &e, int ox, int oy, int dx_, int dy_)
 
 MPD bool sprite_collision(const Sprite &a, const Sprite &b)    // sprite.cpp:536-541
 {
+    MP_COV(sprite_collision);
     return a.frame != 0 && b.frame != 0
         && (iabs((a.x + a.xHot) - (b.x + b.xHot)) + iabs((a.y + a.yHot) - (b.y + b.yHot))) < 30;
 }
 
 MPD void explode_sprite(Env &e, int si)                        // sprite.cpp:1649-1688
 {
+    MP_COV(explode_sprite);
     Sprite &sp = e.spr()[si];
     sp.frame = 0;
     make_explosion_at(e, sp.x + sp.xHot, sp.y + sp.yHot);
@@ -202,6 +216,7 @@ MPD void explode_sprite(Env &e, int si)                        // sprite.cpp:164
 // [LEAD] sprite.cpp:1752-1786 startFireInZone
 MPD void start_fire_in_zone(Env &e, int x, int y, int ch)
 {
+    MP_COV(start_fire_in_zone);
     int v = tclamp(s8get(e.rog(), x, y) - 20, -200, 200);
     s8set(e.rog(), x, y, v);
     ch &= LOMASK;
@@ -216,6 +231,7 @@ MPD void start_fire_in_zone(Env &e, int x, int y, int ch)
 // [LEAD] sprite.cpp:1709-1746 destroyMapTile
 MPN void destroy_map_tile(Env &e, int ox, int oy)
 {
+    MP_COV(destroy_map_tile);
     int x = (int16_t)(ox >> 4), y = (int16_t)(oy >> 4);
     if (!inb(x, y)) return;
     int16_t z = (int16_t)e.map()[tix(x, y)];
@@ -238,6 +254,7 @@ MPN void destroy_map_tile(Env &e, int ox, int oy)
 // [LEAD] sprite.cpp:1800-1822 startFire
 MPD void start_fire(Env &e, int x, int y)
 {
+    MP_COV(start_fire);
     x >>= 4; y >>= 4;
     if (!inb(x, y)) return;
     int z = e.map()[tix(x, y)], t = z & LOMASK;
@@ -250,6 +267,7 @@ MPD void start_fire(Env &e, int x, int y)
 // [LEAD] sprite.cpp:608-673 doTrainSprite
 MPN void do_train(Env &e, int si)
 {
+    MP_COV(do_train);
     Sprite &sp = e.spr()[si];
     const int16_t Cx[4] = { 0, 16, 0, -16 }, Cy[4] = { -16, 0, 16, 0 };
     const int16_t Dx[5] = { 0, 4, 0, -4, 0 }, Dy[5] = { -4, 0, 4, 0, 0 };
@@ -279,6 +297,7 @@ MPN void do_train(Env &e, int si)
 // [LEAD] sprite.cpp:680-770 doCopterSprite
 MPN void do_copter(Env &e, int si)
 {
+    MP_COV(do_copter);
     Sprite &sp = e.spr()[si];
     const int16_t CDx[9] = { 0, 0, 3, 5, 3, 0, -3, -5, -3 }, CDy[9] = { 0, -5, -3, 0, 3, 5, 3, 0, -3 };
     if (sp.soundCount > 0) sp.soundCount--;
@@ -314,6 +333,7 @@ MPN void do_copter(Env &e, int si)
 // [LEAD] sprite.cpp:777-850 doAirplaneSprite
 MPN void do_airplane(Env &e, int si)
 {
+    MP_COV(do_airplane);
     const int16_t CDx[12] = { 0, 0, 6, 8, 6, 0, -6, -8, -6, 8, 8, 8 };
     const int16_t CDy[12] = { 0, -8, -6, 0, 6, 8, 6, 0, -6, 0, 0, 0 };
     int16_t z = e.spr()[si].frame;
@@ -352,6 +372,7 @@ MPN void do_airplane(Env &e, int si)
 // [LEAD] sprite.cpp:857-984 doShipSprite
 MPN void do_ship(Env &e, int si)
 {
+    MP_COV(do_ship);
     Sprite &sp = e.spr()[si];
     const int16_t BDx[9] = { 0, 0, 1, 1, 1, 0, -1, -1, -1 }, BDy[9] = { 0, -1, -1, 0, 1, 1, 1, 0, -1 };
     const int16_t BPx[9] = { 0, 0, 2, 2, 2, 0, -2, -2, -2 }, BPy[9] = { 0, -2, -2, 0, 2, 2, 2, 0, -2 };
@@ -412,6 +433,7 @@ MPN void do_ship(Env &e, int si)
 
 MPD void hit_vehicles(Env &e, int si)                          // shared by monster and tornado
 {
+    MP_COV(hit_vehicles);
     MP_NOUNROLL for (int s = S.spriteHead; s >= 0; s = e.spr()[s].next) {
         int ty = e.spr()[s].type;
         if (e.spr()[s].frame != 0
@@ -424,6 +446,7 @@ MPD void hit_vehicles(Env &e, int si)                          // shared by mons
 // [LEAD] sprite.cpp:997-1181 doMonsterSprite
 MPN void do_monster(Env &e, int si)
 {
+    MP_COV(do_monster);
     Sprite &sp = e.spr()[si];
     const int16_t Gx[5] = { 2, 2, -2, -2, 0 }, Gy[5] = { -2, 2, 2, -2, 0 };
     const int16_t ND1[4] = { 0, 1, 2, 3 }, ND2[4] = { 1, 2, 3, 0 };
@@ -511,6 +534,7 @@ MPN void do_monster(Env &e, int si)
 // [LEAD] sprite.cpp:1188-1248 doTornadoSprite
 MPN void do_tornado(Env &e, int si)
 {
+    MP_COV(do_tornado);
     Sprite &sp = e.spr()[si];
     const int16_t CDx[9] = { 2, 3, 2, 0, -2, -3, 0, 0, 0 }, CDy[9] = { -2, 0, 2, 3, 2, 0, 0, 0, 0 };
     int16_t z = sp.frame;
@@ -534,6 +558,7 @@ MPN void do_tornado(Env &e, int si)
 // [LEAD] sprite.cpp:1255-1288 doExplosionSprite
 MPN void do_explosion(Env &e, int si)
 {
+    MP_COV(do_explosion);
     Sprite &sp = e.spr()[si];
     if ((S.spriteCycle & 1) == 0) sp.frame++;
     if (sp.frame > 6) {
@@ -551,6 +576,7 @@ MPN void do_explosion(Env &e, int si)
 // (generateBus call commented out, simulate.cpp:1062).
 MPN void move_objects(Env &e)
 {
+    MP_COV(move_objects);
     if (!S.simSpeed) return;
     S.spriteCycle++;
     MP_NOUNROLL for (int si = S.spriteHead; si >= 0;) {
@@ -577,12 +603,14 @@ MPN void move_objects(Env &e)
 // ------------------------------------------------------------------ sprite generators
 MPN void generate_train(Env &e, int x, int y)                  // sprite.cpp:1831-1837
 {
+    MP_COV(generate_train);
     if (S.totalPop > 20 && get_sprite(e, SPR_TRAIN) < 0 && rnd(e, 25) == 0)
         make_sprite(e, SPR_TRAIN, (x << 4) - 39, (y << 4) + 6);
 }
 
 MPN void generate_ship(Env &e)                                 // sprite.cpp:1854-1898
 {
+    MP_COV(generate_ship);
     if (!(rnd16(e) & 3))
         MP_NOUNROLL for (int x = 4; x < WORLD_W - 2; x++)
             if (e.map()[tix(x, 0)] == T_CHANNEL) { make_sprite(e, SPR_SHIP, (x << 4) - 47, 0); return; }
@@ -605,12 +633,14 @@ MPN void generate_ship(Env &e)                                 // sprite.cpp:185
 
 MPN void generate_copter(Env &e, int x, int y)                 // sprite.cpp:1968-1975
 {
+    MP_COV(generate_copter);
     if (get_sprite(e, SPR_HELICOPTER) >= 0) return;
     make_sprite(e, SPR_HELICOPTER, x << 4, (y << 4) + 30);
 }
 
 MPN void generate_plane(Env &e, int x, int y)                  // sprite.cpp:1982-1989
 {
+    MP_COV(generate_plane);
     if (get_sprite(e, SPR_AIRPLANE) >= 0) return;
     make_sprite(e, SPR_AIRPLANE, (x << 4) + 48, (y << 4) + 12);
 }
@@ -618,6 +648,7 @@ MPN void generate_plane(Env &e, int x, int y)                  // sprite.cpp:198
 // [LEAD] sprite.cpp:1912-1953 makeMonster / makeMonsterAt
 MPN void make_monster(Env &e)
 {
+    MP_COV(make_monster);
     int si = get_sprite(e, SPR_MONSTER);
     if (si >= 0) {
         e.spr()[si].soundCount = 1; e.spr()[si].count = 1000;
@@ -639,6 +670,7 @@ MPN void make_monster(Env &e)
 // [LEAD] sprite.cpp:1995-2013 makeTornado
 MPN void make_tornado(Env &e)
 {
+    MP_COV(make_tornado);
     int si = get_sprite(e, SPR_TORNADO);
     if (si >= 0) { e.spr()[si].count = 200; return; }
     int16_t x = (int16_t)(rnd(e, (WORLD_W << 4) - 800) + 400);
@@ -649,6 +681,7 @@ MPN void make_tornado(Env &e)
 // ------------------------------------------------------------------ disasters (disasters.cpp)
 MPD bool vulnerable(int tem)                                   // disasters.cpp:311-320
 {
+    MP_COV(vulnerable);
     int t2 = tem & LOMASK;
     return !(t2 < T_RESBASE || t2 > T_LASTZONE || (tem & ZONEBIT));
 }
@@ -656,6 +689,7 @@ MPD bool vulnerable(int tem)                                   // disasters.cpp:
 // [LEAD] disasters.cpp:246-269 makeEarthquake
 MPN void make_earthquake(Env &e)
 {
+    MP_COV(make_earthquake);
     int strength = rnd(e, 700) + 300;
     MP_NOUNROLL for (int16_t z = 0; z < strength; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
@@ -674,6 +708,7 @@ MPN void make_earthquake(Env &e)
 // and are committed as 2 draws each, that one iteration is replayed by the serial lane, and so on.
 MPN void make_earthquake_coop(Env &e)
 {
+    MP_COV(make_earthquake_coop);
 #if MP_WARP_COOP
     int strength = 0;
     if (e.c.lead()) strength = rnd(e, 700) + 300;
@@ -717,6 +752,7 @@ MPN void make_earthquake_coop(Env &e)
 // [LEAD] disasters.cpp:273-290 setFire
 MPN void set_fire(Env &e)
 {
+    MP_COV(set_fire);
     int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
     int16_t z = (int16_t)e.map()[tix(x, y)];
     if ((z & ZONEBIT) == 0) {
@@ -728,6 +764,7 @@ MPN void set_fire(Env &e)
 // [LEAD] disasters.cpp:327-368 makeFlood
 MPN void make_flood(Env &e)
 {
+    MP_COV(make_flood);
     const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
@@ -753,6 +790,7 @@ MPN void make_flood(Env &e)
 // defer_quake: return 1 instead of running makeEarthquake (the caller runs make_earthquake_coop on all lanes)
 MPN int do_disasters(Env &e, bool defer_quake)
 {
+    MP_COV(do_disasters);
     const int16_t chance[3] = { 10 * 48, 5 * 48, 60 };
     if (S.floodCount) S.floodCount--;
     if (!S.enableDisasters) return 0;

@@ -56,6 +56,8 @@ inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned
 #define MP_WARP_COOP 0
 #endif
 
+#include "mp_cov.h"
+
 namespace mp {
 
 constexpr int WORLD_W = 120, WORLD_H = 100, NTILES = WORLD_W * WORLD_H;

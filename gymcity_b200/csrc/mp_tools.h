@@ -78,6 +78,7 @@ MPD int neutralize_road(int t) { return (t >= 64 && t <= 207) ? (t & 0xf) + 64 :
 
 MPD bool tally(int t)                                              // tool.cpp:381-388
 {
+    MP_COV(tally);
     return (t >= T_FIRSTRIVEDGE && t <= T_LASTRUBBLE) || (t >= T_POWERBASE + 2 && t <= T_POWERBASE + 12)
         || (t >= T_TINYEXP && t <= T_LASTTINYEXP + 2);
 }
@@ -86,6 +87,7 @@ MPD bool is_tree(int v) { int t = v & LOMASK; return t >= T_WOODS_LOW && t <= T_
 // connect.cpp:554-734 fixSingle
 MPN void fix_single(Fx &fx, int x, int y)
 {
+    MP_COV(fix_single);
     const uint16_t RoadTable[16] = { T_ROADS, T_ROADS2, T_ROADS, T_ROADS3, T_ROADS2, T_ROADS2, T_ROADS4,
         T_ROADS8, T_ROADS, T_ROADS6, T_ROADS, T_ROADS7, T_ROADS5, T_ROADS10, T_ROADS9, T_INTERSECTION };
     const uint16_t RailTable[16] = { T_LHRAIL, T_LVRAIL, T_LHRAIL, T_LVRAIL2, T_LVRAIL, T_LVRAIL,
@@ -152,12 +154,14 @@ MPN void fix_single(Fx &fx, int x, int y)
 // usual case (five tiles of ground, water or buildings) costs no calls
 MPD bool fix_candidate(const Fx &fx, int x, int y)
 {
+    MP_COV(fix_candidate);
     const int t = neutralize_road(fx.tile(x, y));
     return (t >= T_ROADS && t <= T_INTERSECTION) || (t >= T_LHRAIL && t <= T_LVRAIL10)
         || (t >= T_LHPOWER && t <= T_LVPOWER10);
 }
 MPD void fix_zone(Fx &fx, int x, int y)                            // connect.cpp:523-545
 {
+    MP_COV(fix_zone);
     if (fix_candidate(fx, x, y)) fix_single(fx, x, y);
     if (y > 0 && fix_candidate(fx, x, y - 1)) fix_single(fx, x, y - 1);
     if (x < WORLD_W - 1 && fix_candidate(fx, x + 1, y)) fix_single(fx, x + 1, y);
@@ -167,6 +171,7 @@ MPD void fix_zone(Fx &fx, int x, int y)                            // connect.cp
 
 MPD int lay_doze(Fx &fx, int x, int y)                             // connect.cpp:193-236
 {
+    MP_COV(lay_doze);
     int v = fx.value(x, y);
     if (!(v & BULLBIT)) return TR_FAILED;
     int t = neutralize_road(v & LOMASK);
@@ -186,6 +191,7 @@ MPD int lay_doze(Fx &fx, int x, int y)                             // connect.cp
 
 MPN int lay_road(Fx &fx, int x, int y)                             // connect.cpp:246-329
 {
+    MP_COV(lay_road);
     int cost = 10, t = fx.tile(x, y);
     switch (t) {
     case T_DIRT: fx.set(x, y, T_ROADS | BULLBIT | BURNBIT); break;
@@ -231,6 +237,7 @@ MPN int lay_road(Fx &fx, int x, int y)                             // connect.cp
 
 MPN int lay_rail(Fx &fx, int x, int y)                             // connect.cpp:338-425
 {
+    MP_COV(lay_rail);
     int cost = 20, t = neutralize_road(fx.tile(x, y));
     switch (t) {
     case T_DIRT: fx.set(x, y, T_LHRAIL | BULLBIT | BURNBIT); break;
@@ -276,6 +283,7 @@ MPN int lay_rail(Fx &fx, int x, int y)                             // connect.cp
 
 MPN int lay_wire(Fx &fx, int x, int y)                             // connect.cpp:434-520
 {
+    MP_COV(lay_wire);
     int cost = 5, t = neutralize_road(fx.tile(x, y));
     switch (t) {
     case T_DIRT: fx.set(x, y, T_LHPOWER | CONDBIT | BURNBIT | BULLBIT); break;
@@ -319,6 +327,7 @@ enum ConnectCmd : int { CC_FIX = 0, CC_BULLDOZE, CC_ROAD, CC_RAILROAD, CC_WIRE }
 // connect.cpp:122-184 connectTile
 MPN int connect_tile(Fx &fx, int x, int y, int cmd)
 {
+    MP_COV(connect_tile);
     Env &e = fx.e;
     int result = TR_OK;
     if (!inb(x, y)) return TR_FAILED;
@@ -346,6 +355,7 @@ MPN int connect_tile(Fx &fx, int x, int y, int cmd)
 // tool.cpp:299-378 checkBigZone: offset of the zone centre from a non-centre tile of a 4x4 / 6x6
 MPD int check_big_zone(int id, int &dh, int &dv)
 {
+    MP_COV(check_big_zone);
     dh = 0; dv = 0;
     const int base4[4] = { T_POWERPLANT, T_PORT, T_NUCLEAR, T_STADIUM };
     MP_NOUNROLL for (int k = 0; k < 4; k++) {
@@ -363,6 +373,7 @@ MPD int check_big_zone(int id, int &dh, int &dv)
 
 MPD int check_size(int t)                                          // tool.cpp:397-413
 {
+    MP_COV(check_size);
     if ((t >= T_RESBASE - 1 && t <= T_PORTBASE - 1) || (t >= T_LASTPOWERPLANT + 1 && t <= T_POLICESTATION + 4)
         || (t >= T_CHURCH1BASE && t <= T_CHURCH7LAST))
         return 3;
@@ -374,6 +385,7 @@ MPD int check_size(int t)                                          // tool.cpp:3
 
 MPD void put_rubble(Fx &fx, int x, int y, int size)                // tool.cpp:910-924
 {
+    MP_COV(put_rubble);
     Env &e = fx.e;
     MP_NOUNROLL for (int xx = x; xx < x + size; xx++)
         MP_NOUNROLL for (int yy = y; yy < y + size; yy++)
@@ -389,6 +401,7 @@ MPD void put_rubble(Fx &fx, int x, int y, int size)                // tool.cpp:9
 // tool.cpp:965-1072 bulldozerTool(x, y, effects)
 MPN int bulldozer_tool(Fx &fx, int x, int y)
 {
+    MP_COV(bulldozer_tool);
     if (!inb(x, y)) return TR_FAILED;
     int v = fx.value(x, y), t = v & LOMASK, size, dh = 0, dv = 0;
     if (v & ZONEBIT) size = check_size(t);
@@ -406,6 +419,7 @@ MPN int bulldozer_tool(Fx &fx, int x, int y)
 // tool.cpp:480-540 buildBuilding (+ :415-478 prepareBuildingSite / putBuilding / checkBorder)
 MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, bool anim)
 {
+    MP_COV(build_building);
     Env &e = fx.e;
     x--; y--;
     if (x < 0 || x + size > WORLD_W) return TR_FAILED;
@@ -440,6 +454,7 @@ MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, b
 // generate.cpp:436-475 smoothTreesAt(x, y, preserve, effects)
 MPD void smooth_trees_at_fx(Fx &fx, int x, int y, bool preserve)
 {
+    MP_COV(smooth_trees_at_fx);
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     if (!is_tree(fx.value(x, y))) return;
@@ -461,6 +476,7 @@ MPD void smooth_trees_at_fx(Fx &fx, int x, int y, bool preserve)
 // [LEAD] tool.cpp:1375-1516 doTool + toolDown.  Returns the ToolResult.
 MPN int tool_down(Env &e, int tool, int x, int y)
 {
+    MP_COV(tool_down);
     const int16_t costOf[TOOL_COUNT] = { 100, 100, 100, 500, 500, 0, 5, 1, 20, 10, 5000, 10, 3000, 3000,
         5000, 10000, 100, 0, 0, 0 };
     x = (int16_t)x; y = (int16_t)y;
@@ -556,6 +572,7 @@ MPN int tool_down(Env &e, int tool, int x, int y)
 // ------------------------------------------------------------------ terrain generator (generate.cpp)
 MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.cpp:572-598
 {
+    MP_COV(put_on_map);
     if (ch == 0 || !inb(x, y)) return;
     int temp = e.map()[tix(x, y)];
     if (temp != T_DIRT) {
@@ -569,6 +586,7 @@ MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.c
 // generate.cpp:604-626 plopBRiver: 9x9 disc, REDGE rim, RIVER body, CHANNEL centre
 MPN void plop_b_river(Env &e, int px, int py)
 {
+    MP_COV(plop_b_river);
     const int8_t lo[9] = { 3, 2, 1, 0, 0, 0, 1, 2, 3 };    // first non-empty column of each row
     MP_NOUNROLL for (int x = 0; x < 9; x++)
         MP_NOUNROLL for (int y = 0; y < 9; y++) {
@@ -582,6 +600,7 @@ MPN void plop_b_river(Env &e, int px, int py)
 // generate.cpp:632-651 plopSRiver: 6x6 disc
 MPN void plop_s_river(Env &e, int px, int py)
 {
+    MP_COV(plop_s_river);
     const int8_t lo[6] = { 2, 1, 0, 0, 1, 2 };
     MP_NOUNROLL for (int x = 0; x < 6; x++)
         MP_NOUNROLL for (int y = 0; y < 6; y++) {
@@ -593,6 +612,7 @@ MPN void plop_s_river(Env &e, int px, int py)
 
 MPN int do_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big)   // generate.cpp:498-570
 {
+    MP_COV(do_river);
     const int rate1 = 100, rate2 = 200;        // terrainCurveLevel = -1 (micropolis.cpp:393)
     const int ext = big ? 4 : 3;
     while (inb(px + ext, py + ext)) {
@@ -609,6 +629,7 @@ MPN int do_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big)
 
 MPN void smooth_river(Env &e)                                      // generate.cpp:354-395
 {
+    MP_COV(smooth_river);
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
     const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
         19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
@@ -633,6 +654,7 @@ MPN void smooth_river(Env &e)                                      // generate.c
 
 MPN void smooth_trees(Env &e)                                      // generate.cpp:410-422 (+ :425-430)
 {
+    MP_COV(smooth_trees);
     const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
@@ -656,6 +678,7 @@ MPN void smooth_trees(Env &e)                                      // generate.c
 
 MPN void do_trees(Env &e)                                          // generate.cpp:330-348 (+ :299-324)
 {
+    MP_COV(do_trees);
     int16_t amount = (int16_t)(rnd(e, 100) + 50);          // terrainTreeLevel = -1
     MP_NOUNROLL for (int16_t i = 0; i < amount; i++) {
         int16_t xloc = rnd(e, WORLD_W - 1), yloc = rnd(e, WORLD_H - 1);
@@ -675,6 +698,7 @@ MPN void do_trees(Env &e)                                          // generate.c
 
 MPN void make_naked_island(Env &e)                                 // generate.cpp:193-231
 {
+    MP_COV(make_naked_island);
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
         MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
             mset(e, tix(x, y), (x < 5 || x >= WORLD_W - 5 || y < 5 || y >= WORLD_H - 5) ? T_RIVER : T_DIRT);
@@ -700,6 +724,7 @@ MPN void make_naked_island(Env &e)                                 // generate.c
 // (terrainTreeLevel = terrainLakeLevel = terrainCurveLevel = terrainCreateIsland = -1)
 MPN void generate_map(Env &e, int seed)
 {
+    MP_COV(generate_map);
     S.rng = (uint32_t)seed;
     if (rnd(e, 100) < 10) {
         make_naked_island(e);
@@ -759,6 +784,7 @@ MPN void generate_map(Env &e, int seed)
 // Tiles are stored directly: generate_some_city rebuilds the derived bitmaps afterwards (rebuild_active).
 MPD void gen_put(Env &e, int ch, int x, int y)                      // generate.cpp:572-598 putOnMap
 {
+    MP_COV(gen_put);
     if (ch == 0 || !inb(x, y)) return;
     int temp = e.map()[tix(x, y)];
     if (temp != T_DIRT) {
@@ -770,6 +796,7 @@ MPD void gen_put(Env &e, int ch, int x, int y)                      // generate.
 }
 MPD void gen_plop_b(Env &e, int px, int py)                         // generate.cpp:604-626
 {
+    MP_COV(gen_plop_b);
     MP_NOUNROLL for (int c = e.c.tid; c < 81; c += 32) {
         const int x = c / 9, y = c - x * 9;
         const int l = y < 4 ? 3 - y : (y > 4 ? y - 5 : 0);         // first non-empty column of the row
@@ -783,6 +810,7 @@ MPD void gen_plop_b(Env &e, int px, int py)                         // generate.
 }
 MPD void gen_plop_s(Env &e, int px, int py)                         // generate.cpp:632-651
 {
+    MP_COV(gen_plop_s);
     MP_NOUNROLL for (int c = e.c.tid; c < 36; c += 32) {
         const int x = c / 6, y = c - x * 6;
         const int l = y < 2 ? 2 - y : (y > 3 ? y - 3 : 0);
@@ -795,6 +823,7 @@ MPD void gen_plop_s(Env &e, int px, int py)                         // generate.
 }
 MPN int gen_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big)   // generate.cpp:498-570
 {
+    MP_COV(gen_river);
     const int ext = big ? 4 : 3;
     while (inb(px + ext, py + ext)) {
         if (big) gen_plop_b(e, px, py); else gen_plop_s(e, px, py);
@@ -814,6 +843,7 @@ MPN int gen_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big
 // generate.cpp:354-395 smoothRiver for one tile (lead lane: the tile whose coin flip was rejected)
 MPD int gen_redge_value(Env &e, int idx)
 {
+    MP_COV(gen_redge_value);
     const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
         19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
         5 | BULLBIT, 2 };
@@ -831,6 +861,7 @@ MPD int gen_redge_value(Env &e, int idx)
 }
 MPN void gen_smooth_river(Env &e)
 {
+    MP_COV(gen_smooth_river);
     const int lane = e.c.tid;
     MP_NOUNROLL for (int base = 0; base < NTILES; base += 32) {
         int pos = base;
@@ -865,6 +896,7 @@ MPN void gen_smooth_river(Env &e)
 // generate.cpp:410-430 smoothTrees as a wavefront over the anti-diagonals
 MPN void gen_smooth_trees(Env &e)
 {
+    MP_COV(gen_smooth_trees);
     const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     const int lane = e.c.tid;
     MP_NOUNROLL for (int d = 0; d < WORLD_W + WORLD_H - 1; d++) {
@@ -891,6 +923,7 @@ MPN void gen_smooth_trees(Env &e)
 // generate.cpp:299-348 doTrees / treeSplash
 MPN void gen_trees(Env &e)
 {
+    MP_COV(gen_trees);
     const int lane = e.c.tid;
     int amount = 0;
     if (lane == 0) amount = rnd(e, 100) + 50;
@@ -940,6 +973,7 @@ MPN void gen_trees(Env &e)
 // [ALL] generate.cpp:119-160 generateMap(seed), same map and same final RNG state as generate_map above
 MPN void generate_map_coop(Env &e, int seed)
 {
+    MP_COV(generate_map_coop);
     const int lane = e.c.tid;
     int island = 0;
     if (lane == 0) { S.rng = (uint32_t)seed; island = rnd(e, 100) < 10; }

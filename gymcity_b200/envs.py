@@ -28,7 +28,8 @@ class BatchedVecEnv:
         return self.env.reset()
 
     def step_async(self, actions, out=None):                 # VecPyTorch.step_async (envs.py:364-366)
-        self._pending = (actions.reshape(-1), out)
+        # one flat action per env; the paint env takes a tool per window cell, (N, W, H)
+        self._pending = (actions if getattr(self.env, "paint_actions", False) else actions.reshape(-1), out)
 
     def step_wait(self):                                     # VecPyTorch.step_wait (envs.py:368-376)
         actions, out = self._pending
@@ -70,10 +71,11 @@ def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, add_timestep, d
                       num_proc=g('num_proc', num_processes), device=dev_index)
         env.seed(seed)
         return env
-    if 'micropolis' not in name or 'paint' in name:
-        raise NotImplementedError("%s: only MicropolisEnv-v0 and GoLMultiEnv-v0 are on the tick path" % env_name)
-    from .micropolis_env import MicropolisVecEnv
-    env = MicropolisVecEnv(num_processes, g('map_width', 20), device=dev_index, seed=seed,
+    if 'micropolis' not in name:
+        raise NotImplementedError("%s: only MicropolisEnv-v0, MicropolisPaintEnv-v0 and GoLMultiEnv-v0 are on the tick path" % env_name)
+    from .micropolis_env import MicropolisPaintEnv, MicropolisVecEnv
+    cls = MicropolisPaintEnv if 'paint' in name else MicropolisVecEnv      # envs.py:74, gym_city/envs/paintenv.py
+    env = cls(num_processes, g('map_width', 20), device=dev_index, seed=seed,
                            max_step=g('max_step', None), empty_start=not g('random_terrain', True),
                            power_puzzle=bool(g('power_puzzle', False)), random_builds=bool(g('random_builds', False)),
                            poet=bool(g('poet', False)),

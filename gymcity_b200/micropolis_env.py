@@ -547,6 +547,7 @@ class MicropolisPaintEnv(MicropolisVecEnv):
     """gym_city/envs/paintenv.py: the agent names a tool for EVERY window cell each step.  Batched:
     step(a) takes (N, W, H) tool indices (uint8 / integer tensor or array); the action space is the
     reference's Box(0, num_tools - 1, (W, H))."""
+    paint_actions = True
 
     def setMapSize(self, size, **kwargs):
         super().setMapSize(size, **kwargs)

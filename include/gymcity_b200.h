@@ -101,6 +101,11 @@ int mpb_group_times(mpb_handle h, float *ms_out);
  * an env-step used): enable != 0 starts / clears the recording, out_host (may be NULL) receives what was
  * recorded so far, enable == 0 stops and frees it.  One batch per process at a time. */
 int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host);
+/* Test infrastructure: function-hit coverage of a -DMP_COVERAGE build (csrc/mp_cov.h).  mpb_coverage copies the
+ * bitmap (bit i = function i was entered by some env since load; uint64 words) and returns the number of functions,
+ * or -1 in a product build; mpb_coverage_name(i) names function i. */
+int mpb_coverage(unsigned long long *bits_out, int cap_words);
+const char *mpb_coverage_name(int id);
 /* Profiling: device time (ms) of the auto-reset part of the last env step and how many envs it reset. */
 int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out);
 /* Profiling: the heavy-first env order the NEXT env-step's launches use (int32 [n_envs] HOST); returns the

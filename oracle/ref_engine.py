@@ -11,7 +11,7 @@ import re
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_LIB = os.path.join(HERE, "_ref", "libmicropolis_ref.so")
+REF_LIB = os.environ.get("MPREF_LIB", os.path.join(HERE, "_ref", "libmicropolis_ref.so"))     # MPREF_LIB: the ASan / UBSan build (tools/sanitize_host.sh)
 SNAPSHOT_H = os.path.join(HERE, "..", "include", "mp_snapshot.h")
 
 WORLD_W, WORLD_H = 120, 100

@@ -16,6 +16,8 @@ LIB = os.path.join(HERE, "_hostbuild", "libmph.so")
 
 
 def build_host_engine():
+    if os.environ.get("MPH_LIB"):                    # the ASan / UBSan build (tools/sanitize_host.sh)
+        return os.environ["MPH_LIB"]
     deps = [SRC] + glob.glob(os.path.join(ROOT, "gymcity_b200", "csrc", "mp_*.h")) \
         + glob.glob(os.path.join(ROOT, "include", "*.h"))
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):

@@ -343,3 +343,44 @@ def test_sticky_obs_buffer_and_per_call_out():
     o4, *_ = env.step(a)
     assert o4.data_ptr() == env.micro.obs.data_ptr()
     env.close()
+
+
+def test_handles_on_threads_do_not_share_state():
+    """Library hygiene: the scheduler / profiling state lives in the handle, so several handles driven from several
+    threads of one process (one learner process with a handle per GPU) run the rollouts they run alone.  Four handles
+    of different batch sizes (8-, 16- and 32-city CTAs, different group geometry) step concurrently on four threads
+    and streams; each rollout is compared with the same handle configuration run on its own."""
+    import threading
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+
+    sizes = [40, 700, 2500, 9600]
+
+    def rollout(n, out, k, barrier=None):
+        torch.cuda.set_device(0)
+        with torch.cuda.stream(torch.cuda.Stream()):
+            env = MicropolisVecEnv(n, 16, seed=40 + k, max_step=6, empty_start=False)
+            env.reset()
+            rng = np.random.default_rng(k)
+            acc = torch.zeros(n, 1, device="cuda")
+            if barrier is not None:
+                barrier.wait()
+            for t in range(14):
+                obs, rew, done, _ = env.step(torch.from_numpy(rng.integers(0, 20 * 256, n)))
+                acc += rew
+            torch.cuda.current_stream().synchronize()
+            out[k] = (obs.sum(dim=(1, 2, 3)).cpu().numpy(), acc.cpu().numpy(), env.micro.counters())
+            env.close()
+
+    alone, together = {}, {}
+    for k, n in enumerate(sizes):
+        rollout(n, alone, k)
+    barrier = threading.Barrier(len(sizes))
+    threads = [threading.Thread(target=rollout, args=(n, together, k, barrier)) for k, n in enumerate(sizes)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for k in range(len(sizes)):
+        for a, b in zip(alone[k], together[k]):
+            assert np.array_equal(a, b), k

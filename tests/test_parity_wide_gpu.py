@@ -227,3 +227,26 @@ def test_tools_every_tool_every_terrain_on_the_gpu():
             _check(b, refs, "tools %d" % k)
     _check(b, refs, "tools final")
     b.close()
+
+
+def test_speed_divider_frames():
+    """simLoop's speed divider (main.cpp:403-425: at simSpeed 1 every 5th frame simulates, at 2 every 3rd, at 3 every
+    one).  The gym path always runs at 3 and takes the frame kernel's fast path; envs at 1, 2 and 0 (paused) take the
+    general one (sim_loop_head / sim_loop_tail) inside the same lockstep CTA."""
+    n = 4
+    b, refs = _mk(n)
+    ss = np.arange(n) + 90
+    b.generate(ss + 10, ss)
+    for i, r in enumerate(refs):
+        r.generate(int(ss[i]) + 10)
+        r.seed(int(ss[i]))
+        sc = r.scalars()
+        sc.simSpeed = [1, 2, 3, 0][i]
+        r.set_scalars(sc)
+        b.set_scalars(i, sc)
+    for k in range(5):
+        b.simFrames(77)
+        for r in refs:
+            r.simFrames(77)
+        _check(b, refs, "frames %d" % k)
+    b.close()

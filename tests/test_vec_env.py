@@ -94,3 +94,25 @@ def test_make_vec_envs_extinction_and_gol():
     obs = gol.reset()
     assert tuple(obs.shape) == (64, 2, 16, 16)
     gol.close()
+
+
+@pytest.mark.gpu
+def test_make_vec_envs_paint_env():
+    """MicropolisPaintEnv-v0 through make_vec_envs (envs.py:74): Box action space, one tool per window cell per step."""
+    from gymcity_b200.envs import make_vec_envs
+    dev = torch.device("cuda", 0)
+    N = 3
+    args = types.SimpleNamespace(map_width=12, max_step=5, random_terrain=True)
+    v = make_vec_envs('MicropolisPaintEnv-v0', 2, N, 0.99, None, False, dev, True, args=args)
+    assert tuple(v.action_space.shape) == (12, 12)
+    obs = v.reset()
+    assert tuple(obs.shape) == (N, 32, 12, 12)
+    rng = np.random.default_rng(0)
+    ended = 0
+    for t in range(8):
+        a = torch.from_numpy(rng.integers(0, 20, (N, 12, 12))).to(dev)
+        obs, rew, done, infos = v.step(a)
+        assert tuple(obs.shape) == (N, 32, 12, 12) and rew.shape == (N, 1) and done.shape == (N,)
+        ended += int(done.sum())
+    assert ended == N                                                    # max_step = 5: one auto-reset each
+    v.close()

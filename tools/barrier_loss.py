@@ -19,11 +19,16 @@ def collect(n, age):
     for t in range(age):
         env.step(torch.randint(0, 20 * 256, (n,), device='cuda', generator=g))
     eng = env.micro.engine
-    perm, G = eng.read_schedule()
     eng.frame_profile(True)
-    env.step(torch.randint(0, 20 * 256, (n,), device='cuda', generator=g))
-    prof = eng.frame_profile(True, read=True)[:, :200]
-    np.savez_compressed('gpurun_out/frame_prof.npz', prof=prof, perm=perm, groups=G, age=age)
+    profs, perms = [], []
+    for k in range(4):                                   # four consecutive steps: how well does a step predict the next?
+        env.step(torch.randint(0, 20 * 256, (n,), device='cuda', generator=g))
+        profs.append(eng.frame_profile(True, read=True)[:, :200].astype(np.uint32))
+        perm, G = eng.read_schedule()                    # the order this step used (rebuilt at the start of every step)
+        perms.append(perm)
+    prof, perm = profs[0], perms[0]
+    np.savez_compressed('gpurun_out/frame_prof.npz', prof=prof, perm=perm, groups=G, age=age, more=np.stack(profs[1:]),
+                        perms=np.stack(perms))
     return prof, perm, G, age
 
 
