@@ -7,6 +7,7 @@
 // it through SWIG (gym_city/envs/corecontrol.py:36-357) -- construction, clearMap/generateMap,
 // toolDown, setFunds, simTick / tickEngine, and the per-cell getters used to read state back.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,7 +48,11 @@ struct MpBatch {
     unsigned long long *cycles;   // [n_envs] SM cycles each env spent in k_mp_frames since the last read (profiling)
     unsigned int *cost;       // [n_envs] cycles of the current step (schedule key for the next one)
     int *perm;                // [n_envs] env ids, most expensive first
-    unsigned int *hist;       // [SCHED_NB + 1]
+    unsigned long long *cls_sum;   // [SCHED_CLASSES] summed cost of the envs of a schedule class
+    unsigned int *cls_cnt;    // [SCHED_CLASSES] how many
+    unsigned int *skey, *skey_out;    // [n_envs] sort keys of the schedule
+    int *sval;                // [n_envs] env ids (sort values in)
+    void *sort_tmp; size_t sort_tmp_bytes;
     int use_sched;
     int sms;                  // SMs of the device
     int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
@@ -162,6 +167,15 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
     unstage_scalars(e, sw);
 }
 
+// A group of envs = the slots { off + (w / chunk) * chunk * stride + w % chunk : w < count } of the schedule:
+// whole chunks of `chunk` consecutive slots (one k_mp_frames CTA's worth), dealt out to the groups in turn, so that
+// the envs of a CTA are neighbours in the schedule -- same class, similar cost.
+struct GroupGeom { int off, stride, count, chunk; };
+__host__ __device__ __forceinline__ int geom_slot(const GroupGeom &q, int w)
+{
+    return q.chunk <= 1 ? w * q.stride + q.off : q.off + (w / q.chunk) * q.chunk * q.stride + (w % q.chunk);
+}
+
 // `count` simFrames (simLoop(true), main.cpp:403-425) for every env, frames [first, first + count) of
 // a simTick of simPasses frames.  All envs of the batch run the same frames in the same launch, so
 // every warp on the GPU is in (nearly) the same simulation phase and executes the same code: the
@@ -179,9 +193,8 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
 template <int MP_FEPC>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
-            int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, int gstride,
-            int goff, int gcount, int scan_block, unsigned int *prof, int prof_off, const uint8_t *mask,
-            const int *gcount_dev)
+            int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, GroupGeom q,
+            int scan_block, unsigned int *prof, int prof_off, const uint8_t *mask, const int *gcount_dev)
 {
     __shared__ int red[8 * MP_FEPC];
     // the scalar block (census counters, cycle counters, RNG state, valves ...) is what the serial
@@ -191,13 +204,13 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     // list-driven launches (device-side auto-reset: `perm` is the list of envs being reset and *gcount_dev its
     // length, unknown to the host) use a fixed grid and walk the list; every other launch has one CTA per
     // MP_FEPC slots and runs the loop body once
-    if (gcount_dev) gcount = *gcount_dev;
+    const int gcount = gcount_dev ? *gcount_dev : q.count;
     for (int cta = blockIdx.x; cta * MP_FEPC < gcount; cta += gridDim.x) {
     const long long t_begin = clock64();
     // heavy-first: slot k of the grid runs the k-th most expensive env of the previous step, so the
     // long envs (flood / fire fields) start in the first wave instead of forming the launch's tail
     const int widx = cta * MP_FEPC + (threadIdx.x >> 5);
-    const int slot = widx * gstride + goff;
+    const int slot = geom_slot(q, widx);
     bool live = widx < gcount && slot < n_envs;
     int env = 0;
     if (live) {
@@ -302,67 +315,55 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
     }
 }
 
-// Schedule key: (phase class, cost bucket).  Envs of one k_mp_frames CTA run in frame lockstep, which only works when
-// they are in the same phase of the 16-phase cycle: an env that was reset (or stepped under a mask) on another step is
-// half a cycle away from its neighbours (200 frames per env-step = 8 mod 16) -- its map-scan block would meet the
-// others' census / power-scan frames and every frame would cost the maximum of the two (measured: episodes of 200
-// steps with staggered resets ran at 34 ms per step instead of 20).  So the order is by phase class first, and by cost,
-// most expensive first, inside a class; only the CTAs at the <= 15 class boundaries are mixed.
-constexpr int SCHED_BUCKETS = 1024;
-constexpr int SCHED_CLASSES = 16;
-constexpr int SCHED_NB = SCHED_BUCKETS * SCHED_CLASSES;
-__device__ __forceinline__ int sched_bucket(unsigned int cost, int phase)      // cost = cycles >> 8 of one step
-{
-    unsigned int k = cost >> 5;                                      // 2^13 busy cycles per bucket (mean env: ~300)
-    return (phase & 15) * SCHED_BUCKETS + SCHED_BUCKETS - 1 - (int)(k < (unsigned)SCHED_BUCKETS ? k : SCHED_BUCKETS - 1);   // expensive first
-}
-__device__ __forceinline__ int env_phase(const uint8_t *blocks, int env)
+// The order in which the envs are dealt out to the CTAs of a step ("schedule").  Envs of one k_mp_frames CTA run in
+// frame lockstep, which pays off only when they execute the same code in the same frame:
+//  * the same phase of the 16-phase cycle: an env that was reset (or stepped under a mask) on another step is half a
+//    cycle away from its neighbours (200 frames per env-step = 8 mod 16) -- its map-scan block would meet the others'
+//    census / power-scan frames (measured: 38.8 ms per step instead of 20 with episodes of 200 steps);
+//  * the same simulation cycle count: the periodic scans (power every 5 cycles, pollution / land value every 17,
+//    crime 18, population density 19, fire coverage 20, the census every 4 and tax / evaluation every 48 city-time
+//    units) fall into the same frames only for envs with the same cityTime; in a CTA of mixed ages some env runs
+//    one of them in almost every cycle and the CTA pays for it every time (28.6 ms instead of 20.4, no reset in
+//    sight: tools/episode_probe2.py).
+// So the primary sort key is the env's schedule CLASS = hash(cityTime, phase) -- envs reset on the same step share
+// it --, classes ordered by their mean cost (most expensive first: long CTAs start early in a launch), and inside a
+// class the envs by their own cost of the previous step, most expensive first.  With one class (all envs reset
+// together: the plain rollout) this is the heavy-first order by cost alone.
+constexpr int SCHED_CLASS_BITS = 12;
+constexpr int SCHED_CLASSES = 1 << SCHED_CLASS_BITS;
+__device__ __forceinline__ unsigned int env_sched_class(const uint8_t *blocks, int env)
 {
     const Scalars *sc = reinterpret_cast<const Scalars *>(blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
-    return sc->initSimLoad ? 0 : (sc->phaseCycle & 15);
+    const unsigned int phase = sc->initSimLoad ? 0u : (unsigned int)(sc->phaseCycle & 15);
+    const unsigned int k = ((unsigned int)sc->cityTime * 16u + phase) * 2654435761u;
+    return k >> (32 - SCHED_CLASS_BITS);
 }
 __global__ void k_mp_sched_identity(int *perm, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) perm[i] = i;
 }
-__global__ void k_mp_sched_hist(const unsigned int *cost, const uint8_t *blocks, int n, unsigned int *hist)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&hist[sched_bucket(cost[i], env_phase(blocks, i))], 1u);
-}
-__global__ void __launch_bounds__(1024) k_mp_sched_scan(unsigned int *hist)     // exclusive prefix sum, one CTA of 1024
-{
-    __shared__ unsigned int wsum[32];
-    constexpr int PER = SCHED_NB / 1024;
-    unsigned int v[PER], tot = 0;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { v[k] = hist[threadIdx.x * PER + k]; tot += v[k]; }
-    unsigned int x = tot;
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((int)(threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned int w = wsum[threadIdx.x], z = w;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, z, o);
-            if ((int)threadIdx.x >= o) z += y;
-        }
-        wsum[threadIdx.x] = z - w;
-    }
-    __syncthreads();
-    unsigned int run = wsum[threadIdx.x >> 5] + x - tot;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { hist[threadIdx.x * PER + k] = run; run += v[k]; }
-}
-__global__ void k_mp_sched_scatter(unsigned int *cost, const uint8_t *blocks, int n, unsigned int *hist, int *perm)
+__global__ void k_mp_sched_class(const unsigned int *cost, const uint8_t *blocks, int n, unsigned long long *cls_sum,
+                                 unsigned int *cls_cnt)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    perm[atomicAdd(&hist[sched_bucket(cost[i], env_phase(blocks, i))], 1u)] = i;
+    const unsigned int c = env_sched_class(blocks, i);
+    atomicAdd(&cls_sum[c], (unsigned long long)cost[i]);
+    atomicAdd(&cls_cnt[c], 1u);
+}
+// key = [mean cost of the class, inverted: 10 bits][class: 12 bits][own cost, inverted: 10 bits]; cost = cycles >> 8 of
+// the previous step, bucketed by 2^5 (2^13 busy cycles per bucket; the mean env is at ~300)
+__global__ void k_mp_sched_keys(unsigned int *cost, const uint8_t *blocks, int n, const unsigned long long *cls_sum,
+                                const unsigned int *cls_cnt, unsigned int *keys, int *vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int c = env_sched_class(blocks, i);
+    const unsigned int mean = (unsigned int)(cls_sum[c] / (unsigned long long)max(1u, cls_cnt[c]));
+    const unsigned int q = min(1023u, mean >> 5), own = min(1023u, cost[i] >> 5);
+    keys[i] = ((1023u - q) << 22) | (c << 10) | (1023u - own);
+    vals[i] = i;
     cost[i] = 0;
 }
 
@@ -473,11 +474,11 @@ k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shad
 // MicropolisPaintEnv.step, part 1 (paintenv.py:43-52): one tool per window cell, then setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre_paint(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-                   const uint8_t *actions, const int *perm, int gstride, int goff, int gcount)
+                   const uint8_t *actions, const int *perm, GroupGeom q)
 {
     __shared__ int red[8 * MP_EPC];
-    if (device_env_index() >= gcount) return;
-    const int slot = device_env_index() * gstride + goff;
+    if (device_env_index() >= q.count) return;
+    const int slot = geom_slot(q, device_env_index());
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
@@ -522,12 +523,11 @@ k_mp_env_extinguish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *
 // MicropolisEnv.step, part 1 (env.py:448-466): decoded action through TileMap.addZoneBot, setFunds
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-             const int64_t *actions, int static_build, const int *perm, int gstride, int goff, int gcount,
-             const uint8_t *mask)
+             const int64_t *actions, int static_build, const int *perm, GroupGeom q, const uint8_t *mask)
 {
     __shared__ int red[8 * MP_EPC];
-    if (device_env_index() >= gcount) return;
-    const int slot = device_env_index() * gstride + goff;
+    if (device_env_index() >= q.count) return;
+    const int slot = geom_slot(q, device_env_index());
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     if (mask && !mask[env]) return;
@@ -547,11 +547,11 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
               float *obs, float *reward, uint8_t *done, int is_reset, const uint8_t *mask, const int *perm,
-              int gstride, int goff, int gcount)
+              GroupGeom q)
 {
     __shared__ int red[8 * MP_EPC];
-    if (device_env_index() >= gcount) return;
-    const int slot = device_env_index() * gstride + goff;
+    if (device_env_index() >= q.count) return;
+    const int slot = geom_slot(q, device_env_index());
     if (slot >= n_envs) return;
     const int env = perm ? perm[slot] : slot;
     const int lane = threadIdx.x & 31;
@@ -594,15 +594,20 @@ __global__ void k_mp_env_counters(const uint8_t *blocks, const uint8_t *shadow, 
 
 #define MP_GRID(b) (((b)->n_envs + MP_EPC - 1) / MP_EPC)
 
-// Rebuild the heavy-first order from the cycles the step that just ended cost each env
-// (bucket sort, most expensive bucket first), then clear the costs for the next step.
+// Rebuild the schedule (see env_sched_class) from the phase / city time every env is at now and the cycles the
+// previous step cost it, then clear the costs for this step.  The sort itself is cub::DeviceRadixSort (n 32-bit
+// keys, ~40 us for 32 768 envs, 0.2 % of a step).
 int rebuild_schedule(MpBatch *b, cudaStream_t st)
 {
     if (!b->use_sched) return 0;
-    cudaMemsetAsync(b->hist, 0, (SCHED_NB + 1) * 4, st);
-    k_mp_sched_hist<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, b->n_envs, b->hist);
-    k_mp_sched_scan<<<1, 1024, 0, st>>>(b->hist);
-    k_mp_sched_scatter<<<(b->n_envs + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, b->n_envs, b->hist, b->perm);
+    const int n = b->n_envs;
+    cudaMemsetAsync(b->cls_sum, 0, SCHED_CLASSES * sizeof(unsigned long long), st);
+    cudaMemsetAsync(b->cls_cnt, 0, SCHED_CLASSES * sizeof(unsigned int), st);
+    k_mp_sched_class<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt);
+    k_mp_sched_keys<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt, b->skey, b->sval);
+    size_t bytes = b->sort_tmp_bytes;
+    const cudaError_t e = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm, n, 0, 32, st);
+    if (e != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = e;
     return 0;
 }
 
@@ -612,11 +617,13 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
 // second).  `mask`: device mask of the envs that take part (NULL = all).  A launch error is recorded in the handle
 // (b->launch_err) and reported by the entry point that enqueued it.
 void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, int animate_before, int respect_passes,
-                   const int *perm, int gstride, int goff, int gcount, const uint8_t *mask, int prof_off = 0, bool heavy = false)
+                   const int *perm, GroupGeom q, const uint8_t *mask, int prof_off = 0, bool heavy = false)
 {
+    const int gcount = q.count;
+    (void)heavy;
     if (gcount <= 0) return;
 #define MP_FRAMES_ARGS b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles, b->cost, perm, \
-                       gstride, goff, gcount, b->scan_block, b->prof, prof_off, mask, (const int *)NULL
+                       q, b->scan_block, b->prof, prof_off, mask, (const int *)NULL
         if (epc >= 32) k_mp_frames<32><<<(gcount + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
         else if (epc >= 16) k_mp_frames<16><<<(gcount + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
         else if (epc >= 8) k_mp_frames<8><<<(gcount + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
@@ -632,18 +639,20 @@ void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, i
 // while the other groups -- the remaining envs dealt out round robin in cost order -- have tight
 // cost distributions and short launch tails.  A group is (offset, stride, count) into the
 // heavy-first permutation.
-struct GroupGeom { int off, stride, count; };
 GroupGeom group_geom(const MpBatch *b, int G, int g)
 {
     GroupGeom q;
+    q.chunk = 1;
     if (G <= 1) { q.off = 0; q.stride = 1; q.count = b->n_envs; return q; }
     int heavy = b->use_sched && b->heavy_div > 0 ? b->n_envs / b->heavy_div : 0;   // ~1.5 % of the batch
     if (heavy < 1 || G < 3) heavy = 0;
-    if (heavy == 0) { q.off = g; q.stride = G; q.count = (b->n_envs - g + G - 1) / G; return q; }
-    if (g == 0) { q.off = 0; q.stride = 1; q.count = heavy; return q; }
-    q.off = heavy + (g - 1); q.stride = G - 1;
-    q.count = (b->n_envs - q.off + q.stride - 1) / q.stride;
-    if (q.count < 0) q.count = 0;
+    if (heavy > 0 && g == 0) { q.off = 0; q.stride = 1; q.count = heavy; return q; }
+    // the other groups: chunks of one CTA's worth of consecutive slots, dealt out in turn
+    const int Gn = heavy > 0 ? G - 1 : G, gi = heavy > 0 ? g - 1 : g;
+    const int CH = b->fepc > 1 ? b->fepc : 1;
+    const int T = b->n_envs - heavy, nchunks = (T + CH - 1) / CH;
+    const int mine = nchunks > gi ? (nchunks - gi + Gn - 1) / Gn : 0;
+    q.chunk = CH; q.stride = Gn; q.off = heavy + gi * CH; q.count = mine * CH;       // slots >= n_envs are skipped in the kernels
     return q;
 }
 #define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
@@ -657,17 +666,17 @@ int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8
     const GroupGeom q = group_geom(b, G, g);
     // the heavy group is not kept in phase lockstep: with few, very uneven envs every launch would
     // wait for ITS slowest member (a different env each time), so it runs a whole simTick per launch
-    const bool heavy_group = (G > 1 && g == 0 && q.stride == 1);
+    const bool heavy_group = (G > 1 && g == 0 && q.stride == 1 && q.chunk == 1);
     const int F = heavy_group ? (P > 0 ? P : 1) : b->frames_per_launch;
     const int epc = heavy_group ? b->heavy_fepc : b->fepc;
     if (q.count <= 0) return 0;
     if (P <= 0) {
         if (animate_before)
-            launch_frames(b, epc, st, 0, 0, 1, 1, perm, q.stride, q.off, q.count, mask, 0, heavy_group);
+            launch_frames(b, epc, st, 0, 0, 1, 1, perm, q, mask, 0, heavy_group);
         return 0;
     }
     for (int f = 0; f < P; f += F)
-        launch_frames(b, epc, st, f, (P - f < F) ? P - f : F, animate_before && f == 0, 1, perm, q.stride, q.off, q.count,
+        launch_frames(b, epc, st, f, (P - f < F) ? P - f : F, animate_before && f == 0, 1, perm, q,
                       mask, animate_before ? P : 0, heavy_group);
     return 0;
 }
@@ -695,8 +704,8 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
                                                                b->rcount, b->auto_terrain, b->run_seed, b->env_offset);
     const int P = b->passes;
     for (int t = 0; t < 2; t++)                               // MicropolisControl.simTick: simTick, animateTiles, simTick
-        k_mp_frames<1><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist, 1, 0,
-                                                    0, b->scan_block, NULL, 0, NULL, b->rcount);
+        k_mp_frames<1><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist,
+                                                    GroupGeom{0, 1, 0, 1}, b->scan_block, NULL, 0, NULL, b->rcount);
     k_mp_env_post_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->obs_out,
                                                               b->reward, b->done, b->rlist, b->rcount);
     cudaEventRecord(b->ev_ar1, st);
@@ -772,12 +781,21 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->cycles, (size_t)n_envs * 8) == cudaSuccess
         && cudaMalloc(&b->cost, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
-        && cudaMalloc(&b->hist, (SCHED_NB + 1) * 4) == cudaSuccess
+        && cudaMalloc(&b->cls_sum, SCHED_CLASSES * sizeof(unsigned long long)) == cudaSuccess
+        && cudaMalloc(&b->cls_cnt, SCHED_CLASSES * sizeof(unsigned int)) == cudaSuccess
+        && cudaMalloc(&b->skey, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->skey_out, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->sval, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->rlist, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->rcount, 4) == cudaSuccess
         && cudaMalloc(&b->amask, n_envs) == cudaSuccess
         && cudaMallocHost(&b->host_blk, ENV_STRIDE) == cudaSuccess
         && cudaMallocHost(&b->host_i32, (size_t)n_envs * 16) == cudaSuccess;
+    if (ok) {
+        b->sort_tmp_bytes = 0;
+        ok = cub::DeviceRadixSort::SortPairs(NULL, b->sort_tmp_bytes, b->skey, b->skey_out, b->sval, b->perm, n_envs, 0, 32) == cudaSuccess
+            && cudaMalloc(&b->sort_tmp, b->sort_tmp_bytes ? b->sort_tmp_bytes : 16) == cudaSuccess;
+    }
     if (!ok) { mpb_destroy(b); return NULL; }
     cudaMemcpy(b->anim, anim, sizeof(anim), cudaMemcpyHostToDevice);
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
@@ -804,7 +822,8 @@ void mpb_destroy(mpb_handle h)
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_ar0) cudaEventDestroy(b->ev_ar0);
     if (b->ev_ar1) cudaEventDestroy(b->ev_ar1);
-    cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->hist);
+    cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->cls_sum); cudaFree(b->cls_cnt);
+    cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
@@ -832,13 +851,13 @@ int mpb_launches_per_env_step(mpb_handle h)
 {
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
-    int total = b->use_sched ? 4 : 0;                       // memset + 3 scheduling kernels
+    int total = b->use_sched ? 2 : 0;                       // the two scheduling kernels of this library (the sort is CUB's)
     if (b->auto_reset) total += 6;                          // list, reset, 2 x frames, post (+ a memset node)
     const int G = step_groups(b);
     for (int g = 0; g < G; g++) {
         const GroupGeom q = group_geom(b, G, g);
         if (q.count <= 0) continue;
-        const int F = (G > 1 && g == 0 && q.stride == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
+        const int F = (G > 1 && g == 0 && q.stride == 1 && q.chunk == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
         const int per = b->passes > 0 ? (b->passes + F - 1) / F : 1;
         total += 2 + 2 * per;
     }
@@ -961,8 +980,8 @@ int mpb_sim_frames(mpb_handle h, int n, void *stream)
     cudaSetDevice(b->device);
     const int F = b->frames_per_launch;
     for (int f = 0; f < n; f += F)
-        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, (n - f < F) ? n - f : F, 0, 0, b->use_sched ? b->perm : NULL, 1, 0,
-                      b->n_envs, NULL);
+        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, (n - f < F) ? n - f : F, 0, 0, b->use_sched ? b->perm : NULL,
+                      GroupGeom{0, 1, b->n_envs, 1}, NULL);
     CK_LAUNCHES();
     return 0;
 }
@@ -984,7 +1003,7 @@ int mpb_sim_tick(mpb_handle h, int animate, void *stream)
     cudaSetDevice(b->device);
     launch_sim_tick(b, (cudaStream_t)stream, 0, NULL);
     if (animate)
-        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, 0, 1, 1, b->use_sched ? b->perm : NULL, 1, 0, b->n_envs, NULL);
+        launch_frames(b, b->fepc, (cudaStream_t)stream, 0, 0, 1, 1, b->use_sched ? b->perm : NULL, GroupGeom{0, 1, b->n_envs, 1}, NULL);
     CK_LAUNCHES();
     return 0;
 }
@@ -1274,7 +1293,7 @@ int mpb_env_reset_finish(mpb_handle h, const uint8_t *mask_host, void *stream)
     if (upload_mask(b, mask_host, st)) return -1;
     launch_control_sim_tick(b, st, mask_host ? b->mask : NULL);
     k_mp_env_post<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                    b->obs_out, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, 1, 0, b->n_envs);
+                                                    b->obs_out, b->reward, b->done, 1, mask_host ? b->mask : NULL, NULL, GroupGeom{0, 1, b->n_envs, 1});
     CK_LAUNCHES();
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -1426,13 +1445,13 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
         if (paint_dev)
             k_mp_env_pre_paint<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
-                                                           b->cfg, paint_dev, perm, q.stride, q.off, q.count);
+                                                           b->cfg, paint_dev, perm, q);
         else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                     actions_dev, static_build, perm, q.stride, q.off, q.count, mask_dev);
+                                                     actions_dev, static_build, perm, q, mask_dev);
         launch_control_sim_tick(b, gs, mask_dev, G, g);
         k_mp_env_post<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                  b->obs_out, b->reward, b->done, 0, mask_dev, perm, q.stride, q.off, q.count);
+                                                  b->obs_out, b->reward, b->done, 0, mask_dev, perm, q);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);

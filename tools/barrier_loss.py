@@ -56,12 +56,13 @@ def main():
     # units of a 50-frame launch: barrier after a frame unless its phase is 1..7
     cta_time = np.zeros(16); env_time = np.zeros(16); nunits = np.zeros(16)
     total_cta = 0.0; total_env = 0.0
-    for g in range(1, G) if heavy else range(G):
-        if heavy:
-            slots = np.arange(heavy + (g - 1), n, G - 1)
-        else:
-            slots = np.arange(g, n, G)
-        envs = perm[slots]
+    Gn = G - 1 if heavy else G
+    for gi in range(Gn):
+        # group gi takes the chunks gi, gi + Gn, ... of 32 consecutive slots after the heavy ones (group_geom)
+        T = n - heavy
+        chunks = np.arange(gi, (T + 31) // 32, Gn)
+        slots = (heavy + chunks[:, None] * 32 + np.arange(32)[None, :]).ravel()
+        envs = perm[slots[slots < n]]
         for c0 in range(0, len(envs), 32):
             ce = c[envs[c0:c0 + 32]]                     # [<=32, 200]
             for l0 in range(0, 200, 50):
