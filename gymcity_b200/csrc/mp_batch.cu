@@ -61,6 +61,11 @@ struct MpBatch {
     // per-episode seeds derived on the device (gym_episode_seed) and the device-side auto-reset of mpb_env_step*
     long long run_seed; int env_offset;
     int auto_reset, auto_terrain;
+    // terrain prefetch: the map of every env's NEXT episode, generated ahead of time on a low-priority stream
+    uint16_t *next_map;       // [n_envs][12000]
+    int32_t *next_ep;         // [n_envs] episode index next_map holds (-1: none)
+    unsigned int *pf_stats;   // [2] resets served from a prepared map / generated in line
+    cudaStream_t pf_stream; cudaEvent_t ev_pf;
     int *rlist, *rcount;      // [n_envs] envs being reset by the current step, [1] how many
     uint8_t *amask;           // [n_envs] the same as a byte mask
     int32_t *xt_rnd; size_t xt_rnd_bytes;    // device buffer of mpb_env_extinguish's draws (grown on demand)
@@ -372,11 +377,67 @@ __device__ __forceinline__ void bind_device_gym(Gym &gy, uint8_t *shadow, int st
     bind_gym(gy, shadow + (size_t)device_env_index() * stride, cfg);
 }
 
+// ---- terrain prefetch ------------------------------------------------------------------------------------------
+// generateMap is 2.5 ms of single-warp latency, and in an auto-reset it sits on the step's critical path with the GPU
+// nearly idle (a few hundred envs reset per step).  The seeds of an env's next episode are known the moment the current
+// one starts, so its map is generated ahead of time, into next_map, by a low-priority kernel that runs in the gaps of
+// the following steps; the reset then copies 24 KB instead of generating.  next_ep[env] says which episode the
+// prepared map belongs to and is written last; a reset that finds another value generates in line.
+__device__ __forceinline__ const uint16_t *prepared_terrain(const uint16_t *next_map, const int32_t *next_ep,
+                                                            unsigned int *pf_stats, int env, int ep)
+{
+    if (!next_map) return nullptr;
+    int have = 0;
+    if ((threadIdx.x & 31) == 0) {
+        have = *reinterpret_cast<const volatile int32_t *>(next_ep + env) == ep;
+        atomicAdd(&pf_stats[have ? 0 : 1], 1u);
+    }
+    have = __shfl_sync(0xffffffffu, have, 0);
+    __threadfence();
+    return have ? next_map + (size_t)env * NTILES : nullptr;
+}
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_prefetch_terrain(const uint8_t *shadow, int stride, GymCfg cfg, int n, uint16_t *next_map, int32_t *next_ep,
+                      long long run_seed, int env_offset)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_SHARED_ENV();
+    const int lane = threadIdx.x & 31;
+    for (int env = blockIdx.x; env < n; env += gridDim.x) {
+        int ep = 0, need = 0;
+        if (lane == 0) {
+            Gym gy;
+            bind_gym(gy, const_cast<uint8_t *>(shadow) + (size_t)env * stride, &cfg);
+            ep = *reinterpret_cast<const volatile int32_t *>(&gy.g->episode);
+            need = *reinterpret_cast<const volatile int32_t *>(next_ep + env) != ep;
+        }
+        ep = __shfl_sync(0xffffffffu, ep, 0);
+        need = __shfl_sync(0xffffffffu, need, 0);
+        if (!need) continue;
+        for (int i = lane; i < SCAL_WORDS; i += 32) sw[i] = 0;       // a private scalar block: the generator only uses its RNG
+        if (lane == 0) {
+            bind_env(e, reinterpret_cast<uint8_t *>(next_map + (size_t)env * NTILES));     // map() is the block's first field
+            e.s = reinterpret_cast<Scalars *>(sw);
+            e.anim = nullptr;
+            e.c.red = red;
+        }
+        __syncwarp();
+#if MP_WARP_COOP                                             // (the host pass of nvcc does not see the warp-cooperative generator)
+        generate_map_coop(e, gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 0));
+#endif
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int32_t *>(next_ep + env) = ep;
+        __syncwarp();
+    }
+}
+static_assert(EnvLayout::MAP == 0, "the prefetch kernel binds an Env whose block is just the map");
+
 // terrain_seeds == NULL with terrain != 0: the seeds of the env's next episode are derived here (gym_episode_seed)
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
                      const int32_t *terrain_seeds, const int32_t *sim_seeds, const uint8_t *mask, int terrain,
-                     long long run_seed, int env_offset)
+                     long long run_seed, int env_offset, const uint16_t *next_map, const int32_t *next_ep, unsigned int *pf_stats)
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
@@ -386,14 +447,16 @@ k_mp_env_reset_begin(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t 
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
     int ts = 0, ss = 0;
+    const uint16_t *prepared = nullptr;
     if (terrain && terrain_seeds) { ts = terrain_seeds[env]; ss = sim_seeds[env]; }
     else if (terrain) {
         const int ep = gy.g->episode;
         ts = gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 0);
         ss = gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 1);
+        prepared = prepared_terrain(next_map, next_ep, pf_stats, env, ep);
     }
     __syncwarp();
-    gym_reset_begin(e, gy, terrain, ts, ss);
+    gym_reset_begin(e, gy, terrain, ts, ss, prepared);
     if (lane == 0 && terrain && !terrain_seeds) gy.g->episode++;
     unstage_scalars(e, sw);
 }
@@ -411,7 +474,8 @@ __global__ void k_mp_env_auto_list(const uint8_t *done, const uint8_t *step_mask
 // reset, first half, for the envs of the list (a fixed grid walks it: the host does not know its length)
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_reset_list(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int stride, GymCfg cfg, const int *list,
-                    const int *count, int terrain, long long run_seed, int env_offset)
+                    const int *count, int terrain, long long run_seed, int env_offset, const uint16_t *next_map,
+                    const int32_t *next_ep, unsigned int *pf_stats)
 {
     __shared__ int red[8 * MP_EPC];
     MP_SHARED_ENV();
@@ -423,10 +487,12 @@ k_mp_env_reset_list(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int 
         Gym gy;
         bind_gym(gy, shadow + (size_t)env * stride, &cfg);
         const int ep = gy.g->episode;
+        const uint16_t *prepared = terrain ? prepared_terrain(next_map, next_ep, pf_stats, env, ep) : nullptr;
         __syncwarp();
         gym_reset_begin(e, gy, terrain,
                         terrain ? gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 0) : 0,
-                        terrain ? gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 1) : 0);
+                        terrain ? gym_episode_seed((uint64_t)run_seed, (uint64_t)(env_offset + env), (uint64_t)ep, 1) : 0,
+                        prepared);
         if (lane == 0 && terrain) gy.g->episode = ep + 1;
         unstage_scalars(e, sw);
         __syncwarp();
@@ -701,7 +767,8 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
     cudaMemsetAsync(b->rcount, 0, 4, st);
     k_mp_env_auto_list<<<(n + 255) / 256, 256, 0, st>>>(b->done, step_mask, n, b->rlist, b->rcount, b->amask);
     k_mp_env_reset_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->rlist,
-                                                               b->rcount, b->auto_terrain, b->run_seed, b->env_offset);
+                                                               b->rcount, b->auto_terrain, b->run_seed, b->env_offset,
+                                                               b->next_map, b->next_ep, b->pf_stats);
     const int P = b->passes;
     for (int t = 0; t < 2; t++)                               // MicropolisControl.simTick: simTick, animateTiles, simTick
         k_mp_frames<1><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist,
@@ -709,6 +776,12 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
     k_mp_env_post_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->obs_out,
                                                               b->reward, b->done, b->rlist, b->rcount);
     cudaEventRecord(b->ev_ar1, st);
+    if (b->next_map && b->auto_terrain) {                    // maps of the next episodes, in the gaps of the following steps
+        cudaEventRecord(b->ev_pf, st);
+        cudaStreamWaitEvent(b->pf_stream, b->ev_pf, 0);
+        k_mp_prefetch_terrain<<<grid, MP_THREADS, MP_DYN_SMEM, b->pf_stream>>>(b->shadow, b->shadow_stride, b->cfg, n, b->next_map,
+                                                                              b->next_ep, b->run_seed, b->env_offset);
+    }
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
 }
@@ -826,6 +899,9 @@ void mpb_destroy(mpb_handle h)
     cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
+    if (b->pf_stream) { cudaStreamSynchronize(b->pf_stream); cudaStreamDestroy(b->pf_stream); }
+    if (b->ev_pf) cudaEventDestroy(b->ev_pf);
+    cudaFree(b->next_map); cudaFree(b->next_ep); cudaFree(b->pf_stats);
     cudaFree(b->blocks); cudaFree(b->anim); cudaFree(b->i32_a); cudaFree(b->i32_b); cudaFree(b->mask);
     cudaFree(b->shadow); cudaFree(b->obs); cudaFree(b->reward); cudaFree(b->done); cudaFree(b->act_dev);
     if (b->host_blk) cudaFreeHost(b->host_blk);
@@ -1205,7 +1281,7 @@ int mpb_env_configure(mpb_handle h, int W, int H, int xs, int ys, int num_tools,
     b->configured = 1;
     // MicropolisControl.__init__ builds an empty TileMap (tilemap.py:185 setEmpty)
     k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                   NULL, NULL, NULL, 0, 0, 0);
+                                                   NULL, NULL, NULL, 0, 0, 0, NULL, NULL, NULL);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     return 0;
@@ -1236,6 +1312,10 @@ int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset)
 {
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
+    if (b->next_ep && (b->run_seed != seed || b->env_offset != env_offset)) {      // prepared maps belong to the old seeds
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemset(b->next_ep, 0xff, (size_t)b->n_envs * 4));
+    }
     b->run_seed = seed; b->env_offset = env_offset;
     return 0;
 }
@@ -1259,7 +1339,30 @@ int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain)
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
     b->auto_reset = enable ? 1 : 0; b->auto_terrain = terrain ? 1 : 0;
+    if (b->auto_reset && b->auto_terrain && !b->next_map && !getenv("MPB_NO_PREFETCH")) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);         // lo = the lowest priority
+        CK(cudaMalloc(&b->next_map, (size_t)b->n_envs * NTILES * sizeof(uint16_t)));
+        CK(cudaMalloc(&b->next_ep, (size_t)b->n_envs * 4));
+        CK(cudaMalloc(&b->pf_stats, 8));
+        CK(cudaMemset(b->next_ep, 0xff, (size_t)b->n_envs * 4));
+        CK(cudaMemset(b->pf_stats, 0, 8));
+        CK(cudaStreamCreateWithPriority(&b->pf_stream, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&b->ev_pf, cudaEventDisableTiming));
+    }
     return 0;
+}
+
+int mpb_env_prefetch_stats(mpb_handle h, unsigned int *served_out, unsigned int *inline_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    unsigned int v[2] = { 0, 0 };
+    CK(cudaDeviceSynchronize());
+    if (b->pf_stats) CK(cudaMemcpy(v, b->pf_stats, 8, cudaMemcpyDeviceToHost));
+    if (served_out) *served_out = v[0];
+    if (inline_out) *inline_out = v[1];
+    return b->next_map ? 1 : 0;
 }
 
 int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_host,
@@ -1279,7 +1382,7 @@ int mpb_env_reset_begin(mpb_handle h, int terrain, const int32_t *terrain_seeds_
     }
     k_mp_env_reset_begin<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
         b->cfg, host_seeds ? b->i32_a : NULL, host_seeds ? b->i32_b : NULL, mask_host ? b->mask : NULL, terrain,
-        b->run_seed, b->env_offset);
+        b->run_seed, b->env_offset, b->next_map, b->next_ep, b->pf_stats);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     return 0;

@@ -64,12 +64,21 @@ MPD void clear_map(Env &e)
     e.c.sync();
 }
 
-// [ALL] generate.cpp:92-110 generateSomeCity(seed), then seedRandom(sim_seed)
-MPD void generate_some_city(Env &e, int terrain_seed, int sim_seed)
+// [ALL] generate.cpp:92-110 generateSomeCity(seed), then seedRandom(sim_seed).  `prepared`: the map generateMap(seed)
+// produces, made ahead of time (terrain prefetch of the auto-reset, mp_batch.cu) -- copied instead of generated; the
+// generator's RNG state does not outlive this function (the simulation seed replaces it below).
+MPD void generate_some_city(Env &e, int terrain_seed, int sim_seed, const uint16_t *prepared = nullptr)
 {
 #if MP_WARP_COOP
-    generate_map_coop(e, terrain_seed);
+    if (prepared) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(prepared);
+        uint4 *dst = reinterpret_cast<uint4 *>(e.map());
+        for (int i = e.c.tid; i < NTILES * 2 / 16; i += e.c.n) dst[i] = src[i];
+    } else {
+        generate_map_coop(e, terrain_seed);
+    }
 #else
+    (void)prepared;
     if (e.c.lead()) generate_map(e, terrain_seed);
 #endif
     e.c.sync();

@@ -511,14 +511,14 @@ MPD void gym_step(Env &e, Gym &gy, long long action, bool static_build, float *o
 
 // [ALL] MicropolisEnv.reset, first half (env.py:264-274): clearMap (+ newMap) and num_step = 0.
 // terrain: 0 = empty_start (clearMap only), 1 = generateSomeCity(terrain_seed) + seedRandom(sim_seed).
-MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim_seed)
+MPD void gym_reset_begin(Env &e, Gym &gy, int terrain, int terrain_seed, int sim_seed, const uint16_t *prepared = nullptr)
 {
     MP_COV(gym_reset_begin);
     gym_set_empty(e, gy);
     clear_map(e);
     gym_update_map(e, gy);
     if (terrain) {
-        generate_some_city(e, terrain_seed, sim_seed);
+        generate_some_city(e, terrain_seed, sim_seed, prepared);
         gym_update_map(e, gy);
     }
     if (e.c.lead()) G.num_step = 0;

@@ -145,7 +145,7 @@ class MicropolisControl:
             "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
             "mpb_env_step_masked": (i32, [vp, vp, i32, vp, vp]),
             "mpb_env_set_seed": (i32, [vp, C.c_longlong, i32]), "mpb_env_set_auto_reset": (i32, [vp, i32, i32]),
-            "mpb_env_set_num_step": (i32, [vp, vp, vp]),
+            "mpb_env_set_num_step": (i32, [vp, vp, vp]), "mpb_env_prefetch_stats": (i32, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -182,6 +182,12 @@ class MicropolisControl:
         out = np.zeros((self.num_envs, 17), np.float64)
         self._ck(self._L.mpb_env_get_counters(self._h, out.ctypes.data))
         return out
+
+    def prefetch_stats(self):
+        """(active, resets served from a prepared terrain, resets that generated theirs in line)."""
+        a, b = C.c_uint(), C.c_uint()
+        on = self._ck(self._L.mpb_env_prefetch_stats(self._h, C.byref(a), C.byref(b)))
+        return bool(on), a.value, b.value
 
     def doSimTool(self, x, y, tool):                        # corecontrol.py:296-301
         return self.engine.toolDown(self.engineTools.index(tool), np.asarray(x) + self.MAP_XS,

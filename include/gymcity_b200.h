@@ -190,6 +190,11 @@ int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset);
  * running the reset's simTick for them and writing their reset observation.  Reward and done stay those of the
  * step that ended the episode.  No host round trip: the finished envs are a device-side list. */
 int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain);
+/* With auto-reset on the terrain path, the map of every env's NEXT episode is generated ahead of time by a
+ * low-priority kernel in the gaps of the following steps (the seeds are known as soon as the current episode starts),
+ * and a reset copies it instead of generating (ENG/generate.cpp:119-160 is 2.5 ms of one warp's time).  Returns 1 if
+ * the prefetch is active; served_out / inline_out: resets served from a prepared map / generated in line so far. */
+int mpb_env_prefetch_stats(mpb_handle h, unsigned int *served_out, unsigned int *inline_out);
 /* MicropolisEnv.num_step of every env (int32 [n_envs] HOST): episodes that end on different steps (in the reference
  * every worker counts its own steps, env.py:448-460; randomStaticStart gives each its own offset, env.py:228-241). */
 int mpb_env_set_num_step(mpb_handle h, const int32_t *num_step_host, void *stream);

@@ -318,6 +318,8 @@ def test_device_auto_reset_matches_reference_workers():
             assert np.array_equal(np.asarray(o, np.float32), obs[i]), (t, i)
     assert n_resets >= 20 and ended[0] != ended[1] and ended[1] == ended[4]   # staggered episodes, several resets each
     assert np.array_equal(env.micro.counters()[:, 16], episode)
+    on, served, inline = env.micro.prefetch_stats()                   # most resets copied a map generated ahead of time
+    assert on and served + inline == n_resets + 2 + n and served >= n_resets // 2, (served, inline, n_resets)
     for i, r in enumerate(refs):
         assert not diff_snapshots(r.micro.engine.snapshot(), env.micro.engine.snapshot(i))
     env.close()
