@@ -195,7 +195,9 @@ __host__ __device__ __forceinline__ int geom_slot(const GroupGeom &q, int w)
 #ifndef MP_FWARPS
 #define MP_FWARPS 32          // resident warps per SM the frame kernel is compiled for (register budget)
 #endif
-template <int MP_FEPC>
+// MP_PROF: the per-env per-frame cycle profile (mpb_frame_profile) is compiled into its own instantiation; the
+// product launches carry neither the store nor its test (1.1 % of the issued instructions, profiles/r02_notes.md).
+template <int MP_FEPC, bool MP_PROF>
 __global__ void __launch_bounds__(32 * MP_FEPC, MP_FWARPS / MP_FEPC)
 k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int count, int animate_before,
             int respect_passes, unsigned long long *cycles, unsigned int *cost, const int *perm, GroupGeom q,
@@ -249,7 +251,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
     // every frame simulates, so speedCycle and phaseCycle are plain counters (written back after the loop)
     int nrun = 0;
     bool fast = false;
-    int phase = 0, sc = 0;
+    int phase = 0, sc = 0, psc = 0;
     if (live) {
         nrun = count;
         if (respect_passes) nrun = e.s->simSpeed ? min(count, max(0, (int)e.s->simPasses - first)) : 0;
@@ -265,7 +267,16 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
                 sim_phase(e, phase);
                 phase = (phase + 1) & 15;
                 sc = (sc + 1) & 1023;                                  // simFrame: if (++speedCycle > 1023) speedCycle = 0
-                sim_sprites(e);
+                // moveObjects: with an empty sprite list it only counts spriteCycle, which nothing but the sprite
+                // handlers reads -- the count stays in a register until a sprite exists (or the launch ends)
+                if (lane == 0) {
+                    if (e.s->spriteHead < 0) psc++;
+                    else {
+                        if (psc) { e.s->spriteCycle = (int16_t)(e.s->spriteCycle + psc); psc = 0; }
+                        move_objects(e);
+                    }
+                }
+                __syncwarp();
             } else {
                 const int ran = sim_loop_head(e);
                 sim_loop_tail(e, ran);
@@ -273,7 +284,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         }
         const unsigned int dt = (unsigned int)clock64() - t0;          // this env's own time, barrier waits excluded
         busy += dt;
-        if (prof && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
+        if (MP_PROF && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
         if (MP_FEPC > 1) {
             const int ph = (ph0 + i) & 15;
             if (!(scan_block && ph >= 1 && ph <= 7)) __syncthreads();
@@ -283,6 +294,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         if (fast && lane == 0 && nrun > 0) {
             e.s->phaseCycle = (int16_t)phase;
             e.s->speedCycle = (int16_t)sc;
+            e.s->spriteCycle = (int16_t)(e.s->spriteCycle + psc);
         }
         unstage_scalars(e, sw);
         if (lane == 0) {
@@ -690,10 +702,13 @@ void launch_frames(MpBatch *b, int epc, cudaStream_t st, int first, int count, i
     if (gcount <= 0) return;
 #define MP_FRAMES_ARGS b->blocks, b->anim, b->n_envs, first, count, animate_before, respect_passes, b->cycles, b->cost, perm, \
                        q, b->scan_block, b->prof, prof_off, mask, (const int *)NULL
-        if (epc >= 32) k_mp_frames<32><<<(gcount + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-        else if (epc >= 16) k_mp_frames<16><<<(gcount + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-        else if (epc >= 8) k_mp_frames<8><<<(gcount + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
-        else k_mp_frames<1><<<gcount, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS);
+#define MP_FRAMES_LAUNCH(PROF) do { \
+        if (epc >= 32) k_mp_frames<32, PROF><<<(gcount + 31) / 32, 1024, 32 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS); \
+        else if (epc >= 16) k_mp_frames<16, PROF><<<(gcount + 15) / 16, 512, 16 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS); \
+        else if (epc >= 8) k_mp_frames<8, PROF><<<(gcount + 7) / 8, 256, 8 * SCAL_BYTES, st>>>(MP_FRAMES_ARGS); \
+        else k_mp_frames<1, PROF><<<gcount, 32, SCAL_BYTES, st>>>(MP_FRAMES_ARGS); } while (0)
+    if (b->prof) MP_FRAMES_LAUNCH(true); else MP_FRAMES_LAUNCH(false);
+#undef MP_FRAMES_LAUNCH
 #undef MP_FRAMES_ARGS
     const cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = le;
@@ -771,7 +786,7 @@ void launch_auto_reset(MpBatch *b, const uint8_t *step_mask, cudaStream_t st)
                                                                b->next_map, b->next_ep, b->pf_stats);
     const int P = b->passes;
     for (int t = 0; t < 2; t++)                               // MicropolisControl.simTick: simTick, animateTiles, simTick
-        k_mp_frames<1><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist,
+        k_mp_frames<1, false><<<grid, 32, SCAL_BYTES, st>>>(b->blocks, b->anim, n, 0, P > 0 ? P : 0, t, 1, b->cycles, b->cost, b->rlist,
                                                     GroupGeom{0, 1, 0, 1}, b->scan_block, NULL, 0, NULL, b->rcount);
     k_mp_env_post_list<<<grid, MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->shadow, b->shadow_stride, b->cfg, b->obs_out,
                                                               b->reward, b->done, b->rlist, b->rcount);
@@ -838,8 +853,8 @@ mpb_handle mpb_create(int n_envs, int device)
     if (const char *fp = getenv("MPB_FEPC")) b->fepc = atoi(fp);
     if (const char *fp = getenv("MPB_HEAVY_FEPC")) b->heavy_fepc = atoi(fp);
     if (const char *fp = getenv("MPB_CARVEOUT")) {           // experiment: shared-memory share of the L1 (percent)
-        cudaFuncSetAttribute(k_mp_frames<16>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
-        cudaFuncSetAttribute(k_mp_frames<8>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
+        cudaFuncSetAttribute(k_mp_frames<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
+        cudaFuncSetAttribute(k_mp_frames<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
     }
     b->scan_block = 1;
     if (const char *fp = getenv("MPB_SCAN_BLOCK")) b->scan_block = atoi(fp) != 0;

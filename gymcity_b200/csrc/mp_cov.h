@@ -17,23 +17,23 @@
     X(zero_byte2) X(smooth_byte2_box) X(box_add) X(box_reduce) X(smooth_station) X(city_center_distance) \
     X(pollution_value) X(coop_add) X(tie_max_scan) X(ptlv_scan) X(crime_scan) X(population_density_of) \
     X(pop_density_scan) X(com_rate_map) X(fire_analysis) X(city_evaluation) X(coop_bcast) X(scan_due) \
-    X(simulate_phase) X(simulate) X(sim_phase) X(sim_sprites) X(sim_loop_head) X(sim_loop_tail) \
-    X(sim_loop) X(do_sim_init) X(animate_tiles) X(get_sprite) X(init_sprite) X(new_sprite) \
-    X(destroy_sprite) X(make_sprite) X(make_explosion) X(boat_distance) X(get_char) X(turn_to) \
-    X(try_other) X(sprite_not_in_bounds) X(get_dir) X(sprite_collision) X(explode_sprite) X(start_fire_in_zone) \
-    X(destroy_map_tile) X(start_fire) X(do_train) X(do_copter) X(do_airplane) X(do_ship) \
-    X(hit_vehicles) X(do_monster) X(do_tornado) X(do_explosion) X(move_objects) X(generate_train) \
-    X(generate_ship) X(generate_copter) X(generate_plane) X(make_monster) X(make_tornado) X(vulnerable) \
-    X(make_earthquake) X(make_earthquake_coop) X(set_fire) X(make_flood) X(do_disasters) X(tally) \
-    X(fix_single) X(fix_candidate) X(fix_zone) X(lay_doze) X(lay_road) X(lay_rail) \
-    X(lay_wire) X(connect_tile) X(check_big_zone) X(check_size) X(put_rubble) X(bulldozer_tool) \
-    X(build_building) X(smooth_trees_at_fx) X(tool_down) X(put_on_map) X(plop_b_river) X(plop_s_river) \
-    X(do_river) X(smooth_river) X(smooth_trees) X(do_trees) X(make_naked_island) X(generate_map) \
-    X(gen_put) X(gen_plop_b) X(gen_plop_s) X(gen_river) X(gen_redge_value) X(gen_smooth_river) \
-    X(gen_smooth_trees) X(gen_trees) X(generate_map_coop) X(gym_zone_of_tile) X(gym_update_tile) X(gym_clear_tile) \
-    X(gym_clear_patch) X(gym_add_zone) X(gym_add_zone_bot) X(gym_apply_action) X(gym_paint_action) X(gym_init_age_array) \
-    X(gym_extinguish) X(gym_set_empty) X(gym_update_map) X(gym_city_metrics) X(gym_reward) X(gym_observe) \
-    X(gym_step_pre) X(gym_step_post) X(gym_step) X(gym_reset_begin) X(gym_reset_post) X(gym_reset_finish)
+    X(simulate_phase) X(simulate) X(sim_phase) X(sim_loop_head) X(sim_loop_tail) X(sim_loop) \
+    X(do_sim_init) X(animate_tiles) X(get_sprite) X(init_sprite) X(new_sprite) X(destroy_sprite) \
+    X(make_sprite) X(make_explosion) X(boat_distance) X(get_char) X(turn_to) X(try_other) \
+    X(sprite_not_in_bounds) X(get_dir) X(sprite_collision) X(explode_sprite) X(start_fire_in_zone) X(destroy_map_tile) \
+    X(start_fire) X(do_train) X(do_copter) X(do_airplane) X(do_ship) X(hit_vehicles) \
+    X(do_monster) X(do_tornado) X(do_explosion) X(move_objects) X(generate_train) X(generate_ship) \
+    X(generate_copter) X(generate_plane) X(make_monster) X(make_tornado) X(vulnerable) X(make_earthquake) \
+    X(make_earthquake_coop) X(set_fire) X(make_flood) X(do_disasters) X(tally) X(fix_single) \
+    X(fix_candidate) X(fix_zone) X(lay_doze) X(lay_road) X(lay_rail) X(lay_wire) \
+    X(connect_tile) X(check_big_zone) X(check_size) X(put_rubble) X(bulldozer_tool) X(build_building) \
+    X(smooth_trees_at_fx) X(tool_down) X(put_on_map) X(plop_b_river) X(plop_s_river) X(do_river) \
+    X(smooth_river) X(smooth_trees) X(do_trees) X(make_naked_island) X(generate_map) X(gen_put) \
+    X(gen_plop_b) X(gen_plop_s) X(gen_river) X(gen_redge_value) X(gen_smooth_river) X(gen_smooth_trees) \
+    X(gen_trees) X(generate_map_coop) X(gym_zone_of_tile) X(gym_update_tile) X(gym_clear_tile) X(gym_clear_patch) \
+    X(gym_add_zone) X(gym_add_zone_bot) X(gym_apply_action) X(gym_paint_action) X(gym_init_age_array) X(gym_extinguish) \
+    X(gym_set_empty) X(gym_update_map) X(gym_city_metrics) X(gym_reward) X(gym_observe) X(gym_step_pre) \
+    X(gym_step_post) X(gym_step) X(gym_reset_begin) X(gym_reset_post) X(gym_reset_finish)
 
 namespace mp {
 #define MP_COV_ENUM(n) COV_##n,

@@ -1880,11 +1880,24 @@ MPN void ptlv_scan(Env &e)
     // tempMap3: +15 per natural tile (0 < tile < RUBBLE) in each 4x4 block (Byte wrap)
     for (int i = e.c.tid; i < N4; i += e.c.n) {
         int bx = (i / H4) * 4, by = (i % H4) * 4, cnt = 0;
+#if defined(__CUDA_ARCH__)
+        // the four tiles of a block column are 8 aligned bytes (by is a multiple of 4, a map column is 200 bytes):
+        // one 64-bit load per column, 1 <= id <= RUBBLE - 1 tested per halfword (this loop was the hottest line of
+        // the kernel outside the barrier: 12 000 scalar tile loads per scan, profiles/r02_notes.md)
+#pragma unroll
+        for (int dx = 0; dx < 4; dx++) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(e.map() + tix(bx + dx, by));
+            const unsigned a = v.x & 0x03ff03ffu, b = v.y & 0x03ff03ffu;
+            cnt += (int)(((a & 0xffffu) - 1u) < (unsigned)(T_RUBBLE - 1)) + (int)(((a >> 16) - 1u) < (unsigned)(T_RUBBLE - 1))
+                 + (int)(((b & 0xffffu) - 1u) < (unsigned)(T_RUBBLE - 1)) + (int)(((b >> 16) - 1u) < (unsigned)(T_RUBBLE - 1));
+        }
+#else
         MP_NOUNROLL for (int dx = 0; dx < 4; dx++)
             MP_NOUNROLL for (int dy = 0; dy < 4; dy++) {
                 int loc = e.map()[tix(bx + dx, by + dy)] & LOMASK;
                 if (loc && loc < T_RUBBLE) cnt++;
             }
+#endif
         e.tmp3()[i] = (uint8_t)(cnt * 15);
     }
     e.c.sync();
@@ -2267,8 +2280,8 @@ MPD bool scan_due(int cyc, int si, int slow, int mid, int fast)
 MPD void simulate_phase(Env &e, int phase)
 {
     MP_COV(simulate_phase);
-    const int si = tclamp((int)S.simSpeed - 1, 0, 2);
-    const int cyc = S.simCycle;
+    // (speed index and cycle count are read by the phases that use them: phases 1..9 pay nothing for them)
+#define MP_SI tclamp((int)S.simSpeed - 1, 0, 2)
     switch (phase) {
     case 0:
         if (e.c.lead()) {
@@ -2298,21 +2311,21 @@ MPD void simulate_phase(Env &e, int phase)
         break;
     }
     case 10:
-        if (!(cyc % 5)) dec_rog_map(e);
+        if (!(S.simCycle % 5)) dec_rog_map(e);
         dec_traffic_map(e);
         if (e.c.lead()) send_messages(e);
         break;
     case 11:
-        if (scan_due(cyc, si, 2, 4, 5)) do_power_scan(e);          // sets newPower (see do_power_scan)
+        if (scan_due(S.simCycle, MP_SI, 2, 4, 5)) do_power_scan(e);          // sets newPower (see do_power_scan)
         break;
     case 12:
-        if (scan_due(cyc, si, 2, 7, 17)) ptlv_scan(e);
+        if (scan_due(S.simCycle, MP_SI, 2, 7, 17)) ptlv_scan(e);
         break;
     case 13:
-        if (scan_due(cyc, si, 1, 8, 18)) crime_scan(e);
+        if (scan_due(S.simCycle, MP_SI, 1, 8, 18)) crime_scan(e);
         break;
     case 14:
-        if (scan_due(cyc, si, 1, 9, 19)) {
+        if (scan_due(S.simCycle, MP_SI, 1, 9, 19)) {
             int cx = S.cityCenterX, cy = S.cityCenterY;
             e.c.sync();
             pop_density_scan(e);
@@ -2320,7 +2333,7 @@ MPD void simulate_phase(Env &e, int phase)
         }
         break;
     case 15:
-        if (scan_due(cyc, si, 1, 10, 20)) fire_analysis(e);
+        if (scan_due(S.simCycle, MP_SI, 1, 10, 20)) fire_analysis(e);
         {   // an earthquake (300-1000 random tile probes) is handed to all lanes instead of the serial lane
             int quake = 0;
             if (e.c.lead()) quake = do_disasters(e, true);
@@ -2328,6 +2341,7 @@ MPD void simulate_phase(Env &e, int phase)
         }
         break;
     }
+#undef MP_SI
 }
 
 // [ALL] simulate.cpp:122-268 simulate
@@ -2353,16 +2367,6 @@ MPN void sim_phase(Env &e, int phase)
 {
     MP_COV(sim_phase);
     simulate_phase(e, phase);
-    e.c.sync();
-}
-// [LEAD-guarded inside] the sprite pass of a frame (moveObjects; an empty list only counts the cycle)
-MPD void sim_sprites(Env &e)
-{
-    MP_COV(sim_sprites);
-    if (e.c.lead()) {
-        if (S.spriteHead < 0) { if (S.simSpeed) S.spriteCycle++; }
-        else move_objects(e);
-    }
     e.c.sync();
 }
 MPN int sim_loop_head(Env &e)
