@@ -50,6 +50,9 @@ struct MpBatch {
     int *perm;                // [n_envs] env ids, most expensive first
     unsigned long long *cls_sum;   // [SCHED_CLASSES] summed cost of the envs of a schedule class
     unsigned int *cls_cnt;    // [SCHED_CLASSES] how many
+    int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
+    int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
+    int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
     unsigned int *skey, *skey_out;    // [n_envs] sort keys of the schedule
     int *sval;                // [n_envs] env ids (sort values in)
     void *sort_tmp; size_t sort_tmp_bytes;
@@ -361,13 +364,13 @@ __global__ void k_mp_sched_identity(int *perm, int n)
     if (i < n) perm[i] = i;
 }
 __global__ void k_mp_sched_class(const unsigned int *cost, const uint8_t *blocks, int n, unsigned long long *cls_sum,
-                                 unsigned int *cls_cnt)
+                                 unsigned int *cls_cnt, int *ncls)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int c = env_sched_class(blocks, i);
     atomicAdd(&cls_sum[c], (unsigned long long)cost[i]);
-    atomicAdd(&cls_cnt[c], 1u);
+    if (atomicAdd(&cls_cnt[c], 1u) == 0u) atomicAdd(ncls, 1);
 }
 // key = [mean cost of the class, inverted: 10 bits][class: 12 bits][own cost, inverted: 10 bits]; cost = cycles >> 8 of
 // the previous step, bucketed by 2^5 (2^13 busy cycles per bucket; the mean env is at ~300)
@@ -681,7 +684,11 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
     const int n = b->n_envs;
     cudaMemsetAsync(b->cls_sum, 0, SCHED_CLASSES * sizeof(unsigned long long), st);
     cudaMemsetAsync(b->cls_cnt, 0, SCHED_CLASSES * sizeof(unsigned int), st);
-    k_mp_sched_class<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt);
+    cudaMemsetAsync(b->ncls_dev, 0, sizeof(int), st);
+    k_mp_sched_class<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt, b->ncls_dev);
+    // how many classes the batch has, for the host's choice of the group geometry of a LATER step (no sync: the
+    // pinned word is read whenever it happens to have arrived)
+    cudaMemcpyAsync(b->ncls_host, b->ncls_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
     k_mp_sched_keys<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt, b->skey, b->sval);
     size_t bytes = b->sort_tmp_bytes;
     const cudaError_t e = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm, n, 0, 32, st);
@@ -737,8 +744,10 @@ GroupGeom group_geom(const MpBatch *b, int G, int g)
     return q;
 }
 #define MP_GRID_N(count) (((count) + MP_EPC - 1) / MP_EPC)
-// env groups of an env-step: the launch tails of b->groups groups overlap on their own streams
-int step_groups(const MpBatch *b) { return b->groups; }
+// env groups of an env-step (their launch tails overlap on their own streams) and frames per launch: see mpb_create
+bool single_class_big(const MpBatch *b) { return b->fepc >= 32 && *reinterpret_cast<volatile int *>(b->ncls_host) <= 1; }
+int step_groups(const MpBatch *b) { return single_class_big(b) ? b->big_groups : b->groups; }
+int step_frames(const MpBatch *b) { return single_class_big(b) ? b->big_frames : b->frames_per_launch; }
 
 int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8_t *mask, int G = 1, int g = 0)
 {
@@ -748,7 +757,7 @@ int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8
     // the heavy group is not kept in phase lockstep: with few, very uneven envs every launch would
     // wait for ITS slowest member (a different env each time), so it runs a whole simTick per launch
     const bool heavy_group = (G > 1 && g == 0 && q.stride == 1 && q.chunk == 1);
-    const int F = heavy_group ? (P > 0 ? P : 1) : b->frames_per_launch;
+    const int F = heavy_group ? (P > 0 ? P : 1) : (b->cur_frames > 0 ? b->cur_frames : b->frames_per_launch);
     const int epc = heavy_group ? b->heavy_fepc : b->fepc;
     if (q.count <= 0) return 0;
     if (P <= 0) {
@@ -871,6 +880,8 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->cls_sum, SCHED_CLASSES * sizeof(unsigned long long)) == cudaSuccess
         && cudaMalloc(&b->cls_cnt, SCHED_CLASSES * sizeof(unsigned int)) == cudaSuccess
+        && cudaMalloc(&b->ncls_dev, sizeof(int)) == cudaSuccess
+        && cudaMallocHost(&b->ncls_host, sizeof(int)) == cudaSuccess
         && cudaMalloc(&b->skey, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->skey_out, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->sval, (size_t)n_envs * 4) == cudaSuccess
@@ -889,8 +900,16 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
     b->use_sched = 1;
+    // Env groups on streams (the heavy 1/64 + two more, 50 frames per launch) pay off while a launch has only a few
+    // waves of CTAs, or CTAs of very different length: small batches (2 048 envs +4 %, 8 192 envs +2 %) and batches
+    // whose envs are in many schedule classes (staggered episodes: 23.8 ms per step against 27.4).  A single-class
+    // batch that gives every SM several 32-env CTAs per launch runs as ONE group with a whole simTick per launch
+    // (32 768 envs: 1.76 M env-ticks/s against 1.70 M).  step_groups() / step_frames() choose per step.
     b->groups = 3;
-    if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) b->groups = v; }
+    b->big_groups = 1; b->big_frames = 100;
+    *b->ncls_host = 1;
+    if (getenv("MPB_FRAMES_PER_LAUNCH")) b->big_frames = b->frames_per_launch;
+    if (const char *gg = getenv("MPB_GROUPS")) { int v = atoi(gg); if (v >= 1 && v <= 8) { b->groups = v; b->big_groups = v; } }
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
     cudaEventCreate(&b->ev_start);
     cudaEventCreate(&b->ev_ar0); cudaEventCreate(&b->ev_ar1);
@@ -911,7 +930,8 @@ void mpb_destroy(mpb_handle h)
     if (b->ev_ar0) cudaEventDestroy(b->ev_ar0);
     if (b->ev_ar1) cudaEventDestroy(b->ev_ar1);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->cls_sum); cudaFree(b->cls_cnt);
-    cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp);
+    cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp); cudaFree(b->ncls_dev);
+    if (b->ncls_host) cudaFreeHost(b->ncls_host);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
     if (b->pf_stream) { cudaStreamSynchronize(b->pf_stream); cudaStreamDestroy(b->pf_stream); }
@@ -948,7 +968,7 @@ int mpb_launches_per_env_step(mpb_handle h)
     for (int g = 0; g < G; g++) {
         const GroupGeom q = group_geom(b, G, g);
         if (q.count <= 0) continue;
-        const int F = (G > 1 && g == 0 && q.stride == 1 && q.chunk == 1) ? (b->passes > 0 ? b->passes : 1) : b->frames_per_launch;
+        const int F = (G > 1 && g == 0 && q.stride == 1 && q.chunk == 1) ? (b->passes > 0 ? b->passes : 1) : step_frames(b);
         const int per = b->passes > 0 ? (b->passes + F - 1) / F : 1;
         total += 2 + 2 * per;
     }
@@ -1549,7 +1569,9 @@ int mpb_env_step_paint(mpb_handle h, const uint8_t *tools_dev, void *stream)
 static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *paint_dev, int static_build,
                          const uint8_t *mask_dev, cudaStream_t st)
 {
-    const int G = step_groups(b);
+    const bool big = single_class_big(b);
+    const int G = big ? b->big_groups : b->groups;
+    b->cur_frames = big ? b->big_frames : b->frames_per_launch;
     const int *perm = b->use_sched ? b->perm : NULL;
     // the order of this step: by the phase each env is in NOW (resets between steps move envs to another phase
     // class) and by what the previous step cost it
@@ -1575,6 +1597,7 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             cudaStreamWaitEvent(st, b->ev_done[g], 0);
         }
     }
+    b->cur_frames = 0;
     if (b->auto_reset) launch_auto_reset(b, mask_dev, st);
     CK_LAUNCHES();
     return 0;
