@@ -50,6 +50,7 @@ struct MpBatch {
     int *perm;                // [n_envs] env ids, most expensive first
     unsigned long long *cls_sum;   // [SCHED_CLASSES] summed cost of the envs of a schedule class
     unsigned int *cls_cnt;    // [SCHED_CLASSES] how many
+    int *perm_pre;            // [n_envs] env ids ordered by the tool of this step's action (k_mp_env_pre of a one-group step)
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
@@ -173,6 +174,18 @@ k_mp_tool(uint8_t *blocks, const uint16_t *anim, int n_envs, const int32_t *txy,
         if (results) results[env] = r;
     }
     unstage_scalars(e, sw);
+}
+
+// k_mp_env_pre is one warp per env running the clear-then-build logic of ITS action: 14 k instructions of tool code,
+// a different tool in every warp, and 55-60 % of its stall samples are no_instruction (profiles/r02_notes.md).  In
+// tool order neighbouring CTAs -- the ones an SM holds at the same time -- run the same tool.
+__global__ void k_mp_pre_keys(const int64_t *actions, int n, int cells, unsigned int *keys, int *vals)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long a = actions[i];
+    keys[i] = a < 0 ? 31u : (unsigned int)min((long long)30, a / cells);
+    vals[i] = i;
 }
 
 // A group of envs = the slots { off + (w / chunk) * chunk * stride + w % chunk : w < count } of the schedule:
@@ -880,6 +893,7 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->perm, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->cls_sum, SCHED_CLASSES * sizeof(unsigned long long)) == cudaSuccess
         && cudaMalloc(&b->cls_cnt, SCHED_CLASSES * sizeof(unsigned int)) == cudaSuccess
+        && cudaMalloc(&b->perm_pre, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->ncls_dev, sizeof(int)) == cudaSuccess
         && cudaMallocHost(&b->ncls_host, sizeof(int)) == cudaSuccess
         && cudaMalloc(&b->skey, (size_t)n_envs * 4) == cudaSuccess
@@ -930,7 +944,7 @@ void mpb_destroy(mpb_handle h)
     if (b->ev_ar0) cudaEventDestroy(b->ev_ar0);
     if (b->ev_ar1) cudaEventDestroy(b->ev_ar1);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->cls_sum); cudaFree(b->cls_cnt);
-    cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp); cudaFree(b->ncls_dev);
+    cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp); cudaFree(b->ncls_dev); cudaFree(b->perm_pre);
     if (b->ncls_host) cudaFreeHost(b->ncls_host);
     cudaFree(b->prof); cudaFree(b->xt_rnd); cudaFree(b->counters_dev);
     cudaFree(b->rlist); cudaFree(b->rcount); cudaFree(b->amask);
@@ -963,8 +977,9 @@ int mpb_launches_per_env_step(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     int total = b->use_sched ? 2 : 0;                       // the two scheduling kernels of this library (the sort is CUB's)
-    if (b->auto_reset) total += 6;                          // list, reset, 2 x frames, post (+ a memset node)
+    if (b->auto_reset) total += 5 + (b->next_map ? 1 : 0);  // list, reset, 2 x frames, post, terrain prefetch
     const int G = step_groups(b);
+    if (G == 1 && b->use_sched) total += 1;                 // k_mp_pre_keys (the action kernel runs in tool order)
     for (int g = 0; g < G; g++) {
         const GroupGeom q = group_geom(b, G, g);
         if (q.count <= 0) continue;
@@ -1586,7 +1601,16 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         if (paint_dev)
             k_mp_env_pre_paint<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
                                                            b->cfg, paint_dev, perm, q);
-        else
+        else if (G == 1 && b->use_sched && !getenv("MPB_NO_PRE_SORT")) {
+            // one group: the action kernel takes the envs in tool order (its own permutation; the frames keep theirs)
+            const int n = b->n_envs;
+            k_mp_pre_keys<<<(n + 255) / 256, 256, 0, gs>>>(actions_dev, n, b->cfg.W * b->cfg.H, b->skey, b->sval);
+            size_t bytes = b->sort_tmp_bytes;
+            const cudaError_t se = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm_pre, n, 0, 5, gs);
+            if (se != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = se;
+            k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                     actions_dev, static_build, b->perm_pre, q, mask_dev);
+        } else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);
         launch_control_sim_tick(b, gs, mask_dev, G, g);

@@ -33,7 +33,8 @@ def main(src_csv, dis_txt, kern, col='# Samples', top=40):
         if r and r[0] == 'Kernel Name':
             want = kern.replace('ILi', '<').split('<')[0].split('EE')[0] in r[1]
             if 'ILi' in kern:
-                want = want and ('<%s>' % kern.split('ILi')[1].split('E')[0]) in r[1] or ('<(int)%s>' % kern.split('ILi')[1].split('E')[0]) in r[1]
+                n = kern.split('ILi')[1].split('E')[0]
+                want = want and any(t in r[1] for t in ('<%s>' % n, '<%s,' % n, '<(int)%s>' % n, '<(int)%s,' % n))
             continue
         if r and r[0] == 'Address':
             h = r
