@@ -54,7 +54,7 @@ struct MpBatch {
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
-    unsigned int *skey, *skey_out;    // [n_envs] sort keys of the schedule
+    unsigned long long *skey, *skey_out;    // [n_envs] sort keys of the schedule (36 bits used; the tool-order sort of k_mp_env_pre reuses the storage as 32-bit keys)
     int *sval;                // [n_envs] env ids (sort values in)
     void *sort_tmp; size_t sort_tmp_bytes;
     int use_sched;
@@ -364,6 +364,11 @@ __global__ void k_mp_set_scalar(uint8_t *blocks, int n, int which, const int32_t
 // together: the plain rollout) this is the heavy-first order by cost alone.
 constexpr int SCHED_CLASS_BITS = 12;
 constexpr int SCHED_CLASSES = 1 << SCHED_CLASS_BITS;
+__device__ __forceinline__ int env_phase(const uint8_t *blocks, int env)
+{
+    const Scalars *sc = reinterpret_cast<const Scalars *>(blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
+    return sc->initSimLoad ? 0 : (sc->phaseCycle & 15);
+}
 __device__ __forceinline__ unsigned int env_sched_class(const uint8_t *blocks, int env)
 {
     const Scalars *sc = reinterpret_cast<const Scalars *>(blocks + (size_t)env * ENV_STRIDE + EnvLayout::SCALARS);
@@ -385,17 +390,21 @@ __global__ void k_mp_sched_class(const unsigned int *cost, const uint8_t *blocks
     atomicAdd(&cls_sum[c], (unsigned long long)cost[i]);
     if (atomicAdd(&cls_cnt[c], 1u) == 0u) atomicAdd(ncls, 1);
 }
-// key = [mean cost of the class, inverted: 10 bits][class: 12 bits][own cost, inverted: 10 bits]; cost = cycles >> 8 of
-// the previous step, bucketed by 2^5 (2^13 busy cycles per bucket; the mean env is at ~300)
+// key = [phase: 4 bits][mean cost of the class, inverted: 10 bits][class: 12 bits][own cost, inverted: 10 bits]; cost =
+// cycles >> 8 of the previous step, bucketed by 2^5 (2^13 busy cycles per bucket; the mean env is at ~300).  The phase
+// comes first so that the classes that meet in a CTA at a class boundary (a 164-env class is 5.1 CTAs) are at least in
+// the same phase: such a CTA then pays the periodic scans of two calendars, not the maximum of two different phases
+// in every frame.
 __global__ void k_mp_sched_keys(unsigned int *cost, const uint8_t *blocks, int n, const unsigned long long *cls_sum,
-                                const unsigned int *cls_cnt, unsigned int *keys, int *vals)
+                                const unsigned int *cls_cnt, unsigned long long *keys, int *vals)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int c = env_sched_class(blocks, i);
     const unsigned int mean = (unsigned int)(cls_sum[c] / (unsigned long long)max(1u, cls_cnt[c]));
     const unsigned int q = min(1023u, mean >> 5), own = min(1023u, cost[i] >> 5);
-    keys[i] = ((1023u - q) << 22) | (c << 10) | (1023u - own);
+    const unsigned int lo = ((1023u - q) << 22) | (c << 10) | (1023u - own);
+    keys[i] = ((unsigned long long)env_phase(blocks, i) << 32) | lo;
     vals[i] = i;
     cost[i] = 0;
 }
@@ -704,7 +713,7 @@ int rebuild_schedule(MpBatch *b, cudaStream_t st)
     cudaMemcpyAsync(b->ncls_host, b->ncls_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
     k_mp_sched_keys<<<(n + 255) / 256, 256, 0, st>>>(b->cost, b->blocks, n, b->cls_sum, b->cls_cnt, b->skey, b->sval);
     size_t bytes = b->sort_tmp_bytes;
-    const cudaError_t e = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm, n, 0, 32, st);
+    const cudaError_t e = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm, n, 0, 36, st);
     if (e != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = e;
     return 0;
 }
@@ -896,8 +905,8 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->perm_pre, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->ncls_dev, sizeof(int)) == cudaSuccess
         && cudaMallocHost(&b->ncls_host, sizeof(int)) == cudaSuccess
-        && cudaMalloc(&b->skey, (size_t)n_envs * 4) == cudaSuccess
-        && cudaMalloc(&b->skey_out, (size_t)n_envs * 4) == cudaSuccess
+        && cudaMalloc(&b->skey, (size_t)n_envs * 8) == cudaSuccess
+        && cudaMalloc(&b->skey_out, (size_t)n_envs * 8) == cudaSuccess
         && cudaMalloc(&b->sval, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->rlist, (size_t)n_envs * 4) == cudaSuccess
         && cudaMalloc(&b->rcount, 4) == cudaSuccess
@@ -906,7 +915,7 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMallocHost(&b->host_i32, (size_t)n_envs * 16) == cudaSuccess;
     if (ok) {
         b->sort_tmp_bytes = 0;
-        ok = cub::DeviceRadixSort::SortPairs(NULL, b->sort_tmp_bytes, b->skey, b->skey_out, b->sval, b->perm, n_envs, 0, 32) == cudaSuccess
+        ok = cub::DeviceRadixSort::SortPairs(NULL, b->sort_tmp_bytes, b->skey, b->skey_out, b->sval, b->perm, n_envs, 0, 36) == cudaSuccess
             && cudaMalloc(&b->sort_tmp, b->sort_tmp_bytes ? b->sort_tmp_bytes : 16) == cudaSuccess;
     }
     if (!ok) { mpb_destroy(b); return NULL; }
@@ -1604,9 +1613,10 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         else if (G == 1 && b->use_sched && !getenv("MPB_NO_PRE_SORT")) {
             // one group: the action kernel takes the envs in tool order (its own permutation; the frames keep theirs)
             const int n = b->n_envs;
-            k_mp_pre_keys<<<(n + 255) / 256, 256, 0, gs>>>(actions_dev, n, b->cfg.W * b->cfg.H, b->skey, b->sval);
+            unsigned int *k32 = reinterpret_cast<unsigned int *>(b->skey), *k32o = reinterpret_cast<unsigned int *>(b->skey_out);
+            k_mp_pre_keys<<<(n + 255) / 256, 256, 0, gs>>>(actions_dev, n, b->cfg.W * b->cfg.H, k32, b->sval);
             size_t bytes = b->sort_tmp_bytes;
-            const cudaError_t se = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, b->skey, b->skey_out, b->sval, b->perm_pre, n, 0, 5, gs);
+            const cudaError_t se = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, k32, k32o, b->sval, b->perm_pre, n, 0, 5, gs);
             if (se != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = se;
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, b->perm_pre, q, mask_dev);
