@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("MPB_NVCC_EXTRA", "").split()      # e.g. -DMP_PROFILE_SPLIT for profiling builds
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".h", ".cuh"))]    # sources, not objects
     inc = os.path.join(HERE, "..", "include")
     deps += [os.path.join(inc, f) for f in os.listdir(inc)]
     if not force and not _newer(LIB, deps):

@@ -1,6 +1,7 @@
 // dlpack_export.cu -- hands borrowed device buffers to the consumer as DLPack tensors
 // (DLPack ABI v0.8 layout: DLManagedTensor).  The handle that owns the memory outlives the
-// tensor by contract (include/gymcity_b200.h), so the deleter only frees the descriptor.
+// tensor by contract (include/gymcity_b200.h), so the deleter only frees the descriptor -- or, with
+// gcb_dlpack_wrap_owned, first tells the owner that this view is gone, so that the owner can keep the memory until then.
 #include <stdint.h>
 #include <stdlib.h>
 #include "../../include/gymcity_b200.h"
@@ -15,8 +16,13 @@ struct DLTensor {
 struct DLManagedTensor {
     DLTensor dl_tensor; void *manager_ctx; void (*deleter)(DLManagedTensor *);
 };
-struct Owned { DLManagedTensor t; int64_t shape[8]; };
-void drop(DLManagedTensor *t) { free(t->manager_ctx); }
+struct Owned { DLManagedTensor t; int64_t shape[8]; void (*release)(void *); void *release_ctx; };
+void drop(DLManagedTensor *t)
+{
+    Owned *o = (Owned *)t->manager_ctx;
+    if (o->release) o->release(o->release_ctx);
+    free(o);
+}
 }
 
 extern "C" void *gcb_dlpack_wrap(void *dev_ptr, int dtype_code, int bits, int ndim,
@@ -37,4 +43,15 @@ extern "C" void *gcb_dlpack_wrap(void *dev_ptr, int dtype_code, int bits, int nd
     o->t.manager_ctx = o;
     o->t.deleter = drop;
     return &o->t;
+}
+
+extern "C" void *gcb_dlpack_wrap_owned(void *dev_ptr, int dtype_code, int bits, int ndim, const int64_t *shape, int device,
+                                       void (*release)(void *), void *release_ctx)
+{
+    void *mt = gcb_dlpack_wrap(dev_ptr, dtype_code, bits, ndim, shape, device);
+    if (!mt) return NULL;
+    Owned *o = (Owned *)((DLManagedTensor *)mt)->manager_ctx;
+    o->release = release;
+    o->release_ctx = release_ctx;
+    return mt;
 }

@@ -610,15 +610,22 @@ k_mp_env_track_ages(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *
 }
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_extinguish(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg, int type,
-                    int n_dels, const int32_t *rnd, const uint8_t *mask, int32_t *dels_out)
+                    int n_dels, const int32_t *rnd, const uint8_t *mask, int32_t *dels_out, double interval)
 {
     __shared__ int red[8 * MP_EPC];
     MP_ENV_GUARD();
     if (mask && !mask[env]) { if (lane == 0) dels_out[env] = 0; return; }
-    MP_SHARED_ENV();
-    bind_device_env(e, blocks, anim, red, sw);
     Gym gy;
     bind_device_gym(gy, shadow, stride, &cfg);
+    if (interval != 0.0) {
+        // Extinguisher.step (wrappers.py:35-40): `if self.num_step % self.extinction_interval == 0` on the env's OWN step
+        // count.  An env that was just reset (num_step == 0) is skipped: in the reference the wrapper sits below the
+        // worker's auto-reset, so the event would have hit the city the reset then replaced.
+        const int k = gy.g->num_step;
+        if (k <= 0 || fmod((double)k, interval) != 0.0) { if (lane == 0) dels_out[env] = 0; return; }
+    }
+    MP_SHARED_ENV();
+    bind_device_env(e, blocks, anim, red, sw);
     if (lane == 0) dels_out[env] = gym_extinguish(e, gy, type, n_dels, rnd + (size_t)env * (n_dels + 2));
     unstage_scalars(e, sw);
 }
@@ -1515,8 +1522,21 @@ int mpb_env_track_ages(mpb_handle h, void *stream)
     return 0;
 }
 
+static int env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
+                          int32_t *dels_host, double interval, void *stream);
 int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
                        int32_t *dels_host, void *stream)
+{
+    return env_extinguish(h, type, n_dels, rnd_host, mask_host, dels_host, 0.0, stream);
+}
+int mpb_env_extinguish_due(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, double interval, int32_t *dels_host,
+                           void *stream)
+{
+    if (interval == 0.0) return -1;
+    return env_extinguish(h, type, n_dels, rnd_host, NULL, dels_host, interval, stream);
+}
+static int env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
+                          int32_t *dels_host, double interval, void *stream)
 {
     MpBatch *b = (MpBatch *)h;
     NEED_CFG();
@@ -1534,7 +1554,7 @@ int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_ho
     CK(cudaMemcpyAsync(rnd_dev, rnd_host, rb, cudaMemcpyHostToDevice, st));
     if (upload_mask(b, mask_host, st)) return -1;
     k_mp_env_extinguish<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                          type, n_dels, rnd_dev, mask_host ? b->mask : NULL, b->i32_b);
+                                                          type, n_dels, rnd_dev, mask_host ? b->mask : NULL, b->i32_b, interval);
     cudaError_t le = cudaGetLastError();
     if (le == cudaSuccess) le = cudaMemcpyAsync(b->host_i32, b->i32_b, (size_t)b->n_envs * 4, cudaMemcpyDeviceToHost, st);
     if (le == cudaSuccess) le = cudaStreamSynchronize(st);

@@ -10,6 +10,7 @@ import re
 import numpy as np
 
 from ._lib import lib
+from .dlpack import ViewOwner
 
 WORLD_W, WORLD_H = 120, 100
 _HDR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "mp_snapshot.h")
@@ -101,7 +102,7 @@ def _bind(L):
     _bound = True
 
 
-class EngineBatch:
+class EngineBatch(ViewOwner):
     def __init__(self, n_envs, device=0):
         import torch
         if not torch.cuda.is_available():
@@ -115,14 +116,16 @@ class EngineBatch:
         self.n = int(n_envs)
         self.device = int(device)
 
-    def close(self):
+    def _destroy_native(self):
+        """mpb_destroy.  close() (dlpack.ViewOwner) calls it at once when no DLPack view of the handle's buffers is
+        alive, otherwise when the last one is released."""
         if getattr(self, "_h", None):
             self._L.mpb_destroy(self._h)
             self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            self._destroy_native()
         except Exception:
             pass
 

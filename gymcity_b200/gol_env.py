@@ -13,7 +13,7 @@ import numpy as np
 
 from . import spaces
 from ._lib import lib
-from .dlpack import device_tensor
+from .dlpack import ViewOwner, device_tensor
 
 GOLB_ROWS, GOLB_OBS, GOLB_REWARD, GOLB_POP, GOLB_DONE = range(5)
 
@@ -23,7 +23,7 @@ def _stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-class _GolBase:
+class _GolBase(ViewOwner):
     classic = 0
 
     def __init__(self):
@@ -49,10 +49,10 @@ class _GolBase:
         self.max_step = int(max_step)
         n, w = self.num_proc, self.map_width
         P = lambda which: self._L.golb_ptr(self._h, which)
-        self._reward = device_tensor(P(GOLB_REWARD), "float32", (n, 1), self.device)
-        self._pop = device_tensor(P(GOLB_POP), "int32", (n,), self.device)
-        self._done = device_tensor(P(GOLB_DONE), "uint8", (n,), self.device)
-        self._rows = device_tensor(P(GOLB_ROWS), "int32", (n, w), self.device)
+        self._reward = device_tensor(P(GOLB_REWARD), "float32", (n, 1), self.device, owner=self)
+        self._pop = device_tensor(P(GOLB_POP), "int32", (n,), self.device, owner=self)
+        self._done = device_tensor(P(GOLB_DONE), "uint8", (n,), self.device, owner=self)
+        self._rows = device_tensor(P(GOLB_ROWS), "int32", (n, w), self.device, owner=self)
         self.intsToActions = [[0, i // w, i % w] for i in range(w * w)]
         self.actionsToInts = np.arange(w * w).reshape(1, w, w)
         self.action_space = spaces.Discrete(self.num_tools * w * w)
@@ -61,14 +61,21 @@ class _GolBase:
         if rc != 0:
             raise RuntimeError(self._L.golb_last_error(self._h).decode())
 
-    def close(self):
-        if self._h:
+    def _destroy_native(self):
+        if getattr(self, "_h", None):
             self._L.golb_destroy(self._h)
             self._h = None
 
+    def close(self):
+        """Frees the handle once no tensor handed out by this env is alive any more (dlpack.ViewOwner)."""
+        for k in ("_obs", "_reward", "_pop", "_done", "_rows"):
+            if hasattr(self, k):
+                setattr(self, k, None)
+        ViewOwner.close(self)
+
     def __del__(self):
         try:
-            self.close()
+            self._destroy_native()
         except Exception:
             pass
 
@@ -125,7 +132,7 @@ class GoLMultiEnv(_GolBase):
         self.num_params = 1
         self.observation_space = spaces.Box(0, 1, (n, 2, w, w), dtype=np.int64)
         self._obs = device_tensor(self._L.golb_ptr(self._h, GOLB_OBS), "float32", (n, 2, w, w),
-                                  self.device)
+                                  self.device, owner=self)
         self.step_count = 0
         self.set_params(self.params)
 
@@ -192,7 +199,7 @@ class GameOfLifeEnv(_GolBase):
         self.size = w
         self.observation_space = spaces.Box(0, 1, (1, w, w), dtype=np.int64)
         self._obs = device_tensor(self._L.golb_ptr(self._h, GOLB_OBS), "uint8", (n, 1, w, w),
-                                  self.device)
+                                  self.device, owner=self)
         self.step_count = 0
 
     def reset(self):

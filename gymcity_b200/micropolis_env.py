@@ -120,16 +120,17 @@ class MicropolisControl:
         P = lambda w: self._L.mpb_env_ptr(self._h, w)
         dev = self.engine.device
         self.obs_channels = 32
-        self.obs = device_tensor(P(MPB_ENV_OBS), "float32", (n, 32, W, H), dev)
-        self.reward = device_tensor(P(MPB_ENV_REWARD), "float32", (n, 1), dev)
-        self.done = device_tensor(P(MPB_ENV_DONE), "uint8", (n,), dev)
+        self.obs = device_tensor(P(MPB_ENV_OBS), "float32", (n, 32, W, H), dev, owner=self.engine)
+        self.reward = device_tensor(P(MPB_ENV_REWARD), "float32", (n, 1), dev, owner=self.engine)
+        self.done = device_tensor(P(MPB_ENV_DONE), "uint8", (n,), dev, owner=self.engine)
 
     def set_poet(self, param_ranges):
         """env.py:301-313 poet observation: 38 planes (pops / ranges, targets / ranges); rebinds self.obs."""
         r = np.ascontiguousarray(param_ranges, np.float64)
         self.obs_channels = self._ck(self._L.mpb_env_set_poet(self._h, 1, r.ctypes.data))
         self.obs = device_tensor(self._L.mpb_env_ptr(self._h, MPB_ENV_OBS), "float32",
-                                 (self.num_envs, self.obs_channels, self.MAP_X, self.MAP_Y), self.engine.device)
+                                 (self.num_envs, self.obs_channels, self.MAP_X, self.MAP_Y), self.engine.device,
+                                 owner=self.engine)
 
     def _bind(self):
         L, vp, i32 = self._L, C.c_void_p, C.c_int
@@ -141,6 +142,7 @@ class MicropolisControl:
             "mpb_env_step_host": (i32, [vp, vp, vp, vp, vp]), "mpb_env_ptr": (vp, [vp, i32]),
             "mpb_env_get_shadow": (i32, [vp, i32, vp, vp, vp, vp]),
             "mpb_env_track_ages": (i32, [vp, vp]), "mpb_env_extinguish": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+            "mpb_env_extinguish_due": (i32, [vp, i32, i32, vp, C.c_double, vp, vp]),
             "mpb_env_get_ages": (i32, [vp, i32, vp]), "mpb_env_set_obs_buffer": (i32, [vp, vp]),
             "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
             "mpb_env_step_masked": (i32, [vp, vp, i32, vp, vp]),
@@ -232,6 +234,9 @@ class MicropolisControl:
         return int(self.map.counters(0)["total_traffic"])
 
     def close(self):
+        """Drops this object's own views, then frees the handle -- at once, or when the last tensor a caller still holds
+        (an observation, a reward) is gone (dlpack.ViewOwner): no view outlives the memory it aliases."""
+        self.obs = self.reward = self.done = None
         self.engine.close()
 
 

@@ -39,14 +39,17 @@ class Extinguisher:
         return self.env.reset(*a, **kw)
 
     def step(self, a, **kw):                           # wrappers.py:35-40
+        """`if self.num_step % self.extinction_interval == 0: self.extinguish(...)` with every env's OWN num_step, decided
+        on the device (episodes of different envs end on different steps; an env the step has just auto-reset is not hit:
+        in the reference the event precedes the worker's reset, which replaces the city)."""
         out = self.env.step(a, **kw)
-        if self.env.num_step % self.extinction_interval == 0:
-            self.extinguish(self.extinction_type)
+        self.extinguish(self.extinction_type, due_interval=self.extinction_interval)
         return out
 
-    def extinguish(self, extinction_type='age', rnd=None, mask=None):   # wrappers.py:42-55
-        """One extinction event in every env (or the masked ones); returns the deletions per env.
-        rnd: optional int32 [num_envs, n_dels + 2] draws (tests pass the oracle's)."""
+    def extinguish(self, extinction_type='age', rnd=None, mask=None, due_interval=None):   # wrappers.py:42-55
+        """One extinction event in every env (or the masked ones, or -- due_interval -- the envs whose num_step is a
+        multiple of it); returns the deletions per env.  rnd: optional int32 [num_envs, n_dels + 2] draws (tests pass
+        the oracle's)."""
         if extinction_type not in XT_TYPES:
             return None
         m = self.env.micro
@@ -55,6 +58,10 @@ class Extinguisher:
             rnd = self.np_random.integers(0, 2 ** 31 - 1, size=(n, self.n_dels + 2))
         rnd = np.ascontiguousarray(rnd, np.int32).reshape(n, self.n_dels + 2)
         dels = np.zeros(n, np.int32)
+        if due_interval is not None:
+            m._ck(m._L.mpb_env_extinguish_due(m._h, XT_TYPES[extinction_type], self.n_dels, rnd.ctypes.data,
+                                              float(due_interval), dels.ctypes.data, m.engine._stream()))
+            return dels
         mk = None if mask is None else np.ascontiguousarray(np.asarray(mask).astype(np.uint8).reshape(n))
         m._ck(m._L.mpb_env_extinguish(m._h, XT_TYPES[extinction_type], self.n_dels, rnd.ctypes.data,
                                       None if mk is None else mk.ctypes.data, dels.ctypes.data, m.engine._stream()))

@@ -27,6 +27,11 @@ extern "C" {
  * storage.py:84-94 RolloutStorage.insert; envs.py:363-375 VecPyTorch.step_wait). */
 void *gcb_dlpack_wrap(void *dev_ptr, int dtype_code, int bits, int ndim, const int64_t *shape,
                       int device);
+/* The same with a release callback: called once, with release_ctx, when the consumer drops the tensor (its storage is
+ * freed).  The host side uses it to keep a handle -- and with it the buffer -- alive while views of it exist
+ * (gymcity_b200/dlpack.py: close() / garbage collection of an env is deferred until its last view is gone). */
+void *gcb_dlpack_wrap_owned(void *dev_ptr, int dtype_code, int bits, int ndim, const int64_t *shape, int device,
+                            void (*release)(void *), void *release_ctx);
 
 /* ------------------------------------------------------------------ Game of Life (golb_*) */
 typedef void *golb_handle;
@@ -245,6 +250,12 @@ int mpb_env_set_obs_buffer(mpb_handle h, float *obs_dev);
 int mpb_env_track_ages(mpb_handle h, void *stream);
 int mpb_env_extinguish(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, const uint8_t *mask_host,
                        int32_t *dels_host, void *stream);
+/* Extinguisher.step's own test (wrappers.py:35-40), per env and on the device: env i is hit iff its num_step > 0 and
+ * num_step % interval == 0 (interval = 1 / extinction_prob, a double; -1 for prob 0 hits every step, as in the reference).
+ * Envs that were just reset (num_step 0) are skipped: in the reference the wrapper runs before the worker's auto-reset
+ * replaces the city. */
+int mpb_env_extinguish_due(mpb_handle h, int type, int n_dels, const int32_t *rnd_host, double interval, int32_t *dels_host,
+                           void *stream);
 int mpb_env_get_ages(mpb_handle h, int env, int32_t *age_out);
 /* MicropolisEnv.step for every env: one fused launch (action, setFunds, 2 x simPasses simFrames +
  * animateTiles, observation, reward, done).  actions_dev = int64 [n_envs] DEVICE pointer. */

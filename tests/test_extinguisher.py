@@ -111,3 +111,41 @@ def test_extinguisher_wrapper_step_triggers_on_interval():
     # every 4th step the 50 oldest cells go: nothing aged is left right after an event
     assert built[3] == 0 and built[7] == 0 and max(built) > 0
     env.close()
+
+
+@pytest.mark.gpu
+def test_extinction_follows_each_envs_own_step_count():
+    """Extinguisher over the auto-resetting vec env: the event hits env i when ITS num_step is a multiple of the interval
+    (episodes staggered by a masked reset), and never the step on which the env was auto-reset (num_step 0: in the
+    reference the wrapper sits below the worker's reset)."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    from gymcity_b200.wrappers import Extinguisher
+    n, size = 4, 16
+    env = MicropolisVecEnv(n, size, seed=9, max_step=6, empty_start=False)
+    wrap = Extinguisher(env, 'age', extinction_prob=0.25, xt_dels=300, seed=1)      # interval 4: every aged cell goes
+    wrap.reset()
+    g = np.random.default_rng(0)
+    road = 8 * size * size                                                            # tool 8 ('Road') always leaves an aged cell
+    for t in range(2):
+        wrap.step(torch.from_numpy(road + g.integers(0, size * size, n)))
+    wrap.reset(mask=np.array([0, 1, 0, 1], bool))                                     # envs 1 and 3 are two steps behind now
+    seen = []
+    prev = np.array([int((wrap.ages(i) > -1).sum()) for i in range(n)])
+    hits = 0
+    for t in range(14):
+        obs, rew, done, _ = wrap.step(torch.from_numpy(road + g.integers(0, size * size, n)))
+        k = env.micro.counters()[:, 4].astype(int)                                    # num_step after the step (0: just reset)
+        aged = np.array([int((wrap.ages(i) > -1).sum()) for i in range(n)])
+        seen.append((k.copy(), aged.copy()))
+        for i in range(n):
+            if k[i] > 0 and k[i] % 4 == 0:
+                assert aged[i] <= 2 and aged[i] <= prev[i], (t, i, k, aged, prev)     # hit: (all but a stubborn cell or two of) the aged cells are gone
+                hits += 1
+            elif k[i] > 1:
+                assert aged[i] >= prev[i], (t, i, k, aged, prev)                      # not hit: nothing was taken away
+        prev = aged
+    assert hits >= 8
+    ks = np.stack([s[0] for s in seen])
+    assert (ks[:, 0] != ks[:, 1]).any() and (ks == 0).any()                           # staggered, and auto-resets happened
+    env.close()

@@ -116,3 +116,36 @@ def test_make_vec_envs_paint_env():
         ended += int(done.sum())
     assert ended == N                                                    # max_step = 5: one auto-reset each
     v.close()
+
+
+@pytest.mark.gpu
+def test_views_keep_the_handle_alive_until_released():
+    """A tensor handed out by an env (DLPack view of the handle's memory) stays valid after close() and after the env
+    object is gone: the handle is destroyed when the last view is released (gymcity_b200/dlpack.py)."""
+    import gc
+    from gymcity_b200 import GoLMultiEnv
+    from gymcity_b200.micropolis_env import MicropolisVecEnv
+    env = MicropolisVecEnv(4, 16, seed=1, max_step=50, empty_start=False)
+    obs = env.reset()
+    want = obs.clone()
+    eng = env.micro.engine
+    env.close()
+    assert eng._h is not None and eng._close_pending               # deferred: `obs` is still alive
+    junk = [torch.empty(1 << 20, device="cuda") for _ in range(8)]  # would reuse freed memory
+    assert torch.equal(obs, want)
+    del env, junk
+    gc.collect()
+    assert torch.equal(obs, want)
+    del obs, want
+    gc.collect()
+    assert eng._h is None                                           # the last view is gone: destroyed
+    g = GoLMultiEnv()
+    g.configure(map_width=16, num_proc=8, max_step=5)
+    o = g.reset()
+    keep = o.clone()
+    g.close()
+    assert g._h is not None
+    assert torch.equal(o, keep)
+    del o
+    gc.collect()
+    assert g._h is None
