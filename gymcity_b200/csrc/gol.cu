@@ -412,7 +412,9 @@ int golb_set_target(golb_handle h, float trg_pop, float range)
     b->trg_pop = trg_pop;
     b->scalar_plane = trg_pop / range;
     b->max_loss = range;
-    return refresh_obs(b, 0);
+    if (refresh_obs(b, 0)) return -1;
+    CK(cudaDeviceSynchronize());       // the legacy stream is not ordered against a caller's non-blocking stream
+    return 0;
 }
 
 int golb_reset(golb_handle h, uint32_t seed, float prob_life, void *stream)

@@ -1168,6 +1168,7 @@ int mpb_read_cycles(mpb_handle h, unsigned long long *out_host)
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out_host, b->cycles, (size_t)b->n_envs * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemset(b->cycles, 0, (size_t)b->n_envs * 8));
+    CK(cudaDeviceSynchronize());       // the legacy stream does not order this against work on non-blocking streams
     return 0;
 }
 
@@ -1238,7 +1239,7 @@ int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host)
     const size_t bytes = (size_t)b->n_envs * 256 * sizeof(unsigned int);
     if (out_host && b->prof) CK(cudaMemcpy(out_host, b->prof, bytes, cudaMemcpyDeviceToHost));
     if (enable && !b->prof) { CK(cudaMalloc(&b->prof, bytes)); }
-    if (enable) CK(cudaMemset(b->prof, 0, bytes));
+    if (enable) { CK(cudaMemset(b->prof, 0, bytes)); CK(cudaDeviceSynchronize()); }
     if (!enable && b->prof) { cudaFree(b->prof); b->prof = NULL; }
     return 0;
 }
@@ -1381,6 +1382,7 @@ int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset)
     if (b->next_ep && (b->run_seed != seed || b->env_offset != env_offset)) {      // prepared maps belong to the old seeds
         CK(cudaDeviceSynchronize());
         CK(cudaMemset(b->next_ep, 0xff, (size_t)b->n_envs * 4));
+        CK(cudaDeviceSynchronize());   // memsets run on the legacy stream: callers' non-blocking streams are not ordered after it
     }
     b->run_seed = seed; b->env_offset = env_offset;
     return 0;
@@ -1413,6 +1415,7 @@ int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain)
         CK(cudaMalloc(&b->pf_stats, 8));
         CK(cudaMemset(b->next_ep, 0xff, (size_t)b->n_envs * 4));
         CK(cudaMemset(b->pf_stats, 0, 8));
+        CK(cudaDeviceSynchronize());   // (a step on a non-blocking stream must not read next_ep before it is cleared)
         CK(cudaStreamCreateWithPriority(&b->pf_stream, cudaStreamNonBlocking, lo));
         CK(cudaEventCreateWithFlags(&b->ev_pf, cudaEventDisableTiming));
     }
@@ -1499,6 +1502,7 @@ int mpb_env_set_poet(mpb_handle h, int enable, const double *param_ranges)
     b->obs = NULL;
     CK(cudaMalloc(&b->obs, (size_t)b->n_envs * on * 4));
     CK(cudaMemset(b->obs, 0, (size_t)b->n_envs * on * 4));
+    CK(cudaDeviceSynchronize());
     b->obs_out = b->obs;
     return gym_obs_channels(b->cfg);
 }

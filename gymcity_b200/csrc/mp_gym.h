@@ -440,16 +440,13 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
         MP_NOUNROLL for (int k = 0; k < GYM_NUM_METRICS; k++) sc[6 + k] = (float)(CFG.trg[k] / CFG.param_range[k]);
     }
     int tsum = 0;
-    // one window cell per lane and iteration: every plane's store is coalesced across the lanes, and
-    // the per-cell inputs (zone id, power bit, the two half-resolution densities) are read once
-    for (int cell = e.c.tid; cell < n; cell += e.c.n) {
+    // per-cell inputs of plane 22 (power), 23 (population density), 24 (traffic density); returns the traffic value the
+    // cell contributes to total_traffic (each half-resolution cluster once)
+    auto cell_inputs = [&](int cell, float &pw, float &vp, float &vt) -> int {
         const int i = cell / H, j = cell - i * H;
-        float *o = obs + cell;
-        const uint32_t feat = kZoneFeatures[gy.zone[cell]];
-        MP_NOUNROLL for (int p = 0; p < kNumFeatures; p++) o[p * n] = (float)((feat >> p) & 1u);
-        o[22 * n] = (float)pwr_get(e, j + CFG.xs, i + CFG.ys);
+        pw = (float)pwr_get(e, j + CFG.xs, i + CFG.ys);
         // cluster (x = j' + MAP_XS/2, y = i' + MAP_YS/2) fills rows 2i'..2i'+1, cols 2j'..2j'+1
-        float vp = 0.0f, vt = 0.0f;
+        vp = 0.0f; vt = 0.0f;
         const int i2 = i >> 1, j2 = j >> 1;
         if (i2 < W / 2 && j2 < H / 2) {
             const int cx = j2 + CFG.xs / 2, cy = i2 + CFG.ys / 2;
@@ -457,9 +454,49 @@ MPD void gym_observe(Env &e, Gym &gy, float *obs)
                 const int dp = e.pop()[cx * H2 + cy], dt = e.traffic()[cx * H2 + cy];
                 vp = (float)dp;
                 vt = (float)dt;
-                if (!(i & 1) && !(j & 1)) tsum += dt;
+                if (!(i & 1) && !(j & 1)) return dt;
             }
         }
+        return 0;
+    };
+#if defined(__CUDA_ARCH__)
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
+        // four consecutive window cells per lane and iteration: every plane is written with 128-bit stores, 512
+        // contiguous bytes per warp instruction (a 120x100 window is 1.5 MB of observation per env: with 32-bit
+        // stores this kernel ran at a quarter of the HBM rate, profiles/r02_notes.md)
+        for (int c0 = e.c.tid * 4; c0 < n; c0 += e.c.n * 4) {
+            const uint32_t z4 = *reinterpret_cast<const uint32_t *>(gy.zone + c0);
+            const uint32_t s4 = *reinterpret_cast<const uint32_t *>(gy.stat + c0);
+            uint32_t feat[4];
+            float pw[4], vp[4], vt[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                feat[q] = kZoneFeatures[(z4 >> (8 * q)) & 0xffu];
+                tsum += cell_inputs(c0 + q, pw[q], vp[q], vt[q]);
+            }
+            float4 *o = reinterpret_cast<float4 *>(obs + c0);
+            const int n4 = n >> 2;
+            MP_NOUNROLL for (int p = 0; p < kNumFeatures; p++)
+                o[p * n4] = make_float4((float)((feat[0] >> p) & 1u), (float)((feat[1] >> p) & 1u),
+                                        (float)((feat[2] >> p) & 1u), (float)((feat[3] >> p) & 1u));
+            o[22 * n4] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+            o[23 * n4] = make_float4(vp[0], vp[1], vp[2], vp[3]);
+            o[24 * n4] = make_float4(vt[0], vt[1], vt[2], vt[3]);
+            MP_NOUNROLL for (int k = 0; k < nsc; k++) o[(25 + k) * n4] = make_float4(sc[k], sc[k], sc[k], sc[k]);
+            o[(25 + nsc) * n4] = make_float4((float)(s4 & 0xffu), (float)((s4 >> 8) & 0xffu), (float)((s4 >> 16) & 0xffu),
+                                             (float)((s4 >> 24) & 0xffu));
+        }
+    } else
+#endif
+    // one window cell per lane and iteration: every plane's store is coalesced across the lanes, and
+    // the per-cell inputs (zone id, power bit, the two half-resolution densities) are read once
+    for (int cell = e.c.tid; cell < n; cell += e.c.n) {
+        float *o = obs + cell;
+        const uint32_t feat = kZoneFeatures[gy.zone[cell]];
+        MP_NOUNROLL for (int p = 0; p < kNumFeatures; p++) o[p * n] = (float)((feat >> p) & 1u);
+        float pw, vp, vt;
+        tsum += cell_inputs(cell, pw, vp, vt);
+        o[22 * n] = pw;
         o[23 * n] = vp;
         o[24 * n] = vt;
         MP_NOUNROLL for (int k = 0; k < nsc; k++) o[(25 + k) * n] = sc[k];

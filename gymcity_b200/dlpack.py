@@ -6,6 +6,8 @@ unregisters it.  While views exist the owner object is referenced from here (so 
 them), and an explicit `close()` is deferred until the last view is released: no tensor handed out by an env can
 outlive the device memory it aliases."""
 import ctypes as C
+import itertools
+import threading
 
 from ._lib import lib
 
@@ -17,7 +19,8 @@ C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
 
 _RELEASE = C.CFUNCTYPE(None, C.c_void_p)
 _live = {}                       # view id -> owner
-_next_id = [1]
+_ids = itertools.count(1)        # next() is atomic: envs may be created from several threads
+_lock = threading.RLock()        # guards the view counts (a view may be released on another thread than its owner's)
 
 
 class ViewOwner:
@@ -30,15 +33,19 @@ class ViewOwner:
         raise NotImplementedError
 
     def close(self):
-        if self._views > 0:
-            self._close_pending = True
-            return
+        with _lock:
+            if self._views > 0:
+                self._close_pending = True
+                return
         self._destroy_native()
 
     def _view_released(self):
-        self._views -= 1
-        if self._views <= 0 and self._close_pending:
-            self._close_pending = False
+        with _lock:
+            self._views -= 1
+            fire = self._views <= 0 and self._close_pending
+            if fire:
+                self._close_pending = False
+        if fire:
             self._destroy_native()
 
 
@@ -65,14 +72,15 @@ def device_tensor(ptr, dtype, shape, device, owner=None):
     if owner is None:
         mt = L.gcb_dlpack_wrap(ptr, code, bits, len(shape), shp, int(device))
     else:
-        vid = _next_id[0]
-        _next_id[0] += 1
-        _live[vid] = owner
-        owner._views += 1
+        vid = next(_ids)
+        with _lock:
+            _live[vid] = owner
+            owner._views += 1
         mt = L.gcb_dlpack_wrap_owned(ptr, code, bits, len(shape), shp, int(device), _on_release, C.c_void_p(vid))
         if not mt:
-            _live.pop(vid, None)
-            owner._views -= 1
+            with _lock:
+                _live.pop(vid, None)
+                owner._views -= 1
     if not mt:
         raise RuntimeError("gcb_dlpack_wrap failed")
     cap = C.pythonapi.PyCapsule_New(mt, b"dltensor", None)
