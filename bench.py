@@ -49,7 +49,21 @@ WORKLOADS = {
                             "actions), terrain path"),
     "mp120": dict(size=(120, 100), envs=2048, xs=0, ys=0, puzzle=False,
                   text="Full 120x100 world window @ (0,0), terrain path, uniform random actions over all 20 tools"),
+    "mp120dense": dict(size=(120, 100), envs=2048, xs=0, ys=0, puzzle=False, dense=True,
+                       text="Full 120x100 world window @ (0,0), every env starts from one of the reference's 24 shipped cities "
+                            "(round robin, tests/golden/cty_maps.npz), uniform random actions over all 20 tools"),
 }
+
+
+def load_dense_cities(env):
+    """BASELINE config 4, dense variant: the maps of the reference's 24 .cty cities into the envs, round robin, and the
+    TileMap shadow re-read from them (MicropolisControl.updateMap) -- big power grids, traffic, zone growth from tick 1."""
+    import numpy as np
+    maps = np.load(os.path.join(ROOT, "tests", "golden", "cty_maps.npz"))["maps"]
+    eng = env.micro.engine
+    for i in range(env.num_envs):
+        eng.set(i, "MPF_MAP", maps[i % maps.shape[0]])
+    env.micro.updateMap()
 
 
 def workload(args):
@@ -112,7 +126,7 @@ def cpu_reference(seconds, name="mp16"):
     from oracle import cpu_bench
     w = WORKLOADS[name]
     W, H = (w["size"], w["size"]) if isinstance(w["size"], int) else w["size"]
-    rate, procs, steps, wall = cpu_bench.run(seconds=seconds, win=W, win_h=H, xs=w["xs"], ys=w["ys"])
+    rate, procs, steps, wall = cpu_bench.run(seconds=seconds, win=W, win_h=H, xs=w["xs"], ys=w["ys"], dense=bool(w.get("dense")))
     return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
             "sample": "%d env-ticks over %d processes (one reference engine each, pinned one per core), %.1f s "
                       "busy each, %dx%d window, terrain path, uniform random tool + Water/Land/Clear per tick, "
@@ -188,6 +202,8 @@ def run_extra_mp(name, args, local, dev, K, age, cpu_seconds):
     cb = None if args.no_cpu_baseline else cpu_reference(cpu_seconds, name)
     env = make_env(name, E, local, 0, args.seed)
     env.reset()
+    if wl.get("dense"):
+        load_dense_cities(env)
     m = env.micro
     g = torch.Generator(device=dev)
     g.manual_seed(args.seed * 1000 + 17)
@@ -282,6 +298,8 @@ def run_ours(args):
 
     env = make_env(args.workload, E, local, rank, args.seed)
     env.reset()
+    if WORKLOADS[args.workload].get("dense"):
+        load_dense_cities(env)
     m = env.micro
     nA = env.action_space.n
     g = torch.Generator(device=dev)
@@ -404,6 +422,7 @@ def run_ours(args):
         try:
             extra["mp16_episode"], extra["mp16_venv_step"] = run_episode_and_venv(args, local, dev, Kx)
             extra["mp120"] = run_extra_mp("mp120", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
+            extra["mp120dense"] = run_extra_mp("mp120dense", args, local, dev, Kx, 10, min(4.0, args.cpu_seconds))
             extra["mp32puzzle"] = run_extra_mp("mp32puzzle", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
             extra["gol16_4096"] = gol_measure(args, 4096, Kx, local)
             extra["gol16_1m"] = gol_measure(args, 1 << 20, Kx, local, cpu=False)

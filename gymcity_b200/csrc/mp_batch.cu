@@ -556,6 +556,22 @@ k_mp_env_post_list(uint8_t *blocks, const uint16_t *anim, uint8_t *shadow, int s
     }
 }
 
+// MicropolisControl.updateMap (corecontrol.py:193-203): every window cell of the shadow map re-read from the engine map
+// (after a city was loaded into the engine: mpb_set_field MPF_MAP / cty.load_env)
+__global__ void __launch_bounds__(MP_THREADS)
+k_mp_env_update_map(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg, const uint8_t *mask)
+{
+    __shared__ int red[8 * MP_EPC];
+    MP_ENV_GUARD();
+    if (mask && !mask[env]) return;
+    MP_SHARED_ENV();
+    bind_device_env(e, blocks, anim, red, sw);
+    Gym gy;
+    bind_device_gym(gy, shadow, stride, &cfg);
+    gym_update_map(e, gy);
+    unstage_scalars(e, sw);
+}
+
 // TileMap.addZoneBot through MicropolisControl.doBotTool, no tick (powerPuzzle / randomStaticStart set-up)
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_action(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
@@ -1385,6 +1401,19 @@ int mpb_env_set_seed(mpb_handle h, long long seed, int env_offset)
         CK(cudaDeviceSynchronize());   // memsets run on the legacy stream: callers' non-blocking streams are not ordered after it
     }
     b->run_seed = seed; b->env_offset = env_offset;
+    return 0;
+}
+
+int mpb_env_update_map(mpb_handle h, const uint8_t *mask_host, void *stream)
+{
+    MpBatch *b = (MpBatch *)h;
+    NEED_CFG();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (upload_mask(b, mask_host, st)) return -1;
+    k_mp_env_update_map<<<MP_GRID(b), MP_THREADS, MP_DYN_SMEM, st>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                                   mask_host ? b->mask : NULL);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -147,7 +147,7 @@ class MicropolisControl:
             "mpb_env_step_paint": (i32, [vp, vp, vp]), "mpb_env_set_poet": (i32, [vp, i32, vp]),
             "mpb_env_step_masked": (i32, [vp, vp, i32, vp, vp]),
             "mpb_env_set_seed": (i32, [vp, C.c_longlong, i32]), "mpb_env_set_auto_reset": (i32, [vp, i32, i32]),
-            "mpb_env_set_num_step": (i32, [vp, vp, vp]), "mpb_env_prefetch_stats": (i32, [vp, vp, vp]),
+            "mpb_env_set_num_step": (i32, [vp, vp, vp]), "mpb_env_update_map": (i32, [vp, vp, vp]), "mpb_env_prefetch_stats": (i32, [vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -218,6 +218,11 @@ class MicropolisControl:
         (seed, global env index, episode) -- mpb_env_set_seed; sharding.mix is the same hash on the host."""
         m, p = EngineBatch._mask(mask, self.num_envs)
         self._ck(self._L.mpb_env_reset_begin(self._h, 1, None, None, p, self.engine._stream()))
+
+    def updateMap(self, mask=None):                         # corecontrol.py:193-203
+        """The TileMap shadow of the window re-read from the engine map (after loading a city into the engine)."""
+        m, p = EngineBatch._mask(mask, self.num_envs)
+        self._ck(self._L.mpb_env_update_map(self._h, p, self.engine._stream()))
 
     def getDensityMaps(self):                               # corecontrol.py:215-239 -> obs planes 22..24
         return self.obs[:, 22:25]

@@ -200,6 +200,10 @@ int mpb_env_set_auto_reset(mpb_handle h, int enable, int terrain);
  * and a reset copies it instead of generating (ENG/generate.cpp:119-160 is 2.5 ms of one warp's time).  Returns 1 if
  * the prefetch is active; served_out / inline_out: resets served from a prepared map / generated in line so far. */
 int mpb_env_prefetch_stats(mpb_handle h, unsigned int *served_out, unsigned int *inline_out);
+/* MicropolisControl.updateMap (corecontrol.py:193-203) for the envs of the mask (NULL = all): the TileMap shadow of the
+ * build window is re-read from the engine map, e.g. after a city file was loaded into the engine (mpb_set_field MPF_MAP,
+ * gymcity_b200.cty.load_env). */
+int mpb_env_update_map(mpb_handle h, const uint8_t *mask_host, void *stream);
 /* MicropolisEnv.num_step of every env (int32 [n_envs] HOST): episodes that end on different steps (in the reference
  * every worker counts its own steps, env.py:448-460; randomStaticStart gives each its own offset, env.py:228-241). */
 int mpb_env_set_num_step(mpb_handle h, const int32_t *num_step_host, void *stream);

@@ -16,7 +16,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(idx, seconds, win, terrain, win_h=None, xs=16, ys=8):
+def _worker(idx, seconds, win, terrain, win_h=None, xs=16, ys=8, dense=0):
     try:
         os.sched_setaffinity(0, {idx % (os.cpu_count() or 1)})
     except Exception:
@@ -28,6 +28,10 @@ def _worker(idx, seconds, win, terrain, win_h=None, xs=16, ys=8):
         r.generate(1000 + idx)
     else:
         r.clearMap()
+    if dense:                                             # BASELINE config 4, dense variant: one of the reference's 24 cities
+        import numpy as np
+        maps = np.load(os.path.join(ROOT, "tests", "golden", "cty_maps.npz"))["maps"]
+        r.set("MPF_MAP", maps[idx % maps.shape[0]])
     r.seed(idx)
     win_h = win_h or win
     r.bench_rollout(50, win, win_h, xs, ys, act_seed=idx)       # warm-up
@@ -40,12 +44,12 @@ def _worker(idx, seconds, win, terrain, win_h=None, xs=16, ys=8):
     print(json.dumps({"steps": steps, "busy": busy}), flush=True)
 
 
-def run(seconds=8.0, procs=None, win=16, terrain=True, win_h=None, xs=16, ys=8):
+def run(seconds=8.0, procs=None, win=16, terrain=True, win_h=None, xs=16, ys=8, dense=False):
     """Returns (env_ticks_per_s_total, procs, total_steps, wall_seconds)."""
     procs = procs or (os.cpu_count() or 1)
     t0 = time.perf_counter()
     ps = [subprocess.Popen([sys.executable, "-m", "oracle.cpu_bench", "--worker", str(i), str(seconds), str(win),
-                            str(int(terrain)), str(win_h or win), str(xs), str(ys)], cwd=ROOT, stdout=subprocess.PIPE, text=True)
+                            str(int(terrain)), str(win_h or win), str(xs), str(ys), str(int(dense))], cwd=ROOT, stdout=subprocess.PIPE, text=True)
           for i in range(procs)]
     res = []
     for p in ps:
@@ -60,7 +64,7 @@ def run(seconds=8.0, procs=None, win=16, terrain=True, win_h=None, xs=16, ys=8):
 
 if __name__ == "__main__":
     if len(sys.argv) >= 6 and sys.argv[1] == "--worker":
-        extra = [int(a) for a in sys.argv[6:9]]
+        extra = [int(a) for a in sys.argv[6:10]]
         _worker(int(sys.argv[2]), float(sys.argv[3]), int(sys.argv[4]), bool(int(sys.argv[5])), *extra)
     else:
         print(run(seconds=float(sys.argv[1]) if len(sys.argv) > 1 else 3.0))

@@ -250,3 +250,42 @@ def test_speed_divider_frames():
             r.simFrames(77)
         _check(b, refs, "frames %d" % k)
     b.close()
+
+
+def test_dense_city_through_the_gym_layer():
+    """BASELINE config 4, dense variant, as bench.py runs it: a reference city loaded into the engine under a
+    120x100 window, the TileMap shadow re-read from it (MicropolisControl.updateMap, corecontrol.py:193-203), random
+    actions over all 20 tools -- observation, reward, done and engine state against the oracle gym layer."""
+    import torch
+    from gymcity_b200.micropolis_env import MicropolisEnv
+    maps = np.load(os.path.join(GOLD, "cty_maps.npz"))["maps"]
+    pick = [1, 7, 23]                                             # badnews, haight, yokohama: the densest
+    n, size = len(pick), (120, 100)
+    seeds = np.arange(n) + 70
+    env = MicropolisEnv(num_envs=n)
+    env.setMapSize(size, max_step=100, empty_start=False, MAP_XS=0, MAP_YS=0)
+    refs = [RefEnv(RefEngine(), size, max_step=100, empty_start=False, xs=0, ys=0) for _ in range(n)]
+    m = env.micro
+    m.newMap(seeds + 1000, seeds)
+    for i, r in enumerate(refs):
+        r.reset_begin(int(seeds[i]) + 1000, int(seeds[i]))
+        r.micro.engine.set("MPF_MAP", maps[pick[i]])
+        r.micro.updateMap()
+        m.engine.set(i, "MPF_MAP", maps[pick[i]])
+    m.updateMap()
+    m._ck(m._L.mpb_env_reset_finish(m._h, None, m.engine._stream()))
+    obs = m.obs.cpu().numpy()
+    for i, r in enumerate(refs):
+        assert np.array_equal(r.reset_finish().astype(np.float32), obs[i]), i
+    rng = np.random.default_rng(4)
+    for t in range(5):
+        acts = rng.integers(0, 20 * 12000, n).astype(np.int64)
+        obs, rew, done, _ = env.step(torch.from_numpy(acts))
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy().reshape(-1), done.cpu().numpy()
+        for i, r in enumerate(refs):
+            o, rr, d, _ = r.step(int(acts[i]), False)
+            assert np.array_equal(np.asarray(o, np.float32), obs[i]), (t, i)
+            assert rr == rew[i] and d == bool(done[i]), (t, i)
+    for i, r in enumerate(refs):
+        assert not diff_snapshots(r.micro.engine.snapshot(), m.engine.snapshot(i)), i
+    env.close()
