@@ -54,6 +54,8 @@ struct MpBatch {
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
+    int timing;                    // MPB_TIMING: events at the phase boundaries of a one-group step (mpb_step_phase_times)
+    cudaEvent_t ev_ph[6];
     unsigned long long *skey, *skey_out;    // [n_envs] sort keys of the schedule (36 bits used; the tool-order sort of k_mp_env_pre reuses the storage as 32-bit keys)
     int *sval;                // [n_envs] env ids (sort values in)
     void *sort_tmp; size_t sort_tmp_bytes;
@@ -959,6 +961,8 @@ mpb_handle mpb_create(int n_envs, int device)
     for (int g = 0; g < 8; g++) { cudaStreamCreateWithFlags(&b->gstream[g], cudaStreamNonBlocking); cudaEventCreate(&b->ev_done[g]); }
     cudaEventCreate(&b->ev_start);
     cudaEventCreate(&b->ev_ar0); cudaEventCreate(&b->ev_ar1);
+    b->timing = getenv("MPB_TIMING") != NULL;
+    for (int i = 0; i < 6; i++) cudaEventCreate(&b->ev_ph[i]);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
     k_mp_construct<<<(n_envs + MP_EPC - 1) / MP_EPC, MP_THREADS, MP_DYN_SMEM>>>(b->blocks, b->anim, n_envs);
@@ -975,6 +979,7 @@ void mpb_destroy(mpb_handle h)
     if (b->ev_start) cudaEventDestroy(b->ev_start);
     if (b->ev_ar0) cudaEventDestroy(b->ev_ar0);
     if (b->ev_ar1) cudaEventDestroy(b->ev_ar1);
+    for (int i = 0; i < 6; i++) if (b->ev_ph[i]) cudaEventDestroy(b->ev_ph[i]);
     cudaFree(b->cycles); cudaFree(b->cost); cudaFree(b->perm); cudaFree(b->cls_sum); cudaFree(b->cls_cnt);
     cudaFree(b->skey); cudaFree(b->skey_out); cudaFree(b->sval); cudaFree(b->sort_tmp); cudaFree(b->ncls_dev); cudaFree(b->perm_pre);
     if (b->ncls_host) cudaFreeHost(b->ncls_host);
@@ -1200,6 +1205,19 @@ int mpb_group_times(mpb_handle h, float *ms_out)
     }
     cudaGetLastError();
     return b->groups;
+}
+
+// Profiling (MPB_TIMING=1, one-group steps): device time of the phases of the last env step -- schedule rebuild,
+// action kernel (with its tool-order sort), the two simTicks, observation / reward, auto-reset -- float [5] ms.
+int mpb_step_phase_times(mpb_handle h, float *ms_out)
+{
+    MpBatch *b = (MpBatch *)h;
+    if (!b || !ms_out || !b->timing) return -1;
+    cudaSetDevice(b->device);
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 5; i++)
+        if (cudaEventElapsedTime(&ms_out[i], b->ev_ph[i], b->ev_ph[i + 1]) != cudaSuccess) { cudaGetLastError(); ms_out[i] = -1.0f; }
+    return 0;
 }
 
 int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out)
@@ -1652,7 +1670,10 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
     const int *perm = b->use_sched ? b->perm : NULL;
     // the order of this step: by the phase each env is in NOW (resets between steps move envs to another phase
     // class) and by what the previous step cost it
+    const bool tm = b->timing && G == 1;
+    if (tm) cudaEventRecord(b->ev_ph[0], st);
     rebuild_schedule(b, st);
+    if (tm) cudaEventRecord(b->ev_ph[1], st);
     if (G > 1) cudaEventRecord(b->ev_start, st);
     for (int g = 0; g < G; g++) {
         cudaStream_t gs = G > 1 ? b->gstream[g] : st;
@@ -1676,9 +1697,12 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         } else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);
+        if (tm) cudaEventRecord(b->ev_ph[2], gs);
         launch_control_sim_tick(b, gs, mask_dev, G, g);
+        if (tm) cudaEventRecord(b->ev_ph[3], gs);
         k_mp_env_post<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                   b->obs_out, b->reward, b->done, 0, mask_dev, perm, q);
+        if (tm) cudaEventRecord(b->ev_ph[4], gs);
         if (G > 1) {
             cudaEventRecord(b->ev_done[g], gs);
             cudaStreamWaitEvent(st, b->ev_done[g], 0);
@@ -1686,6 +1710,7 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
     }
     b->cur_frames = 0;
     if (b->auto_reset) launch_auto_reset(b, mask_dev, st);
+    if (tm) cudaEventRecord(b->ev_ph[5], st);
     CK_LAUNCHES();
     return 0;
 }

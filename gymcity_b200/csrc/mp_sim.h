@@ -1445,7 +1445,6 @@ MPN void dec_traffic_map(Env &e)
     // 3000 cells (+8 zero pad bytes) = 188 uint4; four cells per 32-bit word with byte-SIMD:
     // z - (z > 200 ? 34 : 24) saturated at 0 is exactly the reference's three-way rule.
     uint4 *q = reinterpret_cast<uint4 *>(e.traffic());
-#if MP_WARP_COOP
     uint4 v[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
@@ -1464,18 +1463,6 @@ MPN void dec_traffic_map(Env &e)
             q[i] = r;
         }
     }
-#else
-    MP_NOUNROLL for (int i = 0; i < 188; i++) {
-        const uint4 v = q[i];
-        if (!(v.x | v.y | v.z | v.w)) continue;
-        uint4 r;
-        r.x = __vsubus4(v.x, (__vcmpgtu4(v.x, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
-        r.y = __vsubus4(v.y, (__vcmpgtu4(v.y, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
-        r.z = __vsubus4(v.z, (__vcmpgtu4(v.z, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
-        r.w = __vsubus4(v.w, (__vcmpgtu4(v.w, 0xc8c8c8c8u) & 0x0a0a0a0au) + 0x18181818u);
-        q[i] = r;
-    }
-#endif
 #else
     for (int i = e.c.tid; i < N2; i += e.c.n) e.traffic()[i] = dec_traffic_cell(e.traffic()[i]);
 #endif

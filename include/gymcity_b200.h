@@ -111,6 +111,9 @@ int mpb_frame_profile(mpb_handle h, int enable, unsigned int *out_host);
  * or -1 in a product build; mpb_coverage_name(i) names function i. */
 int mpb_coverage(unsigned long long *bits_out, int cap_words);
 const char *mpb_coverage_name(int id);
+/* Profiling (handles created with MPB_TIMING set): device time (ms) of the five phases of the last one-group env step
+ * -- schedule rebuild, action kernel, the two simTicks, observation / reward, auto-reset -- float [5]. */
+int mpb_step_phase_times(mpb_handle h, float *ms_out);
 /* Profiling: device time (ms) of the auto-reset part of the last env step and how many envs it reset. */
 int mpb_auto_reset_time(mpb_handle h, float *ms_out, int *n_reset_out);
 /* Profiling: the heavy-first env order the NEXT env-step's launches use (int32 [n_envs] HOST); returns the
