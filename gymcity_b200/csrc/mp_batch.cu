@@ -54,6 +54,7 @@ struct MpBatch {
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
+    int resched_mid;               // rebuild the order between the two simTicks of a one-group step (MPB_RESCHED_MID=0: off)
     int timing;                    // MPB_TIMING: events at the phase boundaries of a one-group step (mpb_step_phase_times)
     cudaEvent_t ev_ph[6];
     unsigned long long *skey, *skey_out;    // [n_envs] sort keys of the schedule (36 bits used; the tool-order sort of k_mp_env_pre reuses the storage as 32-bit keys)
@@ -818,9 +819,15 @@ int launch_sim_tick(MpBatch *b, cudaStream_t st, int animate_before, const uint8
     return 0;
 }
 // MicropolisControl.simTick (corecontrol.py:148-152): tickEngine (simTick + animateTiles) + simTick
-int launch_control_sim_tick(MpBatch *b, cudaStream_t st, const uint8_t *mask, int G = 1, int g = 0)
+int rebuild_schedule(MpBatch *b, cudaStream_t st);
+int launch_control_sim_tick(MpBatch *b, cudaStream_t st, const uint8_t *mask, int G = 1, int g = 0, bool resched = false)
 {
     launch_sim_tick(b, st, 0, mask, G, g);
+    // one-group steps: the order is rebuilt between the two simTicks from what the first one cost -- a city that started
+    // to flood or burn during it (40 % of all barrier waiting is for such a city) joins the CTAs of its new peers half a
+    // step earlier: +4 % (1.77 -> 1.85 M env-ticks/s).  A new order before every 50- or 25-frame launch is worse again
+    // (1.81 / 1.70 M: more launch tails, noisier keys), and so is mixing in older costs (profiles/r02_notes.md).
+    if (resched) rebuild_schedule(b, st);
     launch_sim_tick(b, st, 1, mask, G, g);
     return 0;
 }
@@ -928,6 +935,7 @@ mpb_handle mpb_create(int n_envs, int device)
         && cudaMalloc(&b->cls_sum, SCHED_CLASSES * sizeof(unsigned long long)) == cudaSuccess
         && cudaMalloc(&b->cls_cnt, SCHED_CLASSES * sizeof(unsigned int)) == cudaSuccess
         && cudaMalloc(&b->perm_pre, (size_t)n_envs * 4) == cudaSuccess
+
         && cudaMalloc(&b->ncls_dev, sizeof(int)) == cudaSuccess
         && cudaMallocHost(&b->ncls_host, sizeof(int)) == cudaSuccess
         && cudaMalloc(&b->skey, (size_t)n_envs * 8) == cudaSuccess
@@ -947,6 +955,7 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaMemcpy(b->anim, anim, sizeof(anim), cudaMemcpyHostToDevice);
     cudaMemset(b->cycles, 0, (size_t)n_envs * 8);
     cudaMemset(b->cost, 0, (size_t)n_envs * 4);
+
     b->use_sched = 1;
     // Env groups on streams (the heavy 1/64 + two more, 50 frames per launch) pay off while a launch has only a few
     // waves of CTAs, or CTAs of very different length: small batches (2 048 envs +4 %, 8 192 envs +2 %) and batches
@@ -962,6 +971,8 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaEventCreate(&b->ev_start);
     cudaEventCreate(&b->ev_ar0); cudaEventCreate(&b->ev_ar1);
     b->timing = getenv("MPB_TIMING") != NULL;
+    b->resched_mid = getenv("MPB_RESCHED_MID") ? atoi(getenv("MPB_RESCHED_MID")) : 1;
+
     for (int i = 0; i < 6; i++) cudaEventCreate(&b->ev_ph[i]);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
     k_mp_sched_identity<<<(n_envs + 255) / 256, 256>>>(b->perm, n_envs);
@@ -1014,6 +1025,7 @@ int mpb_launches_per_env_step(mpb_handle h)
     MpBatch *b = (MpBatch *)h;
     if (!b) return -1;
     int total = b->use_sched ? 2 : 0;                       // the two scheduling kernels of this library (the sort is CUB's)
+    if (b->use_sched && step_groups(b) == 1 && b->resched_mid) total += 2;      // ... again between the two simTicks
     if (b->auto_reset) total += 5 + (b->next_map ? 1 : 0);  // list, reset, 2 x frames, post, terrain prefetch
     const int G = step_groups(b);
     if (G == 1 && b->use_sched) total += 1;                 // k_mp_pre_keys (the action kernel runs in tool order)
@@ -1698,7 +1710,7 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);
         if (tm) cudaEventRecord(b->ev_ph[2], gs);
-        launch_control_sim_tick(b, gs, mask_dev, G, g);
+        launch_control_sim_tick(b, gs, mask_dev, G, g, G == 1 && b->use_sched && b->resched_mid);
         if (tm) cudaEventRecord(b->ev_ph[3], gs);
         k_mp_env_post<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                   b->obs_out, b->reward, b->done, 0, mask_dev, perm, q);
