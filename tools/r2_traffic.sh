@@ -17,8 +17,15 @@ for r in rows:
     d = launches.setdefault(int(r[0]), {"kernel": r[ik].split("(")[0].split("::")[-1]})
     d[r[im]] = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
 ids = sorted(launches)
-starts = [i for i in ids if launches[i]["kernel"].startswith("k_mp_sched_class")]
-a, b = starts[0], starts[1]
+# a step starts at the k_mp_sched_class launch that precedes a k_mp_env_pre (one-group steps rebuild the schedule a
+# second time between the two simTicks)
+pres = [i for i in ids if launches[i]["kernel"].startswith("k_mp_env_pre")]
+def step_start(p):
+    c = [i for i in ids if i < p and launches[i]["kernel"].startswith("k_mp_sched_class")]
+    return max(c) if c else None
+starts = [s for s in (step_start(p) for p in pres) if s is not None]
+a = starts[0]
+b = min(i for i in ids if i > a and launches[i]["kernel"].startswith("k_mp_env_post")) + 1      # ... through the step's k_mp_env_post
 step = [launches[i] for i in ids if a <= i < b]
 byk = {}
 for l in step:
@@ -31,8 +38,8 @@ envs = 32768
 out = {"envs": envs, "step_kernels": byk, "sum_kernel_ms_serialised": tot_ms, "dram_bytes_per_step": tot_b,
        "dram_bytes_per_env_tick": tot_b / envs,
        "share_of_step_time": {k: v["ms"] / tot_ms for k, v in byk.items()},
-       "note": "ncu --metrics gpu__time_duration.sum,dram__bytes_* --clock-control none: one aged env step (between two "
-               "k_mp_sched_class launches), kernels serialised and cold-cache, so shares are comparable, absolute times are not"}
+       "note": "ncu --metrics gpu__time_duration.sum,dram__bytes_* --clock-control none: one aged env step (from the schedule "
+               "rebuild before k_mp_env_pre to the next one), kernels serialised and cold-cache, so shares are comparable, absolute times are not"}
 json.dump(out, open("gpurun_out/%s_traffic.json" % tag, "w"), indent=1)
 print(json.dumps({k: (v["launches"], round(v["ms"], 3), round(v["dram_bytes"] / 1e6, 1)) for k, v in byk.items()}))
 print("dram bytes per env-tick %.0f, sum of kernel times %.2f ms" % (tot_b / envs, tot_ms))
