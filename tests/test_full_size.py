@@ -85,14 +85,16 @@ def test_power_puzzle_8192_envs_is_deterministic_and_well_formed():
     assert np.array_equal(out[0][2], out[1][2])
 
 
-def test_results_do_not_depend_on_the_schedule(monkeypatch):
+@pytest.mark.parametrize("n,steps", [(32768, 45), (18950, 12), (2047, 12), (8197, 12)])
+def test_results_do_not_depend_on_the_schedule(n, steps, monkeypatch):
     """Every env of a 32768-env batch, 45 aged steps (flood fields, sprites, the dense scan path and the
     heavy group are all live by then): the default schedule (3 env groups on streams, heavy-first order, 32
     envs per CTA in frame lockstep) against the plainest one (one group, index order, one free-running warp
     per CTA) -- observations, rewards, dones and bookkeeping counters of ALL envs must be identical."""
     import torch
     from gymcity_b200.micropolis_env import MicropolisVecEnv
-    n, steps = 32768, 45
+    # 32 768: the headline batch; 18 950: just above the one-group threshold, last CTA partial; 2 047 / 8 197: three groups
+    # of 8- / 16-env chunks with a partial last chunk and a heavy group that is not a multiple of the chunk
 
     def run(envvars):
         for k, v in envvars.items():
@@ -105,10 +107,11 @@ def test_results_do_not_depend_on_the_schedule(monkeypatch):
         for t in range(steps):
             obs, rew, done, _ = env.step(torch.from_numpy(rng.integers(0, 20 * 256, n)))
             rsum += rew
-            if t % 15 == 14:
+            if t % 15 == 14 or t == steps - 1:
                 snaps.append((obs.clone(), done.clone()))
         ctr = env.micro.counters()
         maps = [env.micro.engine.get(i, "MPF_MAP").copy() for i in (0, 777, n - 1)]
+        assert int(ctr[:, 4].min()) == steps == int(ctr[:, 4].max())          # every env stepped exactly `steps` times
         env.close()
         for k in envvars:
             monkeypatch.delenv(k)
