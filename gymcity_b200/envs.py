@@ -54,6 +54,59 @@ class BatchedVecEnv:
         self.env.close()
 
 
+class VecPyTorchFrameStack:
+    """envs.py:406-456 for nstack > 1: the last `nstack` observations of every env along the channel axis, newest
+    last; an env that finished (and was auto-reset) keeps only the observation of its new episode.  Batch tensors
+    on the env's device, no per-env loop."""
+
+    def __init__(self, venv, nstack, device=None):
+        import torch
+        self.venv, self.nstack = venv, int(nstack)
+        self.num_envs, self.action_space, self.device = venv.num_envs, venv.action_space, device
+        wos = venv.observation_space
+        self.shape_dim0 = wos.shape[0]
+        self.observation_space = spaces.Box(-1, 1, (wos.shape[0] * self.nstack,) + tuple(wos.shape[1:]), dtype=np.float32)
+        self.stacked_obs = torch.zeros((venv.num_envs,) + self.observation_space.shape, device=device)
+
+    def _push(self, obs, news=None):
+        import torch
+        c = self.shape_dim0
+        self.stacked_obs[:, :-c] = self.stacked_obs[:, c:].clone()
+        if news is not None:
+            keep = 1.0 - torch.as_tensor(np.asarray(news), dtype=torch.float32).to(self.stacked_obs.device)
+            self.stacked_obs[:, :-c] *= keep.reshape(-1, 1, 1, 1)
+        self.stacked_obs[:, -c:] = obs
+        return self.stacked_obs
+
+    def step_async(self, actions):
+        self.venv.step_async(actions)
+
+    def step_wait(self):
+        obs, rews, news, infos = self.venv.step_wait()
+        return self._push(obs, news), rews, news, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def reset(self):
+        obs = self.venv.reset()
+        self.stacked_obs.zero_()
+        return self._push(obs)
+
+    def close(self):
+        self.venv.close()
+
+    def get_param_bounds(self):
+        return self.venv.get_param_bounds()
+
+    def set_param_bounds(self, bounds):
+        return self.venv.set_param_bounds(bounds)
+
+    def set_params(self, params):
+        return self.venv.set_params(params)
+
+
 def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, add_timestep, device, allow_early_resets,
                   num_frame_stack=None, args=None):
     """envs.py:270-308 for the envs of this package; `args` carries the reference's CLI fields
@@ -83,9 +136,10 @@ def make_vec_envs(env_name, seed, num_processes, gamma, log_dir, add_timestep, d
     if g('extinction_type') is not None:                    # envs.py:255-257
         from .wrappers import Extinguisher
         env = Extinguisher(env, g('extinction_type'), g('extinction_prob', 0.1), seed=seed)
-    if num_frame_stack not in (None, 1):
-        raise NotImplementedError("frame stacking > 1 is not used by the reference's Micropolis runs")
-    return BatchedVecEnv(env, device)
+    venv = BatchedVecEnv(env, device)
+    if num_frame_stack not in (None, 1):                    # envs.py:301-303
+        return VecPyTorchFrameStack(venv, num_frame_stack, device)
+    return venv
 
 
 class RolloutStorage:

@@ -149,3 +149,63 @@ def test_views_keep_the_handle_alive_until_released():
     del o
     gc.collect()
     assert g._h is None
+
+
+def test_frame_stack_matches_the_reference_wrapper_logic():
+    """VecPyTorchFrameStack(nstack = 3) against a literal per-env restatement of envs.py:425-443 on a scripted venv."""
+    from gymcity_b200.envs import VecPyTorchFrameStack
+    N, C, W = 5, 2, 3
+    g = torch.Generator().manual_seed(1)
+    script = [(torch.rand(N, C, W, W, generator=g), np.array([(i + t) % 4 == 0 for i in range(N)])) for t in range(9)]
+
+    class Venv:
+        num_envs, action_space = N, spaces.Discrete(4)
+        observation_space = spaces.Box(-1, 1, (C, W, W), dtype=np.float32)
+        t = 0
+        def reset(self):
+            self.t = 0
+            return script[0][0]
+        def step_async(self, a):
+            self.t += 1
+        def step_wait(self):
+            o, d = script[self.t]
+            return o, torch.zeros(N, 1), d, [{} for _ in range(N)]
+        def close(self):
+            pass
+
+    fs = VecPyTorchFrameStack(Venv(), 3, torch.device("cpu"))
+    assert fs.observation_space.shape == (3 * C, W, W)
+    ref = torch.zeros(N, 3 * C, W, W)
+    ref[:, -C:] = script[0][0]
+    assert torch.equal(fs.reset(), ref)
+    for t in range(1, 9):
+        obs, rew, news, infos = fs.step(torch.zeros(N, 1, dtype=torch.long))
+        ref[:, :-C] = ref[:, C:].clone()
+        for i, new in enumerate(script[t][1]):
+            if new:
+                ref[i] = 0
+        ref[:, -C:] = script[t][0]
+        assert torch.equal(obs, ref) and np.array_equal(news, script[t][1])
+
+
+@pytest.mark.gpu
+def test_make_vec_envs_frame_stack_2():
+    from gymcity_b200.envs import make_vec_envs
+    N = 4
+    args = types.SimpleNamespace(map_width=16, max_step=5, random_terrain=True)
+    dev = torch.device("cuda", 0)
+    a = make_vec_envs('MicropolisEnv-v0', 3, N, 0.99, None, False, dev, True, num_frame_stack=2, args=args)
+    b = make_vec_envs('MicropolisEnv-v0', 3, N, 0.99, None, False, dev, True, args=args)
+    assert a.observation_space.shape == (64, 16, 16)
+    o, prev = a.reset(), b.reset().clone()
+    assert torch.equal(o[:, 32:], prev) and not o[:, :32].any()
+    rng = np.random.default_rng(0)
+    for t in range(8):
+        act = torch.from_numpy(rng.integers(0, 20 * 256, (N, 1))).to(dev)
+        o, _, done, _ = a.step(act)
+        ob, _, done_b, _ = b.step(act)
+        assert np.array_equal(done, done_b) and torch.equal(o[:, 32:], ob)
+        keep = torch.from_numpy(~done).to(dev).reshape(N, 1, 1, 1)
+        assert torch.equal(o[:, :32], prev * keep)
+        prev = ob.clone()
+    a.close(); b.close()
