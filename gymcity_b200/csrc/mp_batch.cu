@@ -54,6 +54,7 @@ struct MpBatch {
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
+    int pre_simt;                  // the action kernel runs one THREAD per env, four envs to a warp (k_mp_env_pre_t; MPB_PRE_SIMT=0: a warp per env)
     int resched_mid;               // rebuild the order between the two simTicks of a one-group step (MPB_RESCHED_MID=0: off)
     int timing;                    // MPB_TIMING: events at the phase boundaries of a one-group step (mpb_step_phase_times)
     cudaEvent_t ev_ph[6];
@@ -672,6 +673,58 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
     unstage_scalars(e, sw);
 }
 
+// The same step part with one THREAD per env, four envs to a warp: gym_step_pre and everything below it (TileMap
+// bookkeeping, toolDown, connect / fixZone, the tool overlay) is single-lane code without a warp collective in it, so
+// lanes 0..3 of a warp can run it for four different envs (in tool order: the same tool).  The lanes share next to
+// nothing -- 16 or 32 envs per warp take 16 or 32 times as long as one, also when ordered by (tool, zone at the
+// target) -- but a warp that interleaves four diverged instruction streams hides their latencies from one another, and
+// the kernel runs on a quarter of the warps: 1.91 -> 1.51 ms for 32 768 envs (2 envs 1.71, 8 envs 1.56, 16 envs 2.89 ms;
+// profiles/r02_notes.md).  Scalars: staged per thread in dynamic shared memory, copied in and out by the whole warp
+// (coalesced); the tool overlay stays in the env block's scratch.
+constexpr int PRE_T = 128;                      // threads per CTA
+constexpr int PRE_L = 4;                        // lanes of every warp that take an env each
+constexpr int PRE_ENVS = (PRE_T / 32) * PRE_L;  // envs per CTA
+__global__ void __launch_bounds__(PRE_T)
+k_mp_env_pre_t(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
+               const int64_t *actions, int static_build, const int *perm, GroupGeom q, const uint8_t *mask)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = (blockIdx.x * (PRE_T / 32) + warp) * PRE_L + lane;
+    uint32_t *wsw = reinterpret_cast<uint32_t *>(mp_dyn_smem) + (size_t)warp * PRE_L * SCAL_WORDS;
+    int env = -1;
+    if (lane < PRE_L && idx < q.count) {
+        const int slot = geom_slot(q, idx);
+        if (slot < n_envs) {
+            env = perm ? perm[slot] : slot;
+            if (mask && !mask[env]) env = -1;
+        }
+    }
+    MP_NOUNROLL for (int k = 0; k < PRE_L; k++) {
+        const int ek = __shfl_sync(0xffffffffu, env, k);
+        if (ek < 0) continue;
+        const uint32_t *gs = reinterpret_cast<const uint32_t *>(blocks + (size_t)ek * ENV_STRIDE + EnvLayout::SCALARS);
+        for (int i = lane; i < SCAL_WORDS; i += 32) wsw[k * SCAL_WORDS + i] = gs[i];
+    }
+    __syncwarp();
+    if (env >= 0) {
+        Env e;
+        bind_env(e, blocks + (size_t)env * ENV_STRIDE);
+        e.s = reinterpret_cast<Scalars *>(wsw + lane * SCAL_WORDS);
+        e.anim = anim;
+        e.c.red = nullptr;
+        Gym gy;
+        bind_gym(gy, shadow + (size_t)env * stride, &cfg);
+        gym_step_pre(e, gy, actions[env], static_build != 0);
+    }
+    __syncwarp();
+    MP_NOUNROLL for (int k = 0; k < PRE_L; k++) {
+        const int ek = __shfl_sync(0xffffffffu, env, k);
+        if (ek < 0) continue;
+        uint32_t *gs = reinterpret_cast<uint32_t *>(blocks + (size_t)ek * ENV_STRIDE + EnvLayout::SCALARS);
+        for (int i = lane; i < SCAL_WORDS; i += 32) gs[i] = wsw[k * SCAL_WORDS + i];
+    }
+}
+
 // MicropolisEnv.step, part 3 (env.py:468-540): observation, metrics, reward, done
 __global__ void __launch_bounds__(MP_THREADS)
 k_mp_env_post(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
@@ -972,6 +1025,9 @@ mpb_handle mpb_create(int n_envs, int device)
     cudaEventCreate(&b->ev_ar0); cudaEventCreate(&b->ev_ar1);
     b->timing = getenv("MPB_TIMING") != NULL;
     b->resched_mid = getenv("MPB_RESCHED_MID") ? atoi(getenv("MPB_RESCHED_MID")) : 1;
+    // 1: the tool-ordered action kernel of one-group steps, 2: the action kernels of multi-group steps as well (a few
+    // thousand envs in all are better off with a warp each: 2 048 envs on the 120x100 window 331 k against 328 k)
+    b->pre_simt = getenv("MPB_PRE_SIMT") ? atoi(getenv("MPB_PRE_SIMT")) : (n_envs >= 4096 ? 2 : 1);
 
     for (int i = 0; i < 6; i++) cudaEventCreate(&b->ev_ph[i]);
     if (const char *sc = getenv("MPB_SCHED")) b->use_sched = atoi(sc) != 0;
@@ -1704,9 +1760,17 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             size_t bytes = b->sort_tmp_bytes;
             const cudaError_t se = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, k32, k32o, b->sval, b->perm_pre, n, 0, 5, gs);
             if (se != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = se;
-            k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
-                                                     actions_dev, static_build, b->perm_pre, q, mask_dev);
-        } else
+            if (b->pre_simt)
+                k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
+                    b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, static_build, b->perm_pre,
+                    q, mask_dev);
+            else
+                k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
+                                                         actions_dev, static_build, b->perm_pre, q, mask_dev);
+        } else if (b->pre_simt >= 2)
+            k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
+                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, static_build, perm, q, mask_dev);
+        else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);
         if (tm) cudaEventRecord(b->ev_ph[2], gs);
