@@ -273,8 +273,22 @@ def run_episode_and_venv(args, local, dev, K):
     venv = {"workload": "the same env through MicropolisVecEnv.step(actions (N,1) CUDA tensor) -> (obs, reward, done, "
                         "infos), device auto-reset on; wall clock, device sync at both ends",
             "value": E * K / dt, "unit": UNIT, "steps": K, "ms_per_step": dt * 1000.0 / K}
+    # the reference's own rhythm: every worker starts together and runs max_step ticks, so all envs are the same age
+    # and reset in the same step.  One whole episode, from the reset's first step to the step that resets everyone.
+    env.reset()
+    for i in range(2):                               # two steps of warm-up belong to the episode (ages 0, 1)
+        m._ck(m._L.mpb_env_step(m._h, acts[i % pool].data_ptr(), 0, sp))
+    torch.cuda.synchronize(dev)
+    ep3 = m.counters()[:, 16].sum()
+    n_sync = max_step + 1                            # one episode length (+1): contains the step that resets every env
+    total_ms, ms = time_steps(lambda i: m._ck(m._L.mpb_env_step(m._h, acts[(i + 2) % pool].data_ptr(), 0, sp)), n_sync, stream, dev)
+    ep4 = m.counters()[:, 16].sum()
+    sync = {"workload": "mp16 with episodes the way the reference's workers run them: all envs start together, max_step 200, "
+                        "the whole batch is reset on the device inside one step of the timed region (max_step + 1 consecutive steps timed)",
+            "value": E * n_sync / (total_ms / 1000.0), "unit": UNIT, "steps": n_sync, "ms_per_step": total_ms / n_sync,
+            "step_ms": ms_stats(ms), "resets_in_timed_region": int(ep4 - ep3), "flags": divergence_flags(m)}
     env.close()
-    return episode, venv
+    return episode, venv, sync
 
 
 def run_ours(args):
@@ -419,7 +433,7 @@ def run_ours(args):
         Kx = max(5, min(K, 20))
         extra = {}
         try:
-            extra["mp16_episode"], extra["mp16_venv_step"] = run_episode_and_venv(args, local, dev, Kx)
+            extra["mp16_episode"], extra["mp16_venv_step"], extra["mp16_episode_sync"] = run_episode_and_venv(args, local, dev, Kx)
             extra["mp120"] = run_extra_mp("mp120", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
             extra["mp120dense"] = run_extra_mp("mp120dense", args, local, dev, Kx, 10, min(4.0, args.cpu_seconds))
             extra["mp32puzzle"] = run_extra_mp("mp32puzzle", args, local, dev, Kx, 40, min(4.0, args.cpu_seconds))
