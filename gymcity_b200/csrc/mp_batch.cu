@@ -63,7 +63,7 @@ struct MpBatch {
     void *sort_tmp; size_t sort_tmp_bytes;
     int use_sched;
     int sms;                  // SMs of the device
-    int scan_block;           // k_mp_frames: map-scan phases 1..8 free-run inside a CTA (no frame lockstep among them)
+    int scan_block;           // k_mp_frames: phases after which there is no CTA barrier (bit mask; 0x00fe: the map-scan phases 1..8 free-run inside a CTA)
     unsigned int *prof;       // per-env per-frame cycles [n_envs][256] (profiling, mpb_frame_profile)
     cudaError_t launch_err;   // first error of a launch enqueued by launch_frames since the last check
     // per-episode seeds derived on the device (gym_episode_seed) and the device-side auto-reset of mpb_env_step*
@@ -307,7 +307,7 @@ k_mp_frames(uint8_t *blocks, const uint16_t *anim, int n_envs, int first, int co
         if (MP_PROF && go && lane == 0) prof[(size_t)env * 256 + prof_off + first + i] = dt;
         if (MP_FEPC > 1) {
             const int ph = (ph0 + i) & 15;
-            if (!(scan_block && ph >= 1 && ph <= 7)) __syncthreads();
+            if (!((scan_block >> ph) & 1)) __syncthreads();
         }
     }
     if (live) {
@@ -972,8 +972,9 @@ mpb_handle mpb_create(int n_envs, int device)
         cudaFuncSetAttribute(k_mp_frames<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
         cudaFuncSetAttribute(k_mp_frames<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(fp));
     }
-    b->scan_block = 1;
-    if (const char *fp = getenv("MPB_SCAN_BLOCK")) b->scan_block = atoi(fp) != 0;
+    b->scan_block = 0x00fe;                         // bit p set: no CTA barrier after a frame of phase p (phases 1..7)
+    if (const char *fp = getenv("MPB_SCAN_BLOCK")) b->scan_block = atoi(fp) != 0 ? 0x00fe : 0;
+    if (const char *fp = getenv("MPB_NOBAR_MASK")) b->scan_block = (int)strtol(fp, NULL, 0) & 0xffff;
     uint16_t anim[1024];
     for (int i = 0; i < 1024; i++) anim[i] = (uint16_t)i;
     for (int i = 0; i < kAnimPairCount; i++) anim[kAnimPairs[i][0]] = kAnimPairs[i][1];
