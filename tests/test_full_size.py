@@ -118,7 +118,8 @@ def test_results_do_not_depend_on_the_schedule(n, steps, monkeypatch):
         return snaps, rsum, ctr, maps
 
     a = run({})
-    b = run({"MPB_GROUPS": "1", "MPB_FEPC": "1", "MPB_HEAVY_FEPC": "1", "MPB_SCHED": "0"})
+    # ... and the action kernel with a warp per env (k_mp_env_pre) instead of four envs to a warp (k_mp_env_pre_t)
+    b = run({"MPB_GROUPS": "1", "MPB_FEPC": "1", "MPB_HEAVY_FEPC": "1", "MPB_SCHED": "0", "MPB_PRE_SIMT": "0"})
     for (oa, da), (ob, db) in zip(a[0], b[0]):
         assert torch.equal(oa, ob) and torch.equal(da, db)
     assert torch.equal(a[1], b[1]) and np.array_equal(a[2], b[2])
