@@ -686,7 +686,8 @@ constexpr int PRE_L = 4;                        // lanes of every warp that take
 constexpr int PRE_ENVS = (PRE_T / 32) * PRE_L;  // envs per CTA
 __global__ void __launch_bounds__(PRE_T)
 k_mp_env_pre_t(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
-               const int64_t *actions, int static_build, const int *perm, GroupGeom q, const uint8_t *mask)
+               const int64_t *actions, const uint8_t *paint, int static_build, const int *perm, GroupGeom q,
+               const uint8_t *mask)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = (blockIdx.x * (PRE_T / 32) + warp) * PRE_L + lane;
@@ -714,7 +715,11 @@ k_mp_env_pre_t(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shado
         e.c.red = nullptr;
         Gym gy;
         bind_gym(gy, shadow + (size_t)env * stride, &cfg);
-        gym_step_pre(e, gy, actions[env], static_build != 0);
+        if (paint) {                                    // MicropolisPaintEnv.step, part 1 (paintenv.py:43-52)
+            gym_paint_action(e, gy, paint + (size_t)env * cfg.W * cfg.H);
+            e.s->totalFunds = cfg.init_funds;
+        } else
+            gym_step_pre(e, gy, actions[env], static_build != 0);
     }
     __syncwarp();
     MP_NOUNROLL for (int k = 0; k < PRE_L; k++) {
@@ -1750,7 +1755,10 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         const int grid = MP_GRID_N(q.count);
         if (grid <= 0) continue;
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
-        if (paint_dev)
+        if (paint_dev && b->pre_simt >= 2)
+            k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
+                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, NULL, paint_dev, 0, perm, q, NULL);
+        else if (paint_dev)
             k_mp_env_pre_paint<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
                                                            b->cfg, paint_dev, perm, q);
         else if (G == 1 && b->use_sched && !getenv("MPB_NO_PRE_SORT")) {
@@ -1763,14 +1771,14 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             if (se != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = se;
             if (b->pre_simt)
                 k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
-                    b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, static_build, b->perm_pre,
+                    b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, NULL, static_build, b->perm_pre,
                     q, mask_dev);
             else
                 k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                          actions_dev, static_build, b->perm_pre, q, mask_dev);
         } else if (b->pre_simt >= 2)
             k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
-                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, static_build, perm, q, mask_dev);
+                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, NULL, static_build, perm, q, mask_dev);
         else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);

@@ -44,9 +44,11 @@ def test_harness_paint_step_matches_oracle(seed, size, terrain):
 
 
 @pytest.mark.gpu
-def test_gpu_paint_env_matches_oracle():
+@pytest.mark.parametrize("pre_simt", ["1", "2"])       # 2: the paint action on a thread per env (k_mp_env_pre_t), as batches of >= 4096 envs run it
+def test_gpu_paint_env_matches_oracle(pre_simt, monkeypatch):
     import torch
     from gymcity_b200.micropolis_env import MicropolisPaintEnv
+    monkeypatch.setenv("MPB_PRE_SIMT", pre_simt)
     n, size, steps = 3, 12, 12
     seeds = np.arange(n) + 60
     env = MicropolisPaintEnv(n, size, max_step=10 ** 6, empty_start=False)
