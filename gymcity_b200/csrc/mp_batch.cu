@@ -54,6 +54,7 @@ struct MpBatch {
     int *ncls_dev, *ncls_host;     // number of non-empty schedule classes of the last rebuild (device / pinned host copy)
     int big_groups, big_frames;    // env groups / frames per launch of a single-class batch of >= 32-env CTAs
     int cur_frames;                // frames per launch of the env step being enqueued (0: frames_per_launch)
+    int pre_t, pre_l;              // its CTA size and envs per warp
     int pre_simt;                  // the action kernel runs one THREAD per env, four envs to a warp (k_mp_env_pre_t; MPB_PRE_SIMT=0: a warp per env)
     int resched_mid;               // rebuild the order between the two simTicks of a one-group step (MPB_RESCHED_MID=0: off)
     int timing;                    // MPB_TIMING: events at the phase boundaries of a one-group step (mpb_step_phase_times)
@@ -673,24 +674,23 @@ k_mp_env_pre(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow,
     unstage_scalars(e, sw);
 }
 
-// The same step part with one THREAD per env, four envs to a warp: gym_step_pre and everything below it (TileMap
+// The same step part with one THREAD per env, a few envs to a warp: gym_step_pre and everything below it (TileMap
 // bookkeeping, toolDown, connect / fixZone, the tool overlay) is single-lane code without a warp collective in it, so
-// lanes 0..3 of a warp can run it for four different envs (in tool order: the same tool).  The lanes share next to
+// the first lanes of a warp can run it for an env each (in tool order: the same tool).  The lanes share next to
 // nothing -- 16 or 32 envs per warp take 16 or 32 times as long as one, also when ordered by (tool, zone at the
-// target) -- but a warp that interleaves four diverged instruction streams hides their latencies from one another, and
-// the kernel runs on a quarter of the warps: 1.91 -> 1.51 ms for 32 768 envs (2 envs 1.71, 8 envs 1.56, 16 envs 2.89 ms;
+// target) -- but a warp that interleaves a few diverged instruction streams hides their latencies from one another:
+// 1.91 -> 1.37 ms for 32 768 envs (128-thread CTAs: 2 envs per warp 1.71, 4 envs 1.51, 8 envs 1.56, 16 envs 2.89 ms;
 // profiles/r02_notes.md).  Scalars: staged per thread in dynamic shared memory, copied in and out by the whole warp
 // (coalesced); the tool overlay stays in the env block's scratch.
-constexpr int PRE_T = 128;                      // threads per CTA
-constexpr int PRE_L = 4;                        // lanes of every warp that take an env each
-constexpr int PRE_ENVS = (PRE_T / 32) * PRE_L;  // envs per CTA
-__global__ void __launch_bounds__(PRE_T)
+constexpr int PRE_T = 64;                       // threads per CTA (MPB_PRE_T)
+constexpr int PRE_L = 6;                        // lanes of every warp that take an env each (MPB_PRE_L; 64 x 6: 1.37 ms, 128 x 4: 1.47 ms)
+__global__ void __launch_bounds__(256)
 k_mp_env_pre_t(uint8_t *blocks, const uint16_t *anim, int n_envs, uint8_t *shadow, int stride, GymCfg cfg,
                const int64_t *actions, const uint8_t *paint, int static_build, const int *perm, GroupGeom q,
-               const uint8_t *mask)
+               const uint8_t *mask, int PRE_L)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int idx = (blockIdx.x * (PRE_T / 32) + warp) * PRE_L + lane;
+    const int idx = (blockIdx.x * (blockDim.x / 32) + warp) * PRE_L + lane;
     uint32_t *wsw = reinterpret_cast<uint32_t *>(mp_dyn_smem) + (size_t)warp * PRE_L * SCAL_WORDS;
     int env = -1;
     if (lane < PRE_L && idx < q.count) {
@@ -1033,6 +1033,8 @@ mpb_handle mpb_create(int n_envs, int device)
     b->resched_mid = getenv("MPB_RESCHED_MID") ? atoi(getenv("MPB_RESCHED_MID")) : 1;
     // 1: the tool-ordered action kernel of one-group steps, 2: the action kernels of multi-group steps as well (a few
     // thousand envs in all are better off with a warp each: 2 048 envs on the 120x100 window 331 k against 328 k)
+    b->pre_t = getenv("MPB_PRE_T") ? atoi(getenv("MPB_PRE_T")) : PRE_T;
+    b->pre_l = getenv("MPB_PRE_L") ? atoi(getenv("MPB_PRE_L")) : PRE_L;
     b->pre_simt = getenv("MPB_PRE_SIMT") ? atoi(getenv("MPB_PRE_SIMT")) : (n_envs >= 4096 ? 2 : 1);
 
     for (int i = 0; i < 6; i++) cudaEventCreate(&b->ev_ph[i]);
@@ -1756,8 +1758,8 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
         if (grid <= 0) continue;
         if (G > 1) cudaStreamWaitEvent(gs, b->ev_start, 0);
         if (paint_dev && b->pre_simt >= 2)
-            k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
-                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, NULL, paint_dev, 0, perm, q, NULL);
+            k_mp_env_pre_t<<<(q.count + b->pre_t / 32 * b->pre_l - 1) / (b->pre_t / 32 * b->pre_l), b->pre_t, b->pre_t / 32 * b->pre_l * SCAL_BYTES, gs>>>(
+                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, NULL, paint_dev, 0, perm, q, NULL, b->pre_l);
         else if (paint_dev)
             k_mp_env_pre_paint<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride,
                                                            b->cfg, paint_dev, perm, q);
@@ -1770,15 +1772,15 @@ static int env_step_impl(MpBatch *b, const int64_t *actions_dev, const uint8_t *
             const cudaError_t se = cub::DeviceRadixSort::SortPairs(b->sort_tmp, bytes, k32, k32o, b->sval, b->perm_pre, n, 0, 5, gs);
             if (se != cudaSuccess && b->launch_err == cudaSuccess) b->launch_err = se;
             if (b->pre_simt)
-                k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
+                k_mp_env_pre_t<<<(q.count + b->pre_t / 32 * b->pre_l - 1) / (b->pre_t / 32 * b->pre_l), b->pre_t, b->pre_t / 32 * b->pre_l * SCAL_BYTES, gs>>>(
                     b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, NULL, static_build, b->perm_pre,
-                    q, mask_dev);
+                    q, mask_dev, b->pre_l);
             else
                 k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                          actions_dev, static_build, b->perm_pre, q, mask_dev);
         } else if (b->pre_simt >= 2)
-            k_mp_env_pre_t<<<(q.count + PRE_ENVS - 1) / PRE_ENVS, PRE_T, PRE_ENVS * SCAL_BYTES, gs>>>(
-                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, NULL, static_build, perm, q, mask_dev);
+            k_mp_env_pre_t<<<(q.count + b->pre_t / 32 * b->pre_l - 1) / (b->pre_t / 32 * b->pre_l), b->pre_t, b->pre_t / 32 * b->pre_l * SCAL_BYTES, gs>>>(
+                b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg, actions_dev, NULL, static_build, perm, q, mask_dev, b->pre_l);
         else
             k_mp_env_pre<<<grid, MP_THREADS, MP_DYN_SMEM, gs>>>(b->blocks, b->anim, b->n_envs, b->shadow, b->shadow_stride, b->cfg,
                                                      actions_dev, static_build, perm, q, mask_dev);
