@@ -286,18 +286,18 @@ MPN int16_t land_pollution_value(const Env &e, int x, int y)       // zone.cpp:2
 MPN bool zone_plop(Env &e, int x, int y, int base)
 {
     MP_COV(zone_plop);
-    MP_NOUNROLL for (int z = 0; z < 9; z++) {
-        int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
-        if (inb(xx, yy)) {
-            int t = e.map()[tix(xx, yy)] & LOMASK;
-            if (t >= T_FLOOD && t < T_ROADBASE) return false;
+    // z = 0..8 in the reference's order: x fastest (xx = x + z % 3 - 1, yy = y + z / 3 - 1)
+    MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
+        MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++)
+            if (inb(xx, yy)) {
+                int t = e.map()[tix(xx, yy)] & LOMASK;
+                if (t >= T_FLOOD && t < T_ROADBASE) return false;
+            }
+    MP_NOUNROLL for (int yy = y - 1; yy <= y + 1; yy++)
+        MP_NOUNROLL for (int xx = x - 1; xx <= x + 1; xx++) {
+            if (inb(xx, yy)) mset(e, tix(xx, yy), (uint16_t)(base + BNCNBIT));
+            base++;
         }
-    }
-    MP_NOUNROLL for (int z = 0; z < 9; z++) {
-        int xx = x + (z % 3) - 1, yy = y + (z / 3) - 1;
-        if (inb(xx, yy)) mset(e, tix(xx, yy), (uint16_t)(base + BNCNBIT));
-        base++;
-    }
     set_zone_power(e, x, y);
     mset(e, tix(x, y), e.map()[tix(x, y)] | (ZONEBIT + BULLBIT));
     return true;
@@ -779,14 +779,15 @@ MPN void do_fire(Env &e, int x, int y)
             }
         }
     }
-    int16_t rate = 10;
-    int z = s8get(e.fireEff(), x, y);
-    if (z > 0) {
-        rate = 3;
-        if (z > 20) rate = 2;
-        if (z > 100) rate = 1;
-    }
-    if (rnd(e, rate) == 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
+    // getRandom(rate), rate = 10 / 3 / 2 / 1 by fire-station coverage: a literal range per branch (a runtime range
+    // costs a 16-bit division and a remainder subroutine call)
+    const int z = s8get(e.fireEff(), x, y);
+    int r;
+    if (z > 100) r = rnd(e, 1);
+    else if (z > 20) r = rnd(e, 2);
+    else if (z > 0) r = rnd(e, 3);
+    else r = rnd(e, 10);
+    if (r == 0) mset(e, tix(x, y), (uint16_t)random_rubble(e));
 }
 
 // [LEAD] disasters.cpp:375-405 doFlood
@@ -2260,7 +2261,11 @@ MPD int coop_bcast(Env &e, int v)
 MPD bool scan_due(int cyc, int si, int slow, int mid, int fast)
 {
     MP_COV(scan_due);
-    return si == 2 ? (cyc % fast) == 0 : (si == 1 ? (cyc % mid) == 0 : (cyc % slow) == 0);
+    // three remainders by literals (a multiply each) and a select: with the period selected first the compiler calls
+    // its 16-bit remainder subroutine, five times a cycle (1.3 % of the frame kernel's instructions)
+    const unsigned c = (unsigned)cyc;                       // simCycle is 0..1023
+    const bool f = (c % (unsigned)fast) == 0u, m = (c % (unsigned)mid) == 0u, sl = (c % (unsigned)slow) == 0u;
+    return si == 2 ? f : (si == 1 ? m : sl);
 }
 
 // [ALL] one phase of simulate() (simulate.cpp:122-268).  `phase` is uniform across the lanes.
@@ -2282,7 +2287,18 @@ MPD void simulate_phase(Env &e, int phase)
             if (!(S.simCycle & 1)) set_valves(e);
             clear_census_scalars(e);
         }
+#if MP_WARP_COOP
+        {   // 2 x 195 int16 (padded to 400 bytes each in EnvLayout): one 128-bit store per lane and map
+            static_assert(a16(N8 * 2) == 25 * 16, "station maps are cleared with 25 uint4 stores");
+            const int i = e.c.tid;
+            if (i < 25) {
+                reinterpret_cast<uint4 *>(e.fireSt())[i] = make_uint4(0u, 0u, 0u, 0u);
+                reinterpret_cast<uint4 *>(e.policeSt())[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+#else
         for (int i = e.c.tid; i < N8; i += e.c.n) { e.fireSt()[i] = 0; e.policeSt()[i] = 0; }
+#endif
         break;
     case 1: case 2: case 3: case 4: case 5: case 6: case 7: case 8:
         map_scan(e, (phase - 1) * WORLD_W / 8, phase * WORLD_W / 8);
