@@ -1213,12 +1213,15 @@ MPP void map_scan(Env &e, int x1, int x2)
     }
     MP_NOUNROLL for (int wb = w0; wb <= w1; wb += 32) {
         const int w = wb + lane;
+        // tiles in [i0, i1): only the first and the last word of the strip are cut, and the scan position moves by
+        // whole words (the serial lane finishes the word it takes), so the per-iteration mask is "words from wn on"
+        uint32_t edge = 0xffffffffu;
+        if (w == w0) edge &= 0xffffffffu << (i0 & 31);
+        if (w == w1 && (i1 & 31)) edge &= 0xffffffffu >> (32 - (i1 & 31));
+        if (w > w1) edge = 0u;
+        int wn = pos >> 5;                                  // first word not yet passed (pos is i0 or a word boundary)
         for (;;) {
-            uint32_t m = (w <= w1) ? e.need()[w] : 0u;
-            // keep tiles in [pos, i1)
-            const int lo = pos - w * 32, hi = i1 - w * 32;
-            if (lo > 0) m &= (lo >= 32) ? 0u : (0xffffffffu << lo);
-            if (hi < 32) m &= (hi <= 0) ? 0u : (0xffffffffu >> (32 - hi));
+            const uint32_t m = (w >= wn && edge) ? (e.need()[w] & edge) : 0u;
             const unsigned any = __ballot_sync(0xffffffffu, m != 0);
             if (!any) break;
             const int wi = wb + __ffs(any) - 1;             // first word with work: the serial lane takes all of it
@@ -1239,6 +1242,7 @@ MPP void map_scan(Env &e, int x1, int x2)
             }
             __syncwarp();
             pos = (wi + 1) * 32;
+            wn = wi + 1;
         }
     }
 #else
@@ -2261,11 +2265,15 @@ MPD int coop_bcast(Env &e, int v)
 MPD bool scan_due(int cyc, int si, int slow, int mid, int fast)
 {
     MP_COV(scan_due);
-    // three remainders by literals (a multiply each) and a select: with the period selected first the compiler calls
-    // its 16-bit remainder subroutine, five times a cycle (1.3 % of the frame kernel's instructions)
-    const unsigned c = (unsigned)cyc;                       // simCycle is 0..1023
-    const bool f = (c % (unsigned)fast) == 0u, m = (c % (unsigned)mid) == 0u, sl = (c % (unsigned)slow) == 0u;
-    return si == 2 ? f : (si == 1 ? m : sl);
+    // cyc % period == 0 without a runtime remainder (the compiler selects the period first and then emits its generic
+    // 32-bit remainder -- int-to-float, reciprocal, two corrections -- or calls the 16-bit subroutine, five times a
+    // cycle): simCycle < 1024 and every period <= 20, so floor(c / d) = (c * ceil(2^16 / d)) >> 16 exactly
+    // (c * (d * ceil(2^16 / d) - 2^16) < 1024 * 20 < 2^16), with the reciprocals folded from the literals
+    const unsigned c = (unsigned)cyc;
+    const unsigned d = si == 2 ? (unsigned)fast : (si == 1 ? (unsigned)mid : (unsigned)slow);
+    const unsigned r = si == 2 ? (65535u + (unsigned)fast) / (unsigned)fast
+                               : (si == 1 ? (65535u + (unsigned)mid) / (unsigned)mid : (65535u + (unsigned)slow) / (unsigned)slow);
+    return c - ((c * r) >> 16) * d == 0u;
 }
 
 // [ALL] one phase of simulate() (simulate.cpp:122-268).  `phase` is uniform across the lanes.

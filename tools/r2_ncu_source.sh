@@ -14,7 +14,7 @@ cubin=$(ls /tmp/cub_$tag/*mp_batch*.cubin | head -1)
 nvdisasm -g -c $cubin > /tmp/ncu_${tag}_dis.txt 2>/dev/null
 for col in "# Samples" "Instructions Executed" "stall_no_inst" "stall_long_sb" "stall_barrier"; do
     echo "==== top source lines by $col ====" >> gpurun_out/${tag}_k_mp_frames_by_line.txt
-    python tools/ncu_by_line.py /tmp/ncu_${tag}_src.csv /tmp/ncu_${tag}_dis.txt k_mp_framesILi32E "$col" 45 >> gpurun_out/${tag}_k_mp_frames_by_line.txt 2>&1
+    python tools/ncu_by_line.py /tmp/ncu_${tag}_src.csv /tmp/ncu_${tag}_dis.txt k_mp_framesILi32E "$col" 90 >> gpurun_out/${tag}_k_mp_frames_by_line.txt 2>&1
 done
 python tools/ncu_by_function.py /tmp/ncu_${tag}_src.csv /tmp/ncu_${tag}_dis.txt k_mp_frames k_mp_framesILi32E > gpurun_out/${tag}_k_mp_frames_by_function.txt 2>&1
 ls -la /tmp/ncu_$tag.ncu-rep /tmp/ncu_${tag}_src.csv | awk '{print $5, $9}'
