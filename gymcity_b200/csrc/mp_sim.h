@@ -14,12 +14,12 @@ namespace mp {
 #define S (*e.s)
 
 MPN void city_evaluation(Env &e);                       // mp_eval part below
-MPN void move_objects(Env &e);                          // mp_sprites.h
+MPR void move_objects(Env &e);                          // mp_sprites.h
 MPN int do_disasters(Env &e, bool defer_quake);         // mp_sprites.h
 MPN void make_earthquake_coop(Env &e);                  // mp_sprites.h
 MPN void make_explosion_at(Env &e, int x, int y);       // mp_sprites.h
 MPN void make_explosion(Env &e, int x, int y);          // mp_sprites.h
-MPN void generate_train(Env &e, int x, int y);          // mp_sprites.h
+MPN void generate_train_make(Env &e, int x, int y);     // mp_sprites.h
 MPN void generate_ship(Env &e);                         // mp_sprites.h
 MPN void generate_plane(Env &e, int x, int y);          // mp_sprites.h
 MPN void generate_copter(Env &e, int x, int y);         // mp_sprites.h
@@ -910,6 +910,14 @@ MPQ void do_road(Env &e, int x, int y)
         if (td > 0) z |= ANIMBIT;
         mset(e, tix(x, y), (uint16_t)z);
     }
+}
+
+// sprite.cpp:1831-1837 generateTrain: the guard is inline (every rail tile of every scan asks), the sprite is made out of line
+MPD void generate_train(Env &e, int x, int y)
+{
+    MP_COV(generate_train);
+    const int ti = S.globalSprites[SPR_TRAIN];                  // getSprite (sprite.cpp:336-344)
+    if (S.totalPop > 20 && (ti < 0 || e.spr()[ti].frame == 0) && rnd(e, 25) == 0) generate_train_make(e, x, y);
 }
 
 // [LEAD] simulate.cpp:1005-1037 doRail
@@ -2374,7 +2382,7 @@ MPP void simulate(Env &e)
 // simulation phase and the sprite pass (each half then runs the same code in every warp).
 // Returns phase + 1 if the phase was simulated, 0 if the speed divider skipped it.
 // [ALL] one simulation phase + its closing barrier, out of line once (the frame loops call it)
-MPN void sim_phase(Env &e, int phase)
+MPR void sim_phase(Env &e, int phase)
 {
     MP_COV(sim_phase);
     simulate_phase(e, phase);

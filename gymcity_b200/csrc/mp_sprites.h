@@ -229,7 +229,7 @@ MPD void start_fire_in_zone(Env &e, int x, int y, int ch)
 }
 
 // [LEAD] sprite.cpp:1709-1746 destroyMapTile
-MPN void destroy_map_tile(Env &e, int ox, int oy)
+MPS void destroy_map_tile(Env &e, int ox, int oy)
 {
     MP_COV(destroy_map_tile);
     int x = (int16_t)(ox >> 4), y = (int16_t)(oy >> 4);
@@ -295,7 +295,7 @@ MPN void do_train(Env &e, int si)
 }
 
 // [LEAD] sprite.cpp:680-770 doCopterSprite
-MPN void do_copter(Env &e, int si)
+MPS void do_copter(Env &e, int si)
 {
     MP_COV(do_copter);
     Sprite &sp = e.spr()[si];
@@ -331,7 +331,7 @@ MPN void do_copter(Env &e, int si)
 }
 
 // [LEAD] sprite.cpp:777-850 doAirplaneSprite
-MPN void do_airplane(Env &e, int si)
+MPS void do_airplane(Env &e, int si)
 {
     MP_COV(do_airplane);
     const int16_t CDx[12] = { 0, 0, 6, 8, 6, 0, -6, -8, -6, 8, 8, 8 };
@@ -370,7 +370,7 @@ MPN void do_airplane(Env &e, int si)
 }
 
 // [LEAD] sprite.cpp:857-984 doShipSprite
-MPN void do_ship(Env &e, int si)
+MPS void do_ship(Env &e, int si)
 {
     MP_COV(do_ship);
     Sprite &sp = e.spr()[si];
@@ -532,7 +532,7 @@ MPN void do_monster(Env &e, int si)
 }
 
 // [LEAD] sprite.cpp:1188-1248 doTornadoSprite
-MPN void do_tornado(Env &e, int si)
+MPS void do_tornado(Env &e, int si)
 {
     MP_COV(do_tornado);
     Sprite &sp = e.spr()[si];
@@ -574,7 +574,7 @@ MPN void do_explosion(Env &e, int si)
 // [LEAD] sprite.cpp:548-600 moveObjects.  Every sprite is created with name "" so a sprite whose
 // frame is 0 is destroyed when the walk reaches it.  The bus sprite is never generated
 // (generateBus call commented out, simulate.cpp:1062).
-MPN void move_objects(Env &e)
+MPR void move_objects(Env &e)
 {
     MP_COV(move_objects);
     if (!S.simSpeed) return;
@@ -601,11 +601,9 @@ MPN void move_objects(Env &e)
 }
 
 // ------------------------------------------------------------------ sprite generators
-MPN void generate_train(Env &e, int x, int y)                  // sprite.cpp:1831-1837
+MPN void generate_train_make(Env &e, int x, int y)             // sprite.cpp:1831-1837 (guard: generate_train, mp_sim.h)
 {
-    MP_COV(generate_train);
-    if (S.totalPop > 20 && get_sprite(e, SPR_TRAIN) < 0 && rnd(e, 25) == 0)
-        make_sprite(e, SPR_TRAIN, (x << 4) - 39, (y << 4) + 6);
+    make_sprite(e, SPR_TRAIN, (x << 4) - 39, (y << 4) + 6);
 }
 
 MPN void generate_ship(Env &e)                                 // sprite.cpp:1854-1898

@@ -27,17 +27,23 @@
 #else
 #define MPP __device__ __forceinline__
 #endif
-// MPQ: per-tile dispatch targets; out of line unless -DMP_INLINE_TILE
-#if defined(MP_INLINE_TILE)
-#define MPQ __device__ __forceinline__
-#else
+// MPQ: the per-tile dispatch targets (doZone, doRoad, doRail) and the per-frame entry points (sim_phase, moveObjects).
+// Inline: a call on the serial lane is a jump into code the SM has not got -- one call per 200 instructions was worth
+// 9 % of the step (profiles/r02_notes.md); out of line only for per-function profiles.
+#if defined(MP_PROFILE_SPLIT)
 #define MPQ __device__ __noinline__
+#else
+#define MPQ __device__ __forceinline__
 #endif
+#define MPR MPQ
+#define MPS MPQ         // the sprite handlers moveObjects dispatches to, destroyMapTile
 #else
 // host harness: the 128-bit vector type the device code moves cells with
 struct uint4 { unsigned int x, y, z, w; };
 inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { uint4 v = { x, y, z, w }; return v; }
 #define MPQ inline
+#define MPR inline
+#define MPS inline
 #define MPP inline
 #define MPD inline
 #define MPN inline
@@ -429,9 +435,10 @@ MPD int rnd16s(Env &e)
     if (i > 0x7fff) i = 0x7fff - i;
     return i;
 }
-// getRandom(range): the rejection loop lives out of line once; the inline wrapper only folds the
-// (almost always constant) range into the two numbers the loop needs.
-MPN int rnd_reject(Env &e, int maxMultiple)
+// getRandom(range).  The rejection loop is inline: a call on the serial lane costs far more than the ten instructions
+// it saves at each site (out of line: 1.93 M, inline: 2.04 M env-ticks/s; profiles/r02_notes.md); the inline wrapper
+// folds the (almost always literal) range into the two numbers the loop needs.
+MPD int rnd_reject(Env &e, int maxMultiple)
 {
     int r;
     do {

@@ -19,3 +19,5 @@ done
 python tools/ncu_by_function.py /tmp/ncu_${tag}_src.csv /tmp/ncu_${tag}_dis.txt k_mp_frames k_mp_framesILi32E > gpurun_out/${tag}_k_mp_frames_by_function.txt 2>&1
 ls -la /tmp/ncu_$tag.ncu-rep /tmp/ncu_${tag}_src.csv | awk '{print $5, $9}'
 head -30 gpurun_out/${tag}_k_mp_frames_by_line.txt
+python tools/ncu_calls.py /tmp/ncu_${tag}_src.csv /root/repo/gymcity_b200/libgymcity_b200.so k_mp_framesILi32ELb0 60 > gpurun_out/${tag}_k_mp_frames_calls.txt 2>&1
+head -40 gpurun_out/${tag}_k_mp_frames_calls.txt
