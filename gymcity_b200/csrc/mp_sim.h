@@ -32,7 +32,7 @@ MPD int boat_distance(Env &e, int x, int y);            // mp_sprites.h
 MPN void set_valves(Env &e)
 {
     MP_COV(set_valves);
-    const int16_t taxTable[21] = { 200, 150, 120, 100, 80, 50, 30, 0, -10, -40, -100,
+    MP_TAB int16_t taxTable[21] = { 200, 150, 120, 100, 80, 50, 30, 0, -10, -40, -100,
         -150, -200, -250, -300, -350, -400, -450, -500, -550, -600 };
     const float extMarketParamTable[3] = { 1.2f, 1.1f, 0.98f };
     const float birthRate = 0.02f, laborBaseMax = 1.3f, internalMarketDenom = 3.7f;
@@ -134,8 +134,8 @@ MPD bool road_test(int mv)                                // traffic.cpp:489-503
 MPD bool find_perimeter_road(Env &e, int &x, int &y)
 {
     MP_COV(find_perimeter_road);
-    const int8_t px[12] = { -1, 0, 1, 2, 2, 2, 1, 0, -1, -2, -2, -2 };
-    const int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
+    MP_TAB int8_t px[12] = { -1, 0, 1, 2, 2, 2, 1, 0, -1, -2, -2, -2 };
+    MP_TAB int8_t py[12] = { -2, -2, -2, -1, 0, 1, 2, 2, 2, 1, 0, -1 };
     MP_NOUNROLL for (int z = 0; z < 12; z++) {
         int tx = x + px[z], ty = y + py[z];
         if (inb(tx, ty) && road_test(e.map()[tix(tx, ty)])) {
@@ -185,8 +185,8 @@ MPD int try_go(Env &e, int x, int y, int dirLast)
 MPD bool drive_done(const Env &e, int x, int y, int dest)
 {
     MP_COV(drive_done);
-    const int lo[3] = { T_COMBASE, T_LHTHR, T_LHTHR };
-    const int hi[3] = { T_NUCLEAR, T_PORT, T_COMBASE };
+    MP_TAB int lo[3] = { T_COMBASE, T_LHTHR, T_LHTHR };
+    MP_TAB int hi[3] = { T_NUCLEAR, T_PORT, T_COMBASE };
     int l = lo[dest], h = hi[dest], z;
     if (y > 0) { z = e.map()[tix(x, y - 1)] & LOMASK; if (z >= l && z <= h) return true; }
     if (x < WORLD_W - 1) { z = e.map()[tix(x + 1, y)] & LOMASK; if (z >= l && z <= h) return true; }
@@ -323,7 +323,7 @@ MPD int16_t ind_zone_pop(int t) { return t == T_INDCLR ? (int16_t)0 : (int16_t)(
 MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:493-517
 {
     MP_COV(eval_lot);
-    const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
+    MP_TAB int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     int16_t z = (int16_t)(e.map()[tix(x, y)] & LOMASK);
     if (z && (z < T_RESBASE || z > T_RESBASE + 8)) return -1;
     int16_t score = 1;
@@ -339,7 +339,7 @@ MPD int16_t eval_lot(const Env &e, int x, int y)                   // zone.cpp:4
 MPN void build_house(Env &e, int x, int y, int value)
 {
     MP_COV(build_house);
-    const int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
+    MP_TAB int8_t zx[9] = { 0, -1, 0, 1, -1, 1, -1, 0, 1 }, zy[9] = { 0, -1, -1, -1, 0, 0, 1, 1, 1 };
     int16_t best = 0, hscore = 0;
     MP_NOUNROLL for (int16_t z = 1; z < 9; z++) {
         int xx = x + zx[z], yy = y + zy[z];
@@ -404,7 +404,7 @@ MPN void do_res_in(Env &e, int x, int y, int pop, int value)
 MPN void do_res_out(Env &e, int x, int y, int pop, int value)
 {
     MP_COV(do_res_out);
-    const int8_t brdr[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
+    MP_TAB int8_t brdr[9] = { 0, 3, 6, 1, 4, 7, 2, 5, 8 };
     if (!pop) return;
     if (pop > 16) {
         res_plop(e, x, y, (pop - 24) / 8, value);
@@ -532,11 +532,11 @@ MPN void do_commercial(Env &e, int x, int y, bool zonePower)
 MPN void set_smoke(Env &e, int x, int y, bool zonePower)
 {
     MP_COV(set_smoke);
-    const uint8_t aniThis[8] = { 1, 0, 1, 1, 0, 0, 1, 1 };
-    const int8_t dx1[8] = { -1, 0, 1, 0, 0, 0, 0, 1 }, dy1[8] = { -1, 0, -1, -1, 0, 0, -1, -1 };
-    const int16_t aniTabB[8] = { 0, 0, 36, 44, 0, 0, 52, 60 };
-    const int16_t aniTabC[8] = { T_IND1, 0, T_IND2, T_IND4, 0, 0, T_IND6, T_IND8 };
-    const int16_t aniTabD[8] = { T_IND1, 0, T_IND3, T_IND5, 0, 0, T_IND7, T_IND9 };
+    MP_TAB uint8_t aniThis[8] = { 1, 0, 1, 1, 0, 0, 1, 1 };
+    MP_TAB int8_t dx1[8] = { -1, 0, 1, 0, 0, 0, 0, 1 }, dy1[8] = { -1, 0, -1, -1, 0, 0, -1, -1 };
+    MP_TAB int16_t aniTabB[8] = { 0, 0, 36, 44, 0, 0, 52, 60 };
+    MP_TAB int16_t aniTabC[8] = { T_IND1, 0, T_IND2, T_IND4, 0, 0, T_IND6, T_IND8 };
+    MP_TAB int16_t aniTabD[8] = { T_IND1, 0, T_IND3, T_IND5, 0, 0, T_IND7, T_IND9 };
     int t = e.map()[tix(x, y)] & LOMASK;
     if (t < T_IZB) return;
     int z = ((t - T_IZB) >> 3) & 7;
@@ -650,15 +650,15 @@ MPN void do_meltdown(Env &e, int x, int y)
 MPN void do_special_zone(Env &e, int x, int y, bool powerOn)
 {
     MP_COV(do_special_zone);
-    const int meltdownTable[3] = { 30000, 20000, 10000 };
+    MP_TAB int meltdownTable[3] = { 30000, 20000, 10000 };
     int t = e.map()[tix(x, y)] & LOMASK;
     switch (t) {
     case T_POWERPLANT: {
         S.coalPowerPop++;
         if ((S.cityTime & 7) == 0) repair_zone(e, x, y, T_POWERPLANT, 4);
         push_power_stack(e, x, y);
-        const int16_t sm[4] = { T_COALSMOKE1, T_COALSMOKE2, T_COALSMOKE3, T_COALSMOKE4 };
-        const int8_t dx[4] = { 1, 2, 1, 2 }, dy[4] = { -1, -1, 0, 0 };
+        MP_TAB int16_t sm[4] = { T_COALSMOKE1, T_COALSMOKE2, T_COALSMOKE3, T_COALSMOKE4 };
+        MP_TAB int8_t dx[4] = { 1, 2, 1, 2 }, dy[4] = { -1, -1, 0, 0 };
         MP_NOUNROLL for (int i = 0; i < 4; i++)
             tset(e, x + dx[i], y + dy[i], sm[i] | ANIMBIT | CONDBIT | PWRBIT | BURNBIT);
         return;
@@ -764,7 +764,7 @@ MPN void fire_zone(Env &e, int x, int y, int ch)
 MPN void do_fire(Env &e, int x, int y)
 {
     MP_COV(do_fire);
-    const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
+    MP_TAB int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, -1, 0, 1 };
     MP_NOUNROLL for (int z = 0; z < 4; z++) {
         if ((rnd16(e) & 7) == 0) {
             int xx = x + dx[z], yy = y + dy[z];
@@ -794,7 +794,7 @@ MPN void do_fire(Env &e, int x, int y)
 MPN void do_flood(Env &e, int x, int y)
 {
     MP_COV(do_flood);
-    const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
+    MP_TAB int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     if (S.floodCount > 0) {
         MP_NOUNROLL for (int z = 0; z < 4; z++) {
             if ((rnd16(e) & 7) == 0) {
@@ -818,15 +818,15 @@ MPN void do_flood(Env &e, int x, int y)
 MPN bool do_bridge(Env &e, int x, int y, int tile)
 {
     MP_COV(do_bridge);
-    const int8_t HDx[7] = { -2, 2, -2, -1, 0, 1, 2 }, HDy[7] = { -1, -1, 0, 0, 0, 0, 0 };
-    const int16_t HBRTAB[7] = { T_HBRDG1 | BULLBIT, T_HBRDG3 | BULLBIT, T_HBRDG0 | BULLBIT, T_RIVER,
+    MP_TAB int8_t HDx[7] = { -2, 2, -2, -1, 0, 1, 2 }, HDy[7] = { -1, -1, 0, 0, 0, 0, 0 };
+    MP_TAB int16_t HBRTAB[7] = { T_HBRDG1 | BULLBIT, T_HBRDG3 | BULLBIT, T_HBRDG0 | BULLBIT, T_RIVER,
         T_BRWH | BULLBIT, T_RIVER, T_HBRDG2 | BULLBIT };
-    const int16_t HBRTAB2[7] = { T_RIVER, T_RIVER, T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT,
+    MP_TAB int16_t HBRTAB2[7] = { T_RIVER, T_RIVER, T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT,
         T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT, T_HBRIDGE | BULLBIT };
-    const int8_t VDx[7] = { 0, 1, 0, 0, 0, 0, 1 }, VDy[7] = { -2, -2, -1, 0, 1, 2, 2 };
-    const int16_t VBRTAB[7] = { T_VBRDG0 | BULLBIT, T_VBRDG1 | BULLBIT, T_RIVER, T_BRWV | BULLBIT,
+    MP_TAB int8_t VDx[7] = { 0, 1, 0, 0, 0, 0, 1 }, VDy[7] = { -2, -2, -1, 0, 1, 2, 2 };
+    MP_TAB int16_t VBRTAB[7] = { T_VBRDG0 | BULLBIT, T_VBRDG1 | BULLBIT, T_RIVER, T_BRWV | BULLBIT,
         T_RIVER, T_VBRDG2 | BULLBIT, T_VBRDG3 | BULLBIT };
-    const int16_t VBRTAB2[7] = { T_VBRIDGE | BULLBIT, T_RIVER, T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT,
+    MP_TAB int16_t VBRTAB2[7] = { T_VBRIDGE | BULLBIT, T_RIVER, T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT,
         T_VBRIDGE | BULLBIT, T_VBRIDGE | BULLBIT, T_RIVER };
     if (tile == T_BRWV) {
         if (!(rnd16(e) & 3) && boat_distance(e, x, y) > 340)
@@ -880,7 +880,7 @@ MPN bool do_bridge(Env &e, int x, int y, int tile)
 MPQ void do_road(Env &e, int x, int y)
 {
     MP_COV(do_road);
-    const int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
+    MP_TAB int16_t densityTable[3] = { T_ROADBASE, T_LTRFBASE, T_HTRFBASE };
     S.roadTotal++;
     int mv = e.map()[tix(x, y)], tile = mv & LOMASK;
     if (S.roadEffect < (15 * MAX_ROAD_EFFECT / 16)) {

@@ -186,7 +186,7 @@ MPD bool sprite_not_in_bounds(const Sprite &sp)                // sprite.cpp:451
 MPD int16_t get_dir(Env &e, int ox, int oy, int dx_, int dy_)
 {
     MP_COV(get_dir);
-    const int16_t gd[13] = { 0, 3, 2, 1, 3, 4, 5, 7, 6, 5, 7, 8, 1 };
+    MP_TAB int16_t gd[13] = { 0, 3, 2, 1, 3, 4, 5, 7, 6, 5, 7, 8, 1 };
     int dispX = dx_ - ox, dispY = dy_ - oy, z;
     if (dispX < 0) z = dispY < 0 ? 11 : 8;
     else z = dispY < 0 ? 2 : 5;
@@ -269,9 +269,9 @@ MPN void do_train(Env &e, int si)
 {
     MP_COV(do_train);
     Sprite &sp = e.spr()[si];
-    const int16_t Cx[4] = { 0, 16, 0, -16 }, Cy[4] = { -16, 0, 16, 0 };
-    const int16_t Dx[5] = { 0, 4, 0, -4, 0 }, Dy[5] = { -4, 0, 4, 0, 0 };
-    const int16_t pic2[5] = { 1, 2, 1, 2, 5 };
+    MP_TAB int16_t Cx[4] = { 0, 16, 0, -16 }, Cy[4] = { -16, 0, 16, 0 };
+    MP_TAB int16_t Dx[5] = { 0, 4, 0, -4, 0 }, Dy[5] = { -4, 0, 4, 0, 0 };
+    MP_TAB int16_t pic2[5] = { 1, 2, 1, 2, 5 };
     if (sp.frame == 3 || sp.frame == 4) sp.frame = pic2[sp.dir];
     sp.x = (int16_t)(sp.x + Dx[sp.dir]);
     sp.y = (int16_t)(sp.y + Dy[sp.dir]);
@@ -299,7 +299,7 @@ MPS void do_copter(Env &e, int si)
 {
     MP_COV(do_copter);
     Sprite &sp = e.spr()[si];
-    const int16_t CDx[9] = { 0, 0, 3, 5, 3, 0, -3, -5, -3 }, CDy[9] = { 0, -5, -3, 0, 3, 5, 3, 0, -3 };
+    MP_TAB int16_t CDx[9] = { 0, 0, 3, 5, 3, 0, -3, -5, -3 }, CDy[9] = { 0, -5, -3, 0, 3, 5, 3, 0, -3 };
     if (sp.soundCount > 0) sp.soundCount--;
     if (sp.control < 0) {
         if (sp.count > 0) sp.count--;
@@ -334,8 +334,8 @@ MPS void do_copter(Env &e, int si)
 MPS void do_airplane(Env &e, int si)
 {
     MP_COV(do_airplane);
-    const int16_t CDx[12] = { 0, 0, 6, 8, 6, 0, -6, -8, -6, 8, 8, 8 };
-    const int16_t CDy[12] = { 0, -8, -6, 0, 6, 8, 6, 0, -6, 0, 0, 0 };
+    MP_TAB int16_t CDx[12] = { 0, 0, 6, 8, 6, 0, -6, -8, -6, 8, 8, 8 };
+    MP_TAB int16_t CDy[12] = { 0, -8, -6, 0, 6, 8, 6, 0, -6, 0, 0, 0 };
     int16_t z = e.spr()[si].frame;
     if ((S.spriteCycle % 5) == 0) {
         if (z > 8) {
@@ -374,9 +374,9 @@ MPS void do_ship(Env &e, int si)
 {
     MP_COV(do_ship);
     Sprite &sp = e.spr()[si];
-    const int16_t BDx[9] = { 0, 0, 1, 1, 1, 0, -1, -1, -1 }, BDy[9] = { 0, -1, -1, 0, 1, 1, 1, 0, -1 };
-    const int16_t BPx[9] = { 0, 0, 2, 2, 2, 0, -2, -2, -2 }, BPy[9] = { 0, -2, -2, 0, 2, 2, 2, 0, -2 };
-    const int16_t clr[8] = { T_RIVER, T_CHANNEL, T_POWERBASE, T_POWERBASE + 1, T_RAILBASE, T_RAILBASE + 1,
+    MP_TAB int16_t BDx[9] = { 0, 0, 1, 1, 1, 0, -1, -1, -1 }, BDy[9] = { 0, -1, -1, 0, 1, 1, 1, 0, -1 };
+    MP_TAB int16_t BPx[9] = { 0, 0, 2, 2, 2, 0, -2, -2, -2 }, BPy[9] = { 0, -2, -2, 0, 2, 2, 2, 0, -2 };
+    MP_TAB int16_t clr[8] = { T_RIVER, T_CHANNEL, T_POWERBASE, T_POWERBASE + 1, T_RAILBASE, T_RAILBASE + 1,
         T_BRWH, T_BRWV };
     int16_t x, y, z, t = T_RIVER;
     if (sp.soundCount > 0) sp.soundCount--;
@@ -448,9 +448,9 @@ MPN void do_monster(Env &e, int si)
 {
     MP_COV(do_monster);
     Sprite &sp = e.spr()[si];
-    const int16_t Gx[5] = { 2, 2, -2, -2, 0 }, Gy[5] = { -2, 2, 2, -2, 0 };
-    const int16_t ND1[4] = { 0, 1, 2, 3 }, ND2[4] = { 1, 2, 3, 0 };
-    const int16_t nn1[4] = { 2, 5, 8, 11 }, nn2[4] = { 11, 2, 5, 8 };
+    MP_TAB int16_t Gx[5] = { 2, 2, -2, -2, 0 }, Gy[5] = { -2, 2, 2, -2, 0 };
+    MP_TAB int16_t ND1[4] = { 0, 1, 2, 3 }, ND2[4] = { 1, 2, 3, 0 };
+    MP_TAB int16_t nn1[4] = { 2, 5, 8, 11 }, nn2[4] = { 11, 2, 5, 8 };
     int16_t d, z, c;
     if (sp.soundCount > 0) sp.soundCount--;
     if (sp.control < 0) {
@@ -536,7 +536,7 @@ MPS void do_tornado(Env &e, int si)
 {
     MP_COV(do_tornado);
     Sprite &sp = e.spr()[si];
-    const int16_t CDx[9] = { 2, 3, 2, 0, -2, -3, 0, 0, 0 }, CDy[9] = { -2, 0, 2, 3, 2, 0, 0, 0, 0 };
+    MP_TAB int16_t CDx[9] = { 2, 3, 2, 0, -2, -3, 0, 0, 0 }, CDy[9] = { -2, 0, 2, 3, 2, 0, 0, 0, 0 };
     int16_t z = sp.frame;
     if (z == 2) z = sp.flag ? 3 : 1;
     else {
@@ -763,7 +763,7 @@ MPN void set_fire(Env &e)
 MPN void make_flood(Env &e)
 {
     MP_COV(make_flood);
-    const int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
+    MP_TAB int8_t dx[4] = { 0, 1, 0, -1 }, dy[4] = { -1, 0, 1, 0 };
     MP_NOUNROLL for (int z = 0; z < 300; z++) {
         int x = rnd(e, WORLD_W - 1), y = rnd(e, WORLD_H - 1);
         int c = e.map()[tix(x, y)] & LOMASK;
@@ -789,7 +789,7 @@ MPN void make_flood(Env &e)
 MPN int do_disasters(Env &e, bool defer_quake)
 {
     MP_COV(do_disasters);
-    const int16_t chance[3] = { 10 * 48, 5 * 48, 60 };
+    MP_TAB int16_t chance[3] = { 10 * 48, 5 * 48, 60 };
     if (S.floodCount) S.floodCount--;
     if (!S.enableDisasters) return 0;
     int lvl = S.gameLevel;

@@ -17,6 +17,10 @@
 #define MPN __device__ __noinline__
 #define MPH __host__ __device__ inline
 #define MPA __host__ __device__ __forceinline__
+// MP_TAB: small lookup tables of the engine.  Function-scope `static const`: one copy in constant memory, read with an
+// indexed load -- as a plain local array the compiler rebuilds the table on the stack at every call (a few STL) and
+// reads it back through local memory on the serial lane's dependency chain.
+#define MP_TAB static const
 // The serial lane is latency bound and its code footprint is what hurts (the engine is ~10x the SM
 // instruction caches): keep its loops rolled.
 #define MP_NOUNROLL _Pragma("unroll 1")
@@ -42,6 +46,7 @@
 struct uint4 { unsigned int x, y, z, w; };
 inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { uint4 v = { x, y, z, w }; return v; }
 #define MPQ inline
+#define MP_TAB static const
 #define MPR inline
 #define MPS inline
 #define MPP inline
