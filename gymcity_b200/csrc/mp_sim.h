@@ -34,7 +34,7 @@ MPN void set_valves(Env &e)
     MP_COV(set_valves);
     MP_TAB int16_t taxTable[21] = { 200, 150, 120, 100, 80, 50, 30, 0, -10, -40, -100,
         -150, -200, -250, -300, -350, -400, -450, -500, -550, -600 };
-    const float extMarketParamTable[3] = { 1.2f, 1.1f, 0.98f };
+    MP_TAB float extMarketParamTable[3] = { 1.2f, 1.1f, 0.98f };
     const float birthRate = 0.02f, laborBaseMax = 1.3f, internalMarketDenom = 3.7f;
     const float projectedIndPopMin = 5.0f, resRatioDefault = 1.3f;
     const float resRatioMax = 2, comRatioMax = 2, indRatioMax = 2, taxTableScale = 600;
@@ -1423,7 +1423,7 @@ MPN void do_budget(Env &e)
 MPN void collect_tax(Env &e)
 {
     MP_COV(collect_tax);
-    const float RLevels[3] = { 0.7f, 0.9f, 1.2f }, FLevels[3] = { 1.4f, 1.2f, 0.8f };
+    MP_TAB float RLevels[3] = { 0.7f, 0.9f, 1.2f }, FLevels[3] = { 1.4f, 1.2f, 0.8f };
     S.cashFlow = 0;
     if (!S.taxFlag) {
         S.cityTaxAverage = 0;

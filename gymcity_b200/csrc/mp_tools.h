@@ -88,12 +88,12 @@ MPD bool is_tree(int v) { int t = v & LOMASK; return t >= T_WOODS_LOW && t <= T_
 MPN void fix_single(Fx &fx, int x, int y)
 {
     MP_COV(fix_single);
-    const uint16_t RoadTable[16] = { T_ROADS, T_ROADS2, T_ROADS, T_ROADS3, T_ROADS2, T_ROADS2, T_ROADS4,
+    MP_TAB uint16_t RoadTable[16] = { T_ROADS, T_ROADS2, T_ROADS, T_ROADS3, T_ROADS2, T_ROADS2, T_ROADS4,
         T_ROADS8, T_ROADS, T_ROADS6, T_ROADS, T_ROADS7, T_ROADS5, T_ROADS10, T_ROADS9, T_INTERSECTION };
-    const uint16_t RailTable[16] = { T_LHRAIL, T_LVRAIL, T_LHRAIL, T_LVRAIL2, T_LVRAIL, T_LVRAIL,
+    MP_TAB uint16_t RailTable[16] = { T_LHRAIL, T_LVRAIL, T_LHRAIL, T_LVRAIL2, T_LVRAIL, T_LVRAIL,
         T_LVRAIL3, T_LVRAIL7, T_LHRAIL, T_LVRAIL5, T_LHRAIL, T_LVRAIL6, T_LVRAIL4, T_LVRAIL9, T_LVRAIL8,
         T_LVRAIL10 };
-    const uint16_t WireTable[16] = { T_LHPOWER, T_LVPOWER, T_LHPOWER, T_LVPOWER2, T_LVPOWER, T_LVPOWER,
+    MP_TAB uint16_t WireTable[16] = { T_LHPOWER, T_LVPOWER, T_LHPOWER, T_LVPOWER2, T_LVPOWER, T_LVPOWER,
         T_LVPOWER3, T_LVPOWER7, T_LHPOWER, T_LVPOWER5, T_LHPOWER, T_LVPOWER6, T_LVPOWER4, T_LVPOWER9,
         T_LVPOWER8, T_LVPOWER10 };
     int adj = 0;
@@ -357,7 +357,7 @@ MPD int check_big_zone(int id, int &dh, int &dv)
 {
     MP_COV(check_big_zone);
     dh = 0; dv = 0;
-    const int base4[4] = { T_POWERPLANT, T_PORT, T_NUCLEAR, T_STADIUM };
+    MP_TAB int base4[4] = { T_POWERPLANT, T_PORT, T_NUCLEAR, T_STADIUM };
     MP_NOUNROLL for (int k = 0; k < 4; k++) {
         int d = id - base4[k];
         if (d == 0) return 4;
@@ -455,8 +455,8 @@ MPN int build_building(Fx &fx, int x, int y, int size, int base, int toolCost, b
 MPD void smooth_trees_at_fx(Fx &fx, int x, int y, bool preserve)
 {
     MP_COV(smooth_trees_at_fx);
-    const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
-    const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
+    MP_TAB int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
+    MP_TAB int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     if (!is_tree(fx.value(x, y))) return;
     int bits = 0;
     MP_NOUNROLL for (int z = 0; z < 4; z++) {
@@ -477,7 +477,7 @@ MPD void smooth_trees_at_fx(Fx &fx, int x, int y, bool preserve)
 MPN int tool_down(Env &e, int tool, int x, int y)
 {
     MP_COV(tool_down);
-    const int16_t costOf[TOOL_COUNT] = { 100, 100, 100, 500, 500, 0, 5, 1, 20, 10, 5000, 10, 3000, 3000,
+    MP_TAB int16_t costOf[TOOL_COUNT] = { 100, 100, 100, 500, 500, 0, 5, 1, 20, 10, 5000, 10, 3000, 3000,
         5000, 10000, 100, 0, 0, 0 };
     x = (int16_t)x; y = (int16_t)y;
     Fx fx(e, x, y);
@@ -550,7 +550,7 @@ MPN int tool_down(Env &e, int tool, int x, int y)
             v = fx.value(x, y);
             if (v == T_DIRT) {
                 fx.set(x, y, T_WOODS | BLBNBIT);
-                const int8_t dx[8] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dy[8] = { -1, -1, -1, 0, 0, 1, 1, 1 };
+                MP_TAB int8_t dx[8] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dy[8] = { -1, -1, -1, 0, 0, 1, 1, 1 };
                 MP_NOUNROLL for (int i = 0; i < 8; i++)
                     if (inb(x + dx[i], y + dy[i])) smooth_trees_at_fx(fx, x + dx[i], y + dy[i], true);
                 result = TR_OK;
@@ -587,7 +587,7 @@ MPD void put_on_map(Env &e, int ch, int x, int y)                  // generate.c
 MPN void plop_b_river(Env &e, int px, int py)
 {
     MP_COV(plop_b_river);
-    const int8_t lo[9] = { 3, 2, 1, 0, 0, 0, 1, 2, 3 };    // first non-empty column of each row
+    MP_TAB int8_t lo[9] = { 3, 2, 1, 0, 0, 0, 1, 2, 3 };    // first non-empty column of each row
     MP_NOUNROLL for (int x = 0; x < 9; x++)
         MP_NOUNROLL for (int y = 0; y < 9; y++) {
             int l = lo[y], h = 8 - l, ch = 0;
@@ -601,7 +601,7 @@ MPN void plop_b_river(Env &e, int px, int py)
 MPN void plop_s_river(Env &e, int px, int py)
 {
     MP_COV(plop_s_river);
-    const int8_t lo[6] = { 2, 1, 0, 0, 1, 2 };
+    MP_TAB int8_t lo[6] = { 2, 1, 0, 0, 1, 2 };
     MP_NOUNROLL for (int x = 0; x < 6; x++)
         MP_NOUNROLL for (int y = 0; y < 6; y++) {
             int l = lo[y], h = 5 - l, ch = 0;
@@ -630,8 +630,8 @@ MPN int do_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big)
 MPN void smooth_river(Env &e)                                      // generate.cpp:354-395
 {
     MP_COV(smooth_river);
-    const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
-    const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
+    MP_TAB int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
+    MP_TAB int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
         19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
         5 | BULLBIT, 2 };
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
@@ -655,8 +655,8 @@ MPN void smooth_river(Env &e)                                      // generate.c
 MPN void smooth_trees(Env &e)                                      // generate.cpp:410-422 (+ :425-430)
 {
     MP_COV(smooth_trees);
-    const int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
-    const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
+    MP_TAB int8_t dx[4] = { -1, 0, 1, 0 }, dy[4] = { 0, 1, 0, -1 };
+    MP_TAB int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     MP_NOUNROLL for (int x = 0; x < WORLD_W; x++)
         MP_NOUNROLL for (int y = 0; y < WORLD_H; y++)
             if (is_tree(e.map()[tix(x, y)])) {
@@ -844,7 +844,7 @@ MPN int gen_river(Env &e, int px, int py, int riverDir, int terrainDir, bool big
 MPD int gen_redge_value(Env &e, int idx)
 {
     MP_COV(gen_redge_value);
-    const int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
+    MP_TAB int16_t REdTab[16] = { 13 | BULLBIT, 13 | BULLBIT, 17 | BULLBIT, 15 | BULLBIT, 5 | BULLBIT, 2,
         19 | BULLBIT, 17 | BULLBIT, 9 | BULLBIT, 11 | BULLBIT, 2, 13 | BULLBIT, 7 | BULLBIT, 9 | BULLBIT,
         5 | BULLBIT, 2 };
     const int x = idx / WORLD_H, y = idx - x * WORLD_H;
@@ -897,7 +897,7 @@ MPN void gen_smooth_river(Env &e)
 MPN void gen_smooth_trees(Env &e)
 {
     MP_COV(gen_smooth_trees);
-    const int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
+    MP_TAB int8_t treeTable[16] = { 0, 0, 0, 34, 0, 0, 36, 35, 0, 32, 0, 33, 30, 31, 29, 37 };
     const int lane = e.c.tid;
     MP_NOUNROLL for (int d = 0; d < WORLD_W + WORLD_H - 1; d++) {
         const int x0 = d < WORLD_H ? 0 : d - (WORLD_H - 1), x1 = d < WORLD_W ? d : WORLD_W - 1;
