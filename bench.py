@@ -407,8 +407,10 @@ def run_ours(args):
             "collective": ("all-reduce of 3 doubles per step (sum reward, n done, n envs)" if args.allreduce_stats
                            else "none on the tick path (NCCL: barrier + max of the timings only)"),
             "step_ms": ms_stats(kern_ms),
-            "kernels": "per env group: k_mp_env_pre + k_mp_frames<32> launches of %d frames (32 envs per CTA, frame "
-                       "lockstep) + k_mp_env_post; + memset + 3 scheduling kernels" % int(os.environ.get("MPB_FRAMES_PER_LAUNCH", 50)),
+            "kernels": "one-class batches of >= 18 944 envs (the headline): k_mp_sched_class + k_mp_sched_keys (+ CUB radix "
+                       "sort), k_mp_pre_keys, k_mp_env_pre_t (thread per env, tool order), k_mp_frames<32> x 2 (a simTick of "
+                       "100 frames per launch, 32 envs per CTA in frame lockstep; the schedule is rebuilt between them), "
+                       "k_mp_env_post; other batches: three env groups on streams with 50-frame launches",
             "sim_frames_per_s": world * E * K * 200 / (total_ms / 1000.0),
             "e2e": {"value": world * E * K / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": E * 8,
                     "d2h_bytes_per_step": E * 5,
