@@ -29,6 +29,10 @@ MPD int boat_distance(Env &e, int x, int y);            // mp_sprites.h
 // ------------------------------------------------------------------ phase 0
 // [LEAD] simulate.cpp:546-670 setValves.  fp32 throughout like the reference, including the
 // `resRatio = min(indRatio, ...)` slip at :644.
+// num / den for num >= +0 and den > 0.  A zero numerator (empty histories: the usual case in a young city) sends the
+// IEEE division to its slow-path subroutine (two calls per setValves in the ncu call counts); the quotient is +0.
+MPD float fdiv_pos(float num, float den) { return num == 0.0f ? 0.0f : num / den; }
+
 MPN void set_valves(Env &e)
 {
     MP_COV(set_valves);
@@ -50,14 +54,14 @@ MPN void set_valves(Env &e)
     S.totalPopLast = S.totalPop;
     S.totalPop = f2s(normalizedResPop + S.comPop + S.indPop);
     float employment;
-    if (S.resPop > 0) employment = (float)(e.comHist()[1] + e.indHist()[1]) / normalizedResPop;
+    if (S.resPop > 0) employment = fdiv_pos((float)(e.comHist()[1] + e.indHist()[1]), normalizedResPop);
     else employment = 1;
     float migration = normalizedResPop * (employment - 1);
     float births = normalizedResPop * birthRate;
     float projectedResPop = normalizedResPop + migration + births;
     float temp = (float)(e.comHist()[1] + e.indHist()[1]);
     float laborBase;
-    if (temp > 0.0f) laborBase = (float)e.resHist()[1] / temp;
+    if (temp > 0.0f) laborBase = fdiv_pos((float)e.resHist()[1], temp);
     else laborBase = 1;
     laborBase = tclamp(laborBase, 0.0f, laborBaseMax);
     float internalMarket = (float)(normalizedResPop + S.comPop + S.indPop) / internalMarketDenom;
@@ -67,7 +71,7 @@ MPN void set_valves(Env &e)
     float resRatio, comRatio, indRatio;
     if (normalizedResPop > 0) resRatio = projectedResPop / normalizedResPop;
     else resRatio = resRatioDefault;
-    if (S.comPop > 0) comRatio = projectedComPop / (float)S.comPop;
+    if (S.comPop > 0) comRatio = fdiv_pos(projectedComPop, (float)S.comPop);
     else comRatio = projectedComPop;
     if (S.indPop > 0) indRatio = projectedIndPop / (float)S.indPop;
     else indRatio = projectedIndPop;
