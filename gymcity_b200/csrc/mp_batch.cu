@@ -1035,6 +1035,8 @@ mpb_handle mpb_create(int n_envs, int device)
     // thousand envs in all are better off with a warp each: 2 048 envs on the 120x100 window 331 k against 328 k)
     b->pre_t = getenv("MPB_PRE_T") ? atoi(getenv("MPB_PRE_T")) : PRE_T;
     b->pre_l = getenv("MPB_PRE_L") ? atoi(getenv("MPB_PRE_L")) : PRE_L;
+    b->pre_t = (b->pre_t < 32 ? 32 : (b->pre_t > 256 ? 256 : b->pre_t)) & ~31;       // whole warps, the kernel's launch bound
+    b->pre_l = b->pre_l < 1 ? 1 : (b->pre_l > 32 ? 32 : b->pre_l);
     b->pre_simt = getenv("MPB_PRE_SIMT") ? atoi(getenv("MPB_PRE_SIMT")) : (n_envs >= 4096 ? 2 : 1);
 
     for (int i = 0; i < 6; i++) cudaEventCreate(&b->ev_ph[i]);
