@@ -419,7 +419,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_tick": B,
-                         "note": "the tick is not HBM bound (SURVEY 8d: a few percent expected): ~300 KB of branchy SASS "
+                         "note": "the tick is not HBM bound (SURVEY 8d: a few percent expected): ~430 KB of branchy SASS "
                                  "run by one lane per warp is bound by instruction supply and by the wait for the slowest "
                                  "of the 32 cities of a CTA (profiles/r02_notes.md)"},
             "cpu_baseline": cb, "clocks": sampler.result(), "reward_checksum": checksum, "flags": flags,

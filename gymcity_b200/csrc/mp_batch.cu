@@ -205,7 +205,7 @@ __host__ __device__ __forceinline__ int geom_slot(const GroupGeom &q, int w)
 // `count` simFrames (simLoop(true), main.cpp:403-425) for every env, frames [first, first + count) of
 // a simTick of simPasses frames.  All envs of the batch run the same frames in the same launch, so
 // every warp on the GPU is in (nearly) the same simulation phase and executes the same code: the
-// engine's instruction footprint (~0.3 MB) is far beyond the SM instruction caches, and a launch
+// engine's instruction footprint (~0.4 MB) is far beyond the SM instruction caches, and a launch
 // per few dozen frames keeps the live footprint to a few phases' worth (profiles/r01_notes.md).
 // animate_before != 0 runs tickEngine's animateTiles first (micropolisgtkengine.py:542-552).
 // MP_FEPC = envs (warps) per CTA.  MP_FEPC > 1 adds a CTA barrier per frame: the warps of a CTA run
