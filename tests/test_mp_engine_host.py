@@ -156,3 +156,12 @@ def test_tools_every_tool_every_terrain():
         if k % 500 == 499:
             _same(r, h, "tools %d" % k)
     _same(r, h, "tools final")
+
+
+def test_scan_period_reciprocal_is_exact():
+    """mp_sim.h scan_due replaces `simCycle % period == 0` (simulate.cpp:124-135, periods 1..20, simCycle 0..1023) by a
+    multiply with ceil(2^16 / period) and a shift; the identity is checked here over the whole domain."""
+    for d in range(1, 21):
+        r = (65535 + d) // d
+        for c in range(1024):
+            assert (c - ((c * r) >> 16) * d == 0) == (c % d == 0), (c, d)
